@@ -1,0 +1,248 @@
+/*
+ * sdpb200.h — C-ABI of libsdpb200.so: finite-horizon stochastic dynamic programming
+ * (backward induction) for the inventory models of RobinChen121/Stochastic-Inventory,
+ * solved on NVIDIA B200 (sm_100a) with hand-written CUDA kernels, one launch per period.
+ *
+ *     V_t(s) = opt_{a in A(s)}  sum_j [ p_j * c(s,a,d_j)  (+)  (p_j * gamma) * V_{t+1}( f(s,a,d_j) ) ]
+ *
+ * This header is the drop-in boundary.  The reference has no FFI layer: its "operator API"
+ * is the Java class surface of the recursion engines, which take Java lambdas.  A GPU cannot
+ * call lambdas, so the lambdas of every in-scope reference driver are lowered to ONE
+ * parameterised descriptor (`sdpb_model`); each entry point below names the Java member it
+ * replaces (paths relative to the reference repository root).
+ *
+ *   reference (Java)                                               this library
+ *   -------------------------------------------------------------  ----------------------------
+ *   new Recursion(dir, pmf, A, f, c)   src/sdp/inventory/Recursion.java:49-63      sdpb_create
+ *   new LeadtimeRecursion(pmf,A,f,c)   src/sdp/inventory/LeadtimeRecursion.java:28-45  sdpb_create
+ *   new CashRecursion(dir,pmf,A,f,c,g) src/sdp/cash/CashRecursion.java:39-57       sdpb_create
+ *   new CashLeadtimeRecursion(...)     src/sdp/cash/CashLeadtimeRecursion.java:28-46   sdpb_create
+ *   new RiskRecursion(pmf,A,f,c)       src/sdp/cash/RiskRecursion.java:31-45       sdpb_create
+ *   new CashRecursionXR(...)           src/sdp/cash/CashRecursionXR.java:39-57     sdpb_create
+ *   getExpectedValue(state)            Recursion.java:89-163, CashRecursion.java:79-140,
+ *                                      LeadtimeRecursion.java:47-75, CashLeadtimeRecursion.java:48-79,
+ *                                      CashRecursionXR.java:79-125                 sdpb_solve + sdpb_value
+ *   getSurvProb(state)                 CashRecursion.java:143-194, RiskRecursion.java:64-108
+ *                                                                                  sdpb_solve + sdpb_value
+ *   getAction(state)                   Recursion.java:165-167 (and siblings)       sdpb_value (q out)
+ *   getOptTable()/getCacheActions()    Recursion.java:169-186 (and siblings)       sdpb_reach + sdpb_opt_table
+ *   the lambdas A, f, c                src/capacitated/CLSPTesting.java:78-106, src/leadtime/Leadtime.java:50-81,
+ *                                      src/cash/singleItem/CashConstraint.java:95-133,
+ *                                      src/cash/overdraft/CashOverdraft.java:72-118,
+ *                                      src/cash/overdraft/SingleProductLeadtime.java:72-119,
+ *                                      src/cash/risk/cashSurvival.java:102-147,
+ *                                      src/cash/singleItem/CashConstraintXR.java:71-110   sdpb_model fields
+ *
+ * Conventions: every function returns 0 (SDPB_OK) or a negative sdpb_status; no exceptions
+ * cross the boundary; all result buffers are caller-allocated host memory unless a function
+ * says "device"; a handle is not thread-safe, distinct handles are independent; calls block
+ * until the result is on the host (except sdpb_solve_period_async).  There is NO CPU fallback:
+ * without a CUDA device sdpb_create fails with SDPB_ERR_NO_DEVICE.
+ */
+#ifndef SDPB200_H
+#define SDPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDPB_ABI_VERSION 1
+
+typedef enum sdpb_status {
+    SDPB_OK = 0,
+    SDPB_ERR_ARG = -1,        /* null pointer, bad enum, bad size                     */
+    SDPB_ERR_OFFGRID = -2,    /* grid/pmf/step not exactly representable on the grid  */
+    SDPB_ERR_NO_DEVICE = -3,  /* no CUDA device / wrong architecture                  */
+    SDPB_ERR_CUDA = -4,       /* a CUDA runtime call failed (see sdpb_last_error)     */
+    SDPB_ERR_STATE = -5,      /* call out of order (e.g. value before solve)          */
+    SDPB_ERR_NOMEM = -6,
+    SDPB_ERR_UNSOLVED = -7    /* query of a state outside the grid (Java: NullPointerException,
+                                 Recursion.java:165-167)                               */
+} sdpb_status;
+
+/* Which immediate-value / transition lambdas the descriptor stands for. */
+typedef enum sdpb_cost_kind {
+    /* (a>0?K:0) + v*a + h*max(l,0) + pi*max(-l,0),  l = x + a - d   (lead_time 0)
+     *                                               l = x + q1 - d  (lead_time >= 1)
+     * CLSPTesting.java:89-106, CLSP.java:251-272, Leadtime.java:61-81                 */
+    SDPB_COST_BACKORDER = 0,
+    /* cash increment with deposit interest: CashConstraint.java:103-133,
+     * cashSurvival.java:116-147                                                       */
+    SDPB_COST_CASH_DEPOSIT = 1,
+    /* cash increment with four-branch overdraft interest: CashOverdraft.java:80-118,
+     * SingleProductLeadtime.java:82-119 (lead_time 1)                                 */
+    SDPB_COST_CASH_OVERDRAFT = 2,
+    /* (x, R = w + v*x) re-parameterisation, action = order-up-to level y:
+     * CashConstraintXR.java:71-110 with CashRecursionXR.java:79-125                   */
+    SDPB_COST_CASH_XR = 3
+} sdpb_cost_kind;
+
+typedef enum sdpb_recursion {
+    SDPB_REC_EXPECT = 0,   /* getExpectedValue: s += p*c; s += (p*gamma)*V'            */
+    SDPB_REC_SURVIVAL = 1  /* getSurvProb: terminal 1[w + c >= 0]; continuation 0 if w' < 0,
+                              RiskRecursion.java:73-104, CashRecursion.java:152-185   */
+} sdpb_recursion;
+
+typedef enum sdpb_direction { SDPB_MIN = 0, SDPB_MAX = 1 } sdpb_direction;
+
+/* Cash quantiser applied after the cash clamp.
+ *   kk = Math.round(w * q_mul)                 (Java round-half-up to long)
+ *   SDPB_Q_DIV      w' = (double)kk / q_div            e.g. round(w*10)/10.0
+ *   SDPB_Q_LONGDIV  w' = (double)(kk / (long)q_div)    e.g. round(w*10)/10  (long division) */
+typedef enum sdpb_quantiser { SDPB_Q_DIV = 0, SDPB_Q_LONGDIV = 1 } sdpb_quantiser;
+
+enum sdpb_flags {
+    SDPB_F_CLAMP_INV = 1u << 0,        /* x' = clamp(x', inv_min, inv_max), upper clamp first
+                                          (CLSPTesting.java:91-92); off for Leadtime.java:65-66 */
+    SDPB_F_LOST_SALES = 1u << 1,       /* x' = max(0, .) before the clamp (CashConstraint.java:124) */
+    SDPB_F_GY_MODE = 1u << 2,          /* period 1 is the "no order" G(y) pass, CLSPforDraw.java:147-170 */
+    SDPB_F_NO_ORDER_LAST = 1u << 3,    /* A(s) = {0} when t == T (SingleProductLeadtime.java:74-75) */
+    SDPB_F_CASH_LIMITED_ACTIONS = 1u << 4 /* |A(s)|-1 = (int)min(maxQ, max(0,(w - reserve_t)/v_t))
+                                          (CashConstraint.java:96-99, cashSurvival.java:103-110) */
+};
+
+/*
+ * The model descriptor.  All pointers are caller-owned and are copied by sdpb_create.
+ * Arithmetic is IEEE-754 double, evaluated in the order written in the cited Java lines,
+ * never contracted into FMA (Java has no fused multiply-add).
+ */
+typedef struct sdpb_model {
+    uint32_t struct_size;   /* = sizeof(sdpb_model); ABI guard */
+    int32_t  cost_kind;     /* sdpb_cost_kind */
+    int32_t  recursion;     /* sdpb_recursion */
+    int32_t  direction;     /* sdpb_direction */
+    int32_t  T;             /* horizon = pmf.length */
+    int32_t  lead_time;     /* 0, 1 (LeadtimeState, CashLeadtimeState) or 2 (synthetic C4) */
+    uint32_t flags;         /* sdpb_flags */
+    int32_t  max_order_idx; /* actions are a_i = i*step, i = 0..max_order_idx (order-up-to offset for XR) */
+    double   gamma;         /* discount factor; classes without one use 1.0 (p*1.0 == p exactly) */
+
+    /* demand pmf, GetPmf.getpmf() layout flattened: period t (0-based) owns
+     * entries [off_t, off_t + pmf_len[t]), off_t = sum of earlier lengths. */
+    const int32_t* pmf_len; /* [T] */
+    const double*  pmf_d;   /* demand values  pmf[t][j][0] */
+    const double*  pmf_p;   /* probabilities  pmf[t][j][1] */
+
+    /* inventory axis: x_i = inv_min + i*step, i = 0..(inv_max-inv_min)/step */
+    double inv_min, inv_max, step;
+
+    /* cash axis (cash kinds only): clamp to [cash_min, cash_max], then quantise */
+    double  cash_min, cash_max;
+    int32_t quantiser;      /* sdpb_quantiser */
+    int32_t reserved0;
+    double  q_mul, q_div;
+
+    /* cost parameters (unused ones are ignored) */
+    double fixed_cost;      /* K */
+    double vari_cost;       /* v   (per-period override: vari_cost_t) */
+    double hold_cost;       /* h */
+    double penalty_cost;    /* backorder pi; CASH_DEPOSIT: penalty on negative end cash */
+    double price;           /* per-period override: price_t */
+    double salvage;         /* applied to max(l,0) when t == T */
+    double deposit_rate;    /* CASH_DEPOSIT: (w - K - v a) * (1 + deposit_rate) */
+    double overhead_rate;   /* CASH_DEPOSIT: (1 - overhead_rate) * revenue */
+    double overhead;        /* per-period override: overhead_t */
+    double r0, r2, r3, od_limit, interest_free; /* CASH_OVERDRAFT, CashOverdraft.java:88-95 */
+    const double* price_t;      /* [T] or NULL */
+    const double* vari_cost_t;  /* [T] or NULL */
+    const double* overhead_t;   /* [T] or NULL */
+    const double* reserve_t;    /* [T] or NULL (= 0): cash kept back in the action bound,
+                                   (int)min(maxQ, max(0, ((w - reserve_t) - reserve2) / v_t));
+                                   overhead then K in CashConstraint.java:98, 0 in cashSurvival.java:105 */
+    double reserve2;
+} sdpb_model;
+
+typedef enum sdpb_kernel_choice {
+    SDPB_KERNEL_AUTO = 0,     /* fastest bit-exact kernel available for the model */
+    SDPB_KERNEL_GENERIC = 1,  /* always the generic per-(s,a,d) kernel */
+    SDPB_KERNEL_TILED = 2     /* shared-memory tiled kernel; error if the model has none */
+} sdpb_kernel_choice;
+
+typedef struct sdpb_options {
+    uint32_t struct_size;  /* = sizeof(sdpb_options) */
+    int32_t  device;       /* CUDA ordinal; -1 = current device */
+    int32_t  shard_rank;   /* this handle computes states [lo,hi) of rank r of n contiguous blocks */
+    int32_t  shard_count;  /* 1 = whole grid */
+    int32_t  kernel;       /* sdpb_kernel_choice */
+    int32_t  dedup;        /* 1 = states that provably share (c,f) for every (a,d) are solved once
+                              and broadcast (exact; lead-time kinds). 0 = brute force per state. */
+    void*    stream;       /* cudaStream_t to launch on; NULL = a stream owned by the handle */
+} sdpb_options;
+
+typedef struct sdpb_grid {
+    int32_t ndim;          /* API state vector length: 1 + has_cash + lead_time */
+    int32_t n_inv, n_cash, n_q; /* axis sizes (n_cash = 1 / n_q = 1 when absent) */
+    int64_t n_states;      /* dense states per period */
+    int64_t shard_lo, shard_hi; /* flattened range owned by this handle */
+    int32_t n_actions;     /* max_order_idx + 1 */
+    int32_t T;
+    int64_t cash_k_min;    /* integer cash index of the lowest cash point */
+} sdpb_grid;
+
+typedef struct sdpb_stats {
+    double  evals;          /* sum_t sum_{s in shard} |A_t(s)| * D_t  (feasible actions only) */
+    double  solve_ms;       /* device time of the last sdpb_solve (CUDA events) */
+    double  kernel_ms;      /* of which inside backward-induction kernels */
+    int32_t launches;       /* backward-induction kernel launches in the last solve */
+    int32_t kernel_used;    /* sdpb_kernel_choice actually run */
+    double  fp64_ops;       /* fp64 add/mul/min/max instructions the kernels executed, by construction */
+} sdpb_stats;
+
+typedef struct sdpb_handle sdpb_handle;
+
+int sdpb_abi_version(void);
+/* sizeof(sdpb_model) / sizeof(sdpb_options) as compiled into the library: lets a foreign-function
+ * binding (Panama FFM StructLayout, ctypes.Structure) verify its layout before the first call. */
+size_t sdpb_sizeof_model(void);
+size_t sdpb_sizeof_options(void);
+
+/* Build a solver for `m` on one GPU (opt may be NULL).  Validates that the grid is exact. */
+int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out);
+void sdpb_destroy(sdpb_handle* h);
+const char* sdpb_last_error(const sdpb_handle* h); /* h may be NULL: last create error */
+
+int sdpb_grid_info(const sdpb_handle* h, sdpb_grid* g);
+
+/* Backward induction over periods T..1 for this handle's shard (whole grid when unsharded). */
+int sdpb_solve(sdpb_handle* h);
+/* One period (1-based), asynchronous on the handle's stream.  For a sharded grid the caller
+ * all-gathers the V_t device buffer (sdpb_device_tables) across ranks before period t-1. */
+int sdpb_solve_period_async(sdpb_handle* h, int period);
+int sdpb_sync(sdpb_handle* h);
+
+/* getExpectedValue + getAction for `n` states of one period.  `states` is n*ndim doubles in the
+ * reference constructor order: (inv) | (inv, preQ[, preQ2]) | (inv, cash) | (inv, cash, preQ).
+ * v and q may be NULL.  q is the order quantity (order-up-to level for XR), as a double. */
+int sdpb_value(sdpb_handle* h, int period, const double* states, int n, double* v, double* q);
+
+/* Whole-grid tables of one period in the library's state order (inv outermost, then preQ.., cash
+ * innermost); V and Q are n_states doubles each, either may be NULL. */
+int sdpb_period_tables(sdpb_handle* h, int period, double* V, double* Q);
+/* Device pointers: V_t as double[n_states], action index as int32[n_states]. */
+int sdpb_device_tables(sdpb_handle* h, int period, void** dV, void** dQidx);
+/* Grid coordinates of flattened state `idx` as API-order doubles (ndim of them). */
+int sdpb_state_of_index(const sdpb_handle* h, int64_t idx, double* state);
+
+/* Forward reachability from `n` period-1 states through every feasible action and demand (what
+ * the reference's top-down memoisation visits), then the getOptTable() rows
+ * [t, state dims..., Q*] sorted by (t, state dims).  Call sdpb_opt_table with rows == NULL to get the count. */
+int sdpb_reach(sdpb_handle* h, const double* init_states, int n);
+int sdpb_opt_table(sdpb_handle* h, double* rows, size_t* nrows);
+
+int sdpb_stats_get(const sdpb_handle* h, sdpb_stats* s);
+
+/* Evaluate the descriptor's lambdas on the device for `n` (state, action, demand) triples of one
+ * period, with the same device code the solve uses: c = immediateValue(s,a,d), next = stateTransition
+ * (API-order state of period+1; clipped to the grid when the model does not clamp), n_actions =
+ * |getFeasibleAction(s)|.  Lets a host facade spot-check a descriptor against the user's lambdas
+ * before trusting it (a mismatch would otherwise be silent).  action_idx[i] is the action's index. */
+int sdpb_eval_triples(sdpb_handle* h, int period, const double* states, const int32_t* action_idx,
+                      const double* demand, int n, double* c, double* next_states, int32_t* n_actions);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDPB200_H */

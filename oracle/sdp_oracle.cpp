@@ -1,0 +1,577 @@
+// sdp_oracle.cpp — CPU restatement of the reference's SDP recursion.  TEST INFRASTRUCTURE ONLY.
+//
+// This file is the parity oracle for libsdpb200.so.  It is loaded by tests/, by
+// __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs and by nothing
+// else; the product library never links or calls it.
+//
+// PARITY UNPINNED: the reference (Java 21 + SSJ 3.3.0) cannot run in the build container (no JDK,
+// no jar) and its repository holds no golden vectors, fixtures or known-answer tests for this
+// path.  What pins this restatement instead:
+//   * it is written line-by-line after the Java sources cited at each function;
+//   * two independent evaluation orders of it — `oracle_topdown` (memoised recursion over
+//     real-valued states in ordered maps, exactly the reference's control flow) and
+//     `oracle_dense` (period-by-period over the full grid, states addressed by index) — must
+//     agree bit-for-bit on every state the recursion visits (tests/test_oracle.py);
+//   * closed-form cases (deterministic demand, single action) in tests/test_oracle.py.
+//
+// Arithmetic: IEEE-754 double, operations in the order the Java source writes them, compiled
+// with -ffp-contract=off (Java never fuses a multiply-add).
+//
+// The reference loop (src/sdp/inventory/Recursion.java:129-161, repeated in
+// src/sdp/cash/CashRecursion.java:98-138, src/sdp/inventory/LeadtimeRecursion.java:49-73,
+// src/sdp/cash/CashLeadtimeRecursion.java:50-77, src/sdp/cash/CashRecursionXR.java:82-124,
+// src/capacitated/CLSP.java:111-136):
+//
+//     val = MIN ? Double.MAX_VALUE : -Double.MAX_VALUE;  bestOrderQty = 0;
+//     for i over feasibleActions:  thisQ = 0
+//         for j over pmf[t-1]:     thisQ += p_j * c(s, a_i, d_j)
+//                                  if (t < T) thisQ += p_j * gamma * V(f(s, a_i, d_j))
+//         strict compare -> (val, bestOrderQty)
+//
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <atomic>
+#include <thread>
+
+#include "../include/sdpb200.h"
+
+namespace {
+
+// ---- Java semantics -------------------------------------------------------------------------
+// Math.round(double): round half up to long (exact; Java >= 7 does not compute x + 0.5).
+inline int64_t jround(double x) {
+    double r = std::floor(x);
+    double diff = x - r;  // exact for |x| < 2^52
+    return (int64_t)r + (diff >= 0.5 ? 1 : 0);
+}
+// Math.max / Math.min on doubles (no NaNs on this path); +0.0 > -0.0 as in Java.
+inline double jmax(double a, double b) {
+    if (a == 0.0 && b == 0.0) return (std::signbit(a) && std::signbit(b)) ? -0.0 : 0.0;
+    return a >= b ? a : b;
+}
+inline double jmin(double a, double b) {
+    if (a == 0.0 && b == 0.0) return (std::signbit(a) || std::signbit(b)) ? -0.0 : 0.0;
+    return a <= b ? a : b;
+}
+
+struct St {  // State / LeadtimeState / CashState / CashLeadtimeState / RiskState / CashStateXR
+    int t;   // 1-based period
+    double x = 0, w = 0, q1 = 0, q2 = 0;  // w holds R for the XR kind
+};
+
+struct Model {
+    sdpb_model m;
+    std::vector<int> off;  // pmf offsets
+    int ndemand(int t) const { return m.pmf_len[t - 1]; }
+    double d(int t, int j) const { return m.pmf_d[off[t - 1] + j]; }
+    double p(int t, int j) const { return m.pmf_p[off[t - 1] + j]; }
+    bool cash() const { return m.cost_kind != SDPB_COST_BACKORDER; }
+    bool flag(uint32_t f) const { return (m.flags & f) != 0; }
+    double price(int t) const { return m.price_t ? m.price_t[t - 1] : m.price; }
+    double vcost(int t) const { return m.vari_cost_t ? m.vari_cost_t[t - 1] : m.vari_cost; }
+    double ovh(int t) const { return m.overhead_t ? m.overhead_t[t - 1] : m.overhead; }
+    double reserve(int t) const { return m.reserve_t ? m.reserve_t[t - 1] : 0.0; }
+    int n_inv() const { return (int)jround((m.inv_max - m.inv_min) / m.step) + 1; }
+    int n_q() const { return m.lead_time > 0 ? m.max_order_idx + 1 : 1; }
+    // integer cash index of a cash value that is already on the quantised grid
+    int64_t cash_k(double w) const {
+        if (m.cost_kind == SDPB_COST_CASH_XR) return jround(w);
+        return m.quantiser == SDPB_Q_DIV ? jround(w * m.q_div) : (int64_t)w;
+    }
+    double cash_of_k(int64_t k) const {
+        if (m.cost_kind == SDPB_COST_CASH_XR) return (double)k;
+        return m.quantiser == SDPB_Q_DIV ? (double)k / m.q_div : (double)k;
+    }
+    double quantise(double w) const {
+        int64_t kk = jround(w * m.q_mul);
+        if (m.quantiser == SDPB_Q_DIV) return (double)kk / m.q_div;
+        return (double)(kk / (int64_t)m.q_div);  // Java long division truncates toward zero
+    }
+    int64_t k_min() const {
+        if (m.cost_kind == SDPB_COST_CASH_XR)
+            return jround(quantise(m.cash_min) + m.vari_cost * m.inv_min);
+        return cash_k(quantise(m.cash_min));
+    }
+    int64_t k_max() const {
+        if (m.cost_kind == SDPB_COST_CASH_XR)
+            return jround(quantise(m.cash_max) + m.vari_cost * m.inv_max);
+        return cash_k(quantise(m.cash_max));
+    }
+    int n_cash() const { return cash() ? (int)(k_max() - k_min() + 1) : 1; }
+    int64_t n_states() const {
+        int64_t n = n_inv();
+        for (int l = 0; l < m.lead_time; l++) n *= n_q();
+        return n * n_cash();
+    }
+};
+
+// ---- feasible actions -----------------------------------------------------------------------
+// CLSPTesting.java:78-86 (0..maxQ), CashConstraint.java:95-100 and cashSurvival.java:102-110
+// (cash-limited), SingleProductLeadtime.java:72-77 ({0} in the last period),
+// CashConstraintXR.java:71-75 (order-up-to levels from x).
+int n_actions(const Model& M, const St& s) {
+    const sdpb_model& m = M.m;
+    if (m.cost_kind == SDPB_COST_CASH_XR) {
+        double v = M.vcost(s.t);
+        double maxY = s.w / v < s.x ? s.x : s.w / v;
+        int length = (int)(maxY - s.x) + 1;
+        return std::min(length, m.max_order_idx + 1);  // dense-grid cap, see DESIGN.md
+    }
+    double maxQ = (double)m.max_order_idx;
+    if (M.flag(SDPB_F_CASH_LIMITED_ACTIONS))
+        maxQ = (int)std::min((double)m.max_order_idx,
+                             std::max(0.0, (s.w - M.reserve(s.t) - m.reserve2) / M.vcost(s.t)));
+    if (M.flag(SDPB_F_NO_ORDER_LAST) && s.t == m.T) maxQ = 0;
+    return (int)maxQ + 1;
+}
+inline double action_value(const Model& M, const St& s, int i) {
+    if (M.m.cost_kind == SDPB_COST_CASH_XR) return s.x + i * M.m.step;
+    return i * M.m.step;
+}
+
+// ---- immediate value ------------------------------------------------------------------------
+double immediate(const Model& M, const St& s, double action, double demand) {
+    const sdpb_model& m = M.m;
+    const int T = m.T;
+    switch (m.cost_kind) {
+    case SDPB_COST_BACKORDER: {
+        // CLSPTesting.java:96-106; lead time: Leadtime.java:71-81; G(y) pass: CLSPforDraw.java:156-170
+        double fixedCost, variableCost, inventoryLevel;
+        if (M.flag(SDPB_F_GY_MODE) && s.t == 1) {
+            fixedCost = 0;
+            variableCost = M.vcost(s.t) * s.x;
+            inventoryLevel = s.x - demand;
+        } else {
+            fixedCost = action > 0 ? m.fixed_cost : 0;
+            variableCost = M.vcost(s.t) * action;
+            inventoryLevel = (m.lead_time > 0 ? s.x + s.q1 : s.x + action) - demand;
+        }
+        double holdingCosts = m.hold_cost * jmax(inventoryLevel, 0);
+        double penaltyCosts = m.penalty_cost * jmax(-inventoryLevel, 0);
+        return fixedCost + variableCost + holdingCosts + penaltyCosts;
+    }
+    case SDPB_COST_CASH_DEPOSIT: {
+        // CashConstraint.java:103-121, cashSurvival.java:116-129
+        double stock = m.lead_time > 0 ? s.x + s.q1 : s.x + action;
+        double revenue = M.price(s.t) * jmin(stock, demand);
+        double fixedCost = action > 0 ? m.fixed_cost : 0;
+        double variableCost = M.vcost(s.t) * action;
+        double deposite = (s.w - fixedCost - variableCost) * (1 + m.deposit_rate);
+        double inventoryLevel = stock - demand;
+        double holdCosts = m.hold_cost * jmax(inventoryLevel, 0);
+        double cashIncrement =
+            (1 - m.overhead_rate) * revenue + deposite - holdCosts - M.ovh(s.t) - s.w;
+        double salValue = s.t == T ? m.salvage * jmax(inventoryLevel, 0) : 0;
+        cashIncrement += salValue;
+        double endCash = s.w + cashIncrement;
+        if (endCash < 0) cashIncrement += m.penalty_cost * endCash;
+        return cashIncrement;
+    }
+    case SDPB_COST_CASH_OVERDRAFT: {
+        // CashOverdraft.java:80-104, SingleProductLeadtime.java:82-103
+        double stock = m.lead_time > 0 ? s.x + s.q1 : s.x + action;
+        double revenue = M.price(s.t) * jmin(stock, demand);
+        double fixedCost = action > 0 ? m.fixed_cost : 0;
+        double variableCost = M.vcost(s.t) * action;
+        double inventoryLevel = stock - demand;
+        double cashBalanceBefore = s.w - fixedCost - variableCost - M.ovh(s.t);
+        double interest = 0;
+        if (cashBalanceBefore >= 0)
+            interest = -m.r0 * cashBalanceBefore;
+        else if (cashBalanceBefore >= -m.interest_free)
+            interest = 0;
+        else if (cashBalanceBefore >= -m.od_limit)
+            interest = m.r2 * (-cashBalanceBefore - m.interest_free);
+        else
+            interest = m.r3 * (-cashBalanceBefore - m.od_limit) + m.r2 * (m.od_limit - m.interest_free);
+        double cashBalanceAfter = cashBalanceBefore - interest + revenue;
+        double cashIncrement = cashBalanceAfter - s.w;
+        double salValue = s.t == T ? m.salvage * jmax(inventoryLevel, 0) : 0;
+        cashIncrement += salValue;
+        return cashIncrement;
+    }
+    case SDPB_COST_CASH_XR: {
+        // CashConstraintXR.java:78-92 (action is the order-up-to level y; s.w holds R)
+        double v = M.vcost(s.t);
+        double actionY = action;
+        double revenue = M.price(s.t) * jmin(actionY, demand);
+        double act = actionY - s.x;
+        double fixedCost = actionY > s.x ? m.fixed_cost : 0;
+        double variableCost = v * act;
+        double initCash = s.w - v * s.x;
+        double deposite = (initCash - fixedCost - variableCost) * (1 + m.deposit_rate);
+        double inventoryLevel = actionY - demand;
+        double holdCosts = m.hold_cost * jmax(inventoryLevel, 0);
+        double cashIncrement =
+            (1 - m.overhead_rate) * revenue + deposite - holdCosts - M.ovh(s.t) - initCash;
+        double salValue = s.t == T ? m.salvage * jmax(inventoryLevel, 0) : 0;
+        cashIncrement += salValue;
+        return cashIncrement;
+    }
+    }
+    return 0;
+}
+
+// ---- state transition -----------------------------------------------------------------------
+St transition(const Model& M, const St& s, double action, double demand) {
+    const sdpb_model& m = M.m;
+    St n;
+    n.t = s.t + 1;
+    if (m.cost_kind == SDPB_COST_BACKORDER) {
+        // CLSPTesting.java:89-94, Leadtime.java:61-68, CLSPforDraw.java:147-153
+        double nextInventory;
+        if (M.flag(SDPB_F_GY_MODE) && s.t == 1)
+            nextInventory = s.x - demand;
+        else
+            nextInventory = (m.lead_time > 0 ? s.x + s.q1 : s.x + action) - demand;
+        if (M.flag(SDPB_F_LOST_SALES)) nextInventory = jmax(0, nextInventory);
+        if (M.flag(SDPB_F_CLAMP_INV)) {
+            nextInventory = nextInventory > m.inv_max ? m.inv_max : nextInventory;
+            nextInventory = nextInventory < m.inv_min ? m.inv_min : nextInventory;
+        }
+        n.x = nextInventory;
+    } else if (m.cost_kind == SDPB_COST_CASH_XR) {
+        // CashConstraintXR.java:95-110
+        double v = M.vcost(s.t);
+        double nextInventory = jmax(0, action - demand);
+        double initCash = s.w - v * s.x;
+        double nextCash = initCash + immediate(M, s, action, demand);
+        nextCash = nextCash > m.cash_max ? m.cash_max : nextCash;
+        nextCash = nextCash < m.cash_min ? m.cash_min : nextCash;
+        nextInventory = nextInventory > m.inv_max ? m.inv_max : nextInventory;
+        nextInventory = nextInventory < m.inv_min ? m.inv_min : nextInventory;
+        nextCash = M.quantise(nextCash);
+        n.x = nextInventory;
+        n.w = nextCash + v * nextInventory;  // nextR
+        return n;
+    } else {
+        // CashConstraint.java:123-133, CashOverdraft.java:107-118, SingleProductLeadtime.java:106-119,
+        // cashSurvival.java:132-147
+        double stock = m.lead_time > 0 ? s.x + s.q1 : s.x + action;
+        double nextInventory = stock - demand;
+        if (M.flag(SDPB_F_LOST_SALES)) nextInventory = jmax(0, nextInventory);
+        double nextCash = s.w + immediate(M, s, action, demand);
+        nextCash = nextCash > m.cash_max ? m.cash_max : nextCash;
+        nextCash = nextCash < m.cash_min ? m.cash_min : nextCash;
+        if (M.flag(SDPB_F_CLAMP_INV)) {
+            nextInventory = nextInventory > m.inv_max ? m.inv_max : nextInventory;
+            nextInventory = nextInventory < m.inv_min ? m.inv_min : nextInventory;
+        }
+        nextCash = M.quantise(nextCash);
+        n.x = nextInventory;
+        n.w = nextCash;
+    }
+    if (m.lead_time == 1) {
+        n.q1 = action;
+    } else if (m.lead_time == 2) {
+        n.q1 = s.q2;
+        n.q2 = action;
+    }
+    return n;
+}
+
+// ---- one state: the loop of Recursion.java:129-161 / RiskRecursion.java:66-104 ----------------
+template <class NextValue>
+void solve_state(const Model& M, const St& s, NextValue&& next_value, double* val_out,
+                 double* best_out, double* evals) {
+    const sdpb_model& m = M.m;
+    const int T = m.T;
+    const bool survival = m.recursion == SDPB_REC_SURVIVAL;
+    const bool is_min = !survival && m.direction == SDPB_MIN;
+    int nA = n_actions(M, s);
+    int D = M.ndemand(s.t);
+    double val = is_min ? DBL_MAX : -DBL_MAX;
+    double bestOrderQty = 0;
+    for (int i = 0; i < nA; i++) {
+        double orderQty = action_value(M, s, i);
+        double thisQValue = 0;
+        for (int j = 0; j < D; j++) {
+            double randomDemand = M.d(s.t, j);
+            double dProb = M.p(s.t, j);
+            if (!survival) {
+                thisQValue += dProb * immediate(M, s, orderQty, randomDemand);
+                if (s.t < T) {
+                    St ns = transition(M, s, orderQty, randomDemand);
+                    thisQValue += dProb * m.gamma * next_value(ns);
+                }
+            } else {
+                if (s.t == T) {
+                    double thisDFinalCash = s.w + immediate(M, s, orderQty, randomDemand);
+                    double thisDProb = thisDFinalCash >= 0 ? 1 : 0;
+                    thisQValue += dProb * thisDProb;
+                }
+                if (s.t < T) {
+                    St ns = transition(M, s, orderQty, randomDemand);
+                    double thisDProb = 0;
+                    if (ns.w < 0)
+                        thisDProb = 0;
+                    else
+                        thisDProb = next_value(ns);
+                    thisQValue += dProb * m.gamma * thisDProb;
+                }
+            }
+        }
+        if (is_min) {
+            if (thisQValue < val) { val = thisQValue; bestOrderQty = orderQty; }
+        } else {
+            if (thisQValue > val) { val = thisQValue; bestOrderQty = orderQty; }
+        }
+    }
+    if (evals) *evals += (double)nA * D;
+    *val_out = val;
+    *best_out = bestOrderQty;
+}
+
+// ---- key order of the memo maps ---------------------------------------------------------------
+// Recursion.java:58-60 (period, inv); LeadtimeRecursion.java:37-40 (period, inv, preQ);
+// CashRecursion.java:51-54 (period, inv, cash).  CashLeadtimeRecursion.java:37-41 is an
+// inconsistent comparator in the reference; (period, inv, preQ, cash) is used here, which
+// changes memo hits only, not values.
+struct KeyLess {
+    bool operator()(const St& a, const St& b) const {
+        if (a.t != b.t) return a.t < b.t;
+        if (a.x != b.x) return a.x < b.x;
+        if (a.q1 != b.q1) return a.q1 < b.q1;
+        if (a.q2 != b.q2) return a.q2 < b.q2;
+        return a.w < b.w;
+    }
+};
+
+struct TopDown {
+    const Model& M;
+    std::map<St, double, KeyLess> cacheValues, cacheActions;
+    double evals = 0;
+    explicit TopDown(const Model& m) : M(m) {}
+    double getExpectedValue(const St& s) {
+        auto it = cacheValues.find(s);
+        if (it != cacheValues.end()) return it->second;
+        double val, best;
+        solve_state(M, s, [this](const St& ns) { return getExpectedValue(ns); }, &val, &best, &evals);
+        cacheValues.emplace(s, val);
+        cacheActions.emplace(s, best);
+        return val;
+    }
+};
+
+// ---- dense grid -------------------------------------------------------------------------------
+struct Grid {
+    const Model& M;
+    int nI, nQ, nW, L;
+    int64_t kmin, S;
+    explicit Grid(const Model& m) : M(m) {
+        nI = M.n_inv(); nQ = M.n_q(); nW = M.n_cash(); L = M.m.lead_time;
+        kmin = M.cash() ? M.k_min() : 0;
+        S = M.n_states();
+    }
+    // library state order: inventory outermost, then the order pipeline, cash innermost
+    int64_t index(const St& s, bool* off) const {
+        int64_t ix = jround((s.x - M.m.inv_min) / M.m.step);
+        if (ix < 0) { ix = 0; *off = true; }
+        if (ix >= nI) { ix = nI - 1; *off = true; }
+        int64_t idx = ix;
+        if (L >= 1) { int64_t iq = jround(s.q1 / M.m.step); idx = idx * nQ + iq; }
+        if (L >= 2) { int64_t iq = jround(s.q2 / M.m.step); idx = idx * nQ + iq; }
+        if (M.cash()) {
+            int64_t k = M.cash_k(s.w) - kmin;
+            if (k < 0) { k = 0; *off = true; }
+            if (k >= nW) { k = nW - 1; *off = true; }
+            idx = idx * nW + k;
+        }
+        return idx;
+    }
+    St state(int t, int64_t idx) const {
+        St s; s.t = t;
+        if (M.cash()) { s.w = M.cash_of_k(kmin + idx % nW); idx /= nW; }
+        if (L >= 2) { s.q2 = (double)(idx % nQ) * M.m.step; idx /= nQ; }
+        if (L >= 1) { s.q1 = (double)(idx % nQ) * M.m.step; idx /= nQ; }
+        s.x = M.m.inv_min + (double)idx * M.m.step;
+        return s;
+    }
+    int ndim() const { return 1 + (M.cash() ? 1 : 0) + L; }
+    // API order: (inv) | (inv, preQ[, preQ2]) | (inv, cash) | (inv, cash, preQ)
+    void to_api(const St& s, double* out) const {
+        int k = 0; out[k++] = s.x;
+        if (M.cash()) out[k++] = s.w;
+        if (L >= 1) out[k++] = s.q1;
+        if (L >= 2) out[k++] = s.q2;
+    }
+    St from_api(int t, const double* in) const {
+        St s; s.t = t; int k = 0; s.x = in[k++];
+        if (M.cash()) s.w = in[k++];
+        if (L >= 1) s.q1 = in[k++];
+        if (L >= 2) s.q2 = in[k++];
+        return s;
+    }
+};
+
+Model make_model(const sdpb_model* m) {
+    Model M; M.m = *m;
+    M.off.resize(m->T + 1, 0);
+    for (int t = 0; t < m->T; t++) M.off[t + 1] = M.off[t] + m->pmf_len[t];
+    return M;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Grid sizes the dense oracle uses for `m` (states per period, API state length).
+int oracle_grid(const sdpb_model* m, int64_t* n_states, int* ndim) {
+    Model M = make_model(m);
+    Grid G(M);
+    *n_states = G.S;
+    *ndim = G.ndim();
+    return 0;
+}
+
+// Period-by-period solve of the whole grid.  V and Q are [T][n_states] (period 1 first); Q is the
+// order quantity as a double.  `offgrid` (may be NULL) counts (s,a,d) triples whose successor fell
+// outside the grid and was clipped (only possible without SDPB_F_CLAMP_INV).  `threads` <= 0 means
+// all cores.  Returns total evaluations in *evals.
+int oracle_dense(const sdpb_model* m, double* V, double* Q, double* evals, int64_t* offgrid,
+                 int threads) {
+    Model M = make_model(m);
+    Grid G(M);
+    const int T = m->T;
+    const int64_t S = G.S;
+    double total = 0;
+    int64_t off_total = 0;
+    int nthreads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    for (int t = T; t >= 1; t--) {
+        const double* Vn = t < T ? V + (size_t)t * S : nullptr;
+        double* Vt = V + (size_t)(t - 1) * S;
+        double* Qt = Q + (size_t)(t - 1) * S;
+        std::atomic<int64_t> next{0};
+        const int64_t chunk = 64;
+        std::vector<double> ev_part(nthreads, 0.0);
+        std::vector<int64_t> off_part(nthreads, 0);
+        auto worker = [&](int tid) {
+            double ev = 0;
+            int64_t offc = 0;
+            for (;;) {
+                int64_t lo = next.fetch_add(chunk);
+                if (lo >= S) break;
+                int64_t hi = std::min(S, lo + chunk);
+                for (int64_t idx = lo; idx < hi; idx++) {
+                    St s = G.state(t, idx);
+                    double val, best;
+                    solve_state(M, s,
+                                [&](const St& ns) {
+                                    bool o = false;
+                                    int64_t ni = G.index(ns, &o);
+                                    if (o) offc++;
+                                    return Vn[ni];
+                                },
+                                &val, &best, &ev);
+                    Vt[idx] = val;
+                    Qt[idx] = best;
+                }
+            }
+            ev_part[tid] = ev;
+            off_part[tid] = offc;
+        };
+        if (nthreads == 1) {
+            worker(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (int i = 0; i < nthreads; i++) pool.emplace_back(worker, i);
+            for (auto& th : pool) th.join();
+        }
+        for (int i = 0; i < nthreads; i++) { total += ev_part[i]; off_total += off_part[i]; }
+    }
+    if (evals) *evals = total;
+    if (offgrid) *offgrid = off_total;
+    return 0;
+}
+
+// Literal top-down memoised recursion from `n_init` period-1 states (API order, ndim doubles
+// each).  Returns the number of visited states; when `rows` is non-NULL it receives, sorted by
+// the memo-map order, rows of (ndim + 3) doubles: [t, state dims (API order)..., Q*, V].
+int64_t oracle_topdown(const sdpb_model* m, const double* init_states, int n_init, double* rows,
+                       int64_t max_rows, double* init_values, double* evals) {
+    Model M = make_model(m);
+    Grid G(M);
+    TopDown td(M);
+    for (int i = 0; i < n_init; i++) {
+        St s = G.from_api(1, init_states + (size_t)i * G.ndim());
+        double v = td.getExpectedValue(s);
+        if (init_values) init_values[i] = v;
+    }
+    if (evals) *evals = td.evals;
+    int64_t n = (int64_t)td.cacheActions.size();
+    if (rows) {
+        int w = G.ndim() + 3;
+        int64_t r = 0;
+        for (auto& kv : td.cacheActions) {
+            if (r >= max_rows) break;
+            double* row = rows + (size_t)r * w;
+            row[0] = kv.first.t;
+            G.to_api(kv.first, row + 1);
+            row[1 + G.ndim()] = kv.second;
+            row[2 + G.ndim()] = td.cacheValues[kv.first];
+            r++;
+        }
+    }
+    return n;
+}
+
+// One backward-induction step for selected states: given the full period-(t+1) value table
+// `Vnext` (NULL when t == T), recompute V_t and Q_t at the `n` flattened indices `idx`.
+// Lets a test check a full-size GPU solve period by period on a sample of states.
+int oracle_step_states(const sdpb_model* m, int period, const double* Vnext, const int64_t* idx, int n,
+                       double* v_out, double* q_out) {
+    Model M = make_model(m);
+    Grid G(M);
+    for (int i = 0; i < n; i++) {
+        St s = G.state(period, idx[i]);
+        double val, best;
+        solve_state(M, s,
+                    [&](const St& ns) {
+                        bool o = false;
+                        return Vnext[G.index(ns, &o)];
+                    },
+                    &val, &best, nullptr);
+        v_out[i] = val;
+        q_out[i] = best;
+    }
+    return 0;
+}
+
+// Single (s, a, d) evaluation for descriptor spot checks: c, and the successor in API order.
+int oracle_eval(const sdpb_model* m, int period, const double* state, double action, double demand,
+                double* c, double* next_state) {
+    Model M = make_model(m);
+    Grid G(M);
+    St s = G.from_api(period, state);
+    *c = immediate(M, s, action, demand);
+    St n = transition(M, s, action, demand);
+    G.to_api(n, next_state);
+    return 0;
+}
+
+// Flattened grid index of an API-order state (for tests), -1 when outside the grid.
+int64_t oracle_index(const sdpb_model* m, const double* state) {
+    Model M = make_model(m);
+    Grid G(M);
+    St s = G.from_api(1, state);
+    bool off = false;
+    int64_t i = G.index(s, &off);
+    return off ? -1 : i;
+}
+
+int oracle_n_actions(const sdpb_model* m, int period, const double* state) {
+    Model M = make_model(m);
+    Grid G(M);
+    St s = G.from_api(period, state);
+    return n_actions(M, s);
+}
+
+}  // extern "C"

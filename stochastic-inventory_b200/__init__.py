@@ -1,0 +1,18 @@
+"""sdp-b200: finite-horizon SDP backward induction on B200 behind the reference's recursion API.
+
+Everything that computes lives in libsdpb200.so (hand-written sm_100a CUDA, csrc/); this package
+is the host-side mirror of the reference's Java classes plus the descriptor builders.
+"""
+from . import _abi as abi
+from ._abi import (COST_BACKORDER, COST_CASH_DEPOSIT, COST_CASH_OVERDRAFT, COST_CASH_XR, KERNEL_AUTO,
+                   KERNEL_GENERIC, KERNEL_TILED, MAX, MIN, Q_DIV, Q_LONGDIV, REC_EXPECT, REC_SURVIVAL,
+                   SdpbError)
+from .getpmf import (DiscreteDistribution, GammaDist, GetPmf, NormalDist, PoissonDist, UniformIntDist,
+                     clsp_inline_pmf, poisson_pmf)
+from .models import (ModelSpec, cash_constraint_model, cash_leadtime_model, cash_overdraft_model,
+                     cash_survival_model, cash_xr_model, inventory_model, leadtime_model)
+from .recursion import (CashLeadtimeRecursion, CashLeadtimeState, CashRecursion, CashRecursionXR,
+                        CashState, CashStateXR, LeadtimeRecursion, LeadtimeRecursion2, LeadtimeState,
+                        OptDirection, Recursion, RiskRecursion, RiskState, State)
+from .solver import Solver
+from . import configs

@@ -1,0 +1,126 @@
+"""ctypes binding of include/sdpb200.h (libsdpb200.so).
+
+This is the same binding a Java maintainer would write with Panama FFM (INTEGRATION.md shows that
+one); Python is used here because the build image has no JDK.  There is no fallback: if the
+shared library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdpb200.so")
+
+# --- enums (include/sdpb200.h) -------------------------------------------------------------
+SDPB_OK = 0
+SDPB_ERR_ARG, SDPB_ERR_OFFGRID, SDPB_ERR_NO_DEVICE, SDPB_ERR_CUDA = -1, -2, -3, -4
+SDPB_ERR_STATE, SDPB_ERR_NOMEM, SDPB_ERR_UNSOLVED = -5, -6, -7
+STATUS_NAMES = {0: "SDPB_OK", -1: "SDPB_ERR_ARG", -2: "SDPB_ERR_OFFGRID", -3: "SDPB_ERR_NO_DEVICE",
+                -4: "SDPB_ERR_CUDA", -5: "SDPB_ERR_STATE", -6: "SDPB_ERR_NOMEM", -7: "SDPB_ERR_UNSOLVED"}
+
+COST_BACKORDER, COST_CASH_DEPOSIT, COST_CASH_OVERDRAFT, COST_CASH_XR = 0, 1, 2, 3
+REC_EXPECT, REC_SURVIVAL = 0, 1
+MIN, MAX = 0, 1
+Q_DIV, Q_LONGDIV = 0, 1
+F_CLAMP_INV, F_LOST_SALES, F_GY_MODE, F_NO_ORDER_LAST, F_CASH_LIMITED_ACTIONS = 1, 2, 4, 8, 16
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED = 0, 1, 2
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class SdpbModel(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("cost_kind", C.c_int32), ("recursion", C.c_int32),
+        ("direction", C.c_int32), ("T", C.c_int32), ("lead_time", C.c_int32), ("flags", C.c_uint32),
+        ("max_order_idx", C.c_int32), ("gamma", C.c_double),
+        ("pmf_len", _ip), ("pmf_d", _dp), ("pmf_p", _dp),
+        ("inv_min", C.c_double), ("inv_max", C.c_double), ("step", C.c_double),
+        ("cash_min", C.c_double), ("cash_max", C.c_double),
+        ("quantiser", C.c_int32), ("reserved0", C.c_int32),
+        ("q_mul", C.c_double), ("q_div", C.c_double),
+        ("fixed_cost", C.c_double), ("vari_cost", C.c_double), ("hold_cost", C.c_double),
+        ("penalty_cost", C.c_double), ("price", C.c_double), ("salvage", C.c_double),
+        ("deposit_rate", C.c_double), ("overhead_rate", C.c_double), ("overhead", C.c_double),
+        ("r0", C.c_double), ("r2", C.c_double), ("r3", C.c_double), ("od_limit", C.c_double),
+        ("interest_free", C.c_double),
+        ("price_t", _dp), ("vari_cost_t", _dp), ("overhead_t", _dp), ("reserve_t", _dp),
+        ("reserve2", C.c_double),
+    ]
+
+
+class SdpbOptions(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("shard_rank", C.c_int32),
+        ("shard_count", C.c_int32), ("kernel", C.c_int32), ("dedup", C.c_int32), ("stream", C.c_void_p),
+    ]
+
+
+class SdpbGrid(C.Structure):
+    _fields_ = [
+        ("ndim", C.c_int32), ("n_inv", C.c_int32), ("n_cash", C.c_int32), ("n_q", C.c_int32),
+        ("n_states", C.c_int64), ("shard_lo", C.c_int64), ("shard_hi", C.c_int64),
+        ("n_actions", C.c_int32), ("T", C.c_int32), ("cash_k_min", C.c_int64),
+    ]
+
+
+class SdpbStats(C.Structure):
+    _fields_ = [
+        ("evals", C.c_double), ("solve_ms", C.c_double), ("kernel_ms", C.c_double),
+        ("launches", C.c_int32), ("kernel_used", C.c_int32), ("fp64_ops", C.c_double),
+    ]
+
+
+# every symbol include/sdpb200.h declares
+EXPORTS = [
+    "sdpb_abi_version", "sdpb_sizeof_model", "sdpb_sizeof_options", "sdpb_create", "sdpb_destroy",
+    "sdpb_last_error", "sdpb_grid_info", "sdpb_solve", "sdpb_solve_period_async", "sdpb_sync",
+    "sdpb_value", "sdpb_period_tables", "sdpb_device_tables", "sdpb_state_of_index", "sdpb_reach",
+    "sdpb_opt_table", "sdpb_stats_get", "sdpb_eval_triples",
+]
+
+_lib = None
+
+
+class SdpbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{STATUS_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def load():
+    """Load libsdpb200.so (built in-tree by `make -C stochastic-inventory_b200/csrc`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.sdpb_abi_version.restype = C.c_int
+    lib.sdpb_sizeof_model.restype = C.c_size_t
+    lib.sdpb_sizeof_options.restype = C.c_size_t
+    lib.sdpb_create.argtypes = [C.POINTER(SdpbModel), C.POINTER(SdpbOptions), C.POINTER(vp)]
+    lib.sdpb_destroy.argtypes = [vp]
+    lib.sdpb_destroy.restype = None
+    lib.sdpb_last_error.argtypes = [vp]
+    lib.sdpb_last_error.restype = C.c_char_p
+    lib.sdpb_grid_info.argtypes = [vp, C.POINTER(SdpbGrid)]
+    lib.sdpb_solve.argtypes = [vp]
+    lib.sdpb_solve_period_async.argtypes = [vp, C.c_int]
+    lib.sdpb_sync.argtypes = [vp]
+    lib.sdpb_value.argtypes = [vp, C.c_int, _dp, C.c_int, _dp, _dp]
+    lib.sdpb_period_tables.argtypes = [vp, C.c_int, _dp, _dp]
+    lib.sdpb_device_tables.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
+    lib.sdpb_state_of_index.argtypes = [vp, C.c_int64, _dp]
+    lib.sdpb_reach.argtypes = [vp, _dp, C.c_int]
+    lib.sdpb_opt_table.argtypes = [vp, _dp, C.POINTER(C.c_size_t)]
+    lib.sdpb_stats_get.argtypes = [vp, C.POINTER(SdpbStats)]
+    lib.sdpb_eval_triples.argtypes = [vp, C.c_int, _dp, _ip, _dp, C.c_int, _dp, _dp, _ip]
+    if lib.sdpb_sizeof_model() != C.sizeof(SdpbModel) or lib.sdpb_sizeof_options() != C.sizeof(SdpbOptions):
+        raise ImportError("libsdpb200.so struct layout differs from the ctypes binding")
+    _lib = lib
+    return lib

@@ -1,0 +1,62 @@
+// dev_model.cuh — device-side form of sdpb_model and the Java-semantics helpers the kernels share.
+//
+// Everything here is compiled with -fmad=false: the reference is Java, which never contracts
+// a*b+c into a fused multiply-add, and results must match it bit for bit
+// (/root/reference/src/sdp/inventory/Recursion.java:139,142).
+#pragma once
+#include <cfloat>
+#include <cstdint>
+
+#include "../../include/sdpb200.h"
+
+namespace sdpb {
+
+// Scalars by value, tables by device pointer.  Passed to kernels as a __grid_constant__ param.
+struct DevModel {
+    int cost_kind, recursion, is_min, T, lead, max_order_idx;
+    unsigned flags;
+    int quantiser;
+    int nI, nQ, nW;       // axis sizes: inventory, one pipeline slot, cash (1 when absent)
+    int i_zero;           // inventory index of the value 0.0 (may lie outside [0,nI))
+    long long S;          // states per period = nI * nQ^lead * nW
+    long long kmin;       // integer cash index of the lowest cash grid point
+    long long q_idiv;     // (long) q_div for SDPB_Q_LONGDIV
+    double inv_min, step;
+    double cash_min, cash_max, q_mul, q_div;
+    double K, h, pen, salvage;
+    double one_plus_dr;   // 1 + depositeRate        (CashConstraint.java:107)
+    double one_minus_rho; // 1 - overheadRate        (CashConstraint.java:110)
+    double neg_r0, r2, r3, od_limit, interest_free;
+    double r2_limit_term; // r2 * (limit - interestFreeAmount)   (CashOverdraft.java:95)
+    double reserve2;
+    // per-period parameter tables, always expanded to T entries on the host
+    const double* price_t;
+    const double* v_t;
+    const double* ovh_t;
+    const double* reserve_t;
+    // demand pmf, flattened; pmf_pg[j] = p_j * gamma (same IEEE product the Java loop forms first,
+    // CashRecursion.java:120 `dAndP[j][1] * discountFactor * V`), pmf_di[j] = d_j / step as an int
+    const double* pmf_d;
+    const double* pmf_p;
+    const double* pmf_pg;
+    const int* pmf_di;
+};
+
+// Math.round(double) -> long: round half up, without forming x + 0.5 (Java >= 7 semantics).
+__device__ __forceinline__ long long jround(double x) {
+    double r = floor(x);
+    double diff = x - r;
+    return (long long)r + (diff >= 0.5 ? 1ll : 0ll);
+}
+
+// Lexicographic (value, action) update used by every argopt reduction: strictly better value
+// wins; on an exact tie the lower action index wins — the same result as the reference's
+// ascending scan with a strict compare (Recursion.java:146-157).
+template <bool IS_MIN>
+__device__ __forceinline__ bool better(double v, int i, double bv, int bi) {
+    return IS_MIN ? (v < bv || (v == bv && i < bi)) : (v > bv || (v == bv && i < bi));
+}
+
+constexpr int kNoAction = 0x7fffffff;
+
+}  // namespace sdpb

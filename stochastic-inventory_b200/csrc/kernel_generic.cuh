@@ -1,0 +1,296 @@
+// kernel_generic.cuh — the general backward-induction kernel: one launch per period, every
+// (state, action, demand) triple evaluated exactly as the reference's lambdas write it.
+//
+//   bi_generic<KIND, SURVIVAL, IS_MIN, G>
+//     G lanes cooperate on one state.  G = 32 for the backorder kinds (lanes stride over the
+//     actions, so the V_{t+1} gather V[(x+a-d, .., a)] is unit-stride across lanes, then a
+//     warp-shuffle (value, action) reduction picks the optimum).  G = 1 for the cash kinds (one
+//     thread per state with the cash axis innermost, so lanes of a warp hold consecutive cash
+//     levels and gather consecutive V[(x', w')] addresses; actions run serially in the thread
+//     because |A(s)| depends on the cash level).
+//   reach_forward<KIND>
+//     forward reachability through every feasible action and demand — the set of states the
+//     reference's top-down memoisation visits (Recursion.java:89-90,141-142) — used to reproduce
+//     getOptTable()/getCacheActions() row sets (Recursion.java:169-186).
+//
+// Reference loops restated (relative to /root/reference):
+//   src/sdp/inventory/Recursion.java:129-161        src/sdp/cash/CashRecursion.java:98-138
+//   src/sdp/inventory/LeadtimeRecursion.java:49-73  src/sdp/cash/CashLeadtimeRecursion.java:50-77
+//   src/sdp/cash/CashRecursionXR.java:82-124        src/sdp/cash/RiskRecursion.java:66-104
+// and the lambdas named in include/sdpb200.h.  Per-(s,a) sub-expressions that do not depend on
+// the demand are hoisted out of the j loop; hoisting does not change any rounding.
+#pragma once
+#include "dev_model.cuh"
+
+namespace sdpb {
+
+// A decoded state plus everything that is constant over its (a, d) loop.
+struct StateCtx {
+    int ix, iq1, iq2, iw;
+    double x, q1, w;  // w: cash (R for the XR kind)
+    int nA;           // |A(s)|
+    double price, v, ovh;
+    bool last, lost, gy;
+    long long strideX;
+};
+
+// Per-(s,a) invariants.
+struct ActionCtx {
+    double a;
+    double stock;     // x + a, x + preQ, or the order-up-to level
+    int iy;           // grid index of `stock` relative to inv_min
+    double fv;        // backorder: fixedCost + variableCost
+    double initCash;  // w, or R - v*x for XR
+    double deposite;  // CASH_DEPOSIT / XR
+    double before_minus_interest;  // CASH_OVERDRAFT: cashBalanceBefore - interest
+    long long pipe;   // successor's pipeline-slot offset
+};
+
+template <int KIND>
+__device__ __forceinline__ StateCtx decode_state(const DevModel& M, int t, long long idx) {
+    StateCtx S;
+    long long r = idx;
+    S.iw = 0; S.iq1 = 0; S.iq2 = 0;
+    if (KIND != SDPB_COST_BACKORDER) { S.iw = (int)(r % M.nW); r /= M.nW; }
+    if (M.lead >= 2) { S.iq2 = (int)(r % M.nQ); r /= M.nQ; }
+    if (M.lead >= 1) { S.iq1 = (int)(r % M.nQ); r /= M.nQ; }
+    S.ix = (int)r;
+    S.x = M.inv_min + (double)S.ix * M.step;
+    S.q1 = (double)S.iq1 * M.step;
+    S.w = 0.0;
+    if (KIND != SDPB_COST_BACKORDER) {
+        const long long k = M.kmin + S.iw;
+        S.w = (KIND != SDPB_COST_CASH_XR && M.quantiser == SDPB_Q_DIV) ? (double)k / M.q_div : (double)k;
+    }
+    S.last = (t == M.T);
+    S.price = M.price_t[t - 1];
+    S.v = M.v_t[t - 1];
+    S.ovh = M.ovh_t[t - 1];
+    S.lost = (M.flags & SDPB_F_LOST_SALES) != 0;
+    S.gy = (KIND == SDPB_COST_BACKORDER) && (M.flags & SDPB_F_GY_MODE) && t == 1;
+    S.strideX = (long long)M.nW * (M.lead >= 1 ? M.nQ : 1) * (M.lead >= 2 ? M.nQ : 1);
+
+    // feasible actions
+    int nA = M.max_order_idx + 1;
+    if (KIND == SDPB_COST_CASH_XR) {
+        // CashConstraintXR.java:71-75
+        const double rv = S.w / S.v;
+        const double maxY = rv < S.x ? S.x : rv;
+        const int length = (int)(maxY - S.x) + 1;
+        nA = length < nA ? length : nA;
+    } else {
+        if (M.flags & SDPB_F_CASH_LIMITED_ACTIONS) {
+            // CashConstraint.java:96-99, cashSurvival.java:103-110
+            const double bound = fmax(0.0, ((S.w - M.reserve_t[t - 1]) - M.reserve2) / S.v);
+            nA = (int)fmin((double)M.max_order_idx, bound) + 1;
+        }
+        if ((M.flags & SDPB_F_NO_ORDER_LAST) && S.last) nA = 1;
+    }
+    S.nA = nA;
+    return S;
+}
+
+template <int KIND>
+__device__ __forceinline__ ActionCtx prep_action(const DevModel& M, const StateCtx& S, int i) {
+    ActionCtx A;
+    A.a = (double)i * M.step;
+    A.pipe = 0;
+    if (M.lead == 1) A.pipe = (long long)i * M.nW;
+    if (M.lead == 2) A.pipe = ((long long)S.iq2 * M.nQ + i) * M.nW;
+    A.fv = 0.0; A.deposite = 0.0; A.before_minus_interest = 0.0; A.initCash = S.w;
+    if (KIND == SDPB_COST_BACKORDER) {
+        // CLSPTesting.java:96-106 / Leadtime.java:71-81 / CLSPforDraw.java:156-170
+        const double fixedCost = S.gy ? 0.0 : (A.a > 0.0 ? M.K : 0.0);
+        const double variableCost = S.gy ? S.v * S.x : S.v * A.a;
+        A.fv = fixedCost + variableCost;
+        A.stock = S.gy ? S.x : (M.lead > 0 ? S.x + S.q1 : S.x + A.a);
+        A.iy = S.gy ? S.ix : (M.lead > 0 ? S.ix + S.iq1 : S.ix + i);
+        return A;
+    }
+    double fixedCost, variableCost;
+    if (KIND == SDPB_COST_CASH_XR) {
+        // CashConstraintXR.java:78-86: the action is the order-up-to level y = x + i*step
+        A.stock = S.x + A.a;
+        A.iy = S.ix + i;
+        const double act = A.stock - S.x;
+        fixedCost = A.stock > S.x ? M.K : 0.0;
+        variableCost = S.v * act;
+        A.initCash = S.w - S.v * S.x;
+    } else {
+        A.stock = M.lead > 0 ? S.x + S.q1 : S.x + A.a;
+        A.iy = M.lead > 0 ? S.ix + S.iq1 : S.ix + i;
+        fixedCost = A.a > 0.0 ? M.K : 0.0;
+        variableCost = S.v * A.a;
+    }
+    if (KIND == SDPB_COST_CASH_OVERDRAFT) {
+        // CashOverdraft.java:85-95
+        const double before = ((A.initCash - fixedCost) - variableCost) - S.ovh;
+        double interest;
+        if (before >= 0.0)
+            interest = M.neg_r0 * before;
+        else if (before >= -M.interest_free)
+            interest = 0.0;
+        else if (before >= -M.od_limit)
+            interest = M.r2 * (-before - M.interest_free);
+        else
+            interest = M.r3 * (-before - M.od_limit) + M.r2_limit_term;
+        A.before_minus_interest = before - interest;
+    } else {
+        A.deposite = ((A.initCash - fixedCost) - variableCost) * M.one_plus_dr;
+    }
+    return A;
+}
+
+// Immediate value c(s,a,d).
+template <int KIND>
+__device__ __forceinline__ double immediate(const DevModel& M, const StateCtx& S, const ActionCtx& A,
+                                            double d) {
+    const double lvl = A.stock - d;
+    if (KIND == SDPB_COST_BACKORDER) {
+        const double hold = M.h * fmax(lvl, 0.0);
+        const double pen = M.pen * fmax(-lvl, 0.0);
+        return (A.fv + hold) + pen;
+    }
+    const double revenue = S.price * fmin(A.stock, d);
+    double inc;
+    if (KIND == SDPB_COST_CASH_OVERDRAFT) {
+        const double after = A.before_minus_interest + revenue;  // CashOverdraft.java:99
+        inc = after - A.initCash;
+    } else {
+        const double hold = M.h * fmax(lvl, 0.0);
+        inc = (((M.one_minus_rho * revenue + A.deposite) - hold) - S.ovh) - A.initCash;
+    }
+    const double sal = S.last ? M.salvage * fmax(lvl, 0.0) : 0.0;
+    inc += sal;
+    if (KIND == SDPB_COST_CASH_DEPOSIT) {
+        const double endCash = A.initCash + inc;  // CashConstraint.java:116-119
+        if (endCash < 0.0) inc += M.pen * endCash;
+    }
+    return inc;
+}
+
+// Successor f(s,a,d) as a flattened grid index; `bankrupt` = successor cash < 0 (survival only).
+template <int KIND>
+__device__ __forceinline__ long long successor(const DevModel& M, const StateCtx& S, const ActionCtx& A,
+                                               int di, double c, bool& bankrupt) {
+    int il = A.iy - di;
+    if (S.lost) il = max(il, M.i_zero);
+    il = min(il, M.nI - 1);  // upper clamp first, then lower (CLSPTesting.java:91-92)
+    il = max(il, 0);
+    bankrupt = false;
+    if (KIND == SDPB_COST_BACKORDER) return il * S.strideX + A.pipe;
+    // CashConstraint.java:123-133 / CashConstraintXR.java:95-110
+    double nw = A.initCash + c;
+    nw = nw > M.cash_max ? M.cash_max : nw;
+    nw = nw < M.cash_min ? M.cash_min : nw;
+    const long long kk = jround(nw * M.q_mul);
+    long long k = (M.quantiser == SDPB_Q_DIV) ? kk : kk / M.q_idiv;
+    bankrupt = k < 0;  // quantised cash < 0 (q_div > 0)
+    if (KIND == SDPB_COST_CASH_XR) {
+        const double nwq = (M.quantiser == SDPB_Q_DIV) ? (double)kk / M.q_div : (double)k;
+        const double nx = M.inv_min + (double)il * M.step;
+        k = jround(nwq + S.v * nx);  // nextR, CashConstraintXR.java:107
+    }
+    long long kw = k - M.kmin;
+    kw = kw < 0 ? 0 : (kw >= M.nW ? M.nW - 1 : kw);
+    return il * S.strideX + A.pipe + kw;
+}
+
+template <int KIND, bool SURVIVAL, bool IS_MIN, int G>
+__global__ void __launch_bounds__(256)
+bi_generic(const __grid_constant__ DevModel M, const int t, const int D, const int pmf_off,
+           const double* __restrict__ Vn, double* __restrict__ Vt, int* __restrict__ Qt,
+           const long long lo, const long long hi) {
+    const long long gid = (long long)blockIdx.x * (256 / G) + threadIdx.x / G;
+    const int lane = threadIdx.x % G;
+    const long long idx = lo + gid;
+    const bool live = idx < hi;  // dead groups still take part in the shuffles below
+    const StateCtx S = decode_state<KIND>(M, t, live ? idx : lo);
+
+    const double* __restrict__ pd = M.pmf_d + pmf_off;
+    const double* __restrict__ pp = M.pmf_p + pmf_off;
+    const double* __restrict__ pg = M.pmf_pg + pmf_off;
+    const int* __restrict__ pdi = M.pmf_di + pmf_off;
+
+    double best = IS_MIN ? DBL_MAX : -DBL_MAX;
+    int besti = kNoAction;
+
+    for (int i = lane; i < S.nA; i += G) {
+        const ActionCtx A = prep_action<KIND>(M, S, i);
+        double acc = 0.0;
+        for (int j = 0; j < D; j++) {
+            const double c = immediate<KIND>(M, S, A, __ldg(pd + j));
+            if (!SURVIVAL) acc += __ldg(pp + j) * c;                  // Recursion.java:139
+            if (S.last) {
+                if (SURVIVAL) {                                       // RiskRecursion.java:80-84
+                    const double finalCash = A.initCash + c;
+                    acc += __ldg(pp + j) * (finalCash >= 0.0 ? 1.0 : 0.0);
+                }
+            } else {
+                bool bankrupt;
+                const long long ni = successor<KIND>(M, S, A, __ldg(pdi + j), c, bankrupt);
+                double vn = __ldg(Vn + ni);
+                if (SURVIVAL && bankrupt) vn = 0.0;                   // RiskRecursion.java:87-95
+                acc += __ldg(pg + j) * vn;                            // Recursion.java:142
+            }
+        }
+        // ascending i within a lane: strict compare keeps the first optimum (Recursion.java:146-157)
+        if (IS_MIN ? (acc < best) : (acc > best)) { best = acc; besti = i; }
+    }
+
+    if (G > 1) {
+#pragma unroll
+        for (int s = G / 2; s > 0; s >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, s, G);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, s, G);
+            if (better<IS_MIN>(ov, oi, best, besti)) { best = ov; besti = oi; }
+        }
+    }
+    if (live && lane == 0) {
+        Vt[idx] = best;
+        Qt[idx] = besti == kNoAction ? -1 : besti;
+    }
+}
+
+// One thread per (state of period t): if the state is reached, mark every successor in the
+// period t+1 mask.  Masks are one byte per state; races only ever write 1.
+template <int KIND, bool SURVIVAL>
+__global__ void __launch_bounds__(256)
+reach_forward(const __grid_constant__ DevModel M, const int t, const int D, const int pmf_off,
+              const unsigned char* __restrict__ mask_t, unsigned char* __restrict__ mask_n) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M.S || !mask_t[idx]) return;
+    const StateCtx S = decode_state<KIND>(M, t, idx);
+    const double* __restrict__ pd = M.pmf_d + pmf_off;
+    const int* __restrict__ pdi = M.pmf_di + pmf_off;
+    for (int i = 0; i < S.nA; i++) {
+        const ActionCtx A = prep_action<KIND>(M, S, i);
+        for (int j = 0; j < D; j++) {
+            const double c = immediate<KIND>(M, S, A, __ldg(pd + j));
+            bool bankrupt;
+            const long long ni = successor<KIND>(M, S, A, __ldg(pdi + j), c, bankrupt);
+            // getSurvProb never recurses into a bankrupt successor (RiskRecursion.java:89-94)
+            if (!(SURVIVAL && bankrupt)) mask_n[ni] = 1;
+        }
+    }
+}
+
+// One thread per (state, action, demand) triple: the lambdas alone, for descriptor spot checks.
+template <int KIND>
+__global__ void eval_triples(const __grid_constant__ DevModel M, const int t, const int n,
+                             const long long* __restrict__ sidx, const int* __restrict__ aidx,
+                             const double* __restrict__ dem, const int* __restrict__ demi,
+                             double* __restrict__ c_out, long long* __restrict__ next_out,
+                             int* __restrict__ na_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const StateCtx S = decode_state<KIND>(M, t, sidx[i]);
+    const ActionCtx A = prep_action<KIND>(M, S, aidx[i]);
+    const double c = immediate<KIND>(M, S, A, dem[i]);
+    bool bankrupt;
+    c_out[i] = c;
+    next_out[i] = successor<KIND>(M, S, A, demi[i], c, bankrupt);
+    na_out[i] = S.nA;
+}
+
+}  // namespace sdpb

@@ -1,0 +1,729 @@
+// sdpb200.cu — the C-ABI of libsdpb200.so (include/sdpb200.h): descriptor validation, device
+// tables, one kernel launch per period, result extraction.  No CPU solve path exists here: if the
+// device is missing every entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sdpb200.h"
+#include "dev_model.cuh"
+#include "kernel_generic.cuh"
+#include "kernel_tiled.cuh"
+
+using namespace sdpb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+inline long long h_jround(double x) {  // Math.round(double)
+    double r = std::floor(x);
+    return (long long)r + ((x - r) >= 0.5 ? 1 : 0);
+}
+inline bool is_int(double x) { return std::isfinite(x) && x == std::floor(x) && std::fabs(x) < 1e15; }
+
+#define CU(call)                                                                        \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                \
+            return SDPB_ERR_CUDA;                                                       \
+        }                                                                               \
+    } while (0)
+
+template <class T>
+int upload(sdpb_handle* h, const std::vector<T>& v, T** out);
+
+}  // namespace
+
+struct sdpb_handle {
+    sdpb_model m{};
+    DevModel dm{};
+    sdpb_options opt{};
+    std::vector<int> pmf_len, pmf_off;
+    std::vector<double> pmf_d, pmf_p;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int ndim = 1;
+    long long S = 0, Spad = 0, lo = 0, hi = 0;
+    std::vector<double*> dV;  // [T] each Spad doubles (full grid: period t-1 reads all of period t)
+    std::vector<int*> dQ;     // [T] each Spad int32 action indices (-1 = none)
+    std::vector<unsigned char*> dMask;  // [T] reachability, one byte per state
+    std::vector<char> solved;
+    std::vector<void*> dev_allocs;
+    bool reached = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    sdpb_stats stats{};
+    TiledPlan tiled{};
+    std::string err;
+};
+
+namespace {
+
+template <class T>
+int upload(sdpb_handle* h, const std::vector<T>& v, T** out) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CU(cudaMalloc(&p, bytes));
+    h->dev_allocs.push_back(p);
+    if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (T*)p;
+    return SDPB_OK;
+}
+
+int fail_create(sdpb_handle* h, int code, const std::string& msg) {
+    g_create_error = msg;
+    if (h) sdpb_destroy(h);
+    return code;
+}
+
+bool has_cash(const sdpb_model& m) { return m.cost_kind != SDPB_COST_BACKORDER; }
+
+double cash_of_k(const sdpb_handle* h, long long k) {
+    const sdpb_model& m = h->m;
+    if (m.cost_kind == SDPB_COST_CASH_XR) return (double)k;
+    return m.quantiser == SDPB_Q_DIV ? (double)k / m.q_div : (double)k;
+}
+double quantise(const sdpb_model& m, double w) {
+    long long kk = h_jround(w * m.q_mul);
+    if (m.quantiser == SDPB_Q_DIV) return (double)kk / m.q_div;
+    return (double)(kk / (long long)m.q_div);
+}
+long long cash_k_of(const sdpb_model& m, double wq) {
+    if (m.cost_kind == SDPB_COST_CASH_XR) return h_jround(wq);
+    return m.quantiser == SDPB_Q_DIV ? h_jround(wq * m.q_div) : (long long)wq;
+}
+
+// API-order state -> flattened index, or -1 when it is not a grid point.
+long long index_of_state(const sdpb_handle* h, const double* st) {
+    const sdpb_model& m = h->m;
+    const DevModel& d = h->dm;
+    int k = 0;
+    double x = st[k++];
+    double fi = (x - m.inv_min) / m.step;
+    if (!is_int(fi) || fi < 0 || fi >= d.nI) return -1;
+    long long idx = (long long)fi;
+    long long iw = 0;
+    if (has_cash(m)) {
+        double w = st[k++];
+        long long kk = cash_k_of(m, w);
+        if (cash_of_k(h, kk) != w) return -1;
+        iw = kk - d.kmin;
+        if (iw < 0 || iw >= d.nW) return -1;
+    }
+    for (int l = 0; l < m.lead_time; l++) {
+        double q = st[k++];
+        double fq = q / m.step;
+        if (!is_int(fq) || fq < 0 || fq >= d.nQ) return -1;
+        idx = idx * d.nQ + (long long)fq;
+    }
+    if (has_cash(m)) idx = idx * d.nW + iw;
+    return idx;
+}
+
+void state_of_index(const sdpb_handle* h, long long idx, double* st, double* x_out) {
+    const sdpb_model& m = h->m;
+    const DevModel& d = h->dm;
+    double w = 0, q1 = 0, q2 = 0;
+    if (has_cash(m)) { w = cash_of_k(h, d.kmin + idx % d.nW); idx /= d.nW; }
+    if (m.lead_time >= 2) { q2 = (double)(idx % d.nQ) * m.step; idx /= d.nQ; }
+    if (m.lead_time >= 1) { q1 = (double)(idx % d.nQ) * m.step; idx /= d.nQ; }
+    double x = m.inv_min + (double)idx * m.step;
+    if (x_out) *x_out = x;
+    if (st) {
+        int k = 0;
+        st[k++] = x;
+        if (has_cash(m)) st[k++] = w;
+        if (m.lead_time >= 1) st[k++] = q1;
+        if (m.lead_time >= 2) st[k++] = q2;
+    }
+}
+
+inline double q_of_index(const sdpb_handle* h, long long idx, int qi) {
+    if (qi < 0) return 0.0;  // bestOrderQty stays 0 when nothing beat the initial value
+    if (h->m.cost_kind == SDPB_COST_CASH_XR) {
+        double x;
+        state_of_index(h, idx, nullptr, &x);
+        return x + (double)qi * h->m.step;
+    }
+    return (double)qi * h->m.step;
+}
+
+// |A_t(s)| summed over the shard, times D_t (host arithmetic; mirrors decode_state()).
+double count_evals_period(const sdpb_handle* h, int t) {
+    const sdpb_model& m = h->m;
+    const DevModel& d = h->dm;
+    const double D = h->pmf_len[t - 1];
+    const long long n = h->hi - h->lo;
+    const bool limited = (m.flags & SDPB_F_CASH_LIMITED_ACTIONS) || m.cost_kind == SDPB_COST_CASH_XR;
+    if ((m.flags & SDPB_F_NO_ORDER_LAST) && t == m.T && m.cost_kind != SDPB_COST_CASH_XR) return (double)n * D;
+    if (!limited) return (double)n * (m.max_order_idx + 1) * D;
+    const double v = m.vari_cost_t ? m.vari_cost_t[t - 1] : m.vari_cost;
+    const double res = m.reserve_t ? m.reserve_t[t - 1] : 0.0;
+    double total = 0;
+    // the action count depends on (x, w) only; walk the shard
+    for (long long idx = h->lo; idx < h->hi; idx++) {
+        long long r = idx;
+        double w = cash_of_k(h, d.kmin + r % d.nW);
+        r /= d.nW;
+        for (int l = 0; l < m.lead_time; l++) r /= d.nQ;
+        double x = m.inv_min + (double)r * m.step;
+        int nA;
+        if (m.cost_kind == SDPB_COST_CASH_XR) {
+            double rv = w / v;
+            double maxY = rv < x ? x : rv;
+            nA = std::min((int)(maxY - x) + 1, m.max_order_idx + 1);
+        } else {
+            nA = (int)std::min((double)m.max_order_idx, std::max(0.0, ((w - res) - m.reserve2) / v)) + 1;
+        }
+        total += nA;
+    }
+    return total * D;
+}
+
+template <int KIND, bool SURV, bool IS_MIN, int G>
+void launch_generic(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt) {
+    const long long n = h->hi - h->lo;
+    const int per_block = 256 / G;
+    const long long blocks = (n + per_block - 1) / per_block;
+    bi_generic<KIND, SURV, IS_MIN, G><<<(unsigned)blocks, 256, 0, h->stream>>>(
+        h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, h->lo, h->hi);
+}
+
+int dispatch_generic(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt) {
+    const sdpb_model& m = h->m;
+    const bool surv = m.recursion == SDPB_REC_SURVIVAL;
+    const bool mn = h->dm.is_min != 0;
+    switch (m.cost_kind) {
+    case SDPB_COST_BACKORDER:
+        if (mn) launch_generic<SDPB_COST_BACKORDER, false, true, 32>(h, t, Vn, Vt, Qt);
+        else launch_generic<SDPB_COST_BACKORDER, false, false, 32>(h, t, Vn, Vt, Qt);
+        break;
+    case SDPB_COST_CASH_DEPOSIT:
+        if (surv) launch_generic<SDPB_COST_CASH_DEPOSIT, true, false, 1>(h, t, Vn, Vt, Qt);
+        else if (mn) launch_generic<SDPB_COST_CASH_DEPOSIT, false, true, 1>(h, t, Vn, Vt, Qt);
+        else launch_generic<SDPB_COST_CASH_DEPOSIT, false, false, 1>(h, t, Vn, Vt, Qt);
+        break;
+    case SDPB_COST_CASH_OVERDRAFT:
+        if (surv) launch_generic<SDPB_COST_CASH_OVERDRAFT, true, false, 1>(h, t, Vn, Vt, Qt);
+        else if (mn) launch_generic<SDPB_COST_CASH_OVERDRAFT, false, true, 1>(h, t, Vn, Vt, Qt);
+        else launch_generic<SDPB_COST_CASH_OVERDRAFT, false, false, 1>(h, t, Vn, Vt, Qt);
+        break;
+    case SDPB_COST_CASH_XR:
+        if (mn) launch_generic<SDPB_COST_CASH_XR, false, true, 1>(h, t, Vn, Vt, Qt);
+        else launch_generic<SDPB_COST_CASH_XR, false, false, 1>(h, t, Vn, Vt, Qt);
+        break;
+    default:
+        h->err = "bad cost_kind";
+        return SDPB_ERR_ARG;
+    }
+    return SDPB_OK;
+}
+
+template <int KIND, bool SURV>
+void launch_reach(sdpb_handle* h, int t) {
+    const long long blocks = (h->S + 255) / 256;
+    reach_forward<KIND, SURV><<<(unsigned)blocks, 256, 0, h->stream>>>(
+        h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], h->dMask[t - 1], h->dMask[t]);
+}
+
+__global__ void gather_vq(const long long* __restrict__ idx, int n, const double* __restrict__ V,
+                          const int* __restrict__ Q, double* __restrict__ v, int* __restrict__ q) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { v[i] = V[idx[i]]; q[i] = Q[idx[i]]; }
+}
+
+int solve_period(sdpb_handle* h, int t) {
+    const sdpb_model& m = h->m;
+    if (t < 1 || t > m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
+    if (t < m.T && !h->solved[t]) { h->err = "period t+1 not solved yet"; return SDPB_ERR_STATE; }
+    const double* Vn = t < m.T ? h->dV[t] : nullptr;
+    int rc;
+    if (h->tiled.available && h->opt.kernel != SDPB_KERNEL_GENERIC) {
+        rc = launch_tiled(h->tiled, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, h->dV[t - 1],
+                          h->dQ[t - 1], h->lo, h->hi, h->stream, &h->stats.fp64_ops);
+        h->stats.kernel_used = SDPB_KERNEL_TILED;
+    } else {
+        rc = dispatch_generic(h, t, Vn, h->dV[t - 1], h->dQ[t - 1]);
+        h->stats.kernel_used = SDPB_KERNEL_GENERIC;
+    }
+    if (rc != SDPB_OK) return rc;
+    CU(cudaGetLastError());
+    h->solved[t - 1] = 1;
+    h->stats.launches++;
+    h->stats.evals += count_evals_period(h, t);
+    return SDPB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sdpb_abi_version(void) { return SDPB_ABI_VERSION; }
+size_t sdpb_sizeof_model(void) { return sizeof(sdpb_model); }
+size_t sdpb_sizeof_options(void) { return sizeof(sdpb_options); }
+
+const char* sdpb_last_error(const sdpb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void sdpb_destroy(sdpb_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (void* p : h->dev_allocs) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out) {
+    g_create_error.clear();
+    if (!m || !out) return fail_create(nullptr, SDPB_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (m->struct_size != sizeof(sdpb_model))
+        return fail_create(nullptr, SDPB_ERR_ARG, "sdpb_model.struct_size does not match this library");
+    if (opt && opt->struct_size != sizeof(sdpb_options))
+        return fail_create(nullptr, SDPB_ERR_ARG, "sdpb_options.struct_size does not match this library");
+    if (m->T < 1 || !m->pmf_len || !m->pmf_d || !m->pmf_p)
+        return fail_create(nullptr, SDPB_ERR_ARG, "T < 1 or null pmf");
+    if (m->cost_kind < 0 || m->cost_kind > SDPB_COST_CASH_XR) return fail_create(nullptr, SDPB_ERR_ARG, "bad cost_kind");
+    if (m->lead_time < 0 || m->lead_time > 2) return fail_create(nullptr, SDPB_ERR_ARG, "lead_time must be 0, 1 or 2");
+    if (m->cost_kind == SDPB_COST_CASH_XR && m->lead_time != 0)
+        return fail_create(nullptr, SDPB_ERR_ARG, "XR kind has no lead time");
+    if (m->recursion == SDPB_REC_SURVIVAL &&
+        !(m->cost_kind == SDPB_COST_CASH_DEPOSIT || m->cost_kind == SDPB_COST_CASH_OVERDRAFT))
+        return fail_create(nullptr, SDPB_ERR_ARG, "survival recursion needs a cash kind");
+    if (m->max_order_idx < 0) return fail_create(nullptr, SDPB_ERR_ARG, "max_order_idx < 0");
+
+    // ---- exact-grid validation: every x, a, d is an integer multiple of a power-of-two step ----
+    int ex;
+    if (!(m->step > 0) || std::frexp(m->step, &ex) != 0.5)
+        return fail_create(nullptr, SDPB_ERR_OFFGRID, "step must be a positive power of two");
+    if (!is_int(m->inv_min / m->step) || !is_int(m->inv_max / m->step) || m->inv_max < m->inv_min)
+        return fail_create(nullptr, SDPB_ERR_OFFGRID, "inventory bounds are not multiples of step");
+
+    sdpb_handle* h = new (std::nothrow) sdpb_handle();
+    if (!h) return fail_create(nullptr, SDPB_ERR_NOMEM, "out of host memory");
+    h->m = *m;
+    if (opt) h->opt = *opt;
+    else { h->opt.struct_size = sizeof(sdpb_options); h->opt.device = -1; h->opt.shard_count = 1; }
+    if (h->opt.shard_count < 1) h->opt.shard_count = 1;
+    if (h->opt.shard_rank < 0 || h->opt.shard_rank >= h->opt.shard_count)
+        return fail_create(h, SDPB_ERR_ARG, "shard_rank out of range");
+
+    const int T = m->T;
+    h->pmf_len.assign(m->pmf_len, m->pmf_len + T);
+    h->pmf_off.assign(T + 1, 0);
+    for (int t = 0; t < T; t++) {
+        if (h->pmf_len[t] < 1) return fail_create(h, SDPB_ERR_ARG, "empty pmf row");
+        h->pmf_off[t + 1] = h->pmf_off[t] + h->pmf_len[t];
+    }
+    const int NP = h->pmf_off[T];
+    h->pmf_d.assign(m->pmf_d, m->pmf_d + NP);
+    h->pmf_p.assign(m->pmf_p, m->pmf_p + NP);
+    h->m.pmf_len = h->pmf_len.data();
+    h->m.pmf_d = h->pmf_d.data();
+    h->m.pmf_p = h->pmf_p.data();
+    std::vector<double> pg(NP);
+    std::vector<int> pdi(NP);
+    for (int j = 0; j < NP; j++) {
+        double f = h->pmf_d[j] / m->step;
+        if (!is_int(f) || std::fabs(f) > 1e9)
+            return fail_create(h, SDPB_ERR_OFFGRID, "a demand value is not a multiple of step");
+        pdi[j] = (int)f;
+        pg[j] = h->pmf_p[j] * m->gamma;  // first product of `p * gamma * V` (CashRecursion.java:120)
+    }
+    // per-period parameter tables; deep copies so the caller's arrays may go away
+    std::vector<double> price_t(T), v_t(T), ovh_t(T), res_t(T);
+    for (int t = 0; t < T; t++) {
+        price_t[t] = m->price_t ? m->price_t[t] : m->price;
+        v_t[t] = m->vari_cost_t ? m->vari_cost_t[t] : m->vari_cost;
+        ovh_t[t] = m->overhead_t ? m->overhead_t[t] : m->overhead;
+        res_t[t] = m->reserve_t ? m->reserve_t[t] : 0.0;
+    }
+
+    DevModel& d = h->dm;
+    d.cost_kind = m->cost_kind;
+    d.recursion = m->recursion;
+    d.is_min = (m->recursion == SDPB_REC_SURVIVAL) ? 0 : (m->direction == SDPB_MIN);
+    d.T = T;
+    d.lead = m->lead_time;
+    d.max_order_idx = m->max_order_idx;
+    d.flags = m->flags;
+    d.quantiser = m->quantiser;
+    d.nI = (int)h_jround((m->inv_max - m->inv_min) / m->step) + 1;
+    d.nQ = m->lead_time > 0 ? m->max_order_idx + 1 : 1;
+    d.i_zero = (int)h_jround((0.0 - m->inv_min) / m->step);
+    d.inv_min = m->inv_min;
+    d.step = m->step;
+    d.nW = 1;
+    d.kmin = 0;
+    d.q_mul = d.q_div = 1.0;
+    d.q_idiv = 1;
+    if (has_cash(*m)) {
+        if (!(m->q_mul > 0) || !(m->q_div > 0) || m->cash_max < m->cash_min)
+            return fail_create(h, SDPB_ERR_ARG, "bad cash axis (q_mul, q_div > 0; cash_max >= cash_min)");
+        if (m->quantiser == SDPB_Q_LONGDIV && (!is_int(m->q_div) || m->q_div < 1))
+            return fail_create(h, SDPB_ERR_ARG, "SDPB_Q_LONGDIV needs an integer q_div >= 1");
+        if (m->quantiser != SDPB_Q_DIV && m->quantiser != SDPB_Q_LONGDIV)
+            return fail_create(h, SDPB_ERR_ARG, "bad quantiser");
+        long long kmin, kmax;
+        if (m->cost_kind == SDPB_COST_CASH_XR) {
+            if (m->vari_cost_t) return fail_create(h, SDPB_ERR_ARG, "XR kind takes a constant vari_cost");
+            if (!is_int(m->vari_cost * m->step) || m->quantiser != SDPB_Q_LONGDIV || m->q_div != 1.0)
+                return fail_create(h, SDPB_ERR_OFFGRID, "XR kind needs integer v*step and the round(w*1)/1 quantiser");
+            kmin = h_jround(quantise(*m, m->cash_min) + m->vari_cost * m->inv_min);
+            kmax = h_jround(quantise(*m, m->cash_max) + m->vari_cost * m->inv_max);
+        } else {
+            kmin = cash_k_of(*m, quantise(*m, m->cash_min));
+            kmax = cash_k_of(*m, quantise(*m, m->cash_max));
+        }
+        if (kmax < kmin || kmax - kmin > 100000000ll) return fail_create(h, SDPB_ERR_ARG, "cash axis too large");
+        d.kmin = kmin;
+        d.nW = (int)(kmax - kmin + 1);
+        d.q_mul = m->q_mul;
+        d.q_div = m->q_div;
+        d.q_idiv = (long long)m->q_div;
+    }
+    d.cash_min = m->cash_min;
+    d.cash_max = m->cash_max;
+    d.K = m->fixed_cost;
+    d.h = m->hold_cost;
+    d.pen = m->penalty_cost;
+    d.salvage = m->salvage;
+    d.one_plus_dr = 1 + m->deposit_rate;
+    d.one_minus_rho = 1 - m->overhead_rate;
+    d.neg_r0 = -m->r0;
+    d.r2 = m->r2;
+    d.r3 = m->r3;
+    d.od_limit = m->od_limit;
+    d.interest_free = m->interest_free;
+    d.r2_limit_term = m->r2 * (m->od_limit - m->interest_free);
+    d.reserve2 = m->reserve2;
+    long long S = d.nI;
+    for (int l = 0; l < m->lead_time; l++) S *= d.nQ;
+    S *= d.nW;
+    d.S = S;
+    h->S = S;
+    h->ndim = 1 + (has_cash(*m) ? 1 : 0) + m->lead_time;
+    const long long chunk = (S + h->opt.shard_count - 1) / h->opt.shard_count;
+    h->Spad = chunk * h->opt.shard_count;
+    h->lo = std::min(S, chunk * h->opt.shard_rank);
+    h->hi = std::min(S, h->lo + chunk);
+
+    // ---- device ----
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail_create(h, SDPB_ERR_NO_DEVICE, "no CUDA device (libsdpb200 has no CPU path)");
+    int dev = h->opt.device;
+    if (dev < 0) cudaGetDevice(&dev);
+    if (dev >= ndev) return fail_create(h, SDPB_ERR_NO_DEVICE, "device ordinal out of range");
+    h->device = dev;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+        return fail_create(h, SDPB_ERR_NO_DEVICE, "cannot select CUDA device");
+    if (prop.major != 10)
+        return fail_create(h, SDPB_ERR_NO_DEVICE, "libsdpb200 is built for sm_100a (B200) only");
+    if (h->opt.stream) { h->stream = (cudaStream_t)h->opt.stream; }
+    else {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_CUDA, "cudaStreamCreate failed");
+        h->own_stream = true;
+    }
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+
+    double *dp = nullptr;
+    int* di = nullptr;
+    int rc;
+#define UP(vec, field, tmp) \
+    if ((rc = upload(h, vec, &tmp)) != SDPB_OK) return fail_create(h, rc, h->err); \
+    d.field = tmp;
+    UP(price_t, price_t, dp) UP(v_t, v_t, dp) UP(ovh_t, ovh_t, dp) UP(res_t, reserve_t, dp)
+    UP(h->pmf_d, pmf_d, dp) UP(h->pmf_p, pmf_p, dp) UP(pg, pmf_pg, dp) UP(pdi, pmf_di, di)
+#undef UP
+
+    h->dV.assign(T, nullptr);
+    h->dQ.assign(T, nullptr);
+    h->dMask.assign(T, nullptr);
+    h->solved.assign(T, 0);
+    for (int t = 0; t < T; t++) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, (size_t)h->Spad * sizeof(double)) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "cudaMalloc of a value table failed");
+        h->dev_allocs.push_back(p);
+        h->dV[t] = (double*)p;
+        if (cudaMalloc(&p, (size_t)h->Spad * sizeof(int)) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "cudaMalloc of a policy table failed");
+        h->dev_allocs.push_back(p);
+        h->dQ[t] = (int*)p;
+    }
+
+    // ---- kernel plan ----
+    plan_tiled(h->tiled, h->m, h->dm, h->pmf_len, h->pmf_off, pdi, h->opt.dedup != 0, prop);
+    if (h->opt.kernel == SDPB_KERNEL_TILED && !h->tiled.available)
+        return fail_create(h, SDPB_ERR_ARG, std::string("no tiled kernel for this model: ") + h->tiled.why_not);
+    *out = h;
+    return SDPB_OK;
+}
+
+int sdpb_grid_info(const sdpb_handle* h, sdpb_grid* g) {
+    if (!h || !g) return SDPB_ERR_ARG;
+    g->ndim = h->ndim;
+    g->n_inv = h->dm.nI;
+    g->n_cash = h->dm.nW;
+    g->n_q = h->dm.nQ;
+    g->n_states = h->S;
+    g->shard_lo = h->lo;
+    g->shard_hi = h->hi;
+    g->n_actions = h->m.max_order_idx + 1;
+    g->T = h->m.T;
+    g->cash_k_min = h->dm.kmin;
+    return SDPB_OK;
+}
+
+int sdpb_solve_period_async(sdpb_handle* h, int period) {
+    if (!h) return SDPB_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    return solve_period(h, period);
+}
+
+int sdpb_sync(sdpb_handle* h) {
+    if (!h) return SDPB_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return SDPB_OK;
+}
+
+int sdpb_solve(sdpb_handle* h) {
+    if (!h) return SDPB_ERR_ARG;
+    if (h->opt.shard_count != 1) {
+        h->err = "sdpb_solve needs an unsharded handle; step sharded handles with sdpb_solve_period_async "
+                 "and all-gather V_t between periods";
+        return SDPB_ERR_STATE;
+    }
+    CU(cudaSetDevice(h->device));
+    std::fill(h->solved.begin(), h->solved.end(), 0);
+    h->stats = sdpb_stats{};
+    h->reached = false;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    for (int t = h->m.T; t >= 1; t--) {
+        int rc = solve_period(h, t);
+        if (rc != SDPB_OK) return rc;
+    }
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.solve_ms = ms;
+    h->stats.kernel_ms = ms;
+    return SDPB_OK;
+}
+
+int sdpb_value(sdpb_handle* h, int period, const double* states, int n, double* v, double* q) {
+    if (!h || !states || n < 0) return SDPB_ERR_ARG;
+    if (period < 1 || period > h->m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
+    if (!h->solved[period - 1]) { h->err = "period not solved"; return SDPB_ERR_STATE; }
+    if (n == 0) return SDPB_OK;
+    CU(cudaSetDevice(h->device));
+    std::vector<long long> idx(n);
+    for (int i = 0; i < n; i++) {
+        idx[i] = index_of_state(h, states + (size_t)i * h->ndim);
+        if (idx[i] < 0) {
+            h->err = "state " + std::to_string(i) + " is not a grid point (the reference would throw a "
+                     "NullPointerException from getAction on an unsolved state)";
+            return SDPB_ERR_UNSOLVED;
+        }
+        if (h->opt.shard_count > 1 && (idx[i] < h->lo || idx[i] >= h->hi) && q) {
+            h->err = "policy of a state owned by another shard";
+            return SDPB_ERR_UNSOLVED;
+        }
+    }
+    long long* dIdx = nullptr;
+    double* dv = nullptr;
+    int* dq = nullptr;
+    CU(cudaMalloc(&dIdx, n * sizeof(long long)));
+    CU(cudaMalloc(&dv, n * sizeof(double)));
+    CU(cudaMalloc(&dq, n * sizeof(int)));
+    std::vector<double> hv(n);
+    std::vector<int> hq(n);
+    cudaError_t e = cudaMemcpyAsync(dIdx, idx.data(), n * sizeof(long long), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        gather_vq<<<(n + 255) / 256, 256, 0, h->stream>>>(dIdx, n, h->dV[period - 1], h->dQ[period - 1], dv, dq);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hv.data(), dv, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hq.data(), dq, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dIdx); cudaFree(dv); cudaFree(dq);
+    if (e != cudaSuccess) { h->err = std::string("sdpb_value: ") + cudaGetErrorString(e); return SDPB_ERR_CUDA; }
+    for (int i = 0; i < n; i++) {
+        if (v) v[i] = hv[i];
+        if (q) q[i] = q_of_index(h, idx[i], hq[i]);
+    }
+    return SDPB_OK;
+}
+
+int sdpb_period_tables(sdpb_handle* h, int period, double* V, double* Q) {
+    if (!h) return SDPB_ERR_ARG;
+    if (period < 1 || period > h->m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
+    if (!h->solved[period - 1]) { h->err = "period not solved"; return SDPB_ERR_STATE; }
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (V) CU(cudaMemcpy(V, h->dV[period - 1], (size_t)h->S * sizeof(double), cudaMemcpyDeviceToHost));
+    if (Q) {
+        std::vector<int> hq((size_t)h->S);
+        CU(cudaMemcpy(hq.data(), h->dQ[period - 1], (size_t)h->S * sizeof(int), cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < h->S; i++) Q[i] = q_of_index(h, i, hq[i]);
+    }
+    return SDPB_OK;
+}
+
+int sdpb_device_tables(sdpb_handle* h, int period, void** dV, void** dQidx) {
+    if (!h) return SDPB_ERR_ARG;
+    if (period < 1 || period > h->m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
+    if (dV) *dV = h->dV[period - 1];
+    if (dQidx) *dQidx = h->dQ[period - 1];
+    return SDPB_OK;
+}
+
+int sdpb_state_of_index(const sdpb_handle* h, int64_t idx, double* state) {
+    if (!h || !state || idx < 0 || idx >= h->S) return SDPB_ERR_ARG;
+    state_of_index(h, idx, state, nullptr);
+    return SDPB_OK;
+}
+
+int sdpb_reach(sdpb_handle* h, const double* init_states, int n) {
+    if (!h || !init_states || n < 1) return SDPB_ERR_ARG;
+    if (h->opt.shard_count != 1) { h->err = "sdpb_reach needs an unsharded handle"; return SDPB_ERR_STATE; }
+    CU(cudaSetDevice(h->device));
+    const int T = h->m.T;
+    for (int t = 0; t < T; t++) {
+        if (!h->dMask[t]) {
+            void* p = nullptr;
+            CU(cudaMalloc(&p, (size_t)h->S));
+            h->dev_allocs.push_back(p);
+            h->dMask[t] = (unsigned char*)p;
+        }
+        CU(cudaMemsetAsync(h->dMask[t], 0, (size_t)h->S, h->stream));
+    }
+    for (int i = 0; i < n; i++) {
+        long long idx = index_of_state(h, init_states + (size_t)i * h->ndim);
+        if (idx < 0) { h->err = "initial state is not a grid point"; return SDPB_ERR_UNSOLVED; }
+        CU(cudaMemsetAsync(h->dMask[0] + idx, 1, 1, h->stream));
+    }
+    const bool surv = h->m.recursion == SDPB_REC_SURVIVAL;
+    for (int t = 1; t < T; t++) {
+        switch (h->m.cost_kind) {
+        case SDPB_COST_BACKORDER: launch_reach<SDPB_COST_BACKORDER, false>(h, t); break;
+        case SDPB_COST_CASH_DEPOSIT:
+            if (surv) launch_reach<SDPB_COST_CASH_DEPOSIT, true>(h, t);
+            else launch_reach<SDPB_COST_CASH_DEPOSIT, false>(h, t);
+            break;
+        case SDPB_COST_CASH_OVERDRAFT:
+            if (surv) launch_reach<SDPB_COST_CASH_OVERDRAFT, true>(h, t);
+            else launch_reach<SDPB_COST_CASH_OVERDRAFT, false>(h, t);
+            break;
+        case SDPB_COST_CASH_XR: launch_reach<SDPB_COST_CASH_XR, false>(h, t); break;
+        }
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    h->reached = true;
+    return SDPB_OK;
+}
+
+int sdpb_opt_table(sdpb_handle* h, double* rows, size_t* nrows) {
+    if (!h || !nrows) return SDPB_ERR_ARG;
+    if (!h->reached) { h->err = "call sdpb_reach first"; return SDPB_ERR_STATE; }
+    for (int t = 0; t < h->m.T; t++)
+        if (!h->solved[t]) { h->err = "not solved"; return SDPB_ERR_STATE; }
+    CU(cudaSetDevice(h->device));
+    const size_t cap = *nrows;
+    const int w = h->ndim + 2;
+    size_t count = 0;
+    std::vector<unsigned char> mask((size_t)h->S);
+    std::vector<int> hq;
+    if (rows) hq.resize((size_t)h->S);
+    for (int t = 0; t < h->m.T; t++) {
+        CU(cudaMemcpy(mask.data(), h->dMask[t], (size_t)h->S, cudaMemcpyDeviceToHost));
+        if (rows) CU(cudaMemcpy(hq.data(), h->dQ[t], (size_t)h->S * sizeof(int), cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < h->S; i++) {
+            if (!mask[i]) continue;
+            if (rows && count < cap) {
+                double* r = rows + count * w;
+                r[0] = t + 1;
+                state_of_index(h, i, r + 1, nullptr);
+                r[w - 1] = q_of_index(h, i, hq[i]);
+            }
+            count++;
+        }
+    }
+    *nrows = count;
+    return SDPB_OK;
+}
+
+int sdpb_eval_triples(sdpb_handle* h, int period, const double* states, const int32_t* action_idx,
+                      const double* demand, int n, double* c, double* next_states, int32_t* n_actions) {
+    if (!h || !states || !action_idx || !demand || n < 1) return SDPB_ERR_ARG;
+    if (period < 1 || period > h->m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
+    CU(cudaSetDevice(h->device));
+    std::vector<long long> sidx(n), hnext(n);
+    std::vector<int> demi(n), hna(n);
+    std::vector<double> hc(n);
+    for (int i = 0; i < n; i++) {
+        sidx[i] = index_of_state(h, states + (size_t)i * h->ndim);
+        if (sidx[i] < 0) { h->err = "state is not a grid point"; return SDPB_ERR_UNSOLVED; }
+        double f = demand[i] / h->m.step;
+        if (!is_int(f)) { h->err = "demand is not a multiple of step"; return SDPB_ERR_OFFGRID; }
+        demi[i] = (int)f;
+        if (action_idx[i] < 0 || action_idx[i] > h->m.max_order_idx) { h->err = "action index out of range"; return SDPB_ERR_ARG; }
+    }
+    long long *dS = nullptr, *dN = nullptr;
+    int *dA = nullptr, *dDi = nullptr, *dNa = nullptr;
+    double *dD = nullptr, *dC = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto al = [&](void** p, size_t b) { if (e == cudaSuccess) e = cudaMalloc(p, b); };
+    al((void**)&dS, n * 8); al((void**)&dN, n * 8); al((void**)&dA, n * 4); al((void**)&dDi, n * 4);
+    al((void**)&dNa, n * 4); al((void**)&dD, n * 8); al((void**)&dC, n * 8);
+    auto cp = [&](void* d, const void* s, size_t b, cudaMemcpyKind k) { if (e == cudaSuccess) e = cudaMemcpyAsync(d, s, b, k, h->stream); };
+    cp(dS, sidx.data(), n * 8, cudaMemcpyHostToDevice);
+    cp(dA, action_idx, n * 4, cudaMemcpyHostToDevice);
+    cp(dDi, demi.data(), n * 4, cudaMemcpyHostToDevice);
+    cp(dD, demand, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const int blocks = (n + 127) / 128;
+        switch (h->m.cost_kind) {
+        case SDPB_COST_BACKORDER: eval_triples<SDPB_COST_BACKORDER><<<blocks, 128, 0, h->stream>>>(h->dm, period, n, dS, dA, dD, dDi, dC, dN, dNa); break;
+        case SDPB_COST_CASH_DEPOSIT: eval_triples<SDPB_COST_CASH_DEPOSIT><<<blocks, 128, 0, h->stream>>>(h->dm, period, n, dS, dA, dD, dDi, dC, dN, dNa); break;
+        case SDPB_COST_CASH_OVERDRAFT: eval_triples<SDPB_COST_CASH_OVERDRAFT><<<blocks, 128, 0, h->stream>>>(h->dm, period, n, dS, dA, dD, dDi, dC, dN, dNa); break;
+        case SDPB_COST_CASH_XR: eval_triples<SDPB_COST_CASH_XR><<<blocks, 128, 0, h->stream>>>(h->dm, period, n, dS, dA, dD, dDi, dC, dN, dNa); break;
+        }
+        e = cudaGetLastError();
+    }
+    cp(hc.data(), dC, n * 8, cudaMemcpyDeviceToHost);
+    cp(hnext.data(), dN, n * 8, cudaMemcpyDeviceToHost);
+    cp(hna.data(), dNa, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dS); cudaFree(dN); cudaFree(dA); cudaFree(dDi); cudaFree(dNa); cudaFree(dD); cudaFree(dC);
+    if (e != cudaSuccess) { h->err = std::string("sdpb_eval_triples: ") + cudaGetErrorString(e); return SDPB_ERR_CUDA; }
+    for (int i = 0; i < n; i++) {
+        if (c) c[i] = hc[i];
+        if (next_states) state_of_index(h, hnext[i], next_states + (size_t)i * h->ndim, nullptr);
+        if (n_actions) n_actions[i] = hna[i];
+    }
+    return SDPB_OK;
+}
+
+int sdpb_stats_get(const sdpb_handle* h, sdpb_stats* s) {
+    if (!h || !s) return SDPB_ERR_ARG;
+    *s = h->stats;
+    return SDPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+"""Host-side mirror of the reference's pmf-table builder.
+
+Follows /root/reference/src/sdp/inventory/GetPmf.java:82-134 (`getpmf()`): truncated, renormalised
+demand tables `pmf[t][j] = (d_j, p_j)`.  The reference builds them with SSJ 3.3.0 probability
+classes (pom.xml:25-29), which are not available here; scipy.stats stands in for `prob`, `cdf` and
+`inverseF`, so tables agree with SSJ to rounding (~1e-15 relative), not bit for bit.  In a Java
+deployment SSJ keeps producing the table and only the table crosses the C-ABI, so solver parity is
+defined at the table boundary.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+from scipy import stats
+
+
+class Distribution:
+    discrete_int = False
+
+    def cdf(self, x):
+        return float(self._d.cdf(x))
+
+    def inverseF(self, u):
+        return float(self._d.ppf(u))
+
+
+class PoissonDist(Distribution):
+    """umontreal.ssj.probdist.PoissonDist(lambda)."""
+    discrete_int = True
+
+    def __init__(self, mean):
+        self.mean = float(mean)
+        self._d = stats.poisson(self.mean)
+
+    def prob(self, j):
+        return float(self._d.pmf(j))
+
+
+class NormalDist(Distribution):
+    """umontreal.ssj.probdist.NormalDist(mu, sigma)."""
+
+    def __init__(self, mu, sigma):
+        self._d = stats.norm(loc=mu, scale=sigma)
+
+
+class GammaDist(Distribution):
+    """umontreal.ssj.probdist.GammaDist(alpha, lambda): shape alpha, rate lambda."""
+
+    def __init__(self, alpha, lam):
+        self._d = stats.gamma(a=alpha, scale=1.0 / lam)
+
+
+class UniformIntDist(Distribution):
+    """umontreal.ssj.probdist.UniformIntDist(i, j)."""
+    discrete_int = True
+
+    def __init__(self, i, j):
+        self.i, self.j = int(i), int(j)
+        self._d = stats.randint(self.i, self.j + 1)
+
+    def prob(self, x):
+        return 1.0 / (self.j - self.i + 1) if self.i <= x <= self.j else 0.0
+
+
+class DiscreteDistribution(Distribution):
+    """umontreal.ssj.probdist.DiscreteDistribution(values, probs, n): goes through the
+    cdf-difference branch of GetPmf (GetPmf.java:120-129), giving tables with zero-probability
+    support points."""
+
+    def __init__(self, values, probs, n=None):
+        order = np.argsort(values)
+        self.values = np.asarray(values, dtype=float)[order]
+        self.probs = np.asarray(probs, dtype=float)[order]
+
+    def cdf(self, x):
+        return float(self.probs[self.values <= x].sum())
+
+    def inverseF(self, u):
+        c = np.cumsum(self.probs)
+        k = int(np.searchsorted(c, u, side="left"))
+        return float(self.values[min(k, len(self.values) - 1)])
+
+
+class GetPmf:
+    """`new GetPmf(distributions, truncationQuantile, stepSize).getpmf()` (GetPmf.java:35-41,82-134)."""
+
+    def __init__(self, distributions, truncationQuantile, stepSize):
+        self.distributions = list(distributions)
+        self.truncationQuantile = float(truncationQuantile)
+        self.stepSize = float(stepSize)
+
+    def getpmf(self):
+        dists, q, step = self.distributions, self.truncationQuantile, self.stepSize
+        T = len(dists)
+        first = dists[0]
+        if isinstance(first, UniformIntDist):  # GetPmf.java:97-111 (uses distributions[0] for every period)
+            rows = []
+            for _ in range(T):
+                rows.append(np.array([[j, first.prob(j)] for j in range(first.i, first.j + 1)], dtype=float))
+            return rows
+        rows = []
+        for i in range(T):
+            lb = float(int(dists[i].inverseF(1 - q)))
+            if first.discrete_int:
+                lb = 0.0
+            ub = float(int(dists[i].inverseF(q)))
+            n = int((ub - lb + 1) / step)
+            row = np.zeros((n, 2))
+            for j in range(n):
+                row[j, 0] = lb + j * step
+                if first.discrete_int:
+                    psum = dists[i].cdf(ub) - dists[i].cdf(lb - 1)
+                    row[j, 1] = dists[i].prob(j) / psum
+                else:
+                    psum = dists[i].cdf(ub + 0.5 * step) - dists[i].cdf(lb - 0.5 * step)
+                    row[j, 1] = (dists[i].cdf(row[j, 0] + 0.5 * step) - dists[i].cdf(row[j, 0] - 0.5 * step)) / psum
+            rows.append(row)
+        return rows
+
+
+def poisson_pmf(means, truncationQuantile=0.9999, stepSize=1.0):
+    """Shorthand used by the drivers: Poisson demand per period, truncated at the quantile."""
+    return GetPmf([PoissonDist(m) for m in means], truncationQuantile, stepSize).getpmf()
+
+
+def clsp_inline_pmf(means, truncationQuantile=0.99999, stepSize=1.0):
+    """The pmf CLSP.main builds inline (src/capacitated/CLSP.java:218-247): supports are
+    inverseF(1-q)..inverseF(q) without the (int) cast or the LB=0 override.  PoissonDist is not an
+    instance of SSJ's DiscreteDistribution (it extends DiscreteDistributionInt), so the else-branch
+    (cdf differences) is the one that runs."""
+    rows = []
+    for m in means:
+        d = PoissonDist(m)
+        lb, ub = d.inverseF(1 - truncationQuantile), d.inverseF(truncationQuantile)
+        n = int((ub - lb + 1) / stepSize)
+        row = np.zeros((n, 2))
+        psum = d.cdf(ub + 0.5 * stepSize) - d.cdf(lb - 0.5 * stepSize)
+        for j in range(n):
+            row[j, 0] = lb + j * stepSize
+            row[j, 1] = (d.cdf(row[j, 0] + 0.5 * stepSize) - d.cdf(row[j, 0] - 0.5 * stepSize)) / psum
+        rows.append(row)
+    return rows

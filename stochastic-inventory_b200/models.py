@@ -1,0 +1,228 @@
+"""Model descriptors: the reference drivers' lambdas (A, f, c) lowered to `sdpb_model` parameters.
+
+Each factory below names the reference driver whose `getFeasibleAction`, `stateTransition` and
+`immediateValue` lambdas it stands for, with that driver's constants as defaults
+(paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _abi as A
+
+
+@dataclass
+class ModelSpec:
+    cost_kind: int
+    pmf: Sequence[np.ndarray]            # per period: array [D_t, 2] of (demand, prob) as GetPmf returns
+    inv_min: float
+    inv_max: float
+    max_order_idx: int
+    direction: int = A.MIN
+    recursion: int = A.REC_EXPECT
+    lead_time: int = 0
+    flags: int = A.F_CLAMP_INV
+    gamma: float = 1.0
+    step: float = 1.0
+    cash_min: float = 0.0
+    cash_max: float = 0.0
+    quantiser: int = A.Q_LONGDIV
+    q_mul: float = 1.0
+    q_div: float = 1.0
+    fixed_cost: float = 0.0
+    vari_cost: float = 0.0
+    hold_cost: float = 0.0
+    penalty_cost: float = 0.0
+    price: float = 0.0
+    salvage: float = 0.0
+    deposit_rate: float = 0.0
+    overhead_rate: float = 0.0
+    overhead: float = 0.0
+    r0: float = 0.0
+    r2: float = 0.0
+    r3: float = 0.0
+    od_limit: float = 0.0
+    interest_free: float = 0.0
+    price_t: Optional[Sequence[float]] = None
+    vari_cost_t: Optional[Sequence[float]] = None
+    overhead_t: Optional[Sequence[float]] = None
+    reserve_t: Optional[Sequence[float]] = None
+    reserve2: float = 0.0
+    name: str = ""
+
+    @property
+    def T(self):
+        return len(self.pmf)
+
+    @property
+    def has_cash(self):
+        return self.cost_kind != A.COST_BACKORDER
+
+    @property
+    def ndim(self):
+        return 1 + (1 if self.has_cash else 0) + self.lead_time
+
+    def to_struct(self) -> A.SdpbModel:
+        """Build the C struct; the arrays it points to are kept alive on the struct object."""
+        m = A.SdpbModel()
+        m.struct_size = C.sizeof(A.SdpbModel)
+        for f in ("cost_kind", "recursion", "direction", "lead_time", "flags", "max_order_idx", "gamma",
+                  "inv_min", "inv_max", "step", "cash_min", "cash_max", "quantiser", "q_mul", "q_div",
+                  "fixed_cost", "vari_cost", "hold_cost", "penalty_cost", "price", "salvage",
+                  "deposit_rate", "overhead_rate", "overhead", "r0", "r2", "r3", "od_limit",
+                  "interest_free", "reserve2"):
+            setattr(m, f, getattr(self, f))
+        m.T = self.T
+        lens = np.ascontiguousarray([len(r) for r in self.pmf], dtype=np.int32)
+        d = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.float64)[:, 0] for r in self.pmf]))
+        p = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.float64)[:, 1] for r in self.pmf]))
+        keep = [lens, d, p]
+        m.pmf_len = lens.ctypes.data_as(C.POINTER(C.c_int32))
+        m.pmf_d = d.ctypes.data_as(C.POINTER(C.c_double))
+        m.pmf_p = p.ctypes.data_as(C.POINTER(C.c_double))
+        for f in ("price_t", "vari_cost_t", "overhead_t", "reserve_t"):
+            v = getattr(self, f)
+            if v is not None:
+                arr = np.ascontiguousarray(v, dtype=np.float64)
+                if arr.shape != (self.T,):
+                    raise ValueError(f"{f} must have T={self.T} entries")
+                keep.append(arr)
+                setattr(m, f, arr.ctypes.data_as(C.POINTER(C.c_double)))
+        m._keep = keep  # the struct owns its arrays
+        return m
+
+    def evals_dense(self) -> float:
+        """sum_t sum_s |A_t(s)| * D_t on the dense grid for state-independent action sets."""
+        n_states = self.n_states()
+        tot = 0.0
+        for t, row in enumerate(self.pmf):
+            nA = self.max_order_idx + 1
+            if (self.flags & A.F_NO_ORDER_LAST) and t == self.T - 1:
+                nA = 1
+            tot += n_states * nA * len(row)
+        return tot
+
+    def n_states(self) -> int:
+        n = int(round((self.inv_max - self.inv_min) / self.step)) + 1
+        n *= (self.max_order_idx + 1) ** self.lead_time
+        return n  # cash axis excluded (the library reports the exact figure: sdpb_grid_info)
+
+
+# ---------------------------------------------------------------------------------------------
+def inventory_model(pmf, fixed_cost=100.0, vari_cost=0.0, hold_cost=1.0, penalty_cost=10.0,
+                    max_order=500, inv_min=-500.0, inv_max=500.0, step=1.0, direction=A.MIN,
+                    gy_mode=False, name="inventory") -> ModelSpec:
+    """Single-item / capacitated stochastic lot sizing.
+    Lambdas: src/capacitated/CLSPTesting.java:78-106 (same in CLSP.java:251-272,
+    CLSPforDraw.java:73-103, fitss/LevelFitsS.java:74-102); G(y) pass CLSPforDraw.java:147-170.
+    Engine: src/sdp/inventory/Recursion.java:89-163."""
+    flags = A.F_CLAMP_INV | (A.F_GY_MODE if gy_mode else 0)
+    return ModelSpec(cost_kind=A.COST_BACKORDER, pmf=pmf, inv_min=inv_min, inv_max=inv_max,
+                     max_order_idx=int(max_order / step), direction=direction, flags=flags, step=step,
+                     fixed_cost=fixed_cost, vari_cost=vari_cost, hold_cost=hold_cost,
+                     penalty_cost=penalty_cost, name=name)
+
+
+def leadtime_model(pmf, fixed_cost=0.0, vari_cost=1.0, hold_cost=2.0, penalty_cost=10.0, max_order=100,
+                   inv_min=-150.0, inv_max=300.0, step=1.0, lead_time=1, clamp=False,
+                   name="leadtime") -> ModelSpec:
+    """Lead-time inventory model.  Lambdas: src/leadtime/Leadtime.java:50-81 (lead time 1, the
+    transition is NOT clamped there, :65-66).  lead_time=2 with clamp=True is the synthetic C4
+    extension.  Engine: src/sdp/inventory/LeadtimeRecursion.java:47-75 (MIN only)."""
+    return ModelSpec(cost_kind=A.COST_BACKORDER, pmf=pmf, inv_min=inv_min, inv_max=inv_max,
+                     max_order_idx=int(max_order / step), direction=A.MIN, lead_time=lead_time,
+                     flags=(A.F_CLAMP_INV if clamp else 0), step=step, fixed_cost=fixed_cost,
+                     vari_cost=vari_cost, hold_cost=hold_cost, penalty_cost=penalty_cost, name=name)
+
+
+def cash_constraint_model(pmf, price=10.0, vari_cost=1.0, fixed_cost=0.0, hold_cost=0.0, salvage=0.5,
+                          overhead=0.0, overhead_rate=0.0, deposit_rate=0.0, penalty_cost=0.0,
+                          max_order=100, inv_min=0.0, inv_max=500.0, cash_min=0.0, cash_max=2000.0,
+                          quantiser=A.Q_DIV, q_mul=10.0, q_div=10.0, gamma=1.0, direction=A.MAX,
+                          recursion=A.REC_EXPECT, name="cash_constraint") -> ModelSpec:
+    """Cash-constrained inventory.  Lambdas: src/cash/singleItem/CashConstraint.java:95-133
+    (quantiser round(w*10)/10.0 at :131; CashConstraintTesting.java:146 uses round(w*1)/1).
+    Engine: src/sdp/cash/CashRecursion.java:79-140 (MAX, discount factor)."""
+    T = len(pmf)
+    return ModelSpec(cost_kind=A.COST_CASH_DEPOSIT, pmf=pmf, inv_min=inv_min, inv_max=inv_max,
+                     max_order_idx=int(max_order), direction=direction, recursion=recursion,
+                     flags=A.F_CLAMP_INV | A.F_LOST_SALES | A.F_CASH_LIMITED_ACTIONS, gamma=gamma,
+                     cash_min=cash_min, cash_max=cash_max, quantiser=quantiser, q_mul=q_mul, q_div=q_div,
+                     fixed_cost=fixed_cost, vari_cost=vari_cost, hold_cost=hold_cost,
+                     penalty_cost=penalty_cost, price=price, salvage=salvage, deposit_rate=deposit_rate,
+                     overhead_rate=overhead_rate, overhead=overhead,
+                     reserve_t=[overhead] * T, reserve2=fixed_cost, name=name)
+
+
+def cash_overdraft_model(pmf, price=10.0, vari_cost=1.0, fixed_cost=0.0, salvage=0.0, overhead_t=None,
+                         r0=0.0, r2=0.1, r3=2.0, od_limit=1000.0, interest_free=0.0, max_order=100,
+                         inv_min=0.0, inv_max=100.0, cash_min=-200.0, cash_max=800.0,
+                         quantiser=A.Q_LONGDIV, q_mul=10.0, q_div=10.0, gamma=1.0,
+                         name="cash_overdraft") -> ModelSpec:
+    """Overdraft model.  Lambdas: src/cash/overdraft/CashOverdraft.java:72-118 (four-branch interest
+    :88-95; quantiser round(w*10)/10 with LONG division :116).  Engine: CashRecursion (MAX)."""
+    T = len(pmf)
+    if overhead_t is None:
+        overhead_t = [100.0] * T
+    return ModelSpec(cost_kind=A.COST_CASH_OVERDRAFT, pmf=pmf, inv_min=inv_min, inv_max=inv_max,
+                     max_order_idx=int(max_order), direction=A.MAX,
+                     flags=A.F_CLAMP_INV | A.F_LOST_SALES, gamma=gamma, cash_min=cash_min,
+                     cash_max=cash_max, quantiser=quantiser, q_mul=q_mul, q_div=q_div,
+                     fixed_cost=fixed_cost, vari_cost=vari_cost, price=price, salvage=salvage,
+                     overhead_t=list(overhead_t), r0=r0, r2=r2, r3=r3, od_limit=od_limit,
+                     interest_free=interest_free, name=name)
+
+
+def cash_leadtime_model(pmf, price=5.0, vari_cost=1.0, salvage=0.5, overhead_t=None, r0=0.0, r2=0.1,
+                        r3=2.0, od_limit=500.0, interest_free=0.0, max_order=30, inv_min=0.0,
+                        inv_max=60.0, cash_min=-200.0, cash_max=300.0, quantiser=A.Q_DIV, q_mul=100.0,
+                        q_div=100.0, name="cash_leadtime") -> ModelSpec:
+    """Cash + lead time 1.  Lambdas: src/cash/overdraft/SingleProductLeadtime.java:72-119 (no order
+    in the last period :74-75; quantiser round(w*100)/100.0 :117).
+    Engine: src/sdp/cash/CashLeadtimeRecursion.java:48-79 (MAX, no discount)."""
+    T = len(pmf)
+    if overhead_t is None:
+        overhead_t = [0.0] * T
+    return ModelSpec(cost_kind=A.COST_CASH_OVERDRAFT, pmf=pmf, inv_min=inv_min, inv_max=inv_max,
+                     max_order_idx=int(max_order), direction=A.MAX, lead_time=1,
+                     flags=A.F_CLAMP_INV | A.F_LOST_SALES | A.F_NO_ORDER_LAST, cash_min=cash_min,
+                     cash_max=cash_max, quantiser=quantiser, q_mul=q_mul, q_div=q_div,
+                     vari_cost=vari_cost, price=price, salvage=salvage, overhead_t=list(overhead_t),
+                     r0=r0, r2=r2, r3=r3, od_limit=od_limit, interest_free=interest_free, name=name)
+
+
+def cash_survival_model(pmf, price_t=None, vari_cost_t=None, overhead_t=None, salvage=0.5, hold_cost=0.0,
+                        deposit_rate=0.0, fixed_cost=0.0, max_order=1000, inv_min=0.0, inv_max=1000.0,
+                        cash_min=-500.0, cash_max=5000.0, name="cash_survival") -> ModelSpec:
+    """Survival-probability model.  Lambdas: src/cash/risk/cashSurvival.java:102-147 (per-period
+    price/cost arrays, quantiser round(w*1)/1 :140).  Engine: src/sdp/cash/RiskRecursion.java:64-108."""
+    T = len(pmf)
+    price_t = [4.0] * T if price_t is None else list(price_t)
+    vari_cost_t = [1.0] * T if vari_cost_t is None else list(vari_cost_t)
+    overhead_t = [100.0] * T if overhead_t is None else list(overhead_t)
+    return ModelSpec(cost_kind=A.COST_CASH_DEPOSIT, pmf=pmf, inv_min=inv_min, inv_max=inv_max,
+                     max_order_idx=int(max_order), direction=A.MAX, recursion=A.REC_SURVIVAL,
+                     flags=A.F_CLAMP_INV | A.F_LOST_SALES | A.F_CASH_LIMITED_ACTIONS,
+                     cash_min=cash_min, cash_max=cash_max, quantiser=A.Q_LONGDIV, q_mul=1.0, q_div=1.0,
+                     fixed_cost=fixed_cost, hold_cost=hold_cost, salvage=salvage,
+                     deposit_rate=deposit_rate, price_t=price_t, vari_cost_t=vari_cost_t,
+                     overhead_t=overhead_t, name=name)
+
+
+def cash_xr_model(pmf, price=4.0, vari_cost=2.0, fixed_cost=0.0, hold_cost=0.0, salvage=1.0,
+                  overhead=0.0, overhead_rate=0.0, deposit_rate=0.0, max_order=200, inv_min=0.0,
+                  inv_max=500.0, cash_min=-100.0, cash_max=2000.0, gamma=1.0, name="cash_xr") -> ModelSpec:
+    """(x, R) formulation.  Lambdas: src/cash/singleItem/CashConstraintXR.java:71-110.
+    Engine: src/sdp/cash/CashRecursionXR.java:79-125.  `max_order` caps the number of order-up-to
+    levels per state on the dense grid (the reference has no cap; choose it >= R_max / v)."""
+    return ModelSpec(cost_kind=A.COST_CASH_XR, pmf=pmf, inv_min=inv_min, inv_max=inv_max,
+                     max_order_idx=int(max_order), direction=A.MAX,
+                     flags=A.F_CLAMP_INV | A.F_LOST_SALES, gamma=gamma, cash_min=cash_min,
+                     cash_max=cash_max, quantiser=A.Q_LONGDIV, q_mul=1.0, q_div=1.0,
+                     fixed_cost=fixed_cost, vari_cost=vari_cost, hold_cost=hold_cost, price=price,
+                     salvage=salvage, deposit_rate=deposit_rate, overhead_rate=overhead_rate,
+                     overhead=overhead, name=name)

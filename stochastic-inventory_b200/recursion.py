@@ -1,0 +1,286 @@
+"""Host-side mirror of the reference's recursion engines, over libsdpb200.so.
+
+Same class and member names as the Java classes (paths relative to /root/reference):
+
+    State / Recursion                       src/sdp/inventory/State.java:12-71, Recursion.java:33-186
+    LeadtimeState / LeadtimeRecursion       src/sdp/inventory/LeadtimeState.java:10-20, LeadtimeRecursion.java:20-102
+    CashState / CashRecursion               src/sdp/cash/CashState.java:12-23, CashRecursion.java:24-220
+    CashLeadtimeState / CashLeadtimeRecursion  src/sdp/cash/CashLeadtimeState.java:11-21, CashLeadtimeRecursion.java:20-105
+    RiskState / RiskRecursion               src/sdp/cash/RiskState.java:12-26, RiskRecursion.java:24-135
+    CashStateXR / CashRecursionXR           src/sdp/cash/CashStateXR.java:13-31, CashRecursionXR.java:24-150
+
+The Java constructors take three lambdas (A, f, c).  A GPU cannot call them, so the constructors
+here take a `ModelSpec` descriptor in their place (models.py lowers every in-scope reference driver
+to one); the lambdas may still be passed as Python callables, in which case the descriptor is
+spot-checked against them on random (state, action, demand) triples before anything is solved.
+
+Behaviour kept from the reference: `getExpectedValue(state)` may be called for any state at any
+time (the whole grid is solved on the first call — the GPU analogue of the lazy memoised solve);
+`getAction(state)` on a state that was never solved raises (Java: NullPointerException from
+unboxing, Recursion.java:165-167); `getOptTable()` returns only the states the top-down recursion
+would have visited from the states queried so far, sorted by (period, state).
+"""
+from __future__ import annotations
+
+import random
+from enum import Enum
+
+import numpy as np
+
+from . import _abi as A
+from .models import ModelSpec
+from .solver import Solver
+
+
+class OptDirection(Enum):
+    MIN = 0
+    MAX = 1
+
+
+# ---- states -------------------------------------------------------------------------------
+class State:
+    def __init__(self, period, iniInventory):
+        self.period = int(period)
+        self.initialInventory = float(iniInventory)
+
+    def getPeriod(self):
+        return self.period
+
+    def getIniInventory(self):
+        return self.initialInventory
+
+    def _vec(self):
+        return (self.initialInventory,)
+
+    def _key(self):
+        return (self.period,) + self._vec()
+
+    def __eq__(self, o):
+        return isinstance(o, State) and self._key() == o._key()
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __repr__(self):
+        return f"period = {self.period}, initialInventory = {self.initialInventory}"
+
+
+class LeadtimeState(State):
+    def __init__(self, period, iniInventory, preQ):
+        super().__init__(period, iniInventory)
+        self.preQ = float(preQ)
+
+    def getPreQ(self):
+        return self.preQ
+
+    def _vec(self):
+        return (self.initialInventory, self.preQ)
+
+
+class CashState(State):
+    def __init__(self, period, iniInventory, iniCash):
+        super().__init__(period, iniInventory)
+        self.iniCash = float(iniCash)
+
+    def getIniCash(self):
+        return self.iniCash
+
+    def _vec(self):
+        return (self.initialInventory, self.iniCash)
+
+
+class CashLeadtimeState(CashState):
+    def __init__(self, period, iniInventory, iniCash, preQ):
+        super().__init__(period, iniInventory, iniCash)
+        self.preQ = float(preQ)
+
+    def getPreQ(self):
+        return self.preQ
+
+    def _vec(self):
+        return (self.initialInventory, self.iniCash, self.preQ)
+
+
+class RiskState(CashState):
+    def __init__(self, period, iniInventory, iniCash, bankruptBefore=False):
+        super().__init__(period, iniInventory, iniCash)
+        self.bankruptBefore = False  # the reference constructor ignores its argument (RiskState.java:15-18)
+
+    def getBankruptBefore(self):
+        return self.bankruptBefore
+
+
+class CashStateXR(State):
+    def __init__(self, period, iniInventory, R, variCost):
+        super().__init__(period, iniInventory)
+        self.iniR = float(R)
+        self.unitVariCost = float(variCost)
+
+    def getIniR(self):
+        return self.iniR
+
+    def _vec(self):
+        return (self.initialInventory, self.iniR)
+
+
+# ---- engines ------------------------------------------------------------------------------
+class _Engine:
+    state_cls = State
+    _kinds = (A.COST_BACKORDER,)
+    _lead = 0
+
+    def __init__(self, spec: ModelSpec, getFeasibleAction=None, stateTransition=None, immediateValue=None,
+                 device: int = -1, kernel: int = A.KERNEL_AUTO, dedup: bool = False, spot_checks: int = 200):
+        if spec.cost_kind not in self._kinds or spec.lead_time != self._lead:
+            raise ValueError(f"{type(self).__name__} does not take this descriptor "
+                             f"(cost_kind={spec.cost_kind}, lead_time={spec.lead_time})")
+        self.spec = spec
+        self.pmf = spec.pmf
+        self.getFeasibleActions = getFeasibleAction
+        self.stateTransition = stateTransition
+        self.immediateValue = immediateValue
+        self._solver = Solver(spec, device=device, kernel=kernel, dedup=dedup)
+        self._solved = False
+        self._queried = []  # period-1 states asked for so far: roots of the top-down visit set
+        self._tree_map = False
+        if immediateValue is not None or stateTransition is not None or getFeasibleAction is not None:
+            self._spot_check(spot_checks)
+
+    # -- the reference's accessors --
+    def getStateTransitionFunction(self):
+        return self.stateTransition
+
+    def getImmediateValueFunction(self):
+        return self.immediateValue
+
+    def setTreeMapCacheAction(self):
+        """Recursion.java:80-86: swaps the action map for a TreeMap with the same key order; a no-op
+        here because tables are always produced in (period, state) order."""
+        self._tree_map = True
+
+    def _ensure_solved(self):
+        if not self._solved:
+            self._solver.solve()
+            self._solved = True
+
+    def _value(self, state):
+        self._ensure_solved()
+        v, q = self._solver.value(state.getPeriod(), [state._vec()])
+        return float(v[0]), float(q[0])
+
+    def getExpectedValue(self, state):
+        val, _ = self._value(state)
+        if state.getPeriod() == 1 and state._vec() not in self._queried:
+            self._queried.append(state._vec())
+        return val
+
+    def getAction(self, state):
+        if not self._solved:
+            # Java: cacheActions.get(state) is null -> NullPointerException on unboxing
+            raise KeyError("getAction on a state that was never solved (Recursion.java:165-167)")
+        return self._value(state)[1]
+
+    def getOptTable(self):
+        """Rows [t, state dims..., Q*] for the visited states only (Recursion.java:177-186)."""
+        if not self._queried:
+            return np.empty((0, self._solver.ndim + 2))
+        self._ensure_solved()
+        self._solver.reach(self._queried)
+        return self._solver.opt_table()
+
+    def getCacheActions(self):
+        """Map state -> optimal action over the visited states (Recursion.java:169-171)."""
+        out = {}
+        for row in self.getOptTable():
+            out[self.state_cls(int(row[0]), *row[1:-1]) if self.state_cls is not CashStateXR
+                else CashStateXR(int(row[0]), row[1], row[2], self.spec.vari_cost)] = float(row[-1])
+        return out
+
+    def stats(self):
+        return self._solver.stats()
+
+    # -- descriptor <-> lambda validation --
+    def _spot_check(self, n):
+        """A descriptor/lambda mismatch would be silent, so compare them on random triples."""
+        from . import _spot
+        rng = random.Random(20261018)
+        for _ in range(n):
+            st, a, d = _spot.random_triple(self.spec, rng)
+            state = self._make_state(st)
+            c_desc, nxt_desc, nA = _spot.eval_descriptor(self.spec, st, a, d)
+            if self.immediateValue is not None:
+                c_user = float(self.immediateValue(state, a, d))
+                if c_user != c_desc:
+                    raise ValueError(f"descriptor and immediateValue lambda disagree at {state}, a={a}, d={d}: "
+                                     f"{c_desc!r} vs {c_user!r}")
+            if self.stateTransition is not None and st[0] < self.spec.T:
+                nxt = self.stateTransition(state, a, d)
+                if tuple(nxt._vec()) != tuple(nxt_desc):
+                    raise ValueError(f"descriptor and stateTransition lambda disagree at {state}, a={a}, d={d}: "
+                                     f"{nxt_desc} vs {nxt._vec()}")
+            if self.getFeasibleActions is not None:
+                if len(self.getFeasibleActions(state)) != nA:
+                    raise ValueError(f"descriptor and getFeasibleAction lambda disagree at {state}")
+
+    def _make_state(self, st):
+        t, vec = st[0], st[1:]
+        if self.state_cls is CashStateXR:
+            return CashStateXR(t, vec[0], vec[1], self.spec.vari_cost)
+        return self.state_cls(t, *vec)
+
+
+class Recursion(_Engine):
+    """new Recursion(OptDirection, pmf, A, f, c) -> Recursion(spec[, A, f, c]); Recursion.java:49-63."""
+    OptDirection = OptDirection
+    state_cls = State
+
+
+class LeadtimeRecursion(_Engine):
+    state_cls = LeadtimeState
+    _lead = 1
+
+
+class LeadtimeRecursion2(_Engine):
+    """Lead time 2 (state (x, q1, q2)): the synthetic C4 extension; not a reference class."""
+    _lead = 2
+
+    class state_cls(State):  # noqa: N801
+        def __init__(self, period, iniInventory, preQ, preQ2):
+            super().__init__(period, iniInventory)
+            self.preQ, self.preQ2 = float(preQ), float(preQ2)
+
+        def _vec(self):
+            return (self.initialInventory, self.preQ, self.preQ2)
+
+
+class CashRecursion(_Engine):
+    OptDirection = OptDirection
+    state_cls = CashState
+    _kinds = (A.COST_CASH_DEPOSIT, A.COST_CASH_OVERDRAFT)
+
+    def getSurvProb(self, state):
+        """CashRecursion.java:143-194: needs a descriptor built with recursion=REC_SURVIVAL."""
+        if self.spec.recursion != A.REC_SURVIVAL:
+            raise ValueError("build the descriptor with recursion=REC_SURVIVAL to use getSurvProb")
+        return self.getExpectedValue(state)
+
+
+class RiskRecursion(CashRecursion):
+    state_cls = RiskState
+
+    def __init__(self, spec, *a, **k):
+        if spec.recursion != A.REC_SURVIVAL:
+            raise ValueError("RiskRecursion takes a REC_SURVIVAL descriptor (RiskRecursion.java:64-108)")
+        super().__init__(spec, *a, **k)
+
+
+class CashLeadtimeRecursion(_Engine):
+    state_cls = CashLeadtimeState
+    _kinds = (A.COST_CASH_DEPOSIT, A.COST_CASH_OVERDRAFT)
+    _lead = 1
+
+
+class CashRecursionXR(_Engine):
+    OptDirection = OptDirection
+    state_cls = CashStateXR
+    _kinds = (A.COST_CASH_XR,)

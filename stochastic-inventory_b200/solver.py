@@ -1,0 +1,115 @@
+"""`Solver`: one sdpb_handle.  Thin, typed access to the C-ABI; all compute happens in
+libsdpb200.so on the GPU.  Nothing here can solve anything on the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+from .models import ModelSpec
+
+
+class Solver:
+    def __init__(self, spec: ModelSpec, device: int = -1, shard_rank: int = 0, shard_count: int = 1,
+                 kernel: int = A.KERNEL_AUTO, dedup: bool = False, stream: int | None = None):
+        self.lib = A.load()
+        self.spec = spec
+        self._model = spec.to_struct()
+        opt = A.SdpbOptions()
+        opt.struct_size = C.sizeof(A.SdpbOptions)
+        opt.device, opt.shard_rank, opt.shard_count = device, shard_rank, shard_count
+        opt.kernel, opt.dedup = kernel, 1 if dedup else 0
+        opt.stream = stream
+        h = C.c_void_p()
+        rc = self.lib.sdpb_create(C.byref(self._model), C.byref(opt), C.byref(h))
+        if rc != A.SDPB_OK:
+            raise A.SdpbError(rc, self.lib.sdpb_last_error(None).decode())
+        self.h = h
+        g = A.SdpbGrid()
+        self._check(self.lib.sdpb_grid_info(self.h, C.byref(g)))
+        self.grid = g
+        self.ndim = g.ndim
+        self.n_states = g.n_states
+        self.T = g.T
+
+    def _check(self, rc):
+        if rc != A.SDPB_OK:
+            raise A.SdpbError(rc, self.lib.sdpb_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sdpb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- solve ----
+    def solve(self):
+        self._check(self.lib.sdpb_solve(self.h))
+        return self
+
+    def solve_period_async(self, period: int):
+        self._check(self.lib.sdpb_solve_period_async(self.h, period))
+
+    def sync(self):
+        self._check(self.lib.sdpb_sync(self.h))
+
+    # ---- results ----
+    def value(self, period: int, states):
+        """(V, Q) for an array of API-order states [n, ndim]."""
+        st = np.ascontiguousarray(np.atleast_2d(np.asarray(states, dtype=np.float64)))
+        if st.shape[1] != self.ndim:
+            raise ValueError(f"states must have {self.ndim} columns")
+        n = st.shape[0]
+        v = np.empty(n)
+        q = np.empty(n)
+        dp = C.POINTER(C.c_double)
+        self._check(self.lib.sdpb_value(self.h, period, st.ctypes.data_as(dp), n,
+                                        v.ctypes.data_as(dp), q.ctypes.data_as(dp)))
+        return v, q
+
+    def period_tables(self, period: int, want_q: bool = True):
+        dp = C.POINTER(C.c_double)
+        V = np.empty(self.n_states)
+        Q = np.empty(self.n_states) if want_q else None
+        self._check(self.lib.sdpb_period_tables(self.h, period, V.ctypes.data_as(dp),
+                                                Q.ctypes.data_as(dp) if want_q else None))
+        return V, Q
+
+    def device_tables(self, period: int):
+        dv, dq = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.sdpb_device_tables(self.h, period, C.byref(dv), C.byref(dq)))
+        return dv.value, dq.value
+
+    def state_of_index(self, idx: int):
+        st = np.empty(self.ndim)
+        self._check(self.lib.sdpb_state_of_index(self.h, idx, st.ctypes.data_as(C.POINTER(C.c_double))))
+        return st
+
+    def reach(self, init_states):
+        st = np.ascontiguousarray(np.atleast_2d(np.asarray(init_states, dtype=np.float64)))
+        self._check(self.lib.sdpb_reach(self.h, st.ctypes.data_as(C.POINTER(C.c_double)), st.shape[0]))
+
+    def opt_table(self):
+        n = C.c_size_t(0)
+        self._check(self.lib.sdpb_opt_table(self.h, None, C.byref(n)))
+        rows = np.empty((n.value, self.ndim + 2))
+        self._check(self.lib.sdpb_opt_table(self.h, rows.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n)))
+        return rows
+
+    def stats(self):
+        s = A.SdpbStats()
+        self._check(self.lib.sdpb_stats_get(self.h, C.byref(s)))
+        return {"evals": s.evals, "solve_ms": s.solve_ms, "kernel_ms": s.kernel_ms,
+                "launches": s.launches, "kernel_used": s.kernel_used, "fp64_ops": s.fp64_ops}

@@ -1,0 +1,140 @@
+"""Small instances of every model family: sizes the CPU oracle solves in about a second."""
+from __future__ import annotations
+
+import numpy as np
+
+import sdpb200 as S
+from sdpb200 import abi as A
+
+
+def pmf(means, q=0.999):
+    return S.poisson_pmf(means, q)
+
+
+def two_point(T, lo, hi, p=0.5):
+    """a pmf with non-consecutive demand values {lo, hi}"""
+    return [np.array([[lo, p], [hi, 1 - p]], dtype=float) for _ in range(T)]
+
+
+def case_A_small():
+    return S.inventory_model(pmf([5, 8, 6]), fixed_cost=20, vari_cost=1, hold_cost=1, penalty_cost=5,
+                             max_order=15, inv_min=-30, inv_max=30, name="A_small"), [[0.0]]
+
+
+def case_A_max():
+    # Recursion supports MAX (Recursion.java:44-47,152-157); same lambdas, maximised
+    return S.inventory_model(pmf([3, 4]), fixed_cost=7, vari_cost=0.5, hold_cost=1.5, penalty_cost=4,
+                             max_order=9, inv_min=-12, inv_max=14, direction=A.MAX, name="A_max"), [[2.0]]
+
+
+def case_A_gy():
+    return S.inventory_model(pmf([9, 23, 13], 0.9999), fixed_cost=500, vari_cost=0, hold_cost=2,
+                             penalty_cost=10, max_order=30, inv_min=-80, inv_max=80, gy_mode=True,
+                             name="A_gy"), [[1.0]]
+
+
+def case_A_twopoint():
+    # non-consecutive demand support and exact ties between actions
+    return S.inventory_model(two_point(3, 4.0, 10.0), fixed_cost=0, vari_cost=0, hold_cost=1, penalty_cost=1,
+                             max_order=12, inv_min=-20, inv_max=20, name="A_twopoint"), [[0.0]]
+
+
+def case_A_halfstep():
+    p = [np.array([[0.0, 0.25], [0.5, 0.25], [1.0, 0.25], [1.5, 0.25]]) for _ in range(3)]
+    return S.inventory_model(p, fixed_cost=3, vari_cost=1, hold_cost=1, penalty_cost=9, max_order=4,
+                             inv_min=-6, inv_max=6, step=0.5, name="A_halfstep"), [[0.0]]
+
+
+def case_B1_ref():
+    # Leadtime.java:25-68 scaled down; unclamped, so the grid is the reachable hull
+    T, mean, maxq = 3, 4, 12
+    p = pmf([mean] * T)
+    dmax = max(r[-1, 0] for r in p)
+    return S.leadtime_model(p, fixed_cost=0, vari_cost=1, hold_cost=2, penalty_cost=10, max_order=maxq,
+                            inv_min=-T * dmax, inv_max=T * maxq, lead_time=1, clamp=False,
+                            name="B1_ref"), [[0.0, 0.0]]
+
+
+def case_B1_fixed():
+    return S.leadtime_model(pmf([4, 6, 5]), fixed_cost=15, vari_cost=1, hold_cost=2, penalty_cost=10,
+                            max_order=10, inv_min=-25, inv_max=40, lead_time=1, clamp=True,
+                            name="B1_fixed"), [[0.0, 0.0], [3.0, 2.0]]
+
+
+def case_B2_small():
+    return S.leadtime_model(pmf([3, 4, 3, 4]), fixed_cost=0, vari_cost=1, hold_cost=2, penalty_cost=10,
+                            max_order=7, inv_min=-15, inv_max=15, lead_time=2, clamp=True,
+                            name="B2_small"), [[0.0, 0.0, 0.0]]
+
+
+def case_C_small():
+    # CashConstraint.java:44-133 scaled down, 0.1 cash grid
+    return S.cash_constraint_model(pmf([5, 5, 5]), price=10, vari_cost=1, salvage=0.5, max_order=12,
+                                   inv_min=0, inv_max=25, cash_min=0, cash_max=120, name="C_small"), [[0.0, 10.0]]
+
+
+def case_C_rich():
+    # every optional term switched on: K, h, overhead, overhead rate, deposit rate, penalty, discount
+    return S.cash_constraint_model(pmf([4, 6, 5]), price=6, vari_cost=2, fixed_cost=3, hold_cost=0.5,
+                                   salvage=1.0, overhead=2, overhead_rate=0.125, deposit_rate=0.25,
+                                   penalty_cost=0.5, max_order=9, inv_min=0, inv_max=20, cash_min=-20,
+                                   cash_max=90, quantiser=A.Q_LONGDIV, q_mul=1.0, q_div=1.0, gamma=0.95,
+                                   name="C_rich"), [[0.0, 20.0], [2.0, 5.0]]
+
+
+def case_D_small():
+    return S.cash_overdraft_model(pmf([6, 6, 6]), price=10, vari_cost=1, overhead_t=[20, 20, 20],
+                                  od_limit=30, max_order=15, inv_min=0, inv_max=25, cash_min=-60,
+                                  cash_max=150, name="D_small"), [[0.0, 0.0]]
+
+
+def case_D_rich():
+    return S.cash_overdraft_model(pmf([5, 7]), price=8, vari_cost=2, fixed_cost=4, salvage=1,
+                                  overhead_t=[10, 15], r0=0.25, r2=0.125, r3=1.5, od_limit=20, interest_free=5,
+                                  max_order=10, inv_min=0, inv_max=18, cash_min=-50, cash_max=100,
+                                  quantiser=A.Q_DIV, q_mul=10.0, q_div=10.0, gamma=0.9,
+                                  name="D_rich"), [[0.0, 10.0]]
+
+
+def case_E_small():
+    # SingleProductLeadtime.java:28-119 scaled down; cash grid 0.5 instead of 0.01 to keep it small
+    return S.cash_leadtime_model(pmf([4, 4, 4]), price=5, vari_cost=1, salvage=0.5, od_limit=40, max_order=8,
+                                 inv_min=0, inv_max=16, cash_min=-40, cash_max=60, q_mul=2.0, q_div=2.0,
+                                 name="E_small"), [[0.0, 0.0, 0.0]]
+
+
+def case_F_small():
+    # cashSurvival.java:51-147 scaled down
+    T = 3
+    return S.cash_survival_model(pmf([5, 7, 6], 0.99), price_t=[4, 5, 4], vari_cost_t=[1, 1, 2],
+                                 overhead_t=[12, 10, 14], salvage=0.5, max_order=20, inv_min=0,
+                                 inv_max=30, cash_min=-30, cash_max=120, name="F_small"), [[0.0, 15.0]]
+
+
+def case_XR_small():
+    # CashConstraintXR.java:34-110 scaled down (integer-valued Poisson table instead of Gamma)
+    return S.cash_xr_model(pmf([4, 4, 4], 0.99), price=4, vari_cost=2, salvage=1, max_order=30, inv_min=0,
+                           inv_max=30, cash_min=-10, cash_max=90, name="XR_small"), [[0.0, 30.0]]
+
+
+ALL = [case_A_small, case_A_max, case_A_gy, case_A_twopoint, case_A_halfstep, case_B1_ref, case_B1_fixed,
+       case_B2_small, case_C_small, case_C_rich, case_D_small, case_D_rich, case_E_small, case_F_small,
+       case_XR_small]
+
+
+# ---- golden fixtures --------------------------------------------------------------------------
+import os
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN = ["A_small", "A_gy", "A_twopoint", "B1_ref", "B2_small", "C_rich", "D_rich", "E_small", "F_small",
+          "XR_small"]
+
+
+def load_golden(name):
+    """-> (spec with the pmf table stored in the fixture, init states, fixture dict)"""
+    spec, init = globals()["case_" + name]()
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    lens = g["pmf_len"]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    spec.pmf = [g["pmf"][off[i]:off[i + 1]] for i in range(len(lens))]
+    return spec, init, g

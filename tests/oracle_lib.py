@@ -1,0 +1,115 @@
+"""ctypes access to the CPU oracle (oracle/libsdp_oracle.so).  Test infrastructure only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "libsdp_oracle.so")
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    src = os.path.join(ORACLE_DIR, "sdp_oracle.cpp")
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        build()
+    lib = C.CDLL(ORACLE_SO)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
+    lib.oracle_grid.argtypes = [vp, C.POINTER(C.c_int64), ip]
+    lib.oracle_dense.argtypes = [vp, dp, dp, dp, C.POINTER(C.c_int64), C.c_int]
+    lib.oracle_topdown.argtypes = [vp, dp, C.c_int, dp, C.c_int64, dp, dp]
+    lib.oracle_topdown.restype = C.c_int64
+    lib.oracle_step_states.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int64), C.c_int, dp, dp]
+    lib.oracle_eval.argtypes = [vp, C.c_int, dp, C.c_double, C.c_double, dp, dp]
+    lib.oracle_index.argtypes = [vp, dp]
+    lib.oracle_index.restype = C.c_int64
+    lib.oracle_n_actions.argtypes = [vp, C.c_int, dp]
+    _lib = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def grid(spec):
+    lib = load()
+    m = spec.to_struct()
+    n, nd = C.c_int64(), C.c_int()
+    lib.oracle_grid(C.byref(m), C.byref(n), C.byref(nd))
+    return n.value, nd.value
+
+
+def dense(spec, threads=0):
+    """-> V[T,S], Q[T,S], evals, offgrid_count"""
+    lib = load()
+    m = spec.to_struct()
+    S, _ = grid(spec)
+    V = np.empty((spec.T, S))
+    Q = np.empty((spec.T, S))
+    ev, off = C.c_double(), C.c_int64()
+    lib.oracle_dense(C.byref(m), _dp(V), _dp(Q), C.byref(ev), C.byref(off), threads)
+    return V, Q, ev.value, off.value
+
+
+def topdown(spec, init_states):
+    """-> rows [n, ndim+3] = [t, state..., Q, V] sorted by the memo order; init values; evals"""
+    lib = load()
+    m = spec.to_struct()
+    st = np.ascontiguousarray(np.atleast_2d(np.asarray(init_states, dtype=np.float64)))
+    _, nd = grid(spec)
+    iv = np.empty(st.shape[0])
+    ev = C.c_double()
+    n = lib.oracle_topdown(C.byref(m), _dp(st), st.shape[0], None, 0, _dp(iv), C.byref(ev))
+    rows = np.empty((n, nd + 3))
+    lib.oracle_topdown(C.byref(m), _dp(st), st.shape[0], _dp(rows), n, _dp(iv), C.byref(ev))
+    return rows, iv, ev.value
+
+
+def step_states(spec, period, Vnext, idx):
+    """Recompute (V_t, Q_t) at flattened indices `idx` from the full V_{t+1} table."""
+    lib = load()
+    m = spec.to_struct()
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    v = np.empty(len(idx))
+    q = np.empty(len(idx))
+    vn = None if Vnext is None else _dp(np.ascontiguousarray(Vnext, dtype=np.float64))
+    lib.oracle_step_states(C.byref(m), period, vn, idx.ctypes.data_as(C.POINTER(C.c_int64)), len(idx),
+                           _dp(v), _dp(q))
+    return v, q
+
+
+def eval_triple(spec, period, state, action, demand):
+    lib = load()
+    m = spec.to_struct()
+    st = np.ascontiguousarray(state, dtype=np.float64)
+    c = C.c_double()
+    nxt = np.empty(len(st))
+    lib.oracle_eval(C.byref(m), period, _dp(st), float(action), float(demand), C.byref(c), _dp(nxt))
+    return c.value, nxt
+
+
+def index(spec, state):
+    lib = load()
+    m = spec.to_struct()
+    st = np.ascontiguousarray(state, dtype=np.float64)
+    return lib.oracle_index(C.byref(m), _dp(st))
+
+
+def n_actions(spec, period, state):
+    lib = load()
+    m = spec.to_struct()
+    st = np.ascontiguousarray(state, dtype=np.float64)
+    return lib.oracle_n_actions(C.byref(m), period, _dp(st))

@@ -1,0 +1,234 @@
+"""GPU parity tests: libsdpb200.so (through the C-ABI) against the CPU oracle, bit for bit.
+
+Values are compared with ==, order quantities with == (the argopt reduction reproduces the
+reference's first-wins tie rule, so even exact ties must agree)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve_all(S, spec, **kw):
+    s = S.Solver(spec, **kw)
+    s.solve()
+    V = np.empty((spec.T, s.n_states))
+    Q = np.empty((spec.T, s.n_states))
+    for t in range(1, spec.T + 1):
+        V[t - 1], Q[t - 1] = s.period_tables(t)
+    return s, V, Q
+
+
+@pytest.mark.parametrize("case", cases.ALL, ids=lambda f: f.__name__[5:])
+def test_generic_kernel_whole_grid(case, S, oracle):
+    spec, init = case()
+    Vo, Qo, evals, _ = oracle.dense(spec)
+    s, V, Q = _solve_all(S, spec, kernel=S.KERNEL_GENERIC)
+    assert s.n_states == Vo.shape[1]
+    assert np.array_equal(V, Vo)
+    assert np.array_equal(Q, Qo)
+    st = s.stats()
+    assert st["evals"] == evals
+    assert st["launches"] == spec.T and st["kernel_used"] == S.KERNEL_GENERIC
+
+
+@pytest.mark.parametrize("case", cases.ALL, ids=lambda f: f.__name__[5:])
+def test_auto_kernel_whole_grid(case, S, oracle):
+    """Whatever kernel AUTO picks (tiled where one exists) must give the same bits."""
+    spec, init = case()
+    Vo, Qo, evals, _ = oracle.dense(spec)
+    s, V, Q = _solve_all(S, spec)
+    assert np.array_equal(V, Vo)
+    assert np.array_equal(Q, Qo)
+    assert s.stats()["evals"] == evals
+
+
+@pytest.mark.parametrize("name", cases.GOLDEN)
+def test_against_golden_fixtures(name, S):
+    spec, init, g = cases.load_golden(name)
+    s, V, Q = _solve_all(S, spec)
+    per = g["periods"] - 1
+    assert np.array_equal(V[per], g["V"])
+    assert np.array_equal(Q[per].astype(np.float32), g["Q"])
+    v, q = s.value(1, g["init"])
+    assert np.array_equal(v, g["init_values"])
+
+
+@pytest.mark.parametrize("case", cases.ALL, ids=lambda f: f.__name__[5:])
+def test_value_and_opt_table_match_topdown(case, S, oracle):
+    """getExpectedValue/getAction and the getOptTable() row set (visited states only, sorted)."""
+    spec, init = case()
+    rows, iv, _ = oracle.topdown(spec, init)
+    s = S.Solver(spec).solve()
+    v, q = s.value(1, init)
+    assert np.array_equal(v, iv)
+    s.reach(init)
+    tab = s.opt_table()
+    nd = spec.ndim
+    assert tab.shape == (len(rows), nd + 2)
+    # the oracle emits rows in the memo-map order (period, inv, preQ.., cash); the library in its
+    # grid order, which is the same ordering
+    assert np.array_equal(tab[:, :nd + 1], rows[:, :nd + 1])
+    assert np.array_equal(tab[:, -1], rows[:, -2])
+    # every visited state answers through sdpb_value too
+    for t in range(1, spec.T + 1):
+        sel = rows[rows[:, 0] == t]
+        if len(sel):
+            v, q = s.value(t, sel[:, 1:1 + nd])
+            assert np.array_equal(v, sel[:, -1]) and np.array_equal(q, sel[:, -2])
+
+
+@pytest.mark.parametrize("case", cases.ALL, ids=lambda f: f.__name__[5:])
+def test_device_lambdas_match_oracle(case, S, oracle):
+    """sdpb_eval_triples (the device code of c, f, |A|) against the oracle's lambdas."""
+    import random
+    spec, _ = case()
+    pkg = S.package
+    from importlib import import_module
+    spot = import_module(pkg.__name__ + "._spot")
+    rng = random.Random(7)
+    s = S.Solver(spec)
+    for _ in range(60):
+        st, a, d = spot.random_triple(spec, rng)
+        c, nxt, na = spot.eval_descriptor(spec, st, a, d, solver=s)
+        assert na == oracle.n_actions(spec, st[0], st[1:])
+        co, no = oracle.eval_triple(spec, st[0], st[1:], a, d)
+        assert c == co
+        if st[0] < spec.T and oracle.index(spec, no) >= 0:
+            assert tuple(no) == nxt
+
+
+def test_unsolved_state_raises(S):
+    spec, _ = cases.case_A_small()
+    s = S.Solver(spec)
+    with pytest.raises(S.SdpbError) as e:
+        s.value(1, [[0.0]])
+    assert e.value.code == S.abi.SDPB_ERR_STATE
+    s.solve()
+    with pytest.raises(S.SdpbError) as e:
+        s.value(1, [[1000.0]])  # outside the grid: Java would throw from getAction
+    assert e.value.code == S.abi.SDPB_ERR_UNSOLVED
+    with pytest.raises(S.SdpbError):
+        s.value(1, [[0.25]])    # not a grid point
+
+
+def test_reference_style_driver_capacitated(S, oracle):
+    """Reads like src/capacitated/CLSPTesting.java:75-120: build pmf, lambdas, Recursion, solve."""
+    pmf = S.GetPmf([S.PoissonDist(m) for m in (5, 8, 6)], 0.999, 1).getpmf()
+    K, v, h, pi, maxQ, lo, hi = 20.0, 1.0, 1.0, 5.0, 15, -30.0, 30.0
+
+    def getFeasibleAction(s):
+        return [float(i) for i in range(maxQ + 1)]
+
+    def stateTransition(state, action, randomDemand):
+        nxt = state.getIniInventory() + action - randomDemand
+        nxt = hi if nxt > hi else nxt
+        nxt = lo if nxt < lo else nxt
+        return S.State(state.getPeriod() + 1, nxt)
+
+    def immediateValue(state, action, randomDemand):
+        fixed = K if action > 0 else 0
+        lvl = state.getIniInventory() + action - randomDemand
+        return fixed + v * action + h * max(lvl, 0) + pi * max(-lvl, 0)
+
+    spec = S.inventory_model(pmf, K, v, h, pi, max_order=maxQ, inv_min=lo, inv_max=hi)
+    recursion = S.Recursion(spec, getFeasibleAction, stateTransition, immediateValue)
+    with pytest.raises(KeyError):
+        recursion.getAction(S.State(1, 0))      # NullPointerException in the reference
+    initialState = S.State(1, 0)
+    finalValue = recursion.getExpectedValue(initialState)
+    rows, iv, _ = oracle.topdown(spec, [[0.0]])
+    assert finalValue == iv[0]
+    assert recursion.getAction(initialState) == rows[0][-2]
+    assert np.array_equal(recursion.getOptTable(), rows[:, :3])
+    acts = recursion.getCacheActions()
+    assert len(acts) == len(rows) and acts[S.State(1, 0)] == rows[0][-2]
+    # a wrong descriptor is caught by the spot check
+    wrong = S.inventory_model(pmf, K, v, h, pi + 1, max_order=maxQ, inv_min=lo, inv_max=hi)
+    with pytest.raises(ValueError):
+        S.Recursion(wrong, getFeasibleAction, stateTransition, immediateValue)
+
+
+def test_reference_style_driver_cash(S, oracle):
+    """Reads like src/cash/singleItem/CashConstraint.java:91-146."""
+    spec, init = cases.case_C_rich()
+    recursion = S.CashRecursion(spec)
+    recursion.setTreeMapCacheAction()
+    s0 = S.CashState(1, *init[0])
+    rows, iv, _ = oracle.topdown(spec, init[:1])
+    assert recursion.getExpectedValue(s0) == iv[0]
+    assert recursion.getAction(s0) == rows[0][-2]
+    assert np.array_equal(recursion.getOptTable(), rows[:, :4])
+
+
+def test_reference_style_driver_survival(S, oracle):
+    spec, init = cases.case_F_small()
+    recursion = S.RiskRecursion(spec)
+    s0 = S.RiskState(1, init[0][0], init[0][1], False)
+    rows, iv, _ = oracle.topdown(spec, init)
+    assert recursion.getSurvProb(s0) == iv[0]
+    assert 0.0 <= iv[0] <= 1.0
+
+
+# ---- full-size configurations ----------------------------------------------------------------
+def _sample_check(S, oracle, spec, s, n=48, seed=3):
+    """Period-by-period inductive check on a sample: recompute V_t, Q_t on the CPU from the GPU's
+    own V_{t+1} table and compare bits."""
+    rng = np.random.default_rng(seed)
+    idx = np.unique(np.concatenate([[0, s.n_states - 1], rng.integers(0, s.n_states, n)]))
+    Vn = None
+    for t in range(spec.T, 0, -1):
+        V, Q = s.period_tables(t)
+        vo, qo = oracle.step_states(spec, t, Vn, idx)
+        assert np.array_equal(V[idx], vo), f"period {t}"
+        assert np.array_equal(Q[idx], qo), f"period {t}"
+        Vn = V
+
+
+def test_config_c1_full(S, oracle):
+    spec = S.configs.c1()
+    Vo, Qo, evals, _ = oracle.dense(spec)
+    for kernel in (S.KERNEL_GENERIC, S.KERNEL_AUTO):
+        s, V, Q = _solve_all(S, spec, kernel=kernel)
+        assert np.array_equal(V, Vo) and np.array_equal(Q, Qo)
+        assert s.stats()["evals"] == evals == 133399266.0
+
+
+def test_config_c2_full(S, oracle):
+    spec = S.configs.c2()
+    Vo, Qo, evals, _ = oracle.dense(spec)
+    s, V, Q = _solve_all(S, spec)
+    assert np.array_equal(V, Vo) and np.array_equal(Q, Qo)
+
+
+def test_config_c3_sampled(S, oracle):
+    spec = S.configs.c3(T=3)          # full 501 x 2001 grid, 3 of the 12 periods
+    s = S.Solver(spec).solve()
+    assert s.n_states == 1002501
+    _sample_check(S, oracle, spec, s, n=24)
+
+
+def test_config_c4_sampled(S, oracle):
+    spec = S.configs.c4(T=3)          # full 1001 x 101 x 101 grid, 3 of the 20 periods
+    s = S.Solver(spec).solve()
+    assert s.n_states == 10211201
+    _sample_check(S, oracle, spec, s, n=64)
+    # V(x, q1, q2) depends on (x, q1) only through x + q1: an exact structural identity
+    V, _ = s.period_tables(1)
+    V = V.reshape(1001, 101, 101)
+    assert np.array_equal(V[100, 7, :], V[107, 0, :]) and np.array_equal(V[500, 50, :], V[520, 30, :])
+
+
+def test_config_c5_sampled(S, oracle):
+    spec = S.configs.c5(n_states=1_000_000, T=2)
+    s = S.Solver(spec).solve()
+    _sample_check(S, oracle, spec, s, n=64)
+    # tiled and generic kernels are independent implementations: whole-grid agreement at this size
+    g = S.Solver(spec, kernel=S.KERNEL_GENERIC).solve()
+    for t in (1, 2):
+        Va, Qa = s.period_tables(t)
+        Vg, Qg = g.period_tables(t)
+        assert np.array_equal(Va, Vg) and np.array_equal(Qa, Qg)
