@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — SDP solve time and state-action-demand evaluations/s (fp64) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W  # CPU arm: the oracle port on host cores
+
+A "step" is one full-horizon solve (T backward-induction launches) of the workload.  The default
+workload is BASELINE.json configs[4], the synthetic scale sweep the metric is quoted on at 1/2/4/8
+GPUs: family A (src/capacitated lambdas), S states x 200 actions x 200 demand points, T = 4, with
+S = 1e7 per GPU (weak scaling: the state grid grows with N and is block-partitioned across ranks;
+every period each rank solves its block and V_t is all-gathered over NCCL).  The other configs
+(C1-C4) are solved once each and reported under "configs".
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "state-action-demand evaluations/s (fp64), full-horizon SDP solve"
+UNIT = "evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--states-per-gpu", type=int, default=10_000_000, help="C5 only")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tiled"])
+    ap.add_argument("--dedup", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the one-shot C1-C4 solves")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def make_spec(S, name, n_gpus, states_per_gpu):
+    c = S.configs
+    if name == "c5":
+        return c.c5(n_states=states_per_gpu * n_gpus)
+    return {"c1": c.c1, "c2": c.c2, "c3": c.c3, "c4": c.c4}[name]()
+
+
+def workload_desc(spec, name, n_gpus):
+    D = [len(r) for r in spec.pmf]
+    return {
+        "workload": {
+            "c1": "C1 src/sdp single-item lot sizing T=4 Poisson[20,40,60,40] 1001 states x 501 actions",
+            "c2": "C2 src/capacitated T=20 2001 states x 101 actions",
+            "c3": "C3 src/cash (inventory, cash) 1,002,501 states x <=201 actions x 200 demands T=12",
+            "c4": "C4 src/leadtime L=2 10,211,201 states x 101 actions x 25 demands T=20",
+            "c5": f"C5 synthetic sweep family A: {spec.n_states()} states x {spec.max_order_idx + 1} actions x "
+                  f"{D[0]} demand points, T={spec.T}",
+        }[name],
+        "T": spec.T, "demand_points": D[0] if len(set(D)) == 1 else D,
+        "actions": spec.max_order_idx + 1,
+        "partition": f"state grid in {n_gpus} contiguous blocks, V_t all-gather per period" if n_gpus > 1 else "none",
+        "l2": "inputs exceed L2 only for S>=1.6e7 (V_t is 8*S bytes); kernel is fp64-pipe bound and reads "
+              "V_{t+1} once per tile through shared memory, so L2 state does not move the number",
+    }
+
+
+# ---- clocks ---------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v == "Active":
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- CPU arm ----------------------------------------------------------------------------------
+def cpu_sample_spec(S, spec, n_states):
+    """Same family, same actions / demand table / horizon, fewer inventory states."""
+    import copy
+    s = copy.copy(spec)
+    if spec.cost_kind == S.COST_BACKORDER and spec.lead_time == 0:
+        half = n_states // 2
+        s.inv_min, s.inv_max = float(-half), float(n_states - half - 1)
+    return s
+
+
+def time_oracle(S, spec, seconds, threads=0):
+    """Time the oracle's dense solve (all host threads) on a bounded sample of `spec`."""
+    import oracle_lib as O
+    n = 256
+    t0 = time.perf_counter()
+    _, _, ev, _ = O.dense(cpu_sample_spec(S, spec, n), threads)
+    dt = max(time.perf_counter() - t0, 1e-3)
+    rate = ev / dt
+    per_state = ev / n
+    n_big = int(max(n, min(spec.n_states(), rate * seconds / per_state)))
+    sample = cpu_sample_spec(S, spec, n_big)
+    t0 = time.perf_counter()
+    _, _, ev, _ = O.dense(sample, threads)
+    dt = time.perf_counter() - t0
+    return ev / dt, ev, dt, n_big
+
+
+def time_topdown(S, spec, n_states=2048):
+    import oracle_lib as O
+    sample = cpu_sample_spec(S, spec, n_states)
+    init = [[0.0] * sample.ndim]
+    t0 = time.perf_counter()
+    rows, _, ev = O.topdown(sample, init)
+    dt = time.perf_counter() - t0
+    return ev / dt, ev, dt, len(rows)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import sdpb200 as S
+    spec = make_spec(S, args.workload, 1, args.states_per_gpu)
+    cores = os.cpu_count() or 1
+    # size one step to ~ (180 s budget) / (steps + warmup)
+    per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    rate, ev, dt, n_s = time_oracle(S, spec, per_step)
+    for _ in range(max(0, args.warmup - 1)):
+        time_oracle_fixed(S, spec, n_s)
+    t_total, ev_total = 0.0, 0.0
+    for _ in range(args.steps):
+        e, d = time_oracle_fixed(S, spec, n_s)
+        t_total += d
+        ev_total += e
+    value = ev_total / t_total
+    sample = (f"oracle_dense (C++ restatement of Recursion.java:129-161, {cores} host threads) on {n_s} of "
+              f"{spec.n_states()} states, all {spec.max_order_idx + 1} actions x {len(spec.pmf[0])} demands x T={spec.T}")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_desc(spec, args.workload, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "the reference is Java (no JDK in the image); this is the C++ oracle port, "
+                                 "multi-threaded, which is faster than the single-threaded Java original"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+    return 0
+
+
+def time_oracle_fixed(S, spec, n_states):
+    import oracle_lib as O
+    sample = cpu_sample_spec(S, spec, n_states)
+    t0 = time.perf_counter()
+    _, _, ev, _ = O.dense(sample, 0)
+    return ev, time.perf_counter() - t0
+
+
+# ---- GPU arm ----------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import sdpb200 as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libsdpb200 has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    par = S.package.parallel
+    _CAI = par._CAI
+
+    def ShardedSolve(S_, torch_, dist_, spec_, rank_, world_, device_, stream_, kernel_, dedup_):
+        return par.ShardedSolve(S_.Solver, torch_, dist_, spec_, rank_, world_, device_, stream_, kernel_, dedup_)
+
+    kernel = {"auto": S.KERNEL_AUTO, "generic": S.KERNEL_GENERIC, "tiled": S.KERNEL_TILED}[args.kernel]
+    spec = make_spec(S, args.workload, world, args.states_per_gpu)
+    stream = torch.cuda.Stream(device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        sh = ShardedSolve(S, torch, dist, spec, rank, world, local, stream, kernel, args.dedup)
+        # evaluations per step, whole job (exact for state-independent action sets; cash-limited
+        # workloads take the library's own count)
+        for _ in range(args.warmup):
+            sh.step()
+        barrier()
+        ev_local_before = sh.solver.stats()["evals"]
+        fp_before = sh.solver.stats()["fp64_ops"]
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            sh.step()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        st = sh.solver.stats()
+        ev_local = st["evals"] - ev_local_before
+        fp_local = st["fp64_ops"] - fp_before
+        t = torch.tensor([ms, ev_local, fp_local], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone()
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            ms, ev_total, fp_total = float(tmax[0]), float(tsum[1]), float(tsum[2])
+        else:
+            ev_total, fp_total = ev_local, fp_local
+        kernel_used = st["kernel_used"]
+        value = ev_total / (ms * 1e-3)
+
+        # ---- e2e: through the C-ABI with host buffers; H2D of the descriptor tables and D2H of the
+        # period-1 value/policy tables inside the timed region, every step ----
+        e2e_steps = max(1, min(args.steps, 3))
+        barrier()
+        t0 = time.perf_counter()
+        d2h = h2d = 0
+        for _ in range(e2e_steps):
+            s2 = ShardedSolve(S, torch, dist, spec, rank, world, local, stream, kernel, args.dedup)
+            s2.step()
+            if world == 1:
+                v1, q1 = s2.solver.value(1, [[0.0] * s2.solver.ndim] if args.workload != "c3" else [[0.0, 100.0]])
+                V1, Q1 = s2.solver.period_tables(1)
+                d2h = s2.n * 12 + 12
+            else:
+                s2.solver.sync()
+                dv, dq = s2.solver.device_tables(1)
+                nloc = s2.hi - s2.lo
+                Vt = torch.as_tensor(_CAI(dv + 8 * s2.lo, nloc, "<f8"), device=f"cuda:{local}")
+                Qt = torch.as_tensor(_CAI(dq + 4 * s2.lo, nloc, "<i4"), device=f"cuda:{local}")
+                V1 = Vt.cpu()
+                Q1 = Qt.cpu()
+                d2h = nloc * 12
+            npmf = sum(len(r) for r in spec.pmf)
+            h2d = npmf * 28 + spec.T * 32
+            s2.close()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e_value = (ev_total / args.steps) * e2e_steps / float(e2e_t[0])
+
+    out = None
+    if rank == 0:
+        peaks = S.abi.microbench(local)
+        mp = {}
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        achieved = fp_total / (ms * 1e-3) / 1e12 / world  # per GPU
+        hbm_bytes = 24.0 * spec.n_states() * spec.T * args.steps  # 8 B read + 16 B written per state-period
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak" if args.workload == "c5" else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_desc(spec, args.workload, world),
+            "solve_time_s": ms / args.steps * 1e-3,
+            "evals_per_step": ev_total / args.steps,
+            "kernel": {1: "bi_generic", 2: "bi_inv_tiled"}.get(kernel_used, str(kernel_used)),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps,
+                    "what": "sdpb_create (H2D pmf/parameter tables) + solve + sdpb_value + D2H of the period-1 "
+                            "value and policy tables + sdpb_destroy, wall clock"},
+            "gpu_launches": args.steps * spec.T * world,
+            "clocks": clocks,
+            "roofline": {
+                "bound": "fp64", "achieved": achieved, "peak": peaks["nofma_tops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["nofma_tops"] if peaks["nofma_tops"] else None, "traffic": None,
+                "what": "non-fused fp64 instructions (DADD/DMUL; Java parity forbids DFMA) the kernel executes "
+                        "per GPU per second vs the same mix measured live by sdpb_microbench on this GPU; "
+                        "MEASURED_PEAKS.json has no fp64 figure",
+                "fp64_instr_per_eval": fp_total / ev_total if ev_total else None,
+                "reference_formulation_fp64_per_eval": 20,
+                "lds_peak_gbs": peaks["lds_gbs"], "fma_peak_tflops": peaks["fma_tflops"],
+                "hbm": {"achieved_gbs": hbm_bytes / (ms * 1e-3) / 1e9 / world, "peak_gbs": mp.get("hbm_gbs"),
+                        "note": "algorithmic HBM bytes: 24 B per state-period; not the bound"},
+            },
+        }
+    sh.close()
+
+    # ---- the other configurations, solved once each (plus CPU baseline), rank 0 prints ----
+    configs = {}
+    if not args.no_configs:
+        for name in ("c1", "c2", "c3", "c4"):
+            sp = make_spec(S, name, world, args.states_per_gpu)
+            shard = name in ("c3", "c4") and world > 1
+            w = world if shard else 1
+            if not shard and rank != 0:
+                continue
+            with torch.cuda.stream(stream):
+                s3 = ShardedSolve(S, torch, dist if shard else None, sp, rank if shard else 0, w, local, stream,
+                                  S.KERNEL_AUTO, False)
+                s3.step()  # warm
+                if shard:
+                    barrier()
+                else:
+                    torch.cuda.synchronize()
+                b0 = s3.solver.stats()["evals"]
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(stream)
+                s3.step()
+                a1.record(stream)
+                torch.cuda.synchronize()
+                cms = a0.elapsed_time(a1)
+                ev = s3.solver.stats()["evals"] - b0
+                tt = torch.tensor([cms, ev], dtype=torch.float64, device=f"cuda:{local}")
+                if shard:
+                    mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                    sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+                    cms, ev = float(mx[0]), float(sm[1])
+                init = {"c1": [[0.0]], "c2": [[0.0]], "c3": [[0.0, 100.0]], "c4": [[0.0, 0.0, 0.0]]}[name]
+                v0 = q0 = None
+                if not shard:
+                    v, q = s3.solver.value(1, init)
+                    v0, q0 = float(v[0]), float(q[0])
+                configs[name] = {"solve_ms": cms, "evals": ev, "evals_per_s": ev / (cms * 1e-3), "n_gpus": w,
+                                 "kernel": {1: "bi_generic", 2: "bi_inv_tiled"}.get(s3.solver.stats()["kernel_used"]),
+                                 "V1_init": v0, "Q1_init": q0}
+                s3.close()
+    if rank == 0:
+        out["configs"] = configs
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            base = make_spec(S, args.workload, 1, args.states_per_gpu)
+            rate, ev, dt, n_s = time_oracle(S, base, args.cpu_seconds)
+            td_rate, td_ev, td_dt, td_rows = time_topdown(S, base)
+            out["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"oracle_dense on {n_s} of {base.n_states()} states (all actions, demands, T), {dt:.1f} s, "
+                          f"{cores} threads",
+                "topdown_1core": {"value": td_rate, "unit": UNIT,
+                                  "sample": f"oracle_topdown (literal memoised recursion) from x0=0 on a {2048}-state "
+                                            f"grid: {td_rows} visited states, {td_dt:.1f} s"},
+                "note": "reference is single-threaded Java (no JDK in the image): C++ port timed instead"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_gpu(a))

@@ -242,6 +242,13 @@ int sdpb_stats_get(const sdpb_handle* h, sdpb_stats* s);
 int sdpb_eval_triples(sdpb_handle* h, int period, const double* states, const int32_t* action_idx,
                       const double* demand, int n, double* c, double* next_states, int32_t* n_actions);
 
+/* Roofline denominators of this path, measured on `device` with CUDA events (best of 5):
+ *   nofma_tops  non-fused fp64 instruction rate, DADD/DMUL mix, in 1e12 instructions/s
+ *   fma_tflops  fused fp64 rate in TFLOP/s (2 flops per DFMA) — for context, the kernels cannot use it
+ *   lds_gbs     shared-memory LDS.128 bandwidth, GB/s
+ * Any pointer may be NULL. */
+int sdpb_microbench(int device, double* nofma_tops, double* fma_tflops, double* lds_gbs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,3 +16,4 @@ from .recursion import (CashLeadtimeRecursion, CashLeadtimeState, CashRecursion,
                         OptDirection, Recursion, RiskRecursion, RiskState, State)
 from .solver import Solver
 from . import configs
+from . import parallel

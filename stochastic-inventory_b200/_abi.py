@@ -77,7 +77,7 @@ EXPORTS = [
     "sdpb_abi_version", "sdpb_sizeof_model", "sdpb_sizeof_options", "sdpb_create", "sdpb_destroy",
     "sdpb_last_error", "sdpb_grid_info", "sdpb_solve", "sdpb_solve_period_async", "sdpb_sync",
     "sdpb_value", "sdpb_period_tables", "sdpb_device_tables", "sdpb_state_of_index", "sdpb_reach",
-    "sdpb_opt_table", "sdpb_stats_get", "sdpb_eval_triples",
+    "sdpb_opt_table", "sdpb_stats_get", "sdpb_eval_triples", "sdpb_microbench",
 ]
 
 _lib = None
@@ -87,6 +87,16 @@ class SdpbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"{STATUS_NAMES.get(code, code)}: {msg}")
         self.code = code
+
+
+def microbench(device=-1):
+    """-> dict(nofma_tops, fma_tflops, lds_gbs): the fp64 / shared-memory roofline denominators."""
+    lib = load()
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    rc = lib.sdpb_microbench(device, C.byref(a), C.byref(b), C.byref(c))
+    if rc != SDPB_OK:
+        raise SdpbError(rc, "sdpb_microbench failed")
+    return {"nofma_tops": a.value, "fma_tflops": b.value, "lds_gbs": c.value}
 
 
 def load():
@@ -120,6 +130,7 @@ def load():
     lib.sdpb_opt_table.argtypes = [vp, _dp, C.POINTER(C.c_size_t)]
     lib.sdpb_stats_get.argtypes = [vp, C.POINTER(SdpbStats)]
     lib.sdpb_eval_triples.argtypes = [vp, C.c_int, _dp, _ip, _dp, C.c_int, _dp, _dp, _ip]
+    lib.sdpb_microbench.argtypes = [C.c_int, _dp, _dp, _dp]
     if lib.sdpb_sizeof_model() != C.sizeof(SdpbModel) or lib.sdpb_sizeof_options() != C.sizeof(SdpbOptions):
         raise ImportError("libsdpb200.so struct layout differs from the ctypes binding")
     _lib = lib

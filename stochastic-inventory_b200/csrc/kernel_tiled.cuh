@@ -1,7 +1,29 @@
-// kernel_tiled.cuh — shared-memory tiled backward-induction kernels (placeholder plan: none yet).
+// kernel_tiled.cuh — shared-memory tiled backward induction for the 1-D inventory family
+// (SDPB_COST_BACKORDER, lead_time 0: Recursion.java:129-161 with the lambdas of
+// CLSPTesting.java:78-106 / CLSP.java:251-272).  Bit-identical to bi_generic by construction.
+//
+// Where the work goes.  Per (state x, action a, demand d_j) the reference computes
+//     lvl = x + a - d_j;  c = ((fixed + v*a) + h*max(lvl,0)) + pi*max(-lvl,0)
+//     Q += p_j * c;       Q += (p_j*gamma) * V_{t+1}(clamp(lvl))
+// 1. One of the holding / penalty terms is always +0, so ((fv + hold) + pen) == fv + (hold + pen)
+//    bit for bit, and (hold + pen) and the successor's value depend on the integer level
+//    il = ix + ia - id_j alone.  Each CTA tabulates W[il] = (hold+pen, V_{t+1}[succ(il)]) for the
+//    window of levels its tile can reach, once, in shared memory (coalesced fp64 loads of V_{t+1}).
+// 2. A thread owns one order-up-to level y = x + a and R consecutive actions (so R states
+//    x = y - a on a diagonal).  All R evaluations of a demand point share W[y - d_j] — ONE
+//    16-byte shared-memory load — and the product (p_j*gamma)*V, leaving 4 fp64 instructions per
+//    evaluation (+1/R): add, mul, add, add.  No FMA: Java has none.
+// 3. The thread's R states do not change from one action chunk to the next, so the running
+//    (best, argbest) per state stays in registers; a state's R residue classes live in R adjacent
+//    threads and are merged once per launch through shared memory with the lexicographic
+//    (value, action) rule == the reference's ascending first-wins scan (Recursion.java:146-157).
+// 4. Small grids (C1: 1,001 states) cannot fill 148 SMs with state tiles alone, so the action
+//    range is also split across CTAs (gridDim.y); the last CTA of a tile to finish merges the
+//    partial optima.  Still one launch per period.
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -9,19 +31,303 @@
 
 namespace sdpb {
 
-struct TiledPlan {
-    bool available = false;
-    const char* why_not = "not implemented";
-};
+constexpr int kTiledThreads = 256;
+constexpr int kTiledR = 8;                                // actions (and states) per thread
+constexpr int kTiledBX = kTiledThreads - kTiledR + 1;     // states per tile (249)
 
-inline void plan_tiled(TiledPlan& P, const sdpb_model&, const DevModel&, const std::vector<int>&,
-                       const std::vector<int>&, const std::vector<int>&, bool, const cudaDeviceProp&) {
-    P.available = false;
+// bytes before the demand table: the level window, later aliased by the residue-merge area
+__host__ __device__ inline size_t tiled_head_bytes(int WN) {
+    const size_t w_bytes = (size_t)WN * 16;
+    const size_t red_bytes = (((size_t)kTiledR * kTiledBX * 12) + 15) & ~(size_t)15;
+    return w_bytes > red_bytes ? w_bytes : red_bytes;
 }
 
-inline int launch_tiled(const TiledPlan&, const DevModel&, int, int, int, const double*, double*, int*,
-                        long long, long long, cudaStream_t, double*) {
-    return SDPB_ERR_ARG;
+struct TiledPeriod {
+    bool ok = false;
+    bool consec = false;  // demand indices are di_0, di_0+1, ...
+    int di_max = 0, span = 0;
+    int WN = 0;           // window entries
+    size_t smem = 0;
+};
+
+struct TiledPlan {
+    bool available = false;
+    const char* why_not = "";
+    std::vector<TiledPeriod> period;  // [T]
+    int n_chunks = 0;                 // ceil(n_actions / R)
+    int sm_count = 148;
+    // cross-CTA merge scratch for action splitting (allocated lazily by the owner)
+    double* part_v = nullptr;
+    int* part_a = nullptr;
+    unsigned* counters = nullptr;
+    size_t part_cap = 0, counter_cap = 0;
+};
+
+struct TiledArgs {
+    int t, D, pmf_off;
+    const double* Vn;
+    double* Vt;
+    int* Qt;
+    long long lo, hi;
+    int di_max, WN, n_chunks, chunks_per_split, nsplit;
+    double* part_v;
+    int* part_a;
+    unsigned* counters;
+};
+
+template <bool IS_MIN, bool LAST, bool CONSEC>
+__global__ void __launch_bounds__(kTiledThreads)
+bi_inv_tiled(const __grid_constant__ DevModel M, const __grid_constant__ TiledArgs a) {
+    constexpr int R = kTiledR, BX = kTiledBX, NT = kTiledThreads;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [ W window | reduction area (aliased) ] [ (p, p*gamma) per demand ] [ e_j ]
+    double2* W = reinterpret_cast<double2*>(smem_raw);
+    const size_t head = tiled_head_bytes(a.WN);
+    double2* PP = reinterpret_cast<double2*>(smem_raw + head);
+    int* E = reinterpret_cast<int*>(smem_raw + head + (size_t)a.D * sizeof(double2));
+
+    const int u = threadIdx.x;
+    const long long X0 = a.lo + (long long)blockIdx.x * BX;  // first state of the tile
+    const int split = blockIdx.y;
+
+    // ---- stage the demand table ----
+    for (int j = u; j < a.D; j += NT) {
+        PP[j] = make_double2(M.pmf_p[a.pmf_off + j], M.pmf_pg[a.pmf_off + j]);
+        E[j] = a.di_max - M.pmf_di[a.pmf_off + j];
+    }
+    // ---- stage the level window: W[wi] <-> level index il = X0 - di_max + wi ----
+    const bool lost = (M.flags & SDPB_F_LOST_SALES) != 0;
+    for (int wi = u; wi < a.WN; wi += NT) {
+        const long long il = X0 - a.di_max + wi;
+        const double lvl = M.inv_min + (double)il * M.step;  // exact on the validated grid
+        const double hold = M.h * fmax(lvl, 0.0);
+        const double pen = M.pen * fmax(-lvl, 0.0);
+        double vn = 0.0;
+        if (!LAST) {
+            long long is = il;
+            if (lost) is = is > M.i_zero ? is : M.i_zero;
+            is = is < M.nI - 1 ? is : M.nI - 1;  // upper clamp first (CLSPTesting.java:91-92)
+            is = is > 0 ? is : 0;
+            vn = a.Vn[is];
+        }
+        W[wi] = make_double2(hold + pen, vn);
+    }
+    __syncthreads();
+
+    double best[R];
+    int arg[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { best[r] = IS_MIN ? DBL_MAX : -DBL_MAX; arg[r] = kNoAction; }
+
+    const double v = M.v_t[a.t - 1];
+    const int c_begin = split * a.chunks_per_split;
+    const int c_end = min(a.n_chunks, c_begin + a.chunks_per_split);
+    const int e0 = a.D - 1;  // CONSEC: e_j = (D-1) - j
+
+    for (int c = c_begin; c < c_end; c++) {
+        double fv[R], acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = c * R + r;
+            const double av = (double)i * M.step;
+            const double fixedCost = av > 0.0 ? M.K : 0.0;
+            fv[r] = fixedCost + v * av;  // fixedCost + variableCost (CLSPTesting.java:98-99,104)
+            acc[r] = 0.0;
+        }
+        const double2* Wt = W + u + c * R;
+#pragma unroll 4
+        for (int j = 0; j < a.D; j++) {
+            const double2 pp = PP[j];
+            const double2 w = Wt[CONSEC ? (e0 - j) : E[j]];
+            if (!LAST) {
+                const double pv = pp.y * w.y;            // (p*gamma) * V_{t+1}(f)   Recursion.java:142
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const double cst = fv[r] + w.x;      // immediate value
+                    acc[r] += pp.x * cst;                // Recursion.java:139
+                    acc[r] += pv;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const double cst = fv[r] + w.x;
+                    acc[r] += pp.x * cst;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = c * R + r;
+            if (i <= M.max_order_idx && (IS_MIN ? (acc[r] < best[r]) : (acc[r] > best[r]))) {
+                best[r] = acc[r];
+                arg[r] = i;
+            }
+        }
+    }
+
+    // ---- merge the R residue classes of each state (aliases the window) ----
+    __syncthreads();
+    double* red_v = reinterpret_cast<double*>(smem_raw);
+    int* red_a = reinterpret_cast<int*>(smem_raw + (size_t)R * BX * sizeof(double));
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int s = u - r;  // thread u, residue r evaluated state X0 + u - r
+        if (s >= 0 && s < BX) { red_v[r * BX + s] = best[r]; red_a[r * BX + s] = arg[r]; }
+    }
+    __syncthreads();
+    double bv = IS_MIN ? DBL_MAX : -DBL_MAX;
+    int ba = kNoAction;
+    const bool owner = u < BX && X0 + u < a.hi;
+    if (u < BX) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const double ov = red_v[r * BX + u];
+            const int oa = red_a[r * BX + u];
+            if (better<IS_MIN>(ov, oa, bv, ba)) { bv = ov; ba = oa; }
+        }
+    }
+    if (a.nsplit == 1) {
+        if (owner) { a.Vt[X0 + u] = bv; a.Qt[X0 + u] = ba == kNoAction ? -1 : ba; }
+        return;
+    }
+    // ---- action range was split over gridDim.y CTAs: the last one to arrive merges ----
+    const size_t slot = ((size_t)blockIdx.x * a.nsplit + split) * BX + u;
+    if (u < BX) { a.part_v[slot] = bv; a.part_a[slot] = ba; }
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (u == 0) is_last = (atomicAdd(&a.counters[blockIdx.x], 1u) == (unsigned)a.nsplit - 1u);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (owner) {
+        bv = IS_MIN ? DBL_MAX : -DBL_MAX;
+        ba = kNoAction;
+        for (int sp = 0; sp < a.nsplit; sp++) {
+            const size_t q = ((size_t)blockIdx.x * a.nsplit + sp) * BX + u;
+            const double ov = __ldcg(a.part_v + q);
+            const int oa = __ldcg(a.part_a + q);
+            if (better<IS_MIN>(ov, oa, bv, ba)) { bv = ov; ba = oa; }
+        }
+        a.Vt[X0 + u] = bv;
+        a.Qt[X0 + u] = ba == kNoAction ? -1 : ba;
+    }
+    if (u == 0) a.counters[blockIdx.x] = 0;  // ready for the next launch
+}
+
+// ---- host side --------------------------------------------------------------------------------
+inline void plan_tiled(TiledPlan& P, const sdpb_model& m, const DevModel& d, const std::vector<int>& pmf_len,
+                       const std::vector<int>& pmf_off, const std::vector<int>& pdi, bool /*dedup*/,
+                       const cudaDeviceProp& prop) {
+    P.available = false;
+    P.sm_count = prop.multiProcessorCount;
+    if (m.cost_kind != SDPB_COST_BACKORDER) { P.why_not = "only the backorder cost kind is tiled"; return; }
+    if (m.lead_time != 0) { P.why_not = "lead-time states are not tiled yet"; return; }
+    if (!(m.flags & SDPB_F_CLAMP_INV)) { P.why_not = "needs the inventory clamp"; return; }
+    P.n_chunks = (d.max_order_idx + 1 + kTiledR - 1) / kTiledR;
+    P.period.assign(m.T, TiledPeriod{});
+    bool any = false;
+    for (int t = 0; t < m.T; t++) {
+        TiledPeriod& tp = P.period[t];
+        if ((m.flags & SDPB_F_GY_MODE) && t == 0) continue;  // the G(y) pass runs on the generic kernel
+        const int D = pmf_len[t];
+        const int* di = pdi.data() + pmf_off[t];
+        int lo = di[0], hi = di[0];
+        bool consec = true;
+        for (int j = 0; j < D; j++) {
+            lo = std::min(lo, di[j]);
+            hi = std::max(hi, di[j]);
+            if (di[j] != di[0] + j) consec = false;
+        }
+        tp.consec = consec;
+        tp.di_max = hi;
+        tp.span = hi - lo;
+        tp.WN = kTiledBX + P.n_chunks * kTiledR + tp.span;
+        tp.smem = tiled_head_bytes(tp.WN) + (size_t)D * 16 + (size_t)D * 4 + 16;
+        tp.ok = tp.smem <= 200 * 1024;
+        any = any || tp.ok;
+    }
+    if (!any) { P.why_not = "window does not fit in shared memory"; return; }
+    P.available = true;
+}
+
+template <bool IS_MIN, bool LAST, bool CONSEC>
+inline cudaError_t launch_tiled_inst(const DevModel& dm, const TiledArgs& a, dim3 grid, size_t smem,
+                                     cudaStream_t stream) {
+    auto k = bi_inv_tiled<IS_MIN, LAST, CONSEC>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k<<<grid, kTiledThreads, smem, stream>>>(dm, a);
+    return cudaGetLastError();
+}
+
+// Returns SDPB_OK, or SDPB_ERR_STATE when this period has no tiled plan (caller falls back to the
+// generic kernel), or SDPB_ERR_CUDA / SDPB_ERR_NOMEM.
+inline int launch_tiled(TiledPlan& P, const DevModel& dm, int t, int D, int pmf_off, const double* Vn,
+                        double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream,
+                        double* fp64_ops) {
+    const TiledPeriod& tp = P.period[t - 1];
+    if (!tp.ok) return SDPB_ERR_STATE;
+    const long long n = hi - lo;
+    if (n <= 0) return SDPB_OK;
+    const long long tiles = (n + kTiledBX - 1) / kTiledBX;
+    // fill the machine: about 4 CTAs per SM; split the action range when state tiles are too few
+    const long long target = 4LL * P.sm_count;
+    int nsplit = 1;
+    if (tiles < target) nsplit = (int)std::min<long long>(P.n_chunks, (target + tiles - 1) / tiles);
+    const int cps = (P.n_chunks + nsplit - 1) / nsplit;
+    nsplit = (P.n_chunks + cps - 1) / cps;
+    if (nsplit > 1) {
+        const size_t need = (size_t)tiles * nsplit * kTiledBX;
+        if (need > P.part_cap) {
+            if (P.part_v) cudaFree(P.part_v);
+            if (P.part_a) cudaFree(P.part_a);
+            P.part_v = nullptr; P.part_a = nullptr; P.part_cap = 0;
+            if (cudaMalloc((void**)&P.part_v, need * sizeof(double)) != cudaSuccess) return SDPB_ERR_NOMEM;
+            if (cudaMalloc((void**)&P.part_a, need * sizeof(int)) != cudaSuccess) return SDPB_ERR_NOMEM;
+            P.part_cap = need;
+        }
+        if ((size_t)tiles > P.counter_cap) {
+            if (P.counters) cudaFree(P.counters);
+            P.counters = nullptr; P.counter_cap = 0;
+            if (cudaMalloc((void**)&P.counters, (size_t)tiles * sizeof(unsigned)) != cudaSuccess) return SDPB_ERR_NOMEM;
+            if (cudaMemsetAsync(P.counters, 0, (size_t)tiles * sizeof(unsigned), stream) != cudaSuccess) return SDPB_ERR_CUDA;
+            P.counter_cap = (size_t)tiles;
+        }
+    }
+    TiledArgs a;
+    a.t = t; a.D = D; a.pmf_off = pmf_off; a.Vn = Vn; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
+    a.di_max = tp.di_max; a.WN = tp.WN; a.n_chunks = P.n_chunks; a.chunks_per_split = cps; a.nsplit = nsplit;
+    a.part_v = P.part_v; a.part_a = P.part_a; a.counters = P.counters;
+    const dim3 grid((unsigned)tiles, (unsigned)nsplit);
+    const bool last = (t == dm.T);
+    const bool mn = dm.is_min != 0;
+    cudaError_t e;
+#define SDPB_TILED_CASE(MN, LS, CS) e = launch_tiled_inst<MN, LS, CS>(dm, a, grid, tp.smem, stream)
+    if (mn) {
+        if (last) { if (tp.consec) SDPB_TILED_CASE(true, true, true); else SDPB_TILED_CASE(true, true, false); }
+        else      { if (tp.consec) SDPB_TILED_CASE(true, false, true); else SDPB_TILED_CASE(true, false, false); }
+    } else {
+        if (last) { if (tp.consec) SDPB_TILED_CASE(false, true, true); else SDPB_TILED_CASE(false, true, false); }
+        else      { if (tp.consec) SDPB_TILED_CASE(false, false, true); else SDPB_TILED_CASE(false, false, false); }
+    }
+#undef SDPB_TILED_CASE
+    if (e != cudaSuccess) return SDPB_ERR_CUDA;
+    if (fp64_ops) {
+        // useful fp64 instructions: per evaluation add+mul+add(+add), plus one mul per R evaluations
+        const double evals = (double)n * (dm.max_order_idx + 1) * D;
+        *fp64_ops += last ? evals * 3.0 : evals * 4.0 + evals / kTiledR;
+    }
+    return SDPB_OK;
+}
+
+inline void free_tiled(TiledPlan& P) {
+    if (P.part_v) cudaFree(P.part_v);
+    if (P.part_a) cudaFree(P.part_a);
+    if (P.counters) cudaFree(P.counters);
+    P.part_v = nullptr; P.part_a = nullptr; P.counters = nullptr;
 }
 
 }  // namespace sdpb

@@ -14,6 +14,7 @@
 #include "dev_model.cuh"
 #include "kernel_generic.cuh"
 #include "kernel_tiled.cuh"
+#include "microbench.cuh"
 
 using namespace sdpb;
 
@@ -244,14 +245,16 @@ int solve_period(sdpb_handle* h, int t) {
     if (t < 1 || t > m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
     if (t < m.T && !h->solved[t]) { h->err = "period t+1 not solved yet"; return SDPB_ERR_STATE; }
     const double* Vn = t < m.T ? h->dV[t] : nullptr;
-    int rc;
+    int rc = SDPB_ERR_STATE;
     if (h->tiled.available && h->opt.kernel != SDPB_KERNEL_GENERIC) {
         rc = launch_tiled(h->tiled, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, h->dV[t - 1],
                           h->dQ[t - 1], h->lo, h->hi, h->stream, &h->stats.fp64_ops);
-        h->stats.kernel_used = SDPB_KERNEL_TILED;
-    } else {
+        if (rc == SDPB_OK) h->stats.kernel_used = SDPB_KERNEL_TILED;
+        else if (rc != SDPB_ERR_STATE) { h->err = "tiled kernel launch failed"; return rc; }
+    }
+    if (rc == SDPB_ERR_STATE) {  // no tiled plan for this model / period
         rc = dispatch_generic(h, t, Vn, h->dV[t - 1], h->dQ[t - 1]);
-        h->stats.kernel_used = SDPB_KERNEL_GENERIC;
+        if (h->stats.kernel_used != SDPB_KERNEL_TILED) h->stats.kernel_used = SDPB_KERNEL_GENERIC;
     }
     if (rc != SDPB_OK) return rc;
     CU(cudaGetLastError());
@@ -275,6 +278,7 @@ void sdpb_destroy(sdpb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (void* p : h->dev_allocs) cudaFree(p);
+    free_tiled(h->tiled);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -718,6 +722,48 @@ int sdpb_eval_triples(sdpb_handle* h, int period, const double* states, const in
         if (n_actions) n_actions[i] = hna[i];
     }
     return SDPB_OK;
+}
+
+int sdpb_microbench(int device, double* nofma_tops, double* fma_tflops, double* lds_gbs) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SDPB_ERR_NO_DEVICE;
+    if (device < 0) cudaGetDevice(&device);
+    if (device >= ndev || cudaSetDevice(device) != cudaSuccess) return SDPB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SDPB_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    double* out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return SDPB_ERR_NOMEM;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    auto best_ms = [&](auto launch) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 6; rep++) {
+            cudaEventRecord(e0);
+            launch();
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        return (double)best;
+    };
+    const int iters = 20000;
+    const double n_thr = (double)blocks * threads;
+    double ms = best_ms([&] { mb_fp64_nofma<<<blocks, threads>>>(out, iters, 1.0000001, 1e-7); });
+    if (nofma_tops) *nofma_tops = n_thr * iters * kMbChains * 2.0 / (ms * 1e-3) / 1e12;
+    ms = best_ms([&] { mb_fp64_fma<<<blocks, threads>>>(out, iters, 1.0000001, 1e-7); });
+    if (fma_tflops) *fma_tflops = n_thr * iters * kMbChains * 2.0 * 2.0 / (ms * 1e-3) / 1e12;
+    const int lds_iters = 20000;
+    ms = best_ms([&] { mb_lds128<<<blocks, threads>>>(out, lds_iters); });
+    if (lds_gbs) *lds_gbs = n_thr * lds_iters * 4.0 * 16.0 / (ms * 1e-3) / 1e9;
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return e == cudaSuccess ? SDPB_OK : SDPB_ERR_CUDA;
 }
 
 int sdpb_stats_get(const sdpb_handle* h, sdpb_stats* s) {

@@ -1,0 +1,72 @@
+"""world_size-2 (and 3) test of the multi-GPU schedule on CPU with the gloo backend: the block
+partition, the padded all-gather of V_t every period and the period ordering are the code the GPU
+path runs (stochastic-inventory_b200/parallel.py); the per-block solve is played by the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, case_name, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import cases
+    import oracle_lib as O
+    import sdpb200 as S
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    spec, _ = getattr(cases, case_name)()
+    n, _ = O.grid(spec)
+    par = S.package.parallel
+    lo, hi, chunk = par.shard_bounds(n, rank, world)
+    full = [torch.full((chunk * world,), float("nan"), dtype=torch.float64) for _ in range(spec.T)]
+    Q = np.full((spec.T, n), np.nan)
+
+    def solve_block(t):
+        vn = None if t == spec.T else full[t].numpy()[:n]
+        idx = np.arange(lo, hi, dtype=np.int64)
+        v, q = O.step_states(spec, t, vn, idx)
+        full[t - 1][lo:hi] = torch.from_numpy(v)
+        Q[t - 1, lo:hi] = q
+
+    par.backward_induction_sharded(spec.T, n, rank, world, solve_block, full, dist.all_gather_into_tensor)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), V=torch.stack(full).numpy()[:, :n], Q=Q, lo=lo, hi=hi)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,case_name", [(2, "case_A_small"), (2, "case_C_rich"), (3, "case_B2_small")])
+def test_sharded_schedule_matches_unsharded(world, case_name, tmp_path, oracle):
+    import cases
+    port = 29500 + (os.getpid() % 2000) + world
+    mp.start_processes(_worker, args=(world, port, case_name, str(tmp_path)), nprocs=world, join=True,
+                       start_method="spawn")
+    spec, _ = getattr(cases, case_name)()
+    Vo, Qo, _, _ = oracle.dense(spec)
+    covered = np.zeros(Vo.shape[1], dtype=bool)
+    for r in range(world):
+        g = np.load(tmp_path / f"r{r}.npz")
+        assert np.array_equal(g["V"], Vo)            # every rank ends with every full V_t
+        lo, hi = int(g["lo"]), int(g["hi"])
+        assert np.array_equal(g["Q"][:, lo:hi], Qo[:, lo:hi])
+        covered[lo:hi] = True
+    assert covered.all()
+
+
+def test_shard_bounds_cover_and_pad(S):
+    par = S.package.parallel
+    for n in (1, 7, 61, 1000, 10211201):
+        for world in (1, 2, 3, 4, 8):
+            pieces = [par.shard_bounds(n, r, world) for r in range(world)]
+            assert pieces[0][0] == 0 and pieces[-1][1] == n
+            for a, b in zip(pieces, pieces[1:]):
+                assert a[1] == b[0]
+            chunk = pieces[0][2]
+            assert chunk * world >= n and all(p[1] - p[0] <= chunk for p in pieces)
