@@ -29,6 +29,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+KERNEL_NAMES = {1: "bi_generic", 2: "bi_inv_tiled", 3: "bi_backorder_staged", 4: "bi_cash_int"}
 METRIC = "state-action-demand evaluations/s (fp64), full-horizon SDP solve"
 UNIT = "evals/s"
 
@@ -323,7 +324,7 @@ def run_gpu(args):
             "data": "synthetic", "config": workload_desc(spec, args.workload, world),
             "solve_time_s": ms / args.steps * 1e-3,
             "evals_per_step": ev_total / args.steps,
-            "kernel": {1: "bi_generic", 2: "bi_inv_tiled"}.get(kernel_used, str(kernel_used)),
+            "kernel": KERNEL_NAMES.get(kernel_used, str(kernel_used)),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps,
                     "what": "sdpb_create (H2D pmf/parameter tables) + solve + sdpb_value + D2H of the period-1 "
@@ -348,7 +349,9 @@ def run_gpu(args):
     # ---- the other configurations, solved once each (plus CPU baseline), rank 0 prints ----
     configs = {}
     if not args.no_configs:
-        for name in ("c1", "c2", "c3", "c4"):
+        for name in ("c1", "c2", "c3", "c4", "c4_dedup"):
+            dedup = name.endswith("_dedup")
+            name_key, name = name, name.split("_")[0]
             sp = make_spec(S, name, world, args.states_per_gpu)
             shard = name in ("c3", "c4") and world > 1
             w = world if shard else 1
@@ -356,13 +359,14 @@ def run_gpu(args):
                 continue
             with torch.cuda.stream(stream):
                 s3 = ShardedSolve(S, torch, dist if shard else None, sp, rank if shard else 0, w, local, stream,
-                                  S.KERNEL_AUTO, False)
+                                  S.KERNEL_AUTO, dedup)
                 s3.step()  # warm
                 if shard:
                     barrier()
                 else:
                     torch.cuda.synchronize()
                 b0 = s3.solver.stats()["evals"]
+                x0 = s3.solver.stats()["evals_executed"]
                 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a0.record(stream)
                 s3.step()
@@ -370,19 +374,21 @@ def run_gpu(args):
                 torch.cuda.synchronize()
                 cms = a0.elapsed_time(a1)
                 ev = s3.solver.stats()["evals"] - b0
-                tt = torch.tensor([cms, ev], dtype=torch.float64, device=f"cuda:{local}")
+                evx = s3.solver.stats()["evals_executed"] - x0
+                tt = torch.tensor([cms, ev, evx], dtype=torch.float64, device=f"cuda:{local}")
                 if shard:
                     mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
                     sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-                    cms, ev = float(mx[0]), float(sm[1])
+                    cms, ev, evx = float(mx[0]), float(sm[1]), float(sm[2])
                 init = {"c1": [[0.0]], "c2": [[0.0]], "c3": [[0.0, 100.0]], "c4": [[0.0, 0.0, 0.0]]}[name]
                 v0 = q0 = None
                 if not shard:
                     v, q = s3.solver.value(1, init)
                     v0, q0 = float(v[0]), float(q[0])
-                configs[name] = {"solve_ms": cms, "evals": ev, "evals_per_s": ev / (cms * 1e-3), "n_gpus": w,
-                                 "kernel": {1: "bi_generic", 2: "bi_inv_tiled"}.get(s3.solver.stats()["kernel_used"]),
-                                 "V1_init": v0, "Q1_init": q0}
+                configs[name_key] = {"solve_ms": cms, "evals": ev, "evals_per_s": ev / (cms * 1e-3),
+                                     "evals_executed": evx, "n_gpus": w,
+                                     "kernel": KERNEL_NAMES.get(s3.solver.stats()["kernel_used"]),
+                                     "dedup": dedup, "V1_init": v0, "Q1_init": q0}
                 s3.close()
     if rank == 0:
         out["configs"] = configs

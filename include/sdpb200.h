@@ -158,7 +158,10 @@ typedef struct sdpb_model {
 typedef enum sdpb_kernel_choice {
     SDPB_KERNEL_AUTO = 0,     /* fastest bit-exact kernel available for the model */
     SDPB_KERNEL_GENERIC = 1,  /* always the generic per-(s,a,d) kernel */
-    SDPB_KERNEL_TILED = 2     /* shared-memory tiled kernel; error if the model has none */
+    SDPB_KERNEL_TILED = 2,    /* shared-memory kernel (tiled for lead_time 0, staged warp-per-state
+                                 for backorder lead-time models); error if the model has none */
+    SDPB_KERNEL_STAGED = 3,   /* reported in sdpb_stats.kernel_used only */
+    SDPB_KERNEL_CASH_INT = 4  /* reported only: integer-exact cash kernel (last period: generic) */
 } sdpb_kernel_choice;
 
 typedef struct sdpb_options {
@@ -189,6 +192,7 @@ typedef struct sdpb_stats {
     int32_t launches;       /* backward-induction kernel launches in the last solve */
     int32_t kernel_used;    /* sdpb_kernel_choice actually run */
     double  fp64_ops;       /* fp64 add/mul/min/max instructions the kernels executed, by construction */
+    double  evals_executed; /* = evals unless dedup folded identical states together */
 } sdpb_stats;
 
 typedef struct sdpb_handle sdpb_handle;

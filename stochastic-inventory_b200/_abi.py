@@ -24,7 +24,7 @@ REC_EXPECT, REC_SURVIVAL = 0, 1
 MIN, MAX = 0, 1
 Q_DIV, Q_LONGDIV = 0, 1
 F_CLAMP_INV, F_LOST_SALES, F_GY_MODE, F_NO_ORDER_LAST, F_CASH_LIMITED_ACTIONS = 1, 2, 4, 8, 16
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED = 0, 1, 2
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED, KERNEL_STAGED, KERNEL_CASH_INT = 0, 1, 2, 3, 4
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -69,6 +69,7 @@ class SdpbStats(C.Structure):
     _fields_ = [
         ("evals", C.c_double), ("solve_ms", C.c_double), ("kernel_ms", C.c_double),
         ("launches", C.c_int32), ("kernel_used", C.c_int32), ("fp64_ops", C.c_double),
+        ("evals_executed", C.c_double),
     ]
 
 

@@ -1,0 +1,235 @@
+// kernel_cash.cuh — backward induction for the cash-constrained family (CashConstraint.java:95-133,
+// cashSurvival.java:102-147 lambdas; CashRecursion.java:98-138 / RiskRecursion.java:66-104 loops) when
+// every cash quantity is an exact integer.  Bit-identical to bi_generic by construction.
+//
+// Conditions (checked on the host, plan_cash): unit grid step, integer price / unit cost / fixed cost /
+// overhead / cash bounds, no deposit interest, no overhead rate, no holding cost, no end-cash penalty,
+// identity quantiser (round(w*1)/1), lost sales, consecutive integer demands.  Then, for t < T,
+//     c(s,a,d) = price*min(x+a,d) - (K 1[a>0] + v a + overhead)
+// and every intermediate of the reference's expression (revenue, deposit, the running differences,
+// w + c, its clamp and Math.round) is an exactly representable integer, so
+//   * the immediate value is F_j(y) - C_a with F_j(y) = price*min(y,d_j): ONE fp64 subtract, the same
+//     for every cash level w — a thread owns R cash levels and shares it (and p_j * c) among them;
+//   * the successor's cash index is iw + (F_j - C_a) clamped, in the integer ALU: no fp64 clamp, no
+//     floor, no double->int conversion;
+//   * once d_j >= y the sale is y units whatever the demand: successor and immediate value are
+//     constant over the rest of the demand loop, so V_{t+1} is read once for all of those j.
+// Per evaluation that leaves 3 + 2/R fp64 instructions (mul, add, add) and one coalesced 8-byte
+// gather of V_{t+1} (lanes hold consecutive cash levels).  The last period (salvage, terminal
+// indicator) runs on the generic kernel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <vector>
+
+#include "dev_model.cuh"
+
+namespace sdpb {
+
+constexpr int kCashThreads = 64;
+constexpr int kCashR = 4;                             // cash levels per thread
+constexpr int kCashTile = kCashThreads * kCashR;      // cash levels per CTA
+
+struct CashPeriod {
+    bool ok = false;
+    int price = 0, v = 0, ovh = 0, d0 = 0;
+};
+
+struct CashPlan {
+    bool available = false;
+    const char* why_not = "";
+    int K = 0;
+    std::vector<CashPeriod> period;
+};
+
+struct CashArgs {
+    int t, D, pmf_off;
+    const double* Vn;
+    double* Vt;
+    int* Qt;
+    long long lo, hi;
+    int ix0;                     // first inventory row of the shard
+    int price, v, K, ovh, d0, inv_min_i;
+};
+
+template <bool SURVIVAL, bool IS_MIN>
+__global__ void __launch_bounds__(kCashThreads)
+bi_cash_int(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs a) {
+    constexpr int R = kCashR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* PP = reinterpret_cast<double2*>(smem_raw);                          // (p, p*gamma)
+    double* PRd = reinterpret_cast<double*>(smem_raw + (size_t)a.D * 16);        // price * d_j
+    int* PRi = reinterpret_cast<int*>(smem_raw + (size_t)a.D * 24);              // same, as int
+    for (int j = threadIdx.x; j < a.D; j += kCashThreads) {
+        PP[j] = make_double2(M.pmf_p[a.pmf_off + j], M.pmf_pg[a.pmf_off + j]);
+        const int pr = a.price * (a.d0 + j);
+        PRi[j] = pr;
+        PRd[j] = (double)pr;
+    }
+    __syncthreads();
+
+    const int ix = a.ix0 + blockIdx.x;
+    const int iw0 = blockIdx.y * kCashTile + threadIdx.x;
+    const double v_d = M.v_t[a.t - 1];
+    const double res = M.reserve_t[a.t - 1];
+
+    int iw[R], nA[R], arg[R];
+    double best[R];
+    bool valid[R];
+    int nAmax = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        iw[r] = iw0 + r * kCashThreads;
+        const long long idx = (long long)ix * M.nW + iw[r];
+        valid[r] = iw[r] < M.nW && idx >= a.lo && idx < a.hi;
+        iw[r] = min(iw[r], M.nW - 1);
+        const double w = (double)(M.kmin + iw[r]);
+        int n = M.max_order_idx + 1;
+        if (M.flags & SDPB_F_CASH_LIMITED_ACTIONS) {  // CashConstraint.java:96-99
+            const double bound = fmax(0.0, ((w - res) - M.reserve2) / v_d);
+            n = (int)fmin((double)M.max_order_idx, bound) + 1;
+        }
+        nA[r] = valid[r] ? n : 0;
+        nAmax = max(nAmax, nA[r]);
+        best[r] = IS_MIN ? DBL_MAX : -DBL_MAX;
+        arg[r] = kNoAction;
+    }
+
+    const int nW1 = M.nW - 1;
+    for (int ai = 0; ai < nAmax; ai++) {
+        const int yv = a.inv_min_i + ix + ai;                 // stock after ordering, as a value
+        const int CI = (ai > 0 ? a.K : 0) + a.v * ai + a.ovh;  // K 1[a>0] + v a + overhead
+        const double Cd = (double)CI;
+        const int jy = min(max(yv - a.d0, 0), a.D);          // demands d_j < y  <=>  j < jy
+        double acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = 0.0;
+
+        // ---- demand below the stock: sale = d_j, successor inventory y - d_j > 0 ----
+        for (int j = 0; j < jy; j++) {
+            const double2 pp = PP[j];
+            const int shift = PRi[j] - CI;                    // exact cash increment
+            int il = ix + ai - (a.d0 + j);                    // successor inventory index
+            il = min(il, M.nI - 1);
+            il = max(il, 0);
+            const double* __restrict__ row = a.Vn + (long long)il * M.nW;
+            double m = 0.0;
+            if (!SURVIVAL) m = pp.x * (PRd[j] - Cd);          // p_j * c(s,a,d_j)
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int k = min(max(iw[r] + shift, 0), nW1);  // clamp to [cash_min, cash_max]
+                double vn = __ldg(row + k);
+                if (SURVIVAL && M.kmin + k < 0) vn = 0.0;      // RiskRecursion.java:87-95
+                if (!SURVIVAL) acc[r] += m;                    // CashRecursion.java:117
+                acc[r] += pp.y * vn;                           // CashRecursion.java:120
+            }
+        }
+        // ---- stock-out: sale = y for every remaining demand, successor inventory 0 ----
+        if (jy < a.D) {
+            const int PYi = a.price * yv;
+            const int shift = PYi - CI;
+            int il = min(max(M.i_zero, 0), M.nI - 1);
+            if (yv < 0) il = min(max(max(ix + ai - a.d0, M.i_zero), 0), M.nI - 1);  // not reachable: inv_min >= 0
+            const double* __restrict__ row = a.Vn + (long long)il * M.nW;
+            const double inc = (double)PYi - Cd;
+            double vn[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int k = min(max(iw[r] + shift, 0), nW1);
+                vn[r] = __ldg(row + k);
+                if (SURVIVAL && M.kmin + k < 0) vn[r] = 0.0;
+            }
+            for (int j = jy; j < a.D; j++) {
+                const double2 pp = PP[j];
+                double m = 0.0;
+                if (!SURVIVAL) m = pp.x * inc;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (!SURVIVAL) acc[r] += m;
+                    acc[r] += pp.y * vn[r];
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (ai < nA[r] && (IS_MIN ? (acc[r] < best[r]) : (acc[r] > best[r]))) { best[r] = acc[r]; arg[r] = ai; }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        if (valid[r]) {
+            const long long idx = (long long)ix * M.nW + iw[r];
+            a.Vt[idx] = best[r];
+            a.Qt[idx] = arg[r] == kNoAction ? -1 : arg[r];
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+inline bool cash_is_small_int(double x, double lim = 1048576.0) { return x == std::floor(x) && std::fabs(x) < lim; }
+
+inline void plan_cash(CashPlan& P, const sdpb_model& m, const DevModel& d, const std::vector<int>& pmf_len,
+                      const std::vector<int>& pmf_off, const std::vector<int>& pdi) {
+    P.available = false;
+    P.period.assign(m.T, CashPeriod{});
+    if (m.cost_kind != SDPB_COST_CASH_DEPOSIT) { P.why_not = "only the deposit cash kind"; return; }
+    if (m.lead_time != 0) { P.why_not = "lead time"; return; }
+    if (m.step != 1.0) { P.why_not = "step != 1"; return; }
+    if (!(m.flags & SDPB_F_LOST_SALES) || !(m.flags & SDPB_F_CLAMP_INV)) { P.why_not = "needs lost sales + clamp"; return; }
+    if (m.q_mul != 1.0 || m.q_div != 1.0) { P.why_not = "quantiser is not round(w*1)/1"; return; }
+    if (m.deposit_rate != 0.0 || m.overhead_rate != 0.0 || m.penalty_cost != 0.0 || m.hold_cost != 0.0) {
+        P.why_not = "deposit rate, overhead rate, penalty and holding cost must be 0";
+        return;
+    }
+    if (!cash_is_small_int(m.fixed_cost) || !cash_is_small_int(m.cash_min) || !cash_is_small_int(m.cash_max) ||
+        !cash_is_small_int(m.inv_min) || m.inv_min < 0) { P.why_not = "non-integer parameters"; return; }
+    P.K = (int)m.fixed_cost;
+    bool any = false;
+    for (int t = 0; t + 1 < m.T; t++) {  // the last period runs on the generic kernel
+        const double price = m.price_t ? m.price_t[t] : m.price;
+        const double v = m.vari_cost_t ? m.vari_cost_t[t] : m.vari_cost;
+        const double ovh = m.overhead_t ? m.overhead_t[t] : m.overhead;
+        if (!cash_is_small_int(price, 32768) || !cash_is_small_int(v, 32768) || !cash_is_small_int(ovh) || v <= 0) continue;
+        const int* di = pdi.data() + pmf_off[t];
+        bool consec = true;
+        for (int j = 0; j < pmf_len[t]; j++) consec = consec && di[j] == di[0] + j;
+        if (!consec) continue;
+        // magnitude guard: every integer stays far inside int32
+        const double big = std::fabs(price) * (std::fabs(m.inv_max) + d.max_order_idx + std::abs(di[0]) + pmf_len[t]) +
+                           std::fabs(m.cash_min) + std::fabs(m.cash_max) + std::fabs(v) * d.max_order_idx +
+                           std::fabs(m.fixed_cost) + std::fabs(ovh);
+        if (big > 5e8) continue;
+        CashPeriod& cp = P.period[t];
+        cp.ok = true;
+        cp.price = (int)price; cp.v = (int)v; cp.ovh = (int)ovh; cp.d0 = di[0];
+        any = true;
+    }
+    if (!any) { P.why_not = "no period qualifies"; return; }
+    P.available = true;
+}
+
+// SDPB_OK, SDPB_ERR_STATE (no plan for this period: use the generic kernel) or SDPB_ERR_CUDA.
+inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& dm, int t, int D, int pmf_off,
+                       const double* Vn, double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream,
+                       double* fp64_ops, double evals) {
+    if (!P.available || t >= m.T || !P.period[t - 1].ok) return SDPB_ERR_STATE;
+    if (hi <= lo) return SDPB_OK;
+    const CashPeriod& cp = P.period[t - 1];
+    CashArgs a;
+    a.t = t; a.D = D; a.pmf_off = pmf_off; a.Vn = Vn; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
+    a.ix0 = (int)(lo / dm.nW);
+    const int ix1 = (int)((hi - 1) / dm.nW);
+    a.price = cp.price; a.v = cp.v; a.K = P.K; a.ovh = cp.ovh; a.d0 = cp.d0; a.inv_min_i = (int)m.inv_min;
+    const dim3 grid((unsigned)(ix1 - a.ix0 + 1), (unsigned)((dm.nW + kCashTile - 1) / kCashTile));
+    const size_t smem = (size_t)D * 28 + 16;
+    const bool surv = m.recursion == SDPB_REC_SURVIVAL;
+    if (surv) bi_cash_int<true, false><<<grid, kCashThreads, smem, stream>>>(dm, a);
+    else if (dm.is_min) bi_cash_int<false, true><<<grid, kCashThreads, smem, stream>>>(dm, a);
+    else bi_cash_int<false, false><<<grid, kCashThreads, smem, stream>>>(dm, a);
+    if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+    if (fp64_ops) *fp64_ops += evals * (surv ? 2.0 : 3.0 + 2.0 / kCashR);
+    return SDPB_OK;
+}
+
+}  // namespace sdpb

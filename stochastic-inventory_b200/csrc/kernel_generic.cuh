@@ -46,14 +46,17 @@ struct ActionCtx {
     long long pipe;   // successor's pipeline-slot offset
 };
 
+// `dedup`: idx addresses a VIRTUAL state (y = x + preQ, [preQ2], [cash]) with preQ folded into the
+// inventory index — lead-time models depend on (x, preQ) only through their sum, so every real
+// state with the same sum has the same value and policy (exactly, not approximately).
 template <int KIND>
-__device__ __forceinline__ StateCtx decode_state(const DevModel& M, int t, long long idx) {
+__device__ __forceinline__ StateCtx decode_state(const DevModel& M, int t, long long idx, bool dedup = false) {
     StateCtx S;
     long long r = idx;
     S.iw = 0; S.iq1 = 0; S.iq2 = 0;
     if (KIND != SDPB_COST_BACKORDER) { S.iw = (int)(r % M.nW); r /= M.nW; }
     if (M.lead >= 2) { S.iq2 = (int)(r % M.nQ); r /= M.nQ; }
-    if (M.lead >= 1) { S.iq1 = (int)(r % M.nQ); r /= M.nQ; }
+    if (M.lead >= 1 && !dedup) { S.iq1 = (int)(r % M.nQ); r /= M.nQ; }
     S.ix = (int)r;
     S.x = M.inv_min + (double)S.ix * M.step;
     S.q1 = (double)S.iq1 * M.step;
@@ -184,7 +187,8 @@ __device__ __forceinline__ long long successor(const DevModel& M, const StateCtx
     nw = nw > M.cash_max ? M.cash_max : nw;
     nw = nw < M.cash_min ? M.cash_min : nw;
     const long long kk = jround(nw * M.q_mul);
-    long long k = (M.quantiser == SDPB_Q_DIV) ? kk : kk / M.q_idiv;
+    // Java long division; q_idiv == 1 (round(w*1)/1) is the common case and needs no divide
+    long long k = (M.quantiser == SDPB_Q_DIV || M.q_idiv == 1) ? kk : kk / M.q_idiv;
     bankrupt = k < 0;  // quantised cash < 0 (q_div > 0)
     if (KIND == SDPB_COST_CASH_XR) {
         const double nwq = (M.quantiser == SDPB_Q_DIV) ? (double)kk / M.q_div : (double)k;
@@ -196,7 +200,8 @@ __device__ __forceinline__ long long successor(const DevModel& M, const StateCtx
     return il * S.strideX + A.pipe + kw;
 }
 
-template <int KIND, bool SURVIVAL, bool IS_MIN, int G>
+// DEDUP: [lo, hi) indexes virtual states and (Vt, Qt) are the virtual tables H; see expand_dedup.
+template <int KIND, bool SURVIVAL, bool IS_MIN, int G, bool DEDUP>
 __global__ void __launch_bounds__(256)
 bi_generic(const __grid_constant__ DevModel M, const int t, const int D, const int pmf_off,
            const double* __restrict__ Vn, double* __restrict__ Vt, int* __restrict__ Qt,
@@ -205,7 +210,7 @@ bi_generic(const __grid_constant__ DevModel M, const int t, const int D, const i
     const int lane = threadIdx.x % G;
     const long long idx = lo + gid;
     const bool live = idx < hi;  // dead groups still take part in the shuffles below
-    const StateCtx S = decode_state<KIND>(M, t, live ? idx : lo);
+    const StateCtx S = decode_state<KIND>(M, t, live ? idx : lo, DEDUP);
 
     const double* __restrict__ pd = M.pmf_d + pmf_off;
     const double* __restrict__ pp = M.pmf_p + pmf_off;
@@ -250,6 +255,117 @@ bi_generic(const __grid_constant__ DevModel M, const int t, const int D, const i
         Vt[idx] = best;
         Qt[idx] = besti == kNoAction ? -1 : besti;
     }
+}
+
+// Lead-time backorder models, one warp per state: everything that depends on the demand alone —
+// (p_j, p_j*gamma), the holding+penalty term at level y - d_j and the successor's row offset — is
+// tabulated per warp in shared memory once, so an evaluation is LDS + 5 fp64 instructions + the
+// V_{t+1} gather (unit-stride across lanes: the successor's last pipeline slot is the action).
+// Each lane carries 4 actions at a time for instruction-level parallelism.
+// ((fv + hold) + pen) == fv + (hold + pen) bit for bit because one of hold/pen is always +0.
+struct StagedRow { double L; long long row; };
+
+template <bool IS_MIN, bool DEDUP>
+__global__ void __launch_bounds__(256)
+bi_backorder_staged(const __grid_constant__ DevModel M, const int t, const int D, const int pmf_off,
+                    const double* __restrict__ Vn, double* __restrict__ Vt, int* __restrict__ Qt,
+                    const long long lo, const long long hi) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* PP = reinterpret_cast<double2*>(smem_raw);                       // [D] (p, p*gamma)
+    StagedRow* LR = reinterpret_cast<StagedRow*>(smem_raw + (size_t)D * 16);  // [8 warps][D]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long idx = lo + (long long)blockIdx.x * 8 + warp;
+    const bool live = idx < hi;
+    const StateCtx S = decode_state<SDPB_COST_BACKORDER>(M, t, live ? idx : lo, DEDUP);
+    for (int j = threadIdx.x; j < D; j += 256)
+        PP[j] = make_double2(M.pmf_p[pmf_off + j], M.pmf_pg[pmf_off + j]);
+    StagedRow* my = LR + (size_t)warp * D;
+    const double stock = S.x + S.q1;  // Leadtime.java:64,75
+    const int iy = S.ix + S.iq1;
+    for (int j = lane; j < D; j += 32) {
+        const double lvl = stock - M.pmf_d[pmf_off + j];
+        const double hold = M.h * fmax(lvl, 0.0);
+        const double pen = M.pen * fmax(-lvl, 0.0);
+        int il = iy - M.pmf_di[pmf_off + j];
+        if (S.lost) il = max(il, M.i_zero);
+        il = min(il, M.nI - 1);
+        il = max(il, 0);
+        my[j].L = hold + pen;
+        my[j].row = il * S.strideX;
+    }
+    __syncthreads();
+
+    double best = IS_MIN ? DBL_MAX : -DBL_MAX;
+    int besti = kNoAction;
+    const long long pipe_q2 = (M.lead == 2) ? (long long)S.iq2 * M.nQ : 0;
+    for (int base = 0; base < S.nA; base += 128) {
+        double fv[4], acc[4];
+        long long pipe[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int i = min(base + 32 * r + lane, S.nA - 1);  // out-of-range lanes recompute a valid action
+            const double a = (double)i * M.step;
+            fv[r] = (a > 0.0 ? M.K : 0.0) + S.v * a;
+            pipe[r] = pipe_q2 + i;
+            acc[r] = 0.0;
+        }
+        if (S.last) {
+            for (int j = 0; j < D; j++) {
+                const double2 pp = PP[j];
+                const double L = my[j].L;
+#pragma unroll
+                for (int r = 0; r < 4; r++) acc[r] += pp.x * (fv[r] + L);
+            }
+        } else {
+#pragma unroll 2
+            for (int j = 0; j < D; j++) {
+                const double2 pp = PP[j];
+                const StagedRow lr = my[j];
+                const double* __restrict__ row = Vn + lr.row;
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const double vn = __ldg(row + pipe[r]);
+                    acc[r] += pp.x * (fv[r] + lr.L);
+                    acc[r] += pp.y * vn;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int i = base + 32 * r + lane;
+            if (i < S.nA && (IS_MIN ? (acc[r] < best) : (acc[r] > best))) { best = acc[r]; besti = i; }
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, s);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, s);
+        if (better<IS_MIN>(ov, oi, best, besti)) { best = ov; besti = oi; }
+    }
+    if (live && lane == 0) {
+        Vt[idx] = best;
+        Qt[idx] = besti == kNoAction ? -1 : besti;
+    }
+}
+
+// Broadcast the virtual tables H(y, [preQ2], [cash]) to every real state (x, preQ, ...) of [lo, hi).
+template <int KIND>
+__global__ void __launch_bounds__(256)
+expand_dedup(const __grid_constant__ DevModel M, const double* __restrict__ Hv, const int* __restrict__ Ha,
+             double* __restrict__ Vt, int* __restrict__ Qt, const long long lo, const long long hi) {
+    const long long idx = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= hi) return;
+    long long r = idx;
+    int iw = 0, iq2 = 0;
+    if (KIND != SDPB_COST_BACKORDER) { iw = (int)(r % M.nW); r /= M.nW; }
+    if (M.lead >= 2) { iq2 = (int)(r % M.nQ); r /= M.nQ; }
+    const int iq1 = (int)(r % M.nQ);
+    const long long iy = r / M.nQ + iq1;
+    long long v = iy;
+    if (M.lead >= 2) v = v * M.nQ + iq2;
+    if (KIND != SDPB_COST_BACKORDER) v = v * M.nW + iw;
+    Vt[idx] = Hv[v];
+    Qt[idx] = Ha[v];
 }
 
 // One thread per (state of period t): if the state is reached, mark every successor in the

@@ -14,6 +14,7 @@
 #include "dev_model.cuh"
 #include "kernel_generic.cuh"
 #include "kernel_tiled.cuh"
+#include "kernel_cash.cuh"
 #include "microbench.cuh"
 
 using namespace sdpb;
@@ -62,6 +63,11 @@ struct sdpb_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     sdpb_stats stats{};
     TiledPlan tiled{};
+    CashPlan cash{};
+    bool dedup = false;        // lead-time models: fold (x, preQ) -> x + preQ
+    long long vS = 0;          // virtual states per period
+    double* dHv = nullptr;     // [vS] virtual value table of the period being solved
+    int* dHa = nullptr;        // [vS] virtual policy table
     std::string err;
 };
 
@@ -188,37 +194,41 @@ double count_evals_period(const sdpb_handle* h, int t) {
     return total * D;
 }
 
-template <int KIND, bool SURV, bool IS_MIN, int G>
-void launch_generic(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt) {
-    const long long n = h->hi - h->lo;
+// Launch the general kernel over index range [lo, hi) of the real grid, or (DEDUP) of the virtual grid.
+template <int KIND, bool SURV, bool IS_MIN, int G, bool DEDUP>
+void launch_generic(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt, long long lo, long long hi) {
+    const long long n = hi - lo;
+    if (n <= 0) return;
     const int per_block = 256 / G;
     const long long blocks = (n + per_block - 1) / per_block;
-    bi_generic<KIND, SURV, IS_MIN, G><<<(unsigned)blocks, 256, 0, h->stream>>>(
-        h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, h->lo, h->hi);
+    bi_generic<KIND, SURV, IS_MIN, G, DEDUP><<<(unsigned)blocks, 256, 0, h->stream>>>(
+        h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi);
 }
 
-int dispatch_generic(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt) {
+template <bool DEDUP>
+int dispatch_generic_d(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt, long long lo, long long hi) {
     const sdpb_model& m = h->m;
     const bool surv = m.recursion == SDPB_REC_SURVIVAL;
     const bool mn = h->dm.is_min != 0;
     switch (m.cost_kind) {
     case SDPB_COST_BACKORDER:
-        if (mn) launch_generic<SDPB_COST_BACKORDER, false, true, 32>(h, t, Vn, Vt, Qt);
-        else launch_generic<SDPB_COST_BACKORDER, false, false, 32>(h, t, Vn, Vt, Qt);
+        if (mn) launch_generic<SDPB_COST_BACKORDER, false, true, 32, DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
+        else launch_generic<SDPB_COST_BACKORDER, false, false, 32, DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
         break;
     case SDPB_COST_CASH_DEPOSIT:
-        if (surv) launch_generic<SDPB_COST_CASH_DEPOSIT, true, false, 1>(h, t, Vn, Vt, Qt);
-        else if (mn) launch_generic<SDPB_COST_CASH_DEPOSIT, false, true, 1>(h, t, Vn, Vt, Qt);
-        else launch_generic<SDPB_COST_CASH_DEPOSIT, false, false, 1>(h, t, Vn, Vt, Qt);
+        if (surv) launch_generic<SDPB_COST_CASH_DEPOSIT, true, false, 1, DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
+        else if (mn) launch_generic<SDPB_COST_CASH_DEPOSIT, false, true, 1, DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
+        else launch_generic<SDPB_COST_CASH_DEPOSIT, false, false, 1, DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
         break;
     case SDPB_COST_CASH_OVERDRAFT:
-        if (surv) launch_generic<SDPB_COST_CASH_OVERDRAFT, true, false, 1>(h, t, Vn, Vt, Qt);
-        else if (mn) launch_generic<SDPB_COST_CASH_OVERDRAFT, false, true, 1>(h, t, Vn, Vt, Qt);
-        else launch_generic<SDPB_COST_CASH_OVERDRAFT, false, false, 1>(h, t, Vn, Vt, Qt);
+        if (surv) launch_generic<SDPB_COST_CASH_OVERDRAFT, true, false, 1, DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
+        else if (mn) launch_generic<SDPB_COST_CASH_OVERDRAFT, false, true, 1, DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
+        else launch_generic<SDPB_COST_CASH_OVERDRAFT, false, false, 1, DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
         break;
     case SDPB_COST_CASH_XR:
-        if (mn) launch_generic<SDPB_COST_CASH_XR, false, true, 1>(h, t, Vn, Vt, Qt);
-        else launch_generic<SDPB_COST_CASH_XR, false, false, 1>(h, t, Vn, Vt, Qt);
+        if (DEDUP) { h->err = "XR kind has no lead time to fold"; return SDPB_ERR_ARG; }
+        if (mn) launch_generic<SDPB_COST_CASH_XR, false, true, 1, false>(h, t, Vn, Vt, Qt, lo, hi);
+        else launch_generic<SDPB_COST_CASH_XR, false, false, 1, false>(h, t, Vn, Vt, Qt, lo, hi);
         break;
     default:
         h->err = "bad cost_kind";
@@ -227,11 +237,77 @@ int dispatch_generic(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Q
     return SDPB_OK;
 }
 
+// Staged warp-per-state kernel for backorder lead-time models.
+template <bool DEDUP>
+int launch_staged(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt, long long lo, long long hi) {
+    const long long n = hi - lo;
+    if (n <= 0) return SDPB_OK;
+    const int D = h->pmf_len[t - 1];
+    const size_t smem = (size_t)D * 16 + (size_t)8 * D * sizeof(StagedRow);
+    const long long blocks = (n + 7) / 8;
+    cudaError_t e = cudaSuccess;
+    if (h->dm.is_min) {
+        auto k = bi_backorder_staged<true, DEDUP>;
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) k<<<(unsigned)blocks, 256, smem, h->stream>>>(h->dm, t, D, h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi);
+    } else {
+        auto k = bi_backorder_staged<false, DEDUP>;
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) k<<<(unsigned)blocks, 256, smem, h->stream>>>(h->dm, t, D, h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi);
+    }
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return SDPB_ERR_CUDA; }
+    return SDPB_OK;
+}
+
+bool staged_ok(const sdpb_handle* h, int t) {
+    const size_t smem = (size_t)h->pmf_len[t - 1] * (16 + 8 * sizeof(StagedRow));
+    return h->m.cost_kind == SDPB_COST_BACKORDER && h->m.lead_time >= 1 && smem <= 200 * 1024;
+}
+
+// Solve [lo, hi) of the real grid (or of the virtual grid when DEDUP) with the best kernel allowed.
+template <bool DEDUP>
+int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt, long long lo, long long hi) {
+    if (h->opt.kernel != SDPB_KERNEL_GENERIC && staged_ok(h, t)) {
+        h->stats.kernel_used = SDPB_KERNEL_STAGED;
+        // per evaluation: add, mul, add (+ mul, add when a continuation exists)
+        h->stats.fp64_ops += (double)(hi - lo) * (h->m.max_order_idx + 1) * h->pmf_len[t - 1] * (t == h->m.T ? 3.0 : 5.0);
+        return launch_staged<DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
+    }
+    if (h->stats.kernel_used == 0) h->stats.kernel_used = SDPB_KERNEL_GENERIC;
+    return dispatch_generic_d<DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
+}
+
+template <int KIND>
+void launch_expand(sdpb_handle* h, double* Vt, int* Qt) {
+    const long long n = h->hi - h->lo;
+    if (n <= 0) return;
+    expand_dedup<KIND><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->dm, h->dHv, h->dHa, Vt, Qt, h->lo, h->hi);
+}
+
+// Evaluations actually executed for one period in dedup mode (virtual states only).
+double count_evals_virtual(const sdpb_handle* h, int t);
+
 template <int KIND, bool SURV>
 void launch_reach(sdpb_handle* h, int t) {
     const long long blocks = (h->S + 255) / 256;
     reach_forward<KIND, SURV><<<(unsigned)blocks, 256, 0, h->stream>>>(
         h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], h->dMask[t - 1], h->dMask[t]);
+}
+
+double count_evals_virtual(const sdpb_handle* h, int t) {
+    const sdpb_model& m = h->m;
+    const DevModel& d = h->dm;
+    const double D = h->pmf_len[t - 1];
+    if ((m.flags & SDPB_F_NO_ORDER_LAST) && t == m.T) return (double)h->vS * D;
+    if (!(m.flags & SDPB_F_CASH_LIMITED_ACTIONS)) return (double)h->vS * (m.max_order_idx + 1) * D;
+    const double v = m.vari_cost_t ? m.vari_cost_t[t - 1] : m.vari_cost;
+    const double res = m.reserve_t ? m.reserve_t[t - 1] : 0.0;
+    double per_w = 0;
+    for (int iw = 0; iw < d.nW; iw++) {
+        const double w = cash_of_k(h, d.kmin + iw);
+        per_w += (int)std::min((double)m.max_order_idx, std::max(0.0, ((w - res) - m.reserve2) / v)) + 1;
+    }
+    return per_w * (double)(h->vS / d.nW) * D;
 }
 
 __global__ void gather_vq(const long long* __restrict__ idx, int n, const double* __restrict__ V,
@@ -246,21 +322,45 @@ int solve_period(sdpb_handle* h, int t) {
     if (t < m.T && !h->solved[t]) { h->err = "period t+1 not solved yet"; return SDPB_ERR_STATE; }
     const double* Vn = t < m.T ? h->dV[t] : nullptr;
     int rc = SDPB_ERR_STATE;
+    const int D = h->pmf_len[t - 1];
+    if (h->dedup) {
+        // lead-time models: solve each distinct (x + preQ, ...) once, then broadcast (exact)
+        rc = run_period_kernel<true>(h, t, Vn, h->dHv, h->dHa, 0, h->vS);
+        if (rc != SDPB_OK) return rc;
+        switch (m.cost_kind) {
+        case SDPB_COST_BACKORDER: launch_expand<SDPB_COST_BACKORDER>(h, h->dV[t - 1], h->dQ[t - 1]); break;
+        case SDPB_COST_CASH_DEPOSIT: launch_expand<SDPB_COST_CASH_DEPOSIT>(h, h->dV[t - 1], h->dQ[t - 1]); break;
+        default: launch_expand<SDPB_COST_CASH_OVERDRAFT>(h, h->dV[t - 1], h->dQ[t - 1]); break;
+        }
+        CU(cudaGetLastError());
+        h->solved[t - 1] = 1;
+        h->stats.launches += 2;
+        h->stats.evals += count_evals_period(h, t);
+        h->stats.evals_executed += count_evals_virtual(h, t);
+        (void)D;
+        return SDPB_OK;
+    }
     if (h->tiled.available && h->opt.kernel != SDPB_KERNEL_GENERIC) {
         rc = launch_tiled(h->tiled, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, h->dV[t - 1],
                           h->dQ[t - 1], h->lo, h->hi, h->stream, &h->stats.fp64_ops);
         if (rc == SDPB_OK) h->stats.kernel_used = SDPB_KERNEL_TILED;
         else if (rc != SDPB_ERR_STATE) { h->err = "tiled kernel launch failed"; return rc; }
     }
-    if (rc == SDPB_ERR_STATE) {  // no tiled plan for this model / period
-        rc = dispatch_generic(h, t, Vn, h->dV[t - 1], h->dQ[t - 1]);
-        if (h->stats.kernel_used != SDPB_KERNEL_TILED) h->stats.kernel_used = SDPB_KERNEL_GENERIC;
+    if (rc == SDPB_ERR_STATE && h->opt.kernel != SDPB_KERNEL_GENERIC) {  // integer cash models
+        rc = launch_cash(h->cash, m, h->dm, t, D, h->pmf_off[t - 1], Vn, h->dV[t - 1], h->dQ[t - 1], h->lo, h->hi,
+                         h->stream, &h->stats.fp64_ops, count_evals_period(h, t));
+        if (rc == SDPB_OK) h->stats.kernel_used = SDPB_KERNEL_CASH_INT;
+        else if (rc != SDPB_ERR_STATE) { h->err = "cash kernel launch failed"; return rc; }
     }
+    if (rc == SDPB_ERR_STATE)  // no specialised plan for this model / period
+        rc = run_period_kernel<false>(h, t, Vn, h->dV[t - 1], h->dQ[t - 1], h->lo, h->hi);
     if (rc != SDPB_OK) return rc;
     CU(cudaGetLastError());
     h->solved[t - 1] = 1;
     h->stats.launches++;
-    h->stats.evals += count_evals_period(h, t);
+    const double ev = count_evals_period(h, t);
+    h->stats.evals += ev;
+    h->stats.evals_executed += ev;
     return SDPB_OK;
 }
 
@@ -468,10 +568,27 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         h->dQ[t] = (int*)p;
     }
 
+    // ---- exact folding of lead-time states (opt-in) ----
+    if (h->opt.dedup && m->lead_time >= 1) {
+        h->dedup = true;
+        h->vS = (long long)(d.nI + d.nQ - 1) * (m->lead_time >= 2 ? d.nQ : 1) * d.nW;
+        void* p = nullptr;
+        if (cudaMalloc(&p, (size_t)h->vS * sizeof(double)) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "cudaMalloc of the folded value table failed");
+        h->dev_allocs.push_back(p);
+        h->dHv = (double*)p;
+        if (cudaMalloc(&p, (size_t)h->vS * sizeof(int)) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "cudaMalloc of the folded policy table failed");
+        h->dev_allocs.push_back(p);
+        h->dHa = (int*)p;
+    }
+
     // ---- kernel plan ----
     plan_tiled(h->tiled, h->m, h->dm, h->pmf_len, h->pmf_off, pdi, h->opt.dedup != 0, prop);
-    if (h->opt.kernel == SDPB_KERNEL_TILED && !h->tiled.available)
-        return fail_create(h, SDPB_ERR_ARG, std::string("no tiled kernel for this model: ") + h->tiled.why_not);
+    plan_cash(h->cash, h->m, h->dm, h->pmf_len, h->pmf_off, pdi);
+    if (h->opt.kernel == SDPB_KERNEL_TILED && !h->tiled.available &&
+        !(m->cost_kind == SDPB_COST_BACKORDER && m->lead_time >= 1) && !h->cash.available)
+        return fail_create(h, SDPB_ERR_ARG, std::string("no shared-memory kernel for this model: ") + h->tiled.why_not);
     *out = h;
     return SDPB_OK;
 }

@@ -112,4 +112,5 @@ class Solver:
         s = A.SdpbStats()
         self._check(self.lib.sdpb_stats_get(self.h, C.byref(s)))
         return {"evals": s.evals, "solve_ms": s.solve_ms, "kernel_ms": s.kernel_ms,
-                "launches": s.launches, "kernel_used": s.kernel_used, "fp64_ops": s.fp64_ops}
+                "launches": s.launches, "kernel_used": s.kernel_used, "fp64_ops": s.fp64_ops,
+                "evals_executed": s.evals_executed}

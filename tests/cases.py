@@ -82,6 +82,21 @@ def case_C_rich():
                                    name="C_rich"), [[0.0, 20.0], [2.0, 5.0]]
 
 
+def case_C_int():
+    # CashConstraint.java:44-133 with the integer cash grid of CashConstraintTesting.java:146
+    return S.cash_constraint_model(pmf([5, 6, 5, 4]), price=10, vari_cost=1, salvage=0.5, max_order=14,
+                                   inv_min=0, inv_max=25, cash_min=0, cash_max=260, quantiser=A.Q_LONGDIV,
+                                   q_mul=1.0, q_div=1.0, name="C_int"), [[0.0, 12.0]]
+
+
+def case_C_int_K():
+    # integer fixed cost / overhead / unit cost 2, negative cash allowed, discounting, inventory from 2
+    return S.cash_constraint_model(pmf([4, 6, 5]), price=7, vari_cost=2, fixed_cost=3, salvage=1.0, overhead=2,
+                                   max_order=11, inv_min=2, inv_max=19, cash_min=-15, cash_max=140,
+                                   quantiser=A.Q_DIV, q_mul=1.0, q_div=1.0, gamma=0.9,
+                                   name="C_int_K"), [[2.0, 20.0], [4.0, -3.0]]
+
+
 def case_D_small():
     return S.cash_overdraft_model(pmf([6, 6, 6]), price=10, vari_cost=1, overhead_t=[20, 20, 20],
                                   od_limit=30, max_order=15, inv_min=0, inv_max=25, cash_min=-60,
@@ -118,7 +133,7 @@ def case_XR_small():
 
 
 ALL = [case_A_small, case_A_max, case_A_gy, case_A_twopoint, case_A_halfstep, case_B1_ref, case_B1_fixed,
-       case_B2_small, case_C_small, case_C_rich, case_D_small, case_D_rich, case_E_small, case_F_small,
+       case_B2_small, case_C_small, case_C_rich, case_C_int, case_C_int_K, case_D_small, case_D_rich, case_E_small, case_F_small,
        case_XR_small]
 
 

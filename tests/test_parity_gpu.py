@@ -46,6 +46,40 @@ def test_auto_kernel_whole_grid(case, S, oracle):
     assert s.stats()["evals"] == evals
 
 
+LEAD_CASES = [cases.case_B1_ref, cases.case_B1_fixed, cases.case_B2_small, cases.case_E_small]
+
+
+@pytest.mark.parametrize("case", LEAD_CASES, ids=lambda f: f.__name__[5:])
+@pytest.mark.parametrize("kernel", ["auto", "generic"])
+def test_dedup_whole_grid(case, kernel, S, oracle):
+    """Lead-time models depend on (x, preQ) only through x + preQ; folding those states is exact."""
+    spec, init = case()
+    Vo, Qo, evals, _ = oracle.dense(spec)
+    k = S.KERNEL_AUTO if kernel == "auto" else S.KERNEL_GENERIC
+    s, V, Q = _solve_all(S, spec, dedup=True, kernel=k)
+    assert np.array_equal(V, Vo)
+    assert np.array_equal(Q, Qo)
+    st = s.stats()
+    assert st["evals"] == evals and 0 < st["evals_executed"] < evals
+
+
+def test_integer_cash_kernel_is_used(S):
+    for case in (cases.case_C_int, cases.case_C_int_K, cases.case_F_small):
+        spec, _ = case()
+        assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_CASH_INT, spec.name
+    for case in (cases.case_C_small, cases.case_C_rich, cases.case_D_small):
+        spec, _ = case()
+        assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_GENERIC, spec.name
+
+
+def test_staged_kernel_is_used_for_leadtime(S):
+    spec, _ = cases.case_B2_small()
+    assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_STAGED
+    assert S.Solver(spec, kernel=S.KERNEL_GENERIC).solve().stats()["kernel_used"] == S.KERNEL_GENERIC
+    spec, _ = cases.case_A_small()
+    assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_TILED
+
+
 @pytest.mark.parametrize("name", cases.GOLDEN)
 def test_against_golden_fixtures(name, S):
     spec, init, g = cases.load_golden(name)
@@ -207,8 +241,13 @@ def test_config_c2_full(S, oracle):
 def test_config_c3_sampled(S, oracle):
     spec = S.configs.c3(T=3)          # full 501 x 2001 grid, 3 of the 12 periods
     s = S.Solver(spec).solve()
-    assert s.n_states == 1002501
+    assert s.n_states == 1002501 and s.stats()["kernel_used"] == S.KERNEL_CASH_INT
     _sample_check(S, oracle, spec, s, n=24)
+    g = S.Solver(spec, kernel=S.KERNEL_GENERIC).solve()
+    for t in (1, 2, 3):
+        Va, Qa = s.period_tables(t)
+        Vg, Qg = g.period_tables(t)
+        assert np.array_equal(Va, Vg) and np.array_equal(Qa, Qg)
 
 
 def test_config_c4_sampled(S, oracle):
@@ -217,9 +256,14 @@ def test_config_c4_sampled(S, oracle):
     assert s.n_states == 10211201
     _sample_check(S, oracle, spec, s, n=64)
     # V(x, q1, q2) depends on (x, q1) only through x + q1: an exact structural identity
-    V, _ = s.period_tables(1)
-    V = V.reshape(1001, 101, 101)
-    assert np.array_equal(V[100, 7, :], V[107, 0, :]) and np.array_equal(V[500, 50, :], V[520, 30, :])
+    V, Q = s.period_tables(1)
+    V3 = V.reshape(1001, 101, 101)
+    assert np.array_equal(V3[100, 7, :], V3[107, 0, :]) and np.array_equal(V3[500, 50, :], V3[520, 30, :])
+    # the folded solve and the generic kernel give the same tables as the staged brute-force kernel
+    for kw in ({"dedup": True}, {"kernel": S.KERNEL_GENERIC}):
+        d = S.Solver(spec, **kw).solve()
+        Vd, Qd = d.period_tables(1)
+        assert np.array_equal(Vd, V) and np.array_equal(Qd, Q)
 
 
 def test_config_c5_sampled(S, oracle):
