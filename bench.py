@@ -29,7 +29,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-KERNEL_NAMES = {1: "bi_generic", 2: "bi_inv_tiled", 3: "bi_backorder_staged", 4: "bi_cash_int"}
+KERNEL_NAMES = {1: "bi_generic", 2: "bi_inv_tiled", 3: "bi_backorder_staged", 4: "bi_cash_int", 5: "bi_inv_tiled2"}
 METRIC = "state-action-demand evaluations/s (fp64), full-horizon SDP solve"
 UNIT = "evals/s"
 
@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--states-per-gpu", type=int, default=10_000_000, help="C5 only")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tiled"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tiled", "tiled2"])
     ap.add_argument("--dedup", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the one-shot C1-C4 solves")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -209,6 +209,19 @@ def time_oracle_fixed(S, spec, n_states):
 
 
 # ---- GPU arm ----------------------------------------------------------------------------------
+def per_step_counts(sh, sync):
+    """(evals, evals_executed, fp64_ops) of ONE step.  Unsharded handles reset their counters at every
+    solve; sharded ones (stepped period by period) accumulate, so take a difference there."""
+    a = sh.solver.stats()
+    sh.step()
+    sync()
+    b = sh.solver.stats()
+    if sh.world == 1:
+        return b["evals"], b["evals_executed"], b["fp64_ops"], b["kernel_used"]
+    return (b["evals"] - a["evals"], b["evals_executed"] - a["evals_executed"], b["fp64_ops"] - a["fp64_ops"],
+            b["kernel_used"])
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -230,7 +243,8 @@ def run_gpu(args):
     def ShardedSolve(S_, torch_, dist_, spec_, rank_, world_, device_, stream_, kernel_, dedup_):
         return par.ShardedSolve(S_.Solver, torch_, dist_, spec_, rank_, world_, device_, stream_, kernel_, dedup_)
 
-    kernel = {"auto": S.KERNEL_AUTO, "generic": S.KERNEL_GENERIC, "tiled": S.KERNEL_TILED}[args.kernel]
+    kernel = {"auto": S.KERNEL_AUTO, "generic": S.KERNEL_GENERIC, "tiled": S.KERNEL_TILED,
+              "tiled2": S.KERNEL_TILED2}[args.kernel]
     spec = make_spec(S, args.workload, world, args.states_per_gpu)
     stream = torch.cuda.Stream(device=local)
 
@@ -243,11 +257,10 @@ def run_gpu(args):
         sh = ShardedSolve(S, torch, dist, spec, rank, world, local, stream, kernel, args.dedup)
         # evaluations per step, whole job (exact for state-independent action sets; cash-limited
         # workloads take the library's own count)
-        for _ in range(args.warmup):
+        for _ in range(max(0, args.warmup - 1)):
             sh.step()
         barrier()
-        ev_local_before = sh.solver.stats()["evals"]
-        fp_before = sh.solver.stats()["fp64_ops"]
+        ev_step, evx_step, fp_step, kernel_used = per_step_counts(sh, barrier)  # the last warm-up step
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
@@ -260,9 +273,8 @@ def run_gpu(args):
         barrier()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else None
-        st = sh.solver.stats()
-        ev_local = st["evals"] - ev_local_before
-        fp_local = st["fp64_ops"] - fp_before
+        ev_local = ev_step * args.steps
+        fp_local = fp_step * args.steps
         t = torch.tensor([ms, ev_local, fp_local], dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:
             tmax = t.clone()
@@ -272,7 +284,6 @@ def run_gpu(args):
             ms, ev_total, fp_total = float(tmax[0]), float(tsum[1]), float(tsum[2])
         else:
             ev_total, fp_total = ev_local, fp_local
-        kernel_used = st["kernel_used"]
         value = ev_total / (ms * 1e-3)
 
         # ---- e2e: through the C-ABI with host buffers; H2D of the descriptor tables and D2H of the
@@ -281,9 +292,14 @@ def run_gpu(args):
         barrier()
         t0 = time.perf_counter()
         d2h = h2d = 0
+        phases = {"create_s": 0.0, "solve_s": 0.0, "fetch_s": 0.0, "destroy_s": 0.0}
         for _ in range(e2e_steps):
+            p0 = time.perf_counter()
             s2 = ShardedSolve(S, torch, dist, spec, rank, world, local, stream, kernel, args.dedup)
+            p1 = time.perf_counter()
             s2.step()
+            s2.solver.sync()
+            p2 = time.perf_counter()
             if world == 1:
                 v1, q1 = s2.solver.value(1, [[0.0] * s2.solver.ndim] if args.workload != "c3" else [[0.0, 100.0]])
                 V1, Q1 = s2.solver.period_tables(1)
@@ -299,7 +315,11 @@ def run_gpu(args):
                 d2h = nloc * 12
             npmf = sum(len(r) for r in spec.pmf)
             h2d = npmf * 28 + spec.T * 32
+            p3 = time.perf_counter()
             s2.close()
+            p4 = time.perf_counter()
+            for k, v in zip(phases, (p1 - p0, p2 - p1, p3 - p2, p4 - p3)):
+                phases[k] += v / e2e_steps
         barrier()
         e2e_s = time.perf_counter() - t0
         e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
@@ -326,7 +346,7 @@ def run_gpu(args):
             "evals_per_step": ev_total / args.steps,
             "kernel": KERNEL_NAMES.get(kernel_used, str(kernel_used)),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps,
+                    "steps": e2e_steps, "phases_s_per_step": phases,
                     "what": "sdpb_create (H2D pmf/parameter tables) + solve + sdpb_value + D2H of the period-1 "
                             "value and policy tables + sdpb_destroy, wall clock"},
             "gpu_launches": args.steps * spec.T * world,
@@ -360,21 +380,18 @@ def run_gpu(args):
             with torch.cuda.stream(stream):
                 s3 = ShardedSolve(S, torch, dist if shard else None, sp, rank if shard else 0, w, local, stream,
                                   S.KERNEL_AUTO, dedup)
-                s3.step()  # warm
-                if shard:
-                    barrier()
-                else:
-                    torch.cuda.synchronize()
-                b0 = s3.solver.stats()["evals"]
-                x0 = s3.solver.stats()["evals_executed"]
+                csync = barrier if shard else torch.cuda.synchronize
+                s3.step()  # warm (plain launches)
+                csync()
+                ev, evx, _, _ = per_step_counts(s3, csync)  # second solve: captured as a CUDA graph when unsharded
+                reps = 5 if name in ("c1", "c2") else 1
                 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a0.record(stream)
-                s3.step()
+                for _ in range(reps):
+                    s3.step()
                 a1.record(stream)
                 torch.cuda.synchronize()
-                cms = a0.elapsed_time(a1)
-                ev = s3.solver.stats()["evals"] - b0
-                evx = s3.solver.stats()["evals_executed"] - x0
+                cms = a0.elapsed_time(a1) / reps
                 tt = torch.tensor([cms, ev, evx], dtype=torch.float64, device=f"cuda:{local}")
                 if shard:
                     mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)

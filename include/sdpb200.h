@@ -161,7 +161,9 @@ typedef enum sdpb_kernel_choice {
     SDPB_KERNEL_TILED = 2,    /* shared-memory kernel (tiled for lead_time 0, staged warp-per-state
                                  for backorder lead-time models); error if the model has none */
     SDPB_KERNEL_STAGED = 3,   /* reported in sdpb_stats.kernel_used only */
-    SDPB_KERNEL_CASH_INT = 4  /* reported only: integer-exact cash kernel (last period: generic) */
+    SDPB_KERNEL_CASH_INT = 4, /* reported only: integer-exact cash kernel (last period: generic) */
+    SDPB_KERNEL_TILED2 = 5    /* 2-D register-tile variant of the tiled kernel: chosen automatically for
+                                 large grids; as a request it forces the variant wherever it applies */
 } sdpb_kernel_choice;
 
 typedef struct sdpb_options {
@@ -212,6 +214,10 @@ int sdpb_grid_info(const sdpb_handle* h, sdpb_grid* g);
 
 /* Backward induction over periods T..1 for this handle's shard (whole grid when unsharded). */
 int sdpb_solve(sdpb_handle* h);
+/* sdpb_solve without the final synchronisation: every period is enqueued on the handle's stream and the
+ * call returns.  From the second solve of a handle on, the T launches are replayed as one CUDA graph
+ * (the per-period launch latency dominates small grids such as C1/C2). */
+int sdpb_solve_async(sdpb_handle* h);
 /* One period (1-based), asynchronous on the handle's stream.  For a sharded grid the caller
  * all-gathers the V_t device buffer (sdpb_device_tables) across ranks before period t-1. */
 int sdpb_solve_period_async(sdpb_handle* h, int period);

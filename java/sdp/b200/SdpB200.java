@@ -1,0 +1,81 @@
+package sdp.b200;
+
+import java.lang.foreign.*;
+import java.lang.invoke.MethodHandle;
+
+import static java.lang.foreign.ValueLayout.*;
+
+/**
+ * Panama FFM (java.lang.foreign, final in JDK 22) binding of include/sdpb200.h.
+ *
+ * NOT COMPILED OR RUN in the build image (no JDK there); written against the header so that a
+ * maintainer with JDK >= 22 can drop it next to src/sdp/inventory/Recursion.java.  The Python ctypes
+ * binding (stochastic-inventory_b200/_abi.py) is the one the tests exercise; both mirror the same
+ * struct layouts, and sdpb_sizeof_model()/sdpb_sizeof_options() let either verify them at load time.
+ */
+public final class SdpB200 {
+    public static final int COST_BACKORDER = 0, COST_CASH_DEPOSIT = 1, COST_CASH_OVERDRAFT = 2, COST_CASH_XR = 3;
+    public static final int REC_EXPECT = 0, REC_SURVIVAL = 1;
+    public static final int MIN = 0, MAX = 1;
+    public static final int Q_DIV = 0, Q_LONGDIV = 1;
+    public static final int F_CLAMP_INV = 1, F_LOST_SALES = 2, F_GY_MODE = 4, F_NO_ORDER_LAST = 8,
+            F_CASH_LIMITED_ACTIONS = 16;
+
+    /** struct sdpb_model, field for field (include/sdpb200.h). */
+    public static final StructLayout MODEL = MemoryLayout.structLayout(
+            JAVA_INT.withName("struct_size"), JAVA_INT.withName("cost_kind"), JAVA_INT.withName("recursion"),
+            JAVA_INT.withName("direction"), JAVA_INT.withName("T"), JAVA_INT.withName("lead_time"),
+            JAVA_INT.withName("flags"), JAVA_INT.withName("max_order_idx"), JAVA_DOUBLE.withName("gamma"),
+            ADDRESS.withName("pmf_len"), ADDRESS.withName("pmf_d"), ADDRESS.withName("pmf_p"),
+            JAVA_DOUBLE.withName("inv_min"), JAVA_DOUBLE.withName("inv_max"), JAVA_DOUBLE.withName("step"),
+            JAVA_DOUBLE.withName("cash_min"), JAVA_DOUBLE.withName("cash_max"),
+            JAVA_INT.withName("quantiser"), JAVA_INT.withName("reserved0"),
+            JAVA_DOUBLE.withName("q_mul"), JAVA_DOUBLE.withName("q_div"),
+            JAVA_DOUBLE.withName("fixed_cost"), JAVA_DOUBLE.withName("vari_cost"), JAVA_DOUBLE.withName("hold_cost"),
+            JAVA_DOUBLE.withName("penalty_cost"), JAVA_DOUBLE.withName("price"), JAVA_DOUBLE.withName("salvage"),
+            JAVA_DOUBLE.withName("deposit_rate"), JAVA_DOUBLE.withName("overhead_rate"),
+            JAVA_DOUBLE.withName("overhead"), JAVA_DOUBLE.withName("r0"), JAVA_DOUBLE.withName("r2"),
+            JAVA_DOUBLE.withName("r3"), JAVA_DOUBLE.withName("od_limit"), JAVA_DOUBLE.withName("interest_free"),
+            ADDRESS.withName("price_t"), ADDRESS.withName("vari_cost_t"), ADDRESS.withName("overhead_t"),
+            ADDRESS.withName("reserve_t"), JAVA_DOUBLE.withName("reserve2"));
+
+    private static final Linker LINKER = Linker.nativeLinker();
+    private static final SymbolLookup LIB =
+            SymbolLookup.libraryLookup(System.getProperty("sdpb200.lib", "libsdpb200.so"), Arena.global());
+
+    private static MethodHandle fn(String name, FunctionDescriptor d) {
+        return LINKER.downcallHandle(LIB.find(name).orElseThrow(), d);
+    }
+
+    static final MethodHandle SIZEOF_MODEL = fn("sdpb_sizeof_model", FunctionDescriptor.of(JAVA_LONG));
+    static final MethodHandle CREATE = fn("sdpb_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle DESTROY = fn("sdpb_destroy", FunctionDescriptor.ofVoid(ADDRESS));
+    static final MethodHandle LAST_ERROR = fn("sdpb_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
+    static final MethodHandle SOLVE = fn("sdpb_solve", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle VALUE = fn("sdpb_value",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle REACH = fn("sdpb_reach", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+    static final MethodHandle OPT_TABLE = fn("sdpb_opt_table", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle EVAL_TRIPLES = fn("sdpb_eval_triples", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT,
+            ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+
+    static {
+        try {
+            if ((long) SIZEOF_MODEL.invokeExact() != MODEL.byteSize())
+                throw new IllegalStateException("libsdpb200.so struct layout differs from SdpB200.MODEL");
+        } catch (Throwable t) {
+            throw new ExceptionInInitializerError(t);
+        }
+    }
+
+    static String lastError(MemorySegment handle) throws Throwable {
+        MemorySegment s = (MemorySegment) LAST_ERROR.invokeExact(handle);
+        return s.reinterpret(4096).getString(0);
+    }
+
+    static void check(int rc, MemorySegment handle) throws Throwable {
+        if (rc != 0) throw new IllegalStateException("sdpb error " + rc + ": " + lastError(handle));
+    }
+
+    private SdpB200() {}
+}

@@ -24,7 +24,7 @@ REC_EXPECT, REC_SURVIVAL = 0, 1
 MIN, MAX = 0, 1
 Q_DIV, Q_LONGDIV = 0, 1
 F_CLAMP_INV, F_LOST_SALES, F_GY_MODE, F_NO_ORDER_LAST, F_CASH_LIMITED_ACTIONS = 1, 2, 4, 8, 16
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED, KERNEL_STAGED, KERNEL_CASH_INT = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED, KERNEL_STAGED, KERNEL_CASH_INT, KERNEL_TILED2 = 0, 1, 2, 3, 4, 5
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -76,7 +76,7 @@ class SdpbStats(C.Structure):
 # every symbol include/sdpb200.h declares
 EXPORTS = [
     "sdpb_abi_version", "sdpb_sizeof_model", "sdpb_sizeof_options", "sdpb_create", "sdpb_destroy",
-    "sdpb_last_error", "sdpb_grid_info", "sdpb_solve", "sdpb_solve_period_async", "sdpb_sync",
+    "sdpb_last_error", "sdpb_grid_info", "sdpb_solve", "sdpb_solve_async", "sdpb_solve_period_async", "sdpb_sync",
     "sdpb_value", "sdpb_period_tables", "sdpb_device_tables", "sdpb_state_of_index", "sdpb_reach",
     "sdpb_opt_table", "sdpb_stats_get", "sdpb_eval_triples", "sdpb_microbench",
 ]
@@ -121,6 +121,7 @@ def load():
     lib.sdpb_last_error.restype = C.c_char_p
     lib.sdpb_grid_info.argtypes = [vp, C.POINTER(SdpbGrid)]
     lib.sdpb_solve.argtypes = [vp]
+    lib.sdpb_solve_async.argtypes = [vp]
     lib.sdpb_solve_period_async.argtypes = [vp, C.c_int]
     lib.sdpb_sync.argtypes = [vp]
     lib.sdpb_value.argtypes = [vp, C.c_int, _dp, C.c_int, _dp, _dp]

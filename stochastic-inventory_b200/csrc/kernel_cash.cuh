@@ -107,20 +107,24 @@ bi_cash_int(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs
         for (int r = 0; r < R; r++) acc[r] = 0.0;
 
         // ---- demand below the stock: sale = d_j, successor inventory y - d_j > 0 ----
+        // All index arithmetic is 32-bit (plan_cash checks nI*nW < 2^31): the successor's flat index
+        // is clamp(rowoff + iw + shift, rowoff, rowoff + nW-1), one add-max and one min per level.
+#pragma unroll 2
         for (int j = 0; j < jy; j++) {
             const double2 pp = PP[j];
-            const int shift = PRi[j] - CI;                    // exact cash increment
             int il = ix + ai - (a.d0 + j);                    // successor inventory index
             il = min(il, M.nI - 1);
             il = max(il, 0);
-            const double* __restrict__ row = a.Vn + (long long)il * M.nW;
+            const int rowoff = il * M.nW;
+            const int kk0 = rowoff + PRi[j] - CI;             // + iw[r] = unclamped flat index
+            const int khi = rowoff + nW1;
             double m = 0.0;
             if (!SURVIVAL) m = pp.x * (PRd[j] - Cd);          // p_j * c(s,a,d_j)
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                const int k = min(max(iw[r] + shift, 0), nW1);  // clamp to [cash_min, cash_max]
-                double vn = __ldg(row + k);
-                if (SURVIVAL && M.kmin + k < 0) vn = 0.0;      // RiskRecursion.java:87-95
+                const int k = min(max(kk0 + iw[r], rowoff), khi);  // clamp to [cash_min, cash_max]
+                double vn = __ldg(a.Vn + (unsigned)k);
+                if (SURVIVAL && k - rowoff < -M.kmin) vn = 0.0;  // successor cash < 0: RiskRecursion.java:87-95
                 if (!SURVIVAL) acc[r] += m;                    // CashRecursion.java:117
                 acc[r] += pp.y * vn;                           // CashRecursion.java:120
             }
@@ -128,18 +132,19 @@ bi_cash_int(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs
         // ---- stock-out: sale = y for every remaining demand, successor inventory 0 ----
         if (jy < a.D) {
             const int PYi = a.price * yv;
-            const int shift = PYi - CI;
-            int il = min(max(M.i_zero, 0), M.nI - 1);
-            if (yv < 0) il = min(max(max(ix + ai - a.d0, M.i_zero), 0), M.nI - 1);  // not reachable: inv_min >= 0
-            const double* __restrict__ row = a.Vn + (long long)il * M.nW;
+            const int il = min(max(M.i_zero, 0), M.nI - 1);
+            const int rowoff = il * M.nW;
+            const int kk0 = rowoff + PYi - CI;
+            const int khi = rowoff + nW1;
             const double inc = (double)PYi - Cd;
             double vn[R];
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                const int k = min(max(iw[r] + shift, 0), nW1);
-                vn[r] = __ldg(row + k);
-                if (SURVIVAL && M.kmin + k < 0) vn[r] = 0.0;
+                const int k = min(max(kk0 + iw[r], rowoff), khi);
+                vn[r] = __ldg(a.Vn + (unsigned)k);
+                if (SURVIVAL && k - rowoff < -M.kmin) vn[r] = 0.0;
             }
+#pragma unroll 2
             for (int j = jy; j < a.D; j++) {
                 const double2 pp = PP[j];
                 double m = 0.0;
@@ -199,7 +204,7 @@ inline void plan_cash(CashPlan& P, const sdpb_model& m, const DevModel& d, const
         const double big = std::fabs(price) * (std::fabs(m.inv_max) + d.max_order_idx + std::abs(di[0]) + pmf_len[t]) +
                            std::fabs(m.cash_min) + std::fabs(m.cash_max) + std::fabs(v) * d.max_order_idx +
                            std::fabs(m.fixed_cost) + std::fabs(ovh);
-        if (big > 5e8) continue;
+        if (big > 5e8 || (double)d.nI * d.nW > 2.0e9) continue;
         CashPeriod& cp = P.period[t];
         cp.ok = true;
         cp.price = (int)price; cp.v = (int)v; cp.ovh = (int)ovh; cp.d0 = di[0];

@@ -48,6 +48,9 @@ struct TiledPeriod {
     int di_max = 0, span = 0;
     int WN = 0;           // window entries
     size_t smem = 0;
+    bool ok2 = false;     // bi_inv_tiled2 (needs consecutive demands)
+    int WN2 = 0;
+    size_t smem2 = 0;
 };
 
 struct TiledPlan {
@@ -55,6 +58,8 @@ struct TiledPlan {
     const char* why_not = "";
     std::vector<TiledPeriod> period;  // [T]
     int n_chunks = 0;                 // ceil(n_actions / R)
+    int n_chunks2 = 0;                // ceil(n_actions / RA) for bi_inv_tiled2
+    int variant = 0;                  // 0 = choose by size, 1 = bi_inv_tiled only, 2 = bi_inv_tiled2 when possible
     int sm_count = 148;
     // cross-CTA merge scratch for action splitting (allocated lazily by the owner)
     double* part_v = nullptr;
@@ -215,6 +220,188 @@ bi_inv_tiled(const __grid_constant__ DevModel M, const __grid_constant__ TiledAr
     if (u == 0) a.counters[blockIdx.x] = 0;  // ready for the next launch
 }
 
+// ---------------------------------------------------------------------------------------------
+// bi_inv_tiled2 — the same model, 2-D register tile.  A thread owns Y = 4 consecutive order-up-to
+// levels y and RA = 4 consecutive actions, i.e. 16 (state, action) pairs on 7 diagonals x = y - a.
+// With consecutive integer demands the level y_k - d_j that slot k needs at demand j+1 is the one
+// slot k-1 needed at demand j, so the immediate costs cst[k][r] = fv_r + W.x(level) and the
+// successor values slide through registers: per demand point a thread loads ONE new level, forms 4
+// new costs and 4 products (p*gamma)*V, and then spends 3 fp64 instructions on each of its 16
+// evaluations (mul, add, add):  (4 + 4 + 48) / 16 = 3.5 per evaluation, 2.25 in the last period,
+// against 4.125 / 3 in bi_inv_tiled.  The rotation is unrolled 4x so slots are compile-time
+// registers.  The window is stored permuted ([level & 3][level >> 2]) so that the stride-4 level
+// loads of a warp are unit-stride in shared memory.
+constexpr int kT2Y = 4, kT2RA = 4;
+constexpr int kT2BX = kTiledThreads * kT2Y - kT2RA + 1;  // 1021 states per tile
+
+template <bool IS_MIN, bool LAST>
+__global__ void __launch_bounds__(kTiledThreads, 2)
+bi_inv_tiled2(const __grid_constant__ DevModel M, const __grid_constant__ TiledArgs a) {
+    constexpr int Y = kT2Y, RA = kT2RA, BX = kT2BX, NT = kTiledThreads;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* W = reinterpret_cast<double2*>(smem_raw);  // permuted window, later aliased by the merge area
+    const int Wq = (a.WN + 3) >> 2;
+    const size_t head = (size_t)4 * Wq * sizeof(double2);
+    double2* PP = reinterpret_cast<double2*>(smem_raw + head);
+
+    const int u = threadIdx.x;
+    const long long X0 = a.lo + (long long)blockIdx.x * BX;
+    const int split = blockIdx.y;
+    const int D = a.D;
+
+    for (int j = u; j < D; j += NT) PP[j] = make_double2(M.pmf_p[a.pmf_off + j], M.pmf_pg[a.pmf_off + j]);
+    const bool lost = (M.flags & SDPB_F_LOST_SALES) != 0;
+    for (int wi = u; wi < a.WN; wi += NT) {
+        const long long il = X0 - a.di_max + wi;
+        const double lvl = M.inv_min + (double)il * M.step;
+        const double hold = M.h * fmax(lvl, 0.0);
+        const double pen = M.pen * fmax(-lvl, 0.0);
+        double vn = 0.0;
+        if (!LAST) {
+            long long is = il;
+            if (lost) is = is > M.i_zero ? is : M.i_zero;
+            is = is < M.nI - 1 ? is : M.nI - 1;
+            is = is > 0 ? is : 0;
+            vn = a.Vn[is];
+        }
+        W[(wi & 3) * Wq + (wi >> 2)] = make_double2(hold + pen, vn);
+    }
+    __syncthreads();
+
+    // running optimum per diagonal delta = k - r in [-3, 3]  (state s = 4u + delta)
+    double best[Y + RA - 1];
+    int arg[Y + RA - 1];
+#pragma unroll
+    for (int q = 0; q < Y + RA - 1; q++) { best[q] = IS_MIN ? DBL_MAX : -DBL_MAX; arg[q] = kNoAction; }
+
+    const double v = M.v_t[a.t - 1];
+    const int c_begin = split * a.chunks_per_split;
+    const int c_end = min(a.n_chunks, c_begin + a.chunks_per_split);
+
+    for (int c = c_begin; c < c_end; c++) {
+        double fv[RA], acc[Y][RA], cst[Y][RA], Vw[Y];
+#pragma unroll
+        for (int r = 0; r < RA; r++) {
+            const double av = (double)(c * RA + r) * M.step;
+            fv[r] = (av > 0.0 ? M.K : 0.0) + v * av;
+        }
+        // level needed by slot k at demand j:  wi = 4u + 4c + (D-1-j) + k
+        int b = Y * u + RA * c + (D - 1);
+#pragma unroll
+        for (int k = 0; k < Y; k++) {
+            const int wi = b + k;
+            const double2 w = W[(wi & 3) * Wq + (wi >> 2)];
+#pragma unroll
+            for (int r = 0; r < RA; r++) { cst[k][r] = fv[r] + w.x; acc[k][r] = 0.0; }
+            Vw[k] = w.y;
+        }
+        for (int j0 = 0; j0 < D; j0 += 4) {
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int j = j0 + jj;
+                if (j < D) {
+                    const double2 pp = PP[j];
+                    // prefetch the level that enters at demand j+1 (slot 0 of the next step)
+                    const int wn = max(b - 1, 0);
+                    const double2 wnew = W[(wn & 3) * Wq + (wn >> 2)];
+#pragma unroll
+                    for (int k = 0; k < Y; k++) {
+                        const int ph = (k - jj) & 3;  // physical register slot of level slot k
+                        if (!LAST) {
+                            const double pv = pp.y * Vw[ph];
+#pragma unroll
+                            for (int r = 0; r < RA; r++) {
+                                acc[k][r] += pp.x * cst[ph][r];
+                                acc[k][r] += pv;
+                            }
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < RA; r++) acc[k][r] += pp.x * cst[ph][r];
+                        }
+                    }
+                    // the slot that held level slot 3 is free now: it becomes slot 0 of demand j+1
+                    const int pn = (3 - jj) & 3;
+#pragma unroll
+                    for (int r = 0; r < RA; r++) cst[pn][r] = fv[r] + wnew.x;
+                    Vw[pn] = wnew.y;
+                    b -= 1;
+                }
+            }
+        }
+        // ascending actions within the chunk, strict compare: first optimum wins
+#pragma unroll
+        for (int r = 0; r < RA; r++) {
+            const int i = c * RA + r;
+#pragma unroll
+            for (int k = 0; k < Y; k++) {
+                const int q = k - r + (RA - 1);
+                if (i <= M.max_order_idx && (IS_MIN ? (acc[k][r] < best[q]) : (acc[k][r] > best[q]))) {
+                    best[q] = acc[k][r];
+                    arg[q] = i;
+                }
+            }
+        }
+    }
+
+    // ---- merge: state s gets one partial from thread s/4 (delta >= 0) and one from thread s/4+1 ----
+    __syncthreads();
+    double* redA_v = reinterpret_cast<double*>(smem_raw);
+    double* redB_v = redA_v + NT * Y;
+    int* redA_a = reinterpret_cast<int*>(redB_v + NT * Y);
+    int* redB_a = redA_a + NT * Y;
+#pragma unroll
+    for (int k = 0; k < Y; k++) { redB_v[Y * u + k] = IS_MIN ? DBL_MAX : -DBL_MAX; redB_a[Y * u + k] = kNoAction; }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < Y + RA - 1; q++) {
+        const int delta = q - (RA - 1);
+        const int s = Y * u + delta;
+        if (delta >= 0) { redA_v[s] = best[q]; redA_a[s] = arg[q]; }
+        else if (s >= 0) { redB_v[s] = best[q]; redB_a[s] = arg[q]; }
+    }
+    __syncthreads();
+    // each thread finishes 4 states (s = u, u + NT, ...): coalesced writes
+#pragma unroll
+    for (int k = 0; k < Y; k++) {
+        const int s = u + k * NT;
+        if (s >= BX) continue;
+        double bv = redA_v[s];
+        int ba = redA_a[s];
+        if (better<IS_MIN>(redB_v[s], redB_a[s], bv, ba)) { bv = redB_v[s]; ba = redB_a[s]; }
+        if (a.nsplit == 1) {
+            if (X0 + s < a.hi) { a.Vt[X0 + s] = bv; a.Qt[X0 + s] = ba == kNoAction ? -1 : ba; }
+        } else {
+            const size_t slot = ((size_t)blockIdx.x * a.nsplit + split) * BX + s;
+            a.part_v[slot] = bv;
+            a.part_a[slot] = ba;
+        }
+    }
+    if (a.nsplit == 1) return;
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (u == 0) is_last = (atomicAdd(&a.counters[blockIdx.x], 1u) == (unsigned)a.nsplit - 1u);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < Y; k++) {
+        const int s = u + k * NT;
+        if (s >= BX || X0 + s >= a.hi) continue;
+        double bv = IS_MIN ? DBL_MAX : -DBL_MAX;
+        int ba = kNoAction;
+        for (int sp = 0; sp < a.nsplit; sp++) {
+            const size_t q = ((size_t)blockIdx.x * a.nsplit + sp) * BX + s;
+            const double ov = __ldcg(a.part_v + q);
+            const int oa = __ldcg(a.part_a + q);
+            if (better<IS_MIN>(ov, oa, bv, ba)) { bv = ov; ba = oa; }
+        }
+        a.Vt[X0 + s] = bv;
+        a.Qt[X0 + s] = ba == kNoAction ? -1 : ba;
+    }
+    if (u == 0) a.counters[blockIdx.x] = 0;
+}
+
 // ---- host side --------------------------------------------------------------------------------
 inline void plan_tiled(TiledPlan& P, const sdpb_model& m, const DevModel& d, const std::vector<int>& pmf_len,
                        const std::vector<int>& pmf_off, const std::vector<int>& pdi, bool /*dedup*/,
@@ -246,6 +433,13 @@ inline void plan_tiled(TiledPlan& P, const sdpb_model& m, const DevModel& d, con
         tp.smem = tiled_head_bytes(tp.WN) + (size_t)D * 16 + (size_t)D * 4 + 16;
         tp.ok = tp.smem <= 200 * 1024;
         any = any || tp.ok;
+        // 2-D register tile variant
+        P.n_chunks2 = (d.max_order_idx + 1 + kT2RA - 1) / kT2RA;
+        tp.WN2 = kTiledThreads * kT2Y + P.n_chunks2 * kT2RA + D;
+        const size_t head2 = (size_t)4 * ((tp.WN2 + 3) >> 2) * 16;
+        const size_t red2 = (size_t)kTiledThreads * kT2Y * 2 * 12;
+        tp.smem2 = std::max(head2, red2) + (size_t)D * 16 + 16;
+        tp.ok2 = consec && tp.smem2 <= 100 * 1024;
     }
     if (!any) { P.why_not = "window does not fit in shared memory"; return; }
     P.available = true;
@@ -263,47 +457,92 @@ inline cudaError_t launch_tiled_inst(const DevModel& dm, const TiledArgs& a, dim
     return cudaGetLastError();
 }
 
+inline int tiled_scratch(TiledPlan& P, long long tiles, int nsplit, int bx, cudaStream_t stream) {
+    if (nsplit <= 1) return SDPB_OK;
+    const size_t need = (size_t)tiles * nsplit * bx;
+    if (need > P.part_cap) {
+        if (P.part_v) cudaFree(P.part_v);
+        if (P.part_a) cudaFree(P.part_a);
+        P.part_v = nullptr; P.part_a = nullptr; P.part_cap = 0;
+        if (cudaMalloc((void**)&P.part_v, need * sizeof(double)) != cudaSuccess) return SDPB_ERR_NOMEM;
+        if (cudaMalloc((void**)&P.part_a, need * sizeof(int)) != cudaSuccess) return SDPB_ERR_NOMEM;
+        P.part_cap = need;
+    }
+    if ((size_t)tiles > P.counter_cap) {
+        if (P.counters) cudaFree(P.counters);
+        P.counters = nullptr; P.counter_cap = 0;
+        if (cudaMalloc((void**)&P.counters, (size_t)tiles * sizeof(unsigned)) != cudaSuccess) return SDPB_ERR_NOMEM;
+        if (cudaMemsetAsync(P.counters, 0, (size_t)tiles * sizeof(unsigned), stream) != cudaSuccess) return SDPB_ERR_CUDA;
+        P.counter_cap = (size_t)tiles;
+    }
+    return SDPB_OK;
+}
+
+template <bool IS_MIN, bool LAST>
+inline cudaError_t launch_tiled2_inst(const DevModel& dm, const TiledArgs& a, dim3 grid, size_t smem,
+                                      cudaStream_t stream) {
+    auto k = bi_inv_tiled2<IS_MIN, LAST>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k<<<grid, kTiledThreads, smem, stream>>>(dm, a);
+    return cudaGetLastError();
+}
+
 // Returns SDPB_OK, or SDPB_ERR_STATE when this period has no tiled plan (caller falls back to the
-// generic kernel), or SDPB_ERR_CUDA / SDPB_ERR_NOMEM.
+// generic kernel), or SDPB_ERR_CUDA / SDPB_ERR_NOMEM.  *variant_used: 1 = bi_inv_tiled, 2 = bi_inv_tiled2.
 inline int launch_tiled(TiledPlan& P, const DevModel& dm, int t, int D, int pmf_off, const double* Vn,
                         double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream,
-                        double* fp64_ops) {
+                        double* fp64_ops, int* variant_used = nullptr) {
     const TiledPeriod& tp = P.period[t - 1];
-    if (!tp.ok) return SDPB_ERR_STATE;
+    if (!tp.ok && !tp.ok2) return SDPB_ERR_STATE;
     const long long n = hi - lo;
     if (n <= 0) return SDPB_OK;
+    const bool last = (t == dm.T);
+    const bool mn = dm.is_min != 0;
+    const long long target = 4LL * P.sm_count;  // about 4 CTAs per SM
+    const double evals = (double)n * (dm.max_order_idx + 1) * D;
+    TiledArgs a;
+    a.t = t; a.D = D; a.pmf_off = pmf_off; a.Vn = Vn; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
+    a.di_max = tp.di_max;
+
+    // the 2-D register tile pays off once there are enough 1021-state tiles to fill the machine
+    const long long tiles2 = (n + kT2BX - 1) / kT2BX;
+    const bool use2 = tp.ok2 && (P.variant == 2 || (P.variant == 0 && tiles2 >= 2LL * P.sm_count) || !tp.ok);
+    if (use2) {
+        int nsplit = 1;
+        if (tiles2 < target / 2) nsplit = (int)std::min<long long>(P.n_chunks2, (target / 2 + tiles2 - 1) / tiles2);
+        const int cps = (P.n_chunks2 + nsplit - 1) / nsplit;
+        nsplit = (P.n_chunks2 + cps - 1) / cps;
+        int rc = tiled_scratch(P, tiles2, nsplit, kT2BX, stream);
+        if (rc != SDPB_OK) return rc;
+        a.WN = tp.WN2; a.n_chunks = P.n_chunks2; a.chunks_per_split = cps; a.nsplit = nsplit;
+        a.part_v = P.part_v; a.part_a = P.part_a; a.counters = P.counters;
+        const dim3 grid((unsigned)tiles2, (unsigned)nsplit);
+        cudaError_t e;
+        if (mn) e = last ? launch_tiled2_inst<true, true>(dm, a, grid, tp.smem2, stream)
+                         : launch_tiled2_inst<true, false>(dm, a, grid, tp.smem2, stream);
+        else e = last ? launch_tiled2_inst<false, true>(dm, a, grid, tp.smem2, stream)
+                      : launch_tiled2_inst<false, false>(dm, a, grid, tp.smem2, stream);
+        if (e != cudaSuccess) return SDPB_ERR_CUDA;
+        // per 16 evaluations: 4 new costs + 4 products + 16 * (mul, add, add); last period: 4 + 16 * 2
+        if (fp64_ops) *fp64_ops += last ? evals * 2.25 : evals * 3.5;
+        if (variant_used) *variant_used = 2;
+        return SDPB_OK;
+    }
+
     const long long tiles = (n + kTiledBX - 1) / kTiledBX;
-    // fill the machine: about 4 CTAs per SM; split the action range when state tiles are too few
-    const long long target = 4LL * P.sm_count;
+    // split the action range when state tiles are too few to fill the machine
     int nsplit = 1;
     if (tiles < target) nsplit = (int)std::min<long long>(P.n_chunks, (target + tiles - 1) / tiles);
     const int cps = (P.n_chunks + nsplit - 1) / nsplit;
     nsplit = (P.n_chunks + cps - 1) / cps;
-    if (nsplit > 1) {
-        const size_t need = (size_t)tiles * nsplit * kTiledBX;
-        if (need > P.part_cap) {
-            if (P.part_v) cudaFree(P.part_v);
-            if (P.part_a) cudaFree(P.part_a);
-            P.part_v = nullptr; P.part_a = nullptr; P.part_cap = 0;
-            if (cudaMalloc((void**)&P.part_v, need * sizeof(double)) != cudaSuccess) return SDPB_ERR_NOMEM;
-            if (cudaMalloc((void**)&P.part_a, need * sizeof(int)) != cudaSuccess) return SDPB_ERR_NOMEM;
-            P.part_cap = need;
-        }
-        if ((size_t)tiles > P.counter_cap) {
-            if (P.counters) cudaFree(P.counters);
-            P.counters = nullptr; P.counter_cap = 0;
-            if (cudaMalloc((void**)&P.counters, (size_t)tiles * sizeof(unsigned)) != cudaSuccess) return SDPB_ERR_NOMEM;
-            if (cudaMemsetAsync(P.counters, 0, (size_t)tiles * sizeof(unsigned), stream) != cudaSuccess) return SDPB_ERR_CUDA;
-            P.counter_cap = (size_t)tiles;
-        }
-    }
-    TiledArgs a;
-    a.t = t; a.D = D; a.pmf_off = pmf_off; a.Vn = Vn; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
-    a.di_max = tp.di_max; a.WN = tp.WN; a.n_chunks = P.n_chunks; a.chunks_per_split = cps; a.nsplit = nsplit;
+    int rc = tiled_scratch(P, tiles, nsplit, kTiledBX, stream);
+    if (rc != SDPB_OK) return rc;
+    a.WN = tp.WN; a.n_chunks = P.n_chunks; a.chunks_per_split = cps; a.nsplit = nsplit;
     a.part_v = P.part_v; a.part_a = P.part_a; a.counters = P.counters;
     const dim3 grid((unsigned)tiles, (unsigned)nsplit);
-    const bool last = (t == dm.T);
-    const bool mn = dm.is_min != 0;
     cudaError_t e;
 #define SDPB_TILED_CASE(MN, LS, CS) e = launch_tiled_inst<MN, LS, CS>(dm, a, grid, tp.smem, stream)
     if (mn) {
@@ -315,11 +554,9 @@ inline int launch_tiled(TiledPlan& P, const DevModel& dm, int t, int D, int pmf_
     }
 #undef SDPB_TILED_CASE
     if (e != cudaSuccess) return SDPB_ERR_CUDA;
-    if (fp64_ops) {
-        // useful fp64 instructions: per evaluation add+mul+add(+add), plus one mul per R evaluations
-        const double evals = (double)n * (dm.max_order_idx + 1) * D;
-        *fp64_ops += last ? evals * 3.0 : evals * 4.0 + evals / kTiledR;
-    }
+    // useful fp64 instructions: per evaluation add+mul+add(+add), plus one mul per R evaluations
+    if (fp64_ops) *fp64_ops += last ? evals * 3.0 : evals * 4.0 + evals / kTiledR;
+    if (variant_used) *variant_used = 1;
     return SDPB_OK;
 }
 

@@ -64,6 +64,10 @@ struct sdpb_handle {
     sdpb_stats stats{};
     TiledPlan tiled{};
     CashPlan cash{};
+    int solve_count = 0;
+    cudaGraphExec_t graph_exec = nullptr;  // the T launches of one solve, captured on the second solve
+    bool graph_failed = false;
+    sdpb_stats graph_stats{};
     bool dedup = false;        // lead-time models: fold (x, preQ) -> x + preQ
     long long vS = 0;          // virtual states per period
     double* dHv = nullptr;     // [vS] virtual value table of the period being solved
@@ -73,13 +77,31 @@ struct sdpb_handle {
 
 namespace {
 
+// Device memory comes from the stream-ordered pool allocator with the release threshold lifted, so a
+// create/solve/destroy cycle reuses the previous cycle's memory instead of paying cudaMalloc/cudaFree
+// (cudaFree of the C5 tables alone cost 1.1 s per cycle).
+cudaError_t dev_alloc(sdpb_handle* h, void** p, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(p, std::max<size_t>(bytes, 16), h->stream);
+    if (e == cudaSuccess) h->dev_allocs.push_back(*p);
+    return e;
+}
+
+void lift_pool_threshold(int dev) {
+    static bool done[64] = {false};
+    if (dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[dev] = true;
+}
+
 template <class T>
 int upload(sdpb_handle* h, const std::vector<T>& v, T** out) {
     void* p = nullptr;
-    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-    CU(cudaMalloc(&p, bytes));
-    h->dev_allocs.push_back(p);
-    if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    CU(dev_alloc(h, &p, v.size() * sizeof(T)));
+    if (!v.empty()) CU(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
     *out = (T*)p;
     return SDPB_OK;
 }
@@ -341,9 +363,10 @@ int solve_period(sdpb_handle* h, int t) {
         return SDPB_OK;
     }
     if (h->tiled.available && h->opt.kernel != SDPB_KERNEL_GENERIC) {
+        int variant = 1;
         rc = launch_tiled(h->tiled, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, h->dV[t - 1],
-                          h->dQ[t - 1], h->lo, h->hi, h->stream, &h->stats.fp64_ops);
-        if (rc == SDPB_OK) h->stats.kernel_used = SDPB_KERNEL_TILED;
+                          h->dQ[t - 1], h->lo, h->hi, h->stream, &h->stats.fp64_ops, &variant);
+        if (rc == SDPB_OK) h->stats.kernel_used = variant == 2 ? SDPB_KERNEL_TILED2 : SDPB_KERNEL_TILED;
         else if (rc != SDPB_ERR_STATE) { h->err = "tiled kernel launch failed"; return rc; }
     }
     if (rc == SDPB_ERR_STATE && h->opt.kernel != SDPB_KERNEL_GENERIC) {  // integer cash models
@@ -377,11 +400,12 @@ const char* sdpb_last_error(const sdpb_handle* h) { return h ? h->err.c_str() : 
 void sdpb_destroy(sdpb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    for (void* p : h->dev_allocs) cudaFree(p);
+    if (h->stream) for (void* p : h->dev_allocs) cudaFreeAsync(p, h->stream);
     free_tiled(h->tiled);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     delete h;
 }
 
@@ -541,6 +565,7 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
+    lift_pool_threshold(dev);
 
     double *dp = nullptr;
     int* di = nullptr;
@@ -558,13 +583,11 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     h->solved.assign(T, 0);
     for (int t = 0; t < T; t++) {
         void* p = nullptr;
-        if (cudaMalloc(&p, (size_t)h->Spad * sizeof(double)) != cudaSuccess)
-            return fail_create(h, SDPB_ERR_NOMEM, "cudaMalloc of a value table failed");
-        h->dev_allocs.push_back(p);
+        if (dev_alloc(h, &p, (size_t)h->Spad * sizeof(double)) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "allocation of a value table failed");
         h->dV[t] = (double*)p;
-        if (cudaMalloc(&p, (size_t)h->Spad * sizeof(int)) != cudaSuccess)
-            return fail_create(h, SDPB_ERR_NOMEM, "cudaMalloc of a policy table failed");
-        h->dev_allocs.push_back(p);
+        if (dev_alloc(h, &p, (size_t)h->Spad * sizeof(int)) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "allocation of a policy table failed");
         h->dQ[t] = (int*)p;
     }
 
@@ -573,20 +596,19 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         h->dedup = true;
         h->vS = (long long)(d.nI + d.nQ - 1) * (m->lead_time >= 2 ? d.nQ : 1) * d.nW;
         void* p = nullptr;
-        if (cudaMalloc(&p, (size_t)h->vS * sizeof(double)) != cudaSuccess)
-            return fail_create(h, SDPB_ERR_NOMEM, "cudaMalloc of the folded value table failed");
-        h->dev_allocs.push_back(p);
+        if (dev_alloc(h, &p, (size_t)h->vS * sizeof(double)) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "allocation of the folded value table failed");
         h->dHv = (double*)p;
-        if (cudaMalloc(&p, (size_t)h->vS * sizeof(int)) != cudaSuccess)
-            return fail_create(h, SDPB_ERR_NOMEM, "cudaMalloc of the folded policy table failed");
-        h->dev_allocs.push_back(p);
+        if (dev_alloc(h, &p, (size_t)h->vS * sizeof(int)) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "allocation of the folded policy table failed");
         h->dHa = (int*)p;
     }
 
     // ---- kernel plan ----
     plan_tiled(h->tiled, h->m, h->dm, h->pmf_len, h->pmf_off, pdi, h->opt.dedup != 0, prop);
     plan_cash(h->cash, h->m, h->dm, h->pmf_len, h->pmf_off, pdi);
-    if (h->opt.kernel == SDPB_KERNEL_TILED && !h->tiled.available &&
+    h->tiled.variant = h->opt.kernel == SDPB_KERNEL_TILED2 ? 2 : (h->opt.kernel == SDPB_KERNEL_TILED ? 1 : 0);
+    if ((h->opt.kernel == SDPB_KERNEL_TILED || h->opt.kernel == SDPB_KERNEL_TILED2) && !h->tiled.available &&
         !(m->cost_kind == SDPB_COST_BACKORDER && m->lead_time >= 1) && !h->cash.available)
         return fail_create(h, SDPB_ERR_ARG, std::string("no shared-memory kernel for this model: ") + h->tiled.why_not);
     *out = h;
@@ -621,7 +643,17 @@ int sdpb_sync(sdpb_handle* h) {
     return SDPB_OK;
 }
 
-int sdpb_solve(sdpb_handle* h) {
+static int enqueue_all_periods(sdpb_handle* h) {
+    std::fill(h->solved.begin(), h->solved.end(), 0);
+    h->stats = sdpb_stats{};
+    for (int t = h->m.T; t >= 1; t--) {
+        int rc = solve_period(h, t);
+        if (rc != SDPB_OK) return rc;
+    }
+    return SDPB_OK;
+}
+
+int sdpb_solve_async(sdpb_handle* h) {
     if (!h) return SDPB_ERR_ARG;
     if (h->opt.shard_count != 1) {
         h->err = "sdpb_solve needs an unsharded handle; step sharded handles with sdpb_solve_period_async "
@@ -629,14 +661,43 @@ int sdpb_solve(sdpb_handle* h) {
         return SDPB_ERR_STATE;
     }
     CU(cudaSetDevice(h->device));
-    std::fill(h->solved.begin(), h->solved.end(), 0);
-    h->stats = sdpb_stats{};
     h->reached = false;
-    CU(cudaEventRecord(h->ev0, h->stream));
-    for (int t = h->m.T; t >= 1; t--) {
-        int rc = solve_period(h, t);
-        if (rc != SDPB_OK) return rc;
+    if (h->graph_exec) {
+        h->stats = h->graph_stats;
+        CU(cudaGraphLaunch(h->graph_exec, h->stream));
+        return SDPB_OK;
     }
+    if (h->solve_count >= 1 && !h->graph_failed) {
+        // second solve: every scratch buffer exists by now, so the launches can be captured
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            int rc = enqueue_all_periods(h);
+            cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+            if (rc == SDPB_OK && e == cudaSuccess && graph &&
+                cudaGraphInstantiate(&h->graph_exec, graph, 0) == cudaSuccess) {
+                cudaGraphDestroy(graph);
+                h->graph_stats = h->stats;
+                CU(cudaGraphLaunch(h->graph_exec, h->stream));
+                h->solve_count++;
+                return SDPB_OK;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            h->graph_exec = nullptr;
+        }
+        cudaGetLastError();
+        h->graph_failed = true;  // fall back to plain launches for good
+    }
+    int rc = enqueue_all_periods(h);
+    if (rc == SDPB_OK) h->solve_count++;
+    return rc;
+}
+
+int sdpb_solve(sdpb_handle* h) {
+    if (!h) return SDPB_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    int rc = sdpb_solve_async(h);
+    if (rc != SDPB_OK) return rc;
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     float ms = 0;
@@ -727,8 +788,7 @@ int sdpb_reach(sdpb_handle* h, const double* init_states, int n) {
     for (int t = 0; t < T; t++) {
         if (!h->dMask[t]) {
             void* p = nullptr;
-            CU(cudaMalloc(&p, (size_t)h->S));
-            h->dev_allocs.push_back(p);
+            CU(dev_alloc(h, &p, (size_t)h->S));
             h->dMask[t] = (unsigned char*)p;
         }
         CU(cudaMemsetAsync(h->dMask[t], 0, (size_t)h->S, h->stream));

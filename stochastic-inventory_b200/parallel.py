@@ -61,6 +61,9 @@ class ShardedSolve:
                 self.V.append(wrap_device(torch, dv, self.chunk * world, "<f8", device))
 
     def step(self):
+        if self.world == 1:
+            self.solver.solve_async()  # one CUDA graph per solve after the first
+            return
         backward_induction_sharded(
             self.T, self.n, self.rank, self.world, self.solver.solve_period_async, self.V,
             self.dist.all_gather_into_tensor if self.world > 1 else None)

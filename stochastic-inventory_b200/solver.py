@@ -59,6 +59,10 @@ class Solver:
         self._check(self.lib.sdpb_solve(self.h))
         return self
 
+    def solve_async(self):
+        """Enqueue the whole solve on the handle's stream (CUDA-graph replay from the second call)."""
+        self._check(self.lib.sdpb_solve_async(self.h))
+
     def solve_period_async(self, period: int):
         self._check(self.lib.sdpb_solve_period_async(self.h, period))
 

@@ -46,6 +46,41 @@ def test_auto_kernel_whole_grid(case, S, oracle):
     assert s.stats()["evals"] == evals
 
 
+A_CASES = [cases.case_A_small, cases.case_A_max, cases.case_A_gy, cases.case_A_twopoint, cases.case_A_halfstep]
+
+
+@pytest.mark.parametrize("case", A_CASES, ids=lambda f: f.__name__[5:])
+@pytest.mark.parametrize("kernel", ["tiled", "tiled2"])
+def test_both_tiled_variants_whole_grid(case, kernel, S, oracle):
+    """bi_inv_tiled (1 level x 8 actions per thread) and bi_inv_tiled2 (4 levels x 4 actions, sliding
+    register window), forced on small grids so the action-split / last-CTA merge path runs too."""
+    spec, init = case()
+    Vo, Qo, evals, _ = oracle.dense(spec)
+    k = S.KERNEL_TILED if kernel == "tiled" else S.KERNEL_TILED2
+    s, V, Q = _solve_all(S, spec, kernel=k)
+    assert np.array_equal(V, Vo)
+    assert np.array_equal(Q, Qo)
+    used = s.stats()["kernel_used"]
+    if kernel == "tiled2" and case is not cases.case_A_twopoint:   # two-point demand is not consecutive
+        assert used == S.KERNEL_TILED2
+    else:
+        assert used == S.KERNEL_TILED
+
+
+def test_tiled2_wide_cases(S, oracle):
+    """Shapes that exercise tile edges of the 1021-state tile: several tiles, D not a multiple of 4,
+    action count not a multiple of 4, MAX direction."""
+    for (n_inv, max_order, means, direction) in [(2500, 37, [7, 9, 8], S.MIN), (1021 * 2 + 5, 10, [3, 11], S.MAX),
+                                                 (1500, 3, [2, 2, 2], S.MIN)]:
+        spec = S.inventory_model(S.poisson_pmf(means, 0.999), fixed_cost=12, vari_cost=1, hold_cost=1,
+                                 penalty_cost=6, max_order=max_order, inv_min=-(n_inv // 2),
+                                 inv_max=n_inv - n_inv // 2 - 1, direction=direction)
+        Vo, Qo, _, _ = oracle.dense(spec)
+        for k in (S.KERNEL_TILED2, S.KERNEL_TILED):
+            s, V, Q = _solve_all(S, spec, kernel=k)
+            assert np.array_equal(V, Vo) and np.array_equal(Q, Qo), (n_inv, max_order, k)
+
+
 LEAD_CASES = [cases.case_B1_ref, cases.case_B1_fixed, cases.case_B2_small, cases.case_E_small]
 
 
@@ -77,7 +112,7 @@ def test_staged_kernel_is_used_for_leadtime(S):
     assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_STAGED
     assert S.Solver(spec, kernel=S.KERNEL_GENERIC).solve().stats()["kernel_used"] == S.KERNEL_GENERIC
     spec, _ = cases.case_A_small()
-    assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_TILED
+    assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_TILED  # small grid: 1-D tile variant
 
 
 @pytest.mark.parametrize("name", cases.GOLDEN)
@@ -133,6 +168,24 @@ def test_device_lambdas_match_oracle(case, S, oracle):
         assert c == co
         if st[0] < spec.T and oracle.index(spec, no) >= 0:
             assert tuple(no) == nxt
+
+
+def test_repeated_solves_replay_a_cuda_graph(S, oracle):
+    """From the second sdpb_solve on, the T launches are one captured graph: results must not change."""
+    for case in (cases.case_A_small, cases.case_C_int, cases.case_B2_small):
+        spec, init = case()
+        Vo, Qo, evals, _ = oracle.dense(spec)
+        s = S.Solver(spec)
+        for rep in range(4):
+            s.solve()
+            for t in (1, spec.T):
+                V, Q = s.period_tables(t)
+                assert np.array_equal(V, Vo[t - 1]) and np.array_equal(Q, Qo[t - 1]), (spec.name, rep, t)
+            assert s.stats()["evals"] == evals
+        s.solve_async()
+        s.sync()
+        v, _ = s.value(1, init)
+        assert v[0] == Vo[0][oracle.index(spec, init[0])]
 
 
 def test_unsolved_state_raises(S):
@@ -270,9 +323,11 @@ def test_config_c5_sampled(S, oracle):
     spec = S.configs.c5(n_states=1_000_000, T=2)
     s = S.Solver(spec).solve()
     _sample_check(S, oracle, spec, s, n=64)
-    # tiled and generic kernels are independent implementations: whole-grid agreement at this size
-    g = S.Solver(spec, kernel=S.KERNEL_GENERIC).solve()
-    for t in (1, 2):
-        Va, Qa = s.period_tables(t)
-        Vg, Qg = g.period_tables(t)
-        assert np.array_equal(Va, Vg) and np.array_equal(Qa, Qg)
+    assert s.stats()["kernel_used"] == S.KERNEL_TILED2
+    # the tiled variants and the generic kernel are independent implementations: whole-grid agreement
+    for k in (S.KERNEL_GENERIC, S.KERNEL_TILED):
+        g = S.Solver(spec, kernel=k).solve()
+        for t in (1, 2):
+            Va, Qa = s.period_tables(t)
+            Vg, Qg = g.period_tables(t)
+            assert np.array_equal(Va, Vg) and np.array_equal(Qa, Qg)
