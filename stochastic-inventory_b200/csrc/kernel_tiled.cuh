@@ -231,6 +231,12 @@ bi_inv_tiled(const __grid_constant__ DevModel M, const __grid_constant__ TiledAr
 // against 4.125 / 3 in bi_inv_tiled.  The rotation is unrolled 4x so slots are compile-time
 // registers.  The window is stored permuted ([level & 3][level >> 2]) so that the stride-4 level
 // loads of a warp are unit-stride in shared memory.
+__device__ __forceinline__ double2 lds_double2(unsigned shared_addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(shared_addr));
+    return v;
+}
+
 constexpr int kT2Y = 4, kT2RA = 4;
 constexpr int kT2BX = kTiledThreads * kT2Y - kT2RA + 1;  // 1021 states per tile
 
@@ -268,6 +274,9 @@ bi_inv_tiled2(const __grid_constant__ DevModel M, const __grid_constant__ TiledA
     }
     __syncthreads();
 
+    const unsigned w_base = (unsigned)__cvta_generic_to_shared(W);
+    const unsigned pp_base = (unsigned)__cvta_generic_to_shared(PP);
+
     // running optimum per diagonal delta = k - r in [-3, 3]  (state s = 4u + delta)
     double best[Y + RA - 1];
     int arg[Y + RA - 1];
@@ -290,44 +299,49 @@ bi_inv_tiled2(const __grid_constant__ DevModel M, const __grid_constant__ TiledA
 #pragma unroll
         for (int k = 0; k < Y; k++) {
             const int wi = b + k;
-            const double2 w = W[(wi & 3) * Wq + (wi >> 2)];
+            const double2 w = lds_double2(w_base + (unsigned)(((wi & 3) * Wq + (wi >> 2)) << 4));
 #pragma unroll
             for (int r = 0; r < RA; r++) { cst[k][r] = fv[r] + w.x; acc[k][r] = 0.0; }
             Vw[k] = w.y;
         }
-        for (int j0 = 0; j0 < D; j0 += 4) {
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                const int j = j0 + jj;
-                if (j < D) {
-                    const double2 pp = PP[j];
-                    // prefetch the level that enters at demand j+1 (slot 0 of the next step)
-                    const int wn = max(b - 1, 0);
-                    const double2 wnew = W[(wn & 3) * Wq + (wn >> 2)];
-#pragma unroll
-                    for (int k = 0; k < Y; k++) {
-                        const int ph = (k - jj) & 3;  // physical register slot of level slot k
-                        if (!LAST) {
-                            const double pv = pp.y * Vw[ph];
-#pragma unroll
-                            for (int r = 0; r < RA; r++) {
-                                acc[k][r] += pp.x * cst[ph][r];
-                                acc[k][r] += pv;
-                            }
-                        } else {
-#pragma unroll
-                            for (int r = 0; r < RA; r++) acc[k][r] += pp.x * cst[ph][r];
-                        }
-                    }
-                    // the slot that held level slot 3 is free now: it becomes slot 0 of demand j+1
-                    const int pn = (3 - jj) & 3;
-#pragma unroll
-                    for (int r = 0; r < RA; r++) cst[pn][r] = fv[r] + wnew.x;
-                    Vw[pn] = wnew.y;
-                    b -= 1;
-                }
-            }
+        // One demand point for all 16 pairs.  JJ is the rotation phase (j mod 4): level slot k lives in
+        // physical register slot (k - JJ) & 3.  Software-pipelined: this step's (p, p*gamma) was loaded
+        // one step ago; the loads for the next step (probabilities, the level entering slot 0) issue
+        // first.  Shared memory is addressed through explicit 32-bit shared-space addresses so the
+        // base is not re-derived every step.
+#define SDPB_T2_STEP(JJ)                                                                         \
+        {                                                                                            \
+            const double2 pp = pp_next;                                                              \
+            pp_next = lds_double2(pp_addr);                                                          \
+            pp_addr += (j + 1 < D - 1) ? 16u : 0u;                                                   \
+            const int wn = max(b - 1, 0);                                                            \
+            const double2 wnew = lds_double2(w_base + (unsigned)(((wn & 3) * Wq + (wn >> 2)) << 4)); \
+            _Pragma("unroll") for (int k = 0; k < Y; k++) {                                          \
+                const int ph = (k - (JJ)) & 3;                                                       \
+                if (!LAST) {                                                                         \
+                    const double pv = pp.y * Vw[ph];                                                 \
+                    _Pragma("unroll") for (int r = 0; r < RA; r++) {                                 \
+                        acc[k][r] += pp.x * cst[ph][r];                                              \
+                        acc[k][r] += pv;                                                             \
+                    }                                                                                \
+                } else {                                                                             \
+                    _Pragma("unroll") for (int r = 0; r < RA; r++) acc[k][r] += pp.x * cst[ph][r];   \
+                }                                                                                    \
+            }                                                                                        \
+            const int pn = (3 - (JJ)) & 3; /* freed slot becomes slot 0 of the next demand */        \
+            _Pragma("unroll") for (int r = 0; r < RA; r++) cst[pn][r] = fv[r] + wnew.x;              \
+            Vw[pn] = wnew.y;                                                                         \
+            b -= 1;                                                                                  \
+            j += 1;                                                                                  \
         }
+        double2 pp_next = lds_double2(pp_base);
+        unsigned pp_addr = pp_base + (D > 1 ? 16u : 0u);
+        int j = 0;
+        for (; j + 4 <= D;) { SDPB_T2_STEP(0) SDPB_T2_STEP(1) SDPB_T2_STEP(2) SDPB_T2_STEP(3) }
+        if (j < D) SDPB_T2_STEP(0)
+        if (j < D) SDPB_T2_STEP(1)
+        if (j < D) SDPB_T2_STEP(2)
+#undef SDPB_T2_STEP
         // ascending actions within the chunk, strict compare: first optimum wins
 #pragma unroll
         for (int r = 0; r < RA; r++) {

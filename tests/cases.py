@@ -45,6 +45,29 @@ def case_A_halfstep():
                              inv_min=-6, inv_max=6, step=0.5, name="A_halfstep"), [[0.0]]
 
 
+def case_A_sparse_pmf():
+    # generic DiscreteDistribution through GetPmf's cdf-difference branch (GetPmf.java:120-129): long
+    # tables that are zero almost everywhere, as in fitss/LevelFitsS.java:66-71 (scaled down)
+    values = [[3, 15, 28, 29], [1, 22, 23, 24], [1, 6, 12, 17]]
+    probs = [[0.018, 0.888, 0.046, 0.048], [0.028, 0.271, 0.17, 0.531], [0.041, 0.027, 0.889, 0.043]]
+    dists = [S.DiscreteDistribution(v, p) for v, p in zip(values, probs)]
+    table = S.GetPmf(dists, 0.9999, 1).getpmf()
+    return S.inventory_model(table, fixed_cost=50, vari_cost=0, hold_cost=1, penalty_cost=10, max_order=25,
+                             inv_min=-60, inv_max=60, name="A_sparse_pmf"), [[0.0]]
+
+
+def case_A_degenerate():
+    # T = 1, a single action (order nothing), a single demand point
+    return S.inventory_model([np.array([[2.0, 1.0]])], fixed_cost=5, vari_cost=1, hold_cost=1, penalty_cost=3,
+                             max_order=0, inv_min=-3, inv_max=3, name="A_degenerate"), [[0.0]]
+
+
+def case_A_one_state():
+    # a grid of one inventory point: every successor clamps onto it
+    return S.inventory_model(pmf([2, 3]), fixed_cost=1, vari_cost=1, hold_cost=1, penalty_cost=2, max_order=4,
+                             inv_min=0, inv_max=0, name="A_one_state"), [[0.0]]
+
+
 def case_B1_ref():
     # Leadtime.java:25-68 scaled down; unclamped, so the grid is the reachable hull
     T, mean, maxq = 3, 4, 12
@@ -132,7 +155,8 @@ def case_XR_small():
                            inv_max=30, cash_min=-10, cash_max=90, name="XR_small"), [[0.0, 30.0]]
 
 
-ALL = [case_A_small, case_A_max, case_A_gy, case_A_twopoint, case_A_halfstep, case_B1_ref, case_B1_fixed,
+ALL = [case_A_small, case_A_max, case_A_gy, case_A_twopoint, case_A_halfstep, case_A_sparse_pmf,
+       case_A_degenerate, case_A_one_state, case_B1_ref, case_B1_fixed,
        case_B2_small, case_C_small, case_C_rich, case_C_int, case_C_int_K, case_D_small, case_D_rich, case_E_small, case_F_small,
        case_XR_small]
 

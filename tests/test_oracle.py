@@ -3,6 +3,7 @@ for this path, so the oracle is pinned by (1) top-down == dense, bit for bit, on
 state, (2) an independent pure-Python transliteration of the Java loop on tiny cases,
 (3) closed-form answers, (4) the frozen fixtures under tests/golden/."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -204,3 +205,22 @@ def test_oracle_reproduces_golden(name, oracle):
     rows, iv, _ = oracle.topdown(spec, init)
     assert np.array_equal(rows, g["topdown_rows"])
     assert np.array_equal(iv, g["init_values"])
+
+
+# ---- (5) the reference author's own recorded output ----------------------------------------------
+def test_reference_known_answer_two_product_T2(oracle):
+    """src/cash/overdraft/MultiProductLeadtime.java:34-44 records, for discrete demands
+    {20,30,40} x {10,15,20} with probabilities {.25,.5,.25} and T = 2:
+        "final optimal cash  is -17.800000000000008 ... Q1 = 40, Q2 = 20".
+    oracle/multi_item_oracle.cpp is the same kind of line-by-line restatement as sdp_oracle.cpp (same
+    loop, same p*gamma*V association, same overdraft-interest branches, same clamp / (int) idioms) and
+    reproduces that output to the last digit, for both values Qbound has had in the file (45, 50)."""
+    import subprocess
+    subprocess.run(["make", "-C", oracle.ORACLE_DIR, "multi_item_oracle"], check=True, capture_output=True)
+    exe = os.path.join(oracle.ORACLE_DIR, "multi_item_oracle")
+    for qbound in (45, 50):
+        out = subprocess.run([exe, "2", str(qbound), "3", "20", "30", "40", "0.25", "0.5", "0.25",
+                              "10", "15", "20", "0.25", "0.5", "0.25"], capture_output=True, text=True, check=True)
+        val, q1, q2 = out.stdout.split()[:3]
+        assert val == "-17.800000000000008"
+        assert (int(q1), int(q2)) == (40, 20)

@@ -46,7 +46,8 @@ def test_auto_kernel_whole_grid(case, S, oracle):
     assert s.stats()["evals"] == evals
 
 
-A_CASES = [cases.case_A_small, cases.case_A_max, cases.case_A_gy, cases.case_A_twopoint, cases.case_A_halfstep]
+A_CASES = [cases.case_A_small, cases.case_A_max, cases.case_A_gy, cases.case_A_twopoint, cases.case_A_halfstep,
+           cases.case_A_sparse_pmf, cases.case_A_degenerate, cases.case_A_one_state]
 
 
 @pytest.mark.parametrize("case", A_CASES, ids=lambda f: f.__name__[5:])
