@@ -160,8 +160,10 @@ typedef enum sdpb_kernel_choice {
     SDPB_KERNEL_GENERIC = 1,  /* always the generic per-(s,a,d) kernel */
     SDPB_KERNEL_TILED = 2,    /* shared-memory kernel (tiled for lead_time 0, staged warp-per-state
                                  for backorder lead-time models); error if the model has none */
-    SDPB_KERNEL_STAGED = 3,   /* reported in sdpb_stats.kernel_used only */
+    SDPB_KERNEL_STAGED = 3,   /* warp-per-state staged kernel for backorder lead-time models (as a request:
+                                 skip the slab kernel) */
     SDPB_KERNEL_CASH_INT = 4, /* reported only: integer-exact cash kernel (last period: generic) */
+    SDPB_KERNEL_LEAD_SLAB = 6,/* reported only: shared-memory slab kernel for backorder lead-time models */
     SDPB_KERNEL_TILED2 = 5    /* 2-D register-tile variant of the tiled kernel: chosen automatically for
                                  large grids; as a request it forces the variant wherever it applies */
 } sdpb_kernel_choice;

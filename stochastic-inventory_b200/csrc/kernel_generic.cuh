@@ -274,8 +274,25 @@ bi_backorder_staged(const __grid_constant__ DevModel M, const int t, const int D
     double2* PP = reinterpret_cast<double2*>(smem_raw);                       // [D] (p, p*gamma)
     StagedRow* LR = reinterpret_cast<StagedRow*>(smem_raw + (size_t)D * 16);  // [8 warps][D]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long idx = lo + (long long)blockIdx.x * 8 + warp;
-    const bool live = idx < hi;
+    // Which 8 states share a CTA.  Lead time 1, and every folded (DEDUP) grid: 8 consecutive indices
+    // already differ in the level y only, so their warps read the same successor rows one demand
+    // step apart.  Lead time 2 on the real grid: consecutive indices differ in preQ2, i.e. in the
+    // COLUMN block, and share nothing — so a CTA takes 8 consecutive preQ1 for one (x, preQ2) instead:
+    // 8 warps x D demands then touch 8 + D - 1 rows instead of 8 * D and L1 serves the rest.
+    long long idx;
+    if (M.lead == 2 && !DEDUP) {
+        const int groups = (M.nQ + 7) >> 3;                       // preQ1 groups of 8
+        const long long first = lo / ((long long)M.nQ * M.nQ);    // first inventory row of the shard
+        long long b = blockIdx.x;
+        const int q2 = (int)(b % M.nQ); b /= M.nQ;
+        const int g = (int)(b % groups); b /= groups;
+        const int q1 = g * 8 + warp;
+        idx = ((first + b) * M.nQ + q1) * M.nQ + q2;
+        if (q1 >= M.nQ) idx = -1;
+    } else {
+        idx = lo + (long long)blockIdx.x * 8 + warp;
+    }
+    const bool live = idx >= lo && idx < hi;
     const StateCtx S = decode_state<SDPB_COST_BACKORDER>(M, t, live ? idx : lo, DEDUP);
     for (int j = threadIdx.x; j < D; j += 256)
         PP[j] = make_double2(M.pmf_p[pmf_off + j], M.pmf_pg[pmf_off + j]);

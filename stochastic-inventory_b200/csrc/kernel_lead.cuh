@@ -1,0 +1,272 @@
+// kernel_lead.cuh — shared-memory slab kernel for backorder lead-time models
+// (LeadtimeRecursion.java:49-73 with the lambdas of Leadtime.java:50-81; lead time 1, and the lead
+// time 2 extension of config C4).  Brute force per real state, bit-identical to bi_generic.
+//
+// State (x, q1[, q2]); stock level l = x + q1 - d; successor (succ(l), [q2,] a).  For a fixed action a
+// (and column q2) the successor values V_{t+1}[succ(y - d_j), q2, a] of consecutive levels
+// y = x + q1 slide by one row per demand step, exactly like the 1-D kernel — so a thread owns one
+// action a, YT = 4 consecutive preQ1 (levels) and RQ preQ2 columns, i.e. 4*RQ states:
+//   per demand point it loads ONE new row of RQ values and one level cost from shared memory, forms
+//   cst = fv_a + L(level) once, m_k = p*cst_k for its 4 levels (shared by the RQ columns), and then
+//   spends (mul, add, add) on each evaluation: (1 + 4 + 3*4*RQ) / (4*RQ) = 3.31 fp64 instr per eval
+//   for RQ = 4 (5 in bi_backorder_staged), and 3.5 B of shared memory per eval instead of 8 B of L1.
+// A CTA takes one inventory level x, NYB = 4*NYT consecutive preQ1, RQ consecutive preQ2 and all
+// actions; the slab of successor rows it can reach, slab[level window][RQ][A], is staged once
+// (coalesced along a).  Q-values go back through shared memory (aliasing the slab) for the
+// lexicographic (value, action) argopt per state.  Needs consecutive integer demands and a slab
+// that fits in shared memory; otherwise bi_backorder_staged runs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "dev_model.cuh"
+#include "kernel_tiled.cuh"  // lds_double2
+
+namespace sdpb {
+
+constexpr int kLeadYT = 4;
+
+struct LeadArgs {
+    int t, D, pmf_off;
+    const double* Vn;
+    double* Vt;
+    int* Qt;
+    long long lo, hi;
+    long long row0;      // first inventory row (or virtual level tile origin) of the range
+    int NYT;             // level groups per CTA (NYB = 4 * NYT levels)
+    int ny_tiles, nq2_tiles;
+    int A, Apad, di_max, NR;  // actions, padded row length, max demand index, slab rows
+    int nthreads;
+};
+
+__device__ __forceinline__ double lds_double(unsigned shared_addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(shared_addr));
+    return v;
+}
+
+template <bool IS_MIN, bool LAST, int RQ, bool DEDUP>
+__global__ void __launch_bounds__(256)
+bi_lead_slab(const __grid_constant__ DevModel M, const __grid_constant__ LeadArgs a) {
+    constexpr int YT = kLeadYT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NYB = YT * a.NYT;
+    const int D = a.D, A = a.A, Apad = a.Apad;
+    // layout: [ slab NR*RQ*Apad doubles | later: Q-values NYB*RQ*Apad ] [ Lw NR doubles ] [ PP D double2 ]
+    double* slab = reinterpret_cast<double*>(smem_raw);
+    const size_t slab_elems = (size_t)max(a.NR, NYB) * RQ * Apad;
+    double* Lw = slab + slab_elems;
+    double2* PP = reinterpret_cast<double2*>(Lw + ((a.NR + 1) & ~1));
+
+    // ---- which states: one x (or none when folded), NYB consecutive levels, RQ consecutive preQ2 ----
+    long long b = blockIdx.x;
+    int q2_0 = 0;
+    if (M.lead == 2) { q2_0 = (int)(b % a.nq2_tiles) * RQ; b /= a.nq2_tiles; }
+    const int ytile = (int)(b % a.ny_tiles); b /= a.ny_tiles;
+    // real grid: level y = ix + q1 with q1 = ytile*NYB + local; folded grid: level = ytile*NYB + local
+    const long long ix = DEDUP ? 0 : a.row0 + b;
+    const int q1_0 = ytile * NYB;
+    const long long y0 = ix + q1_0;  // level index of local 0
+    const int n_levels = DEDUP ? (M.nI + M.nQ - 1) : M.nQ;  // valid range of (q1_0 + local)
+
+    const int tid = threadIdx.x;
+    for (int j = tid; j < D; j += a.nthreads) PP[j] = make_double2(M.pmf_p[a.pmf_off + j], M.pmf_pg[a.pmf_off + j]);
+    const bool lost = (M.flags & SDPB_F_LOST_SALES) != 0;
+    const long long strideX = (M.lead == 2) ? (long long)M.nQ * M.nQ : (long long)M.nQ;
+    // window index wi <-> unclamped level index il = y0 - di_max + wi
+    for (int wi = tid; wi < a.NR; wi += a.nthreads) {
+        const double lvl = M.inv_min + (double)(y0 - a.di_max + wi) * M.step;
+        Lw[wi] = M.h * fmax(lvl, 0.0) + M.pen * fmax(-lvl, 0.0);
+    }
+    if (!LAST) {
+        // one warp per (window row, column block): coalesced along the action, no integer division
+        const int warp_s = tid >> 5, lane_s = tid & 31, nwarps_s = a.nthreads >> 5;
+        for (int row = warp_s; row < a.NR * RQ; row += nwarps_s) {
+            const int wi = row / RQ, rr = row - wi * RQ;  // RQ is a compile-time constant
+            long long is = y0 - a.di_max + wi;
+            if (lost) is = is > M.i_zero ? is : M.i_zero;
+            is = is < M.nI - 1 ? is : M.nI - 1;  // upper clamp first; also the memory-safety clip
+            is = is > 0 ? is : 0;
+            const int q2 = min(q2_0 + rr, M.nQ - 1);
+            const double* __restrict__ src = a.Vn + is * strideX + ((M.lead == 2) ? (long long)q2 * M.nQ : 0);
+            // asynchronous 8-byte copies (LDGSTS): every load of the slab is in flight before any is
+            // waited for, so staging costs one memory latency instead of one per row
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(slab + (size_t)row * Apad);
+            for (int ai = lane_s; ai < A; ai += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)ai * 8u), "l"(src + ai));
+        }
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int g = tid / A, ai = tid - g * A;  // level group, action
+    const bool worker = g < a.NYT;
+    double acc[YT][RQ];
+#pragma unroll
+    for (int k = 0; k < YT; k++)
+#pragma unroll
+        for (int r = 0; r < RQ; r++) acc[k][r] = 0.0;
+
+    if (worker) {
+        const double av = (double)ai * M.step;
+        const double fv = (av > 0.0 ? M.K : 0.0) + M.v_t[a.t - 1] * av;  // Leadtime.java:73-74,79
+        const unsigned slab_s = (unsigned)__cvta_generic_to_shared(slab) + (unsigned)ai * 8u;
+        const unsigned lw_s = (unsigned)__cvta_generic_to_shared(Lw);
+        const unsigned pp_s = (unsigned)__cvta_generic_to_shared(PP);
+        const unsigned row_bytes = (unsigned)(RQ * Apad) * 8u;
+        // level slot k at demand j needs window row  wi = 4g + k + (D-1-j)
+        int wi0 = YT * g + (D - 1);
+        double cst[YT], Vw[YT][RQ];
+#pragma unroll
+        for (int k = 0; k < YT; k++) {
+            cst[k] = fv + lds_double(lw_s + (unsigned)(wi0 + k) * 8u);
+#pragma unroll
+            for (int r = 0; r < RQ; r++)
+                Vw[k][r] = LAST ? 0.0 : lds_double(slab_s + (unsigned)(wi0 + k) * row_bytes + (unsigned)(r * Apad) * 8u);
+        }
+#define SDPB_LEAD_STEP(JJ)                                                                          \
+        {                                                                                               \
+            const double2 pp = lds_double2(pp_s + (unsigned)j * 16u);                                   \
+            const int wn = max(wi0 - 1, 0);                                                             \
+            const double lnew = lds_double(lw_s + (unsigned)wn * 8u);                                   \
+            double vnew[RQ];                                                                            \
+            _Pragma("unroll") for (int r = 0; r < RQ; r++)                                              \
+                vnew[r] = LAST ? 0.0 : lds_double(slab_s + (unsigned)wn * row_bytes + (unsigned)(r * Apad) * 8u); \
+            _Pragma("unroll") for (int k = 0; k < YT; k++) {                                            \
+                const int ph = (k - (JJ)) & 3;                                                          \
+                const double m = pp.x * cst[ph];                    /* p_j * c(s,a,d_j) */            \
+                _Pragma("unroll") for (int r = 0; r < RQ; r++) {                                        \
+                    acc[k][r] += m;                                 /* LeadtimeRecursion.java:59 */    \
+                    if (!LAST) acc[k][r] += pp.y * Vw[ph][r];       /* LeadtimeRecursion.java:62 */    \
+                }                                                                                       \
+            }                                                                                           \
+            const int pn = (3 - (JJ)) & 3;                                                              \
+            cst[pn] = fv + lnew;                                                                        \
+            _Pragma("unroll") for (int r = 0; r < RQ; r++) Vw[pn][r] = vnew[r];                         \
+            wi0 -= 1;                                                                                   \
+            j += 1;                                                                                     \
+        }
+        int j = 0;
+        for (; j + 4 <= D;) { SDPB_LEAD_STEP(0) SDPB_LEAD_STEP(1) SDPB_LEAD_STEP(2) SDPB_LEAD_STEP(3) }
+        if (j < D) SDPB_LEAD_STEP(0)
+        if (j < D) SDPB_LEAD_STEP(1)
+        if (j < D) SDPB_LEAD_STEP(2)
+#undef SDPB_LEAD_STEP
+    }
+
+    // ---- Q-values to shared memory (aliasing the slab), then one warp per state picks the optimum ----
+    __syncthreads();
+    double* Qs = slab;  // [NYB][RQ][Apad]
+    if (worker) {
+#pragma unroll
+        for (int k = 0; k < YT; k++)
+#pragma unroll
+            for (int r = 0; r < RQ; r++) Qs[((size_t)(YT * g + k) * RQ + r) * Apad + ai] = acc[k][r];
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nwarps = a.nthreads >> 5;
+    for (int s = warp; s < NYB * RQ; s += nwarps) {
+        const int local = s / RQ, r = s - local * RQ;
+        const double* q = Qs + (size_t)s * Apad;
+        double best = IS_MIN ? DBL_MAX : -DBL_MAX;
+        int besti = kNoAction;
+        for (int i = lane; i < A; i += 32) {  // ascending within a lane: first optimum wins
+            const double v = q[i];
+            if (IS_MIN ? (v < best) : (v > best)) { best = v; besti = i; }
+        }
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, sh);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, sh);
+            if (better<IS_MIN>(ov, oi, best, besti)) { best = ov; besti = oi; }
+        }
+        if (lane == 0) {
+            const int lev = q1_0 + local;
+            const int q2 = q2_0 + r;
+            if (lev < n_levels && (M.lead != 2 || q2 < M.nQ)) {
+                long long idx = DEDUP ? (long long)lev : ix * M.nQ + lev;
+                if (M.lead == 2) idx = idx * M.nQ + q2;
+                if (idx >= a.lo && idx < a.hi) {
+                    a.Vt[idx] = best;
+                    a.Qt[idx] = besti == kNoAction ? -1 : besti;
+                }
+            }
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+struct LeadPlan {
+    bool ok = false;
+    int NYT = 0, RQ = 1, Apad = 0, nthreads = 0, di_max = 0, span = 0, NR = 0;
+    size_t smem = 0;
+};
+
+// Plan for one period; ok == false means "use bi_backorder_staged".
+inline LeadPlan plan_lead(const sdpb_model& m, const DevModel& d, int D, const int* di) {
+    LeadPlan P;
+    if (m.cost_kind != SDPB_COST_BACKORDER || m.lead_time < 1) return P;
+    int lo = di[0], hi = di[0];
+    for (int j = 0; j < D; j++) {
+        if (di[j] != di[0] + j) return P;  // the register window needs consecutive demands
+        lo = std::min(lo, di[j]);
+        hi = std::max(hi, di[j]);
+    }
+    const int A = d.max_order_idx + 1;
+    P.RQ = m.lead_time == 2 ? 4 : 1;
+    P.NYT = std::max(1, std::min(256 / A, 4));
+    if (A > 256) return P;
+    P.Apad = (A + 1) & ~1;
+    P.nthreads = std::min(256, ((P.NYT * A + 31) / 32) * 32);
+    P.di_max = hi;
+    P.span = hi - lo;
+    const int NYB = kLeadYT * P.NYT;
+    P.NR = NYB + P.span;
+    P.smem = ((size_t)std::max(P.NR, NYB) * P.RQ * P.Apad + ((P.NR + 1) & ~1)) * 8 + (size_t)D * 16 + 16;
+    P.ok = P.smem <= 110 * 1024;  // two CTAs per SM
+    return P;
+}
+
+template <bool DEDUP>
+inline int launch_lead(const LeadPlan& P, const DevModel& dm, int t, int D, int pmf_off, const double* Vn,
+                       double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream) {
+    if (hi <= lo) return SDPB_OK;
+    LeadArgs a;
+    a.t = t; a.D = D; a.pmf_off = pmf_off; a.Vn = Vn; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
+    a.NYT = P.NYT; a.A = dm.max_order_idx + 1; a.Apad = P.Apad; a.di_max = P.di_max; a.NR = P.NR;
+    a.nthreads = P.nthreads;
+    const int NYB = kLeadYT * P.NYT;
+    a.nq2_tiles = dm.lead == 2 ? (dm.nQ + P.RQ - 1) / P.RQ : 1;
+    long long rows;
+    if (DEDUP) {
+        a.ny_tiles = (dm.nI + dm.nQ - 1 + NYB - 1) / NYB;
+        a.row0 = 0;
+        rows = 1;
+    } else {
+        a.ny_tiles = (dm.nQ + NYB - 1) / NYB;
+        const long long per_x = dm.lead == 2 ? (long long)dm.nQ * dm.nQ : (long long)dm.nQ;
+        a.row0 = lo / per_x;
+        rows = (hi - 1) / per_x - a.row0 + 1;
+    }
+    const long long blocks = rows * a.ny_tiles * a.nq2_tiles;
+    const bool last = (t == dm.T), mn = dm.is_min != 0;
+    cudaError_t e = cudaSuccess;
+#define SDPB_LEAD_LAUNCH(MN, LS, RQ_)                                                                  \
+    {                                                                                                  \
+        auto k = bi_lead_slab<MN, LS, RQ_, DEDUP>;                                                     \
+        if (P.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem); \
+        if (e == cudaSuccess) k<<<(unsigned)blocks, P.nthreads, P.smem, stream>>>(dm, a);              \
+    }
+    if (P.RQ == 4) {
+        if (mn) { if (last) SDPB_LEAD_LAUNCH(true, true, 4) else SDPB_LEAD_LAUNCH(true, false, 4) }
+        else    { if (last) SDPB_LEAD_LAUNCH(false, true, 4) else SDPB_LEAD_LAUNCH(false, false, 4) }
+    } else {
+        if (mn) { if (last) SDPB_LEAD_LAUNCH(true, true, 1) else SDPB_LEAD_LAUNCH(true, false, 1) }
+        else    { if (last) SDPB_LEAD_LAUNCH(false, true, 1) else SDPB_LEAD_LAUNCH(false, false, 1) }
+    }
+#undef SDPB_LEAD_LAUNCH
+    if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+    return SDPB_OK;
+}
+
+}  // namespace sdpb

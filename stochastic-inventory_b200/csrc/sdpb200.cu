@@ -15,6 +15,7 @@
 #include "kernel_generic.cuh"
 #include "kernel_tiled.cuh"
 #include "kernel_cash.cuh"
+#include "kernel_lead.cuh"
 #include "microbench.cuh"
 
 using namespace sdpb;
@@ -49,6 +50,7 @@ struct sdpb_handle {
     sdpb_options opt{};
     std::vector<int> pmf_len, pmf_off;
     std::vector<double> pmf_d, pmf_p;
+    std::vector<int> pmf_di;  // demand values in units of step
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -266,7 +268,12 @@ int launch_staged(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt, 
     if (n <= 0) return SDPB_OK;
     const int D = h->pmf_len[t - 1];
     const size_t smem = (size_t)D * 16 + (size_t)8 * D * sizeof(StagedRow);
-    const long long blocks = (n + 7) / 8;
+    long long blocks = (n + 7) / 8;
+    if (h->dm.lead == 2 && !DEDUP) {  // CTA = 8 consecutive preQ1 of one (x, preQ2): see the kernel
+        const long long per_x = (long long)h->dm.nQ * h->dm.nQ;
+        const long long rows = (hi - 1) / per_x - lo / per_x + 1;
+        blocks = rows * ((h->dm.nQ + 7) / 8) * h->dm.nQ;
+    }
     cudaError_t e = cudaSuccess;
     if (h->dm.is_min) {
         auto k = bi_backorder_staged<true, DEDUP>;
@@ -289,6 +296,17 @@ bool staged_ok(const sdpb_handle* h, int t) {
 // Solve [lo, hi) of the real grid (or of the virtual grid when DEDUP) with the best kernel allowed.
 template <bool DEDUP>
 int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt, long long lo, long long hi) {
+    if (h->opt.kernel != SDPB_KERNEL_GENERIC && h->opt.kernel != SDPB_KERNEL_STAGED && h->m.lead_time >= 1 &&
+        h->m.cost_kind == SDPB_COST_BACKORDER) {
+        const LeadPlan lp = plan_lead(h->m, h->dm, h->pmf_len[t - 1], h->pmf_di.data() + h->pmf_off[t - 1]);
+        if (lp.ok) {
+            h->stats.kernel_used = SDPB_KERNEL_LEAD_SLAB;
+            const double ev = (double)(hi - lo) * (h->m.max_order_idx + 1) * h->pmf_len[t - 1];
+            const double q = 4.0 * lp.RQ;  // evaluations per thread per demand point
+            h->stats.fp64_ops += ev * (t == h->m.T ? (5.0 + q) / q : (5.0 + 3.0 * q) / q);
+            return launch_lead<DEDUP>(lp, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi, h->stream);
+        }
+    }
     if (h->opt.kernel != SDPB_KERNEL_GENERIC && staged_ok(h, t)) {
         h->stats.kernel_used = SDPB_KERNEL_STAGED;
         // per evaluation: add, mul, add (+ mul, add when a continuation exists)
@@ -466,6 +484,7 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         pdi[j] = (int)f;
         pg[j] = h->pmf_p[j] * m->gamma;  // first product of `p * gamma * V` (CashRecursion.java:120)
     }
+    h->pmf_di = pdi;
     // per-period parameter tables; deep copies so the caller's arrays may go away
     std::vector<double> price_t(T), v_t(T), ovh_t(T), res_t(T);
     for (int t = 0; t < T; t++) {

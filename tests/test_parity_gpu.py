@@ -108,9 +108,40 @@ def test_integer_cash_kernel_is_used(S):
         assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_GENERIC, spec.name
 
 
+@pytest.mark.parametrize("case", [cases.case_B1_ref, cases.case_B1_fixed, cases.case_B2_small],
+                         ids=lambda f: f.__name__[5:])
+@pytest.mark.parametrize("dedup", [False, True])
+def test_staged_kernel_whole_grid(case, dedup, S, oracle):
+    """bi_backorder_staged requested explicitly (AUTO prefers the slab kernel)."""
+    spec, _ = case()
+    Vo, Qo, _, _ = oracle.dense(spec)
+    s, V, Q = _solve_all(S, spec, kernel=S.KERNEL_STAGED, dedup=dedup)
+    assert np.array_equal(V, Vo) and np.array_equal(Q, Qo)
+    assert s.stats()["kernel_used"] == S.KERNEL_STAGED
+
+
+def test_lead_slab_wide_cases(S, oracle):
+    """Slab-kernel tile edges: preQ counts that are not multiples of 8 / 4, D not a multiple of 4,
+    lead time 1 and 2, clamped and unclamped, with and without folding."""
+    for (lead, max_order, means, clamp) in [(2, 9, [3, 4, 3], True), (2, 12, [5, 2], True), (1, 21, [6, 7, 5], True),
+                                            (1, 10, [3, 3, 3], False), (2, 4, [2, 2, 2], False)]:
+        p = S.poisson_pmf(means, 0.999)
+        dmax = max(r[-1, 0] for r in p)
+        T = len(means)
+        inv_min, inv_max = (-T * dmax, T * max_order) if not clamp else (-14, 17)
+        spec = S.leadtime_model(p, fixed_cost=4, vari_cost=1, hold_cost=2, penalty_cost=9, max_order=max_order,
+                                inv_min=inv_min, inv_max=inv_max, lead_time=lead, clamp=clamp)
+        Vo, Qo, _, _ = oracle.dense(spec)
+        for dedup in (False, True):
+            s, V, Q = _solve_all(S, spec, dedup=dedup)
+            assert s.stats()["kernel_used"] == S.KERNEL_LEAD_SLAB
+            assert np.array_equal(V, Vo) and np.array_equal(Q, Qo), (lead, max_order, clamp, dedup)
+
+
 def test_staged_kernel_is_used_for_leadtime(S):
     spec, _ = cases.case_B2_small()
-    assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_STAGED
+    assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_LEAD_SLAB
+    assert S.Solver(spec, kernel=S.KERNEL_STAGED).solve().stats()["kernel_used"] == S.KERNEL_STAGED
     assert S.Solver(spec, kernel=S.KERNEL_GENERIC).solve().stats()["kernel_used"] == S.KERNEL_GENERIC
     spec, _ = cases.case_A_small()
     assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_TILED  # small grid: 1-D tile variant
@@ -314,7 +345,8 @@ def test_config_c4_sampled(S, oracle):
     V3 = V.reshape(1001, 101, 101)
     assert np.array_equal(V3[100, 7, :], V3[107, 0, :]) and np.array_equal(V3[500, 50, :], V3[520, 30, :])
     # the folded solve and the generic kernel give the same tables as the staged brute-force kernel
-    for kw in ({"dedup": True}, {"kernel": S.KERNEL_GENERIC}):
+    assert s.stats()["kernel_used"] == S.KERNEL_LEAD_SLAB
+    for kw in ({"dedup": True}, {"kernel": S.KERNEL_GENERIC}, {"kernel": S.KERNEL_STAGED}):
         d = S.Solver(spec, **kw).solve()
         Vd, Qd = d.period_tables(1)
         assert np.array_equal(Vd, V) and np.array_equal(Qd, Q)
