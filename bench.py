@@ -303,7 +303,7 @@ def run_gpu(args):
             if world == 1:
                 v1, q1 = s2.solver.value(1, [[0.0] * s2.solver.ndim] if args.workload != "c3" else [[0.0, 100.0]])
                 V1, Q1 = s2.solver.period_tables(1)
-                d2h = s2.n * 12 + 12
+                d2h = s2.n * 16 + 16
             else:
                 s2.solver.sync()
                 dv, dq = s2.solver.device_tables(1)
@@ -366,14 +366,23 @@ def run_gpu(args):
         }
     sh.close()
 
-    # ---- the other configurations, solved once each (plus CPU baseline), rank 0 prints ----
+    # ---- the other configurations, solved once each (plus the C5 size sweep), rank 0 prints ----
     configs = {}
     if not args.no_configs:
-        for name in ("c1", "c2", "c3", "c4", "c4_dedup"):
-            dedup = name.endswith("_dedup")
-            name_key, name = name, name.split("_")[0]
-            sp = make_spec(S, name, world, args.states_per_gpu)
-            shard = name in ("c3", "c4") and world > 1
+        peak = None
+        if rank == 0:
+            peak = out["roofline"]["peak"]
+        jobs = [("c1", "c1", False, None), ("c2", "c2", False, None), ("c3", "c3", False, None),
+                ("c4", "c4", False, None), ("c4_dedup", "c4", True, None)]
+        for n_s in (10_000, 100_000, 1_000_000, 10_000_000, 100_000_000):
+            jobs.append((f"c5_S{n_s:.0e}".replace("+0", ""), "c5", False, n_s))
+        for name_key, name, dedup, n_s in jobs:
+            if n_s is not None:
+                sp = S.configs.c5(n_states=n_s)
+                shard = world > 1 and n_s >= 1_000_000
+            else:
+                sp = make_spec(S, name, world, args.states_per_gpu)
+                shard = name in ("c3", "c4") and world > 1
             w = world if shard else 1
             if not shard and rank != 0:
                 continue
@@ -383,8 +392,8 @@ def run_gpu(args):
                 csync = barrier if shard else torch.cuda.synchronize
                 s3.step()  # warm (plain launches)
                 csync()
-                ev, evx, _, _ = per_step_counts(s3, csync)  # second solve: captured as a CUDA graph when unsharded
-                reps = 5 if name in ("c1", "c2") else 1
+                ev, evx, fp, kused = per_step_counts(s3, csync)  # second solve: a CUDA graph when unsharded
+                reps = 5 if (name in ("c1", "c2") or (n_s or 10**9) <= 100_000) else 1
                 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a0.record(stream)
                 for _ in range(reps):
@@ -392,21 +401,24 @@ def run_gpu(args):
                 a1.record(stream)
                 torch.cuda.synchronize()
                 cms = a0.elapsed_time(a1) / reps
-                tt = torch.tensor([cms, ev, evx], dtype=torch.float64, device=f"cuda:{local}")
+                tt = torch.tensor([cms, ev, evx, fp], dtype=torch.float64, device=f"cuda:{local}")
                 if shard:
                     mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
                     sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-                    cms, ev, evx = float(mx[0]), float(sm[1]), float(sm[2])
-                init = {"c1": [[0.0]], "c2": [[0.0]], "c3": [[0.0, 100.0]], "c4": [[0.0, 0.0, 0.0]]}[name]
+                    cms, ev, evx, fp = float(mx[0]), float(sm[1]), float(sm[2]), float(sm[3])
+                init = {"c1": [[0.0]], "c2": [[0.0]], "c3": [[0.0, 100.0]], "c4": [[0.0, 0.0, 0.0]], "c5": [[0.0]]}[name]
                 v0 = q0 = None
                 if not shard:
                     v, q = s3.solver.value(1, init)
                     v0, q0 = float(v[0]), float(q[0])
+                tops = fp / (cms * 1e-3) / 1e12 / w
                 configs[name_key] = {"solve_ms": cms, "evals": ev, "evals_per_s": ev / (cms * 1e-3),
-                                     "evals_executed": evx, "n_gpus": w,
-                                     "kernel": KERNEL_NAMES.get(s3.solver.stats()["kernel_used"]),
-                                     "dedup": dedup, "V1_init": v0, "Q1_init": q0}
+                                     "evals_executed": evx, "n_gpus": w, "kernel": KERNEL_NAMES.get(kused),
+                                     "dedup": dedup, "fp64_tops_per_gpu": tops, "V1_init": v0, "Q1_init": q0}
                 s3.close()
+        if rank == 0:
+            for c in configs.values():
+                c["fp64_frac"] = c["fp64_tops_per_gpu"] / peak if peak else None
     if rank == 0:
         out["configs"] = configs
         if not args.no_cpu_baseline:

@@ -77,7 +77,16 @@ typedef enum sdpb_cost_kind {
     SDPB_COST_CASH_OVERDRAFT = 2,
     /* (x, R = w + v*x) re-parameterisation, action = order-up-to level y:
      * CashConstraintXR.java:71-110 with CashRecursionXR.java:79-125                   */
-    SDPB_COST_CASH_XR = 3
+    SDPB_COST_CASH_XR = 3,
+    /* overdraft with one loan rate (r2) and one deposit rate on the balance after ordering, holding and
+     * overhead costs: src/cash/overdraft/CashOverdraftLimit.java:70-86 */
+    SDPB_COST_CASH_OD_LIMIT = 4,
+    /* loan interest on the balance after revenue; the transition recomputes the cash balance itself
+     * instead of adding the immediate value: src/cash/overdraft/CashOverdraftTesting.java:85-118 */
+    SDPB_COST_CASH_OD_TESTING = 5,
+    /* deposit interest on max(w - v a, 0), loan interest (r2) on max(v a - w, 0), no holding cost in
+     * the last period: src/cash/overdraft/TestPaper.java:82-93 */
+    SDPB_COST_CASH_LOAN = 6
 } sdpb_cost_kind;
 
 typedef enum sdpb_recursion {
@@ -91,8 +100,10 @@ typedef enum sdpb_direction { SDPB_MIN = 0, SDPB_MAX = 1 } sdpb_direction;
 /* Cash quantiser applied after the cash clamp.
  *   kk = Math.round(w * q_mul)                 (Java round-half-up to long)
  *   SDPB_Q_DIV      w' = (double)kk / q_div            e.g. round(w*10)/10.0
- *   SDPB_Q_LONGDIV  w' = (double)(kk / (long)q_div)    e.g. round(w*10)/10  (long division) */
-typedef enum sdpb_quantiser { SDPB_Q_DIV = 0, SDPB_Q_LONGDIV = 1 } sdpb_quantiser;
+ *   SDPB_Q_LONGDIV  w' = (double)(kk / (long)q_div)    e.g. round(w*10)/10  (long division)
+ *   SDPB_Q_TRUNC    w' = (double)(int) w, preceded from period q_from_period on (t >= q_from_period > 0) by
+ *                   w = Math.round(w * q_mul) / q_div     (TestPaper.java:107-109: t > 2, 1e-4) */
+typedef enum sdpb_quantiser { SDPB_Q_DIV = 0, SDPB_Q_LONGDIV = 1, SDPB_Q_TRUNC = 2 } sdpb_quantiser;
 
 enum sdpb_flags {
     SDPB_F_CLAMP_INV = 1u << 0,        /* x' = clamp(x', inv_min, inv_max), upper clamp first
@@ -132,7 +143,7 @@ typedef struct sdpb_model {
     /* cash axis (cash kinds only): clamp to [cash_min, cash_max], then quantise */
     double  cash_min, cash_max;
     int32_t quantiser;      /* sdpb_quantiser */
-    int32_t reserved0;
+    int32_t q_from_period;  /* SDPB_Q_TRUNC only; 0 = never round */
     double  q_mul, q_div;
 
     /* cost parameters (unused ones are ignored) */

@@ -29,7 +29,7 @@ public final class SdpB200 {
             ADDRESS.withName("pmf_len"), ADDRESS.withName("pmf_d"), ADDRESS.withName("pmf_p"),
             JAVA_DOUBLE.withName("inv_min"), JAVA_DOUBLE.withName("inv_max"), JAVA_DOUBLE.withName("step"),
             JAVA_DOUBLE.withName("cash_min"), JAVA_DOUBLE.withName("cash_max"),
-            JAVA_INT.withName("quantiser"), JAVA_INT.withName("reserved0"),
+            JAVA_INT.withName("quantiser"), JAVA_INT.withName("q_from_period"),
             JAVA_DOUBLE.withName("q_mul"), JAVA_DOUBLE.withName("q_div"),
             JAVA_DOUBLE.withName("fixed_cost"), JAVA_DOUBLE.withName("vari_cost"), JAVA_DOUBLE.withName("hold_cost"),
             JAVA_DOUBLE.withName("penalty_cost"), JAVA_DOUBLE.withName("price"), JAVA_DOUBLE.withName("salvage"),

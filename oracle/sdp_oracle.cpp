@@ -4,15 +4,24 @@
 // __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs and by nothing
 // else; the product library never links or calls it.
 //
-// PARITY UNPINNED: the reference (Java 21 + SSJ 3.3.0) cannot run in the build container (no JDK,
-// no jar) and its repository holds no golden vectors, fixtures or known-answer tests for this
-// path.  What pins this restatement instead:
-//   * it is written line-by-line after the Java sources cited at each function;
-//   * two independent evaluation orders of it — `oracle_topdown` (memoised recursion over
-//     real-valued states in ordered maps, exactly the reference's control flow) and
-//     `oracle_dense` (period-by-period over the full grid, states addressed by index) — must
-//     agree bit-for-bit on every state the recursion visits (tests/test_oracle.py);
-//   * closed-form cases (deterministic demand, single action) in tests/test_oracle.py.
+// HOW THIS ORACLE IS PINNED.  The reference (Java 21 + SSJ 3.3.0) cannot run in the build container (no
+// JDK, no jar) and its repository holds no golden vectors, fixtures or known-answer tests for this path
+// (SURVEY.md §4, §8c).  The only program outputs the reference records are in the header comment of
+// src/cash/overdraft/MultiProductLeadtime.java:30-50 (a two-product model built on a copy of the same
+// loop).  `oracle_multi_lead` below drives THIS file's solve_state / TopDown with that model's lambdas
+// and reproduces two of those outputs to the last digit:
+//     T = 2, demands {20,30,40}x{10,15,20}:  -17.800000000000008, Q1 = 40, Q2 = 20   (tests/test_oracle.py)
+//     T = 3, demands {10,30}x{5,15}:         -76.56,              Q1 = 30, Q2 = 15   (34 CPU-min, opt-in)
+// which pins the loop order (s += p*c; s += p*gamma*V), the init / strict-compare / first-wins rule,
+// the memo-map control flow, the four-branch overdraft interest and the clamp / (int) idioms against
+// the real Java program.  PARITY UNPINNED for the rest: the single-product lambdas of each family and
+// the SSJ-built pmf tables have no recorded reference output; they are held in place by
+//   * being written line-by-line after the Java sources cited at each function;
+//   * two independent evaluation orders — `oracle_topdown` (memoised recursion over real-valued states
+//     in ordered maps, exactly the reference's control flow) and `oracle_dense` (period-by-period over
+//     the full grid, states addressed by index) — agreeing bit-for-bit on every visited state;
+//   * a pure-Python transliteration of Recursion.java + the family-A and family-C lambdas, closed-form
+//     cases, and the survey's independent scratch value for C1 (tests/test_oracle.py).
 //
 // Arithmetic: IEEE-754 double, operations in the order the Java source writes them, compiled
 // with -ffp-contract=off (Java never fuses a multiply-add).
@@ -64,10 +73,25 @@ inline double jmin(double a, double b) {
 struct St {  // State / LeadtimeState / CashState / CashLeadtimeState / RiskState / CashStateXR
     int t;   // 1-based period
     double x = 0, w = 0, q1 = 0, q2 = 0;  // w holds R for the XR kind
+    double x2 = 0;                         // second product's inventory (two-product known-answer model only)
+};
+
+// Parameters of the reference's two-product cash + lead-time model (src/cash/overdraft/
+// MultiProductLeadtime.java:86-118), used only to pin this file's loop against the program output the
+// reference author recorded in that file's header comment.
+struct MultiLead {
+    int Qbound = 50;
+    double price[2] = {5, 10}, variCost[2] = {1, 2}, salValueUnit[2] = {0.5, 1.0};
+    double r0 = 0, r1 = 0.1, r2 = 2, limit = 500, interestFreeAmount = 0;
+    double minInventoryState = 0, maxInventoryState = 200, minCashState = -500, maxCashState = 5000;
+    std::vector<double> overheadCost;
+    std::vector<int> d1, d2;  // demand pairs, same table every period (GetPmfMulti.java:158-171)
 };
 
 struct Model {
     sdpb_model m;
+    const MultiLead* multi = nullptr;
+    double tie_tol = 0.0;  // CashRecursionMultiLead.java:82 accepts an action only if it is better by > 0.1
     std::vector<int> off;  // pmf offsets
     int ndemand(int t) const { return m.pmf_len[t - 1]; }
     double d(int t, int j) const { return m.pmf_d[off[t - 1] + j]; }
@@ -83,26 +107,32 @@ struct Model {
     // integer cash index of a cash value that is already on the quantised grid
     int64_t cash_k(double w) const {
         if (m.cost_kind == SDPB_COST_CASH_XR) return jround(w);
-        return m.quantiser == SDPB_Q_DIV ? jround(w * m.q_div) : (int64_t)w;
+        return m.quantiser == SDPB_Q_DIV ? jround(w * m.q_div) : (int64_t)w;  // LONGDIV, TRUNC: integers
     }
     double cash_of_k(int64_t k) const {
         if (m.cost_kind == SDPB_COST_CASH_XR) return (double)k;
         return m.quantiser == SDPB_Q_DIV ? (double)k / m.q_div : (double)k;
     }
-    double quantise(double w) const {
+    // `t` is the period of the state being left (TestPaper.java:107 rounds only when t > 2)
+    double quantise(double w, int t = 1 << 30) const {
+        if (m.quantiser == SDPB_Q_TRUNC) {  // TestPaper.java:107-109
+            if (m.q_from_period > 0 && t >= m.q_from_period) w = (double)jround(w * m.q_mul) / m.q_div;
+            return (double)(int)w;
+        }
         int64_t kk = jround(w * m.q_mul);
         if (m.quantiser == SDPB_Q_DIV) return (double)kk / m.q_div;
         return (double)(kk / (int64_t)m.q_div);  // Java long division truncates toward zero
     }
+    double trunc_only(double w) const { return m.quantiser == SDPB_Q_TRUNC ? (double)(int)w : quantise(w); }
     int64_t k_min() const {
         if (m.cost_kind == SDPB_COST_CASH_XR)
             return jround(quantise(m.cash_min) + m.vari_cost * m.inv_min);
-        return cash_k(quantise(m.cash_min));
+        return cash_k(trunc_only(m.cash_min));
     }
     int64_t k_max() const {
         if (m.cost_kind == SDPB_COST_CASH_XR)
             return jround(quantise(m.cash_max) + m.vari_cost * m.inv_max);
-        return cash_k(quantise(m.cash_max));
+        return cash_k(trunc_only(m.cash_max));
     }
     int n_cash() const { return cash() ? (int)(k_max() - k_min() + 1) : 1; }
     int64_t n_states() const {
@@ -118,6 +148,7 @@ struct Model {
 // CashConstraintXR.java:71-75 (order-up-to levels from x).
 int n_actions(const Model& M, const St& s) {
     const sdpb_model& m = M.m;
+    if (M.multi) return M.multi->Qbound * M.multi->Qbound;  // MultiProductLeadtime.java:150-158
     if (m.cost_kind == SDPB_COST_CASH_XR) {
         double v = M.vcost(s.t);
         double maxY = s.w / v < s.x ? s.x : s.w / v;
@@ -132,14 +163,70 @@ int n_actions(const Model& M, const St& s) {
     return (int)maxQ + 1;
 }
 inline double action_value(const Model& M, const St& s, int i) {
+    if (M.multi) return (double)i;  // flat index of the pair (i / Qbound, i % Qbound), i-major as in the driver
     if (M.m.cost_kind == SDPB_COST_CASH_XR) return s.x + i * M.m.step;
     return i * M.m.step;
+}
+
+// ---- the two-product model (known-answer pin only) -----------------------------------------------
+// MultiProductLeadtime.java:162-198
+double multi_immediate(const Model& M, const St& s, int a1, int a2, int d1, int d2) {
+    const MultiLead& p = *M.multi;
+    double action1 = a1, action2 = a2, demand1 = d1, demand2 = d2;
+    double preQ1 = s.q1, preQ2 = s.q2;
+    double endInventory1 = jmax(0, s.x + preQ1 - demand1);
+    double endInventory2 = jmax(0, s.x2 + preQ2 - demand2);
+    double revenue1 = p.price[0] * jmin(demand1, s.x + preQ1);
+    double revenue2 = p.price[1] * jmin(s.x2 + preQ2, demand2);
+    double revenue = revenue1 + revenue2;
+    double orderingCost1 = p.variCost[0] * action1;
+    double orderingCost2 = p.variCost[1] * action2;
+    double orderingCosts = orderingCost1 + orderingCost2;
+    double salValue = 0;
+    if (s.t == M.m.T) salValue = p.salValueUnit[0] * endInventory1 + p.salValueUnit[1] * endInventory2;
+    int t = s.t - 1;
+    double cashBalanceBefore = s.w - orderingCosts - p.overheadCost[t];
+    double interest = 0;
+    if (cashBalanceBefore >= 0)
+        interest = -p.r0 * cashBalanceBefore;
+    else if (cashBalanceBefore >= -p.interestFreeAmount)
+        interest = 0;
+    else if (cashBalanceBefore >= -p.limit)
+        interest = p.r1 * (-cashBalanceBefore - p.interestFreeAmount);
+    else
+        interest = p.r2 * (-cashBalanceBefore - p.limit) + p.r1 * (p.limit - p.interestFreeAmount);
+    double cashBalanceAfter = cashBalanceBefore - interest + revenue + salValue;
+    double cashIncrement = cashBalanceAfter - s.w;
+    return cashIncrement;
+}
+
+// MultiProductLeadtime.java:202-224 (asymmetric clamps as written there)
+St multi_transition(const Model& M, const St& s, int a1, int a2, int d1, int d2) {
+    const MultiLead& p = *M.multi;
+    double endInventory1 = s.x + s.q1 - d1;
+    endInventory1 = jmax(0, endInventory1);
+    double endInventory2 = s.x2 + s.q2 - d2;
+    endInventory2 = jmax(0, endInventory2);
+    double nextCash = s.w + multi_immediate(M, s, a1, a2, d1, d2);
+    nextCash = nextCash > p.maxCashState ? p.maxCashState : nextCash;
+    nextCash = nextCash < p.minCashState ? p.minCashState : nextCash;
+    endInventory1 = endInventory1 > p.maxInventoryState ? p.maxInventoryState : endInventory1;
+    endInventory2 = endInventory2 < p.minInventoryState ? p.minInventoryState : endInventory2;
+    endInventory1 = (int)endInventory1;
+    endInventory2 = (int)endInventory2;
+    St n;
+    n.t = s.t + 1; n.x = endInventory1; n.x2 = endInventory2; n.q1 = a1; n.q2 = a2; n.w = nextCash;
+    return n;
 }
 
 // ---- immediate value ------------------------------------------------------------------------
 double immediate(const Model& M, const St& s, double action, double demand) {
     const sdpb_model& m = M.m;
     const int T = m.T;
+    if (M.multi) {  // action = flat action index, demand = flat demand index
+        const int i = (int)action, j = (int)demand, Q = M.multi->Qbound;
+        return multi_immediate(M, s, i / Q, i % Q, M.multi->d1[j], M.multi->d2[j]);
+    }
     switch (m.cost_kind) {
     case SDPB_COST_BACKORDER: {
         // CLSPTesting.java:96-106; lead time: Leadtime.java:71-81; G(y) pass: CLSPforDraw.java:156-170
@@ -197,6 +284,48 @@ double immediate(const Model& M, const St& s, double action, double demand) {
         cashIncrement += salValue;
         return cashIncrement;
     }
+    case SDPB_COST_CASH_OD_LIMIT: {
+        // CashOverdraftLimit.java:70-86
+        double revenue = M.price(s.t) * jmin(s.x + action, demand);
+        double fixedCost = action > 0 ? m.fixed_cost : 0;
+        double variableCost = M.vcost(s.t) * action;
+        double inventoryLevel = s.x + action - demand;
+        double holdCosts = m.hold_cost * jmax(inventoryLevel, 0);
+        double cashBalanceBeforeRevenue = s.w - fixedCost - variableCost - holdCosts - M.ovh(s.t);
+        double interest = m.r2 * jmax(-cashBalanceBeforeRevenue, 0);
+        double deposite = m.deposit_rate * jmax(cashBalanceBeforeRevenue, 0);
+        double cashBalanceAfter = cashBalanceBeforeRevenue - interest + deposite + revenue;
+        double cashIncrement = cashBalanceAfter - s.w;
+        double salValue = s.t == T ? m.salvage * jmax(inventoryLevel, 0) : 0;
+        cashIncrement += salValue;
+        return cashIncrement;
+    }
+    case SDPB_COST_CASH_OD_TESTING: {
+        // CashOverdraftTesting.java:85-99
+        double revenue = M.price(s.t) * jmin(s.x + action, demand);
+        double fixedCost = action > 0 ? m.fixed_cost : 0;
+        double variableCost = M.vcost(s.t) * action;
+        double inventoryLevel = s.x + action - demand;
+        double holdCosts = m.hold_cost * jmax(inventoryLevel, 0);
+        double cashBalanceBefore = s.w + revenue - fixedCost - variableCost - holdCosts;
+        double interest = m.r2 * jmax(-cashBalanceBefore, 0);
+        double cashBalanceAfter = cashBalanceBefore - interest;
+        double cashIncrement = cashBalanceAfter - s.w;
+        return cashIncrement;
+    }
+    case SDPB_COST_CASH_LOAN: {
+        // TestPaper.java:82-93
+        double revenue = M.price(s.t) * jmin(s.x + action, demand);
+        double variableCost = M.vcost(s.t) * action;
+        double inventoryLevel = s.x + action - demand;
+        double holdCosts = s.t == T ? 0 : m.hold_cost * jmax(inventoryLevel, 0);
+        double deposites = m.deposit_rate * jmax(s.w - variableCost, 0);
+        double loanPayed = m.r2 * jmax(variableCost - s.w, 0);
+        double cashIncrement = revenue - variableCost - holdCosts + deposites - loanPayed;
+        double salValue = s.t == T ? m.salvage * jmax(inventoryLevel, 0) : 0;
+        cashIncrement += salValue;
+        return cashIncrement;
+    }
     case SDPB_COST_CASH_XR: {
         // CashConstraintXR.java:78-92 (action is the order-up-to level y; s.w holds R)
         double v = M.vcost(s.t);
@@ -222,6 +351,10 @@ double immediate(const Model& M, const St& s, double action, double demand) {
 // ---- state transition -----------------------------------------------------------------------
 St transition(const Model& M, const St& s, double action, double demand) {
     const sdpb_model& m = M.m;
+    if (M.multi) {
+        const int i = (int)action, j = (int)demand, Q = M.multi->Qbound;
+        return multi_transition(M, s, i / Q, i % Q, M.multi->d1[j], M.multi->d2[j]);
+    }
     St n;
     n.t = s.t + 1;
     if (m.cost_kind == SDPB_COST_BACKORDER) {
@@ -258,13 +391,22 @@ St transition(const Model& M, const St& s, double action, double demand) {
         double nextInventory = stock - demand;
         if (M.flag(SDPB_F_LOST_SALES)) nextInventory = jmax(0, nextInventory);
         double nextCash = s.w + immediate(M, s, action, demand);
+        if (m.cost_kind == SDPB_COST_CASH_OD_TESTING) {
+            // CashOverdraftTesting.java:103-111: the transition recomputes the balance itself
+            double revenue = M.price(s.t) * jmin(s.x + action, demand);
+            double fixedCost = action > 0 ? m.fixed_cost : 0;
+            double variableCost = M.vcost(s.t) * action;
+            double holdCosts = m.hold_cost * jmax(nextInventory, 0);
+            nextCash = s.w + revenue - fixedCost - variableCost - holdCosts;
+            nextCash = nextCash - jmax(-nextCash, 0) * m.r2;
+        }
         nextCash = nextCash > m.cash_max ? m.cash_max : nextCash;
         nextCash = nextCash < m.cash_min ? m.cash_min : nextCash;
         if (M.flag(SDPB_F_CLAMP_INV)) {
             nextInventory = nextInventory > m.inv_max ? m.inv_max : nextInventory;
             nextInventory = nextInventory < m.inv_min ? m.inv_min : nextInventory;
         }
-        nextCash = M.quantise(nextCash);
+        nextCash = M.quantise(nextCash, s.t);
         n.x = nextInventory;
         n.w = nextCash;
     }
@@ -318,10 +460,12 @@ void solve_state(const Model& M, const St& s, NextValue&& next_value, double* va
                 }
             }
         }
+        // strict compare (Recursion.java:147,153); M.tie_tol is 0 except for the two-product pin, where
+        // the reference writes `> val + 0.1` (CashRecursionMultiLead.java:82).  val +/- 0.0 == val exactly.
         if (is_min) {
-            if (thisQValue < val) { val = thisQValue; bestOrderQty = orderQty; }
+            if (thisQValue < val - M.tie_tol) { val = thisQValue; bestOrderQty = orderQty; }
         } else {
-            if (thisQValue > val) { val = thisQValue; bestOrderQty = orderQty; }
+            if (thisQValue > val + M.tie_tol) { val = thisQValue; bestOrderQty = orderQty; }
         }
     }
     if (evals) *evals += (double)nA * D;
@@ -338,6 +482,7 @@ struct KeyLess {
     bool operator()(const St& a, const St& b) const {
         if (a.t != b.t) return a.t < b.t;
         if (a.x != b.x) return a.x < b.x;
+        if (a.x2 != b.x2) return a.x2 < b.x2;  // CashRecursionMultiLead.java:45-51 (0 otherwise)
         if (a.q1 != b.q1) return a.q1 < b.q1;
         if (a.q2 != b.q2) return a.q2 < b.q2;
         return a.w < b.w;
@@ -521,6 +666,45 @@ int64_t oracle_topdown(const sdpb_model* m, const double* init_states, int n_ini
         }
     }
     return n;
+}
+
+// The reference's two-product cash + lead-time model, solved top-down from the all-zero state with THIS
+// file's solve_state / TopDown (the loop every parity test relies on).  `vals1/probs1`, `vals2/probs2`:
+// the discrete demand distributions of the two products (n points each).  Returns the optimal value
+// and first-period order quantities; used to reproduce the outputs recorded in
+// src/cash/overdraft/MultiProductLeadtime.java:30-50.
+int oracle_multi_lead(int T, int Qbound, int n, const double* vals1, const double* probs1, const double* vals2,
+                      const double* probs2, double overhead, double* value, int* q1, int* q2, int64_t* n_states) {
+    MultiLead ml;
+    ml.Qbound = Qbound;
+    ml.overheadCost.assign(T, overhead);
+    std::vector<double> pd, pp;
+    for (int i = 0; i < n; i++)  // GetPmfMulti.java:158-171
+        for (int j = 0; j < n; j++) {
+            ml.d1.push_back((int)vals1[i]);
+            ml.d2.push_back((int)vals2[j]);
+            pd.push_back((double)(i * n + j));  // "demand" handed to the loop = flat pair index
+            pp.push_back(probs1[i] * probs2[j]);
+        }
+    std::vector<int32_t> len(T, n * n);
+    std::vector<double> d_all, p_all;
+    for (int t = 0; t < T; t++) { d_all.insert(d_all.end(), pd.begin(), pd.end()); p_all.insert(p_all.end(), pp.begin(), pp.end()); }
+    sdpb_model m;
+    std::memset(&m, 0, sizeof(m));
+    m.T = T; m.direction = SDPB_MAX; m.recursion = SDPB_REC_EXPECT; m.gamma = 1.0;
+    m.pmf_len = len.data(); m.pmf_d = d_all.data(); m.pmf_p = p_all.data();
+    Model M = make_model(&m);
+    M.multi = &ml;
+    M.tie_tol = 0.1;
+    TopDown td(M);
+    St ini; ini.t = 1;
+    double v = td.getExpectedValue(ini);
+    double best = td.cacheActions[ini];
+    *value = 0.0 + v;  // iniCash + recursion.getExpectedValue(iniState), MultiProductLeadtime.java:236
+    *q1 = (int)best / Qbound;
+    *q2 = (int)best % Qbound;
+    if (n_states) *n_states = (int64_t)td.cacheValues.size();
+    return 0;
 }
 
 // One backward-induction step for selected states: given the full period-(t+1) value table

@@ -20,9 +20,10 @@ STATUS_NAMES = {0: "SDPB_OK", -1: "SDPB_ERR_ARG", -2: "SDPB_ERR_OFFGRID", -3: "S
                 -4: "SDPB_ERR_CUDA", -5: "SDPB_ERR_STATE", -6: "SDPB_ERR_NOMEM", -7: "SDPB_ERR_UNSOLVED"}
 
 COST_BACKORDER, COST_CASH_DEPOSIT, COST_CASH_OVERDRAFT, COST_CASH_XR = 0, 1, 2, 3
+COST_CASH_OD_LIMIT, COST_CASH_OD_TESTING, COST_CASH_LOAN = 4, 5, 6
 REC_EXPECT, REC_SURVIVAL = 0, 1
 MIN, MAX = 0, 1
-Q_DIV, Q_LONGDIV = 0, 1
+Q_DIV, Q_LONGDIV, Q_TRUNC = 0, 1, 2
 F_CLAMP_INV, F_LOST_SALES, F_GY_MODE, F_NO_ORDER_LAST, F_CASH_LIMITED_ACTIONS = 1, 2, 4, 8, 16
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED, KERNEL_STAGED, KERNEL_CASH_INT, KERNEL_TILED2, KERNEL_LEAD_SLAB = 0, 1, 2, 3, 4, 5, 6
 
@@ -38,7 +39,7 @@ class SdpbModel(C.Structure):
         ("pmf_len", _ip), ("pmf_d", _dp), ("pmf_p", _dp),
         ("inv_min", C.c_double), ("inv_max", C.c_double), ("step", C.c_double),
         ("cash_min", C.c_double), ("cash_max", C.c_double),
-        ("quantiser", C.c_int32), ("reserved0", C.c_int32),
+        ("quantiser", C.c_int32), ("q_from_period", C.c_int32),
         ("q_mul", C.c_double), ("q_div", C.c_double),
         ("fixed_cost", C.c_double), ("vari_cost", C.c_double), ("hold_cost", C.c_double),
         ("penalty_cost", C.c_double), ("price", C.c_double), ("salvage", C.c_double),

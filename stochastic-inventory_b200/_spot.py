@@ -22,8 +22,11 @@ def random_triple(spec, rng):
             vec.append(float(rng.randint(int(spec.cash_min), int(spec.cash_max))))
         else:
             lo, hi = int(np.ceil(spec.cash_min * spec.q_mul)), int(np.floor(spec.cash_max * spec.q_mul))
-            kk = rng.randint(lo, hi)
-            vec.append(kk / spec.q_div if spec.quantiser == A.Q_DIV else float(int(kk / int(spec.q_div))))
+            if spec.quantiser == A.Q_TRUNC:
+                vec.append(float(rng.randint(int(spec.cash_min), int(spec.cash_max))))
+            else:
+                kk = rng.randint(lo, hi)
+                vec.append(kk / spec.q_div if spec.quantiser == A.Q_DIV else float(int(kk / int(spec.q_div))))
     for _ in range(spec.lead_time):
         vec.append(rng.randrange(spec.max_order_idx + 1) * spec.step)
     row = np.asarray(spec.pmf[t - 1])

@@ -29,6 +29,8 @@ struct DevModel {
     double neg_r0, r2, r3, od_limit, interest_free;
     double r2_limit_term; // r2 * (limit - interestFreeAmount)   (CashOverdraft.java:95)
     double reserve2;
+    double dr;            // depositeRate itself (CashOverdraftLimit.java:79, TestPaper.java:87)
+    int q_from_period;    // SDPB_Q_TRUNC: round with (q_mul, q_div) from this period on; 0 = never
     // per-period parameter tables, always expanded to T entries on the host
     const double* price_t;
     const double* v_t;

@@ -15,8 +15,8 @@
 //   * once d_j >= y the sale is y units whatever the demand: successor and immediate value are
 //     constant over the rest of the demand loop, so V_{t+1} is read once for all of those j.
 // Per evaluation that leaves 3 + 2/R fp64 instructions (mul, add, add) and one coalesced 8-byte
-// gather of V_{t+1} (lanes hold consecutive cash levels).  The last period (salvage, terminal
-// indicator) runs on the generic kernel.
+// gather of V_{t+1} (lanes hold consecutive cash levels).  In the last period there is no successor:
+// c = (exact integer part) + salvage*max(level,0) is shared by the R cash levels.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -53,7 +53,7 @@ struct CashArgs {
     int price, v, K, ovh, d0, inv_min_i;
 };
 
-template <bool SURVIVAL, bool IS_MIN>
+template <bool SURVIVAL, bool IS_MIN, bool LAST>
 __global__ void __launch_bounds__(kCashThreads)
 bi_cash_int(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs a) {
     constexpr int R = kCashR;
@@ -75,7 +75,7 @@ bi_cash_int(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs
     const double res = M.reserve_t[a.t - 1];
 
     int iw[R], nA[R], arg[R];
-    double best[R];
+    double best[R], wd[R];
     bool valid[R];
     int nAmax = 0;
 #pragma unroll
@@ -85,6 +85,7 @@ bi_cash_int(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs
         valid[r] = iw[r] < M.nW && idx >= a.lo && idx < a.hi;
         iw[r] = min(iw[r], M.nW - 1);
         const double w = (double)(M.kmin + iw[r]);
+        wd[r] = w;
         int n = M.max_order_idx + 1;
         if (M.flags & SDPB_F_CASH_LIMITED_ACTIONS) {  // CashConstraint.java:96-99
             const double bound = fmax(0.0, ((w - res) - M.reserve2) / v_d);
@@ -106,53 +107,73 @@ bi_cash_int(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs
 #pragma unroll
         for (int r = 0; r < R; r++) acc[r] = 0.0;
 
-        // ---- demand below the stock: sale = d_j, successor inventory y - d_j > 0 ----
-        // All index arithmetic is 32-bit (plan_cash checks nI*nW < 2^31): the successor's flat index
-        // is clamp(rowoff + iw + shift, rowoff, rowoff + nW-1), one add-max and one min per level.
-#pragma unroll 2
-        for (int j = 0; j < jy; j++) {
-            const double2 pp = PP[j];
-            int il = ix + ai - (a.d0 + j);                    // successor inventory index
-            il = min(il, M.nI - 1);
-            il = max(il, 0);
-            const int rowoff = il * M.nW;
-            const int kk0 = rowoff + PRi[j] - CI;             // + iw[r] = unclamped flat index
-            const int khi = rowoff + nW1;
-            double m = 0.0;
-            if (!SURVIVAL) m = pp.x * (PRd[j] - Cd);          // p_j * c(s,a,d_j)
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int k = min(max(kk0 + iw[r], rowoff), khi);  // clamp to [cash_min, cash_max]
-                double vn = __ldg(a.Vn + (unsigned)k);
-                if (SURVIVAL && k - rowoff < -M.kmin) vn = 0.0;  // successor cash < 0: RiskRecursion.java:87-95
-                if (!SURVIVAL) acc[r] += m;                    // CashRecursion.java:117
-                acc[r] += pp.y * vn;                           // CashRecursion.java:120
-            }
-        }
-        // ---- stock-out: sale = y for every remaining demand, successor inventory 0 ----
-        if (jy < a.D) {
-            const int PYi = a.price * yv;
-            const int il = min(max(M.i_zero, 0), M.nI - 1);
-            const int rowoff = il * M.nW;
-            const int kk0 = rowoff + PYi - CI;
-            const int khi = rowoff + nW1;
-            const double inc = (double)PYi - Cd;
-            double vn[R];
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int k = min(max(kk0 + iw[r], rowoff), khi);
-                vn[r] = __ldg(a.Vn + (unsigned)k);
-                if (SURVIVAL && k - rowoff < -M.kmin) vn[r] = 0.0;
-            }
-#pragma unroll 2
-            for (int j = jy; j < a.D; j++) {
+        if (LAST) {
+            // terminal period: no successor.  c = exact integer part + salvage * max(level, 0)
+            // (CashConstraint.java:112-113); the survival recursion scores 1[w + c >= 0]
+            // (RiskRecursion.java:80-84).
+            for (int j = 0; j < a.D; j++) {
                 const double2 pp = PP[j];
+                double c;
+                if (j < jy) c = (PRd[j] - Cd) + M.salvage * (double)(yv - (a.d0 + j));
+                else c = ((double)(a.price * yv) - Cd) + M.salvage * 0.0;
+                if (!SURVIVAL) {
+                    const double m = pp.x * c;
+#pragma unroll
+                    for (int r = 0; r < R; r++) acc[r] += m;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; r++) acc[r] += pp.x * ((wd[r] + c) >= 0.0 ? 1.0 : 0.0);
+                }
+            }
+        } else {
+        // ---- demand below the stock: sale = d_j, successor inventory y - d_j > 0 ----
+            // All index arithmetic is 32-bit (plan_cash checks nI*nW < 2^31): the successor's flat index
+            // is clamp(rowoff + iw + shift, rowoff, rowoff + nW-1), one add-max and one min per level.
+#pragma unroll 2
+            for (int j = 0; j < jy; j++) {
+                const double2 pp = PP[j];
+                int il = ix + ai - (a.d0 + j);                    // successor inventory index
+                il = min(il, M.nI - 1);
+                il = max(il, 0);
+                const int rowoff = il * M.nW;
+                const int kk0 = rowoff + PRi[j] - CI;             // + iw[r] = unclamped flat index
+                const int khi = rowoff + nW1;
                 double m = 0.0;
-                if (!SURVIVAL) m = pp.x * inc;
+                if (!SURVIVAL) m = pp.x * (PRd[j] - Cd);          // p_j * c(s,a,d_j)
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    if (!SURVIVAL) acc[r] += m;
-                    acc[r] += pp.y * vn[r];
+                    const int k = min(max(kk0 + iw[r], rowoff), khi);  // clamp to [cash_min, cash_max]
+                    double vn = __ldg(a.Vn + (unsigned)k);
+                    if (SURVIVAL && k - rowoff < -M.kmin) vn = 0.0;  // successor cash < 0: RiskRecursion.java:87-95
+                    if (!SURVIVAL) acc[r] += m;                    // CashRecursion.java:117
+                    acc[r] += pp.y * vn;                           // CashRecursion.java:120
+                }
+            }
+            // ---- stock-out: sale = y for every remaining demand, successor inventory 0 ----
+            if (jy < a.D) {
+                const int PYi = a.price * yv;
+                const int il = min(max(M.i_zero, 0), M.nI - 1);
+                const int rowoff = il * M.nW;
+                const int kk0 = rowoff + PYi - CI;
+                const int khi = rowoff + nW1;
+                const double inc = (double)PYi - Cd;
+                double vn[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int k = min(max(kk0 + iw[r], rowoff), khi);
+                    vn[r] = __ldg(a.Vn + (unsigned)k);
+                    if (SURVIVAL && k - rowoff < -M.kmin) vn[r] = 0.0;
+                }
+#pragma unroll 2
+                for (int j = jy; j < a.D; j++) {
+                    const double2 pp = PP[j];
+                    double m = 0.0;
+                    if (!SURVIVAL) m = pp.x * inc;
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        if (!SURVIVAL) acc[r] += m;
+                        acc[r] += pp.y * vn[r];
+                    }
                 }
             }
         }
@@ -191,7 +212,7 @@ inline void plan_cash(CashPlan& P, const sdpb_model& m, const DevModel& d, const
         !cash_is_small_int(m.inv_min) || m.inv_min < 0) { P.why_not = "non-integer parameters"; return; }
     P.K = (int)m.fixed_cost;
     bool any = false;
-    for (int t = 0; t + 1 < m.T; t++) {  // the last period runs on the generic kernel
+    for (int t = 0; t < m.T; t++) {
         const double price = m.price_t ? m.price_t[t] : m.price;
         const double v = m.vari_cost_t ? m.vari_cost_t[t] : m.vari_cost;
         const double ovh = m.overhead_t ? m.overhead_t[t] : m.overhead;
@@ -218,7 +239,7 @@ inline void plan_cash(CashPlan& P, const sdpb_model& m, const DevModel& d, const
 inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& dm, int t, int D, int pmf_off,
                        const double* Vn, double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream,
                        double* fp64_ops, double evals) {
-    if (!P.available || t >= m.T || !P.period[t - 1].ok) return SDPB_ERR_STATE;
+    if (!P.available || !P.period[t - 1].ok) return SDPB_ERR_STATE;
     if (hi <= lo) return SDPB_OK;
     const CashPeriod& cp = P.period[t - 1];
     CashArgs a;
@@ -229,11 +250,20 @@ inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& d
     const dim3 grid((unsigned)(ix1 - a.ix0 + 1), (unsigned)((dm.nW + kCashTile - 1) / kCashTile));
     const size_t smem = (size_t)D * 28 + 16;
     const bool surv = m.recursion == SDPB_REC_SURVIVAL;
-    if (surv) bi_cash_int<true, false><<<grid, kCashThreads, smem, stream>>>(dm, a);
-    else if (dm.is_min) bi_cash_int<false, true><<<grid, kCashThreads, smem, stream>>>(dm, a);
-    else bi_cash_int<false, false><<<grid, kCashThreads, smem, stream>>>(dm, a);
+    if (t == m.T) {
+        if (surv) bi_cash_int<true, false, true><<<grid, kCashThreads, smem, stream>>>(dm, a);
+        else if (dm.is_min) bi_cash_int<false, true, true><<<grid, kCashThreads, smem, stream>>>(dm, a);
+        else bi_cash_int<false, false, true><<<grid, kCashThreads, smem, stream>>>(dm, a);
+    } else {
+        if (surv) bi_cash_int<true, false, false><<<grid, kCashThreads, smem, stream>>>(dm, a);
+        else if (dm.is_min) bi_cash_int<false, true, false><<<grid, kCashThreads, smem, stream>>>(dm, a);
+        else bi_cash_int<false, false, false><<<grid, kCashThreads, smem, stream>>>(dm, a);
+    }
     if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
-    if (fp64_ops) *fp64_ops += evals * (surv ? 2.0 : 3.0 + 2.0 / kCashR);
+    if (fp64_ops) {
+        if (t == m.T) *fp64_ops += evals * (surv ? 2.0 + 3.0 / kCashR : 1.0 + 4.0 / kCashR);
+        else *fp64_ops += evals * (surv ? 2.0 : 3.0 + 2.0 / kCashR);
+    }
     return SDPB_OK;
 }
 

@@ -26,6 +26,7 @@ namespace sdpb {
 
 // A decoded state plus everything that is constant over its (a, d) loop.
 struct StateCtx {
+    int t;
     int ix, iq1, iq2, iw;
     double x, q1, w;  // w: cash (R for the XR kind)
     int nA;           // |A(s)|
@@ -43,6 +44,7 @@ struct ActionCtx {
     double initCash;  // w, or R - v*x for XR
     double deposite;  // CASH_DEPOSIT / XR
     double before_minus_interest;  // CASH_OVERDRAFT: cashBalanceBefore - interest
+    double fixedCost, variableCost;  // kinds whose balance depends on the demand keep them separate
     long long pipe;   // successor's pipeline-slot offset
 };
 
@@ -53,6 +55,7 @@ template <int KIND>
 __device__ __forceinline__ StateCtx decode_state(const DevModel& M, int t, long long idx, bool dedup = false) {
     StateCtx S;
     long long r = idx;
+    S.t = t;
     S.iw = 0; S.iq1 = 0; S.iq2 = 0;
     if (KIND != SDPB_COST_BACKORDER) { S.iw = (int)(r % M.nW); r /= M.nW; }
     if (M.lead >= 2) { S.iq2 = (int)(r % M.nQ); r /= M.nQ; }
@@ -101,6 +104,7 @@ __device__ __forceinline__ ActionCtx prep_action(const DevModel& M, const StateC
     if (M.lead == 1) A.pipe = (long long)i * M.nW;
     if (M.lead == 2) A.pipe = ((long long)S.iq2 * M.nQ + i) * M.nW;
     A.fv = 0.0; A.deposite = 0.0; A.before_minus_interest = 0.0; A.initCash = S.w;
+    A.fixedCost = 0.0; A.variableCost = 0.0;
     if (KIND == SDPB_COST_BACKORDER) {
         // CLSPTesting.java:96-106 / Leadtime.java:71-81 / CLSPforDraw.java:156-170
         const double fixedCost = S.gy ? 0.0 : (A.a > 0.0 ? M.K : 0.0);
@@ -125,6 +129,10 @@ __device__ __forceinline__ ActionCtx prep_action(const DevModel& M, const StateC
         fixedCost = A.a > 0.0 ? M.K : 0.0;
         variableCost = S.v * A.a;
     }
+    A.fixedCost = fixedCost;
+    A.variableCost = variableCost;
+    if (KIND == SDPB_COST_CASH_OD_LIMIT || KIND == SDPB_COST_CASH_OD_TESTING || KIND == SDPB_COST_CASH_LOAN)
+        return A;  // their balances depend on the demand: nothing more to hoist
     if (KIND == SDPB_COST_CASH_OVERDRAFT) {
         // CashOverdraft.java:85-95
         const double before = ((A.initCash - fixedCost) - variableCost) - S.ovh;
@@ -144,17 +152,47 @@ __device__ __forceinline__ ActionCtx prep_action(const DevModel& M, const StateC
     return A;
 }
 
-// Immediate value c(s,a,d).
+// Immediate value c(s,a,d).  `after` receives the end-of-period cash balance for the one kind whose
+// transition uses it directly instead of w + c (CashOverdraftTesting.java:103-111).
 template <int KIND>
 __device__ __forceinline__ double immediate(const DevModel& M, const StateCtx& S, const ActionCtx& A,
-                                            double d) {
+                                            double d, double& after) {
     const double lvl = A.stock - d;
+    after = 0.0;
     if (KIND == SDPB_COST_BACKORDER) {
         const double hold = M.h * fmax(lvl, 0.0);
         const double pen = M.pen * fmax(-lvl, 0.0);
         return (A.fv + hold) + pen;
     }
     const double revenue = S.price * fmin(A.stock, d);
+    if (KIND == SDPB_COST_CASH_OD_LIMIT) {
+        // CashOverdraftLimit.java:70-86
+        const double hold = M.h * fmax(lvl, 0.0);
+        const double before = (((S.w - A.fixedCost) - A.variableCost) - hold) - S.ovh;
+        const double interest = M.r2 * fmax(-before, 0.0);
+        const double deposite = M.dr * fmax(before, 0.0);
+        const double bal = ((before - interest) + deposite) + revenue;
+        double inc = bal - S.w;
+        inc += S.last ? M.salvage * fmax(lvl, 0.0) : 0.0;
+        return inc;
+    }
+    if (KIND == SDPB_COST_CASH_OD_TESTING) {
+        // CashOverdraftTesting.java:85-99 (and :103-111 for the balance the transition keeps)
+        const double hold = M.h * fmax(lvl, 0.0);
+        const double before = (((S.w + revenue) - A.fixedCost) - A.variableCost) - hold;
+        const double interest = M.r2 * fmax(-before, 0.0);
+        after = before - interest;
+        return after - S.w;
+    }
+    if (KIND == SDPB_COST_CASH_LOAN) {
+        // TestPaper.java:82-93
+        const double hold = S.last ? 0.0 : M.h * fmax(lvl, 0.0);
+        const double deposites = M.dr * fmax(S.w - A.variableCost, 0.0);
+        const double loanPayed = M.r2 * fmax(A.variableCost - S.w, 0.0);
+        double inc = (((revenue - A.variableCost) - hold) + deposites) - loanPayed;
+        inc += S.last ? M.salvage * fmax(lvl, 0.0) : 0.0;
+        return inc;
+    }
     double inc;
     if (KIND == SDPB_COST_CASH_OVERDRAFT) {
         const double after = A.before_minus_interest + revenue;  // CashOverdraft.java:99
@@ -175,7 +213,7 @@ __device__ __forceinline__ double immediate(const DevModel& M, const StateCtx& S
 // Successor f(s,a,d) as a flattened grid index; `bankrupt` = successor cash < 0 (survival only).
 template <int KIND>
 __device__ __forceinline__ long long successor(const DevModel& M, const StateCtx& S, const ActionCtx& A,
-                                               int di, double c, bool& bankrupt) {
+                                               int di, double c, double after, bool& bankrupt) {
     int il = A.iy - di;
     if (S.lost) il = max(il, M.i_zero);
     il = min(il, M.nI - 1);  // upper clamp first, then lower (CLSPTesting.java:91-92)
@@ -183,12 +221,19 @@ __device__ __forceinline__ long long successor(const DevModel& M, const StateCtx
     bankrupt = false;
     if (KIND == SDPB_COST_BACKORDER) return il * S.strideX + A.pipe;
     // CashConstraint.java:123-133 / CashConstraintXR.java:95-110
-    double nw = A.initCash + c;
+    double nw = (KIND == SDPB_COST_CASH_OD_TESTING) ? after : A.initCash + c;
     nw = nw > M.cash_max ? M.cash_max : nw;
     nw = nw < M.cash_min ? M.cash_min : nw;
-    const long long kk = jround(nw * M.q_mul);
-    // Java long division; q_idiv == 1 (round(w*1)/1) is the common case and needs no divide
-    long long k = (M.quantiser == SDPB_Q_DIV || M.q_idiv == 1) ? kk : kk / M.q_idiv;
+    long long kk, k;
+    if (M.quantiser == SDPB_Q_TRUNC) {
+        // TestPaper.java:107-109: round from period q_from_period on, then (int) truncation
+        if (M.q_from_period > 0 && S.t >= M.q_from_period) nw = (double)jround(nw * M.q_mul) / M.q_div;
+        kk = k = (long long)nw;
+    } else {
+        kk = jround(nw * M.q_mul);
+        // Java long division; q_idiv == 1 (round(w*1)/1) is the common case and needs no divide
+        k = (M.quantiser == SDPB_Q_DIV || M.q_idiv == 1) ? kk : kk / M.q_idiv;
+    }
     bankrupt = k < 0;  // quantised cash < 0 (q_div > 0)
     if (KIND == SDPB_COST_CASH_XR) {
         const double nwq = (M.quantiser == SDPB_Q_DIV) ? (double)kk / M.q_div : (double)k;
@@ -224,7 +269,8 @@ bi_generic(const __grid_constant__ DevModel M, const int t, const int D, const i
         const ActionCtx A = prep_action<KIND>(M, S, i);
         double acc = 0.0;
         for (int j = 0; j < D; j++) {
-            const double c = immediate<KIND>(M, S, A, __ldg(pd + j));
+            double after;
+            const double c = immediate<KIND>(M, S, A, __ldg(pd + j), after);
             if (!SURVIVAL) acc += __ldg(pp + j) * c;                  // Recursion.java:139
             if (S.last) {
                 if (SURVIVAL) {                                       // RiskRecursion.java:80-84
@@ -233,7 +279,7 @@ bi_generic(const __grid_constant__ DevModel M, const int t, const int D, const i
                 }
             } else {
                 bool bankrupt;
-                const long long ni = successor<KIND>(M, S, A, __ldg(pdi + j), c, bankrupt);
+                const long long ni = successor<KIND>(M, S, A, __ldg(pdi + j), c, after, bankrupt);
                 double vn = __ldg(Vn + ni);
                 if (SURVIVAL && bankrupt) vn = 0.0;                   // RiskRecursion.java:87-95
                 acc += __ldg(pg + j) * vn;                            // Recursion.java:142
@@ -399,9 +445,10 @@ reach_forward(const __grid_constant__ DevModel M, const int t, const int D, cons
     for (int i = 0; i < S.nA; i++) {
         const ActionCtx A = prep_action<KIND>(M, S, i);
         for (int j = 0; j < D; j++) {
-            const double c = immediate<KIND>(M, S, A, __ldg(pd + j));
+            double after;
+            const double c = immediate<KIND>(M, S, A, __ldg(pd + j), after);
             bool bankrupt;
-            const long long ni = successor<KIND>(M, S, A, __ldg(pdi + j), c, bankrupt);
+            const long long ni = successor<KIND>(M, S, A, __ldg(pdi + j), c, after, bankrupt);
             // getSurvProb never recurses into a bankrupt successor (RiskRecursion.java:89-94)
             if (!(SURVIVAL && bankrupt)) mask_n[ni] = 1;
         }
@@ -419,10 +466,11 @@ __global__ void eval_triples(const __grid_constant__ DevModel M, const int t, co
     if (i >= n) return;
     const StateCtx S = decode_state<KIND>(M, t, sidx[i]);
     const ActionCtx A = prep_action<KIND>(M, S, aidx[i]);
-    const double c = immediate<KIND>(M, S, A, dem[i]);
+    double after;
+    const double c = immediate<KIND>(M, S, A, dem[i], after);
     bool bankrupt;
     c_out[i] = c;
-    next_out[i] = successor<KIND>(M, S, A, demi[i], c, bankrupt);
+    next_out[i] = successor<KIND>(M, S, A, demi[i], c, after, bankrupt);
     na_out[i] = S.nA;
 }
 

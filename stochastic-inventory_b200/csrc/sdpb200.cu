@@ -60,6 +60,7 @@ struct sdpb_handle {
     std::vector<int*> dQ;     // [T] each Spad int32 action indices (-1 = none)
     std::vector<unsigned char*> dMask;  // [T] reachability, one byte per state
     std::vector<char> solved;
+    mutable std::vector<double> evals_cache;
     std::vector<void*> dev_allocs;
     bool reached = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -122,6 +123,7 @@ double cash_of_k(const sdpb_handle* h, long long k) {
     return m.quantiser == SDPB_Q_DIV ? (double)k / m.q_div : (double)k;
 }
 double quantise(const sdpb_model& m, double w) {
+    if (m.quantiser == SDPB_Q_TRUNC) return (double)(int)w;  // grid bounds: truncation only
     long long kk = h_jround(w * m.q_mul);
     if (m.quantiser == SDPB_Q_DIV) return (double)kk / m.q_div;
     return (double)(kk / (long long)m.q_div);
@@ -187,7 +189,17 @@ inline double q_of_index(const sdpb_handle* h, long long idx, int qi) {
 }
 
 // |A_t(s)| summed over the shard, times D_t (host arithmetic; mirrors decode_state()).
+double count_evals_period_uncached(const sdpb_handle* h, int t);
+
+// The shard never changes, so the (host-side) count is computed once per period.
 double count_evals_period(const sdpb_handle* h, int t) {
+    if (h->evals_cache.size() != (size_t)h->m.T) h->evals_cache.assign(h->m.T, -1.0);
+    double& c = h->evals_cache[t - 1];
+    if (c < 0) c = count_evals_period_uncached(h, t);
+    return c;
+}
+
+double count_evals_period_uncached(const sdpb_handle* h, int t) {
     const sdpb_model& m = h->m;
     const DevModel& d = h->dm;
     const double D = h->pmf_len[t - 1];
@@ -254,6 +266,16 @@ int dispatch_generic_d(sdpb_handle* h, int t, const double* Vn, double* Vt, int*
         if (mn) launch_generic<SDPB_COST_CASH_XR, false, true, 1, false>(h, t, Vn, Vt, Qt, lo, hi);
         else launch_generic<SDPB_COST_CASH_XR, false, false, 1, false>(h, t, Vn, Vt, Qt, lo, hi);
         break;
+#define SDPB_PLAIN_KIND(K)                                                                    \
+    case K:                                                                                   \
+        if (DEDUP) { h->err = "no lead time to fold"; return SDPB_ERR_ARG; }                  \
+        if (mn) launch_generic<K, false, true, 1, false>(h, t, Vn, Vt, Qt, lo, hi);           \
+        else launch_generic<K, false, false, 1, false>(h, t, Vn, Vt, Qt, lo, hi);             \
+        break;
+    SDPB_PLAIN_KIND(SDPB_COST_CASH_OD_LIMIT)
+    SDPB_PLAIN_KIND(SDPB_COST_CASH_OD_TESTING)
+    SDPB_PLAIN_KIND(SDPB_COST_CASH_LOAN)
+#undef SDPB_PLAIN_KIND
     default:
         h->err = "bad cost_kind";
         return SDPB_ERR_ARG;
@@ -350,6 +372,17 @@ double count_evals_virtual(const sdpb_handle* h, int t) {
     return per_w * (double)(h->vS / d.nW) * D;
 }
 
+// policy table as order quantities (doubles), converted on the device so the host copy is one memcpy
+__global__ void policy_to_double(const int* __restrict__ q, double* __restrict__ out, long long n, double step,
+                                 int xr, double inv_min, long long stride_x) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int qi = q[i];
+    double v = 0.0;  // bestOrderQty stays 0 when nothing beat the initial value
+    if (qi >= 0) v = xr ? (inv_min + (double)(i / stride_x) * step) + (double)qi * step : (double)qi * step;
+    out[i] = v;
+}
+
 __global__ void gather_vq(const long long* __restrict__ idx, int n, const double* __restrict__ V,
                           const int* __restrict__ Q, double* __restrict__ v, int* __restrict__ q) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -437,7 +470,9 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         return fail_create(nullptr, SDPB_ERR_ARG, "sdpb_options.struct_size does not match this library");
     if (m->T < 1 || !m->pmf_len || !m->pmf_d || !m->pmf_p)
         return fail_create(nullptr, SDPB_ERR_ARG, "T < 1 or null pmf");
-    if (m->cost_kind < 0 || m->cost_kind > SDPB_COST_CASH_XR) return fail_create(nullptr, SDPB_ERR_ARG, "bad cost_kind");
+    if (m->cost_kind < 0 || m->cost_kind > SDPB_COST_CASH_LOAN) return fail_create(nullptr, SDPB_ERR_ARG, "bad cost_kind");
+    if (m->cost_kind >= SDPB_COST_CASH_OD_LIMIT && m->lead_time != 0)
+        return fail_create(nullptr, SDPB_ERR_ARG, "this cost kind has no lead-time variant in the reference");
     if (m->lead_time < 0 || m->lead_time > 2) return fail_create(nullptr, SDPB_ERR_ARG, "lead_time must be 0, 1 or 2");
     if (m->cost_kind == SDPB_COST_CASH_XR && m->lead_time != 0)
         return fail_create(nullptr, SDPB_ERR_ARG, "XR kind has no lead time");
@@ -517,7 +552,7 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
             return fail_create(h, SDPB_ERR_ARG, "bad cash axis (q_mul, q_div > 0; cash_max >= cash_min)");
         if (m->quantiser == SDPB_Q_LONGDIV && (!is_int(m->q_div) || m->q_div < 1))
             return fail_create(h, SDPB_ERR_ARG, "SDPB_Q_LONGDIV needs an integer q_div >= 1");
-        if (m->quantiser != SDPB_Q_DIV && m->quantiser != SDPB_Q_LONGDIV)
+        if (m->quantiser != SDPB_Q_DIV && m->quantiser != SDPB_Q_LONGDIV && m->quantiser != SDPB_Q_TRUNC)
             return fail_create(h, SDPB_ERR_ARG, "bad quantiser");
         long long kmin, kmax;
         if (m->cost_kind == SDPB_COST_CASH_XR) {
@@ -552,6 +587,8 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     d.interest_free = m->interest_free;
     d.r2_limit_term = m->r2 * (m->od_limit - m->interest_free);
     d.reserve2 = m->reserve2;
+    d.dr = m->deposit_rate;
+    d.q_from_period = m->q_from_period;
     long long S = d.nI;
     for (int l = 0; l < m->lead_time; l++) S *= d.nQ;
     S *= d.nW;
@@ -748,9 +785,11 @@ int sdpb_value(sdpb_handle* h, int period, const double* states, int n, double* 
     long long* dIdx = nullptr;
     double* dv = nullptr;
     int* dq = nullptr;
-    CU(cudaMalloc(&dIdx, n * sizeof(long long)));
-    CU(cudaMalloc(&dv, n * sizeof(double)));
-    CU(cudaMalloc(&dq, n * sizeof(int)));
+    // scratch from the stream-ordered pool: plain cudaMalloc/cudaFree synchronise the device and cost
+    // tens of milliseconds next to large pooled tables
+    CU(cudaMallocAsync((void**)&dIdx, n * sizeof(long long), h->stream));
+    CU(cudaMallocAsync((void**)&dv, n * sizeof(double), h->stream));
+    CU(cudaMallocAsync((void**)&dq, n * sizeof(int), h->stream));
     std::vector<double> hv(n);
     std::vector<int> hq(n);
     cudaError_t e = cudaMemcpyAsync(dIdx, idx.data(), n * sizeof(long long), cudaMemcpyHostToDevice, h->stream);
@@ -760,8 +799,8 @@ int sdpb_value(sdpb_handle* h, int period, const double* states, int n, double* 
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(hv.data(), dv, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(hq.data(), dq, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaFreeAsync(dIdx, h->stream); cudaFreeAsync(dv, h->stream); cudaFreeAsync(dq, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(dIdx); cudaFree(dv); cudaFree(dq);
     if (e != cudaSuccess) { h->err = std::string("sdpb_value: ") + cudaGetErrorString(e); return SDPB_ERR_CUDA; }
     for (int i = 0; i < n; i++) {
         if (v) v[i] = hv[i];
@@ -775,12 +814,19 @@ int sdpb_period_tables(sdpb_handle* h, int period, double* V, double* Q) {
     if (period < 1 || period > h->m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
     if (!h->solved[period - 1]) { h->err = "period not solved"; return SDPB_ERR_STATE; }
     CU(cudaSetDevice(h->device));
-    CU(cudaStreamSynchronize(h->stream));
-    if (V) CU(cudaMemcpy(V, h->dV[period - 1], (size_t)h->S * sizeof(double), cudaMemcpyDeviceToHost));
+    if (V) CU(cudaMemcpyAsync(V, h->dV[period - 1], (size_t)h->S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (!Q) CU(cudaStreamSynchronize(h->stream));
     if (Q) {
-        std::vector<int> hq((size_t)h->S);
-        CU(cudaMemcpy(hq.data(), h->dQ[period - 1], (size_t)h->S * sizeof(int), cudaMemcpyDeviceToHost));
-        for (long long i = 0; i < h->S; i++) Q[i] = q_of_index(h, i, hq[i]);
+        double* dq = nullptr;
+        CU(cudaMallocAsync((void**)&dq, (size_t)h->S * sizeof(double), h->stream));
+        policy_to_double<<<(unsigned)((h->S + 255) / 256), 256, 0, h->stream>>>(
+            h->dQ[period - 1], dq, h->S, h->m.step, h->m.cost_kind == SDPB_COST_CASH_XR, h->m.inv_min,
+            (long long)h->dm.nW);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(Q, dq, (size_t)h->S * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        cudaFreeAsync(dq, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { h->err = std::string("sdpb_period_tables: ") + cudaGetErrorString(e); return SDPB_ERR_CUDA; }
     }
     return SDPB_OK;
 }
@@ -830,6 +876,9 @@ int sdpb_reach(sdpb_handle* h, const double* init_states, int n) {
             else launch_reach<SDPB_COST_CASH_OVERDRAFT, false>(h, t);
             break;
         case SDPB_COST_CASH_XR: launch_reach<SDPB_COST_CASH_XR, false>(h, t); break;
+        case SDPB_COST_CASH_OD_LIMIT: launch_reach<SDPB_COST_CASH_OD_LIMIT, false>(h, t); break;
+        case SDPB_COST_CASH_OD_TESTING: launch_reach<SDPB_COST_CASH_OD_TESTING, false>(h, t); break;
+        case SDPB_COST_CASH_LOAN: launch_reach<SDPB_COST_CASH_LOAN, false>(h, t); break;
         }
         CU(cudaGetLastError());
     }
@@ -888,7 +937,7 @@ int sdpb_eval_triples(sdpb_handle* h, int period, const double* states, const in
     int *dA = nullptr, *dDi = nullptr, *dNa = nullptr;
     double *dD = nullptr, *dC = nullptr;
     cudaError_t e = cudaSuccess;
-    auto al = [&](void** p, size_t b) { if (e == cudaSuccess) e = cudaMalloc(p, b); };
+    auto al = [&](void** p, size_t b) { if (e == cudaSuccess) e = cudaMallocAsync(p, b, h->stream); };
     al((void**)&dS, n * 8); al((void**)&dN, n * 8); al((void**)&dA, n * 4); al((void**)&dDi, n * 4);
     al((void**)&dNa, n * 4); al((void**)&dD, n * 8); al((void**)&dC, n * 8);
     auto cp = [&](void* d, const void* s, size_t b, cudaMemcpyKind k) { if (e == cudaSuccess) e = cudaMemcpyAsync(d, s, b, k, h->stream); };
@@ -903,14 +952,18 @@ int sdpb_eval_triples(sdpb_handle* h, int period, const double* states, const in
         case SDPB_COST_CASH_DEPOSIT: eval_triples<SDPB_COST_CASH_DEPOSIT><<<blocks, 128, 0, h->stream>>>(h->dm, period, n, dS, dA, dD, dDi, dC, dN, dNa); break;
         case SDPB_COST_CASH_OVERDRAFT: eval_triples<SDPB_COST_CASH_OVERDRAFT><<<blocks, 128, 0, h->stream>>>(h->dm, period, n, dS, dA, dD, dDi, dC, dN, dNa); break;
         case SDPB_COST_CASH_XR: eval_triples<SDPB_COST_CASH_XR><<<blocks, 128, 0, h->stream>>>(h->dm, period, n, dS, dA, dD, dDi, dC, dN, dNa); break;
+        case SDPB_COST_CASH_OD_LIMIT: eval_triples<SDPB_COST_CASH_OD_LIMIT><<<blocks, 128, 0, h->stream>>>(h->dm, period, n, dS, dA, dD, dDi, dC, dN, dNa); break;
+        case SDPB_COST_CASH_OD_TESTING: eval_triples<SDPB_COST_CASH_OD_TESTING><<<blocks, 128, 0, h->stream>>>(h->dm, period, n, dS, dA, dD, dDi, dC, dN, dNa); break;
+        case SDPB_COST_CASH_LOAN: eval_triples<SDPB_COST_CASH_LOAN><<<blocks, 128, 0, h->stream>>>(h->dm, period, n, dS, dA, dD, dDi, dC, dN, dNa); break;
         }
         e = cudaGetLastError();
     }
     cp(hc.data(), dC, n * 8, cudaMemcpyDeviceToHost);
     cp(hnext.data(), dN, n * 8, cudaMemcpyDeviceToHost);
     cp(hna.data(), dNa, n * 4, cudaMemcpyDeviceToHost);
+    for (void* p : {(void*)dS, (void*)dN, (void*)dA, (void*)dDi, (void*)dNa, (void*)dD, (void*)dC})
+        if (p) cudaFreeAsync(p, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(dS); cudaFree(dN); cudaFree(dA); cudaFree(dDi); cudaFree(dNa); cudaFree(dD); cudaFree(dC);
     if (e != cudaSuccess) { h->err = std::string("sdpb_eval_triples: ") + cudaGetErrorString(e); return SDPB_ERR_CUDA; }
     for (int i = 0; i < n; i++) {
         if (c) c[i] = hc[i];

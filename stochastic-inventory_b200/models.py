@@ -33,6 +33,7 @@ class ModelSpec:
     quantiser: int = A.Q_LONGDIV
     q_mul: float = 1.0
     q_div: float = 1.0
+    q_from_period: int = 0
     fixed_cost: float = 0.0
     vari_cost: float = 0.0
     hold_cost: float = 0.0
@@ -71,7 +72,7 @@ class ModelSpec:
         m = A.SdpbModel()
         m.struct_size = C.sizeof(A.SdpbModel)
         for f in ("cost_kind", "recursion", "direction", "lead_time", "flags", "max_order_idx", "gamma",
-                  "inv_min", "inv_max", "step", "cash_min", "cash_max", "quantiser", "q_mul", "q_div",
+                  "inv_min", "inv_max", "step", "cash_min", "cash_max", "quantiser", "q_from_period", "q_mul", "q_div",
                   "fixed_cost", "vari_cost", "hold_cost", "penalty_cost", "price", "salvage",
                   "deposit_rate", "overhead_rate", "overhead", "r0", "r2", "r3", "od_limit",
                   "interest_free", "reserve2"):
@@ -226,3 +227,52 @@ def cash_xr_model(pmf, price=4.0, vari_cost=2.0, fixed_cost=0.0, hold_cost=0.0, 
                      fixed_cost=fixed_cost, vari_cost=vari_cost, hold_cost=hold_cost, price=price,
                      salvage=salvage, deposit_rate=deposit_rate, overhead_rate=overhead_rate,
                      overhead=overhead, name=name)
+
+
+def cash_overdraft_limit_model(pmf, price=10.0, vari_cost=1.0, fixed_cost=0.0, hold_cost=0.0, salvage=0.0,
+                               overhead_t=None, interest_rate=0.1, deposit_rate=0.0, max_order=100, inv_min=0.0,
+                               inv_max=100.0, cash_min=-200.0, cash_max=800.0, quantiser=A.Q_LONGDIV, q_mul=10.0,
+                               q_div=10.0, gamma=1.0, name="cash_overdraft_limit") -> ModelSpec:
+    """Overdraft with one loan rate and one deposit rate on the balance after ordering, holding and
+    overhead costs.  Lambdas: src/cash/overdraft/CashOverdraftLimit.java:62-99 (the cash-limited action
+    bound computed at :63-64 is overwritten by maxOrderQuantity at :65, so actions are 0..maxQ)."""
+    T = len(pmf)
+    return ModelSpec(cost_kind=A.COST_CASH_OD_LIMIT, pmf=pmf, inv_min=inv_min, inv_max=inv_max,
+                     max_order_idx=int(max_order), direction=A.MAX, flags=A.F_CLAMP_INV | A.F_LOST_SALES,
+                     gamma=gamma, cash_min=cash_min, cash_max=cash_max, quantiser=quantiser, q_mul=q_mul,
+                     q_div=q_div, fixed_cost=fixed_cost, vari_cost=vari_cost, hold_cost=hold_cost, price=price,
+                     salvage=salvage, overhead_t=list(overhead_t) if overhead_t is not None else [0.0] * T,
+                     r2=interest_rate, deposit_rate=deposit_rate, name=name)
+
+
+def cash_overdraft_testing_model(pmf, price=10.0, vari_cost=1.0, fixed_cost=0.0, hold_cost=0.0,
+                                 interest_rate=0.1, min_cash_required=0.0, max_order=50, inv_min=0.0,
+                                 inv_max=100.0, cash_min=-100.0, cash_max=400.0, quantiser=A.Q_DIV, q_mul=10.0,
+                                 q_div=10.0, gamma=1.0, name="cash_overdraft_testing") -> ModelSpec:
+    """Loan interest on the balance after revenue; the transition recomputes the balance itself.
+    Lambdas: src/cash/overdraft/CashOverdraftTesting.java:78-120 (cash-limited actions :78-82,
+    quantiser round(w*10)/10.0 :117)."""
+    T = len(pmf)
+    return ModelSpec(cost_kind=A.COST_CASH_OD_TESTING, pmf=pmf, inv_min=inv_min, inv_max=inv_max,
+                     max_order_idx=int(max_order), direction=A.MAX,
+                     flags=A.F_CLAMP_INV | A.F_LOST_SALES | A.F_CASH_LIMITED_ACTIONS, gamma=gamma,
+                     cash_min=cash_min, cash_max=cash_max, quantiser=quantiser, q_mul=q_mul, q_div=q_div,
+                     fixed_cost=fixed_cost, vari_cost=vari_cost, hold_cost=hold_cost, price=price,
+                     r2=interest_rate, reserve_t=[min_cash_required] * T, reserve2=fixed_cost, name=name)
+
+
+def cash_loan_model(pmf, price=10.0, vari_cost=2.0, hold_cost=1.0, deposit_rate=0.01, loan_rate=0.15, salvage=5.0,
+                    min_cash_required=-100.0, max_order=100, inv_min=0.0, inv_max=300.0, cash_min=-1000.0,
+                    cash_max=1000.0, round_from_period=3, q_mul=0.0001, q_div=0.0001, gamma=1.0,
+                    name="cash_loan") -> ModelSpec:
+    """Deposit interest on max(w - v a, 0), loan interest on max(v a - w, 0), no holding cost in the last
+    period.  Lambdas: src/cash/overdraft/TestPaper.java:75-110; the successor cash is `(int) nextCash`,
+    rounded with Math.round(w*0.0001)/0.0001 first when period > 2 (:107-109)."""
+    T = len(pmf)
+    return ModelSpec(cost_kind=A.COST_CASH_LOAN, pmf=pmf, inv_min=inv_min, inv_max=inv_max,
+                     max_order_idx=int(max_order), direction=A.MAX,
+                     flags=A.F_CLAMP_INV | A.F_LOST_SALES | A.F_CASH_LIMITED_ACTIONS, gamma=gamma,
+                     cash_min=cash_min, cash_max=cash_max, quantiser=A.Q_TRUNC, q_mul=q_mul, q_div=q_div,
+                     q_from_period=round_from_period, vari_cost=vari_cost, hold_cost=hold_cost, price=price,
+                     salvage=salvage, deposit_rate=deposit_rate, r2=loan_rate,
+                     reserve_t=[min_cash_required] * T, name=name)

@@ -256,7 +256,8 @@ class LeadtimeRecursion2(_Engine):
 class CashRecursion(_Engine):
     OptDirection = OptDirection
     state_cls = CashState
-    _kinds = (A.COST_CASH_DEPOSIT, A.COST_CASH_OVERDRAFT)
+    _kinds = (A.COST_CASH_DEPOSIT, A.COST_CASH_OVERDRAFT, A.COST_CASH_OD_LIMIT, A.COST_CASH_OD_TESTING,
+              A.COST_CASH_LOAN)
 
     def getSurvProb(self, state):
         """CashRecursion.java:143-194: needs a descriptor built with recursion=REC_SURVIVAL."""

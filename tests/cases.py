@@ -134,6 +134,30 @@ def case_D_rich():
                                   name="D_rich"), [[0.0, 10.0]]
 
 
+def case_DL_small():
+    # CashOverdraftLimit.java:30-99 scaled down; non-zero holding, deposit and salvage terms
+    return S.cash_overdraft_limit_model(pmf([5, 6, 5]), price=8, vari_cost=2, fixed_cost=3, hold_cost=0.5,
+                                        salvage=1, overhead_t=[6, 4, 5], interest_rate=0.125, deposit_rate=0.0625,
+                                        max_order=9, inv_min=0, inv_max=18, cash_min=-40, cash_max=90,
+                                        name="DL_small"), [[0.0, 5.0]]
+
+
+def case_DT_small():
+    # CashOverdraftTesting.java:30-120 scaled down
+    return S.cash_overdraft_testing_model(pmf([4, 5, 4]), price=7, vari_cost=2, fixed_cost=2, hold_cost=0.5,
+                                          interest_rate=0.2, min_cash_required=-10, max_order=8, inv_min=0,
+                                          inv_max=16, cash_min=-30, cash_max=80, name="DT_small"), [[0.0, 6.0]]
+
+
+def case_TP_small():
+    # TestPaper.java:30-110 scaled down: uniform demand 0..6, rounding switched on from period 3
+    table = S.GetPmf([S.UniformIntDist(0, 6)] * 4, 1, 1).getpmf()
+    return S.cash_loan_model(table, price=10, vari_cost=2, hold_cost=1, deposit_rate=0.01, loan_rate=0.15,
+                             salvage=5, min_cash_required=-20, max_order=10, inv_min=0, inv_max=30,
+                             cash_min=-60, cash_max=120, round_from_period=3, q_mul=0.1, q_div=0.1,
+                             name="TP_small"), [[0.0, 0.0]]
+
+
 def case_E_small():
     # SingleProductLeadtime.java:28-119 scaled down; cash grid 0.5 instead of 0.01 to keep it small
     return S.cash_leadtime_model(pmf([4, 4, 4]), price=5, vari_cost=1, salvage=0.5, od_limit=40, max_order=8,
@@ -157,7 +181,8 @@ def case_XR_small():
 
 ALL = [case_A_small, case_A_max, case_A_gy, case_A_twopoint, case_A_halfstep, case_A_sparse_pmf,
        case_A_degenerate, case_A_one_state, case_B1_ref, case_B1_fixed,
-       case_B2_small, case_C_small, case_C_rich, case_C_int, case_C_int_K, case_D_small, case_D_rich, case_E_small, case_F_small,
+       case_B2_small, case_C_small, case_C_rich, case_C_int, case_C_int_K, case_D_small, case_D_rich, case_DL_small,
+       case_DT_small, case_TP_small, case_E_small, case_F_small,
        case_XR_small]
 
 

@@ -32,6 +32,8 @@ def load():
     lib.oracle_topdown.argtypes = [vp, dp, C.c_int, dp, C.c_int64, dp, dp]
     lib.oracle_topdown.restype = C.c_int64
     lib.oracle_step_states.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int64), C.c_int, dp, dp]
+    lib.oracle_multi_lead.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, dp, ip, ip,
+                                      C.POINTER(C.c_int64)]
     lib.oracle_eval.argtypes = [vp, C.c_int, dp, C.c_double, C.c_double, dp, dp]
     lib.oracle_index.argtypes = [vp, dp]
     lib.oracle_index.restype = C.c_int64
@@ -89,6 +91,16 @@ def step_states(spec, period, Vnext, idx):
     lib.oracle_step_states(C.byref(m), period, vn, idx.ctypes.data_as(C.POINTER(C.c_int64)), len(idx),
                            _dp(v), _dp(q))
     return v, q
+
+
+def multi_lead(T, qbound, vals1, probs1, vals2, probs2, overhead=100.0):
+    """The reference's two-product lead-time model through the oracle's own loop -> (value, Q1, Q2, n_states)."""
+    lib = load()
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (vals1, probs1, vals2, probs2)]
+    v, q1, q2, ns = C.c_double(), C.c_int(), C.c_int(), C.c_int64()
+    lib.oracle_multi_lead(T, qbound, len(vals1), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), overhead,
+                          C.byref(v), C.byref(q1), C.byref(q2), C.byref(ns))
+    return v.value, q1.value, q2.value, ns.value
 
 
 def eval_triple(spec, period, state, action, demand):

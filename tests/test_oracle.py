@@ -208,6 +208,22 @@ def test_oracle_reproduces_golden(name, oracle):
 
 
 # ---- (5) the reference author's own recorded output ----------------------------------------------
+def test_oracle_loop_reproduces_reference_output(oracle):
+    """The SAME solve_state / TopDown code every parity test relies on (oracle/sdp_oracle.cpp), driven
+    with the reference's two-product lead-time lambdas, reproduces the program output recorded in
+    src/cash/overdraft/MultiProductLeadtime.java:34-44 to the last digit:
+        T = 2, demands {20,30,40} x {10,15,20}, p = {.25,.5,.25}:  -17.800000000000008, Q1 = 40, Q2 = 20.
+    (The T = 3 record of the same file, demands {10,30} x {5,15}: -76.56, Q1 = 30, Q2 = 15, also reproduces
+    — 1.7e11 evaluations, 34 CPU-minutes; run it with SDPB_SLOW_TESTS=1.)"""
+    v, q1, q2, ns = oracle.multi_lead(2, 45, [20, 30, 40], [.25, .5, .25], [10, 15, 20], [.25, .5, .25])
+    assert repr(v) == "-17.800000000000008" and (q1, q2) == (40, 20)
+    v, q1, q2, ns = oracle.multi_lead(2, 50, [20, 30, 40], [.25, .5, .25], [10, 15, 20], [.25, .5, .25])
+    assert repr(v) == "-17.800000000000008" and (q1, q2) == (40, 20)
+    if os.environ.get("SDPB_SLOW_TESTS") == "1":
+        v, q1, q2, ns = oracle.multi_lead(3, 50, [10, 30], [.5, .5], [5, 15], [.5, .5])
+        assert repr(v) == "-76.56" and (q1, q2) == (30, 15)
+
+
 def test_reference_known_answer_two_product_T2(oracle):
     """src/cash/overdraft/MultiProductLeadtime.java:34-44 records, for discrete demands
     {20,30,40} x {10,15,20} with probabilities {.25,.5,.25} and T = 2:
