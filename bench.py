@@ -29,7 +29,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-KERNEL_NAMES = {1: "bi_generic", 2: "bi_inv_tiled", 3: "bi_backorder_staged", 4: "bi_cash_int", 5: "bi_inv_tiled2", 6: "bi_lead_slab"}
+KERNEL_NAMES = {1: "bi_generic", 2: "bi_inv_tiled", 3: "bi_backorder_staged", 4: "bi_cash_int", 5: "bi_inv_tiled2", 6: "bi_lead_slab", 7: "bi_lead_col"}
 METRIC = "state-action-demand evaluations/s (fp64), full-horizon SDP solve"
 UNIT = "evals/s"
 
@@ -336,6 +336,13 @@ def run_gpu(args):
         except Exception:
             pass
         achieved = fp_total / (ms * 1e-3) / 1e12 / world  # per GPU
+        traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
+        try:
+            if args.workload == "c5" and args.states_per_gpu == 10_000_000 and kernel_used == 5:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_tiled2.json")))
+                traffic = [v["dram_bytes_per_launch"] for k, v in tj.items() if not k.startswith("_")][0]
+        except Exception:
+            traffic = None
         hbm_bytes = 24.0 * spec.n_states() * spec.T * args.steps  # 8 B read + 16 B written per state-period
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -353,7 +360,9 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peaks["nofma_tops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["nofma_tops"] if peaks["nofma_tops"] else None, "traffic": None,
+                "frac": achieved / peaks["nofma_tops"] if peaks["nofma_tops"] else None, "traffic": traffic,
+                "traffic_note": "ncu dram read+write bytes of one non-last-period launch at S=1e7 "
+                                "(profiles/r01_traffic_tiled2.json); algorithmic bytes per launch = 20 B/state = 2.0e8",
                 "what": "non-fused fp64 instructions (DADD/DMUL; Java parity forbids DFMA) the kernel executes "
                         "per GPU per second vs the same mix measured live by sdpb_microbench on this GPU; "
                         "MEASURED_PEAKS.json has no fp64 figure",

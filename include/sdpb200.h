@@ -174,7 +174,9 @@ typedef enum sdpb_kernel_choice {
     SDPB_KERNEL_STAGED = 3,   /* warp-per-state staged kernel for backorder lead-time models (as a request:
                                  skip the slab kernel) */
     SDPB_KERNEL_CASH_INT = 4, /* reported only: integer-exact cash kernel (last period: generic) */
-    SDPB_KERNEL_LEAD_SLAB = 6,/* reported only: shared-memory slab kernel for backorder lead-time models */
+    SDPB_KERNEL_LEAD_SLAB = 6,/* shared-memory slab kernel for backorder lead-time models (as a request: skip
+                                 the column kernel) */
+    SDPB_KERNEL_LEAD_COL = 7, /* reported only: thread-per-successor-column kernel for lead-time models */
     SDPB_KERNEL_TILED2 = 5    /* 2-D register-tile variant of the tiled kernel: chosen automatically for
                                  large grids; as a request it forces the variant wherever it applies */
 } sdpb_kernel_choice;

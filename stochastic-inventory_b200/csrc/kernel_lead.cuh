@@ -18,6 +18,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "dev_model.cuh"
 #include "kernel_tiled.cuh"  // lds_double2
 
@@ -37,6 +39,17 @@ struct LeadArgs {
     int A, Apad, di_max, NR;  // actions, padded row length, max demand index, slab rows
     int nthreads;
 };
+
+__device__ __forceinline__ long long lds_s64(unsigned shared_addr) {
+    long long v;
+    asm volatile("ld.shared.s64 %0, [%1];" : "=l"(v) : "r"(shared_addr));
+    return v;
+}
+
+// one fp64 value at base + byte offset, through the read-only path
+__device__ __forceinline__ double ldg_at(const char* base, long long byte_off) {
+    return __ldg(reinterpret_cast<const double*>(base + byte_off));
+}
 
 __device__ __forceinline__ double lds_double(unsigned shared_addr) {
     double v;
@@ -265,6 +278,236 @@ inline int launch_lead(const LeadPlan& P, const DevModel& dm, int t, int D, int 
         else    { if (last) SDPB_LEAD_LAUNCH(false, true, 1) else SDPB_LEAD_LAUNCH(false, false, 1) }
     }
 #undef SDPB_LEAD_LAUNCH
+    if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+    return SDPB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bi_lead_col — one thread per successor COLUMN.  For a fixed inventory level x and a fixed column
+// c = (preQ2, a) the values G(y, c), y = x + preQ1, form a 1-D sliding problem along preQ1 with the
+// column's own value vector V_{t+1}[., c]: the row slot k needs at demand j+1 is the row slot k-1
+// needed at demand j.  So a thread walks the whole preQ1 axis in chunks of YT = 8 levels, keeps the 8
+// level costs and 8 successor values in registers (rotation unrolled x8), and per demand point loads
+// ONE new value of its column straight from global memory (lanes = consecutive columns: coalesced;
+// every row is re-read D/8 times by the same thread, so L1 serves it) and one level cost from shared
+// memory (CTA-uniform: a broadcast).  fp64 per evaluation: (1 + 8 + 8 + 16) / 8 = 4.125; no slab
+// staging, no per-tile set-up.  A CTA is NQB whole preQ2 values x all actions (505 of 512 threads
+// busy for C4), so the argopt over a stays inside the CTA: after each chunk the 8 x NQB states are
+// reduced through shared memory with the lexicographic (value, action) rule.
+constexpr int kColYT = 8;
+
+struct ColArgs {
+    int t, D, pmf_off;
+    const double* Vn;
+    double* Vt;
+    int* Qt;
+    long long lo, hi;
+    long long row0;           // first inventory row of the range (real grid)
+    int A, NQB, nq2_groups;   // actions; preQ2 values per CTA; CTAs along preQ2
+    int LT, n_ltiles;         // levels (preQ1 values) per CTA (multiple of 8), CTAs along the level axis
+    int di_max, NRW;          // window rows = LT + span
+    int nthreads;
+};
+
+template <bool IS_MIN, bool LAST, bool DEDUP>
+__global__ void __launch_bounds__(512)
+bi_lead_col(const __grid_constant__ DevModel M, const __grid_constant__ ColArgs a) {
+    constexpr int YT = kColYT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = a.D, A = a.A;
+    // layout: [ red 2 x YT*nthreads doubles (double-buffered) ][ Lw NRW doubles ][ RO NRW int64 row offsets ][ PP D double2 ]
+    double* red_base = reinterpret_cast<double*>(smem_raw);
+    double* Lw = red_base + (size_t)2 * YT * a.nthreads;
+    long long* RO = reinterpret_cast<long long*>(Lw + a.NRW);
+    double2* PP = reinterpret_cast<double2*>(smem_raw + ((((size_t)2 * YT * a.nthreads + 2 * (size_t)a.NRW) * 8 + 15) & ~(size_t)15));
+
+    long long b = blockIdx.x;
+    const int q2g = (int)(b % a.nq2_groups); b /= a.nq2_groups;
+    const int lt = (int)(b % a.n_ltiles); b /= a.n_ltiles;
+    const long long ix = DEDUP ? 0 : a.row0 + b;
+    const int l_begin = lt * a.LT;
+    const int n_levels = DEDUP ? (M.nI + M.nQ - 1) : M.nQ;
+    const int l_end = min(l_begin + a.LT, n_levels);
+    const long long y_tile0 = ix + l_begin;  // level index of the tile's first level
+
+    const int tid = threadIdx.x;
+    const int qq = tid / A, ai = tid - qq * A;
+    const int q2 = q2g * a.NQB + qq;
+    const bool worker = qq < a.NQB && (M.lead != 2 || q2 < M.nQ);
+    const bool lost = (M.flags & SDPB_F_LOST_SALES) != 0;
+    const long long strideX = (M.lead == 2) ? (long long)M.nQ * M.nQ : (long long)M.nQ;
+
+    for (int j = tid; j < D; j += a.nthreads) PP[j] = make_double2(M.pmf_p[a.pmf_off + j], M.pmf_pg[a.pmf_off + j]);
+    // window index wi <-> unclamped level index il = y_tile0 - di_max + wi
+    for (int wi = tid; wi < a.NRW; wi += a.nthreads) {
+        const long long il = y_tile0 - a.di_max + wi;
+        const double lvl = M.inv_min + (double)il * M.step;
+        Lw[wi] = M.h * fmax(lvl, 0.0) + M.pen * fmax(-lvl, 0.0);
+        long long is = il;
+        if (lost) is = is > M.i_zero ? is : M.i_zero;
+        is = is < M.nI - 1 ? is : M.nI - 1;  // upper clamp first; also the memory-safety clip
+        is = is > 0 ? is : 0;
+        RO[wi] = is * strideX * (long long)sizeof(double);  // byte offset of the successor's row
+    }
+    __syncthreads();
+
+    const double av = (double)ai * M.step;
+    const double fv = (av > 0.0 ? M.K : 0.0) + M.v_t[a.t - 1] * av;  // Leadtime.java:73-74,79
+    const char* __restrict__ col = reinterpret_cast<const char*>(
+        a.Vn + ((M.lead == 2) ? (long long)min(q2, M.nQ - 1) * M.nQ + ai : (long long)ai));
+    const unsigned lw_s = (unsigned)__cvta_generic_to_shared(Lw);
+    const unsigned ro_s = (unsigned)__cvta_generic_to_shared(RO);
+    const unsigned pp_s = (unsigned)__cvta_generic_to_shared(PP);
+    const int warp = tid >> 5, lane = tid & 31, nwarps = a.nthreads >> 5;
+
+    int parity = 0;
+    for (int l0 = l_begin; l0 < l_end; l0 += YT, parity ^= 1) {
+        // Q-values of this chunk go to buffer `parity`; the other buffer may still be read by slower
+        // warps finishing the previous chunk's argopt, so one barrier per chunk is enough.
+        double* red_v = red_base + (size_t)parity * YT * a.nthreads;
+        double acc[YT], cst[YT], Vw[YT];
+#pragma unroll
+        for (int k = 0; k < YT; k++) acc[k] = 0.0;
+        if (worker) {
+            // level slot k at demand j needs window row  wi = (l0 - l_begin) + k + (D-1-j)
+            int wi0 = (l0 - l_begin) + (D - 1);
+#pragma unroll
+            for (int k = 0; k < YT; k++) {
+                const int wi = min(wi0 + k, a.NRW - 1);
+                cst[k] = fv + lds_double(lw_s + (unsigned)wi * 8u);
+                Vw[k] = LAST ? 0.0 : ldg_at(col, lds_s64(ro_s + (unsigned)wi * 8u));
+            }
+            // two-deep software pipeline on the global loads: `pre` is the value entering at step j+1
+            double pre = 0.0;
+            if (!LAST) pre = ldg_at(col, lds_s64(ro_s + (unsigned)max(wi0 - 1, 0) * 8u));
+#define SDPB_COL_STEP(JJ)                                                                             \
+            {                                                                                             \
+                const double2 pp = lds_double2(pp_s + (unsigned)j * 16u);                                 \
+                const double vnew = pre;                                                                  \
+                if (!LAST) pre = ldg_at(col, lds_s64(ro_s + (unsigned)max(wi0 - 2, 0) * 8u));             \
+                const double lnew = lds_double(lw_s + (unsigned)max(wi0 - 1, 0) * 8u);                    \
+                _Pragma("unroll") for (int k = 0; k < YT; k++) {                                          \
+                    const int ph = (k - (JJ)) & 7;                                                        \
+                    acc[k] += pp.x * cst[ph];                      /* LeadtimeRecursion.java:59 */       \
+                    if (!LAST) acc[k] += pp.y * Vw[ph];            /* LeadtimeRecursion.java:62 */       \
+                }                                                                                         \
+                const int pn = (7 - (JJ)) & 7;                                                            \
+                cst[pn] = fv + lnew;                                                                      \
+                Vw[pn] = vnew;                                                                            \
+                wi0 -= 1;                                                                                 \
+                j += 1;                                                                                   \
+            }
+            int j = 0;
+            for (; j + 8 <= D;) {
+                SDPB_COL_STEP(0) SDPB_COL_STEP(1) SDPB_COL_STEP(2) SDPB_COL_STEP(3)
+                SDPB_COL_STEP(4) SDPB_COL_STEP(5) SDPB_COL_STEP(6) SDPB_COL_STEP(7)
+            }
+            if (j < D) SDPB_COL_STEP(0)
+            if (j < D) SDPB_COL_STEP(1)
+            if (j < D) SDPB_COL_STEP(2)
+            if (j < D) SDPB_COL_STEP(3)
+            if (j < D) SDPB_COL_STEP(4)
+            if (j < D) SDPB_COL_STEP(5)
+            if (j < D) SDPB_COL_STEP(6)
+#undef SDPB_COL_STEP
+        }
+        // ---- argopt over the actions of each of the YT x NQB states of this chunk ----
+#pragma unroll
+        for (int k = 0; k < YT; k++) red_v[(size_t)k * a.nthreads + tid] = acc[k];
+        __syncthreads();
+        for (int s = warp; s < YT * a.NQB; s += nwarps) {
+            const int k = s / a.NQB, sq = s - k * a.NQB;
+            const double* q = red_v + (size_t)k * a.nthreads + sq * A;
+            double best = IS_MIN ? DBL_MAX : -DBL_MAX;
+            int besti = kNoAction;
+            for (int i = lane; i < A; i += 32) {  // ascending within a lane: first optimum wins
+                const double v = q[i];
+                if (IS_MIN ? (v < best) : (v > best)) { best = v; besti = i; }
+            }
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, sh);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti, sh);
+                if (better<IS_MIN>(ov, oi, best, besti)) { best = ov; besti = oi; }
+            }
+            if (lane == 0) {
+                const int lev = l0 + k;
+                const int sq2 = q2g * a.NQB + sq;
+                if (lev < l_end && (M.lead != 2 || sq2 < M.nQ)) {
+                    long long idx = DEDUP ? (long long)lev : ix * M.nQ + lev;
+                    if (M.lead == 2) idx = idx * M.nQ + sq2;
+                    if (idx >= a.lo && idx < a.hi) {
+                        a.Vt[idx] = best;
+                        a.Qt[idx] = besti == kNoAction ? -1 : besti;
+                    }
+                }
+            }
+        }
+    }
+}
+
+struct ColPlan {
+    bool ok = false;
+    int NQB = 1, nthreads = 0, LT = 0, di_max = 0, span = 0, NRW = 0;
+    size_t smem = 0;
+};
+
+inline ColPlan plan_col(const sdpb_model& m, const DevModel& d, int D, const int* di, bool dedup) {
+    ColPlan P;
+    if (m.cost_kind != SDPB_COST_BACKORDER || m.lead_time < 1) return P;
+    int lo = di[0], hi = di[0];
+    for (int j = 0; j < D; j++) {
+        if (di[j] != di[0] + j) return P;  // the register window needs consecutive demands
+        lo = std::min(lo, di[j]);
+        hi = std::max(hi, di[j]);
+    }
+    const int A = d.max_order_idx + 1;
+    if (A > 512) return P;
+    int max_threads = 512;  // measured best on C4 (512: 238 ms, 128: 244, 224: 270, 320: 317)
+    if (const char* e = std::getenv("SDPB_COL_THREADS")) max_threads = std::max(32, std::min(512, std::atoi(e)));  // tuning knob
+    P.NQB = m.lead_time == 2 ? std::max(1, std::min(max_threads / A, d.nQ)) : 1;
+    P.nthreads = ((P.NQB * A + 31) / 32) * 32;
+    const int n_levels = dedup ? d.nI + d.nQ - 1 : d.nQ;
+    // real grid: one CTA walks the whole preQ1 axis; folded grid: 64 levels per CTA for parallelism
+    P.LT = dedup ? 64 : ((n_levels + kColYT - 1) / kColYT) * kColYT;
+    P.di_max = hi;
+    P.span = hi - lo;
+    P.NRW = P.LT + P.span;
+    P.smem = ((((size_t)2 * kColYT * P.nthreads + 2 * (size_t)P.NRW) * 8 + 15) & ~(size_t)15) + (size_t)D * 16 + 16;
+    P.ok = P.smem <= 100 * 1024;
+    return P;
+}
+
+template <bool DEDUP>
+inline int launch_col(const ColPlan& P, const DevModel& dm, int t, int D, int pmf_off, const double* Vn,
+                      double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream) {
+    if (hi <= lo) return SDPB_OK;
+    ColArgs a;
+    a.t = t; a.D = D; a.pmf_off = pmf_off; a.Vn = Vn; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
+    a.A = dm.max_order_idx + 1; a.NQB = P.NQB; a.LT = P.LT; a.di_max = P.di_max; a.NRW = P.NRW;
+    a.nthreads = P.nthreads;
+    a.nq2_groups = dm.lead == 2 ? (dm.nQ + P.NQB - 1) / P.NQB : 1;
+    const int n_levels = DEDUP ? dm.nI + dm.nQ - 1 : dm.nQ;
+    a.n_ltiles = (n_levels + P.LT - 1) / P.LT;
+    long long rows = 1;
+    a.row0 = 0;
+    if (!DEDUP) {
+        const long long per_x = dm.lead == 2 ? (long long)dm.nQ * dm.nQ : (long long)dm.nQ;
+        a.row0 = lo / per_x;
+        rows = (hi - 1) / per_x - a.row0 + 1;
+    }
+    const long long blocks = rows * a.n_ltiles * a.nq2_groups;
+    const bool last = (t == dm.T), mn = dm.is_min != 0;
+    cudaError_t e = cudaSuccess;
+#define SDPB_COL_LAUNCH(MN, LS)                                                                        \
+    {                                                                                                  \
+        auto k = bi_lead_col<MN, LS, DEDUP>;                                                           \
+        if (P.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem); \
+        if (e == cudaSuccess) k<<<(unsigned)blocks, P.nthreads, P.smem, stream>>>(dm, a);              \
+    }
+    if (mn) { if (last) SDPB_COL_LAUNCH(true, true) else SDPB_COL_LAUNCH(true, false) }
+    else    { if (last) SDPB_COL_LAUNCH(false, true) else SDPB_COL_LAUNCH(false, false) }
+#undef SDPB_COL_LAUNCH
     if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
     return SDPB_OK;
 }

@@ -320,6 +320,14 @@ template <bool DEDUP>
 int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt, long long lo, long long hi) {
     if (h->opt.kernel != SDPB_KERNEL_GENERIC && h->opt.kernel != SDPB_KERNEL_STAGED && h->m.lead_time >= 1 &&
         h->m.cost_kind == SDPB_COST_BACKORDER) {
+        const ColPlan cp = plan_col(h->m, h->dm, h->pmf_len[t - 1], h->pmf_di.data() + h->pmf_off[t - 1], DEDUP);
+        if (cp.ok && h->opt.kernel != SDPB_KERNEL_LEAD_SLAB) {
+            h->stats.kernel_used = SDPB_KERNEL_LEAD_COL;
+            const double ev = (double)(hi - lo) * (h->m.max_order_idx + 1) * h->pmf_len[t - 1];
+            // per 8 evaluations: 1 new cost + 8 (p*c) + 8 adds (+ 8 (p*gamma*V) + 8 adds)
+            h->stats.fp64_ops += ev * (t == h->m.T ? 17.0 / 8.0 : 33.0 / 8.0);
+            return launch_col<DEDUP>(cp, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi, h->stream);
+        }
         const LeadPlan lp = plan_lead(h->m, h->dm, h->pmf_len[t - 1], h->pmf_di.data() + h->pmf_off[t - 1]);
         if (lp.ok) {
             h->stats.kernel_used = SDPB_KERNEL_LEAD_SLAB;
