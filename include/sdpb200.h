@@ -173,7 +173,9 @@ typedef enum sdpb_kernel_choice {
                                  for backorder lead-time models); error if the model has none */
     SDPB_KERNEL_STAGED = 3,   /* warp-per-state staged kernel for backorder lead-time models (as a request:
                                  skip the slab kernel) */
-    SDPB_KERNEL_CASH_INT = 4, /* reported only: integer-exact cash kernel (last period: generic) */
+    SDPB_KERNEL_CASH_INT = 4, /* integer-exact cash kernel (as a request: skip the diagonal-window variant) */
+    SDPB_KERNEL_CASH_DIAG = 8,/* reported only: integer-exact cash kernel with a register window along the
+                                 (1, -price) diagonal; the last period runs on SDPB_KERNEL_CASH_INT */
     SDPB_KERNEL_LEAD_SLAB = 6,/* shared-memory slab kernel for backorder lead-time models (as a request: skip
                                  the column kernel) */
     SDPB_KERNEL_LEAD_COL = 7, /* reported only: thread-per-successor-column kernel for lead-time models */

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "dev_model.cuh"
+#include "kernel_lead.cuh"  // lds_double, lds_double2
 
 namespace sdpb {
 
@@ -264,6 +265,191 @@ inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& d
         if (t == m.T) *fp64_ops += evals * (surv ? 2.0 + 3.0 / kCashR : 1.0 + 4.0 / kCashR);
         else *fp64_ops += evals * (surv ? 2.0 : 3.0 + 2.0 / kCashR);
     }
+    return SDPB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bi_cash_diag — the same integer-exact model with a register window along the (1, -price) diagonal.
+//
+// For a fixed action a and demand d_j < y = x + a the successor is
+//     ( level l = y - d_j ,  cash w + price*d_j - C_a )  =  ( l ,  [w + price*x] + price*a - C_a - price*l ),
+// which depends on the state only through phi = w + price*x.  States (x+k, w - price*k) share phi, so
+// slot k at demand j+1 needs exactly the value slot k-1 needed at demand j (the cash and inventory
+// clamps are functions of the unclamped successor and therefore shared too), and once d_j >= y every
+// slot's successor is the same stock-out entry (0, phi + price*a - C_a).  A thread owns YT = 8 such
+// diagonal states for ALL actions (no cross-thread argopt at all); per demand point it gathers ONE new
+// value (instead of 8), forms p_j*c once for all slots still in stock, and spends (add, mul, add) per
+// evaluation: 3 + 2/8 fp64 instructions and 1/8 gather per evaluation (bi_cash_int: 3.5 and 1).
+// Lanes hold consecutive cash levels, so every gather is a coalesced row segment.
+// Demand steps split into: all slots in stock (fast path, rotation unrolled x8) / mixed (per-slot
+// select, at most ~16 steps) / all slots stocked out (no window, no loads).
+constexpr int kDiagYT = 8;
+constexpr int kDiagThreads = 128;
+
+template <bool SURVIVAL, bool IS_MIN>
+__global__ void __launch_bounds__(kDiagThreads)
+bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs a) {
+    constexpr int YT = kDiagYT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* PP = reinterpret_cast<double2*>(smem_raw);                    // (p, p*gamma)
+    double* PRd = reinterpret_cast<double*>(smem_raw + (size_t)a.D * 16);  // price * d_j
+    for (int j = threadIdx.x; j < a.D; j += kDiagThreads) {
+        PP[j] = make_double2(M.pmf_p[a.pmf_off + j], M.pmf_pg[a.pmf_off + j]);
+        PRd[j] = (double)(a.price * (a.d0 + j));
+    }
+    __syncthreads();
+    const unsigned pp_s = (unsigned)__cvta_generic_to_shared(PP);
+    const unsigned pr_s = (unsigned)__cvta_generic_to_shared(PRd);
+
+    const int D = a.D, price = a.price, nW1 = M.nW - 1;
+    const int ix0 = a.ix0 + blockIdx.y * YT;                                  // inventory index of slot 0
+    const int iw0 = blockIdx.x * kDiagThreads + threadIdx.x;                  // cash index of slot 0
+    const double v_d = M.v_t[a.t - 1];
+    const double res = M.reserve_t[a.t - 1];
+
+    int nA[YT], arg[YT];
+    double best[YT];
+    int nAmax = 0;
+#pragma unroll
+    for (int k = 0; k < YT; k++) {
+        const int iw = iw0 - price * k, ix = ix0 + k;
+        const long long idx = (long long)ix * M.nW + iw;
+        const bool valid = iw >= 0 && iw < M.nW && ix < M.nI && idx >= a.lo && idx < a.hi;
+        int n = M.max_order_idx + 1;
+        if (M.flags & SDPB_F_CASH_LIMITED_ACTIONS) {  // CashConstraint.java:96-99
+            const double w = (double)(M.kmin + iw);
+            const double bound = fmax(0.0, ((w - res) - M.reserve2) / v_d);
+            n = (int)fmin((double)M.max_order_idx, bound) + 1;
+        }
+        nA[k] = valid ? n : 0;
+        nAmax = max(nAmax, nA[k]);
+        best[k] = IS_MIN ? DBL_MAX : -DBL_MAX;
+        arg[k] = kNoAction;
+    }
+    if (nAmax == 0) return;
+
+    const int xv0 = a.inv_min_i + ix0;  // inventory VALUE of slot 0
+    const int row_tail = min(max(M.i_zero, 0), M.nI - 1) * M.nW;
+
+    for (int ai = 0; ai < nAmax; ai++) {
+        const int CI = (ai > 0 ? a.K : 0) + a.v * ai + a.ovh;  // K 1[a>0] + v a + overhead
+        const double Cd = (double)CI;
+        const int base = iw0 + price * (ix0 + ai) - CI;        // successor cash index = base - price*il
+        const int L0 = ix0 + ai - a.d0;                        // slot k, demand j: level index L0 + k - j
+        const int jy0 = min(max(xv0 + ai - a.d0, 0), D);       // slot 0 is in stock for j < jy0
+        const int jy7 = min(max(xv0 + (YT - 1) + ai - a.d0, 0), D);
+        double acc[YT], Vw[YT];
+#pragma unroll
+        for (int k = 0; k < YT; k++) acc[k] = 0.0;
+
+        // gather V_{t+1} at level index il (needed only for levels > 0, i.e. il > i_zero)
+        auto gather = [&](int il) -> double {
+            if (il <= M.i_zero) return 0.0;
+            const int row = max(min(il, M.nI - 1), 0) * M.nW;  // upper clamp first, as in the reference
+            const int kc = min(max(base - price * il, 0), nW1);
+            double vn = __ldg(a.Vn + (unsigned)(row + kc));
+            if (SURVIVAL && M.kmin + kc < 0) vn = 0.0;  // RiskRecursion.java:87-95
+            return vn;
+        };
+#pragma unroll
+        for (int k = 0; k < YT; k++) Vw[k] = gather(L0 + k);
+        double pre = gather(L0 - 1);  // enters slot 0 at demand 1
+
+        int j = 0;
+        // ---- all 8 slots in stock: shared p*c, one new gather per demand point ----
+#define SDPB_DIAG_FAST(JJ)                                                                       \
+        {                                                                                            \
+            const double2 pp = lds_double2(pp_s + (unsigned)j * 16u);                                \
+            const double vnew = pre;                                                                 \
+            pre = gather(L0 - (j + 2));                                                              \
+            double m = 0.0;                                                                          \
+            if (!SURVIVAL) m = pp.x * (lds_double(pr_s + (unsigned)j * 8u) - Cd);  /* p_j * c */    \
+            _Pragma("unroll") for (int k = 0; k < YT; k++) {                                         \
+                if (!SURVIVAL) acc[k] += m;                        /* CashRecursion.java:117 */     \
+                acc[k] += pp.y * Vw[(k - (JJ)) & 7];               /* CashRecursion.java:120 */     \
+            }                                                                                        \
+            Vw[(7 - (JJ)) & 7] = vnew;                                                               \
+            j += 1;                                                                                  \
+        }
+        while (j + 8 <= jy0) {
+            SDPB_DIAG_FAST(0) SDPB_DIAG_FAST(1) SDPB_DIAG_FAST(2) SDPB_DIAG_FAST(3)
+            SDPB_DIAG_FAST(4) SDPB_DIAG_FAST(5) SDPB_DIAG_FAST(6) SDPB_DIAG_FAST(7)
+        }
+#undef SDPB_DIAG_FAST
+        // ---- stock-out entry: the same for every slot ----
+        const int kt = min(max(iw0 + price * (xv0 + ai) - CI, 0), nW1);
+        double Vtail = __ldg(a.Vn + (unsigned)(row_tail + kt));
+        if (SURVIVAL && M.kmin + kt < 0) Vtail = 0.0;
+        double inct[YT];  // price*y_k - C_a
+#pragma unroll
+        for (int k = 0; k < YT; k++) inct[k] = (double)(price * (xv0 + k + ai) - CI);
+        // ---- mixed region: some slots in stock, some stocked out ----
+#define SDPB_DIAG_MIXED(JJ)                                                                      \
+        if (j < D) {                                                                                 \
+            const double2 pp = lds_double2(pp_s + (unsigned)j * 16u);                                \
+            const double vnew = pre;                                                                 \
+            pre = gather(L0 - (j + 2));                                                              \
+            const double cin = lds_double(pr_s + (unsigned)j * 8u) - Cd;                             \
+            _Pragma("unroll") for (int k = 0; k < YT; k++) {                                         \
+                const bool in_stock = j < min(max(xv0 + k + ai - a.d0, 0), D);                       \
+                if (!SURVIVAL) acc[k] += pp.x * (in_stock ? cin : inct[k]);                          \
+                acc[k] += pp.y * (in_stock ? Vw[(k - (JJ)) & 7] : Vtail);                            \
+            }                                                                                        \
+            Vw[(7 - (JJ)) & 7] = vnew;                                                               \
+            j += 1;                                                                                  \
+        }
+        while (j < jy7) {
+            SDPB_DIAG_MIXED(0) SDPB_DIAG_MIXED(1) SDPB_DIAG_MIXED(2) SDPB_DIAG_MIXED(3)
+            SDPB_DIAG_MIXED(4) SDPB_DIAG_MIXED(5) SDPB_DIAG_MIXED(6) SDPB_DIAG_MIXED(7)
+        }
+#undef SDPB_DIAG_MIXED
+        // ---- every slot stocked out: no window, no loads ----
+        for (; j < D; j++) {
+            const double2 pp = lds_double2(pp_s + (unsigned)j * 16u);
+            const double pvt = pp.y * Vtail;
+#pragma unroll
+            for (int k = 0; k < YT; k++) {
+                if (!SURVIVAL) acc[k] += pp.x * inct[k];
+                acc[k] += pvt;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < YT; k++) {
+            if (ai < nA[k] && (IS_MIN ? (acc[k] < best[k]) : (acc[k] > best[k]))) { best[k] = acc[k]; arg[k] = ai; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < YT; k++) {
+        if (nA[k] > 0) {
+            const long long idx = (long long)(ix0 + k) * M.nW + (iw0 - price * k);
+            a.Vt[idx] = best[k];
+            a.Qt[idx] = arg[k] == kNoAction ? -1 : arg[k];
+        }
+    }
+}
+
+inline int launch_cash_diag(const CashPlan& P, const sdpb_model& m, const DevModel& dm, int t, int D, int pmf_off,
+                            const double* Vn, double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream,
+                            double* fp64_ops, double evals) {
+    if (!P.available || t >= m.T || !P.period[t - 1].ok) return SDPB_ERR_STATE;
+    if (hi <= lo) return SDPB_OK;
+    const CashPeriod& cp = P.period[t - 1];
+    if (cp.price <= 0 || cp.price * (kDiagYT - 1) > dm.nW) return SDPB_ERR_STATE;  // diagonal must stay on the cash axis
+    CashArgs a;
+    a.t = t; a.D = D; a.pmf_off = pmf_off; a.Vn = Vn; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
+    a.ix0 = (int)(lo / dm.nW);
+    const int ix1 = (int)((hi - 1) / dm.nW);
+    a.price = cp.price; a.v = cp.v; a.K = P.K; a.ovh = cp.ovh; a.d0 = cp.d0; a.inv_min_i = (int)m.inv_min;
+    const int span_w = dm.nW + cp.price * (kDiagYT - 1);  // slot 0's cash index runs past the axis so slot 7 covers it
+    const dim3 grid((unsigned)((span_w + kDiagThreads - 1) / kDiagThreads),
+                    (unsigned)((ix1 - a.ix0 + 1 + kDiagYT - 1) / kDiagYT));
+    const size_t smem = (size_t)D * 24 + 16;
+    const bool surv = m.recursion == SDPB_REC_SURVIVAL;
+    if (surv) bi_cash_diag<true, false><<<grid, kDiagThreads, smem, stream>>>(dm, a);
+    else if (dm.is_min) bi_cash_diag<false, true><<<grid, kDiagThreads, smem, stream>>>(dm, a);
+    else bi_cash_diag<false, false><<<grid, kDiagThreads, smem, stream>>>(dm, a);
+    if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+    if (fp64_ops) *fp64_ops += evals * (surv ? 2.0 : 3.0 + 2.0 / kDiagYT);
     return SDPB_OK;
 }
 

@@ -14,8 +14,8 @@
 #include "dev_model.cuh"
 #include "kernel_generic.cuh"
 #include "kernel_tiled.cuh"
-#include "kernel_cash.cuh"
 #include "kernel_lead.cuh"
+#include "kernel_cash.cuh"
 #include "microbench.cuh"
 
 using namespace sdpb;
@@ -429,9 +429,16 @@ int solve_period(sdpb_handle* h, int t) {
         else if (rc != SDPB_ERR_STATE) { h->err = "tiled kernel launch failed"; return rc; }
     }
     if (rc == SDPB_ERR_STATE && h->opt.kernel != SDPB_KERNEL_GENERIC) {  // integer cash models
-        rc = launch_cash(h->cash, m, h->dm, t, D, h->pmf_off[t - 1], Vn, h->dV[t - 1], h->dQ[t - 1], h->lo, h->hi,
-                         h->stream, &h->stats.fp64_ops, count_evals_period(h, t));
-        if (rc == SDPB_OK) h->stats.kernel_used = SDPB_KERNEL_CASH_INT;
+        rc = SDPB_ERR_STATE;
+        if (h->opt.kernel != SDPB_KERNEL_CASH_INT)  // (as a request: skip the diagonal-window variant)
+            rc = launch_cash_diag(h->cash, m, h->dm, t, D, h->pmf_off[t - 1], Vn, h->dV[t - 1], h->dQ[t - 1], h->lo,
+                                  h->hi, h->stream, &h->stats.fp64_ops, count_evals_period(h, t));
+        if (rc == SDPB_OK) h->stats.kernel_used = SDPB_KERNEL_CASH_DIAG;
+        else if (rc == SDPB_ERR_STATE) {
+            rc = launch_cash(h->cash, m, h->dm, t, D, h->pmf_off[t - 1], Vn, h->dV[t - 1], h->dQ[t - 1], h->lo, h->hi,
+                             h->stream, &h->stats.fp64_ops, count_evals_period(h, t));
+            if (rc == SDPB_OK && h->stats.kernel_used != SDPB_KERNEL_CASH_DIAG) h->stats.kernel_used = SDPB_KERNEL_CASH_INT;
+        }
         else if (rc != SDPB_ERR_STATE) { h->err = "cash kernel launch failed"; return rc; }
     }
     if (rc == SDPB_ERR_STATE)  // no specialised plan for this model / period

@@ -99,10 +99,38 @@ def test_dedup_whole_grid(case, kernel, S, oracle):
     assert st["evals"] == evals and 0 < st["evals_executed"] < evals
 
 
+@pytest.mark.parametrize("case", [cases.case_C_int, cases.case_C_int_K, cases.case_F_small],
+                         ids=lambda f: f.__name__[5:])
+def test_integer_cash_kernels_whole_grid(case, S, oracle):
+    """bi_cash_diag (AUTO) and bi_cash_int (requested) against the oracle."""
+    spec, _ = case()
+    Vo, Qo, _, _ = oracle.dense(spec)
+    for k, used in ((S.KERNEL_AUTO, S.KERNEL_CASH_DIAG), (S.KERNEL_CASH_INT, S.KERNEL_CASH_INT)):
+        s, V, Q = _solve_all(S, spec, kernel=k)
+        assert s.stats()["kernel_used"] == used, spec.name
+        assert np.array_equal(V, Vo) and np.array_equal(Q, Qo), (spec.name, k)
+
+
+def test_cash_diag_wide_cases(S, oracle):
+    """Diagonal-window kernel edges: price larger than the cash tile step, inventory rows not a multiple
+    of 8, short and long demand tables (stock-out region dominant / absent), MIN direction, discounting."""
+    for (price, v, K, means, inv_max, cash_max, max_order, direction, gamma) in [
+            (10, 1, 0, [5, 6, 5], 21, 300, 13, S.MAX, 1.0), (3, 2, 4, [9, 3], 30, 150, 20, S.MAX, 0.9),
+            (25, 3, 0, [2, 2, 2], 9, 400, 6, S.MIN, 1.0), (7, 1, 2, [30, 28], 70, 260, 40, S.MAX, 1.0)]:
+        spec = S.cash_constraint_model(S.poisson_pmf(means, 0.999), price=price, vari_cost=v, fixed_cost=K,
+                                       salvage=0.5, max_order=max_order, inv_min=0, inv_max=inv_max, cash_min=-20,
+                                       cash_max=cash_max, quantiser=S.Q_LONGDIV, q_mul=1.0, q_div=1.0, gamma=gamma,
+                                       direction=direction)
+        Vo, Qo, _, _ = oracle.dense(spec)
+        s, V, Q = _solve_all(S, spec)
+        assert s.stats()["kernel_used"] == S.KERNEL_CASH_DIAG
+        assert np.array_equal(V, Vo) and np.array_equal(Q, Qo), (price, v, K, means)
+
+
 def test_integer_cash_kernel_is_used(S):
     for case in (cases.case_C_int, cases.case_C_int_K, cases.case_F_small):
         spec, _ = case()
-        assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_CASH_INT, spec.name
+        assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_CASH_DIAG, spec.name
     for case in (cases.case_C_small, cases.case_C_rich, cases.case_D_small):
         spec, _ = case()
         assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_GENERIC, spec.name
@@ -328,13 +356,14 @@ def test_config_c2_full(S, oracle):
 def test_config_c3_sampled(S, oracle):
     spec = S.configs.c3(T=3)          # full 501 x 2001 grid, 3 of the 12 periods
     s = S.Solver(spec).solve()
-    assert s.n_states == 1002501 and s.stats()["kernel_used"] == S.KERNEL_CASH_INT
+    assert s.n_states == 1002501 and s.stats()["kernel_used"] == S.KERNEL_CASH_DIAG
     _sample_check(S, oracle, spec, s, n=24)
-    g = S.Solver(spec, kernel=S.KERNEL_GENERIC).solve()
-    for t in (1, 2, 3):
-        Va, Qa = s.period_tables(t)
-        Vg, Qg = g.period_tables(t)
-        assert np.array_equal(Va, Vg) and np.array_equal(Qa, Qg)
+    for k in (S.KERNEL_GENERIC, S.KERNEL_CASH_INT):
+        g = S.Solver(spec, kernel=k).solve()
+        for t in (1, 2, 3):
+            Va, Qa = s.period_tables(t)
+            Vg, Qg = g.period_tables(t)
+            assert np.array_equal(Va, Vg) and np.array_equal(Qa, Qg)
 
 
 def test_config_c4_sampled(S, oracle):
