@@ -261,6 +261,21 @@ int sdpb_opt_table(sdpb_handle* h, double* rows, size_t* nrows);
 
 int sdpb_stats_get(const sdpb_handle* h, sdpb_stats* s);
 
+/* Policy roll-out over caller-supplied demand sample paths — the loop of
+ * Simulation.simulateSDPGivenSamplNum (src/sdp/inventory/Simulation.java:53-74) and
+ * CashSimulation.simulateSDPGivenSamplNum (src/sdp/cash/CashSimulation.java:85-118):
+ *     for each path i:  state = init;  sum = 0
+ *         for t = 1..T:  Q = getAction(state);  d = Math.round(samples[i][t-1])
+ *                        sum += Math.pow(discount, t-1) * immediateValue(state, Q, d)
+ *                        state = stateTransition(state, Q, d)
+ *     values[i] = sum
+ * `samples` is n*T doubles, row-major (what Sampling.generateLHSamples returns; the host keeps drawing
+ * them — the reference draws with Math.random(), so its own numbers are not reproducible).  One thread
+ * per path, same device lambdas as the solve.  `values` receives the n sums; averaging (and adding
+ * iniCash, CashSimulation.java:115) is left to the caller.  Needs a solved, unsharded handle. */
+int sdpb_simulate(sdpb_handle* h, const double* init_state, const double* samples, int n, double discount,
+                  double* values);
+
 /* Evaluate the descriptor's lambdas on the device for `n` (state, action, demand) triples of one
  * period, with the same device code the solve uses: c = immediateValue(s,a,d), next = stateTransition
  * (API-order state of period+1; clipped to the grid when the model does not clamp), n_actions =

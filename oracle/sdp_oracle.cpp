@@ -729,6 +729,31 @@ int oracle_step_states(const sdpb_model* m, int period, const double* Vnext, con
     return 0;
 }
 
+// Policy roll-out (Simulation.java:59-70, CashSimulation.java:100-111) over caller-supplied sample
+// paths, using the dense oracle's policy table Q [T][n_states] (order quantities as doubles).
+int oracle_simulate(const sdpb_model* m, const double* Q, const double* init_state, const double* samples, int n,
+                    double discount, double* values) {
+    Model M = make_model(m);
+    Grid G(M);
+    const int T = m->T;
+    for (int i = 0; i < n; i++) {
+        double sum = 0;
+        St state = G.from_api(1, init_state);
+        for (int t = 0; t < T; t++) {
+            state.t = t + 1;
+            bool off = false;
+            const int64_t idx = G.index(state, &off);
+            double optQ = Q[(size_t)t * G.S + idx];
+            double randomDemand = (double)jround(samples[(size_t)i * T + t]);
+            double thisValue = immediate(M, state, optQ, randomDemand);
+            sum += std::pow(discount, (double)t) * thisValue;
+            state = transition(M, state, optQ, randomDemand);
+        }
+        values[i] = sum;
+    }
+    return 0;
+}
+
 // Single (s, a, d) evaluation for descriptor spot checks: c, and the successor in API order.
 int oracle_eval(const sdpb_model* m, int period, const double* state, double action, double demand,
                 double* c, double* next_state) {

@@ -16,5 +16,6 @@ from .recursion import (CashLeadtimeRecursion, CashLeadtimeState, CashRecursion,
                         CashState, CashStateXR, LeadtimeRecursion, LeadtimeRecursion2, LeadtimeState,
                         OptDirection, Recursion, RiskRecursion, RiskState, State)
 from .solver import Solver
+from .simulation import CashSimulation, Simulation, generate_lh_samples
 from . import configs
 from . import parallel

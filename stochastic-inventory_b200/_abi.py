@@ -80,7 +80,7 @@ EXPORTS = [
     "sdpb_abi_version", "sdpb_sizeof_model", "sdpb_sizeof_options", "sdpb_create", "sdpb_destroy",
     "sdpb_last_error", "sdpb_grid_info", "sdpb_solve", "sdpb_solve_async", "sdpb_solve_period_async", "sdpb_sync",
     "sdpb_value", "sdpb_period_tables", "sdpb_device_tables", "sdpb_state_of_index", "sdpb_reach",
-    "sdpb_opt_table", "sdpb_stats_get", "sdpb_eval_triples", "sdpb_microbench",
+    "sdpb_opt_table", "sdpb_stats_get", "sdpb_eval_triples", "sdpb_microbench", "sdpb_simulate",
 ]
 
 _lib = None
@@ -135,6 +135,7 @@ def load():
     lib.sdpb_stats_get.argtypes = [vp, C.POINTER(SdpbStats)]
     lib.sdpb_eval_triples.argtypes = [vp, C.c_int, _dp, _ip, _dp, C.c_int, _dp, _dp, _ip]
     lib.sdpb_microbench.argtypes = [C.c_int, _dp, _dp, _dp]
+    lib.sdpb_simulate.argtypes = [vp, _dp, _dp, C.c_int, C.c_double, _dp]
     if lib.sdpb_sizeof_model() != C.sizeof(SdpbModel) or lib.sdpb_sizeof_options() != C.sizeof(SdpbOptions):
         raise ImportError("libsdpb200.so struct layout differs from the ctypes binding")
     _lib = lib

@@ -455,6 +455,33 @@ reach_forward(const __grid_constant__ DevModel M, const int t, const int D, cons
     }
 }
 
+// One thread per sample path: roll the solved policy forward (Simulation.java:59-70).
+template <int KIND>
+__global__ void __launch_bounds__(128)
+simulate_paths(const __grid_constant__ DevModel M, const long long init_idx, const double* __restrict__ samples,
+               const int n, const double* __restrict__ disc_pow, const int* const* __restrict__ Qt,
+               double* __restrict__ values, int* __restrict__ off_grid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long idx = init_idx;
+    double sum = 0.0;
+    for (int t = 1; t <= M.T; t++) {
+        const StateCtx S = decode_state<KIND>(M, t, idx);
+        int qi = Qt[t - 1][idx];
+        if (qi < 0) qi = 0;  // bestOrderQty stayed 0
+        const ActionCtx A = prep_action<KIND>(M, S, qi);
+        const double d = (double)jround(samples[(size_t)i * M.T + (t - 1)]);  // Math.round(samples[i][t])
+        const double dq = d / M.step;
+        if (dq != floor(dq)) atomicAdd(off_grid, 1);
+        double after;
+        const double c = immediate<KIND>(M, S, A, d, after);
+        sum += disc_pow[t - 1] * c;
+        bool bankrupt;
+        idx = successor<KIND>(M, S, A, (int)dq, c, after, bankrupt);
+    }
+    values[i] = sum;
+}
+
 // One thread per (state, action, demand) triple: the lambdas alone, for descriptor spot checks.
 template <int KIND>
 __global__ void eval_triples(const __grid_constant__ DevModel M, const int t, const int n,

@@ -988,6 +988,53 @@ int sdpb_eval_triples(sdpb_handle* h, int period, const double* states, const in
     return SDPB_OK;
 }
 
+int sdpb_simulate(sdpb_handle* h, const double* init_state, const double* samples, int n, double discount,
+                  double* values) {
+    if (!h || !init_state || !samples || !values || n < 1) return SDPB_ERR_ARG;
+    if (h->opt.shard_count != 1) { h->err = "sdpb_simulate needs an unsharded handle"; return SDPB_ERR_STATE; }
+    const int T = h->m.T;
+    for (int t = 0; t < T; t++)
+        if (!h->solved[t]) { h->err = "not solved"; return SDPB_ERR_STATE; }
+    const long long init_idx = index_of_state(h, init_state);
+    if (init_idx < 0) { h->err = "initial state is not a grid point"; return SDPB_ERR_UNSOLVED; }
+    CU(cudaSetDevice(h->device));
+    std::vector<double> pw(T);
+    for (int t = 0; t < T; t++) pw[t] = std::pow(discount, (double)t);  // Math.pow(discountFactor, t)
+    std::vector<const int*> qptr(h->dQ.begin(), h->dQ.end());
+    double *dS = nullptr, *dP = nullptr, *dV = nullptr;
+    const int** dQp = nullptr;
+    int* dOff = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto al = [&](void** p, size_t b) { if (e == cudaSuccess) e = cudaMallocAsync(p, b, h->stream); };
+    al((void**)&dS, (size_t)n * T * 8); al((void**)&dP, (size_t)T * 8); al((void**)&dV, (size_t)n * 8);
+    al((void**)&dQp, (size_t)T * sizeof(int*)); al((void**)&dOff, 4);
+    auto cp = [&](void* d, const void* s, size_t b, cudaMemcpyKind k) { if (e == cudaSuccess) e = cudaMemcpyAsync(d, s, b, k, h->stream); };
+    cp(dS, samples, (size_t)n * T * 8, cudaMemcpyHostToDevice);
+    cp(dP, pw.data(), (size_t)T * 8, cudaMemcpyHostToDevice);
+    cp(dQp, qptr.data(), (size_t)T * sizeof(int*), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dOff, 0, 4, h->stream);
+    int off = 0;
+    if (e == cudaSuccess) {
+        const int blocks = (n + 127) / 128;
+#define SDPB_SIM(K) case K: simulate_paths<K><<<blocks, 128, 0, h->stream>>>(h->dm, init_idx, dS, n, dP, dQp, dV, dOff); break;
+        switch (h->m.cost_kind) {
+            SDPB_SIM(SDPB_COST_BACKORDER) SDPB_SIM(SDPB_COST_CASH_DEPOSIT) SDPB_SIM(SDPB_COST_CASH_OVERDRAFT)
+            SDPB_SIM(SDPB_COST_CASH_XR) SDPB_SIM(SDPB_COST_CASH_OD_LIMIT) SDPB_SIM(SDPB_COST_CASH_OD_TESTING)
+            SDPB_SIM(SDPB_COST_CASH_LOAN)
+        }
+#undef SDPB_SIM
+        e = cudaGetLastError();
+    }
+    cp(values, dV, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    cp(&off, dOff, 4, cudaMemcpyDeviceToHost);
+    for (void* p : {(void*)dS, (void*)dP, (void*)dV, (void*)dQp, (void*)dOff})
+        if (p) cudaFreeAsync(p, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { h->err = std::string("sdpb_simulate: ") + cudaGetErrorString(e); return SDPB_ERR_CUDA; }
+    if (off) { h->err = "a rounded sample demand is not a multiple of step"; return SDPB_ERR_OFFGRID; }
+    return SDPB_OK;
+}
+
 int sdpb_microbench(int device, double* nofma_tops, double* fma_tflops, double* lds_gbs) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SDPB_ERR_NO_DEVICE;

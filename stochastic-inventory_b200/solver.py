@@ -112,6 +112,18 @@ class Solver:
         self._check(self.lib.sdpb_opt_table(self.h, rows.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n)))
         return rows
 
+    def simulate(self, init_state, samples, discount: float = 1.0):
+        """Roll the solved policy over demand sample paths [n, T] -> per-path sums (Simulation.java:59-70)."""
+        st = np.ascontiguousarray(init_state, dtype=np.float64)
+        sm = np.ascontiguousarray(samples, dtype=np.float64)
+        if sm.ndim != 2 or sm.shape[1] != self.T:
+            raise ValueError(f"samples must be [n, {self.T}]")
+        vals = np.empty(sm.shape[0])
+        dp = C.POINTER(C.c_double)
+        self._check(self.lib.sdpb_simulate(self.h, st.ctypes.data_as(dp), sm.ctypes.data_as(dp), sm.shape[0],
+                                           float(discount), vals.ctypes.data_as(dp)))
+        return vals
+
     def stats(self):
         s = A.SdpbStats()
         self._check(self.lib.sdpb_stats_get(self.h, C.byref(s)))

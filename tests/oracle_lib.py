@@ -34,6 +34,7 @@ def load():
     lib.oracle_step_states.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int64), C.c_int, dp, dp]
     lib.oracle_multi_lead.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, dp, ip, ip,
                                       C.POINTER(C.c_int64)]
+    lib.oracle_simulate.argtypes = [vp, dp, dp, dp, C.c_int, C.c_double, dp]
     lib.oracle_eval.argtypes = [vp, C.c_int, dp, C.c_double, C.c_double, dp, dp]
     lib.oracle_index.argtypes = [vp, dp]
     lib.oracle_index.restype = C.c_int64
@@ -101,6 +102,17 @@ def multi_lead(T, qbound, vals1, probs1, vals2, probs2, overhead=100.0):
     lib.oracle_multi_lead(T, qbound, len(vals1), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), overhead,
                           C.byref(v), C.byref(q1), C.byref(q2), C.byref(ns))
     return v.value, q1.value, q2.value, ns.value
+
+
+def simulate(spec, Q, init_state, samples, discount=1.0):
+    lib = load()
+    m = spec.to_struct()
+    Q = np.ascontiguousarray(Q, dtype=np.float64)
+    st = np.ascontiguousarray(init_state, dtype=np.float64)
+    sm = np.ascontiguousarray(samples, dtype=np.float64)
+    vals = np.empty(sm.shape[0])
+    lib.oracle_simulate(C.byref(m), _dp(Q), _dp(st), _dp(sm), sm.shape[0], float(discount), _dp(vals))
+    return vals
 
 
 def eval_triple(spec, period, state, action, demand):

@@ -250,6 +250,39 @@ def test_repeated_solves_replay_a_cuda_graph(S, oracle):
         assert v[0] == Vo[0][oracle.index(spec, init[0])]
 
 
+@pytest.mark.parametrize("case", [cases.case_A_small, cases.case_B1_fixed, cases.case_B2_small, cases.case_C_rich,
+                                  cases.case_C_int, cases.case_D_rich, cases.case_E_small, cases.case_XR_small,
+                                  cases.case_DT_small, cases.case_TP_small], ids=lambda f: f.__name__[5:])
+def test_policy_rollout_matches_oracle(case, S, oracle):
+    """sdpb_simulate (Simulation.java:59-70) against the oracle's roll-out of its own policy tables,
+    path by path, on seeded samples that include out-of-support demands and non-integer draws."""
+    spec, init = case()
+    Vo, Qo, _, _ = oracle.dense(spec)
+    rng = np.random.default_rng(5)
+    dmax = max(r[-1, 0] for r in spec.pmf)
+    samples = rng.uniform(-0.4, dmax + 3.0, size=(500, spec.T))
+    gamma = spec.gamma
+    s = S.Solver(spec).solve()
+    got = s.simulate(init[0], samples, gamma)
+    want = oracle.simulate(spec, Qo, init[0], samples, gamma)
+    assert np.array_equal(got, want)
+
+
+def test_reference_style_simulation(S, oracle):
+    """Reads like CLSPTesting.java:125-127: Simulation(distributions, sampleNum, recursion)."""
+    dists = [S.PoissonDist(m) for m in (5, 8, 6)]
+    pmf = S.GetPmf(dists, 0.999, 1).getpmf()
+    spec = S.inventory_model(pmf, 20, 1, 1, 5, max_order=15, inv_min=-30, inv_max=30)
+    recursion = S.Recursion(spec)
+    sim = S.Simulation(dists, 2000, recursion)
+    samples = S.generate_lh_samples(dists, 2000)
+    mean = sim.simulateSDPGivenSamplNum(S.State(1, 0), samples)
+    opt = recursion.getExpectedValue(S.State(1, 0))
+    assert abs(mean - opt) / opt < 0.05          # the reference's eyeball check: simulated ~ optimal
+    Vo, Qo, _, _ = oracle.dense(spec)
+    assert np.array_equal(sim.simulate_paths(S.State(1, 0), samples), oracle.simulate(spec, Qo, [0.0], samples))
+
+
 def test_unsolved_state_raises(S):
     spec, _ = cases.case_A_small()
     s = S.Solver(spec)
