@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define SDPB_ABI_VERSION 1
+#define SDPB_ABI_VERSION 2
 
 typedef enum sdpb_status {
     SDPB_OK = 0,
@@ -86,7 +86,12 @@ typedef enum sdpb_cost_kind {
     SDPB_COST_CASH_OD_TESTING = 5,
     /* deposit interest on max(w - v a, 0), loan interest (r2) on max(v a - w, 0), no holding cost in
      * the last period: src/cash/overdraft/TestPaper.java:82-93 */
-    SDPB_COST_CASH_LOAN = 6
+    SDPB_COST_CASH_LOAN = 6,
+    /* two products sharing one cash account, state (inv1, inv2, cash), action pairs (Q1, Q2) limited
+     * by cash, revenue on what is sold, salvage in the last period:
+     * src/cash/multiItem/MultiItemCash.java:69-117 with src/sdp/cash/multiItem/CashRecursionMulti.java:81-116
+     * (MAX only, an action replaces the incumbent only if better by more than `tie_tolerance`). */
+    SDPB_COST_CASH_TWO_PRODUCT = 7
 } sdpb_cost_kind;
 
 typedef enum sdpb_recursion {
@@ -164,6 +169,14 @@ typedef struct sdpb_model {
                                    (int)min(maxQ, max(0, ((w - reserve_t) - reserve2) / v_t));
                                    overhead then K in CashConstraint.java:98, 0 in cashSurvival.java:105 */
     double reserve2;
+
+    /* second product (SDPB_COST_CASH_TWO_PRODUCT only).  Product 1 uses price / vari_cost / salvage and
+     * pmf_d; both inventories live on the inventory axis; actions are pairs (i, j), 0 <= i, j <=
+     * max_order_idx, scanned i-major (MultiItemCash.java:69-79) and feasible while
+     * v1*i + v2*j < cash + 0.1.  sdpb_value / sdpb_period_tables report the pair as i*(max_order_idx+1)+j. */
+    double price2, vari_cost2, salvage2;
+    const double* pmf_d2;   /* second product's demand of every pmf row (same layout as pmf_d) */
+    double tie_tolerance;   /* 0.1 in CashRecursionMulti.java:108; 0 = plain strict compare */
 } sdpb_model;
 
 typedef enum sdpb_kernel_choice {

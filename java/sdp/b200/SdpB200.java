@@ -37,7 +37,9 @@ public final class SdpB200 {
             JAVA_DOUBLE.withName("overhead"), JAVA_DOUBLE.withName("r0"), JAVA_DOUBLE.withName("r2"),
             JAVA_DOUBLE.withName("r3"), JAVA_DOUBLE.withName("od_limit"), JAVA_DOUBLE.withName("interest_free"),
             ADDRESS.withName("price_t"), ADDRESS.withName("vari_cost_t"), ADDRESS.withName("overhead_t"),
-            ADDRESS.withName("reserve_t"), JAVA_DOUBLE.withName("reserve2"));
+            ADDRESS.withName("reserve_t"), JAVA_DOUBLE.withName("reserve2"),
+            JAVA_DOUBLE.withName("price2"), JAVA_DOUBLE.withName("vari_cost2"), JAVA_DOUBLE.withName("salvage2"),
+            ADDRESS.withName("pmf_d2"), JAVA_DOUBLE.withName("tie_tolerance"));
 
     private static final Linker LINKER = Linker.nativeLinker();
     private static final SymbolLookup LIB =

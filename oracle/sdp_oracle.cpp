@@ -94,7 +94,10 @@ struct Model {
     double tie_tol = 0.0;  // CashRecursionMultiLead.java:82 accepts an action only if it is better by > 0.1
     std::vector<int> off;  // pmf offsets
     int ndemand(int t) const { return m.pmf_len[t - 1]; }
-    double d(int t, int j) const { return m.pmf_d[off[t - 1] + j]; }
+    double d(int t, int j) const { return two() ? (double)j : m.pmf_d[off[t - 1] + j]; }  // two-product: row index
+    double d1(int t, int j) const { return m.pmf_d[off[t - 1] + j]; }
+    double d2(int t, int j) const { return m.pmf_d2[off[t - 1] + j]; }
+    bool two() const { return m.cost_kind == SDPB_COST_CASH_TWO_PRODUCT; }
     double p(int t, int j) const { return m.pmf_p[off[t - 1] + j]; }
     bool cash() const { return m.cost_kind != SDPB_COST_BACKORDER; }
     bool flag(uint32_t f) const { return (m.flags & f) != 0; }
@@ -137,6 +140,7 @@ struct Model {
     int n_cash() const { return cash() ? (int)(k_max() - k_min() + 1) : 1; }
     int64_t n_states() const {
         int64_t n = n_inv();
+        if (two()) n *= n_inv();
         for (int l = 0; l < m.lead_time; l++) n *= n_q();
         return n * n_cash();
     }
@@ -149,6 +153,7 @@ struct Model {
 int n_actions(const Model& M, const St& s) {
     const sdpb_model& m = M.m;
     if (M.multi) return M.multi->Qbound * M.multi->Qbound;  // MultiProductLeadtime.java:150-158
+    if (M.two()) return (m.max_order_idx + 1) * (m.max_order_idx + 1);  // scanned i-major; see action_feasible
     if (m.cost_kind == SDPB_COST_CASH_XR) {
         double v = M.vcost(s.t);
         double maxY = s.w / v < s.x ? s.x : s.w / v;
@@ -162,8 +167,14 @@ int n_actions(const Model& M, const St& s) {
     if (M.flag(SDPB_F_NO_ORDER_LAST) && s.t == m.T) maxQ = 0;
     return (int)maxQ + 1;
 }
+// MultiItemCash.java:72-76: the pair (i, j) is in the action list only if it is affordable
+inline bool action_feasible(const Model& M, const St& s, int i) {
+    if (!M.two()) return true;
+    const int Q = M.m.max_order_idx + 1;
+    return M.m.vari_cost * (i / Q) + M.m.vari_cost2 * (i % Q) < s.w + 0.1;
+}
 inline double action_value(const Model& M, const St& s, int i) {
-    if (M.multi) return (double)i;  // flat index of the pair (i / Qbound, i % Qbound), i-major as in the driver
+    if (M.multi || M.two()) return (double)i;  // flat index of the pair (i / Qbound, i % Qbound), i-major as in the driver
     if (M.m.cost_kind == SDPB_COST_CASH_XR) return s.x + i * M.m.step;
     return i * M.m.step;
 }
@@ -226,6 +237,23 @@ double immediate(const Model& M, const St& s, double action, double demand) {
     if (M.multi) {  // action = flat action index, demand = flat demand index
         const int i = (int)action, j = (int)demand, Q = M.multi->Qbound;
         return multi_immediate(M, s, i / Q, i % Q, M.multi->d1[j], M.multi->d2[j]);
+    }
+    if (M.two()) {
+        // MultiItemCash.java:82-103 (action = flat pair index, demand = pmf row index)
+        const int Q = m.max_order_idx + 1, fi = (int)action, j = (int)demand;
+        double action1 = fi / Q, action2 = fi % Q;
+        double demand1 = (int)M.d1(s.t, j), demand2 = (int)M.d2(s.t, j);
+        double endInventory1 = jmax(0, s.x + action1 - demand1);
+        double endInventory2 = jmax(0, s.x2 + action2 - demand2);
+        double revenue1 = m.price * (s.x + action1 - endInventory1);
+        double revenue2 = m.price2 * (s.x2 + action2 - endInventory2);
+        double revenue = revenue1 + revenue2;
+        double orderingCost1 = m.vari_cost * action1;
+        double orderingCost2 = m.vari_cost2 * action2;
+        double orderingCosts = orderingCost1 + orderingCost2;
+        double salValue = 0;
+        if (s.t == T) salValue = m.salvage * endInventory1 + m.salvage2 * endInventory2;
+        return revenue - orderingCosts + salValue;
     }
     switch (m.cost_kind) {
     case SDPB_COST_BACKORDER: {
@@ -355,6 +383,25 @@ St transition(const Model& M, const St& s, double action, double demand) {
         const int i = (int)action, j = (int)demand, Q = M.multi->Qbound;
         return multi_transition(M, s, i / Q, i % Q, M.multi->d1[j], M.multi->d2[j]);
     }
+    if (M.two()) {
+        // MultiItemCash.java:107-121 (upper clamp on item 1, lower clamp on item 2, as written there)
+        const int Q = m.max_order_idx + 1, fi = (int)action, j = (int)demand;
+        double endInventory1 = s.x + (double)(fi / Q) - (double)(int)M.d1(s.t, j);
+        endInventory1 = jmax(0, endInventory1);
+        double endInventory2 = s.x2 + (double)(fi % Q) - (double)(int)M.d2(s.t, j);
+        endInventory2 = jmax(0, endInventory2);
+        double nextCash = s.w + immediate(M, s, action, demand);
+        nextCash = nextCash > m.cash_max ? m.cash_max : nextCash;
+        nextCash = nextCash < m.cash_min ? m.cash_min : nextCash;
+        endInventory1 = endInventory1 > m.inv_max ? m.inv_max : endInventory1;
+        endInventory2 = endInventory2 < m.inv_min ? m.inv_min : endInventory2;
+        nextCash = (int)nextCash;
+        endInventory1 = (int)endInventory1;
+        endInventory2 = (int)endInventory2;
+        St n2;
+        n2.t = s.t + 1; n2.x = endInventory1; n2.x2 = endInventory2; n2.w = nextCash;
+        return n2;
+    }
     St n;
     n.t = s.t + 1;
     if (m.cost_kind == SDPB_COST_BACKORDER) {
@@ -431,7 +478,10 @@ void solve_state(const Model& M, const St& s, NextValue&& next_value, double* va
     int D = M.ndemand(s.t);
     double val = is_min ? DBL_MAX : -DBL_MAX;
     double bestOrderQty = 0;
+    int nFeasible = 0;
     for (int i = 0; i < nA; i++) {
+        if (!action_feasible(M, s, i)) continue;
+        nFeasible++;
         double orderQty = action_value(M, s, i);
         double thisQValue = 0;
         for (int j = 0; j < D; j++) {
@@ -468,7 +518,7 @@ void solve_state(const Model& M, const St& s, NextValue&& next_value, double* va
             if (thisQValue > val + M.tie_tol) { val = thisQValue; bestOrderQty = orderQty; }
         }
     }
-    if (evals) *evals += (double)nA * D;
+    if (evals) *evals += (double)nFeasible * D;
     *val_out = val;
     *best_out = bestOrderQty;
 }
@@ -521,6 +571,12 @@ struct Grid {
         if (ix < 0) { ix = 0; *off = true; }
         if (ix >= nI) { ix = nI - 1; *off = true; }
         int64_t idx = ix;
+        if (M.two()) {
+            int64_t ix2 = jround((s.x2 - M.m.inv_min) / M.m.step);
+            if (ix2 < 0) { ix2 = 0; *off = true; }
+            if (ix2 >= nI) { ix2 = nI - 1; *off = true; }
+            idx = idx * nI + ix2;
+        }
         if (L >= 1) { int64_t iq = jround(s.q1 / M.m.step); idx = idx * nQ + iq; }
         if (L >= 2) { int64_t iq = jround(s.q2 / M.m.step); idx = idx * nQ + iq; }
         if (M.cash()) {
@@ -536,19 +592,22 @@ struct Grid {
         if (M.cash()) { s.w = M.cash_of_k(kmin + idx % nW); idx /= nW; }
         if (L >= 2) { s.q2 = (double)(idx % nQ) * M.m.step; idx /= nQ; }
         if (L >= 1) { s.q1 = (double)(idx % nQ) * M.m.step; idx /= nQ; }
+        if (M.two()) { s.x2 = M.m.inv_min + (double)(idx % nI) * M.m.step; idx /= nI; }
         s.x = M.m.inv_min + (double)idx * M.m.step;
         return s;
     }
-    int ndim() const { return 1 + (M.cash() ? 1 : 0) + L; }
+    int ndim() const { return 1 + (M.two() ? 1 : 0) + (M.cash() ? 1 : 0) + L; }
     // API order: (inv) | (inv, preQ[, preQ2]) | (inv, cash) | (inv, cash, preQ)
     void to_api(const St& s, double* out) const {
         int k = 0; out[k++] = s.x;
+        if (M.two()) out[k++] = s.x2;
         if (M.cash()) out[k++] = s.w;
         if (L >= 1) out[k++] = s.q1;
         if (L >= 2) out[k++] = s.q2;
     }
     St from_api(int t, const double* in) const {
         St s; s.t = t; int k = 0; s.x = in[k++];
+        if (M.two()) s.x2 = in[k++];
         if (M.cash()) s.w = in[k++];
         if (L >= 1) s.q1 = in[k++];
         if (L >= 2) s.q2 = in[k++];
@@ -558,6 +617,7 @@ struct Grid {
 
 Model make_model(const sdpb_model* m) {
     Model M; M.m = *m;
+    if (m->cost_kind == SDPB_COST_CASH_TWO_PRODUCT) M.tie_tol = m->tie_tolerance;
     M.off.resize(m->T + 1, 0);
     for (int t = 0; t < m->T; t++) M.off[t + 1] = M.off[t] + m->pmf_len[t];
     return M;

@@ -31,6 +31,9 @@ struct DevModel {
     double reserve2;
     double dr;            // depositeRate itself (CashOverdraftLimit.java:79, TestPaper.java:87)
     int q_from_period;    // SDPB_Q_TRUNC: round with (q_mul, q_div) from this period on; 0 = never
+    double price2, v2, salvage2, tie_tol;  // second product / tie tolerance (SDPB_COST_CASH_TWO_PRODUCT)
+    const double* pmf_d2;
+    const int* pmf_di2;
     // per-period parameter tables, always expanded to T entries on the host
     const double* price_t;
     const double* v_t;

@@ -16,6 +16,7 @@
 #include "kernel_tiled.cuh"
 #include "kernel_lead.cuh"
 #include "kernel_cash.cuh"
+#include "kernel_two_product.cuh"
 #include "microbench.cuh"
 
 using namespace sdpb;
@@ -51,6 +52,7 @@ struct sdpb_handle {
     std::vector<int> pmf_len, pmf_off;
     std::vector<double> pmf_d, pmf_p;
     std::vector<int> pmf_di;  // demand values in units of step
+    std::vector<double> pmf_d2;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -116,6 +118,7 @@ int fail_create(sdpb_handle* h, int code, const std::string& msg) {
 }
 
 bool has_cash(const sdpb_model& m) { return m.cost_kind != SDPB_COST_BACKORDER; }
+bool two_product(const sdpb_model& m) { return m.cost_kind == SDPB_COST_CASH_TWO_PRODUCT; }
 
 double cash_of_k(const sdpb_handle* h, long long k) {
     const sdpb_model& m = h->m;
@@ -142,6 +145,11 @@ long long index_of_state(const sdpb_handle* h, const double* st) {
     double fi = (x - m.inv_min) / m.step;
     if (!is_int(fi) || fi < 0 || fi >= d.nI) return -1;
     long long idx = (long long)fi;
+    if (two_product(m)) {
+        double f2 = (st[k++] - m.inv_min) / m.step;
+        if (!is_int(f2) || f2 < 0 || f2 >= d.nI) return -1;
+        idx = idx * d.nI + (long long)f2;
+    }
     long long iw = 0;
     if (has_cash(m)) {
         double w = st[k++];
@@ -167,11 +175,14 @@ void state_of_index(const sdpb_handle* h, long long idx, double* st, double* x_o
     if (has_cash(m)) { w = cash_of_k(h, d.kmin + idx % d.nW); idx /= d.nW; }
     if (m.lead_time >= 2) { q2 = (double)(idx % d.nQ) * m.step; idx /= d.nQ; }
     if (m.lead_time >= 1) { q1 = (double)(idx % d.nQ) * m.step; idx /= d.nQ; }
+    double x2 = 0;
+    if (two_product(m)) { x2 = m.inv_min + (double)(idx % d.nI) * m.step; idx /= d.nI; }
     double x = m.inv_min + (double)idx * m.step;
     if (x_out) *x_out = x;
     if (st) {
         int k = 0;
         st[k++] = x;
+        if (two_product(m)) st[k++] = x2;
         if (has_cash(m)) st[k++] = w;
         if (m.lead_time >= 1) st[k++] = q1;
         if (m.lead_time >= 2) st[k++] = q2;
@@ -180,6 +191,7 @@ void state_of_index(const sdpb_handle* h, long long idx, double* st, double* x_o
 
 inline double q_of_index(const sdpb_handle* h, long long idx, int qi) {
     if (qi < 0) return 0.0;  // bestOrderQty stays 0 when nothing beat the initial value
+    if (two_product(h->m)) return (double)qi;  // pair index Q1*(max_order_idx+1) + Q2
     if (h->m.cost_kind == SDPB_COST_CASH_XR) {
         double x;
         state_of_index(h, idx, nullptr, &x);
@@ -203,6 +215,22 @@ double count_evals_period_uncached(const sdpb_handle* h, int t) {
     const sdpb_model& m = h->m;
     const DevModel& d = h->dm;
     const double D = h->pmf_len[t - 1];
+    if (two_product(m)) {
+        // affordable pairs depend on the cash level only (MultiItemCash.java:73)
+        const double v1 = m.vari_cost_t ? m.vari_cost_t[t - 1] : m.vari_cost;
+        const int Q = m.max_order_idx + 1;
+        double total = 0;
+        for (int iw = 0; iw < d.nW; iw++) {
+            const double w = (double)(d.kmin + iw);
+            long long cnt = 0;
+            for (int i = 0; i < Q; i++)
+                for (int j = 0; j < Q; j++) cnt += (v1 * i + m.vari_cost2 * j < w + 0.1);
+            // states of the shard [lo, hi) whose cash index is iw
+            const long long n_iw = (h->hi - iw + d.nW - 1) / d.nW - (h->lo - iw + d.nW - 1) / d.nW;
+            total += (double)cnt * (double)n_iw;
+        }
+        return total * D;
+    }
     const long long n = h->hi - h->lo;
     const bool limited = (m.flags & SDPB_F_CASH_LIMITED_ACTIONS) || m.cost_kind == SDPB_COST_CASH_XR;
     if ((m.flags & SDPB_F_NO_ORDER_LAST) && t == m.T && m.cost_kind != SDPB_COST_CASH_XR) return (double)n * D;
@@ -266,6 +294,16 @@ int dispatch_generic_d(sdpb_handle* h, int t, const double* Vn, double* Vt, int*
         if (mn) launch_generic<SDPB_COST_CASH_XR, false, true, 1, false>(h, t, Vn, Vt, Qt, lo, hi);
         else launch_generic<SDPB_COST_CASH_XR, false, false, 1, false>(h, t, Vn, Vt, Qt, lo, hi);
         break;
+    case SDPB_COST_CASH_TWO_PRODUCT: {
+        if (DEDUP) { h->err = "no lead time to fold"; return SDPB_ERR_ARG; }
+        const long long nst = hi - lo;
+        if (nst > 0) {
+            const unsigned blocks = (unsigned)((nst + 127) / 128);
+            if (t == h->m.T) bi_two_product<true><<<blocks, 128, 0, h->stream>>>(h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi);
+            else bi_two_product<false><<<blocks, 128, 0, h->stream>>>(h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi);
+        }
+        break;
+    }
 #define SDPB_PLAIN_KIND(K)                                                                    \
     case K:                                                                                   \
         if (DEDUP) { h->err = "no lead time to fold"; return SDPB_ERR_ARG; }                  \
@@ -485,7 +523,10 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         return fail_create(nullptr, SDPB_ERR_ARG, "sdpb_options.struct_size does not match this library");
     if (m->T < 1 || !m->pmf_len || !m->pmf_d || !m->pmf_p)
         return fail_create(nullptr, SDPB_ERR_ARG, "T < 1 or null pmf");
-    if (m->cost_kind < 0 || m->cost_kind > SDPB_COST_CASH_LOAN) return fail_create(nullptr, SDPB_ERR_ARG, "bad cost_kind");
+    if (m->cost_kind < 0 || m->cost_kind > SDPB_COST_CASH_TWO_PRODUCT) return fail_create(nullptr, SDPB_ERR_ARG, "bad cost_kind");
+    if (m->cost_kind == SDPB_COST_CASH_TWO_PRODUCT &&
+        (!m->pmf_d2 || m->quantiser != SDPB_Q_TRUNC || m->recursion != SDPB_REC_EXPECT || m->step != 1.0))
+        return fail_create(nullptr, SDPB_ERR_ARG, "two-product kind needs pmf_d2, the (int) cash quantiser, unit step");
     if (m->cost_kind >= SDPB_COST_CASH_OD_LIMIT && m->lead_time != 0)
         return fail_create(nullptr, SDPB_ERR_ARG, "this cost kind has no lead-time variant in the reference");
     if (m->lead_time < 0 || m->lead_time > 2) return fail_create(nullptr, SDPB_ERR_ARG, "lead_time must be 0, 1 or 2");
@@ -525,10 +566,18 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     h->m.pmf_len = h->pmf_len.data();
     h->m.pmf_d = h->pmf_d.data();
     h->m.pmf_p = h->pmf_p.data();
-    std::vector<double> pg(NP);
-    std::vector<int> pdi(NP);
+    std::vector<double> pg(NP), pd2;
+    std::vector<int> pdi(NP), pdi2;
+    if (m->cost_kind == SDPB_COST_CASH_TWO_PRODUCT) {
+        pd2.assign(m->pmf_d2, m->pmf_d2 + NP);
+        pdi2.resize(NP);
+        for (int j = 0; j < NP; j++) pdi2[j] = (int)pd2[j];  // new Demands((int) d1, (int) d2)
+        h->pmf_d2 = pd2;
+        h->m.pmf_d2 = h->pmf_d2.data();
+    }
     for (int j = 0; j < NP; j++) {
         double f = h->pmf_d[j] / m->step;
+        if (m->cost_kind == SDPB_COST_CASH_TWO_PRODUCT) f = (double)(int)h->pmf_d[j];  // (int) cast in the reference
         if (!is_int(f) || std::fabs(f) > 1e9)
             return fail_create(h, SDPB_ERR_OFFGRID, "a demand value is not a multiple of step");
         pdi[j] = (int)f;
@@ -604,12 +653,15 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     d.reserve2 = m->reserve2;
     d.dr = m->deposit_rate;
     d.q_from_period = m->q_from_period;
+    d.price2 = m->price2; d.v2 = m->vari_cost2; d.salvage2 = m->salvage2; d.tie_tol = m->tie_tolerance;
+    d.pmf_d2 = nullptr; d.pmf_di2 = nullptr;
     long long S = d.nI;
+    if (two_product(*m)) S *= d.nI;
     for (int l = 0; l < m->lead_time; l++) S *= d.nQ;
     S *= d.nW;
     d.S = S;
     h->S = S;
-    h->ndim = 1 + (has_cash(*m) ? 1 : 0) + m->lead_time;
+    h->ndim = 1 + (two_product(*m) ? 1 : 0) + (has_cash(*m) ? 1 : 0) + m->lead_time;
     const long long chunk = (S + h->opt.shard_count - 1) / h->opt.shard_count;
     h->Spad = chunk * h->opt.shard_count;
     h->lo = std::min(S, chunk * h->opt.shard_rank);
@@ -646,6 +698,7 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     d.field = tmp;
     UP(price_t, price_t, dp) UP(v_t, v_t, dp) UP(ovh_t, ovh_t, dp) UP(res_t, reserve_t, dp)
     UP(h->pmf_d, pmf_d, dp) UP(h->pmf_p, pmf_p, dp) UP(pg, pmf_pg, dp) UP(pdi, pmf_di, di)
+    if (two_product(*m)) { UP(pd2, pmf_d2, dp) UP(pdi2, pmf_di2, di) }
 #undef UP
 
     h->dV.assign(T, nullptr);
@@ -863,6 +916,7 @@ int sdpb_state_of_index(const sdpb_handle* h, int64_t idx, double* state) {
 int sdpb_reach(sdpb_handle* h, const double* init_states, int n) {
     if (!h || !init_states || n < 1) return SDPB_ERR_ARG;
     if (h->opt.shard_count != 1) { h->err = "sdpb_reach needs an unsharded handle"; return SDPB_ERR_STATE; }
+    if (two_product(h->m)) { h->err = "sdpb_reach is not implemented for two-product models"; return SDPB_ERR_ARG; }
     CU(cudaSetDevice(h->device));
     const int T = h->m.T;
     for (int t = 0; t < T; t++) {
@@ -936,6 +990,7 @@ int sdpb_eval_triples(sdpb_handle* h, int period, const double* states, const in
                       const double* demand, int n, double* c, double* next_states, int32_t* n_actions) {
     if (!h || !states || !action_idx || !demand || n < 1) return SDPB_ERR_ARG;
     if (period < 1 || period > h->m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
+    if (two_product(h->m)) { h->err = "sdpb_eval_triples is not implemented for two-product models"; return SDPB_ERR_ARG; }
     CU(cudaSetDevice(h->device));
     std::vector<long long> sidx(n), hnext(n);
     std::vector<int> demi(n), hna(n);
@@ -992,6 +1047,7 @@ int sdpb_simulate(sdpb_handle* h, const double* init_state, const double* sample
                   double* values) {
     if (!h || !init_state || !samples || !values || n < 1) return SDPB_ERR_ARG;
     if (h->opt.shard_count != 1) { h->err = "sdpb_simulate needs an unsharded handle"; return SDPB_ERR_STATE; }
+    if (two_product(h->m)) { h->err = "sdpb_simulate is not implemented for two-product models"; return SDPB_ERR_ARG; }
     const int T = h->m.T;
     for (int t = 0; t < T; t++)
         if (!h->solved[t]) { h->err = "not solved"; return SDPB_ERR_STATE; }

@@ -141,3 +141,39 @@ def clsp_inline_pmf(means, truncationQuantile=0.99999, stepSize=1.0):
             row[j, 1] = (d.cdf(row[j, 0] + 0.5 * stepSize) - d.cdf(row[j, 0] - 0.5 * stepSize)) / psum
         rows.append(row)
     return rows
+
+
+class GetPmfMulti:
+    """`new GetPmfMulti(distributions, truncationQuantile, stepSize).getPmf(t)` for two products
+    (src/sdp/cash/multiItem/GetPmfMulti.java:35-175): rows (demand1, demand2, prob), product 1 outermost.
+    Implemented branches: DiscreteDistribution (exact products, :158-171) and PoissonDist (:101-128,
+    normalised by (2q-1)^2 as the reference does)."""
+
+    def __init__(self, distributions, truncationQuantile, stepSize):
+        self.distributionGeneral = distributions  # [2][T]
+        self.truncationQuantile = float(truncationQuantile)
+        self.stepSize = float(stepSize)
+
+    def getPmf(self, t):
+        d1, d2 = self.distributionGeneral[0][t], self.distributionGeneral[1][t]
+        q, step = self.truncationQuantile, self.stepSize
+        rows = []
+        if isinstance(d1, DiscreteDistribution):
+            for i in range(len(d1.values)):
+                for j in range(len(d2.values)):
+                    rows.append((d1.values[i], d2.values[j], d1.probs[i] * d2.probs[j]))
+            return np.array(rows, dtype=float)
+        if isinstance(d1, PoissonDist):
+            lb = [float(int(d.inverseF(1 - q))) for d in (d1, d2)]
+            ub = [float(int(d.inverseF(q))) for d in (d1, d2)]
+            n1, n2 = int((ub[0] - lb[0] + 1) / step), int((ub[1] - lb[1] + 1) / step)
+            psum = (2 * q - 1) * (2 * q - 1)
+            for i in range(n1):
+                for j in range(n2):
+                    a, b = lb[0] + i * step, lb[1] + j * step
+                    rows.append((a, b, d1.prob(int(a)) * d2.prob(int(b)) / psum))
+            return np.array(rows, dtype=float)
+        raise NotImplementedError("GetPmfMulti: only the discrete and Poisson branches are mirrored")
+
+    def tables(self):
+        return [self.getPmf(t) for t in range(len(self.distributionGeneral[0]))]

@@ -53,6 +53,10 @@ class ModelSpec:
     overhead_t: Optional[Sequence[float]] = None
     reserve_t: Optional[Sequence[float]] = None
     reserve2: float = 0.0
+    price2: float = 0.0
+    vari_cost2: float = 0.0
+    salvage2: float = 0.0
+    tie_tolerance: float = 0.0
     name: str = ""
 
     @property
@@ -64,8 +68,12 @@ class ModelSpec:
         return self.cost_kind != A.COST_BACKORDER
 
     @property
+    def two_product(self):
+        return self.cost_kind == A.COST_CASH_TWO_PRODUCT
+
+    @property
     def ndim(self):
-        return 1 + (1 if self.has_cash else 0) + self.lead_time
+        return 1 + (1 if self.two_product else 0) + (1 if self.has_cash else 0) + self.lead_time
 
     def to_struct(self) -> A.SdpbModel:
         """Build the C struct; the arrays it points to are kept alive on the struct object."""
@@ -75,13 +83,17 @@ class ModelSpec:
                   "inv_min", "inv_max", "step", "cash_min", "cash_max", "quantiser", "q_from_period", "q_mul", "q_div",
                   "fixed_cost", "vari_cost", "hold_cost", "penalty_cost", "price", "salvage",
                   "deposit_rate", "overhead_rate", "overhead", "r0", "r2", "r3", "od_limit",
-                  "interest_free", "reserve2"):
+                  "interest_free", "reserve2", "price2", "vari_cost2", "salvage2", "tie_tolerance"):
             setattr(m, f, getattr(self, f))
         m.T = self.T
         lens = np.ascontiguousarray([len(r) for r in self.pmf], dtype=np.int32)
         d = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.float64)[:, 0] for r in self.pmf]))
-        p = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.float64)[:, 1] for r in self.pmf]))
+        p = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.float64)[:, -1] for r in self.pmf]))
         keep = [lens, d, p]
+        if self.two_product:  # rows are (d1, d2, p) as GetPmfMulti.getPmf returns them
+            d2 = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.float64)[:, 1] for r in self.pmf]))
+            keep.append(d2)
+            m.pmf_d2 = d2.ctypes.data_as(C.POINTER(C.c_double))
         m.pmf_len = lens.ctypes.data_as(C.POINTER(C.c_int32))
         m.pmf_d = d.ctypes.data_as(C.POINTER(C.c_double))
         m.pmf_p = p.ctypes.data_as(C.POINTER(C.c_double))
@@ -109,6 +121,8 @@ class ModelSpec:
 
     def n_states(self) -> int:
         n = int(round((self.inv_max - self.inv_min) / self.step)) + 1
+        if self.two_product:
+            n *= n
         n *= (self.max_order_idx + 1) ** self.lead_time
         return n  # cash axis excluded (the library reports the exact figure: sdpb_grid_info)
 
@@ -276,3 +290,17 @@ def cash_loan_model(pmf, price=10.0, vari_cost=2.0, hold_cost=1.0, deposit_rate=
                      q_from_period=round_from_period, vari_cost=vari_cost, hold_cost=hold_cost, price=price,
                      salvage=salvage, deposit_rate=deposit_rate, r2=loan_rate,
                      reserve_t=[min_cash_required] * T, name=name)
+
+
+def two_product_cash_model(pmf, price=(4.0, 50.0), vari_cost=(2.0, 4.0), salvage=(1.0, 1.0), q_bound=100,
+                           inv_max=200.0, cash_min=0.0, cash_max=10000.0, gamma=1.0, tie_tolerance=0.1,
+                           name="two_product_cash") -> ModelSpec:
+    """Two products sharing one cash account.  Lambdas: src/cash/multiItem/MultiItemCash.java:69-121
+    (actions (i, j), 0 <= i, j < Qbound, affordable while v1 i + v2 j < cash + 0.1; `(int) nextCash`).
+    Engine: src/sdp/cash/multiItem/CashRecursionMulti.java:81-116 (MAX, `> val + 0.1`).
+    `pmf`: per period an array [D, 3] of (demand1, demand2, prob) as GetPmfMulti.getPmf returns."""
+    return ModelSpec(cost_kind=A.COST_CASH_TWO_PRODUCT, pmf=pmf, inv_min=0.0, inv_max=inv_max,
+                     max_order_idx=int(q_bound) - 1, direction=A.MAX, flags=A.F_CLAMP_INV | A.F_LOST_SALES,
+                     gamma=gamma, cash_min=cash_min, cash_max=cash_max, quantiser=A.Q_TRUNC, q_mul=1.0, q_div=1.0,
+                     price=price[0], vari_cost=vari_cost[0], salvage=salvage[0], price2=price[1],
+                     vari_cost2=vari_cost[1], salvage2=salvage[1], tie_tolerance=tie_tolerance, name=name)

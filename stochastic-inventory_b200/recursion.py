@@ -285,3 +285,74 @@ class CashRecursionXR(_Engine):
     OptDirection = OptDirection
     state_cls = CashStateXR
     _kinds = (A.COST_CASH_XR,)
+
+
+# ---- two products ---------------------------------------------------------------------------
+class CashStateMulti:
+    """src/sdp/cash/multiItem/CashStateMulti.java:14-45."""
+
+    def __init__(self, period, iniInventory1, iniInventory2, iniCash):
+        self.period = int(period)
+        self.iniInventory1, self.iniInventory2, self.iniCash = float(iniInventory1), float(iniInventory2), float(iniCash)
+
+    def getPeriod(self):
+        return self.period
+
+    def getIniInventory1(self):
+        return self.iniInventory1
+
+    def getIniInventory2(self):
+        return self.iniInventory2
+
+    def getIniCash(self):
+        return self.iniCash
+
+    def _vec(self):
+        return (self.iniInventory1, self.iniInventory2, self.iniCash)
+
+
+class Actions:
+    """src/sdp/cash/multiItem/Actions.java:17-33."""
+
+    def __init__(self, action1, action2):
+        self.firstAction, self.secondAction = int(action1), int(action2)
+
+    def getFirstAction(self):
+        return self.firstAction
+
+    def getSecondAction(self):
+        return self.secondAction
+
+    def __eq__(self, o):
+        return (self.firstAction, self.secondAction) == (o.firstAction, o.secondAction)
+
+    def __repr__(self):
+        return f"Actions({self.firstAction}, {self.secondAction})"
+
+
+class CashRecursionMulti:
+    """new CashRecursionMulti(discountFactor, pmf, buildActionList, f, c, T) ->
+    CashRecursionMulti(spec); src/sdp/cash/multiItem/CashRecursionMulti.java:60-116."""
+
+    def __init__(self, spec: ModelSpec, device: int = -1):
+        if spec.cost_kind != A.COST_CASH_TWO_PRODUCT:
+            raise ValueError("CashRecursionMulti takes a two-product descriptor")
+        self.spec = spec
+        self._solver = Solver(spec, device=device)
+        self._solved = False
+
+    def _value(self, state):
+        if not self._solved:
+            self._solver.solve()
+            self._solved = True
+        v, q = self._solver.value(state.getPeriod(), [state._vec()])
+        n = self.spec.max_order_idx + 1
+        return float(v[0]), Actions(int(q[0]) // n, int(q[0]) % n)
+
+    def getExpectedValue(self, state):
+        return self._value(state)[0]
+
+    def getAction(self, state):
+        if not self._solved:
+            raise KeyError("getAction on a state that was never solved")
+        return self._value(state)[1]

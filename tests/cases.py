@@ -179,10 +179,26 @@ def case_XR_small():
                            inv_max=30, cash_min=-10, cash_max=90, name="XR_small"), [[0.0, 30.0]]
 
 
+def case_M2_small():
+    # MultiItemCash.java:33-121 scaled down: two products, discrete demands (GetPmfMulti.java:158-171)
+    d1 = S.DiscreteDistribution([1, 3, 4], [0.3, 0.5, 0.2])
+    d2 = S.DiscreteDistribution([0, 2], [0.4, 0.6])
+    table = S.GetPmfMulti([[d1] * 3, [d2] * 3], 0.999, 1).tables()
+    return S.two_product_cash_model(table, price=(4, 9), vari_cost=(2, 4), salvage=(1, 1), q_bound=6, inv_max=9,
+                                    cash_min=0, cash_max=70, name="M2_small"), [[0.0, 0.0, 12.0]]
+
+
+def case_M2_poisson():
+    # Poisson branch of GetPmfMulti, exact ties broken by the +0.1 tolerance, no tolerance variant below
+    table = S.GetPmfMulti([[S.PoissonDist(1.5)] * 2, [S.PoissonDist(1.0)] * 2], 0.99, 1).tables()
+    return S.two_product_cash_model(table, price=(5, 6), vari_cost=(2, 3), salvage=(1, 1.5), q_bound=5, inv_max=7,
+                                    cash_min=0, cash_max=45, gamma=0.95, name="M2_poisson"), [[1.0, 0.0, 9.0]]
+
+
 ALL = [case_A_small, case_A_max, case_A_gy, case_A_twopoint, case_A_halfstep, case_A_sparse_pmf,
        case_A_degenerate, case_A_one_state, case_B1_ref, case_B1_fixed,
        case_B2_small, case_C_small, case_C_rich, case_C_int, case_C_int_K, case_D_small, case_D_rich, case_DL_small,
-       case_DT_small, case_TP_small, case_E_small, case_F_small,
+       case_DT_small, case_TP_small, case_M2_small, case_M2_poisson, case_E_small, case_F_small,
        case_XR_small]
 
 
