@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define SDPB_ABI_VERSION 2
+#define SDPB_ABI_VERSION 3
 
 typedef enum sdpb_status {
     SDPB_OK = 0,
@@ -91,7 +91,12 @@ typedef enum sdpb_cost_kind {
      * by cash, revenue on what is sold, salvage in the last period:
      * src/cash/multiItem/MultiItemCash.java:69-117 with src/sdp/cash/multiItem/CashRecursionMulti.java:81-116
      * (MAX only, an action replaces the incumbent only if better by more than `tie_tolerance`). */
-    SDPB_COST_CASH_TWO_PRODUCT = 7
+    SDPB_COST_CASH_TWO_PRODUCT = 7,
+    /* workforce planning: state = staff on hand, action = hires, random turnover whose pmf depends on the
+     * hire-up-to level y = x + a:
+     * src/workforce/WorkforcePlanning.java:71-104 with src/workforce/StaffRecursion.java:81-121 (MIN).
+     * c = (a>0?K:0) + v*a + salary*(y-j) + (y-j > minStaff_t ? 0 : penalty*(minStaff_t - (y-j))). */
+    SDPB_COST_STAFF = 8
 } sdpb_cost_kind;
 
 typedef enum sdpb_recursion {
@@ -177,6 +182,15 @@ typedef struct sdpb_model {
     double price2, vari_cost2, salvage2;
     const double* pmf_d2;   /* second product's demand of every pmf row (same layout as pmf_d) */
     double tie_tolerance;   /* 0.1 in CashRecursionMulti.java:108; 0 = plain strict compare */
+
+    /* action-dependent demand (SDPB_COST_STAFF only): for period t and hire-up-to level y (grid index
+     * 0..n_inv-1; levels beyond the grid use the last row, StaffRecursion.java:95-96) the turnover j has
+     * probability apmf_p[off(t,y) + j], j = 0..apmf_len[t*n_inv + y]-1, rows concatenated in (t, y) order.
+     * hold_cost is the salary, penalty_cost the unit penalty, min_level_t the required staff per period.
+     * pmf_len / pmf_d / pmf_p are ignored (pass one dummy row per period). */
+    const int32_t* apmf_len;
+    const double*  apmf_p;
+    const double*  min_level_t;
 } sdpb_model;
 
 typedef enum sdpb_kernel_choice {

@@ -39,7 +39,8 @@ public final class SdpB200 {
             ADDRESS.withName("price_t"), ADDRESS.withName("vari_cost_t"), ADDRESS.withName("overhead_t"),
             ADDRESS.withName("reserve_t"), JAVA_DOUBLE.withName("reserve2"),
             JAVA_DOUBLE.withName("price2"), JAVA_DOUBLE.withName("vari_cost2"), JAVA_DOUBLE.withName("salvage2"),
-            ADDRESS.withName("pmf_d2"), JAVA_DOUBLE.withName("tie_tolerance"));
+            ADDRESS.withName("pmf_d2"), JAVA_DOUBLE.withName("tie_tolerance"),
+            ADDRESS.withName("apmf_len"), ADDRESS.withName("apmf_p"), ADDRESS.withName("min_level_t"));
 
     private static final Linker LINKER = Linker.nativeLinker();
     private static final SymbolLookup LIB =

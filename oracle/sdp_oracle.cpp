@@ -98,8 +98,10 @@ struct Model {
     double d1(int t, int j) const { return m.pmf_d[off[t - 1] + j]; }
     double d2(int t, int j) const { return m.pmf_d2[off[t - 1] + j]; }
     bool two() const { return m.cost_kind == SDPB_COST_CASH_TWO_PRODUCT; }
+    bool staff() const { return m.cost_kind == SDPB_COST_STAFF; }
+    std::vector<int64_t> aoff;  // staff: offsets of the (t, y) rows of apmf_p
     double p(int t, int j) const { return m.pmf_p[off[t - 1] + j]; }
-    bool cash() const { return m.cost_kind != SDPB_COST_BACKORDER; }
+    bool cash() const { return m.cost_kind != SDPB_COST_BACKORDER && m.cost_kind != SDPB_COST_STAFF; }
     bool flag(uint32_t f) const { return (m.flags & f) != 0; }
     double price(int t) const { return m.price_t ? m.price_t[t - 1] : m.price; }
     double vcost(int t) const { return m.vari_cost_t ? m.vari_cost_t[t - 1] : m.vari_cost; }
@@ -354,6 +356,17 @@ double immediate(const Model& M, const St& s, double action, double demand) {
         cashIncrement += salValue;
         return cashIncrement;
     }
+    case SDPB_COST_STAFF: {
+        // WorkforcePlanning.java:92-101 (all-integer state, action, turnover)
+        int act = (int)action, randomDemand = (int)demand, iniStaffNum = (int)s.x;
+        double fixHireCost = act > 0 ? m.fixed_cost : 0;
+        double variHireCost = M.vcost(s.t) * act;
+        int nextStaffNum = iniStaffNum + act - randomDemand;
+        double salaryCost = m.hold_cost * nextStaffNum;
+        int minStaff = (int)m.min_level_t[s.t - 1];
+        double penaltyCost = nextStaffNum > minStaff ? 0 : m.penalty_cost * (minStaff - nextStaffNum);
+        return fixHireCost + variHireCost + salaryCost + penaltyCost;
+    }
     case SDPB_COST_CASH_XR: {
         // CashConstraintXR.java:78-92 (action is the order-up-to level y; s.w holds R)
         double v = M.vcost(s.t);
@@ -382,6 +395,14 @@ St transition(const Model& M, const St& s, double action, double demand) {
     if (M.multi) {
         const int i = (int)action, j = (int)demand, Q = M.multi->Qbound;
         return multi_transition(M, s, i / Q, i % Q, M.multi->d1[j], M.multi->d2[j]);
+    }
+    if (M.staff()) {
+        // WorkforcePlanning.java:84-89
+        int nextStaffNum = (int)s.x + (int)action - (int)demand;
+        nextStaffNum = nextStaffNum > (int)m.inv_max ? (int)m.inv_max : nextStaffNum;
+        nextStaffNum = nextStaffNum < (int)m.inv_min ? (int)m.inv_min : nextStaffNum;
+        St n3; n3.t = s.t + 1; n3.x = nextStaffNum;
+        return n3;
     }
     if (M.two()) {
         // MultiItemCash.java:107-121 (upper clamp on item 1, lower clamp on item 2, as written there)
@@ -479,14 +500,24 @@ void solve_state(const Model& M, const St& s, NextValue&& next_value, double* va
     double val = is_min ? DBL_MAX : -DBL_MAX;
     double bestOrderQty = 0;
     int nFeasible = 0;
+    double nEvalsStaff = 0;
     for (int i = 0; i < nA; i++) {
         if (!action_feasible(M, s, i)) continue;
         nFeasible++;
         double orderQty = action_value(M, s, i);
         double thisQValue = 0;
+        // StaffRecursion.java:93-97: the pmf row is chosen by the hire-up-to level, capped at the last row
+        const double* arow = nullptr;
+        if (M.staff()) {
+            int hireUpTo = (int)jround((s.x - m.inv_min) / m.step) + i;
+            if (hireUpTo >= M.n_inv() - 1) hireUpTo = M.n_inv() - 1;
+            D = m.apmf_len[(s.t - 1) * M.n_inv() + hireUpTo];
+            arow = m.apmf_p + M.aoff[(size_t)(s.t - 1) * M.n_inv() + hireUpTo];
+            nEvalsStaff += D;
+        }
         for (int j = 0; j < D; j++) {
-            double randomDemand = M.d(s.t, j);
-            double dProb = M.p(s.t, j);
+            double randomDemand = M.staff() ? (double)j : M.d(s.t, j);
+            double dProb = M.staff() ? arow[j] : M.p(s.t, j);
             if (!survival) {
                 thisQValue += dProb * immediate(M, s, orderQty, randomDemand);
                 if (s.t < T) {
@@ -518,7 +549,7 @@ void solve_state(const Model& M, const St& s, NextValue&& next_value, double* va
             if (thisQValue > val + M.tie_tol) { val = thisQValue; bestOrderQty = orderQty; }
         }
     }
-    if (evals) *evals += (double)nFeasible * D;
+    if (evals) *evals += M.staff() ? nEvalsStaff : (double)nFeasible * D;
     *val_out = val;
     *best_out = bestOrderQty;
 }
@@ -618,6 +649,11 @@ struct Grid {
 Model make_model(const sdpb_model* m) {
     Model M; M.m = *m;
     if (m->cost_kind == SDPB_COST_CASH_TWO_PRODUCT) M.tie_tol = m->tie_tolerance;
+    if (m->cost_kind == SDPB_COST_STAFF) {
+        const size_t rows = (size_t)m->T * M.n_inv();
+        M.aoff.assign(rows + 1, 0);
+        for (size_t r = 0; r < rows; r++) M.aoff[r + 1] = M.aoff[r] + m->apmf_len[r];
+    }
     M.off.resize(m->T + 1, 0);
     for (int t = 0; t < m->T; t++) M.off[t + 1] = M.off[t] + m->pmf_len[t];
     return M;

@@ -4,15 +4,15 @@ Everything that computes lives in libsdpb200.so (hand-written sm_100a CUDA, csrc
 is the host-side mirror of the reference's Java classes plus the descriptor builders.
 """
 from . import _abi as abi
-from ._abi import (COST_CASH_TWO_PRODUCT, KERNEL_LEAD_COL, KERNEL_CASH_DIAG, COST_CASH_LOAN, COST_CASH_OD_LIMIT, COST_CASH_OD_TESTING, Q_TRUNC, KERNEL_CASH_INT, KERNEL_TILED2, KERNEL_LEAD_SLAB, COST_BACKORDER, COST_CASH_DEPOSIT, COST_CASH_OVERDRAFT, COST_CASH_XR, KERNEL_AUTO,
+from ._abi import (COST_STAFF, COST_CASH_TWO_PRODUCT, KERNEL_LEAD_COL, KERNEL_CASH_DIAG, COST_CASH_LOAN, COST_CASH_OD_LIMIT, COST_CASH_OD_TESTING, Q_TRUNC, KERNEL_CASH_INT, KERNEL_TILED2, KERNEL_LEAD_SLAB, COST_BACKORDER, COST_CASH_DEPOSIT, COST_CASH_OVERDRAFT, COST_CASH_XR, KERNEL_AUTO,
                    KERNEL_GENERIC, KERNEL_STAGED, KERNEL_TILED, MAX, MIN, Q_DIV, Q_LONGDIV, REC_EXPECT, REC_SURVIVAL,
                    SdpbError)
 from .getpmf import (GetPmfMulti, DiscreteDistribution, GammaDist, GetPmf, NormalDist, PoissonDist, UniformIntDist,
                      clsp_inline_pmf, poisson_pmf)
-from .models import (two_product_cash_model, ModelSpec, cash_loan_model, cash_overdraft_limit_model, cash_overdraft_testing_model,
+from .models import (workforce_model, two_product_cash_model, ModelSpec, cash_loan_model, cash_overdraft_limit_model, cash_overdraft_testing_model,
                      cash_constraint_model, cash_leadtime_model, cash_overdraft_model,
                      cash_survival_model, cash_xr_model, inventory_model, leadtime_model)
-from .recursion import (Actions, CashRecursionMulti, CashStateMulti, CashLeadtimeRecursion, CashLeadtimeState, CashRecursion, CashRecursionXR,
+from .recursion import (StaffRecursion, StaffState, Actions, CashRecursionMulti, CashStateMulti, CashLeadtimeRecursion, CashLeadtimeState, CashRecursion, CashRecursionXR,
                         CashState, CashStateXR, LeadtimeRecursion, LeadtimeRecursion2, LeadtimeState,
                         OptDirection, Recursion, RiskRecursion, RiskState, State)
 from .solver import Solver

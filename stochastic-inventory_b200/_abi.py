@@ -20,7 +20,7 @@ STATUS_NAMES = {0: "SDPB_OK", -1: "SDPB_ERR_ARG", -2: "SDPB_ERR_OFFGRID", -3: "S
                 -4: "SDPB_ERR_CUDA", -5: "SDPB_ERR_STATE", -6: "SDPB_ERR_NOMEM", -7: "SDPB_ERR_UNSOLVED"}
 
 COST_BACKORDER, COST_CASH_DEPOSIT, COST_CASH_OVERDRAFT, COST_CASH_XR = 0, 1, 2, 3
-COST_CASH_OD_LIMIT, COST_CASH_OD_TESTING, COST_CASH_LOAN, COST_CASH_TWO_PRODUCT = 4, 5, 6, 7
+COST_CASH_OD_LIMIT, COST_CASH_OD_TESTING, COST_CASH_LOAN, COST_CASH_TWO_PRODUCT, COST_STAFF = 4, 5, 6, 7, 8
 REC_EXPECT, REC_SURVIVAL = 0, 1
 MIN, MAX = 0, 1
 Q_DIV, Q_LONGDIV, Q_TRUNC = 0, 1, 2
@@ -51,6 +51,7 @@ class SdpbModel(C.Structure):
         ("reserve2", C.c_double),
         ("price2", C.c_double), ("vari_cost2", C.c_double), ("salvage2", C.c_double), ("pmf_d2", _dp),
         ("tie_tolerance", C.c_double),
+        ("apmf_len", _ip), ("apmf_p", _dp), ("min_level_t", _dp),
     ]
 
 

@@ -34,6 +34,11 @@ struct DevModel {
     double price2, v2, salvage2, tie_tol;  // second product / tie tolerance (SDPB_COST_CASH_TWO_PRODUCT)
     const double* pmf_d2;
     const int* pmf_di2;
+    // action-dependent pmf (SDPB_COST_STAFF): rows indexed by (t, hire-up-to level)
+    const int* apmf_len;
+    const int* apmf_off;
+    const double* apmf_p;
+    const double* min_level_t;
     // per-period parameter tables, always expanded to T entries on the host
     const double* price_t;
     const double* v_t;

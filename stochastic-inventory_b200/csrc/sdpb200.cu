@@ -17,6 +17,7 @@
 #include "kernel_lead.cuh"
 #include "kernel_cash.cuh"
 #include "kernel_two_product.cuh"
+#include "kernel_staff.cuh"
 #include "microbench.cuh"
 
 using namespace sdpb;
@@ -53,6 +54,7 @@ struct sdpb_handle {
     std::vector<double> pmf_d, pmf_p;
     std::vector<int> pmf_di;  // demand values in units of step
     std::vector<double> pmf_d2;
+    std::vector<int> apmf_len;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -117,7 +119,8 @@ int fail_create(sdpb_handle* h, int code, const std::string& msg) {
     return code;
 }
 
-bool has_cash(const sdpb_model& m) { return m.cost_kind != SDPB_COST_BACKORDER; }
+bool has_cash(const sdpb_model& m) { return m.cost_kind != SDPB_COST_BACKORDER && m.cost_kind != SDPB_COST_STAFF; }
+bool staff_kind(const sdpb_model& m) { return m.cost_kind == SDPB_COST_STAFF; }
 bool two_product(const sdpb_model& m) { return m.cost_kind == SDPB_COST_CASH_TWO_PRODUCT; }
 
 double cash_of_k(const sdpb_handle* h, long long k) {
@@ -215,6 +218,14 @@ double count_evals_period_uncached(const sdpb_handle* h, int t) {
     const sdpb_model& m = h->m;
     const DevModel& d = h->dm;
     const double D = h->pmf_len[t - 1];
+    if (staff_kind(m)) {
+        // sum over the shard's states and actions of the length of the pmf row they use
+        double total = 0;
+        const int* len = h->apmf_len.data() + (size_t)(t - 1) * d.nI;
+        for (long long ix = h->lo; ix < h->hi; ix++)
+            for (int i = 0; i <= m.max_order_idx; i++) total += len[std::min<long long>(ix + i, d.nI - 1)];
+        return total;
+    }
     if (two_product(m)) {
         // affordable pairs depend on the cash level only (MultiItemCash.java:73)
         const double v1 = m.vari_cost_t ? m.vari_cost_t[t - 1] : m.vari_cost;
@@ -294,6 +305,19 @@ int dispatch_generic_d(sdpb_handle* h, int t, const double* Vn, double* Vt, int*
         if (mn) launch_generic<SDPB_COST_CASH_XR, false, true, 1, false>(h, t, Vn, Vt, Qt, lo, hi);
         else launch_generic<SDPB_COST_CASH_XR, false, false, 1, false>(h, t, Vn, Vt, Qt, lo, hi);
         break;
+    case SDPB_COST_STAFF: {
+        if (DEDUP) { h->err = "no lead time to fold"; return SDPB_ERR_ARG; }
+        const long long nst = hi - lo;
+        if (nst > 0) {
+            const unsigned blocks = (unsigned)((nst + 7) / 8);
+            const bool last = t == h->m.T;
+            if (mn) { if (last) bi_staff<true, true><<<blocks, 256, 0, h->stream>>>(h->dm, t, Vn, Vt, Qt, lo, hi);
+                      else bi_staff<true, false><<<blocks, 256, 0, h->stream>>>(h->dm, t, Vn, Vt, Qt, lo, hi); }
+            else    { if (last) bi_staff<false, true><<<blocks, 256, 0, h->stream>>>(h->dm, t, Vn, Vt, Qt, lo, hi);
+                      else bi_staff<false, false><<<blocks, 256, 0, h->stream>>>(h->dm, t, Vn, Vt, Qt, lo, hi); }
+        }
+        break;
+    }
     case SDPB_COST_CASH_TWO_PRODUCT: {
         if (DEDUP) { h->err = "no lead time to fold"; return SDPB_ERR_ARG; }
         const long long nst = hi - lo;
@@ -523,7 +547,11 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         return fail_create(nullptr, SDPB_ERR_ARG, "sdpb_options.struct_size does not match this library");
     if (m->T < 1 || !m->pmf_len || !m->pmf_d || !m->pmf_p)
         return fail_create(nullptr, SDPB_ERR_ARG, "T < 1 or null pmf");
-    if (m->cost_kind < 0 || m->cost_kind > SDPB_COST_CASH_TWO_PRODUCT) return fail_create(nullptr, SDPB_ERR_ARG, "bad cost_kind");
+    if (m->cost_kind < 0 || m->cost_kind > SDPB_COST_STAFF) return fail_create(nullptr, SDPB_ERR_ARG, "bad cost_kind");
+    if (m->cost_kind == SDPB_COST_STAFF &&
+        (!m->apmf_len || !m->apmf_p || !m->min_level_t || m->step != 1.0 || m->lead_time != 0 ||
+         m->recursion != SDPB_REC_EXPECT))
+        return fail_create(nullptr, SDPB_ERR_ARG, "staff kind needs apmf_len, apmf_p, min_level_t and a unit step");
     if (m->cost_kind == SDPB_COST_CASH_TWO_PRODUCT &&
         (!m->pmf_d2 || m->quantiser != SDPB_Q_TRUNC || m->recursion != SDPB_REC_EXPECT || m->step != 1.0))
         return fail_create(nullptr, SDPB_ERR_ARG, "two-product kind needs pmf_d2, the (int) cash quantiser, unit step");
@@ -655,6 +683,7 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     d.q_from_period = m->q_from_period;
     d.price2 = m->price2; d.v2 = m->vari_cost2; d.salvage2 = m->salvage2; d.tie_tol = m->tie_tolerance;
     d.pmf_d2 = nullptr; d.pmf_di2 = nullptr;
+    d.apmf_len = nullptr; d.apmf_off = nullptr; d.apmf_p = nullptr; d.min_level_t = nullptr;
     long long S = d.nI;
     if (two_product(*m)) S *= d.nI;
     for (int l = 0; l < m->lead_time; l++) S *= d.nQ;
@@ -699,6 +728,18 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     UP(price_t, price_t, dp) UP(v_t, v_t, dp) UP(ovh_t, ovh_t, dp) UP(res_t, reserve_t, dp)
     UP(h->pmf_d, pmf_d, dp) UP(h->pmf_p, pmf_p, dp) UP(pg, pmf_pg, dp) UP(pdi, pmf_di, di)
     if (two_product(*m)) { UP(pd2, pmf_d2, dp) UP(pdi2, pmf_di2, di) }
+    if (staff_kind(*m)) {
+        const size_t rows = (size_t)T * d.nI;
+        h->apmf_len.assign(m->apmf_len, m->apmf_len + rows);
+        std::vector<int> aoff(rows + 1, 0);
+        for (size_t r = 0; r < rows; r++) {
+            if (h->apmf_len[r] < 1) return fail_create(h, SDPB_ERR_ARG, "empty action-dependent pmf row");
+            aoff[r + 1] = aoff[r] + h->apmf_len[r];
+        }
+        std::vector<double> ap(m->apmf_p, m->apmf_p + aoff[rows]);
+        std::vector<double> ml(m->min_level_t, m->min_level_t + T);
+        UP(h->apmf_len, apmf_len, di) UP(aoff, apmf_off, di) UP(ap, apmf_p, dp) UP(ml, min_level_t, dp)
+    }
 #undef UP
 
     h->dV.assign(T, nullptr);
@@ -916,7 +957,7 @@ int sdpb_state_of_index(const sdpb_handle* h, int64_t idx, double* state) {
 int sdpb_reach(sdpb_handle* h, const double* init_states, int n) {
     if (!h || !init_states || n < 1) return SDPB_ERR_ARG;
     if (h->opt.shard_count != 1) { h->err = "sdpb_reach needs an unsharded handle"; return SDPB_ERR_STATE; }
-    if (two_product(h->m)) { h->err = "sdpb_reach is not implemented for two-product models"; return SDPB_ERR_ARG; }
+    if (two_product(h->m) || staff_kind(h->m)) { h->err = "sdpb_reach is not implemented for two-product and staff models"; return SDPB_ERR_ARG; }
     CU(cudaSetDevice(h->device));
     const int T = h->m.T;
     for (int t = 0; t < T; t++) {
@@ -990,7 +1031,7 @@ int sdpb_eval_triples(sdpb_handle* h, int period, const double* states, const in
                       const double* demand, int n, double* c, double* next_states, int32_t* n_actions) {
     if (!h || !states || !action_idx || !demand || n < 1) return SDPB_ERR_ARG;
     if (period < 1 || period > h->m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
-    if (two_product(h->m)) { h->err = "sdpb_eval_triples is not implemented for two-product models"; return SDPB_ERR_ARG; }
+    if (two_product(h->m) || staff_kind(h->m)) { h->err = "sdpb_eval_triples is not implemented for two-product and staff models"; return SDPB_ERR_ARG; }
     CU(cudaSetDevice(h->device));
     std::vector<long long> sidx(n), hnext(n);
     std::vector<int> demi(n), hna(n);
@@ -1047,7 +1088,7 @@ int sdpb_simulate(sdpb_handle* h, const double* init_state, const double* sample
                   double* values) {
     if (!h || !init_state || !samples || !values || n < 1) return SDPB_ERR_ARG;
     if (h->opt.shard_count != 1) { h->err = "sdpb_simulate needs an unsharded handle"; return SDPB_ERR_STATE; }
-    if (two_product(h->m)) { h->err = "sdpb_simulate is not implemented for two-product models"; return SDPB_ERR_ARG; }
+    if (two_product(h->m) || staff_kind(h->m)) { h->err = "sdpb_simulate is not implemented for two-product and staff models"; return SDPB_ERR_ARG; }
     const int T = h->m.T;
     for (int t = 0; t < T; t++)
         if (!h->solved[t]) { h->err = "not solved"; return SDPB_ERR_STATE; }

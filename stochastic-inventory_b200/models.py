@@ -57,6 +57,8 @@ class ModelSpec:
     vari_cost2: float = 0.0
     salvage2: float = 0.0
     tie_tolerance: float = 0.0
+    apmf: Optional[Sequence] = None          # staff kind: apmf[t][y] = probabilities of turnover 0..len-1
+    min_level_t: Optional[Sequence[float]] = None
     name: str = ""
 
     @property
@@ -65,7 +67,11 @@ class ModelSpec:
 
     @property
     def has_cash(self):
-        return self.cost_kind != A.COST_BACKORDER
+        return self.cost_kind not in (A.COST_BACKORDER, A.COST_STAFF)
+
+    @property
+    def staff(self):
+        return self.cost_kind == A.COST_STAFF
 
     @property
     def two_product(self):
@@ -97,6 +103,17 @@ class ModelSpec:
         m.pmf_len = lens.ctypes.data_as(C.POINTER(C.c_int32))
         m.pmf_d = d.ctypes.data_as(C.POINTER(C.c_double))
         m.pmf_p = p.ctypes.data_as(C.POINTER(C.c_double))
+        if self.staff:
+            n_inv = int(round((self.inv_max - self.inv_min) / self.step)) + 1
+            if len(self.apmf) != self.T or any(len(rows) != n_inv for rows in self.apmf):
+                raise ValueError("apmf must be [T][n_inv] rows")
+            alen = np.ascontiguousarray([len(r) for rows in self.apmf for r in rows], dtype=np.int32)
+            ap = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.float64) for rows in self.apmf for r in rows]))
+            ml = np.ascontiguousarray(self.min_level_t, dtype=np.float64)
+            keep += [alen, ap, ml]
+            m.apmf_len = alen.ctypes.data_as(C.POINTER(C.c_int32))
+            m.apmf_p = ap.ctypes.data_as(C.POINTER(C.c_double))
+            m.min_level_t = ml.ctypes.data_as(C.POINTER(C.c_double))
         for f in ("price_t", "vari_cost_t", "overhead_t", "reserve_t"):
             v = getattr(self, f)
             if v is not None:
@@ -304,3 +321,25 @@ def two_product_cash_model(pmf, price=(4.0, 50.0), vari_cost=(2.0, 4.0), salvage
                      gamma=gamma, cash_min=cash_min, cash_max=cash_max, quantiser=A.Q_TRUNC, q_mul=1.0, q_div=1.0,
                      price=price[0], vari_cost=vari_cost[0], salvage=salvage[0], price2=price[1],
                      vari_cost2=vari_cost[1], salvage2=salvage[1], tie_tolerance=tie_tolerance, name=name)
+
+
+def workforce_model(turnover_rate, fix_cost=100.0, unit_vari_cost=10.0, salary=20.0, unit_penalty=80.0,
+                    min_staff=None, max_hire=500, max_x=600, name="workforce") -> ModelSpec:
+    """Workforce planning with binomial turnover whose pmf depends on the hire-up-to level.
+    Lambdas: src/workforce/WorkforcePlanning.java:52-104 (pmf[t][y][j] = Binomial(y, turnoverRate[t]).prob(j),
+    :52-68); engine: src/workforce/StaffRecursion.java:81-121 (MIN)."""
+    from scipy import stats
+    T = len(turnover_rate)
+    if min_staff is None:
+        min_staff = [40] * T
+    apmf = []
+    for t in range(T):
+        rows = []
+        for y in range(max_x + 1):
+            rows.append(np.array([1.0]) if y == 0 else stats.binom(y, turnover_rate[t]).pmf(np.arange(y + 1)))
+        apmf.append(rows)
+    dummy = [np.array([[0.0, 1.0]]) for _ in range(T)]
+    return ModelSpec(cost_kind=A.COST_STAFF, pmf=dummy, inv_min=0.0, inv_max=float(max_x), max_order_idx=int(max_hire),
+                     direction=A.MIN, flags=A.F_CLAMP_INV, fixed_cost=fix_cost, vari_cost=unit_vari_cost,
+                     hold_cost=salary, penalty_cost=unit_penalty, apmf=apmf, min_level_t=[float(x) for x in min_staff],
+                     name=name)

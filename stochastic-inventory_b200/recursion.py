@@ -356,3 +356,22 @@ class CashRecursionMulti:
         if not self._solved:
             raise KeyError("getAction on a state that was never solved")
         return self._value(state)[1]
+
+
+# ---- workforce ------------------------------------------------------------------------------
+class StaffState(State):
+    """src/workforce/StaffState.java:4-14."""
+
+    def __init__(self, period, iniStaffNum):
+        super().__init__(period, iniStaffNum)
+        self.iniStaffNum = int(iniStaffNum)
+
+
+class StaffRecursion(_Engine):
+    """new StaffRecursion(A, f, c, pmf, T) -> StaffRecursion(spec); src/workforce/StaffRecursion.java:39-121.
+    getOptTable / spot checks are not wired for this kind yet."""
+    state_cls = StaffState
+    _kinds = (A.COST_STAFF,)
+
+    def getAction(self, state):
+        return int(super().getAction(state))

@@ -195,10 +195,16 @@ def case_M2_poisson():
                                     cash_min=0, cash_max=45, gamma=0.95, name="M2_poisson"), [[1.0, 0.0, 9.0]]
 
 
+def case_W_small():
+    # WorkforcePlanning.java:33-104 scaled down: binomial turnover depending on the hire-up-to level
+    return S.workforce_model([0.5, 0.3, 0.4], fix_cost=30, unit_vari_cost=4, salary=6, unit_penalty=25,
+                             min_staff=[8, 10, 6], max_hire=20, max_x=30, name="W_small"), [[0.0]]
+
+
 ALL = [case_A_small, case_A_max, case_A_gy, case_A_twopoint, case_A_halfstep, case_A_sparse_pmf,
        case_A_degenerate, case_A_one_state, case_B1_ref, case_B1_fixed,
        case_B2_small, case_C_small, case_C_rich, case_C_int, case_C_int_K, case_D_small, case_D_rich, case_DL_small,
-       case_DT_small, case_TP_small, case_M2_small, case_M2_poisson, case_E_small, case_F_small,
+       case_DT_small, case_TP_small, case_M2_small, case_M2_poisson, case_W_small, case_E_small, case_F_small,
        case_XR_small]
 
 

@@ -196,8 +196,8 @@ def test_value_and_opt_table_match_topdown(case, S, oracle):
     s = S.Solver(spec).solve()
     v, q = s.value(1, init)
     assert np.array_equal(v, iv)
-    if spec.two_product:
-        # reachability / opt-table extraction is not implemented for the two-product kind yet; every
+    if spec.two_product or spec.staff:
+        # reachability / opt-table extraction is not implemented for these kinds yet; every
         # visited state still answers through sdpb_value
         nd = spec.ndim
         for t in range(1, spec.T + 1):
@@ -228,8 +228,8 @@ def test_device_lambdas_match_oracle(case, S, oracle):
     """sdpb_eval_triples (the device code of c, f, |A|) against the oracle's lambdas."""
     import random
     spec, _ = case()
-    if spec.two_product:
-        pytest.skip("sdpb_eval_triples is not implemented for the two-product kind")
+    if spec.two_product or spec.staff:
+        pytest.skip("sdpb_eval_triples is not implemented for the two-product and staff kinds")
     pkg = S.package
     from importlib import import_module
     spot = import_module(pkg.__name__ + "._spot")
@@ -383,6 +383,16 @@ def test_two_product_tolerance_changes_the_answer(S, oracle):
     for sp, Vo, Qo in ((spec, Va, Qa), (spec0, Vb, Qb)):
         s, V, Q = _solve_all(S, sp)
         assert np.array_equal(V, Vo) and np.array_equal(Q, Qo)
+
+
+def test_reference_style_driver_workforce(S, oracle):
+    """Reads like src/workforce/WorkforcePlanning.java:106-118."""
+    spec, init = cases.case_W_small()
+    recursion = S.StaffRecursion(spec)
+    initialState = S.StaffState(1, 0)
+    rows, iv, _ = oracle.topdown(spec, init)
+    assert recursion.getExpectedValue(initialState) == iv[0]
+    assert recursion.getAction(initialState) == int(rows[0][-2])
 
 
 def test_reference_style_driver_survival(S, oracle):
