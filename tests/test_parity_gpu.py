@@ -296,6 +296,82 @@ def test_reference_style_simulation(S, oracle):
     assert np.array_equal(sim.simulate_paths(S.State(1, 0), samples), oracle.simulate(spec, Qo, [0.0], samples))
 
 
+@pytest.mark.parametrize("case,world", [(cases.case_A_small, 2), (cases.case_A_gy, 3), (cases.case_B2_small, 3),
+                                        (cases.case_B1_ref, 2), (cases.case_C_int, 3), (cases.case_C_rich, 2),
+                                        (cases.case_F_small, 2), (cases.case_E_small, 2), (cases.case_M2_small, 3),
+                                        (cases.case_W_small, 2)], ids=lambda x: getattr(x, "__name__", str(x))[5:])
+def test_sharded_handles_on_one_gpu(case, world, S, oracle):
+    """The multi-GPU data path on one device: `world` handles with shard_rank 0..world-1, stepped period
+    by period; after each period every rank's block of V_t is copied into every other rank's table (what
+    the NCCL all-gather does).  Checks the kernels' [lo, hi) handling bit for bit."""
+    import torch
+    par = S.package.parallel
+    spec, _ = case()
+    Vo, Qo, evals, _ = oracle.dense(spec)
+    n = Vo.shape[1]
+    hs = [S.Solver(spec, shard_rank=r, shard_count=world) for r in range(world)]
+    bounds = [par.shard_bounds(n, r, world) for r in range(world)]
+    chunk = bounds[0][2]
+    for t in range(spec.T, 0, -1):
+        for h in hs:
+            h.solve_period_async(t)
+        for h in hs:
+            h.sync()
+        tabs = [par.wrap_device(torch, h.device_tables(t)[0], chunk * world, "<f8", 0) for h in hs]
+        for r, (lo, hi, _) in enumerate(bounds):
+            for r2 in range(world):
+                if r2 != r:
+                    tabs[r2][lo:hi].copy_(tabs[r][lo:hi])
+        torch.cuda.synchronize()
+    total = 0.0
+    for r, (lo, hi, _) in enumerate(bounds):
+        for t in range(1, spec.T + 1):
+            dv, dq = hs[r].device_tables(t)
+            V = par.wrap_device(torch, dv, chunk * world, "<f8", 0)[:n].cpu().numpy()
+            Qi = par.wrap_device(torch, dq, chunk * world, "<i4", 0)[lo:hi].cpu().numpy()
+            assert np.array_equal(V, Vo[t - 1]), (r, t)
+            # policy: action index -> order quantity (pair index for the two-product kind)
+            q = np.where(Qi < 0, 0.0, Qi * spec.step)
+            if spec.cost_kind == S.COST_CASH_XR:
+                pytest.skip("XR policy needs the state's inventory")
+            assert np.array_equal(q, Qo[t - 1][lo:hi]), (r, t)
+        total += hs[r].stats()["evals"]
+    assert total == evals
+
+
+def test_large_sharded_c5_on_one_gpu(S, oracle):
+    """tiled2 with shard boundaries that cut through 1021-state tiles."""
+    import torch
+    par = S.package.parallel
+    spec = S.configs.c5(n_states=300_007, T=2, n_actions=37)
+    ref = S.Solver(spec).solve()
+    world = 3
+    hs = [S.Solver(spec, shard_rank=r, shard_count=world, kernel=S.KERNEL_TILED2) for r in range(world)]
+    n = ref.n_states
+    bounds = [par.shard_bounds(n, r, world) for r in range(world)]
+    chunk = bounds[0][2]
+    for t in (2, 1):
+        for h in hs:
+            h.solve_period_async(t)
+        for h in hs:
+            h.sync()
+        tabs = [par.wrap_device(torch, h.device_tables(t)[0], chunk * world, "<f8", 0) for h in hs]
+        for r, (lo, hi, _) in enumerate(bounds):
+            for r2 in range(world):
+                if r2 != r:
+                    tabs[r2][lo:hi].copy_(tabs[r][lo:hi])
+        torch.cuda.synchronize()
+    assert hs[0].stats()["kernel_used"] == S.KERNEL_TILED2
+    for t in (1, 2):
+        Vr, Qr = ref.period_tables(t)
+        for r, (lo, hi, _) in enumerate(bounds):
+            dv, dq = hs[r].device_tables(t)
+            V = par.wrap_device(torch, dv, chunk * world, "<f8", 0)[:n].cpu().numpy()
+            Qi = par.wrap_device(torch, dq, chunk * world, "<i4", 0)[lo:hi].cpu().numpy()
+            assert np.array_equal(V, Vr)
+            assert np.array_equal(Qi * spec.step, Qr[lo:hi])
+
+
 def test_unsolved_state_raises(S):
     spec, _ = cases.case_A_small()
     s = S.Solver(spec)
