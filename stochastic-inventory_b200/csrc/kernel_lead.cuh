@@ -294,7 +294,7 @@ inline int launch_lead(const LeadPlan& P, const DevModel& dm, int t, int D, int 
 // staging, no per-tile set-up.  A CTA is NQB whole preQ2 values x all actions (505 of 512 threads
 // busy for C4), so the argopt over a stays inside the CTA: after each chunk the 8 x NQB states are
 // reduced through shared memory with the lexicographic (value, action) rule.
-constexpr int kColYT = 8;
+constexpr int kColYT = 8;  // default levels per chunk; a 4-level instantiation exists for the tuning knob
 
 struct ColArgs {
     int t, D, pmf_off;
@@ -309,10 +309,9 @@ struct ColArgs {
     int nthreads;
 };
 
-template <bool IS_MIN, bool LAST, bool DEDUP>
-__global__ void __launch_bounds__(512)
+template <bool IS_MIN, bool LAST, bool DEDUP, int YT>
+__global__ void __launch_bounds__(512, (YT == 4 ? 2 : 1))
 bi_lead_col(const __grid_constant__ DevModel M, const __grid_constant__ ColArgs a) {
-    constexpr int YT = kColYT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = a.D, A = a.A;
     // layout: [ red 2 x YT*nthreads doubles (double-buffered) ][ Lw NRW doubles ][ RO NRW int64 row offsets ][ PP D double2 ]
@@ -387,28 +386,24 @@ bi_lead_col(const __grid_constant__ DevModel M, const __grid_constant__ ColArgs 
                 if (!LAST) pre = ldg_at(col, lds_s64(ro_s + (unsigned)max(wi0 - 2, 0) * 8u));             \
                 const double lnew = lds_double(lw_s + (unsigned)max(wi0 - 1, 0) * 8u);                    \
                 _Pragma("unroll") for (int k = 0; k < YT; k++) {                                          \
-                    const int ph = (k - (JJ)) & 7;                                                        \
+                    const int ph = (k - (JJ)) & (YT - 1);                                                 \
                     acc[k] += pp.x * cst[ph];                      /* LeadtimeRecursion.java:59 */       \
                     if (!LAST) acc[k] += pp.y * Vw[ph];            /* LeadtimeRecursion.java:62 */       \
                 }                                                                                         \
-                const int pn = (7 - (JJ)) & 7;                                                            \
+                const int pn = (YT - 1 - (JJ)) & (YT - 1);                                                \
                 cst[pn] = fv + lnew;                                                                      \
                 Vw[pn] = vnew;                                                                            \
                 wi0 -= 1;                                                                                 \
                 j += 1;                                                                                   \
             }
             int j = 0;
-            for (; j + 8 <= D;) {
-                SDPB_COL_STEP(0) SDPB_COL_STEP(1) SDPB_COL_STEP(2) SDPB_COL_STEP(3)
-                SDPB_COL_STEP(4) SDPB_COL_STEP(5) SDPB_COL_STEP(6) SDPB_COL_STEP(7)
+            for (; j + YT <= D;) {
+#pragma unroll
+                for (int jj = 0; jj < YT; jj++) SDPB_COL_STEP(jj)
             }
-            if (j < D) SDPB_COL_STEP(0)
-            if (j < D) SDPB_COL_STEP(1)
-            if (j < D) SDPB_COL_STEP(2)
-            if (j < D) SDPB_COL_STEP(3)
-            if (j < D) SDPB_COL_STEP(4)
-            if (j < D) SDPB_COL_STEP(5)
-            if (j < D) SDPB_COL_STEP(6)
+#pragma unroll
+            for (int jj = 0; jj < YT - 1; jj++)
+                if (j < D) SDPB_COL_STEP(jj)
 #undef SDPB_COL_STEP
         }
         // ---- argopt over the actions of each of the YT x NQB states of this chunk ----
@@ -448,6 +443,7 @@ bi_lead_col(const __grid_constant__ DevModel M, const __grid_constant__ ColArgs 
 
 struct ColPlan {
     bool ok = false;
+    int YT = kColYT;
     int NQB = 1, nthreads = 0, LT = 0, di_max = 0, span = 0, NRW = 0;
     size_t smem = 0;
 };
@@ -467,13 +463,14 @@ inline ColPlan plan_col(const sdpb_model& m, const DevModel& d, int D, const int
     if (const char* e = std::getenv("SDPB_COL_THREADS")) max_threads = std::max(32, std::min(512, std::atoi(e)));  // tuning knob
     P.NQB = m.lead_time == 2 ? std::max(1, std::min(max_threads / A, d.nQ)) : 1;
     P.nthreads = ((P.NQB * A + 31) / 32) * 32;
+    if (const char* e = std::getenv("SDPB_COL_YT")) P.YT = std::atoi(e) == 4 ? 4 : 8;  // tuning knob
     const int n_levels = dedup ? d.nI + d.nQ - 1 : d.nQ;
     // real grid: one CTA walks the whole preQ1 axis; folded grid: 64 levels per CTA for parallelism
-    P.LT = dedup ? 64 : ((n_levels + kColYT - 1) / kColYT) * kColYT;
+    P.LT = dedup ? 64 : ((n_levels + P.YT - 1) / P.YT) * P.YT;
     P.di_max = hi;
     P.span = hi - lo;
     P.NRW = P.LT + P.span;
-    P.smem = ((((size_t)2 * kColYT * P.nthreads + 2 * (size_t)P.NRW) * 8 + 15) & ~(size_t)15) + (size_t)D * 16 + 16;
+    P.smem = ((((size_t)2 * P.YT * P.nthreads + 2 * (size_t)P.NRW) * 8 + 15) & ~(size_t)15) + (size_t)D * 16 + 16;
     P.ok = P.smem <= 100 * 1024;
     return P;
 }
@@ -500,8 +497,12 @@ inline int launch_col(const ColPlan& P, const DevModel& dm, int t, int D, int pm
     const bool last = (t == dm.T), mn = dm.is_min != 0;
     cudaError_t e = cudaSuccess;
 #define SDPB_COL_LAUNCH(MN, LS)                                                                        \
-    {                                                                                                  \
-        auto k = bi_lead_col<MN, LS, DEDUP>;                                                           \
+    if (P.YT == 4) {                                                                                   \
+        auto k = bi_lead_col<MN, LS, DEDUP, 4>;                                                        \
+        if (P.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem); \
+        if (e == cudaSuccess) k<<<(unsigned)blocks, P.nthreads, P.smem, stream>>>(dm, a);              \
+    } else {                                                                                           \
+        auto k = bi_lead_col<MN, LS, DEDUP, 8>;                                                        \
         if (P.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem); \
         if (e == cudaSuccess) k<<<(unsigned)blocks, P.nthreads, P.smem, stream>>>(dm, a);              \
     }

@@ -386,8 +386,8 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
         if (cp.ok && h->opt.kernel != SDPB_KERNEL_LEAD_SLAB) {
             h->stats.kernel_used = SDPB_KERNEL_LEAD_COL;
             const double ev = (double)(hi - lo) * (h->m.max_order_idx + 1) * h->pmf_len[t - 1];
-            // per 8 evaluations: 1 new cost + 8 (p*c) + 8 adds (+ 8 (p*gamma*V) + 8 adds)
-            h->stats.fp64_ops += ev * (t == h->m.T ? 17.0 / 8.0 : 33.0 / 8.0);
+            // per YT evaluations: 1 new cost + YT (p*c) + YT adds (+ YT (p*gamma*V) + YT adds)
+            h->stats.fp64_ops += ev * (t == h->m.T ? (1.0 + 2.0 * cp.YT) / cp.YT : (1.0 + 4.0 * cp.YT) / cp.YT);
             return launch_col<DEDUP>(cp, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi, h->stream);
         }
         const LeadPlan lp = plan_lead(h->m, h->dm, h->pmf_len[t - 1], h->pmf_di.data() + h->pmf_off[t - 1]);
