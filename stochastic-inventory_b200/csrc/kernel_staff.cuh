@@ -63,4 +63,17 @@ bi_staff(const __grid_constant__ DevModel M, const int t, const double* __restri
     }
 }
 
+// Forward reachability for the staff kind (the states StaffRecursion's memoisation visits).
+__global__ void __launch_bounds__(128)
+reach_staff(const __grid_constant__ DevModel M, const int t, const unsigned char* __restrict__ mask_t,
+            unsigned char* __restrict__ mask_n) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ix >= M.nI || !mask_t[ix]) return;
+    const int* __restrict__ alen = M.apmf_len + (size_t)(t - 1) * M.nI;
+    for (int i = 0; i <= M.max_order_idx; i++) {
+        const int D = alen[min(ix + i, M.nI - 1)];
+        for (int j = 0; j < D; j++) mask_n[max(min(ix + i - j, M.nI - 1), 0)] = 1;
+    }
+}
+
 }  // namespace sdpb

@@ -84,4 +84,43 @@ bi_two_product(const __grid_constant__ DevModel M, const int t, const int D, con
     Qt[idx] = besti;
 }
 
+// Forward reachability for the two-product kind (what CashRecursionMulti's memoisation visits).
+__global__ void __launch_bounds__(128)
+reach_two_product(const __grid_constant__ DevModel M, const int t, const int D, const int pmf_off,
+                  const unsigned char* __restrict__ mask_t, unsigned char* __restrict__ mask_n) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M.S || !mask_t[idx]) return;
+    long long r = idx;
+    const int iw = (int)(r % M.nW); r /= M.nW;
+    const int i2 = (int)(r % M.nI);
+    const int i1 = (int)(r / M.nI);
+    const double x1 = M.inv_min + (double)i1 * M.step, x2 = M.inv_min + (double)i2 * M.step;
+    const double w = (double)(M.kmin + iw);
+    const double v1 = M.v_t[t - 1], price1 = M.price_t[t - 1];
+    const int Q = M.max_order_idx + 1;
+    for (int a1i = 0; a1i < Q; a1i++)
+        for (int a2i = 0; a2i < Q; a2i++) {
+            const double oc1 = v1 * (double)a1i, oc2 = M.v2 * (double)a2i;
+            if (!(oc1 + oc2 < w + 0.1)) continue;
+            const double orderingCosts = oc1 + oc2;
+            const double s1 = x1 + (double)a1i, s2 = x2 + (double)a2i;
+            for (int j = 0; j < D; j++) {
+                const double demand1 = (double)(int)M.pmf_d[pmf_off + j], demand2 = (double)(int)M.pmf_d2[pmf_off + j];
+                const double e1 = fmax(0.0, s1 - demand1), e2 = fmax(0.0, s2 - demand2);
+                const double revenue = price1 * (s1 - e1) + M.price2 * (s2 - e2);
+                const double c = revenue - orderingCosts;  // t < T here: no salvage
+                int il1 = max(i1 + a1i - M.pmf_di[pmf_off + j], M.i_zero);
+                int il2 = max(i2 + a2i - M.pmf_di2[pmf_off + j], M.i_zero);
+                il1 = max(min(il1, M.nI - 1), 0);
+                il2 = min(max(il2, 0), M.nI - 1);
+                double nw = w + c;
+                nw = nw > M.cash_max ? M.cash_max : nw;
+                nw = nw < M.cash_min ? M.cash_min : nw;
+                long long kw = (long long)nw - M.kmin;
+                kw = kw < 0 ? 0 : (kw >= M.nW ? M.nW - 1 : kw);
+                mask_n[((long long)il1 * M.nI + il2) * M.nW + kw] = 1;
+            }
+        }
+}
+
 }  // namespace sdpb

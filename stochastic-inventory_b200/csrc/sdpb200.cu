@@ -957,7 +957,7 @@ int sdpb_state_of_index(const sdpb_handle* h, int64_t idx, double* state) {
 int sdpb_reach(sdpb_handle* h, const double* init_states, int n) {
     if (!h || !init_states || n < 1) return SDPB_ERR_ARG;
     if (h->opt.shard_count != 1) { h->err = "sdpb_reach needs an unsharded handle"; return SDPB_ERR_STATE; }
-    if (two_product(h->m) || staff_kind(h->m)) { h->err = "sdpb_reach is not implemented for two-product and staff models"; return SDPB_ERR_ARG; }
+
     CU(cudaSetDevice(h->device));
     const int T = h->m.T;
     for (int t = 0; t < T; t++) {
@@ -989,6 +989,13 @@ int sdpb_reach(sdpb_handle* h, const double* init_states, int n) {
         case SDPB_COST_CASH_OD_LIMIT: launch_reach<SDPB_COST_CASH_OD_LIMIT, false>(h, t); break;
         case SDPB_COST_CASH_OD_TESTING: launch_reach<SDPB_COST_CASH_OD_TESTING, false>(h, t); break;
         case SDPB_COST_CASH_LOAN: launch_reach<SDPB_COST_CASH_LOAN, false>(h, t); break;
+        case SDPB_COST_CASH_TWO_PRODUCT:
+            reach_two_product<<<(unsigned)((h->S + 127) / 128), 128, 0, h->stream>>>(
+                h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], h->dMask[t - 1], h->dMask[t]);
+            break;
+        case SDPB_COST_STAFF:
+            reach_staff<<<(unsigned)((h->S + 127) / 128), 128, 0, h->stream>>>(h->dm, t, h->dMask[t - 1], h->dMask[t]);
+            break;
         }
         CU(cudaGetLastError());
     }

@@ -357,6 +357,25 @@ class CashRecursionMulti:
             raise KeyError("getAction on a state that was never solved")
         return self._value(state)[1]
 
+    def getOptTable(self, variCost, init_states):
+        """CashRecursionMulti.getOptTable (CashRecursionMulti.java:187-209): rows
+        [period, x1, x2, w, R, boolAlpha, alpha, Q1, Q2, c1, c2] over the states the recursion visits
+        from `init_states` (period-1 states (x1, x2, w))."""
+        if not self._solved:
+            self._solver.solve()
+            self._solved = True
+        self._solver.reach(init_states)
+        n = self.spec.max_order_idx + 1
+        out = []
+        for t, x1, x2, w, q in self._solver.opt_table():
+            Q1, Q2 = float(int(q) // n), float(int(q) % n)
+            R = w + x1 * variCost[0] + x2 * variCost[1]
+            boolAlpha, alpha = 0.0, 10000.0
+            if w <= variCost[0] * Q1 + variCost[1] * Q2 and Q1 > 0 and Q2 > 0:
+                boolAlpha, alpha = 1.0, variCost[0] * Q1 / w
+            out.append([t, x1, x2, w, R, boolAlpha, alpha, Q1, Q2, variCost[0], variCost[1]])
+        return np.asarray(out)
+
 
 # ---- workforce ------------------------------------------------------------------------------
 class StaffState(State):
@@ -369,7 +388,8 @@ class StaffState(State):
 
 class StaffRecursion(_Engine):
     """new StaffRecursion(A, f, c, pmf, T) -> StaffRecursion(spec); src/workforce/StaffRecursion.java:39-121.
-    getOptTable / spot checks are not wired for this kind yet."""
+    getOptTable() rows are [t, staff, hires] (StaffRecursion.java:274-283); lambda spot checks are not wired
+    for this kind."""
     state_cls = StaffState
     _kinds = (A.COST_STAFF,)
 

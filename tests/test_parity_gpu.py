@@ -196,17 +196,6 @@ def test_value_and_opt_table_match_topdown(case, S, oracle):
     s = S.Solver(spec).solve()
     v, q = s.value(1, init)
     assert np.array_equal(v, iv)
-    if spec.two_product or spec.staff:
-        # reachability / opt-table extraction is not implemented for these kinds yet; every
-        # visited state still answers through sdpb_value
-        nd = spec.ndim
-        for t in range(1, spec.T + 1):
-            sel = rows[rows[:, 0] == t]
-            v, q = s.value(t, sel[:, 1:1 + nd])
-            assert np.array_equal(v, sel[:, -1]) and np.array_equal(q, sel[:, -2])
-        with pytest.raises(S.SdpbError):
-            s.reach(init)
-        return
     s.reach(init)
     tab = s.opt_table()
     nd = spec.ndim
