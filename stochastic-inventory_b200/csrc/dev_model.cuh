@@ -21,6 +21,7 @@ struct DevModel {
     long long S;          // states per period = nI * nQ^lead * nW
     long long kmin;       // integer cash index of the lowest cash grid point
     long long q_idiv;     // (long) q_div for SDPB_Q_LONGDIV
+    unsigned long long q_magic;  // ceil(2^47 / q_idiv) when q_idiv < 2^15, else 0: division by multiplication
     double inv_min, step;
     double cash_min, cash_max, q_mul, q_div;
     double K, h, pen, salvage;
@@ -57,6 +58,19 @@ __device__ __forceinline__ long long jround(double x) {
     double r = floor(x);
     double diff = x - r;
     return (long long)r + (diff >= 0.5 ? 1ll : 0ll);
+}
+
+// Java `long / long` (truncation toward zero) by the run-time constant q_idiv.  For |kk| < 2^31 and
+// q_idiv < 2^15, floor(|kk| * ceil(2^47/d) / 2^47) == floor(|kk| / d) exactly (|kk|*d < 2^47), which
+// replaces the ~40-instruction 64-bit division of the overdraft models' quantiser
+// (Math.round(w*10)/10, CashOverdraft.java:116) by two wide multiplies and a shift.
+__device__ __forceinline__ long long jdiv(long long kk, long long d, unsigned long long magic) {
+    const long long a = kk < 0 ? -kk : kk;
+    if (magic != 0 && a < 2147483648ll) {
+        const long long q = (long long)(((unsigned long long)a * magic) >> 47);
+        return kk < 0 ? -q : q;
+    }
+    return kk / d;
 }
 
 // Lexicographic (value, action) update used by every argopt reduction: strictly better value

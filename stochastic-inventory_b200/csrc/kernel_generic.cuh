@@ -232,7 +232,7 @@ __device__ __forceinline__ long long successor(const DevModel& M, const StateCtx
     } else {
         kk = jround(nw * M.q_mul);
         // Java long division; q_idiv == 1 (round(w*1)/1) is the common case and needs no divide
-        k = (M.quantiser == SDPB_Q_DIV || M.q_idiv == 1) ? kk : kk / M.q_idiv;
+        k = (M.quantiser == SDPB_Q_DIV || M.q_idiv == 1) ? kk : jdiv(kk, M.q_idiv, M.q_magic);
     }
     bankrupt = k < 0;  // quantised cash < 0 (q_div > 0)
     if (KIND == SDPB_COST_CASH_XR) {

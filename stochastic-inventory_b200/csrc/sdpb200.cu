@@ -639,6 +639,7 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     d.kmin = 0;
     d.q_mul = d.q_div = 1.0;
     d.q_idiv = 1;
+    d.q_magic = 0;
     if (has_cash(*m)) {
         if (!(m->q_mul > 0) || !(m->q_div > 0) || m->cash_max < m->cash_min)
             return fail_create(h, SDPB_ERR_ARG, "bad cash axis (q_mul, q_div > 0; cash_max >= cash_min)");
@@ -663,6 +664,7 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         d.q_mul = m->q_mul;
         d.q_div = m->q_div;
         d.q_idiv = (long long)m->q_div;
+        d.q_magic = (d.q_idiv >= 2 && d.q_idiv < 32768) ? ((1ull << 47) + (unsigned long long)d.q_idiv - 1) / (unsigned long long)d.q_idiv : 0;
     }
     d.cash_min = m->cash_min;
     d.cash_max = m->cash_max;
