@@ -455,7 +455,7 @@ inline void plan_tiled(TiledPlan& P, const sdpb_model& m, const DevModel& d, con
         tp.smem2 = std::max(head2, red2) + (size_t)D * 16 + 16;
         tp.ok2 = consec && tp.smem2 <= 100 * 1024;
     }
-    if (!any) { P.why_not = "window does not fit in shared memory"; return; }
+    if (!any) { P.why_not = "no period qualifies (G(y) pass only, or the level window does not fit in shared memory)"; return; }
     P.available = true;
 }
 
