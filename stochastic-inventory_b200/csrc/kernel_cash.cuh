@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "dev_model.cuh"
@@ -284,10 +285,9 @@ inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& d
 // Demand steps split into: all slots in stock (fast path, rotation unrolled x8) / mixed (per-slot
 // select, at most ~16 steps) / all slots stocked out (no window, no loads).
 constexpr int kDiagYT = 8;
-constexpr int kDiagThreads = 128;
 
-template <bool SURVIVAL, bool IS_MIN>
-__global__ void __launch_bounds__(kDiagThreads)
+template <bool SURVIVAL, bool IS_MIN, int kDiagThreads>
+__global__ void __launch_bounds__(kDiagThreads, 512 / kDiagThreads)
 bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs a) {
     constexpr int YT = kDiagYT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -342,18 +342,20 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
 #pragma unroll
         for (int k = 0; k < YT; k++) acc[k] = 0.0;
 
-        // gather V_{t+1} at level index il (needed only for levels > 0, i.e. il > i_zero)
-        auto gather = [&](int il) -> double {
-            if (il <= M.i_zero) return 0.0;
-            const int row = max(min(il, M.nI - 1), 0) * M.nW;  // upper clamp first, as in the reference
-            const int kc = min(max(base - price * il, 0), nW1);
+        // gather V_{t+1} at level index il.  Levels <= 0 are fetched too (address clamped into the grid) but
+        // never used: a slot reads its window only while it is in stock.
+        const int row_max = (M.nI - 1) * M.nW;
+        auto gather_at = [&](int ro, int c) -> double {  // ro = il*nW, c = base - price*il, both unclamped
+            const int row = max(min(ro, row_max), 0);    // upper clamp first, as in the reference
+            const int kc = max(min(c, nW1), 0);
             double vn = __ldg(a.Vn + (unsigned)(row + kc));
             if (SURVIVAL && M.kmin + kc < 0) vn = 0.0;  // RiskRecursion.java:87-95
             return vn;
         };
 #pragma unroll
-        for (int k = 0; k < YT; k++) Vw[k] = gather(L0 + k);
-        double pre = gather(L0 - 1);  // enters slot 0 at demand 1
+        for (int k = 0; k < YT; k++) Vw[k] = gather_at((L0 + k) * M.nW, base - price * (L0 + k));
+        double pre = gather_at((L0 - 1) * M.nW, base - price * (L0 - 1));  // enters slot 0 at demand 1
+        int ro_run = (L0 - 2) * M.nW, c_run = base - price * (L0 - 2);    // next level to prefetch; one level down per step
 
         int j = 0;
         // ---- all 8 slots in stock: shared p*c, one new gather per demand point ----
@@ -361,7 +363,9 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
         {                                                                                            \
             const double2 pp = lds_double2(pp_s + (unsigned)j * 16u);                                \
             const double vnew = pre;                                                                 \
-            pre = gather(L0 - (j + 2));                                                              \
+            pre = gather_at(ro_run, c_run);                                                          \
+            ro_run -= M.nW;                                                                          \
+            c_run += price;                                                                          \
             double m = 0.0;                                                                          \
             if (!SURVIVAL) m = pp.x * (lds_double(pr_s + (unsigned)j * 8u) - Cd);  /* p_j * c */    \
             _Pragma("unroll") for (int k = 0; k < YT; k++) {                                         \
@@ -375,7 +379,6 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
             SDPB_DIAG_FAST(0) SDPB_DIAG_FAST(1) SDPB_DIAG_FAST(2) SDPB_DIAG_FAST(3)
             SDPB_DIAG_FAST(4) SDPB_DIAG_FAST(5) SDPB_DIAG_FAST(6) SDPB_DIAG_FAST(7)
         }
-#undef SDPB_DIAG_FAST
         // ---- stock-out entry: the same for every slot ----
         const int kt = min(max(iw0 + price * (xv0 + ai) - CI, 0), nW1);
         double Vtail = __ldg(a.Vn + (unsigned)(row_tail + kt));
@@ -383,12 +386,15 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
         double inct[YT];  // price*y_k - C_a
 #pragma unroll
         for (int k = 0; k < YT; k++) inct[k] = (double)(price * (xv0 + k + ai) - CI);
-        // ---- mixed region: some slots in stock, some stocked out ----
+        // ---- remainder of the in-stock run (j < jy0), then the mixed region: some slots stocked out ----
 #define SDPB_DIAG_MIXED(JJ)                                                                      \
-        if (j < D) {                                                                                 \
+        if (j < jy0) SDPB_DIAG_FAST(JJ)                                                              \
+        else if (j < D) {                                                                            \
             const double2 pp = lds_double2(pp_s + (unsigned)j * 16u);                                \
             const double vnew = pre;                                                                 \
-            pre = gather(L0 - (j + 2));                                                              \
+            pre = gather_at(ro_run, c_run);                                                          \
+            ro_run -= M.nW;                                                                          \
+            c_run += price;                                                                          \
             const double cin = lds_double(pr_s + (unsigned)j * 8u) - Cd;                             \
             _Pragma("unroll") for (int k = 0; k < YT; k++) {                                         \
                 const bool in_stock = j < min(max(xv0 + k + ai - a.d0, 0), D);                       \
@@ -403,6 +409,7 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
             SDPB_DIAG_MIXED(4) SDPB_DIAG_MIXED(5) SDPB_DIAG_MIXED(6) SDPB_DIAG_MIXED(7)
         }
 #undef SDPB_DIAG_MIXED
+#undef SDPB_DIAG_FAST
         // ---- every slot stocked out: no window, no loads ----
         for (; j < D; j++) {
             const double2 pp = lds_double2(pp_s + (unsigned)j * 16u);
@@ -435,19 +442,28 @@ inline int launch_cash_diag(const CashPlan& P, const sdpb_model& m, const DevMod
     if (hi <= lo) return SDPB_OK;
     const CashPeriod& cp = P.period[t - 1];
     if (cp.price <= 0 || cp.price * (kDiagYT - 1) > dm.nW) return SDPB_ERR_STATE;  // diagonal must stay on the cash axis
+    if ((long long)(dm.nI + D + std::abs(cp.d0) + 2 * kDiagYT + m.max_order_idx) * dm.nW >= 0x7fffffffLL)
+        return SDPB_ERR_STATE;  // running 32-bit row offsets
     CashArgs a;
     a.t = t; a.D = D; a.pmf_off = pmf_off; a.Vn = Vn; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
     a.ix0 = (int)(lo / dm.nW);
     const int ix1 = (int)((hi - 1) / dm.nW);
     a.price = cp.price; a.v = cp.v; a.K = P.K; a.ovh = cp.ovh; a.d0 = cp.d0; a.inv_min_i = (int)m.inv_min;
     const int span_w = dm.nW + cp.price * (kDiagYT - 1);  // slot 0's cash index runs past the axis so slot 7 covers it
-    const dim3 grid((unsigned)((span_w + kDiagThreads - 1) / kDiagThreads),
-                    (unsigned)((ix1 - a.ix0 + 1 + kDiagYT - 1) / kDiagYT));
+    int nt = 64;
+    if (const char* e = std::getenv("SDPB_DIAG_THREADS")) nt = std::atoi(e) == 128 ? 128 : 64;  // tuning knob
+    const dim3 grid((unsigned)((span_w + nt - 1) / nt), (unsigned)((ix1 - a.ix0 + 1 + kDiagYT - 1) / kDiagYT));
     const size_t smem = (size_t)D * 24 + 16;
     const bool surv = m.recursion == SDPB_REC_SURVIVAL;
-    if (surv) bi_cash_diag<true, false><<<grid, kDiagThreads, smem, stream>>>(dm, a);
-    else if (dm.is_min) bi_cash_diag<false, true><<<grid, kDiagThreads, smem, stream>>>(dm, a);
-    else bi_cash_diag<false, false><<<grid, kDiagThreads, smem, stream>>>(dm, a);
+    if (nt == 128) {
+        if (surv) bi_cash_diag<true, false, 128><<<grid, 128, smem, stream>>>(dm, a);
+        else if (dm.is_min) bi_cash_diag<false, true, 128><<<grid, 128, smem, stream>>>(dm, a);
+        else bi_cash_diag<false, false, 128><<<grid, 128, smem, stream>>>(dm, a);
+    } else {
+        if (surv) bi_cash_diag<true, false, 64><<<grid, 64, smem, stream>>>(dm, a);
+        else if (dm.is_min) bi_cash_diag<false, true, 64><<<grid, 64, smem, stream>>>(dm, a);
+        else bi_cash_diag<false, false, 64><<<grid, 64, smem, stream>>>(dm, a);
+    }
     if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
     if (fp64_ops) *fp64_ops += evals * (surv ? 2.0 : 3.0 + 2.0 / kDiagYT);
     return SDPB_OK;
