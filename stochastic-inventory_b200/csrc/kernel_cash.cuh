@@ -282,11 +282,13 @@ inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& d
 // value (instead of 8), forms p_j*c once for all slots still in stock, and spends (add, mul, add) per
 // evaluation: 3 + 2/8 fp64 instructions and 1/8 gather per evaluation (bi_cash_int: 3.5 and 1).
 // Lanes hold consecutive cash levels, so every gather is a coalesced row segment.
-// Demand steps split into: all slots in stock (fast path, rotation unrolled x8) / mixed (per-slot
-// select, at most ~16 steps) / all slots stocked out (no window, no loads).
+// Demand steps split into: all slots in stock (fast path, window rotation unrolled x(YT+PF)) / mixed
+// (per-slot select, the 7 steps between slot 0 and slot 7 stocking out) / all slots stocked out (no
+// window, no loads).  64-thread CTAs, 8 per SM: the grid is only ~2000 CTAs on a 1e6-state model, so
+// small CTAs are what keeps the last wave short (ncu: profiles/r01_ncu_cash_diag*_raw.csv).
 constexpr int kDiagYT = 8;
 
-template <bool SURVIVAL, bool IS_MIN, int kDiagThreads>
+template <bool SURVIVAL, bool IS_MIN, int kDiagThreads, int PF = 2>
 __global__ void __launch_bounds__(kDiagThreads, 512 / kDiagThreads)
 bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs a) {
     constexpr int YT = kDiagYT;
@@ -338,7 +340,11 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
         const int L0 = ix0 + ai - a.d0;                        // slot k, demand j: level index L0 + k - j
         const int jy0 = min(max(xv0 + ai - a.d0, 0), D);       // slot 0 is in stock for j < jy0
         const int jy7 = min(max(xv0 + (YT - 1) + ai - a.d0, 0), D);
-        double acc[YT], Vw[YT];
+        // Window of W = YT + PF registers: at demand j (phase JJ = j mod W) slot k reads Vw[(k - JJ) mod W]; the PF
+        // free entries hold the levels slot 0 reaches at j+1 .. j+PF (loaded earlier), so every load lands in its
+        // final register PF + 1 steps ahead of its first use and nothing is ever moved.
+        constexpr int W = YT + PF;
+        double acc[YT], Vw[W];
 #pragma unroll
         for (int k = 0; k < YT; k++) acc[k] = 0.0;
 
@@ -353,31 +359,32 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
             return vn;
         };
 #pragma unroll
-        for (int k = 0; k < YT; k++) Vw[k] = gather_at((L0 + k) * M.nW, base - price * (L0 + k));
-        double pre = gather_at((L0 - 1) * M.nW, base - price * (L0 - 1));  // enters slot 0 at demand 1
-        int ro_run = (L0 - 2) * M.nW, c_run = base - price * (L0 - 2);    // next level to prefetch; one level down per step
+        for (int k = 0; k < W; k++) {
+            const int il = k < YT ? L0 + k : L0 + k - W;  // entries YT..W-1: levels L0-PF .. L0-1
+            Vw[k] = gather_at(il * M.nW, base - price * il);
+        }
+        // the entry slot 7 releases at demand j is reloaded with the level slot 0 reaches at demand j + 1 + PF
+        int ro_run = (L0 - PF - 1) * M.nW, c_run = base - price * (L0 - PF - 1);
 
         int j = 0;
         // ---- all 8 slots in stock: shared p*c, one new gather per demand point ----
 #define SDPB_DIAG_FAST(JJ)                                                                       \
         {                                                                                            \
             const double2 pp = lds_double2(pp_s + (unsigned)j * 16u);                                \
-            const double vnew = pre;                                                                 \
-            pre = gather_at(ro_run, c_run);                                                          \
-            ro_run -= M.nW;                                                                          \
-            c_run += price;                                                                          \
             double m = 0.0;                                                                          \
             if (!SURVIVAL) m = pp.x * (lds_double(pr_s + (unsigned)j * 8u) - Cd);  /* p_j * c */    \
             _Pragma("unroll") for (int k = 0; k < YT; k++) {                                         \
                 if (!SURVIVAL) acc[k] += m;                        /* CashRecursion.java:117 */     \
-                acc[k] += pp.y * Vw[(k - (JJ)) & 7];               /* CashRecursion.java:120 */     \
+                acc[k] += pp.y * Vw[(k - (JJ) + W) % W];           /* CashRecursion.java:120 */     \
             }                                                                                        \
-            Vw[(7 - (JJ)) & 7] = vnew;                                                               \
+            Vw[(YT - 1 - (JJ) + W) % W] = gather_at(ro_run, c_run);   /* slot 7's entry is free now */ \
+            ro_run -= M.nW;                                                                          \
+            c_run += price;                                                                          \
             j += 1;                                                                                  \
         }
-        while (j + 8 <= jy0) {
-            SDPB_DIAG_FAST(0) SDPB_DIAG_FAST(1) SDPB_DIAG_FAST(2) SDPB_DIAG_FAST(3)
-            SDPB_DIAG_FAST(4) SDPB_DIAG_FAST(5) SDPB_DIAG_FAST(6) SDPB_DIAG_FAST(7)
+        while (j + W <= jy0) {
+#pragma unroll
+            for (int JJ = 0; JJ < W; JJ++) SDPB_DIAG_FAST(JJ)
         }
         // ---- stock-out entry: the same for every slot ----
         const int kt = min(max(iw0 + price * (xv0 + ai) - CI, 0), nW1);
@@ -387,28 +394,26 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
 #pragma unroll
         for (int k = 0; k < YT; k++) inct[k] = (double)(price * (xv0 + k + ai) - CI);
         // ---- remainder of the in-stock run (j < jy0), then the mixed region: some slots stocked out ----
-#define SDPB_DIAG_MIXED(JJ)                                                                      \
-        if (j < jy0) SDPB_DIAG_FAST(JJ)                                                              \
-        else if (j < D) {                                                                            \
-            const double2 pp = lds_double2(pp_s + (unsigned)j * 16u);                                \
-            const double vnew = pre;                                                                 \
-            pre = gather_at(ro_run, c_run);                                                          \
-            ro_run -= M.nW;                                                                          \
-            c_run += price;                                                                          \
-            const double cin = lds_double(pr_s + (unsigned)j * 8u) - Cd;                             \
-            _Pragma("unroll") for (int k = 0; k < YT; k++) {                                         \
-                const bool in_stock = j < min(max(xv0 + k + ai - a.d0, 0), D);                       \
-                if (!SURVIVAL) acc[k] += pp.x * (in_stock ? cin : inct[k]);                          \
-                acc[k] += pp.y * (in_stock ? Vw[(k - (JJ)) & 7] : Vtail);                            \
-            }                                                                                        \
-            Vw[(7 - (JJ)) & 7] = vnew;                                                               \
-            j += 1;                                                                                  \
-        }
         while (j < jy7) {
-            SDPB_DIAG_MIXED(0) SDPB_DIAG_MIXED(1) SDPB_DIAG_MIXED(2) SDPB_DIAG_MIXED(3)
-            SDPB_DIAG_MIXED(4) SDPB_DIAG_MIXED(5) SDPB_DIAG_MIXED(6) SDPB_DIAG_MIXED(7)
+#pragma unroll
+            for (int JJ = 0; JJ < W; JJ++) {
+                if (j < jy0) SDPB_DIAG_FAST(JJ)
+                else if (j < D) {
+                    const double2 pp = lds_double2(pp_s + (unsigned)j * 16u);
+                    const double cin = lds_double(pr_s + (unsigned)j * 8u) - Cd;
+#pragma unroll
+                    for (int k = 0; k < YT; k++) {
+                        const bool in_stock = j < min(max(xv0 + k + ai - a.d0, 0), D);
+                        if (!SURVIVAL) acc[k] += pp.x * (in_stock ? cin : inct[k]);
+                        acc[k] += pp.y * (in_stock ? Vw[(k - JJ + W) % W] : Vtail);
+                    }
+                    Vw[(YT - 1 - JJ + W) % W] = gather_at(ro_run, c_run);
+                    ro_run -= M.nW;
+                    c_run += price;
+                    j += 1;
+                }
+            }
         }
-#undef SDPB_DIAG_MIXED
 #undef SDPB_DIAG_FAST
         // ---- every slot stocked out: no window, no loads ----
         for (; j < D; j++) {
