@@ -205,7 +205,11 @@ typedef enum sdpb_kernel_choice {
                                  (1, -price) diagonal; the last period runs on SDPB_KERNEL_CASH_INT */
     SDPB_KERNEL_LEAD_SLAB = 6,/* shared-memory slab kernel for backorder lead-time models (as a request: skip
                                  the column kernel) */
-    SDPB_KERNEL_LEAD_COL = 7, /* reported only: thread-per-successor-column kernel for lead-time models */
+    SDPB_KERNEL_LEAD_COL = 7, /* thread-per-successor-column kernel for backorder lead-time models (as a request:
+                                 skip the all-actions-in-thread kernel) */
+    SDPB_KERNEL_LEAD_Q2 = 9,  /* lead time 2: a thread owns 8 preQ1 levels of one (x, preQ2), walks every action
+                                 itself and reads V_{t+1} through a transposed copy; AUTO picks it when the
+                                 model is not folded */
     SDPB_KERNEL_TILED2 = 5    /* 2-D register-tile variant of the tiled kernel: chosen automatically for
                                  large grids; as a request it forces the variant wherever it applies */
 } sdpb_kernel_choice;

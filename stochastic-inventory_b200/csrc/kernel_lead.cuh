@@ -513,4 +513,210 @@ inline int launch_col(const ColPlan& P, const DevModel& dm, int t, int D, int pm
     return SDPB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// bi_lead_q2 — lead time 2, every action inside the thread (no cross-thread argopt, no barrier).
+//
+// A thread owns YT = 8 consecutive preQ1 levels of one (x, preQ2) and walks ALL actions itself, keeping
+// the running optimum of its 8 states in registers.  For a fixed action the successor of slot k at
+// demand j is (x + l0 + k - d_j, preQ2, a): the same sliding window along the level axis as in
+// bi_lead_col.  Lanes hold consecutive preQ2, so the successor table is read TRANSPOSED,
+//     VnT[(il * nQ + a) * nQ + preQ2]  =  V_{t+1}[(il * nQ + preQ2) * nQ + a]
+// (transpose_q2a, one 16 B/state pass per period), which makes every gather a coalesced row segment
+// and every V_t / Q_t store coalesced as well.  Threads are numbered flat over (x, chunk, preQ2) so no
+// lane idles on the 101-wide axes; a CTA's threads span at most a few inventory rows and share one
+// shared-memory table of (level cost, successor row offset) over the levels they can reach.
+// The register window has W = YT + PF entries for both the costs and the successor values, so each
+// load lands in its final register PF + 1 demand steps before its first use (as in bi_cash_diag).
+// fp64 per evaluation: (1 + 4*8) / 8 = 4.125 (2.125 in the last period), as bi_lead_col, but the
+// 8 x NQB shared-memory argopt, its barrier and the one-CTA-per-SM occupancy are gone.
+struct Q2Args {
+    int t, D, pmf_off;
+    const double* VnT;        // transposed V_{t+1} (nullptr in the last period)
+    double* Vt;
+    int* Qt;
+    long long lo, hi;
+    long long f_begin, f_end; // flat thread range: f = (x * n_chunks + chunk) * nQ + preQ2
+    int n_chunks, tpx;        // chunks of 8 levels along preQ1; threads per inventory row
+    int di_max, NRW;
+};
+
+constexpr int kQ2YT = 8, kQ2PF = 2, kQ2PAD = kQ2PF + 1;
+
+__global__ void transpose_q2a(const double* __restrict__ V, double* __restrict__ VT, int nQ) {
+    __shared__ double tile[32][33];
+    const long long base = (long long)blockIdx.x * nQ * nQ;
+    const int c0 = blockIdx.y * 32, r0 = blockIdx.z * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int row = r0 + r, c = c0 + threadIdx.x;
+        if (row < nQ && c < nQ) tile[r][threadIdx.x] = V[base + (long long)row * nQ + c];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int row = c0 + r, c = r0 + threadIdx.x;  // transposed coordinates
+        if (row < nQ && c < nQ) VT[base + (long long)row * nQ + c] = tile[threadIdx.x][r];
+    }
+}
+
+template <bool IS_MIN, bool LAST, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT)
+bi_lead_q2(const __grid_constant__ DevModel M, const __grid_constant__ Q2Args a) {
+    constexpr int YT = kQ2YT, PF = kQ2PF, W = YT + PF, PAD = kQ2PAD;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* WR = reinterpret_cast<double2*>(smem_raw);  // (level cost, successor row offset in the low word)
+    double2* PP = WR + a.NRW;                            // (p, p*gamma)
+    const int D = a.D, nQ = M.nQ, tid = threadIdx.x;
+    const long long F0 = a.f_begin + (long long)blockIdx.x * NT;
+    const long long x_first = F0 / a.tpx;
+    const bool lost = (M.flags & SDPB_F_LOST_SALES) != 0;
+
+    for (int j = tid; j < D; j += NT) PP[j] = make_double2(M.pmf_p[a.pmf_off + j], M.pmf_pg[a.pmf_off + j]);
+    // window index wi <-> unclamped level index il = x_first - di_max - PAD + wi
+    for (int wi = tid; wi < a.NRW; wi += NT) {
+        const long long il = x_first - a.di_max - PAD + wi;
+        const double lvl = M.inv_min + (double)il * M.step;
+        long long is = il;
+        if (lost) is = is > M.i_zero ? is : M.i_zero;
+        is = is < M.nI - 1 ? is : M.nI - 1;  // upper clamp first; also the memory-safety clip
+        is = is > 0 ? is : 0;
+        WR[wi] = make_double2(M.h * fmax(lvl, 0.0) + M.pen * fmax(-lvl, 0.0),
+                              __hiloint2double(0, (int)(is * nQ * nQ)));
+    }
+    __syncthreads();
+
+    const long long F = F0 + tid;
+    if (F >= a.f_end) return;
+    const long long x = F / a.tpx;
+    const int f = (int)(F - x * a.tpx);
+    const int chunk = f / nQ, q2 = f - chunk * nQ, l0 = chunk * YT;
+    const long long idx0 = (x * nQ + l0) * nQ + q2;  // slot k: idx0 + k * nQ
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < YT; k++) any |= (l0 + k < nQ) && idx0 + (long long)k * nQ >= a.lo && idx0 + (long long)k * nQ < a.hi;
+    if (!any) return;
+
+    // slot k at demand j reads window row  (x - x_first) + l0 + k + (D-1-j) + PAD
+    const unsigned wr0 = (unsigned)__cvta_generic_to_shared(WR) + (unsigned)((int)(x - x_first) + l0 + (D - 1) + PAD) * 16u;
+    const unsigned pp_s = (unsigned)__cvta_generic_to_shared(PP);
+    const double* __restrict__ cb = LAST ? nullptr : a.VnT + q2;
+    const double vt = M.v_t[a.t - 1];
+
+    double best[YT];
+    int arg[YT];
+#pragma unroll
+    for (int k = 0; k < YT; k++) { best[k] = IS_MIN ? DBL_MAX : -DBL_MAX; arg[k] = kNoAction; }
+
+    for (int ai = 0; ai <= M.max_order_idx; ai++) {
+        const double av = (double)ai * M.step;
+        const double fv = (av > 0.0 ? M.K : 0.0) + vt * av;  // Leadtime.java:73-74,79
+        double acc[YT], cst[W], Vw[W];
+#pragma unroll
+        for (int k = 0; k < YT; k++) acc[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < W; k++) {  // entries YT..W-1: the levels slot 0 reaches at demands PF..1
+            const double2 e = lds_double2(wr0 + (unsigned)((k < YT ? k : k - W) * 16));
+            cst[k] = fv + e.x;
+            Vw[k] = LAST ? 0.0 : __ldg(cb + __double2loint(e.y));
+        }
+        unsigned wr_run = wr0 - (unsigned)((PF + 1) * 16);
+#define SDPB_Q2_STEP(JJ)                                                                              \
+        {                                                                                                 \
+            const double2 pp = lds_double2(pp_s + (unsigned)j * 16u);                                     \
+            _Pragma("unroll") for (int k = 0; k < YT; k++) {                                              \
+                acc[k] += pp.x * cst[(k - (JJ) + W) % W];          /* LeadtimeRecursion.java:59 */       \
+                if (!LAST) acc[k] += pp.y * Vw[(k - (JJ) + W) % W]; /* LeadtimeRecursion.java:62 */      \
+            }                                                                                             \
+            const double2 e = lds_double2(wr_run);   /* refill the entry slot 7 just released */          \
+            cst[(YT - 1 - (JJ) + W) % W] = fv + e.x;                                                      \
+            if (!LAST) Vw[(YT - 1 - (JJ) + W) % W] = __ldg(cb + __double2loint(e.y));                     \
+            wr_run -= 16u;                                                                                \
+            j += 1;                                                                                       \
+        }
+        int j = 0;
+        while (j + W <= D) {
+#pragma unroll
+            for (int JJ = 0; JJ < W; JJ++) SDPB_Q2_STEP(JJ)
+        }
+#pragma unroll
+        for (int JJ = 0; JJ < W - 1; JJ++)
+            if (j < D) SDPB_Q2_STEP(JJ)
+#undef SDPB_Q2_STEP
+#pragma unroll
+        for (int k = 0; k < YT; k++)
+            if (IS_MIN ? (acc[k] < best[k]) : (acc[k] > best[k])) { best[k] = acc[k]; arg[k] = ai; }
+        if (!LAST) cb += nQ;
+    }
+#pragma unroll
+    for (int k = 0; k < YT; k++) {
+        const long long idx = idx0 + (long long)k * nQ;
+        if (l0 + k < nQ && idx >= a.lo && idx < a.hi) {
+            a.Vt[idx] = best[k];
+            a.Qt[idx] = arg[k] == kNoAction ? -1 : arg[k];
+        }
+    }
+}
+
+struct Q2Plan {
+    bool ok = false;
+    int NT = 128, n_chunks = 0, tpx = 0, di_max = 0, NRW = 0;
+    size_t smem = 0;
+};
+
+inline Q2Plan plan_q2(const sdpb_model& m, const DevModel& d, int D, const int* di) {
+    Q2Plan P;
+    if (m.cost_kind != SDPB_COST_BACKORDER || m.lead_time != 2) return P;
+    for (int j = 0; j < D; j++)
+        if (di[j] != di[0] + j) return P;  // the register window needs consecutive demands
+    if ((long long)d.nI * d.nQ * d.nQ >= 0x7fffffffLL) return P;  // 32-bit successor row offsets
+    if (const char* e = std::getenv("SDPB_Q2_THREADS")) {  // tuning knob
+        const int v = std::atoi(e);
+        P.NT = v == 64 ? 64 : v == 256 ? 256 : v == 512 ? 512 : 128;
+    }
+    P.n_chunks = (d.nQ + kQ2YT - 1) / kQ2YT;
+    P.tpx = P.n_chunks * d.nQ;
+    P.di_max = di[D - 1];
+    const int dx_max = (P.NT + P.tpx - 1) / P.tpx + 1;  // inventory rows a CTA's threads can span
+    P.NRW = P.n_chunks * kQ2YT + D + kQ2PAD + dx_max;
+    P.smem = (size_t)(P.NRW + D) * 16;
+    P.ok = P.smem <= 96 * 1024;
+    return P;
+}
+
+// VnT: scratch of nI*nQ*nQ doubles; filled here from Vn (stream order) unless this is the last period.
+inline int launch_q2(const Q2Plan& P, const DevModel& dm, int t, int D, int pmf_off, const double* Vn, double* VnT,
+                     double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream) {
+    if (hi <= lo) return SDPB_OK;
+    const bool last = (t == dm.T), mn = dm.is_min != 0;
+    if (!last) {
+        const unsigned tiles = (unsigned)((dm.nQ + 31) / 32);
+        transpose_q2a<<<dim3((unsigned)dm.nI, tiles, tiles), dim3(32, 8), 0, stream>>>(Vn, VnT, dm.nQ);
+    }
+    Q2Args a;
+    a.t = t; a.D = D; a.pmf_off = pmf_off; a.VnT = last ? nullptr : VnT; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
+    a.n_chunks = P.n_chunks; a.tpx = P.tpx; a.di_max = P.di_max; a.NRW = P.NRW;
+    const long long per_x = (long long)dm.nQ * dm.nQ;
+    a.f_begin = (lo / per_x) * P.tpx;
+    a.f_end = ((hi - 1) / per_x + 1) * P.tpx;
+    const long long blocks = (a.f_end - a.f_begin + P.NT - 1) / P.NT;
+    cudaError_t e = cudaSuccess;
+#define SDPB_Q2_LAUNCH(MN, LS, NTH)                                                                    \
+    {                                                                                                  \
+        auto k = bi_lead_q2<MN, LS, NTH>;                                                              \
+        if (P.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem); \
+        if (e == cudaSuccess) k<<<(unsigned)blocks, NTH, P.smem, stream>>>(dm, a);                     \
+    }
+#define SDPB_Q2_NT(MN, LS)                                                                             \
+    switch (P.NT) {                                                                                    \
+    case 64: SDPB_Q2_LAUNCH(MN, LS, 64) break;                                                         \
+    case 256: SDPB_Q2_LAUNCH(MN, LS, 256) break;                                                       \
+    case 512: SDPB_Q2_LAUNCH(MN, LS, 512) break;                                                       \
+    default: SDPB_Q2_LAUNCH(MN, LS, 128) break;                                                        \
+    }
+    if (mn) { if (last) SDPB_Q2_NT(true, true) else SDPB_Q2_NT(true, false) }
+    else    { if (last) SDPB_Q2_NT(false, true) else SDPB_Q2_NT(false, false) }
+#undef SDPB_Q2_NT
+#undef SDPB_Q2_LAUNCH
+    if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+    return SDPB_OK;
+}
+
 }  // namespace sdpb

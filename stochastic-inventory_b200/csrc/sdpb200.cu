@@ -79,6 +79,7 @@ struct sdpb_handle {
     long long vS = 0;          // virtual states per period
     double* dHv = nullptr;     // [vS] virtual value table of the period being solved
     int* dHa = nullptr;        // [vS] virtual policy table
+    double* dVT = nullptr;     // [S] V_{t+1} with the two pipeline axes transposed (bi_lead_q2)
     std::string err;
 };
 
@@ -380,6 +381,16 @@ bool staged_ok(const sdpb_handle* h, int t) {
 // Solve [lo, hi) of the real grid (or of the virtual grid when DEDUP) with the best kernel allowed.
 template <bool DEDUP>
 int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt, long long lo, long long hi) {
+    if (!DEDUP && h->dVT && (h->opt.kernel == SDPB_KERNEL_AUTO || h->opt.kernel == SDPB_KERNEL_LEAD_Q2)) {
+        const Q2Plan qp = plan_q2(h->m, h->dm, h->pmf_len[t - 1], h->pmf_di.data() + h->pmf_off[t - 1]);
+        if (qp.ok) {
+            h->stats.kernel_used = SDPB_KERNEL_LEAD_Q2;
+            const double ev = (double)(hi - lo) * (h->m.max_order_idx + 1) * h->pmf_len[t - 1];
+            h->stats.fp64_ops += ev * (t == h->m.T ? (1.0 + 2.0 * kQ2YT) / kQ2YT : (1.0 + 4.0 * kQ2YT) / kQ2YT);
+            if (t < h->m.T) h->stats.launches++;  // the transposition pass
+            return launch_q2(qp, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, h->dVT, Vt, Qt, lo, hi, h->stream);
+        }
+    }
     if (h->opt.kernel != SDPB_KERNEL_GENERIC && h->opt.kernel != SDPB_KERNEL_STAGED && h->m.lead_time >= 1 &&
         h->m.cost_kind == SDPB_COST_BACKORDER) {
         const ColPlan cp = plan_col(h->m, h->dm, h->pmf_len[t - 1], h->pmf_di.data() + h->pmf_off[t - 1], DEDUP);
@@ -769,6 +780,15 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         if (dev_alloc(h, &p, (size_t)h->vS * sizeof(int)) != cudaSuccess)
             return fail_create(h, SDPB_ERR_NOMEM, "allocation of the folded policy table failed");
         h->dHa = (int*)p;
+    }
+
+    // ---- transposed successor table for the lead-time-2 kernel ----
+    if (!h->dedup && m->cost_kind == SDPB_COST_BACKORDER && m->lead_time == 2 &&
+        (h->opt.kernel == SDPB_KERNEL_AUTO || h->opt.kernel == SDPB_KERNEL_LEAD_Q2)) {
+        void* p = nullptr;
+        if (dev_alloc(h, &p, (size_t)h->S * sizeof(double)) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "allocation of the transposed value table failed");
+        h->dVT = (double*)p;
     }
 
     // ---- kernel plan ----

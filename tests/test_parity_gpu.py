@@ -161,7 +161,9 @@ def test_lead_slab_wide_cases(S, oracle):
                                 inv_min=inv_min, inv_max=inv_max, lead_time=lead, clamp=clamp)
         Vo, Qo, _, _ = oracle.dense(spec)
         for dedup in (False, True):
-            for k, used in ((S.KERNEL_AUTO, S.KERNEL_LEAD_COL), (S.KERNEL_LEAD_SLAB, S.KERNEL_LEAD_SLAB)):
+            auto = S.KERNEL_LEAD_Q2 if lead == 2 and not dedup else S.KERNEL_LEAD_COL
+            for k, used in ((S.KERNEL_AUTO, auto), (S.KERNEL_LEAD_COL, S.KERNEL_LEAD_COL),
+                            (S.KERNEL_LEAD_SLAB, S.KERNEL_LEAD_SLAB)):
                 s, V, Q = _solve_all(S, spec, dedup=dedup, kernel=k)
                 assert s.stats()["kernel_used"] == used
                 assert np.array_equal(V, Vo) and np.array_equal(Q, Qo), (lead, max_order, clamp, dedup, k)
@@ -169,7 +171,8 @@ def test_lead_slab_wide_cases(S, oracle):
 
 def test_staged_kernel_is_used_for_leadtime(S):
     spec, _ = cases.case_B2_small()
-    assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_LEAD_COL
+    assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_LEAD_Q2
+    assert S.Solver(spec, kernel=S.KERNEL_LEAD_COL).solve().stats()["kernel_used"] == S.KERNEL_LEAD_COL
     assert S.Solver(spec, kernel=S.KERNEL_LEAD_SLAB).solve().stats()["kernel_used"] == S.KERNEL_LEAD_SLAB
     assert S.Solver(spec, kernel=S.KERNEL_STAGED).solve().stats()["kernel_used"] == S.KERNEL_STAGED
     assert S.Solver(spec, kernel=S.KERNEL_GENERIC).solve().stats()["kernel_used"] == S.KERNEL_GENERIC
@@ -523,8 +526,9 @@ def test_config_c4_sampled(S, oracle):
     V3 = V.reshape(1001, 101, 101)
     assert np.array_equal(V3[100, 7, :], V3[107, 0, :]) and np.array_equal(V3[500, 50, :], V3[520, 30, :])
     # the folded solve and the generic kernel give the same tables as the staged brute-force kernel
-    assert s.stats()["kernel_used"] == S.KERNEL_LEAD_COL
-    for kw in ({"dedup": True}, {"kernel": S.KERNEL_GENERIC}, {"kernel": S.KERNEL_STAGED}, {"kernel": S.KERNEL_LEAD_SLAB}):
+    assert s.stats()["kernel_used"] == S.KERNEL_LEAD_Q2
+    for kw in ({"dedup": True}, {"kernel": S.KERNEL_GENERIC}, {"kernel": S.KERNEL_STAGED}, {"kernel": S.KERNEL_LEAD_SLAB},
+               {"kernel": S.KERNEL_LEAD_COL}):
         d = S.Solver(spec, **kw).solve()
         Vd, Qd = d.period_tables(1)
         assert np.array_equal(Vd, V) and np.array_equal(Qd, Q)
