@@ -528,7 +528,8 @@ inline int launch_col(const ColPlan& P, const DevModel& dm, int t, int D, int pm
 // The register window has W = YT + PF entries for both the costs and the successor values, so each
 // load lands in its final register PF + 1 demand steps before its first use (as in bi_cash_diag).
 // fp64 per evaluation: (1 + 4*8) / 8 = 4.125 (2.125 in the last period), as bi_lead_col, but the
-// 8 x NQB shared-memory argopt, its barrier and the one-CTA-per-SM occupancy are gone.
+// 8 x NQB shared-memory argopt, its barrier and the one-CTA-per-SM occupancy are gone.  (A warp-per-chunk
+// numbering that lets a CTA's warps share successor rows in L1 was measured slower: 149-175 ms vs 140 on C4.)
 struct Q2Args {
     int t, D, pmf_off;
     const double* VnT;        // transposed V_{t+1} (nullptr in the last period)
