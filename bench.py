@@ -222,6 +222,64 @@ def per_step_counts(sh, sync):
             b["kernel_used"])
 
 
+def next_rows(S, device):
+    """SURVEY.md section 8 'next' rows, one timed invocation each (wall clock around the blocking C-ABI
+    calls; second call timed so one-off allocations are outside)."""
+    import numpy as np
+    res = {}
+
+    def timed(fn, reps=2):
+        for _ in range(reps - 1):
+            fn()
+        t0 = time.perf_counter()
+        r = fn()
+        return r, time.perf_counter() - t0
+
+    # f-1: reachability mask + getOptTable() rows; f-2: policy roll-out -- on the C1 instance
+    sp = S.configs.c1()
+    with S.Solver(sp, device=device) as s:
+        s.solve()
+        _, dt_r = timed(lambda: s.reach([[0.0]]))
+        tab, dt_t = timed(lambda: s.opt_table())
+        res["f1_opt_table_c1"] = {"reach_ms": dt_r * 1e3, "opt_table_ms": dt_t * 1e3, "rows": int(len(tab)),
+                                  "what": "sdpb_reach from x0 = 0 + sdpb_opt_table (Recursion.getOptTable())"}
+        rng = np.random.default_rng(7)
+        n = 200_000
+        samples = np.stack([rng.choice(r[:, 0], size=n, p=r[:, 1] / r[:, 1].sum()) for r in sp.pmf], axis=1)
+        vals, dt_s = timed(lambda: s.simulate([0.0], samples))
+        v1, _ = s.value(1, [[0.0]])
+        res["f2_simulate_c1"] = {"paths": n, "ms": dt_s * 1e3, "paths_per_s": n / dt_s, "mean": float(vals.mean()),
+                                 "V1_init": float(v1[0]),
+                                 "what": "sdpb_simulate, host samples in / per-path sums out (Simulation.java:53-74)"}
+    # f-3: two products sharing cash (MultiItemCash lambdas), scaled grid
+    d1, d2 = S.PoissonDist(5), S.PoissonDist(6)
+    rows = S.GetPmfMulti([[d1] * 3, [d2] * 3], 0.999, 1).tables()
+    sp = S.two_product_cash_model(rows, price=(4.0, 5.0), vari_cost=(2.0, 3.0), salvage=(1.0, 1.0), q_bound=20,
+                                  inv_max=40.0, cash_min=0.0, cash_max=400.0)
+    with S.Solver(sp, device=device) as s:
+        s.solve()
+        _, dt = timed(lambda: s.solve(), reps=1)
+        st = s.stats()
+        res["f3_two_product"] = {"states": int(s.n_states), "T": sp.T, "demand_pairs": int(len(rows[0])),
+                                 "solve_ms": dt * 1e3, "evals": st["evals"], "evals_per_s": st["evals"] / dt,
+                                 "kernel": "bi_two_product",
+                                 "what": "CashRecursionMulti + MultiItemCash.java:69-121 lambdas, 41 x 41 x 401 grid, "
+                                         "Qbound 20 (the reference's 201 x 201 x 10001 dense grid is 4e8 states)"}
+    # f-4: workforce planning at the reference's own instance size (WorkforcePlanning.java:33-47)
+    sp = S.workforce_model([0.5, 0.5, 0.5])
+    with S.Solver(sp, device=device) as s:
+        s.solve()
+        _, dt = timed(lambda: s.solve(), reps=1)
+        st = s.stats()
+        v1, q1 = s.value(1, [[0.0]])
+        res["f4_workforce"] = {"states": int(s.n_states), "T": sp.T, "solve_ms": dt * 1e3, "evals": st["evals"],
+                               "evals_per_s": st["evals"] / dt, "kernel": "bi_staff", "V1_init": float(v1[0]),
+                               "Q1_init": float(q1[0]),
+                               "what": "StaffRecursion, WorkforcePlanning.java instance: 601 staff levels x 501 hires x "
+                                       "Binomial(y, 0.5) turnover, T = 3"}
+    return res
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -289,11 +347,17 @@ def run_gpu(args):
         # ---- e2e: through the C-ABI with host buffers; H2D of the descriptor tables and D2H of the
         # period-1 value/policy tables inside the timed region, every step ----
         e2e_steps = max(1, min(args.steps, 3))
-        barrier()
-        t0 = time.perf_counter()
+        host_v = host_q = None
+        if world == 1:  # the caller's result buffers: page-locked host memory, allocated once
+            host_v = torch.empty(spec.n_states(), dtype=torch.float64).pin_memory().numpy()
+            host_q = torch.empty(spec.n_states(), dtype=torch.float64).pin_memory().numpy()
         d2h = h2d = 0
         phases = {"create_s": 0.0, "solve_s": 0.0, "fetch_s": 0.0, "destroy_s": 0.0}
-        for _ in range(e2e_steps):
+        for e2e_it in range(e2e_steps + 1):  # iteration 0 is an untimed warm-up of the whole cycle
+            if e2e_it <= 1:  # (re)start the clock after the warm-up cycle
+                phases = {k: 0.0 for k in phases}
+                barrier()
+                t0 = time.perf_counter()
             p0 = time.perf_counter()
             s2 = ShardedSolve(S, torch, dist, spec, rank, world, local, stream, kernel, args.dedup)
             p1 = time.perf_counter()
@@ -302,7 +366,7 @@ def run_gpu(args):
             p2 = time.perf_counter()
             if world == 1:
                 v1, q1 = s2.solver.value(1, [[0.0] * s2.solver.ndim] if args.workload != "c3" else [[0.0, 100.0]])
-                V1, Q1 = s2.solver.period_tables(1)
+                V1, Q1 = s2.solver.period_tables(1, out_v=host_v, out_q=host_q)
                 d2h = s2.n * 16 + 16
             else:
                 s2.solver.sync()
@@ -355,7 +419,8 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "phases_s_per_step": phases,
                     "what": "sdpb_create (H2D pmf/parameter tables) + solve + sdpb_value + D2H of the period-1 "
-                            "value and policy tables + sdpb_destroy, wall clock"},
+                            "value and policy tables into page-locked host buffers + sdpb_destroy, wall clock; "
+                            "one untimed warm-up cycle first"},
             "gpu_launches": args.steps * spec.T * world,
             "clocks": clocks,
             "roofline": {
@@ -453,6 +518,8 @@ def run_gpu(args):
                 b.close()
             for c in configs.values():
                 c["fp64_frac"] = c["fp64_tops_per_gpu"] / peak if peak else None
+    if rank == 0 and not args.no_configs:
+        out["next_rows"] = next_rows(S, local)
     if rank == 0:
         out["configs"] = configs
         if not args.no_cpu_baseline:

@@ -419,9 +419,9 @@ bi_inv_tiled2(const __grid_constant__ DevModel M, const __grid_constant__ TiledA
 // ---- host side --------------------------------------------------------------------------------
 inline void plan_tiled(TiledPlan& P, const sdpb_model& m, const DevModel& d, const std::vector<int>& pmf_len,
                        const std::vector<int>& pmf_off, const std::vector<int>& pdi, bool /*dedup*/,
-                       const cudaDeviceProp& prop) {
+                       int sm_count) {
     P.available = false;
-    P.sm_count = prop.multiProcessorCount;
+    P.sm_count = sm_count;
     if (m.cost_kind != SDPB_COST_BACKORDER) { P.why_not = "only the backorder cost kind is tiled"; return; }
     if (m.lead_time != 0) { P.why_not = "lead-time states are not tiled yet"; return; }
     if (!(m.flags & SDPB_F_CLAMP_INV)) { P.why_not = "needs the inventory clamp"; return; }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -550,6 +551,14 @@ void sdpb_destroy(sdpb_handle* h) {
 
 int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out) {
     g_create_error.clear();
+    // SDPB_TRACE=1: wall-clock checkpoints of this call on stderr
+    static const bool trace = std::getenv("SDPB_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (trace)
+            std::fprintf(stderr, "[sdpb_create] %-18s %8.3f ms\n", what,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     if (!m || !out) return fail_create(nullptr, SDPB_ERR_ARG, "null argument");
     *out = nullptr;
     if (m->struct_size != sizeof(sdpb_model))
@@ -632,6 +641,7 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         res_t[t] = m->reserve_t ? m->reserve_t[t] : 0.0;
     }
 
+    mark("validated");
     DevModel& d = h->dm;
     d.cost_kind = m->cost_kind;
     d.recursion = m->recursion;
@@ -717,11 +727,15 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     if (dev < 0) cudaGetDevice(&dev);
     if (dev >= ndev) return fail_create(h, SDPB_ERR_NO_DEVICE, "device ordinal out of range");
     h->device = dev;
-    cudaDeviceProp prop;
-    if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+    // two attribute queries instead of cudaGetDeviceProperties, which costs 3-30 ms per call
+    int cc_major = 0, sm_count = 0;
+    if (cudaSetDevice(dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return fail_create(h, SDPB_ERR_NO_DEVICE, "cannot select CUDA device");
-    if (prop.major != 10)
+    if (cc_major != 10)
         return fail_create(h, SDPB_ERR_NO_DEVICE, "libsdpb200 is built for sm_100a (B200) only");
+    mark("device selected");
     if (h->opt.stream) { h->stream = (cudaStream_t)h->opt.stream; }
     else {
         if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -731,6 +745,7 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
     lift_pool_threshold(dev);
+    mark("stream, events");
 
     double *dp = nullptr;
     int* di = nullptr;
@@ -754,6 +769,7 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         UP(h->apmf_len, apmf_len, di) UP(aoff, apmf_off, di) UP(ap, apmf_p, dp) UP(ml, min_level_t, dp)
     }
 #undef UP
+    mark("tables uploaded");
 
     h->dV.assign(T, nullptr);
     h->dQ.assign(T, nullptr);
@@ -769,6 +785,7 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         h->dQ[t] = (int*)p;
     }
 
+    mark("V/Q allocated");
     // ---- exact folding of lead-time states (opt-in) ----
     if (h->opt.dedup && m->lead_time >= 1) {
         h->dedup = true;
@@ -792,12 +809,13 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     }
 
     // ---- kernel plan ----
-    plan_tiled(h->tiled, h->m, h->dm, h->pmf_len, h->pmf_off, pdi, h->opt.dedup != 0, prop);
+    plan_tiled(h->tiled, h->m, h->dm, h->pmf_len, h->pmf_off, pdi, h->opt.dedup != 0, sm_count);
     plan_cash(h->cash, h->m, h->dm, h->pmf_len, h->pmf_off, pdi);
     h->tiled.variant = h->opt.kernel == SDPB_KERNEL_TILED2 ? 2 : (h->opt.kernel == SDPB_KERNEL_TILED ? 1 : 0);
     if ((h->opt.kernel == SDPB_KERNEL_TILED || h->opt.kernel == SDPB_KERNEL_TILED2) && !h->tiled.available &&
         !(m->cost_kind == SDPB_COST_BACKORDER && m->lead_time >= 1) && !h->cash.available)
         return fail_create(h, SDPB_ERR_ARG, std::string("no shared-memory kernel for this model: ") + h->tiled.why_not);
+    mark("planned");
     *out = h;
     return SDPB_OK;
 }
@@ -1166,9 +1184,9 @@ int sdpb_microbench(int device, double* nofma_tops, double* fma_tflops, double* 
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SDPB_ERR_NO_DEVICE;
     if (device < 0) cudaGetDevice(&device);
     if (device >= ndev || cudaSetDevice(device) != cudaSuccess) return SDPB_ERR_NO_DEVICE;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SDPB_ERR_CUDA;
-    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    int sm_count = 0;
+    if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return SDPB_ERR_CUDA;
+    const int blocks = sm_count * 8, threads = 256;
     double* out = nullptr;
     if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return SDPB_ERR_NOMEM;
     cudaEvent_t e0, e1;

@@ -83,10 +83,15 @@ class Solver:
                                         v.ctypes.data_as(dp), q.ctypes.data_as(dp)))
         return v, q
 
-    def period_tables(self, period: int, want_q: bool = True):
+    def period_tables(self, period: int, want_q: bool = True, out_v=None, out_q=None):
+        """Whole-grid V_t and order quantities.  `out_v` / `out_q`: caller-owned float64 arrays of n_states
+        (e.g. views of page-locked memory, which the device copies into at PCIe speed)."""
         dp = C.POINTER(C.c_double)
-        V = np.empty(self.n_states)
-        Q = np.empty(self.n_states) if want_q else None
+        for o in (out_v, out_q):
+            if o is not None and (o.dtype != np.float64 or o.size != self.n_states or not o.flags.c_contiguous):
+                raise ValueError("output buffers must be contiguous float64 arrays of n_states")
+        V = out_v if out_v is not None else np.empty(self.n_states)
+        Q = (out_q if out_q is not None else np.empty(self.n_states)) if want_q else None
         self._check(self.lib.sdpb_period_tables(self.h, period, V.ctypes.data_as(dp),
                                                 Q.ctypes.data_as(dp) if want_q else None))
         return V, Q
