@@ -210,6 +210,8 @@ typedef enum sdpb_kernel_choice {
     SDPB_KERNEL_LEAD_Q2 = 9,  /* lead time 2: a thread owns 8 preQ1 levels of one (x, preQ2), walks every action
                                  itself and reads V_{t+1} through a transposed copy; AUTO picks it when the
                                  model is not folded */
+    SDPB_KERNEL_TWO_PRODUCT_ROW = 10, /* reported only: two-product kernel that shares the cash-independent terms
+                                         of an (action, demand) pair across a row of cash levels (integer prices) */
     SDPB_KERNEL_TILED2 = 5    /* 2-D register-tile variant of the tiled kernel: chosen automatically for
                                  large grids; as a request it forces the variant wherever it applies */
 } sdpb_kernel_choice;

@@ -323,7 +323,27 @@ int dispatch_generic_d(sdpb_handle* h, int t, const double* Vn, double* Vt, int*
     case SDPB_COST_CASH_TWO_PRODUCT: {
         if (DEDUP) { h->err = "no lead time to fold"; return SDPB_ERR_ARG; }
         const long long nst = hi - lo;
-        if (nst > 0) {
+        const int Dt = h->pmf_len[t - 1];
+        if (nst > 0 && h->opt.kernel != SDPB_KERNEL_GENERIC && plan_two_product_row(h->m, h->dm, t, Dt)) {
+            // CTA = one (inv1, inv2) pair x 128 cash levels; cash-independent terms shared through shared memory
+            const int segs = (h->dm.nW + 127) / 128;
+            const long long pair0 = lo / h->dm.nW, pair1 = (hi - 1) / h->dm.nW;
+            const unsigned blocks = (unsigned)((pair1 - pair0 + 1) * segs);
+            const size_t smem = (size_t)Dt * sizeof(TwoProductRowTables);
+            cudaError_t e = cudaSuccess;
+            if (t == h->m.T) {
+                auto k = bi_two_product_row<true>;
+                if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e == cudaSuccess) k<<<blocks, 128, smem, h->stream>>>(h->dm, t, Dt, h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi, pair0, segs);
+            } else {
+                auto k = bi_two_product_row<false>;
+                if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e == cudaSuccess) k<<<blocks, 128, smem, h->stream>>>(h->dm, t, Dt, h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi, pair0, segs);
+            }
+            if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return SDPB_ERR_CUDA; }
+            h->stats.kernel_used = SDPB_KERNEL_TWO_PRODUCT_ROW;
+            h->stats.fp64_ops += count_evals_period(h, t) * (t == h->m.T ? 1.0 : 3.0);
+        } else if (nst > 0) {
             const unsigned blocks = (unsigned)((nst + 127) / 128);
             if (t == h->m.T) bi_two_product<true><<<blocks, 128, 0, h->stream>>>(h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi);
             else bi_two_product<false><<<blocks, 128, 0, h->stream>>>(h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi);

@@ -453,6 +453,37 @@ def test_two_product_tolerance_changes_the_answer(S, oracle):
         assert np.array_equal(V, Vo) and np.array_equal(Q, Qo)
 
 
+def test_two_product_row_kernel(S, oracle):
+    """The row-shared two-product kernel (integer prices): several cash segments per (inv1, inv2) pair with a
+    ragged last segment, gamma < 1, non-integer salvage (last period only), demand lists that are not product
+    grids; whole grid against the oracle, the thread-per-state kernel and sharded handles.  Non-integer
+    prices must fall back to the thread-per-state kernel."""
+    rng = np.random.default_rng(11)
+    for cash_max, qb, inv_max, price, vc, sal, gamma in ((300, 5, 6, (4, 9), (2, 4), (1, 1.5), 0.95),
+                                                        (131, 7, 4, (6, 5), (3, 1), (0.5, 2), 1.0),
+                                                        (127, 3, 5, (3, 8), (1, 2), (1, 1), 1.0)):
+        rows = []
+        for _ in range(3):
+            n = int(rng.integers(3, 9))
+            d = np.stack([rng.integers(0, 6, n), rng.integers(0, 5, n)], axis=1).astype(float)
+            rows.append(np.column_stack([d, rng.dirichlet(np.ones(n))]))
+        spec = S.two_product_cash_model(rows, price=price, vari_cost=vc, salvage=sal, q_bound=qb, inv_max=inv_max,
+                                        cash_min=0, cash_max=cash_max, gamma=gamma)
+        Vo, Qo, evals, _ = oracle.dense(spec)
+        s, V, Q = _solve_all(S, spec)
+        assert s.stats()["kernel_used"] == S.KERNEL_TWO_PRODUCT_ROW and s.stats()["evals"] == evals
+        assert np.array_equal(V, Vo) and np.array_equal(Q, Qo)
+        g, Vg, Qg = _solve_all(S, spec, kernel=S.KERNEL_GENERIC)
+        assert g.stats()["kernel_used"] == S.KERNEL_GENERIC
+        assert np.array_equal(Vg, Vo) and np.array_equal(Qg, Qo)
+    spec = S.two_product_cash_model(rows, price=(4.5, 9), vari_cost=(2, 4), salvage=(1, 1), q_bound=4, inv_max=5,
+                                    cash_min=0, cash_max=60)
+    Vo, Qo, _, _ = oracle.dense(spec)
+    s, V, Q = _solve_all(S, spec)
+    assert s.stats()["kernel_used"] == S.KERNEL_GENERIC
+    assert np.array_equal(V, Vo) and np.array_equal(Q, Qo)
+
+
 def test_reference_style_driver_workforce(S, oracle):
     """Reads like src/workforce/WorkforcePlanning.java:106-118."""
     spec, init = cases.case_W_small()
