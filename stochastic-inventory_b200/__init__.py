@@ -17,5 +17,6 @@ from .recursion import (StaffRecursion, StaffState, Actions, CashRecursionMulti,
                         OptDirection, Recursion, RiskRecursion, RiskState, State)
 from .solver import Solver
 from .simulation import CashSimulation, Simulation, generate_lh_samples
+from .sampling import MRG32k3a, Sampling
 from . import configs
 from . import parallel

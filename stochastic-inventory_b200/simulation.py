@@ -5,7 +5,8 @@
 
 The reference draws its Latin-hypercube samples with Math.random() (src/sdp/sampling/Sampling.java:94),
 so its simulated means are not reproducible run to run; here the sample matrix is an explicit argument
-(or drawn from a seeded numpy generator with the same stratified scheme), and the roll-out itself —
+(from sampling.Sampling, the MRG32k3a mirror of Sampling.java, or from `generate_lh_samples`, a vectorised
+numpy generator with the same stratified scheme), and the roll-out itself —
 Q = getAction(state); d = Math.round(sample); sum += c; state = f — runs on the GPU, one thread per path.
 """
 from __future__ import annotations
