@@ -18,5 +18,6 @@ from .recursion import (StaffRecursion, StaffState, Actions, CashRecursionMulti,
 from .solver import Solver
 from .simulation import CashSimulation, Simulation, generate_lh_samples
 from .sampling import MRG32k3a, Sampling
+from .write import WriteToCsv, WriteToExcelTxt, java_double
 from . import configs
 from . import parallel
