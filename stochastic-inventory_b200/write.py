@@ -57,6 +57,13 @@ def _shortest_digits(a: float):
     lead = len((ip + fp)) - len((ip + fp).lstrip("0"))
     exp = len(ip) - lead + e
     digits = digits.rstrip("0") or "0"
+    if len(digits) == 1:
+        # Java prints at least two digits and, when one would do, takes the two-digit decimal CLOSEST to the
+        # exact value among those that round-trip (Double.MIN_VALUE is "4.9E-324", not "5.0E-324")
+        t = Decimal(a).scaleb(-(exp - 1)).quantize(Decimal("0.1"))  # d.d
+        cand = str(t).replace(".", "")
+        if len(cand) == 2 and float(f"0.{cand}e{exp}") == a:
+            digits = cand.rstrip("0") or cand[0]
     return digits, exp
 
 
