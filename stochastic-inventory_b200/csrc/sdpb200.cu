@@ -819,6 +819,9 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         h->dHa = (int*)p;
     }
 
+    if (h->opt.kernel == SDPB_KERNEL_LEAD_Q2 &&
+        !(m->cost_kind == SDPB_COST_BACKORDER && m->lead_time == 2 && !h->dedup))
+        return fail_create(h, SDPB_ERR_ARG, "SDPB_KERNEL_LEAD_Q2 needs a backorder model with lead_time 2 and dedup off");
     // ---- transposed successor table for the lead-time-2 kernel ----
     if (!h->dedup && m->cost_kind == SDPB_COST_BACKORDER && m->lead_time == 2 &&
         (h->opt.kernel == SDPB_KERNEL_AUTO || h->opt.kernel == SDPB_KERNEL_LEAD_Q2)) {

@@ -174,6 +174,10 @@ def test_staged_kernel_is_used_for_leadtime(S):
     assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_LEAD_Q2
     assert S.Solver(spec, kernel=S.KERNEL_LEAD_COL).solve().stats()["kernel_used"] == S.KERNEL_LEAD_COL
     assert S.Solver(spec, kernel=S.KERNEL_LEAD_SLAB).solve().stats()["kernel_used"] == S.KERNEL_LEAD_SLAB
+    with pytest.raises(S.SdpbError):  # folded grids and lead time 1 have no all-actions-in-thread kernel
+        S.Solver(spec, kernel=S.KERNEL_LEAD_Q2, dedup=True)
+    with pytest.raises(S.SdpbError):
+        S.Solver(cases.case_B1_ref()[0], kernel=S.KERNEL_LEAD_Q2)
     assert S.Solver(spec, kernel=S.KERNEL_STAGED).solve().stats()["kernel_used"] == S.KERNEL_STAGED
     assert S.Solver(spec, kernel=S.KERNEL_GENERIC).solve().stats()["kernel_used"] == S.KERNEL_GENERIC
     spec, _ = cases.case_A_small()
