@@ -287,6 +287,7 @@ inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& d
 // window, no loads).  64-thread CTAs, 8 per SM: the grid is only ~2000 CTAs on a 1e6-state model, so
 // small CTAs are what keeps the last wave short (ncu: profiles/r01_ncu_cash_diag*_raw.csv).
 constexpr int kDiagYT = 8;
+constexpr int kDiagCols = 64;  // state columns (cash levels of slot 0) per CTA
 
 template <bool SURVIVAL, bool IS_MIN, int kDiagThreads, int PF = 2>
 __global__ void __launch_bounds__(kDiagThreads, 512 / kDiagThreads)
@@ -302,10 +303,16 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
     __syncthreads();
     const unsigned pp_s = (unsigned)__cvta_generic_to_shared(PP);
     const unsigned pr_s = (unsigned)__cvta_generic_to_shared(PRd);
+    // action split: the CTA is kDiagCols state columns x `parts` slices of the action range (small grids
+    // cannot fill the GPU with columns alone); slices > 0 hand their optima to slice 0 through shared memory
+    constexpr int parts = kDiagThreads / kDiagCols;
+    const int part = threadIdx.x / kDiagCols, col = threadIdx.x % kDiagCols;
+    double* MV = reinterpret_cast<double*>(smem_raw + (((size_t)a.D * 24 + 15) & ~(size_t)15));  // [parts-1][YT][cols]
+    int* MA = reinterpret_cast<int*>(MV + (size_t)(parts - 1) * YT * kDiagCols);
 
     const int D = a.D, price = a.price, nW1 = M.nW - 1;
     const int ix0 = a.ix0 + blockIdx.y * YT;                                  // inventory index of slot 0
-    const int iw0 = blockIdx.x * kDiagThreads + threadIdx.x;                  // cash index of slot 0
+    const int iw0 = blockIdx.x * kDiagCols + col;                             // cash index of slot 0
     const double v_d = M.v_t[a.t - 1];
     const double res = M.reserve_t[a.t - 1];
 
@@ -328,12 +335,14 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
         best[k] = IS_MIN ? DBL_MAX : -DBL_MAX;
         arg[k] = kNoAction;
     }
-    if (nAmax == 0) return;
+    if (parts == 1 && nAmax == 0) return;
 
     const int xv0 = a.inv_min_i + ix0;  // inventory VALUE of slot 0
     const int row_tail = min(max(M.i_zero, 0), M.nI - 1) * M.nW;
+    const int per_part = (nAmax + parts - 1) / parts;
+    const int ai_end = min(nAmax, (part + 1) * per_part);
 
-    for (int ai = 0; ai < nAmax; ai++) {
+    for (int ai = part * per_part; ai < ai_end; ai++) {
         const int CI = (ai > 0 ? a.K : 0) + a.v * ai + a.ovh;  // K 1[a>0] + v a + overhead
         const double Cd = (double)CI;
         const int base = iw0 + price * (ix0 + ai) - CI;        // successor cash index = base - price*il
@@ -430,6 +439,26 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
             if (ai < nA[k] && (IS_MIN ? (acc[k] < best[k]) : (acc[k] > best[k]))) { best[k] = acc[k]; arg[k] = ai; }
         }
     }
+    if (parts > 1) {
+        if (part > 0) {
+#pragma unroll
+            for (int k = 0; k < YT; k++) {
+                MV[((part - 1) * YT + k) * kDiagCols + col] = best[k];
+                MA[((part - 1) * YT + k) * kDiagCols + col] = arg[k];
+            }
+        }
+        __syncthreads();
+        if (part > 0) return;
+        // ascending slices hold ascending actions: a strict compare keeps the first optimum
+        for (int q = 0; q < parts - 1; q++) {
+#pragma unroll
+            for (int k = 0; k < YT; k++) {
+                const double v = MV[(q * YT + k) * kDiagCols + col];
+                const int av = MA[(q * YT + k) * kDiagCols + col];
+                if (av != kNoAction && (IS_MIN ? (v < best[k]) : (v > best[k]))) { best[k] = v; arg[k] = av; }
+            }
+        }
+    }
 #pragma unroll
     for (int k = 0; k < YT; k++) {
         if (nA[k] > 0) {
@@ -455,20 +484,23 @@ inline int launch_cash_diag(const CashPlan& P, const sdpb_model& m, const DevMod
     const int ix1 = (int)((hi - 1) / dm.nW);
     a.price = cp.price; a.v = cp.v; a.K = P.K; a.ovh = cp.ovh; a.d0 = cp.d0; a.inv_min_i = (int)m.inv_min;
     const int span_w = dm.nW + cp.price * (kDiagYT - 1);  // slot 0's cash index runs past the axis so slot 7 covers it
-    int nt = 64;
-    if (const char* e = std::getenv("SDPB_DIAG_THREADS")) nt = std::atoi(e) == 128 ? 128 : 64;  // tuning knob
-    const dim3 grid((unsigned)((span_w + nt - 1) / nt), (unsigned)((ix1 - a.ix0 + 1 + kDiagYT - 1) / kDiagYT));
-    const size_t smem = (size_t)D * 24 + 16;
+    const dim3 grid((unsigned)((span_w + kDiagCols - 1) / kDiagCols), (unsigned)((ix1 - a.ix0 + 1 + kDiagYT - 1) / kDiagYT));
+    // slices of the action range per CTA: enough warps for ~6 waves of 16 warps per SM
+    int sm_count = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    const double waves = (double)grid.x * grid.y * (kDiagCols / 32) / (16.0 * sm_count);
+    int parts = waves >= 6.0 ? 1 : (waves >= 3.0 ? 2 : 4);
+    if (const char* e = std::getenv("SDPB_DIAG_SPLIT")) parts = std::atoi(e) == 1 ? 1 : std::atoi(e) == 2 ? 2 : 4;  // tuning knob
+    const size_t smem = (((size_t)D * 24 + 15) & ~(size_t)15) + (size_t)(parts - 1) * kDiagYT * kDiagCols * 12 + 16;
     const bool surv = m.recursion == SDPB_REC_SURVIVAL;
-    if (nt == 128) {
-        if (surv) bi_cash_diag<true, false, 128><<<grid, 128, smem, stream>>>(dm, a);
-        else if (dm.is_min) bi_cash_diag<false, true, 128><<<grid, 128, smem, stream>>>(dm, a);
-        else bi_cash_diag<false, false, 128><<<grid, 128, smem, stream>>>(dm, a);
-    } else {
-        if (surv) bi_cash_diag<true, false, 64><<<grid, 64, smem, stream>>>(dm, a);
-        else if (dm.is_min) bi_cash_diag<false, true, 64><<<grid, 64, smem, stream>>>(dm, a);
-        else bi_cash_diag<false, false, 64><<<grid, 64, smem, stream>>>(dm, a);
+#define SDPB_DIAG_LAUNCH(NT)                                                                      \
+    {                                                                                             \
+        if (surv) bi_cash_diag<true, false, NT><<<grid, NT, smem, stream>>>(dm, a);               \
+        else if (dm.is_min) bi_cash_diag<false, true, NT><<<grid, NT, smem, stream>>>(dm, a);     \
+        else bi_cash_diag<false, false, NT><<<grid, NT, smem, stream>>>(dm, a);                   \
     }
+    if (parts == 1) SDPB_DIAG_LAUNCH(64) else if (parts == 2) SDPB_DIAG_LAUNCH(128) else SDPB_DIAG_LAUNCH(256)
+#undef SDPB_DIAG_LAUNCH
     if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
     if (fp64_ops) *fp64_ops += evals * (surv ? 2.0 : 3.0 + 2.0 / kDiagYT);
     return SDPB_OK;
