@@ -71,7 +71,9 @@ def workload_desc(spec, name, n_gpus):
         }[name],
         "T": spec.T, "demand_points": D[0] if len(set(D)) == 1 else D,
         "actions": spec.max_order_idx + 1,
-        "partition": f"state grid in {n_gpus} contiguous blocks, V_t all-gather per period" if n_gpus > 1 else "none",
+        "partition": (f"state grid in {n_gpus} contiguous blocks; per period each rank receives the rows of V_t its "
+                      "block can reach (point-to-point halo exchange over NCCL; all-gather when that is most of "
+                      "the table)") if n_gpus > 1 else "none",
         "l2": "inputs exceed L2 only for S>=1.6e7 (V_t is 8*S bytes); kernel is fp64-pipe bound and reads "
               "V_{t+1} once per tile through shared memory, so L2 state does not move the number",
     }
@@ -495,6 +497,7 @@ def run_gpu(args):
                     v0, q0 = float(v[0]), float(q[0])
                 tops = fp / (cms * 1e-3) / 1e12 / w
                 configs[name_key] = {"solve_ms": cms, "evals": ev, "evals_per_s": ev / (cms * 1e-3),
+                                     "exchange": s3.exchange_kind,
                                      "evals_executed": evx, "n_gpus": w, "kernel": KERNEL_NAMES.get(kused),
                                      "dedup": dedup, "fp64_tops_per_gpu": tops, "V1_init": v0, "Q1_init": q0}
                 s3.close()

@@ -261,6 +261,10 @@ void sdpb_destroy(sdpb_handle* h);
 const char* sdpb_last_error(const sdpb_handle* h); /* h may be NULL: last create error */
 
 int sdpb_grid_info(const sdpb_handle* h, sdpb_grid* g);
+/* Multi-GPU: the contiguous range [lo, hi) of flattened V_{t+1} indices the kernels of this shard may read in
+ * any period (its own band of inventory rows widened by the largest order and the largest demand, plus the
+ * zero row for lost-sales clamps).  Ranks exchange only these rows instead of all-gathering V_t. */
+int sdpb_shard_reads(const sdpb_handle* h, int64_t* lo, int64_t* hi);
 
 /* Backward induction over periods T..1 for this handle's shard (whole grid when unsharded). */
 int sdpb_solve(sdpb_handle* h);

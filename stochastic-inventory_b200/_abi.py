@@ -83,7 +83,7 @@ EXPORTS = [
     "sdpb_abi_version", "sdpb_sizeof_model", "sdpb_sizeof_options", "sdpb_create", "sdpb_destroy",
     "sdpb_last_error", "sdpb_grid_info", "sdpb_solve", "sdpb_solve_async", "sdpb_solve_period_async", "sdpb_sync",
     "sdpb_value", "sdpb_period_tables", "sdpb_device_tables", "sdpb_state_of_index", "sdpb_reach",
-    "sdpb_opt_table", "sdpb_stats_get", "sdpb_eval_triples", "sdpb_microbench", "sdpb_simulate",
+    "sdpb_opt_table", "sdpb_stats_get", "sdpb_eval_triples", "sdpb_microbench", "sdpb_simulate", "sdpb_shard_reads",
 ]
 
 _lib = None
@@ -125,6 +125,7 @@ def load():
     lib.sdpb_last_error.argtypes = [vp]
     lib.sdpb_last_error.restype = C.c_char_p
     lib.sdpb_grid_info.argtypes = [vp, C.POINTER(SdpbGrid)]
+    lib.sdpb_shard_reads.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.sdpb_solve.argtypes = [vp]
     lib.sdpb_solve_async.argtypes = [vp]
     lib.sdpb_solve_period_async.argtypes = [vp, C.c_int]

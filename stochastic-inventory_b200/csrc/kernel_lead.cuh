@@ -539,13 +539,14 @@ struct Q2Args {
     long long f_begin, f_end; // flat thread range: f = (x * n_chunks + chunk) * nQ + preQ2
     int n_chunks, tpx;        // chunks of 8 levels along preQ1; threads per inventory row
     int di_max, NRW;
+    int parts;                // slices of the action range per CTA (1, 2 or 4): small grids cannot fill the GPU otherwise
 };
 
 constexpr int kQ2YT = 8, kQ2PF = 2, kQ2PAD = kQ2PF + 1;
 
-__global__ void transpose_q2a(const double* __restrict__ V, double* __restrict__ VT, int nQ) {
+__global__ void transpose_q2a(const double* __restrict__ V, double* __restrict__ VT, int nQ, int row0) {
     __shared__ double tile[32][33];
-    const long long base = (long long)blockIdx.x * nQ * nQ;
+    const long long base = (long long)(row0 + blockIdx.x) * nQ * nQ;
     const int c0 = blockIdx.y * 32, r0 = blockIdx.z * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int row = r0 + r, c = c0 + threadIdx.x;
@@ -558,7 +559,7 @@ __global__ void transpose_q2a(const double* __restrict__ V, double* __restrict__
     }
 }
 
-template <bool IS_MIN, bool LAST, int NT>
+template <bool IS_MIN, bool LAST, int NT, int PARTS>
 __global__ void __launch_bounds__(NT, 512 / NT)
 bi_lead_q2(const __grid_constant__ DevModel M, const __grid_constant__ Q2Args a) {
     constexpr int YT = kQ2YT, PF = kQ2PF, W = YT + PF, PAD = kQ2PAD;
@@ -566,7 +567,11 @@ bi_lead_q2(const __grid_constant__ DevModel M, const __grid_constant__ Q2Args a)
     double2* WR = reinterpret_cast<double2*>(smem_raw);  // (level cost, successor row offset in the low word)
     double2* PP = WR + a.NRW;                            // (p, p*gamma)
     const int D = a.D, nQ = M.nQ, tid = threadIdx.x;
-    const long long F0 = a.f_begin + (long long)blockIdx.x * NT;
+    constexpr int cols = NT / PARTS;
+    const int part = tid / cols, col = tid - part * cols;
+    double* MV = reinterpret_cast<double*>(PP + D);      // [PARTS-1][YT][cols] optima of the action slices > 0
+    int* MA = reinterpret_cast<int*>(MV + (size_t)(PARTS - 1) * YT * cols);
+    const long long F0 = a.f_begin + (long long)blockIdx.x * cols;
     const long long x_first = F0 / a.tpx;
     const bool lost = (M.flags & SDPB_F_LOST_SALES) != 0;
 
@@ -584,8 +589,7 @@ bi_lead_q2(const __grid_constant__ DevModel M, const __grid_constant__ Q2Args a)
     }
     __syncthreads();
 
-    const long long F = F0 + tid;
-    if (F >= a.f_end) return;
+    const long long F = min(F0 + col, a.f_end - 1);
     const long long x = F / a.tpx;
     const int f = (int)(F - x * a.tpx);
     const int chunk = f / nQ, q2 = f - chunk * nQ, l0 = chunk * YT;
@@ -593,7 +597,8 @@ bi_lead_q2(const __grid_constant__ DevModel M, const __grid_constant__ Q2Args a)
     bool any = false;
 #pragma unroll
     for (int k = 0; k < YT; k++) any |= (l0 + k < nQ) && idx0 + (long long)k * nQ >= a.lo && idx0 + (long long)k * nQ < a.hi;
-    if (!any) return;
+    any = any && F0 + col < a.f_end;
+    if (PARTS == 1 && !any) return;
 
     // slot k at demand j reads window row  (x - x_first) + l0 + k + (D-1-j) + PAD
     const unsigned wr0 = (unsigned)__cvta_generic_to_shared(WR) + (unsigned)((int)(x - x_first) + l0 + (D - 1) + PAD) * 16u;
@@ -606,7 +611,11 @@ bi_lead_q2(const __grid_constant__ DevModel M, const __grid_constant__ Q2Args a)
 #pragma unroll
     for (int k = 0; k < YT; k++) { best[k] = IS_MIN ? DBL_MAX : -DBL_MAX; arg[k] = kNoAction; }
 
-    for (int ai = 0; ai <= M.max_order_idx; ai++) {
+    const int per_part = (M.max_order_idx + PARTS) / PARTS;  // ceil(A / PARTS)
+    const int ai_begin = any ? part * per_part : 0;
+    const int ai_end = any ? min(M.max_order_idx + 1, ai_begin + per_part) : 0;
+    if (!LAST) cb += (long long)ai_begin * nQ;
+    for (int ai = ai_begin; ai < ai_end; ai++) {
         const double av = (double)ai * M.step;
         const double fv = (av > 0.0 ? M.K : 0.0) + vt * av;  // Leadtime.java:73-74,79
         double acc[YT], cst[W], Vw[W];
@@ -646,6 +655,25 @@ bi_lead_q2(const __grid_constant__ DevModel M, const __grid_constant__ Q2Args a)
             if (IS_MIN ? (acc[k] < best[k]) : (acc[k] > best[k])) { best[k] = acc[k]; arg[k] = ai; }
         if (!LAST) cb += nQ;
     }
+    if (PARTS > 1) {
+        if (part > 0) {
+#pragma unroll
+            for (int k = 0; k < YT; k++) {
+                MV[((part - 1) * YT + k) * cols + col] = best[k];
+                MA[((part - 1) * YT + k) * cols + col] = arg[k];
+            }
+        }
+        __syncthreads();
+        if (part > 0 || !any) return;
+        for (int q = 0; q < PARTS - 1; q++) {  // ascending slices hold ascending actions: strict compare = first wins
+#pragma unroll
+            for (int k = 0; k < YT; k++) {
+                const double v = MV[(q * YT + k) * cols + col];
+                const int av = MA[(q * YT + k) * cols + col];
+                if (av != kNoAction && (IS_MIN ? (v < best[k]) : (v > best[k]))) { best[k] = v; arg[k] = av; }
+            }
+        }
+    }
 #pragma unroll
     for (int k = 0; k < YT; k++) {
         const long long idx = idx0 + (long long)k * nQ;
@@ -668,28 +696,25 @@ inline Q2Plan plan_q2(const sdpb_model& m, const DevModel& d, int D, const int* 
     for (int j = 0; j < D; j++)
         if (di[j] != di[0] + j) return P;  // the register window needs consecutive demands
     if ((long long)d.nI * d.nQ * d.nQ >= 0x7fffffffLL) return P;  // 32-bit successor row offsets
-    if (const char* e = std::getenv("SDPB_Q2_THREADS")) {  // tuning knob
-        const int v = std::atoi(e);
-        P.NT = v == 64 ? 64 : v == 256 ? 256 : v == 512 ? 512 : 128;
-    }
     P.n_chunks = (d.nQ + kQ2YT - 1) / kQ2YT;
     P.tpx = P.n_chunks * d.nQ;
     P.di_max = di[D - 1];
     const int dx_max = (P.NT + P.tpx - 1) / P.tpx + 1;  // inventory rows a CTA's threads can span
     P.NRW = P.n_chunks * kQ2YT + D + kQ2PAD + dx_max;
-    P.smem = (size_t)(P.NRW + D) * 16;
+    P.smem = (size_t)(P.NRW + D) * 16 + (size_t)kQ2YT * P.NT * 12;  // + the action-slice merge: (parts-1)/parts * YT * NT entries
     P.ok = P.smem <= 96 * 1024;
     return P;
 }
 
 // VnT: scratch of nI*nQ*nQ doubles; filled here from Vn (stream order) unless this is the last period.
+// [row0, row1): inventory rows of V_{t+1} the range [lo, hi) can read (sdpb_shard_reads); only those are transposed.
 inline int launch_q2(const Q2Plan& P, const DevModel& dm, int t, int D, int pmf_off, const double* Vn, double* VnT,
-                     double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream) {
+                     double* Vt, int* Qt, long long lo, long long hi, int row0, int row1, cudaStream_t stream) {
     if (hi <= lo) return SDPB_OK;
     const bool last = (t == dm.T), mn = dm.is_min != 0;
     if (!last) {
         const unsigned tiles = (unsigned)((dm.nQ + 31) / 32);
-        transpose_q2a<<<dim3((unsigned)dm.nI, tiles, tiles), dim3(32, 8), 0, stream>>>(Vn, VnT, dm.nQ);
+        transpose_q2a<<<dim3((unsigned)(row1 - row0), tiles, tiles), dim3(32, 8), 0, stream>>>(Vn, VnT, dm.nQ, row0);
     }
     Q2Args a;
     a.t = t; a.D = D; a.pmf_off = pmf_off; a.VnT = last ? nullptr : VnT; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
@@ -697,20 +722,26 @@ inline int launch_q2(const Q2Plan& P, const DevModel& dm, int t, int D, int pmf_
     const long long per_x = (long long)dm.nQ * dm.nQ;
     a.f_begin = (lo / per_x) * P.tpx;
     a.f_end = ((hi - 1) / per_x + 1) * P.tpx;
-    const long long blocks = (a.f_end - a.f_begin + P.NT - 1) / P.NT;
+    // slices of the action range per CTA: enough warps for ~6 waves of 16 warps per SM
+    int sm_count = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    const double waves = (double)(a.f_end - a.f_begin) / 32.0 / (16.0 * sm_count);
+    a.parts = waves >= 6.0 ? 1 : (waves >= 3.0 ? 2 : 4);
+    if (const char* e2 = std::getenv("SDPB_Q2_SPLIT")) a.parts = std::atoi(e2) == 1 ? 1 : std::atoi(e2) == 2 ? 2 : 4;  // tuning knob
+    const int cols = P.NT / a.parts;
+    const long long blocks = (a.f_end - a.f_begin + cols - 1) / cols;
     cudaError_t e = cudaSuccess;
-#define SDPB_Q2_LAUNCH(MN, LS, NTH)                                                                    \
+#define SDPB_Q2_LAUNCH(MN, LS, PT)                                                                     \
     {                                                                                                  \
-        auto k = bi_lead_q2<MN, LS, NTH>;                                                              \
+        auto k = bi_lead_q2<MN, LS, 128, PT>;                                                          \
         if (P.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem); \
-        if (e == cudaSuccess) k<<<(unsigned)blocks, NTH, P.smem, stream>>>(dm, a);                     \
+        if (e == cudaSuccess) k<<<(unsigned)blocks, 128, P.smem, stream>>>(dm, a);                     \
     }
 #define SDPB_Q2_NT(MN, LS)                                                                             \
-    switch (P.NT) {                                                                                    \
-    case 64: SDPB_Q2_LAUNCH(MN, LS, 64) break;                                                         \
-    case 256: SDPB_Q2_LAUNCH(MN, LS, 256) break;                                                       \
-    case 512: SDPB_Q2_LAUNCH(MN, LS, 512) break;                                                       \
-    default: SDPB_Q2_LAUNCH(MN, LS, 128) break;                                                        \
+    switch (a.parts) {                                                                                 \
+    case 1: SDPB_Q2_LAUNCH(MN, LS, 1) break;                                                           \
+    case 2: SDPB_Q2_LAUNCH(MN, LS, 2) break;                                                           \
+    default: SDPB_Q2_LAUNCH(MN, LS, 4) break;                                                          \
     }
     if (mn) { if (last) SDPB_Q2_NT(true, true) else SDPB_Q2_NT(true, false) }
     else    { if (last) SDPB_Q2_NT(false, true) else SDPB_Q2_NT(false, false) }

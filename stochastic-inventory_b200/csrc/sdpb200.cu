@@ -409,7 +409,11 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
             const double ev = (double)(hi - lo) * (h->m.max_order_idx + 1) * h->pmf_len[t - 1];
             h->stats.fp64_ops += ev * (t == h->m.T ? (1.0 + 2.0 * kQ2YT) / kQ2YT : (1.0 + 4.0 * kQ2YT) / kQ2YT);
             if (t < h->m.T) h->stats.launches++;  // the transposition pass
-            return launch_q2(qp, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, h->dVT, Vt, Qt, lo, hi, h->stream);
+            int64_t rlo = 0, rhi = h->S;
+            sdpb_shard_reads(h, &rlo, &rhi);
+            const long long per_x = (long long)h->dm.nQ * h->dm.nQ;
+            return launch_q2(qp, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, h->dVT, Vt, Qt, lo, hi,
+                             (int)(rlo / per_x), (int)(rhi / per_x), h->stream);
         }
     }
     if (h->opt.kernel != SDPB_KERNEL_GENERIC && h->opt.kernel != SDPB_KERNEL_STAGED && h->m.lead_time >= 1 &&
@@ -840,6 +844,33 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         return fail_create(h, SDPB_ERR_ARG, std::string("no shared-memory kernel for this model: ") + h->tiled.why_not);
     mark("planned");
     *out = h;
+    return SDPB_OK;
+}
+
+int sdpb_shard_reads(const sdpb_handle* h, int64_t* lo, int64_t* hi) {
+    if (!h || !lo || !hi) return SDPB_ERR_ARG;
+    const DevModel& d = h->dm;
+    const sdpb_model& m = h->m;
+    *lo = 0;
+    *hi = h->S;
+    if (h->hi <= h->lo) { *hi = 0; return SDPB_OK; }
+    // folded solves walk the whole virtual grid on every rank; the workforce kind can lose every employee
+    if (h->dedup || staff_kind(m)) return SDPB_OK;
+    const long long per_x = h->S / d.nI;  // the first inventory axis is outermost
+    long long r0 = h->lo / per_x, r1 = (h->hi - 1) / per_x;
+    int dmin = 0, dmax = 0;
+    for (int v : h->pmf_di) { dmin = std::min(dmin, v); dmax = std::max(dmax, v); }
+    // successor level = x + (order or pipeline quantity, at most max_order_idx) - demand, then clamps
+    r0 -= dmax;
+    r1 += (long long)m.max_order_idx - dmin;
+    if (m.flags & SDPB_F_LOST_SALES) {  // levels below zero are lifted to the zero row
+        r0 = std::min<long long>(r0, d.i_zero);
+        r1 = std::max<long long>(r1, d.i_zero);
+    }
+    r0 = std::max<long long>(r0, 0);
+    r1 = std::min<long long>(r1, d.nI - 1);
+    *lo = r0 * per_x;
+    *hi = (r1 + 1) * per_x;
     return SDPB_OK;
 }
 

@@ -1,10 +1,14 @@
 """Multi-GPU partitioning of one solve: the flattened state grid is cut into `world` contiguous
 blocks (inventory outermost, so each rank owns a band of inventory levels); every period each rank
-solves its block, then V_t is all-gathered so that every rank holds the full table period t-1
-reads.  Q_t is never exchanged.  One process per GPU; the collective is NCCL over NVLink through
-torch.distributed (gloo in the CPU tests).  SURVEY.md §8(e).
+solves its block, then V_t is exchanged so that every rank holds the part of the table period t-1
+reads: either all of it (all-gather) or only the band of inventory rows its own block can reach
+(`HaloExchange`: point-to-point sends of the overlaps, 4-7x fewer bytes on the lead-time grid at 8
+GPUs).  Q_t is never exchanged.  One process per GPU; NCCL over NVLink through torch.distributed
+(gloo in the CPU tests).  SURVEY.md §8(e).
 """
 from __future__ import annotations
+
+import numpy as np
 
 
 def shard_bounds(n_states: int, rank: int, world: int):
@@ -16,20 +20,94 @@ def shard_bounds(n_states: int, rank: int, world: int):
     return lo, hi, chunk
 
 
-def backward_induction_sharded(T, n_states, rank, world, solve_block, full_tables, all_gather):
+def needed_range(spec, lo, hi, n_states):
+    """Host mirror of sdpb_shard_reads: the contiguous range of flattened V_{t+1} indices the block [lo, hi)
+    may read -- its band of inventory rows widened by the largest order / pipeline quantity upwards and the
+    largest demand downwards, plus the zero row when lost-sales clamps lift negative levels to it."""
+    from . import _abi as A
+    if hi <= lo:
+        return 0, 0
+    if spec.staff:
+        return 0, n_states
+    n_inv = int(round((spec.inv_max - spec.inv_min) / spec.step)) + 1
+    per_x = n_states // n_inv
+    r0, r1 = lo // per_x, (hi - 1) // per_x
+    dmin = dmax = 0
+    for row in spec.pmf:
+        d = np.asarray(row, dtype=np.float64)[:, 0]
+        di = np.trunc(d) if spec.two_product else np.rint(d / spec.step)
+        dmin, dmax = min(dmin, int(di.min())), max(dmax, int(di.max()))
+    r0 -= dmax
+    r1 += spec.max_order_idx - dmin
+    if spec.flags & A.F_LOST_SALES:
+        i_zero = int(math_round_half_up((0.0 - spec.inv_min) / spec.step))
+        r0, r1 = min(r0, i_zero), max(r1, i_zero)
+    r0, r1 = max(r0, 0), min(r1, n_inv - 1)
+    return r0 * per_x, (r1 + 1) * per_x
+
+
+def math_round_half_up(x):
+    """Java Math.round."""
+    import math
+    return math.floor(x + 0.5)
+
+
+class HaloExchange:
+    """Point-to-point exchange of V_t: every rank receives, from each peer, the overlap of the peer's block
+    with the range it will read (`needs[rank]`), and sends the mirror image.  `needs` must be identical on
+    all ranks (gather_needs).  Works with NCCL (grouped sends/receives on the current stream) and gloo."""
+
+    def __init__(self, dist, rank, world, n_states, needs):
+        self.dist, self.rank = dist, rank
+        blocks = [shard_bounds(n_states, r, world)[:2] for r in range(world)]
+        self.recv = []  # (peer, lo, hi): slices of peers' blocks that I read
+        self.send = []  # (peer, lo, hi): slices of my block that peers read
+        for peer in range(world):
+            if peer == rank:
+                continue
+            a, b = max(blocks[peer][0], needs[rank][0]), min(blocks[peer][1], needs[rank][1])
+            if b > a:
+                self.recv.append((peer, a, b))
+            a, b = max(blocks[rank][0], needs[peer][0]), min(blocks[rank][1], needs[peer][1])
+            if b > a:
+                self.send.append((peer, a, b))
+        self.bytes_in = sum(b - a for _, a, b in self.recv) * 8
+
+    def __call__(self, full):
+        dist = self.dist
+        ops = [dist.P2POp(dist.isend, full[a:b], peer) for peer, a, b in self.send]
+        ops += [dist.P2POp(dist.irecv, full[a:b], peer) for peer, a, b in self.recv]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+
+def gather_needs(torch, dist, world, need, device=None):
+    """All ranks' (lo, hi) read ranges, identical everywhere (one tiny all-gather at set-up)."""
+    mine = torch.tensor(list(need), dtype=torch.int64, device=device)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    return [(int(t[0]), int(t[1])) for t in out]
+
+
+def backward_induction_sharded(T, n_states, rank, world, solve_block, full_tables, all_gather, exchange=None):
     """The per-period schedule shared by the GPU path and the CPU (gloo) test.
 
     solve_block(t)            computes V_t on [lo, hi) into full_tables[t-1][lo:hi], reading
-                              full_tables[t] (all of it) when t < T
+                              full_tables[t] (the rows its block can reach) when t < T
     full_tables[t-1]          a tensor of chunk*world elements (the padded full V_t)
     all_gather(out, inp)      torch.distributed.all_gather_into_tensor or an equivalent
+    exchange(full)            optional: a HaloExchange used instead of the all-gather
     """
     lo, hi, chunk = shard_bounds(n_states, rank, world)
     for t in range(T, 0, -1):
         solve_block(t)
-        if world > 1:
+        if world > 1 and t > 1:  # V_1 is read by nobody
             full = full_tables[t - 1]
-            all_gather(full, full[chunk * rank: chunk * (rank + 1)])
+            if exchange is not None:
+                exchange(full)
+            else:
+                all_gather(full, full[chunk * rank: chunk * (rank + 1)])
 
 
 class _CAI:
@@ -46,7 +124,7 @@ def wrap_device(torch, ptr, n, typestr, device):
 class ShardedSolve:
     """One rank's share of a GPU solve (libsdpb200 handle created with shard_rank / shard_count)."""
 
-    def __init__(self, Solver, torch, dist, spec, rank, world, device, stream, kernel=0, dedup=False):
+    def __init__(self, Solver, torch, dist, spec, rank, world, device, stream, kernel=0, dedup=False, exchange="auto"):
         self.torch, self.dist, self.world, self.rank = torch, dist, world, rank
         self.solver = Solver(spec, device=device, shard_rank=rank, shard_count=world, kernel=kernel,
                              dedup=dedup, stream=stream.cuda_stream)
@@ -55,10 +133,18 @@ class ShardedSolve:
         self.lo, self.hi, self.chunk = shard_bounds(self.n, rank, world)
         assert (self.lo, self.hi) == (g.shard_lo, g.shard_hi)
         self.V = []
+        self.exchange, self.exchange_kind = None, "none"
         if world > 1:
             for t in range(1, self.T + 1):
                 dv, _ = self.solver.device_tables(t)
                 self.V.append(wrap_device(torch, dv, self.chunk * world, "<f8", device))
+            # halo exchange when a rank reads well under the whole table (the library knows what its kernels read)
+            needs = gather_needs(torch, dist, world, self.solver.shard_reads(), device=f"cuda:{device}")
+            frac = max((b - a) for a, b in needs) / max(self.n, 1)
+            self.exchange_kind = "allgather"
+            if exchange == "halo" or (exchange == "auto" and frac < 0.6):
+                self.exchange = HaloExchange(dist, rank, world, self.n, needs)
+                self.exchange_kind = "halo"
 
     def step(self):
         if self.world == 1:
@@ -66,7 +152,7 @@ class ShardedSolve:
             return
         backward_induction_sharded(
             self.T, self.n, self.rank, self.world, self.solver.solve_period_async, self.V,
-            self.dist.all_gather_into_tensor if self.world > 1 else None)
+            self.dist.all_gather_into_tensor if self.world > 1 else None, self.exchange)
 
     def close(self):
         self.solver.close()

@@ -101,6 +101,12 @@ class Solver:
         self._check(self.lib.sdpb_device_tables(self.h, period, C.byref(dv), C.byref(dq)))
         return dv.value, dq.value
 
+    def shard_reads(self):
+        """[lo, hi) of the flattened V_{t+1} this shard's kernels may read (multi-GPU halo exchange)."""
+        lo, hi = C.c_int64(), C.c_int64()
+        self._check(self.lib.sdpb_shard_reads(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def state_of_index(self, idx: int):
         st = np.empty(self.ndim)
         self._check(self.lib.sdpb_state_of_index(self.h, idx, st.ctypes.data_as(C.POINTER(C.c_double))))

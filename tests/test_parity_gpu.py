@@ -335,6 +335,43 @@ def test_sharded_handles_on_one_gpu(case, world, S, oracle):
     assert total == evals
 
 
+@pytest.mark.parametrize("case,world", [(cases.case_A_small, 3), (cases.case_A_gy, 3), (cases.case_B2_small, 4),
+                                        (cases.case_B1_ref, 3), (cases.case_C_int, 3), (cases.case_C_rich, 2),
+                                        (cases.case_D_small, 3), (cases.case_M2_small, 3), (cases.case_W_small, 2),
+                                        (cases.case_XR_small, 2)], ids=lambda x: getattr(x, "__name__", str(x))[5:])
+def test_halo_exchange_ranges_on_one_gpu(case, world, S, oracle):
+    """sdpb_shard_reads: each rank is given ONLY the rows of V_{t+1} it declared (everything else in its table
+    is NaN) and must still produce the oracle's block; the host mirror of the range agrees with the library."""
+    import torch
+    par = S.package.parallel
+    spec, _ = case()
+    Vo, Qo, _, _ = oracle.dense(spec)
+    n = Vo.shape[1]
+    hs = [S.Solver(spec, shard_rank=r, shard_count=world) for r in range(world)]
+    bounds = [par.shard_bounds(n, r, world) for r in range(world)]
+    chunk = bounds[0][2]
+    needs = [h.shard_reads() for h in hs]
+    for r, (lo, hi, _) in enumerate(bounds):
+        assert needs[r] == par.needed_range(spec, lo, hi, n), (r, needs[r])
+    for t in range(spec.T, 0, -1):
+        tabs = [par.wrap_device(torch, h.device_tables(t)[0], chunk * world, "<f8", 0) for h in hs]
+        for tab in tabs:
+            tab.fill_(float("nan"))
+        torch.cuda.synchronize()
+        for h in hs:
+            h.solve_period_async(t)
+        for h in hs:
+            h.sync()
+        for r, (lo, hi, _) in enumerate(bounds):       # what HaloExchange sends: overlap(block[r], needs[r2])
+            for r2 in range(world):
+                a, b = max(lo, needs[r2][0]), min(hi, needs[r2][1])
+                if r2 != r and b > a:
+                    tabs[r2][a:b].copy_(tabs[r][a:b])
+        torch.cuda.synchronize()
+        for r, (lo, hi, _) in enumerate(bounds):
+            assert np.array_equal(tabs[r][lo:hi].cpu().numpy(), Vo[t - 1][lo:hi]), (r, t)
+
+
 def test_large_sharded_c5_on_one_gpu(S, oracle):
     """tiled2 with shard boundaries that cut through 1021-state tiles."""
     import torch

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, case_name, out_dir):
+def _worker(rank, world, port, case_name, out_dir, mode):
     for p in (ROOT, os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -37,24 +37,39 @@ def _worker(rank, world, port, case_name, out_dir):
         full[t - 1][lo:hi] = torch.from_numpy(v)
         Q[t - 1, lo:hi] = q
 
-    par.backward_induction_sharded(spec.T, n, rank, world, solve_block, full, dist.all_gather_into_tensor)
-    np.savez(os.path.join(out_dir, f"r{rank}.npz"), V=torch.stack(full).numpy()[:, :n], Q=Q, lo=lo, hi=hi)
+    exchange, need = None, (0, n)
+    if mode == "halo":
+        need = par.needed_range(spec, lo, hi, n)
+        needs = par.gather_needs(torch, dist, world, need)
+        assert needs == [par.needed_range(spec, *par.shard_bounds(n, r, world)[:2], n) for r in range(world)]
+        exchange = par.HaloExchange(dist, rank, world, n, needs)
+    par.backward_induction_sharded(spec.T, n, rank, world, solve_block, full, dist.all_gather_into_tensor, exchange)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), V=torch.stack(full).numpy()[:, :n], Q=Q, lo=lo, hi=hi,
+             need=np.array(need))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,case_name", [(2, "case_A_small"), (2, "case_C_rich"), (3, "case_B2_small")])
-def test_sharded_schedule_matches_unsharded(world, case_name, tmp_path, oracle):
+@pytest.mark.parametrize("world,case_name,mode", [(2, "case_A_small", "allgather"), (2, "case_C_rich", "allgather"),
+                                                  (3, "case_B2_small", "allgather"), (3, "case_A_gy", "halo"),
+                                                  (3, "case_B2_small", "halo"), (2, "case_C_int", "halo")])
+def test_sharded_schedule_matches_unsharded(world, case_name, mode, tmp_path, oracle):
     import cases
-    port = 29500 + (os.getpid() % 2000) + world
-    mp.start_processes(_worker, args=(world, port, case_name, str(tmp_path)), nprocs=world, join=True,
+    port = 29500 + (os.getpid() % 2000) + world + (7 if mode == "halo" else 0)
+    mp.start_processes(_worker, args=(world, port, case_name, str(tmp_path), mode), nprocs=world, join=True,
                        start_method="spawn")
     spec, _ = getattr(cases, case_name)()
     Vo, Qo, _, _ = oracle.dense(spec)
     covered = np.zeros(Vo.shape[1], dtype=bool)
     for r in range(world):
         g = np.load(tmp_path / f"r{r}.npz")
-        assert np.array_equal(g["V"], Vo)            # every rank ends with every full V_t
         lo, hi = int(g["lo"]), int(g["hi"])
+        a, b = (int(x) for x in g["need"])
+        # every rank ends with the part of every V_t (t >= 2) it reads -- all of it under the all-gather -- and
+        # with its own block of V_1, which nobody else reads
+        assert np.array_equal(g["V"][1:, a:b], Vo[1:, a:b])
+        assert np.array_equal(g["V"][:, lo:hi], Vo[:, lo:hi])
+        if mode == "halo" and (a > 0 or b < Vo.shape[1]):
+            assert np.isnan(g["V"][1:, :a]).all() and np.isnan(g["V"][1:, b:]).all()   # nothing else was sent
         assert np.array_equal(g["Q"][:, lo:hi], Qo[:, lo:hi])
         covered[lo:hi] = True
     assert covered.all()
