@@ -377,8 +377,13 @@ def run_gpu(args):
                 nloc = s2.hi - s2.lo
                 Vt = torch.as_tensor(_CAI(dv + 8 * s2.lo, nloc, "<f8"), device=f"cuda:{local}")
                 Qt = torch.as_tensor(_CAI(dq + 4 * s2.lo, nloc, "<i4"), device=f"cuda:{local}")
-                V1 = Vt.cpu()
-                Q1 = Qt.cpu()
+                if host_v is None:  # this rank's block of the result tables, page-locked
+                    host_v = torch.empty(nloc, dtype=torch.float64).pin_memory()
+                    host_q = torch.empty(nloc, dtype=torch.int32).pin_memory()
+                host_v.copy_(Vt, non_blocking=True)
+                host_q.copy_(Qt, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                V1, Q1 = host_v, host_q
                 d2h = nloc * 12
             npmf = sum(len(r) for r in spec.pmf)
             h2d = npmf * 28 + spec.T * 32
