@@ -141,6 +141,158 @@ def test_python_transliteration_family_C(oracle):
         assert cv[key] == r[-1] and ca[key] == r[-2]
 
 
+def test_python_transliteration_family_B(oracle):
+    """Leadtime.java:50-81 lambdas (lead time 1, transition NOT clamped) under LeadtimeRecursion.java:47-75."""
+    spec, init = cases.case_B1_ref()
+    K, v, h, pi = spec.fixed_cost, spec.vari_cost, spec.hold_cost, spec.penalty_cost
+
+    def actions(s):  # Leadtime.java:50-58
+        return [float(i) for i in range(spec.max_order_idx + 1)]
+
+    def f(s, a, d):  # Leadtime.java:61-68: (t+1, x + preQ - d, a)
+        return (s[0] + 1, s[1] + s[2] - d, a)
+
+    def c(s, a, d):  # Leadtime.java:71-81
+        fixed = K if a > 0 else 0
+        variable = v * a
+        lvl = s[1] + s[2] - d
+        return fixed + variable + h * max(lvl, 0) + pi * max(-lvl, 0)
+
+    pmf = [[(float(d), float(p)) for d, p in row] for row in spec.pmf]
+    get, cv, ca = _py_recursion(pmf, actions, f, c, True)
+    val = get((1, 0.0, 0.0))
+    rows, iv, _ = oracle.topdown(spec, init)
+    assert val == iv[0]
+    assert len(rows) == len(cv)
+    for r in rows:
+        key = (int(r[0]), r[1], r[2])
+        assert cv[key] == r[-1] and ca[key] == r[-2]
+
+
+@pytest.mark.parametrize("case", [cases.case_D_small, cases.case_D_rich], ids=["D_small", "D_rich"])
+def test_python_transliteration_family_D(case, oracle):
+    """CashOverdraft.java:72-118 lambdas (four-branch interest, round(w*10)/10 with LONG division -- or the
+    /10.0 variant) under CashRecursion.java:79-140 (MAX, discount factor)."""
+    from sdpb200 import abi as A
+    spec, init = case()
+    P, T = spec, spec.T
+
+    def actions(s):  # CashOverdraft.java:72-75
+        return [float(i) for i in range(P.max_order_idx + 1)]
+
+    def c(s, a, d):  # CashOverdraft.java:80-103
+        revenue = P.price * min(s[1] + a, d)
+        fixed = P.fixed_cost if a > 0 else 0
+        variable = P.vari_cost * a
+        lvl = s[1] + a - d
+        before = s[2] - fixed - variable - P.overhead_t[s[0] - 1]
+        if before >= 0:
+            interest = -P.r0 * before
+        elif before >= -P.interest_free:
+            interest = 0
+        elif before >= -P.od_limit:
+            interest = P.r2 * (-before - P.interest_free)
+        else:
+            interest = P.r3 * (-before - P.od_limit) + P.r2 * (P.od_limit - P.interest_free)
+        after = before - interest + revenue
+        inc = after - s[2]
+        inc += P.salvage * max(lvl, 0) if s[0] == T else 0
+        return inc
+
+    def jround(x):  # Math.round
+        r = math.floor(x)
+        return int(r) + (1 if x - r >= 0.5 else 0)
+
+    def jdiv(a, b):  # Java long division truncates toward zero
+        q = abs(a) // abs(b)
+        return q if (a >= 0) == (b > 0) else -q
+
+    def f(s, a, d):  # CashOverdraft.java:106-118
+        nx = max(0, s[1] + a - d)
+        nw = s[2] + c(s, a, d)
+        nw = P.cash_max if nw > P.cash_max else nw
+        nw = P.cash_min if nw < P.cash_min else nw
+        nx = P.inv_max if nx > P.inv_max else nx
+        nx = P.inv_min if nx < P.inv_min else nx
+        k = jround(nw * P.q_mul)
+        nw = float(jdiv(k, int(P.q_div))) if P.quantiser == A.Q_LONGDIV else k / P.q_div
+        return (s[0] + 1, float(nx), nw)
+
+    pmf = [[(float(d), float(p)) for d, p in row] for row in spec.pmf]
+    get, cv, ca = _py_recursion(pmf, actions, f, c, False, gamma=P.gamma)
+    vals = [get((1, float(i[0]), float(i[1]))) for i in init]
+    rows, iv, _ = oracle.topdown(spec, init)
+    assert vals == list(iv)
+    assert len(rows) == len(cv)
+    for r in rows:
+        key = (int(r[0]), r[1], r[2])
+        assert cv[key] == r[-1] and ca[key] == r[-2]
+
+
+def test_python_transliteration_family_F(oracle):
+    """cashSurvival.java:102-147 lambdas under RiskRecursion.getSurvProb (RiskRecursion.java:64-108): survival
+    indicator in the last period, successors with negative cash count as ruin without being expanded."""
+    spec, init = cases.case_F_small()
+    P, T = spec, spec.T
+    pmf = [[(float(d), float(p)) for d, p in row] for row in spec.pmf]
+
+    def actions(s):  # cashSurvival.java:102-109 (bankruptBefore states are never expanded)
+        maxq = max(min(s[2] / P.vari_cost_t[s[0] - 1], P.max_order_idx), 0)
+        return [float(i) for i in range(int(maxq) + 1)]
+
+    def c(s, a, d):  # cashSurvival.java:115-128
+        t = s[0] - 1
+        revenue = P.price_t[t] * min(s[1] + a, d)
+        fixed = P.fixed_cost if a > 0 else 0
+        variable = P.vari_cost_t[t] * a
+        deposite = (s[2] - fixed - variable) * (1 + P.deposit_rate)
+        lvl = s[1] + a - d
+        hold = P.hold_cost * max(lvl, 0)
+        inc = revenue + deposite - hold - P.overhead_t[t] - s[2]
+        inc += P.salvage * max(lvl, 0) if s[0] == T else 0
+        return inc
+
+    def jround(x):
+        r = math.floor(x)
+        return int(r) + (1 if x - r >= 0.5 else 0)
+
+    def f(s, a, d):  # cashSurvival.java:131-146
+        nx = max(0, s[1] + a - d)
+        nw = s[2] + c(s, a, d)
+        nw = P.cash_max if nw > P.cash_max else nw
+        nw = P.cash_min if nw < P.cash_min else nw
+        nx = P.inv_max if nx > P.inv_max else nx
+        nx = P.inv_min if nx < P.inv_min else nx
+        return (s[0] + 1, float(nx), float(jround(nw * 1) // 1))
+
+    cv, ca = {}, {}
+
+    def surv(s):  # RiskRecursion.java:64-108
+        if s in cv:
+            return cv[s]
+        val, best = -sys_float_max, 0.0
+        for a in actions(s):
+            q = 0.0
+            for d, p in pmf[s[0] - 1]:
+                if s[0] == T:
+                    q += p * (1 if s[2] + c(s, a, d) >= 0 else 0)
+                else:
+                    n = f(s, a, d)
+                    q += p * (0 if n[2] < 0 else surv(n))
+            if q > val:
+                val, best = q, a
+        cv[s], ca[s] = val, best
+        return val
+
+    vals = [surv((1, float(i[0]), float(i[1]))) for i in init]
+    rows, iv, _ = oracle.topdown(spec, init)
+    assert vals == list(iv)
+    assert len(rows) == len(cv)
+    for r in rows:
+        key = (int(r[0]), r[1], r[2])
+        assert cv[key] == r[-1] and ca[key] == r[-2]
+
+
 # ---- (3) closed forms ---------------------------------------------------------------------------
 def test_closed_form_twopoint(oracle):
     # demand 4 or 10 (p = 1/2), h = pi = 1, no ordering cost: any order-up-to level in [4,10] costs
