@@ -293,6 +293,63 @@ def test_python_transliteration_family_F(oracle):
         assert cv[key] == r[-1] and ca[key] == r[-2]
 
 
+def test_python_transliteration_family_XR(oracle):
+    """CashConstraintXR.java:68-110 lambdas under CashRecursionXR.java:79-125: state (t, x, R = cash + v x), the
+    action is the order-up-to level.  The dense grid caps the number of levels per state (`max_order_idx`,
+    DESIGN.md a11); the transliteration applies the same cap and counts how often it binds."""
+    spec, init = cases.case_XR_small()
+    spec.max_order_idx = 46  # >= cash_max / v + 1 levels: the cap can never bind, as in the uncapped reference
+    P, T = spec, spec.T
+    binds = [0]
+
+    def actions(s):  # CashConstraintXR.java:69-73
+        max_y = s[1] if s[2] / P.vari_cost < s[1] else s[2] / P.vari_cost
+        length = int(max_y - s[1]) + 1
+        if length > P.max_order_idx + 1:
+            binds[0] += 1
+            length = P.max_order_idx + 1
+        return [s[1] + float(i) for i in range(length)]
+
+    def c(s, y, d):  # CashConstraintXR.java:76-89
+        revenue = P.price * min(y, d)
+        action = y - s[1]
+        fixed = P.fixed_cost if y > s[1] else 0
+        variable = P.vari_cost * action
+        init_cash = s[2] - P.vari_cost * s[1]
+        deposite = (init_cash - fixed - variable) * (1 + P.deposit_rate)
+        lvl = y - d
+        hold = P.hold_cost * max(lvl, 0)
+        inc = (1 - P.overhead_rate) * revenue + deposite - hold - P.overhead - init_cash
+        inc += P.salvage * max(lvl, 0) if s[0] == T else 0
+        return inc
+
+    def jround(x):
+        r = math.floor(x)
+        return int(r) + (1 if x - r >= 0.5 else 0)
+
+    def f(s, y, d):  # CashConstraintXR.java:92-109
+        nx = max(0, y - d)
+        init_cash = s[2] - P.vari_cost * s[1]
+        nw = init_cash + c(s, y, d)
+        nw = P.cash_max if nw > P.cash_max else nw
+        nw = P.cash_min if nw < P.cash_min else nw
+        nx = P.inv_max if nx > P.inv_max else nx
+        nx = P.inv_min if nx < P.inv_min else nx
+        nw = float(jround(nw * 1) // 1)
+        return (s[0] + 1, float(nx), nw + P.vari_cost * nx)
+
+    pmf = [[(float(d), float(p)) for d, p in row] for row in spec.pmf]
+    get, cv, ca = _py_recursion(pmf, actions, f, c, False, gamma=P.gamma)
+    vals = [get((1, float(i[0]), float(i[1]))) for i in init]
+    rows, iv, _ = oracle.topdown(spec, init)
+    assert vals == list(iv)
+    assert len(rows) == len(cv)
+    for r in rows:
+        key = (int(r[0]), r[1], r[2])
+        assert cv[key] == r[-1] and ca[key] == r[-2]
+    assert binds[0] == 0  # the cap never bound on this instance: the comparison is with the uncapped reference
+
+
 # ---- (3) closed forms ---------------------------------------------------------------------------
 def test_closed_form_twopoint(oracle):
     # demand 4 or 10 (p = 1/2), h = pi = 1, no ordering cost: any order-up-to level in [4,10] costs
