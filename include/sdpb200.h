@@ -212,6 +212,9 @@ typedef enum sdpb_kernel_choice {
                                  model is not folded */
     SDPB_KERNEL_TWO_PRODUCT_ROW = 10, /* reported only: two-product kernel that shares the cash-independent terms
                                          of an (action, demand) pair across a row of cash levels (integer prices) */
+    SDPB_KERNEL_FUSED = 11,   /* the whole horizon of a small 1-D inventory model in one cooperative launch (one CTA
+                                 per SM, grid-wide barrier between periods); sdpb_solve / sdpb_solve_async only;
+                                 AUTO picks it when the grid has at most 64 states per SM */
     SDPB_KERNEL_TILED2 = 5    /* 2-D register-tile variant of the tiled kernel: chosen automatically for
                                  large grids; as a request it forces the variant wherever it applies */
 } sdpb_kernel_choice;

@@ -19,6 +19,7 @@
 #include "kernel_cash.cuh"
 #include "kernel_two_product.cuh"
 #include "kernel_staff.cuh"
+#include "kernel_fused.cuh"
 #include "microbench.cuh"
 
 using namespace sdpb;
@@ -72,6 +73,8 @@ struct sdpb_handle {
     sdpb_stats stats{};
     TiledPlan tiled{};
     CashPlan cash{};
+    FusedPlan fused{};
+    int sm_count = 0;
     int solve_count = 0;
     cudaGraphExec_t graph_exec = nullptr;  // the T launches of one solve, captured on the second solve
     bool graph_failed = false;
@@ -842,6 +845,26 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     if ((h->opt.kernel == SDPB_KERNEL_TILED || h->opt.kernel == SDPB_KERNEL_TILED2) && !h->tiled.available &&
         !(m->cost_kind == SDPB_COST_BACKORDER && m->lead_time >= 1) && !h->cash.available)
         return fail_create(h, SDPB_ERR_ARG, std::string("no shared-memory kernel for this model: ") + h->tiled.why_not);
+    h->sm_count = sm_count;
+    if (h->opt.kernel == SDPB_KERNEL_AUTO || h->opt.kernel == SDPB_KERNEL_FUSED) {
+        plan_fused(h->fused, h->m, h->dm, h->pmf_len, h->pmf_off, pdi, sm_count, h->opt.shard_count);
+        // AUTO: the fused kernel trades arithmetic efficiency (5 fp64 instructions per evaluation, one CTA per SM)
+        // for having no per-period launch, window-merge or action-split overhead; measured against the tiled
+        // path (tools/time_small_grids.py) it wins on grids of up to ~1500 states and on short action lists
+        if (h->opt.kernel == SDPB_KERNEL_AUTO &&
+            !(h->S <= 1500 || (double)h->S * (m->max_order_idx + 1) <= 1.1e5))
+            h->fused.ok = false;
+        if (h->fused.ok) {
+            std::vector<int> off(h->pmf_off.begin(), h->pmf_off.begin() + T);
+            if (upload(h, h->pmf_len, &h->fused.d_len) != SDPB_OK || upload(h, off, &h->fused.d_off) != SDPB_OK ||
+                upload(h, h->fused.dimax, &h->fused.d_dimax) != SDPB_OK ||
+                upload(h, h->dV, &h->fused.d_V) != SDPB_OK || upload(h, h->dQ, &h->fused.d_Q) != SDPB_OK)
+                return fail_create(h, SDPB_ERR_NOMEM, "allocation of the fused-solve tables failed");
+        }
+    }
+    if (h->opt.kernel == SDPB_KERNEL_FUSED && !h->fused.ok)
+        return fail_create(h, SDPB_ERR_ARG, "SDPB_KERNEL_FUSED needs an unsharded lead-0 backorder model with the "
+                                            "inventory clamp, no G(y) pass and at most 64 states per SM");
     mark("planned");
     *out = h;
     return SDPB_OK;
@@ -902,9 +925,50 @@ int sdpb_sync(sdpb_handle* h) {
     return SDPB_OK;
 }
 
+// The whole horizon in one cooperative launch (kernel_fused.cuh).  SDPB_ERR_STATE: not launched, use the
+// per-period path.
+static int enqueue_fused(sdpb_handle* h) {
+    FusedPlan& P = h->fused;
+    FusedArgs a;
+    a.T = h->m.T; a.A = h->m.max_order_idx + 1; a.BX = P.BX; a.WN = P.WN; a.Dmax = P.Dmax;
+    a.len = P.d_len; a.off = P.d_off; a.di_max = P.d_dimax; a.V = P.d_V; a.Q = P.d_Q;
+    void* fn = h->dm.is_min ? (void*)bi_inv_fused<true> : (void*)bi_inv_fused<false>;
+    if (P.smem > 48 * 1024 &&
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem) != cudaSuccess) {
+        cudaGetLastError();
+        return SDPB_ERR_STATE;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kFusedThreads, P.smem) != cudaSuccess ||
+        (long long)per_sm * h->sm_count < P.grid) {
+        cudaGetLastError();
+        return SDPB_ERR_STATE;  // the grid barrier needs every CTA resident
+    }
+    void* args[] = {(void*)&h->dm, (void*)&a};
+    if (cudaLaunchCooperativeKernel(fn, dim3((unsigned)P.grid), dim3(kFusedThreads), args, P.smem, h->stream) != cudaSuccess) {
+        cudaGetLastError();
+        return SDPB_ERR_STATE;
+    }
+    std::fill(h->solved.begin(), h->solved.end(), 1);
+    h->stats.launches = 1;
+    h->stats.kernel_used = SDPB_KERNEL_FUSED;
+    for (int t = 1; t <= h->m.T; t++) {
+        const double ev = count_evals_period(h, t);
+        h->stats.evals += ev;
+        h->stats.evals_executed += ev;
+        h->stats.fp64_ops += ev * (t == h->m.T ? 3.0 : 5.0);
+    }
+    return SDPB_OK;
+}
+
 static int enqueue_all_periods(sdpb_handle* h) {
     std::fill(h->solved.begin(), h->solved.end(), 0);
     h->stats = sdpb_stats{};
+    if (h->fused.ok) {
+        const int rc = enqueue_fused(h);
+        if (rc != SDPB_ERR_STATE) return rc;
+        h->fused.ok = false;  // cannot be launched cooperatively here: per-period launches from now on
+    }
     for (int t = h->m.T; t >= 1; t--) {
         int rc = solve_period(h, t);
         if (rc != SDPB_OK) return rc;
@@ -926,7 +990,7 @@ int sdpb_solve_async(sdpb_handle* h) {
         CU(cudaGraphLaunch(h->graph_exec, h->stream));
         return SDPB_OK;
     }
-    if (h->solve_count >= 1 && !h->graph_failed) {
+    if (h->solve_count >= 1 && !h->graph_failed && !h->fused.ok) {  // (a fused solve is one launch already)
         // second solve: every scratch buffer exists by now, so the launches can be captured
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {

@@ -96,7 +96,7 @@ def make_model(family, rng):
 
 
 FAMILIES = ["A", "B", "C", "Cint", "F", "Fint", "D", "E", "XR", "M2"]
-KERNELS = {"A": (S.KERNEL_AUTO, S.KERNEL_GENERIC, S.KERNEL_TILED, S.KERNEL_TILED2),
+KERNELS = {"A": (S.KERNEL_AUTO, S.KERNEL_GENERIC, S.KERNEL_TILED, S.KERNEL_TILED2, S.KERNEL_FUSED),
            "B": (S.KERNEL_AUTO, S.KERNEL_GENERIC, S.KERNEL_STAGED, S.KERNEL_LEAD_SLAB, S.KERNEL_LEAD_COL, S.KERNEL_LEAD_Q2),
            "Cint": (S.KERNEL_AUTO, S.KERNEL_GENERIC, S.KERNEL_CASH_INT),
            "Fint": (S.KERNEL_AUTO, S.KERNEL_GENERIC, S.KERNEL_CASH_INT)}

@@ -181,7 +181,61 @@ def test_staged_kernel_is_used_for_leadtime(S):
     assert S.Solver(spec, kernel=S.KERNEL_STAGED).solve().stats()["kernel_used"] == S.KERNEL_STAGED
     assert S.Solver(spec, kernel=S.KERNEL_GENERIC).solve().stats()["kernel_used"] == S.KERNEL_GENERIC
     spec, _ = cases.case_A_small()
-    assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_TILED  # small grid: 1-D tile variant
+    assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_FUSED  # small grid: the whole horizon in one launch
+    assert S.Solver(spec, kernel=S.KERNEL_TILED).solve().stats()["kernel_used"] == S.KERNEL_TILED
+
+
+@pytest.mark.parametrize("case", A_CASES, ids=lambda f: f.__name__[5:])
+def test_fused_whole_horizon_kernel(case, S, oracle):
+    """bi_inv_fused: one cooperative launch for all periods (small unsharded 1-D grids).  Whole grid against the
+    oracle, repeated solves, and the per-period API (which keeps using the per-period kernels) on the same handle."""
+    spec, init = case()
+    Vo, Qo, evals, _ = oracle.dense(spec)
+    if spec.flags & S.abi.F_GY_MODE:
+        with pytest.raises(S.SdpbError):
+            S.Solver(spec, kernel=S.KERNEL_FUSED)
+        return
+    s, V, Q = _solve_all(S, spec, kernel=S.KERNEL_FUSED)
+    st = s.stats()
+    assert st["kernel_used"] == S.KERNEL_FUSED and st["launches"] == 1 and st["evals"] == evals
+    assert np.array_equal(V, Vo) and np.array_equal(Q, Qo)
+    for _ in range(2):
+        s.solve()
+        V1, Q1 = s.period_tables(1)
+        assert np.array_equal(V1, Vo[0]) and np.array_equal(Q1, Qo[0])
+    for t in range(spec.T, 0, -1):
+        s.solve_period_async(t)
+    s.sync()
+    V1, Q1 = s.period_tables(1)
+    assert np.array_equal(V1, Vo[0]) and np.array_equal(Q1, Qo[0])
+
+
+def test_fused_kernel_shapes(S, oracle):
+    """States not a multiple of the CTA slice, more states than SMs (several states per CTA), fewer states than
+    SMs, MAX direction, sparse demand support, action counts around the 8-pair batch and the 32-lane argopt."""
+    rng = np.random.default_rng(3)
+    for n_states, n_act, direction in ((149, 33, S.abi.MIN), (700, 9, S.abi.MAX), (2001, 40, S.abi.MIN), (37, 257, S.abi.MIN),
+                                       (5000, 3, S.abi.MIN)):
+        rows = []
+        for _ in range(3):
+            sup = np.sort(rng.choice(np.arange(0, 14), size=int(rng.integers(2, 9)), replace=False)).astype(float)
+            rows.append(np.column_stack([sup, rng.dirichlet(np.ones(len(sup)))]))
+        half = n_states // 2
+        spec = S.inventory_model(rows, fixed_cost=7, vari_cost=1, hold_cost=1, penalty_cost=6, max_order=n_act - 1,
+                                 inv_min=-half, inv_max=n_states - half - 1, direction=direction)
+        Vo, Qo, evals, _ = oracle.dense(spec)
+        s, V, Q = _solve_all(S, spec, kernel=S.KERNEL_FUSED)
+        assert s.stats()["kernel_used"] == S.KERNEL_FUSED
+        assert np.array_equal(V, Vo) and np.array_equal(Q, Qo), (n_states, n_act)
+    with pytest.raises(S.SdpbError):
+        S.Solver(cases.case_B1_ref()[0], kernel=S.KERNEL_FUSED)
+    # AUTO: C1 (1,001 states) runs fused, C2 (2,001 x 101) stays on the per-period tiled kernel; same tables either way
+    assert S.Solver(S.configs.c1()).solve().stats()["kernel_used"] == S.KERNEL_FUSED
+    spec = S.configs.c2()
+    a, Va, Qa = _solve_all(S, spec)
+    f, Vf, Qf = _solve_all(S, spec, kernel=S.KERNEL_FUSED)
+    assert a.stats()["kernel_used"] == S.KERNEL_TILED and f.stats()["kernel_used"] == S.KERNEL_FUSED
+    assert np.array_equal(Va, Vf) and np.array_equal(Qa, Qf)
 
 
 @pytest.mark.parametrize("name", cases.GOLDEN)
