@@ -32,6 +32,8 @@ struct DevModel {
     double reserve2;
     double dr;            // depositeRate itself (CashOverdraftLimit.java:79, TestPaper.java:87)
     int q_from_period;    // SDPB_Q_TRUNC: round with (q_mul, q_div) from this period on; 0 = never
+    int small;            // 1: S and every quantised cash magnitude fit in 31 bits, so the successor index can be
+                          //    formed in 32-bit integer arithmetic (same values, a third of the instructions)
     double price2, v2, salvage2, tie_tol;  // second product / tie tolerance (SDPB_COST_CASH_TWO_PRODUCT)
     const double* pmf_d2;
     const int* pmf_di2;
@@ -60,14 +62,31 @@ __device__ __forceinline__ long long jround(double x) {
     return (long long)r + (diff >= 0.5 ? 1ll : 0ll);
 }
 
-// Java `long / long` (truncation toward zero) by the run-time constant q_idiv.  For |kk| < 2^31 and
-// q_idiv < 2^15, floor(|kk| * ceil(2^47/d) / 2^47) == floor(|kk| / d) exactly (|kk|*d < 2^47), which
-// replaces the ~40-instruction 64-bit division of the overdraft models' quantiser
-// (Math.round(w*10)/10, CashOverdraft.java:116) by two wide multiplies and a shift.
+// The same for |x| < 2^31 (DevModel::small): floor through F2I.S32 instead of the 64-bit conversion sequence.
+__device__ __forceinline__ int jround32(double x) {
+    const int fl = __double2int_rd(x);
+    const double diff = x - (double)fl;
+    return fl + (diff >= 0.5 ? 1 : 0);
+}
+
+// Java `long / long` (truncation toward zero) by the run-time constant q_idiv.  For q_idiv < 2^15 and
+// |kk| < q_idiv * 2^16 (< 2^31), floor(|kk| * ceil(2^47/d) / 2^47) == floor(|kk| / d) exactly (|kk|*d < 2^47)
+// and the 64-bit product cannot overflow (|kk| * magic < d 2^16 (2^47/d + 1) < 2^64), which replaces the
+// ~40-instruction 64-bit division of the overdraft models' quantiser (Math.round(w*10)/10,
+// CashOverdraft.java:116) by two wide multiplies and a shift.  Larger magnitudes take the real division.
 __device__ __forceinline__ long long jdiv(long long kk, long long d, unsigned long long magic) {
     const long long a = kk < 0 ? -kk : kk;
-    if (magic != 0 && a < 2147483648ll) {
+    if (magic != 0 && a < (d << 16)) {
         const long long q = (long long)(((unsigned long long)a * magic) >> 47);
+        return kk < 0 ? -q : q;
+    }
+    return kk / d;
+}
+
+__device__ __forceinline__ int jdiv32(int kk, int d, unsigned long long magic) {
+    const unsigned a = (unsigned)(kk < 0 ? -kk : kk);
+    if (magic != 0 && a < ((unsigned)d << 16)) {
+        const int q = (int)(((unsigned long long)a * magic) >> 47);
         return kk < 0 ? -q : q;
     }
     return kk / d;

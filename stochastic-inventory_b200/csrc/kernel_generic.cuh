@@ -245,6 +245,40 @@ __device__ __forceinline__ long long successor(const DevModel& M, const StateCtx
     return il * S.strideX + A.pipe + kw;
 }
 
+// successor() in 32-bit integer arithmetic for DevModel::small grids (identical results: every quantity is
+// below 2^31 there, checked on the host).
+template <int KIND>
+__device__ __forceinline__ int successor32(const DevModel& M, const StateCtx& S, const ActionCtx& A, int di, double c,
+                                           double after, bool& bankrupt) {
+    int il = A.iy - di;
+    if (S.lost) il = max(il, M.i_zero);
+    il = min(il, M.nI - 1);
+    il = max(il, 0);
+    bankrupt = false;
+    const int strideX = (int)S.strideX, pipe = (int)A.pipe;
+    if (KIND == SDPB_COST_BACKORDER) return il * strideX + pipe;
+    double nw = (KIND == SDPB_COST_CASH_OD_TESTING) ? after : A.initCash + c;
+    nw = nw > M.cash_max ? M.cash_max : nw;
+    nw = nw < M.cash_min ? M.cash_min : nw;
+    int kk, k;
+    if (M.quantiser == SDPB_Q_TRUNC) {
+        if (M.q_from_period > 0 && S.t >= M.q_from_period) nw = (double)jround32(nw * M.q_mul) / M.q_div;
+        kk = k = (int)nw;
+    } else {
+        kk = jround32(nw * M.q_mul);
+        k = (M.quantiser == SDPB_Q_DIV || M.q_idiv == 1) ? kk : jdiv32(kk, (int)M.q_idiv, M.q_magic);
+    }
+    bankrupt = k < 0;
+    if (KIND == SDPB_COST_CASH_XR) {
+        const double nwq = (M.quantiser == SDPB_Q_DIV) ? (double)kk / M.q_div : (double)k;
+        const double nx = M.inv_min + (double)il * M.step;
+        k = jround32(nwq + S.v * nx);
+    }
+    int kw = k - (int)M.kmin;
+    kw = max(min(kw, M.nW - 1), 0);
+    return il * strideX + pipe + kw;
+}
+
 // DEDUP: [lo, hi) indexes virtual states and (Vt, Qt) are the virtual tables H; see expand_dedup.
 template <int KIND, bool SURVIVAL, bool IS_MIN, int G, bool DEDUP>
 __global__ void __launch_bounds__(256)
@@ -265,24 +299,42 @@ bi_generic(const __grid_constant__ DevModel M, const int t, const int D, const i
     double best = IS_MIN ? DBL_MAX : -DBL_MAX;
     int besti = kNoAction;
 
+    const bool small = M.small != 0;
     for (int i = lane; i < S.nA; i += G) {
         const ActionCtx A = prep_action<KIND>(M, S, i);
         double acc = 0.0;
-        for (int j = 0; j < D; j++) {
-            double after;
-            const double c = immediate<KIND>(M, S, A, __ldg(pd + j), after);
-            if (!SURVIVAL) acc += __ldg(pp + j) * c;                  // Recursion.java:139
-            if (S.last) {
-                if (SURVIVAL) {                                       // RiskRecursion.java:80-84
+        if (S.last) {
+            for (int j = 0; j < D; j++) {
+                double after;
+                const double c = immediate<KIND>(M, S, A, __ldg(pd + j), after);
+                if (!SURVIVAL) acc += __ldg(pp + j) * c;                  // Recursion.java:139
+                if (SURVIVAL) {                                           // RiskRecursion.java:80-84
                     const double finalCash = A.initCash + c;
                     acc += __ldg(pp + j) * (finalCash >= 0.0 ? 1.0 : 0.0);
                 }
-            } else {
+            }
+        } else if (small) {
+#pragma unroll 2
+            for (int j = 0; j < D; j++) {
+                double after;
+                const double c = immediate<KIND>(M, S, A, __ldg(pd + j), after);
+                if (!SURVIVAL) acc += __ldg(pp + j) * c;                  // Recursion.java:139
+                bool bankrupt;
+                const int ni = successor32<KIND>(M, S, A, __ldg(pdi + j), c, after, bankrupt);
+                double vn = __ldg(Vn + ni);
+                if (SURVIVAL && bankrupt) vn = 0.0;                       // RiskRecursion.java:87-95
+                acc += __ldg(pg + j) * vn;                                // Recursion.java:142
+            }
+        } else {
+            for (int j = 0; j < D; j++) {
+                double after;
+                const double c = immediate<KIND>(M, S, A, __ldg(pd + j), after);
+                if (!SURVIVAL) acc += __ldg(pp + j) * c;                  // Recursion.java:139
                 bool bankrupt;
                 const long long ni = successor<KIND>(M, S, A, __ldg(pdi + j), c, after, bankrupt);
                 double vn = __ldg(Vn + ni);
-                if (SURVIVAL && bankrupt) vn = 0.0;                   // RiskRecursion.java:87-95
-                acc += __ldg(pg + j) * vn;                            // Recursion.java:142
+                if (SURVIVAL && bankrupt) vn = 0.0;                       // RiskRecursion.java:87-95
+                acc += __ldg(pg + j) * vn;                                // Recursion.java:142
             }
         }
         // ascending i within a lane: strict compare keeps the first optimum (Recursion.java:146-157)

@@ -740,6 +740,16 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     S *= d.nW;
     d.S = S;
     h->S = S;
+    {   // 32-bit successor arithmetic (successor32): every index and quantised cash value below 2^30
+        const double cmax = std::max(std::fabs(m->cash_min), std::fabs(m->cash_max));
+        const double qm = std::max(1.0, std::fabs(m->q_mul));
+        double vmax = std::fabs(m->vari_cost);
+        for (double v : v_t) vmax = std::max(vmax, std::fabs(v));
+        const double xr = m->cost_kind == SDPB_COST_CASH_XR
+                              ? vmax * std::max(std::fabs(m->inv_min), std::fabs(m->inv_max)) : 0.0;
+        d.small = (S < (1ll << 30) && (cmax + xr + 1.0) * qm < 1073741824.0 &&
+                   std::llabs(d.kmin) < (1ll << 30) && d.q_idiv < (1ll << 30)) ? 1 : 0;
+    }
     h->ndim = 1 + (two_product(*m) ? 1 : 0) + (has_cash(*m) ? 1 : 0) + m->lead_time;
     const long long chunk = (S + h->opt.shard_count - 1) / h->opt.shard_count;
     h->Spad = chunk * h->opt.shard_count;
