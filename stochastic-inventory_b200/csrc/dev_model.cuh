@@ -53,6 +53,9 @@ struct DevModel {
     const double* pmf_p;
     const double* pmf_pg;
     const int* pmf_di;
+    // the same four streams interleaved, two 16-byte loads per demand point from one pointer:
+    // pmf_rec[2j] = (d_j, p_j), pmf_rec[2j+1] = (p_j*gamma, d_j/step in the low word)
+    const double2* pmf_rec;
 };
 
 // Math.round(double) -> long: round half up, without forming x + 0.5 (Java >= 7 semantics).

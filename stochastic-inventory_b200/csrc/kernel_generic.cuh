@@ -152,6 +152,11 @@ __device__ __forceinline__ ActionCtx prep_action(const DevModel& M, const StateC
     return A;
 }
 
+// Math.max(x, 0) / Math.min(a, b) for the values that occur here (no NaN; a zero result is +0.0 either way):
+// a compare and a select instead of fmax/fmin's NaN-propagating sequence (10 instructions per call in SASS).
+__device__ __forceinline__ double jmax0(double x) { return x > 0.0 ? x : 0.0; }
+__device__ __forceinline__ double jmin(double a, double b) { return a < b ? a : b; }
+
 // Immediate value c(s,a,d).  `after` receives the end-of-period cash balance for the one kind whose
 // transition uses it directly instead of w + c (CashOverdraftTesting.java:103-111).
 template <int KIND>
@@ -160,37 +165,37 @@ __device__ __forceinline__ double immediate(const DevModel& M, const StateCtx& S
     const double lvl = A.stock - d;
     after = 0.0;
     if (KIND == SDPB_COST_BACKORDER) {
-        const double hold = M.h * fmax(lvl, 0.0);
-        const double pen = M.pen * fmax(-lvl, 0.0);
+        const double hold = M.h * jmax0(lvl);
+        const double pen = M.pen * jmax0(-lvl);
         return (A.fv + hold) + pen;
     }
-    const double revenue = S.price * fmin(A.stock, d);
+    const double revenue = S.price * jmin(A.stock, d);
     if (KIND == SDPB_COST_CASH_OD_LIMIT) {
         // CashOverdraftLimit.java:70-86
-        const double hold = M.h * fmax(lvl, 0.0);
+        const double hold = M.h * jmax0(lvl);
         const double before = (((S.w - A.fixedCost) - A.variableCost) - hold) - S.ovh;
-        const double interest = M.r2 * fmax(-before, 0.0);
-        const double deposite = M.dr * fmax(before, 0.0);
+        const double interest = M.r2 * jmax0(-before);
+        const double deposite = M.dr * jmax0(before);
         const double bal = ((before - interest) + deposite) + revenue;
         double inc = bal - S.w;
-        inc += S.last ? M.salvage * fmax(lvl, 0.0) : 0.0;
+        inc += S.last ? M.salvage * jmax0(lvl) : 0.0;
         return inc;
     }
     if (KIND == SDPB_COST_CASH_OD_TESTING) {
         // CashOverdraftTesting.java:85-99 (and :103-111 for the balance the transition keeps)
-        const double hold = M.h * fmax(lvl, 0.0);
+        const double hold = M.h * jmax0(lvl);
         const double before = (((S.w + revenue) - A.fixedCost) - A.variableCost) - hold;
-        const double interest = M.r2 * fmax(-before, 0.0);
+        const double interest = M.r2 * jmax0(-before);
         after = before - interest;
         return after - S.w;
     }
     if (KIND == SDPB_COST_CASH_LOAN) {
         // TestPaper.java:82-93
-        const double hold = S.last ? 0.0 : M.h * fmax(lvl, 0.0);
-        const double deposites = M.dr * fmax(S.w - A.variableCost, 0.0);
-        const double loanPayed = M.r2 * fmax(A.variableCost - S.w, 0.0);
+        const double hold = S.last ? 0.0 : M.h * jmax0(lvl);
+        const double deposites = M.dr * jmax0(S.w - A.variableCost);
+        const double loanPayed = M.r2 * jmax0(A.variableCost - S.w);
         double inc = (((revenue - A.variableCost) - hold) + deposites) - loanPayed;
-        inc += S.last ? M.salvage * fmax(lvl, 0.0) : 0.0;
+        inc += S.last ? M.salvage * jmax0(lvl) : 0.0;
         return inc;
     }
     double inc;
@@ -198,10 +203,10 @@ __device__ __forceinline__ double immediate(const DevModel& M, const StateCtx& S
         const double after = A.before_minus_interest + revenue;  // CashOverdraft.java:99
         inc = after - A.initCash;
     } else {
-        const double hold = M.h * fmax(lvl, 0.0);
+        const double hold = M.h * jmax0(lvl);
         inc = (((M.one_minus_rho * revenue + A.deposite) - hold) - S.ovh) - A.initCash;
     }
-    const double sal = S.last ? M.salvage * fmax(lvl, 0.0) : 0.0;
+    const double sal = S.last ? M.salvage * jmax0(lvl) : 0.0;
     inc += sal;
     if (KIND == SDPB_COST_CASH_DEPOSIT) {
         const double endCash = A.initCash + inc;  // CashConstraint.java:116-119
@@ -291,50 +296,49 @@ bi_generic(const __grid_constant__ DevModel M, const int t, const int D, const i
     const bool live = idx < hi;  // dead groups still take part in the shuffles below
     const StateCtx S = decode_state<KIND>(M, t, live ? idx : lo, DEDUP);
 
-    const double* __restrict__ pd = M.pmf_d + pmf_off;
-    const double* __restrict__ pp = M.pmf_p + pmf_off;
-    const double* __restrict__ pg = M.pmf_pg + pmf_off;
-    const int* __restrict__ pdi = M.pmf_di + pmf_off;
-
     double best = IS_MIN ? DBL_MAX : -DBL_MAX;
     int besti = kNoAction;
 
     const bool small = M.small != 0;
+    const double2* __restrict__ rec = M.pmf_rec + 2 * (size_t)pmf_off;  // (d, p), (p*gamma, d/step) per demand point
     for (int i = lane; i < S.nA; i += G) {
         const ActionCtx A = prep_action<KIND>(M, S, i);
         double acc = 0.0;
         if (S.last) {
             for (int j = 0; j < D; j++) {
                 double after;
-                const double c = immediate<KIND>(M, S, A, __ldg(pd + j), after);
-                if (!SURVIVAL) acc += __ldg(pp + j) * c;                  // Recursion.java:139
+                const double2 dp = __ldg(rec + 2 * j);
+                const double c = immediate<KIND>(M, S, A, dp.x, after);
+                if (!SURVIVAL) acc += dp.y * c;                           // Recursion.java:139
                 if (SURVIVAL) {                                           // RiskRecursion.java:80-84
                     const double finalCash = A.initCash + c;
-                    acc += __ldg(pp + j) * (finalCash >= 0.0 ? 1.0 : 0.0);
+                    acc += dp.y * (finalCash >= 0.0 ? 1.0 : 0.0);
                 }
             }
         } else if (small) {
 #pragma unroll 2
             for (int j = 0; j < D; j++) {
                 double after;
-                const double c = immediate<KIND>(M, S, A, __ldg(pd + j), after);
-                if (!SURVIVAL) acc += __ldg(pp + j) * c;                  // Recursion.java:139
+                const double2 dp = __ldg(rec + 2 * j), gi = __ldg(rec + 2 * j + 1);
+                const double c = immediate<KIND>(M, S, A, dp.x, after);
+                if (!SURVIVAL) acc += dp.y * c;                           // Recursion.java:139
                 bool bankrupt;
-                const int ni = successor32<KIND>(M, S, A, __ldg(pdi + j), c, after, bankrupt);
+                const int ni = successor32<KIND>(M, S, A, __double2loint(gi.y), c, after, bankrupt);
                 double vn = __ldg(Vn + ni);
                 if (SURVIVAL && bankrupt) vn = 0.0;                       // RiskRecursion.java:87-95
-                acc += __ldg(pg + j) * vn;                                // Recursion.java:142
+                acc += gi.x * vn;                                         // Recursion.java:142
             }
         } else {
             for (int j = 0; j < D; j++) {
                 double after;
-                const double c = immediate<KIND>(M, S, A, __ldg(pd + j), after);
-                if (!SURVIVAL) acc += __ldg(pp + j) * c;                  // Recursion.java:139
+                const double2 dp = __ldg(rec + 2 * j), gi = __ldg(rec + 2 * j + 1);
+                const double c = immediate<KIND>(M, S, A, dp.x, after);
+                if (!SURVIVAL) acc += dp.y * c;                           // Recursion.java:139
                 bool bankrupt;
-                const long long ni = successor<KIND>(M, S, A, __ldg(pdi + j), c, after, bankrupt);
+                const long long ni = successor<KIND>(M, S, A, __double2loint(gi.y), c, after, bankrupt);
                 double vn = __ldg(Vn + ni);
                 if (SURVIVAL && bankrupt) vn = 0.0;                       // RiskRecursion.java:87-95
-                acc += __ldg(pg + j) * vn;                                // Recursion.java:142
+                acc += gi.x * vn;                                         // Recursion.java:142
             }
         }
         // ascending i within a lane: strict compare keeps the first optimum (Recursion.java:146-157)

@@ -792,6 +792,18 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     d.field = tmp;
     UP(price_t, price_t, dp) UP(v_t, v_t, dp) UP(ovh_t, ovh_t, dp) UP(res_t, reserve_t, dp)
     UP(h->pmf_d, pmf_d, dp) UP(h->pmf_p, pmf_p, dp) UP(pg, pmf_pg, dp) UP(pdi, pmf_di, di)
+    {
+        std::vector<double> rec((size_t)4 * NP);
+        for (int j = 0; j < NP; j++) {
+            rec[4 * (size_t)j] = h->pmf_d[j];
+            rec[4 * (size_t)j + 1] = h->pmf_p[j];
+            rec[4 * (size_t)j + 2] = pg[j];
+            const long long bits = (long long)(unsigned)pdi[j];  // read back with __double2loint
+            std::memcpy(&rec[4 * (size_t)j + 3], &bits, sizeof bits);
+        }
+        if ((rc = upload(h, rec, &dp)) != SDPB_OK) return fail_create(h, rc, h->err);
+        d.pmf_rec = reinterpret_cast<const double2*>(dp);
+    }
     if (two_product(*m)) { UP(pd2, pmf_d2, dp) UP(pdi2, pmf_di2, di) }
     if (staff_kind(*m)) {
         const size_t rows = (size_t)T * d.nI;
