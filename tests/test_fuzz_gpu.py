@@ -2,6 +2,8 @@
 dispatcher can pick, plus the generic one) against the CPU oracle, whole grid, bit for bit.  Parameters
 are drawn to hit the awkward corners: non-integer costs, negative cash bounds, zero and huge penalties,
 actions wider than the grid, demand tables with gaps, ties, MIN and MAX, discounting, sharding."""
+import os
+
 import numpy as np
 import pytest
 
@@ -105,7 +107,7 @@ KERNELS = {"A": (S.KERNEL_AUTO, S.KERNEL_GENERIC, S.KERNEL_TILED, S.KERNEL_TILED
 @pytest.mark.parametrize("family", FAMILIES)
 def test_fuzz_family(family, oracle):
     rng = np.random.default_rng(abs(hash(family)) % (2 ** 31) if False else sum(map(ord, family)) * 7919)
-    for it in range(40):
+    for it in range(int(os.environ.get("SDPB_FUZZ_ITERS", "40"))):  # raise for a longer one-off campaign
         spec = make_model(family, rng)
         Vo, Qo, evals, _ = oracle.dense(spec)
         for kernel in KERNELS.get(family, (S.KERNEL_AUTO, S.KERNEL_GENERIC)):
