@@ -503,8 +503,27 @@ def run_gpu(args):
                     v, q = s3.solver.value(1, init)
                     v0, q0 = float(v[0]), float(q[0])
                 tops = fp / (cms * 1e-3) / 1e12 / w
+                verified = None
+                if shard and s3.n <= 20_000_000:
+                    # multi-GPU result check (outside every timed region): each rank re-solves the WHOLE grid by
+                    # itself and compares its own block of V_1 and Q_1, bit for bit, with what the sharded solve
+                    # (real NCCL exchange) left in its tables
+                    import numpy as np
+                    torch.cuda.synchronize()
+                    with S.Solver(sp, device=local, dedup=dedup) as ref:
+                        ref.solve()
+                        Vr, Qr = ref.period_tables(1)
+                        qi = np.rint(Qr / sp.step).astype(np.int64)
+                    dv, dq = s3.solver.device_tables(1)
+                    lo_, hi_ = s3.lo, s3.hi
+                    Vm = torch.as_tensor(_CAI(dv + 8 * lo_, hi_ - lo_, "<f8"), device=f"cuda:{local}").cpu().numpy()
+                    Qm = torch.as_tensor(_CAI(dq + 4 * lo_, hi_ - lo_, "<i4"), device=f"cuda:{local}").cpu().numpy()
+                    ok = bool(np.array_equal(Vm, Vr[lo_:hi_]) and np.array_equal(np.maximum(Qm, 0), qi[lo_:hi_]))
+                    okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{local}")
+                    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+                    verified = bool(int(okt[0]))
                 configs[name_key] = {"solve_ms": cms, "evals": ev, "evals_per_s": ev / (cms * 1e-3),
-                                     "exchange": s3.exchange_kind,
+                                     "exchange": s3.exchange_kind, "verified_vs_unsharded": verified,
                                      "evals_executed": evx, "n_gpus": w, "kernel": KERNEL_NAMES.get(kused),
                                      "dedup": dedup, "fp64_tops_per_gpu": tops, "V1_init": v0, "Q1_init": q0}
                 s3.close()
