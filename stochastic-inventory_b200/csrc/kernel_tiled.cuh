@@ -523,7 +523,9 @@ inline int launch_tiled(TiledPlan& P, const DevModel& dm, int t, int D, int pmf_
 
     // the 2-D register tile pays off once there are enough 1021-state tiles to fill the machine
     const long long tiles2 = (n + kT2BX - 1) / kT2BX;
-    const bool use2 = tp.ok2 && (P.variant == 2 || (P.variant == 0 && tiles2 >= 2LL * P.sm_count) || !tp.ok);
+    // measured on C5 (200 x 200): the 2-D register tile (with its action split) wins from ~64 tiles on
+    // (S = 1e5: 3.36 vs 4.02 ms, 2e5: 6.8 vs 8.0, 3e5: 9.0 vs 11.9) and is level at 3e4 (1.40 vs 1.37)
+    const bool use2 = tp.ok2 && (P.variant == 2 || (P.variant == 0 && tiles2 >= 64) || !tp.ok);
     if (use2) {
         int nsplit = 1;
         if (tiles2 < target / 2) nsplit = (int)std::min<long long>(P.n_chunks2, (target / 2 + tiles2 - 1) / tiles2);
