@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -528,7 +529,11 @@ inline int launch_tiled(TiledPlan& P, const DevModel& dm, int t, int D, int pmf_
     const bool use2 = tp.ok2 && (P.variant == 2 || (P.variant == 0 && tiles2 >= 64) || !tp.ok);
     if (use2) {
         int nsplit = 1;
-        if (tiles2 < target / 2) nsplit = (int)std::min<long long>(P.n_chunks2, (target / 2 + tiles2 - 1) / tiles2);
+        // enough CTAs for ~8 waves of 2 CTAs per SM: a grid of a few waves loses its last, partial one
+        // (measured, C5: S = 1e6 32.9 -> 30.0 ms, S = 1e5 3.36 -> 3.17 ms; no change at 3e5 and 3e6)
+        long long want = 16LL * P.sm_count;
+        if (const char* e = std::getenv("SDPB_T2_WAVES")) want = std::max(1, std::atoi(e)) * 2LL * P.sm_count;  // tuning knob
+        if (tiles2 < want) nsplit = (int)std::min<long long>(P.n_chunks2, (want + tiles2 - 1) / tiles2);
         const int cps = (P.n_chunks2 + nsplit - 1) / nsplit;
         nsplit = (P.n_chunks2 + cps - 1) / cps;
         int rc = tiled_scratch(P, tiles2, nsplit, kT2BX, stream);
