@@ -85,3 +85,29 @@ def test_shard_bounds_cover_and_pad(S):
                 assert a[1] == b[0]
             chunk = pieces[0][2]
             assert chunk * world >= n and all(p[1] - p[0] <= chunk for p in pieces)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_needed_range_is_sufficient_for_every_case(world, S, oracle):
+    """The host mirror of sdpb_shard_reads, for every case of the suite: a block solved from a V_{t+1} that is NaN
+    outside its declared range equals the unsharded solve (no process group needed: the oracle plays the kernel)."""
+    import cases
+    import oracle_lib as O
+    par = S.package.parallel
+    for case in cases.ALL:
+        spec, _ = case()
+        Vo, Qo, _, _ = oracle.dense(spec)
+        n = Vo.shape[1]
+        for r in range(world):
+            lo, hi, _ = par.shard_bounds(n, r, world)
+            if hi <= lo:
+                assert par.needed_range(spec, lo, hi, n) == (0, 0)
+                continue
+            a, b = par.needed_range(spec, lo, hi, n)
+            assert 0 <= a < b <= n
+            idx = np.arange(lo, hi, dtype=np.int64)
+            for t in range(spec.T - 1, 0, -1):   # periods that read a successor table
+                vn = np.full(n, np.nan)
+                vn[a:b] = Vo[t][a:b]
+                v, q = O.step_states(spec, t, vn, idx)
+                assert np.array_equal(v, Vo[t - 1][lo:hi]) and np.array_equal(q, Qo[t - 1][lo:hi]), (spec.name, r, t)
