@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "dev_model.cuh"
+#include "kernel_generic.cuh"  // decode_state, prep_action, jmax0 / jmin
 #include "kernel_lead.cuh"  // lds_double, lds_double2
 
 namespace sdpb {
@@ -503,6 +504,137 @@ inline int launch_cash_diag(const CashPlan& P, const sdpb_model& m, const DevMod
 #undef SDPB_DIAG_LAUNCH
     if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
     if (fp64_ops) *fp64_ops += evals * (surv ? 2.0 : 3.0 + 2.0 / kDiagYT);
+    return SDPB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bi_cash_row — the cash-constraint family on ANY cash grid (fractional quantisers included), with the
+// terms that do not depend on the cash level hoisted out of the thread.
+//
+// bi_generic evaluates the whole lambda per (state, action, demand): ~85 instructions per evaluation, and the
+// lanes of a warp (consecutive cash levels of ONE inventory level) recompute identical revenue, holding cost,
+// salvage and successor-row values.  Here a CTA is one inventory level x 128 cash levels; per action the CTA
+// tabulates, one demand point per thread and with the reference's own double arithmetic
+// (CashConstraint.java:103-121 via immediate<>'s expressions),
+//     (1-rho)*price*min(y,d),  h*max(y-d,0),  salvage*max(y-d,0),  p,  p*gamma,  successor row offset,
+// and a thread then only runs the cash-dependent tail of the lambda -- the deposit chain, the bankruptcy
+// penalty, the clamp and the quantiser -- exactly as immediate<> / successor32<> write it.  Same operations in
+// the same order on the same operands: bit-identical to bi_generic.
+struct CashRowEntry {
+    double rev1, hold, sal, p, pg;
+    int row, pad;
+};
+
+template <bool SURVIVAL, bool IS_MIN>
+__global__ void __launch_bounds__(128)
+bi_cash_row(const __grid_constant__ DevModel M, const int t, const int D, const int pmf_off,
+            const double* __restrict__ Vn, double* __restrict__ Vt, int* __restrict__ Qt,
+            const long long lo, const long long hi, const long long row0, const int segs) {
+    constexpr int KIND = SDPB_COST_CASH_DEPOSIT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CashRowEntry* TB = reinterpret_cast<CashRowEntry*>(smem_raw);
+    const int seg = (int)(blockIdx.x % segs);
+    const long long ixl = row0 + blockIdx.x / segs;
+    const int iw = min(seg * 128 + (int)threadIdx.x, M.nW - 1);
+    const long long idx = ixl * M.nW + iw;
+    const bool valid = seg * 128 + (int)threadIdx.x < M.nW && idx >= lo && idx < hi;
+    const StateCtx S = decode_state<KIND>(M, t, idx);
+    // the richest lane of the CTA has the longest action list (the cash bound of CashConstraint.java:96-99 grows with w)
+    const StateCtx Stop = decode_state<KIND>(M, t, ixl * M.nW + min(seg * 128 + 127, M.nW - 1));
+    const int nA_cta = Stop.nA;
+    const double2* __restrict__ rec = M.pmf_rec + 2 * (size_t)pmf_off;
+
+    double best = IS_MIN ? DBL_MAX : -DBL_MAX;
+    int besti = kNoAction;
+    for (int i = 0; i < nA_cta; i++) {
+        const ActionCtx A = prep_action<KIND>(M, S, i);  // per lane: deposite depends on w
+        __syncthreads();  // the previous action's table is no longer read
+        for (int j = threadIdx.x; j < D; j += 128) {
+            const double2 dp = __ldg(rec + 2 * j), gi = __ldg(rec + 2 * j + 1);
+            const double d = dp.x;
+            const double lvl = A.stock - d;                       // stock = x + a: the same for every lane
+            const double revenue = S.price * jmin(A.stock, d);
+            CashRowEntry e;
+            e.rev1 = M.one_minus_rho * revenue;
+            e.hold = M.h * jmax0(lvl);
+            e.sal = S.last ? M.salvage * jmax0(lvl) : 0.0;
+            e.p = dp.y;
+            e.pg = gi.x;
+            int il = A.iy - __double2loint(gi.y);
+            if (S.lost) il = max(il, M.i_zero);
+            il = min(il, M.nI - 1);
+            il = max(il, 0);
+            e.row = il * (int)S.strideX;
+            e.pad = 0;
+            TB[j] = e;
+        }
+        __syncthreads();
+        if (!valid || i >= S.nA) continue;
+        double acc = 0.0;
+        for (int j = 0; j < D; j++) {
+            const CashRowEntry e = TB[j];
+            double inc = (((e.rev1 + A.deposite) - e.hold) - S.ovh) - A.initCash;  // CashConstraint.java:110
+            inc += e.sal;
+            const double endCash = A.initCash + inc;                               // CashConstraint.java:116-119
+            if (endCash < 0.0) inc += M.pen * endCash;
+            if (!SURVIVAL) acc += e.p * inc;                                       // CashRecursion.java:117
+            if (S.last) {
+                if (SURVIVAL) {                                                    // RiskRecursion.java:80-84
+                    const double finalCash = A.initCash + inc;
+                    acc += e.p * (finalCash >= 0.0 ? 1.0 : 0.0);
+                }
+            } else {
+                // successor32<> from the clamp on (CashConstraint.java:125-131)
+                double nw = A.initCash + inc;
+                nw = nw > M.cash_max ? M.cash_max : nw;
+                nw = nw < M.cash_min ? M.cash_min : nw;
+                int kk, k;
+                if (M.quantiser == SDPB_Q_TRUNC) {
+                    if (M.q_from_period > 0 && S.t >= M.q_from_period) nw = (double)jround32(nw * M.q_mul) / M.q_div;
+                    kk = k = (int)nw;
+                } else {
+                    kk = jround32(nw * M.q_mul);
+                    k = (M.quantiser == SDPB_Q_DIV || M.q_idiv == 1) ? kk : jdiv32(kk, (int)M.q_idiv, M.q_magic);
+                }
+                int kw = k - (int)M.kmin;
+                kw = max(min(kw, M.nW - 1), 0);
+                double vn = __ldg(Vn + (e.row + kw));
+                if (SURVIVAL && k < 0) vn = 0.0;                                   // RiskRecursion.java:87-95
+                acc += e.pg * vn;                                                  // CashRecursion.java:120
+            }
+        }
+        if (IS_MIN ? (acc < best) : (acc > best)) { best = acc; besti = i; }
+    }
+    if (valid) {
+        Vt[idx] = best;
+        Qt[idx] = besti == kNoAction ? -1 : besti;
+    }
+}
+
+// CASH_DEPOSIT kind without lead time on a grid whose indices fit 32 bits (DevModel::small).
+inline bool cash_row_ok(const sdpb_model& m, const DevModel& d, int D) {
+    return m.cost_kind == SDPB_COST_CASH_DEPOSIT && m.lead_time == 0 && d.small != 0 &&
+           (size_t)D * sizeof(CashRowEntry) <= 96 * 1024;
+}
+
+inline int launch_cash_row(const sdpb_model& m, const DevModel& dm, int t, int D, int pmf_off, const double* Vn,
+                           double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream) {
+    if (hi <= lo) return SDPB_OK;
+    const int segs = (dm.nW + 127) / 128;
+    const long long row0 = lo / dm.nW, row1 = (hi - 1) / dm.nW;
+    const unsigned blocks = (unsigned)((row1 - row0 + 1) * segs);
+    const size_t smem = (size_t)D * sizeof(CashRowEntry);
+    const bool surv = m.recursion == SDPB_REC_SURVIVAL;
+    cudaError_t e = cudaSuccess;
+#define SDPB_ROW_LAUNCH(SV, MN)                                                                         \
+    {                                                                                                   \
+        auto k = bi_cash_row<SV, MN>;                                                                   \
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) k<<<blocks, 128, smem, stream>>>(dm, t, D, pmf_off, Vn, Vt, Qt, lo, hi, row0, segs); \
+    }
+    if (surv) SDPB_ROW_LAUNCH(true, false) else if (dm.is_min) SDPB_ROW_LAUNCH(false, true) else SDPB_ROW_LAUNCH(false, false)
+#undef SDPB_ROW_LAUNCH
+    if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
     return SDPB_OK;
 }
 

@@ -444,6 +444,13 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
         h->stats.fp64_ops += (double)(hi - lo) * (h->m.max_order_idx + 1) * h->pmf_len[t - 1] * (t == h->m.T ? 3.0 : 5.0);
         return launch_staged<DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
     }
+    if (!DEDUP && h->opt.kernel != SDPB_KERNEL_GENERIC && cash_row_ok(h->m, h->dm, h->pmf_len[t - 1])) {
+        h->stats.kernel_used = SDPB_KERNEL_CASH_ROW;
+        // cash-dependent tail per evaluation: deposit chain 4, salvage 1, end cash 1, p*c 2 (+ clamp / quantiser /
+        // continuation 6 when a successor exists); compares and selects not counted
+        h->stats.fp64_ops += count_evals_period(h, t) * (t == h->m.T ? 8.0 : 14.0);
+        return launch_cash_row(h->m, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi, h->stream);
+    }
     if (h->stats.kernel_used == 0) h->stats.kernel_used = SDPB_KERNEL_GENERIC;
     return dispatch_generic_d<DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
 }

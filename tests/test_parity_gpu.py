@@ -131,9 +131,36 @@ def test_integer_cash_kernel_is_used(S):
     for case in (cases.case_C_int, cases.case_C_int_K, cases.case_F_small):
         spec, _ = case()
         assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_CASH_DIAG, spec.name
-    for case in (cases.case_C_small, cases.case_C_rich, cases.case_D_small):
+    # fractional cash grids: the cash-constraint kind shares its cash-independent terms across a row of cash levels,
+    # the other kinds (whose balance depends on the demand through the cash level) stay on the generic kernel
+    for case, used in ((cases.case_C_small, S.KERNEL_CASH_ROW), (cases.case_C_rich, S.KERNEL_CASH_ROW),
+                       (cases.case_D_small, S.KERNEL_GENERIC)):
         spec, _ = case()
-        assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_GENERIC, spec.name
+        assert S.Solver(spec).solve().stats()["kernel_used"] == used, spec.name
+
+
+def test_cash_row_kernel_shapes(S, oracle):
+    """bi_cash_row: several 128-level cash segments with a ragged last one, 0.1 and integer cash grids, K > 0 with a
+    cash reserve, deposit and overhead rates, bankruptcy penalty, gamma < 1, survival recursion with per-period
+    prices; whole grid against the oracle and the generic kernel."""
+    specs = [
+        S.cash_constraint_model(cases.pmf([4, 6, 5], 0.999), price=7, vari_cost=1.5, fixed_cost=3, hold_cost=0.25, salvage=0.5,
+                                overhead=2, overhead_rate=0.05, deposit_rate=0.02, penalty_cost=0.3, max_order=11,
+                                inv_min=0, inv_max=17, cash_min=0, cash_max=41.7, gamma=0.97),
+        S.cash_constraint_model(cases.pmf([5, 5], 0.99), price=9, vari_cost=2, salvage=1, max_order=9, inv_min=0, inv_max=14,
+                                cash_min=0, cash_max=300, quantiser=S.abi.Q_LONGDIV, q_mul=1.0, q_div=1.0, hold_cost=0.5),
+        S.cash_survival_model(cases.pmf([5, 6, 4], 0.99), price_t=[4.5, 5, 4], vari_cost_t=[1, 1.5, 2], overhead_t=[11, 9, 12],
+                              salvage=0.5, hold_cost=0.25, deposit_rate=0.01, max_order=12, inv_min=0, inv_max=20,
+                              cash_min=-20, cash_max=150),
+    ]
+    for spec in specs:
+        Vo, Qo, evals, _ = oracle.dense(spec)
+        s, V, Q = _solve_all(S, spec)
+        assert s.stats()["kernel_used"] == S.KERNEL_CASH_ROW and s.stats()["evals"] == evals, spec.name
+        assert np.array_equal(V, Vo) and np.array_equal(Q, Qo), spec.name
+        g, Vg, Qg = _solve_all(S, spec, kernel=S.KERNEL_GENERIC)
+        assert g.stats()["kernel_used"] == S.KERNEL_GENERIC
+        assert np.array_equal(Vg, Vo) and np.array_equal(Qg, Qo), spec.name
 
 
 @pytest.mark.parametrize("case", [cases.case_B1_ref, cases.case_B1_fixed, cases.case_B2_small],
