@@ -59,6 +59,14 @@ public final class SdpB200 {
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle REACH = fn("sdpb_reach", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
     static final MethodHandle OPT_TABLE = fn("sdpb_opt_table", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle SOLVE_ASYNC = fn("sdpb_solve_async", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle SOLVE_PERIOD_ASYNC = fn("sdpb_solve_period_async", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    static final MethodHandle SYNC = fn("sdpb_sync", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle PERIOD_TABLES = fn("sdpb_period_tables", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle DEVICE_TABLES = fn("sdpb_device_tables", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle SHARD_READS = fn("sdpb_shard_reads", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle SIMULATE = fn("sdpb_simulate",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, JAVA_DOUBLE, ADDRESS));
     static final MethodHandle EVAL_TRIPLES = fn("sdpb_eval_triples", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT,
             ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
 
