@@ -4,19 +4,21 @@
     python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W  # CPU arm: the oracle port on host cores
 
-A "step" is one full-horizon solve (T backward-induction launches) of the workload.  The default
-workload is BASELINE.json configs[4], the synthetic scale sweep the metric is quoted on at 1/2/4/8
-GPUs: family A (src/capacitated lambdas), S states x 200 actions x 200 demand points, T = 4, with
-S = 1e7 per GPU (weak scaling: the state grid grows with N and is block-partitioned across ranks;
-every period each rank solves its block and V_t is all-gathered over NCCL).  The other configs
-(C1-C4) are solved once each and reported under "configs".
+A "step" is one full-horizon solve (T backward-induction periods) of the workload.  The default
+workload is BASELINE.json configs[3], the instance north_star partitions across GPUs: src/leadtime
+with lead time 2, (x, q1, q2) state, 10,211,201 states x 101 actions x 25 demand points, T = 20, on a FIXED
+grid (strong scaling: at N GPUs the grid is cut into N bands of inventory rows, every rank holds only
+the window of V_t it reads, and after each period the ranks copy the rows their neighbours read
+straight into the neighbours' tables through peer-mapped memory inside libsdpb200 -- no collective
+library on the data path).  The other configs (C1, C2, C3, the C5 sweep) are solved once each and
+reported under "configs".
 
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
-import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -30,9 +32,13 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 REF_F = {"c1": 20, "c2": 20, "c3": 41, "c4": 20, "c5": 20}  # fp64 ops per evaluation as written
-KERNEL_NAMES = {1: "bi_generic", 2: "bi_inv_tiled", 3: "bi_backorder_staged", 4: "bi_cash_int", 5: "bi_inv_tiled2", 6: "bi_lead_slab", 7: "bi_lead_col", 8: "bi_cash_diag", 9: "bi_lead_q2", 10: "bi_two_product_row", 11: "bi_inv_fused", 12: "bi_cash_row"}
+KERNEL_NAMES = {1: "bi_generic", 2: "bi_inv_tiled", 3: "bi_backorder_staged", 4: "bi_cash_int", 5: "bi_inv_tiled2",
+                6: "bi_lead_slab", 7: "bi_lead_col", 8: "bi_cash_diag", 9: "bi_lead_q2", 10: "bi_two_product_row",
+                11: "bi_inv_fused", 12: "bi_cash_row", 13: "bi_overdraft_row"}
 METRIC = "state-action-demand evaluations/s (fp64), full-horizon SDP solve"
 UNIT = "evals/s"
+INIT = {"c1": [[0.0]], "c2": [[0.0]], "c3": [[0.0, 100.0]], "c4": [[0.0, 0.0, 0.0]], "c5": [[0.0]]}
+GOLDEN_KEY = {"c3": "c3", "c4": "c4"}  # tests/golden/fullsize.json entries (c5 only at 1e7 states)
 
 
 def parse():
@@ -41,12 +47,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c1", "c2", "c3", "c4", "c5"])
-    ap.add_argument("--states-per-gpu", type=int, default=10_000_000, help="C5 only")
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: the library's own peer exchange (default) or the round-1 torch.distributed path")
+    ap.add_argument("--states-per-gpu", type=int, default=10_000_000, help="C5 only (weak scaling)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tiled", "tiled2"])
     ap.add_argument("--dedup", action="store_true")
-    ap.add_argument("--no-configs", action="store_true", help="skip the one-shot C1-C4 solves")
+    ap.add_argument("--no-configs", action="store_true", help="skip the one-shot solves of the other configurations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -58,8 +67,15 @@ def make_spec(S, name, n_gpus, states_per_gpu):
     return {"c1": c.c1, "c2": c.c2, "c3": c.c3, "c4": c.c4}[name]()
 
 
-def workload_desc(spec, name, n_gpus):
+def workload_desc(spec, name, n_gpus, exchange="p2p"):
     D = [len(r) for r in spec.pmf]
+    part = "none"
+    if n_gpus > 1:
+        part = (f"state grid in {n_gpus} contiguous blocks (bands of inventory rows); every rank holds the window of "
+                "V_t its kernels read; per period ")
+        part += ("each rank copies the rows its peers read into their tables through CUDA-IPC peer-mapped memory and "
+                 "raises a device-side flag (libsdpb200: sdpb_peer_attach), no collective library"
+                 if exchange == "p2p" else "torch.distributed point-to-point halo exchange / all-gather over NCCL")
     return {
         "workload": {
             "c1": "C1 src/sdp single-item lot sizing T=4 Poisson[20,40,60,40] 1001 states x 501 actions",
@@ -71,13 +87,10 @@ def workload_desc(spec, name, n_gpus):
         }[name],
         "T": spec.T, "demand_points": D[0] if len(set(D)) == 1 else D,
         "actions": spec.max_order_idx + 1,
-        "partition": (f"state grid in {n_gpus} contiguous blocks; per period each rank receives the rows of V_t its "
-                      "block can reach (point-to-point halo exchange over NCCL; all-gather when that is most of "
-                      "the table)") if n_gpus > 1 else "none",
-        "l2": "inputs larger than L2: one C5 step writes 12 B x states x T = 480 MB of tables (126 MB L2) and its first "
-              "launch (period T) reads no table at all, so nothing cached by the previous timed step can be reused; "
-              "within a step V_{t+1} is what the previous period's launch left behind, as in any solve (an explicit "
-              "256 MB memset between steps was tried: it only adds its own time)",
+        "partition": part,
+        "l2": "inputs larger than L2: a C4 step writes 12 B x 10.2e6 states x 20 periods = 2.45 GB of tables (126 MB L2), "
+              "and its first launch (period T) reads no table at all, so nothing cached by the previous timed step "
+              "can be reused; within a step V_{t+1} is what the previous period left behind, as in any solve",
     }
 
 
@@ -133,71 +146,125 @@ class ClockSampler:
 
 
 # ---- CPU arm ----------------------------------------------------------------------------------
-def cpu_sample_spec(S, spec, n_states):
-    """Same family, same actions / demand table / horizon, fewer inventory states."""
+def java_probe():
+    """Is there a JVM on this box?  (time the reference Java itself when one is found.)"""
+    out = {}
+    for exe in ("java", "javac"):
+        try:
+            r = subprocess.run([exe, "-version"], capture_output=True, text=True, timeout=20)
+            out[exe] = (r.stderr or r.stdout).strip().splitlines()[0] if r.returncode == 0 else f"exit {r.returncode}"
+        except FileNotFoundError:
+            out[exe] = "not found"
+        except Exception as e:  # noqa: BLE001
+            out[exe] = f"error: {e}"
+    out["usable"] = all(v != "not found" and not v.startswith(("exit", "error")) for v in (out["java"], out["javac"]))
+    return out
+
+
+def cpu_sample_spec(S, name, spec, rows):
+    """The same model on a sub-grid of `rows` inventory levels: same actions, demand table, horizon, cash axis and
+    pipeline axes -- the per-state work of the CPU solve does not depend on how many inventory rows there are."""
+    c = S.configs
+    if name == "c3":
+        return c.c3(inv_max=max(1, rows - 1))
+    if name == "c4":
+        return c.c4(inv_half=max(1, rows // 2))
     import copy
     s = copy.copy(spec)
-    if spec.cost_kind == S.COST_BACKORDER and spec.lead_time == 0:
-        half = n_states // 2
-        s.inv_min, s.inv_max = float(-half), float(n_states - half - 1)
+    half = rows // 2
+    s.inv_min, s.inv_max = float(-half), float(rows - half - 1)
     return s
 
 
-def time_oracle(S, spec, seconds, threads=0):
-    """Time the oracle's dense solve (all host threads) on a bounded sample of `spec`."""
+def states_per_row(name):
+    return {"c3": 2001, "c4": 101 * 101}.get(name, 1)
+
+
+def time_dense(sample, threads=0):
     import oracle_lib as O
-    n = 256
-    t0 = time.perf_counter()
-    _, _, ev, _ = O.dense(cpu_sample_spec(S, spec, n), threads)
-    dt = max(time.perf_counter() - t0, 1e-3)
-    rate = ev / dt
-    per_state = ev / n
-    n_big = int(max(n, min(spec.n_states(), rate * seconds / per_state)))
-    sample = cpu_sample_spec(S, spec, n_big)
     t0 = time.perf_counter()
     _, _, ev, _ = O.dense(sample, threads)
-    dt = time.perf_counter() - t0
-    return ev / dt, ev, dt, n_big
+    return ev, time.perf_counter() - t0
 
 
-def time_topdown(S, spec, n_states=2048):
+def calibrate_rows(S, name, spec, seconds, threads=0):
+    """Rows of the sub-grid that take about `seconds` of oracle_dense on this box's host cores."""
     import oracle_lib as O
-    sample = cpu_sample_spec(S, spec, n_states)
-    init = [[0.0] * sample.ndim]
+    small = cpu_sample_spec(S, name, spec, {"c3": 2, "c4": 3}.get(name, 256))
+    ev, dt = time_dense(small, threads)
+    rows_small = O.grid(small)[0] // states_per_row(name)
+    rate = ev / max(dt, 1e-3)
+    per_row = ev / rows_small
+    full_rows = O.grid(spec)[0] // states_per_row(name)
+    return int(max(rows_small, min(full_rows, rate * seconds / per_row)))
+
+
+def time_topdown(S, name, spec):
+    """The reference's own control flow (memoised top-down recursion, one thread) from the initial state, on an
+    instance cut down until it takes seconds: the first 3 periods of C3 / C4 on a few inventory rows, a 2048-state
+    grid for the 1-D families.  A rate (evaluations/s of the literal recursion), not a solve of the workload."""
+    import oracle_lib as O
+    c = S.configs
+    if name == "c3":
+        sample = c.c3(T=3, inv_max=7)
+    elif name == "c4":
+        sample = c.c4(T=3, inv_half=3)
+    else:
+        sample = cpu_sample_spec(S, name, spec, 2048)
     t0 = time.perf_counter()
-    rows, _, ev = O.topdown(sample, init)
+    vis, _, ev = O.topdown(sample, INIT[name])
     dt = time.perf_counter() - t0
-    return ev / dt, ev, dt, len(rows)
+    return ev / dt, ev, dt, len(vis), O.grid(sample)[0]
+
+
+def workload_evals(name, spec):
+    return 4.612e11 if name == "c3" else spec.evals_dense()  # (C3's action sets depend on the cash level)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    import oracle_lib as O
     import sdpb200 as S
-    spec = make_spec(S, args.workload, 1, args.states_per_gpu)
+    name = args.workload
+    spec = make_spec(S, name, 1, args.states_per_gpu)
     cores = os.cpu_count() or 1
-    # size one step to ~ (180 s budget) / (steps + warmup)
+    # size one step to ~ (150 s budget) / (steps + warmup)
     per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
-    rate, ev, dt, n_s = time_oracle(S, spec, per_step)
+    rows = calibrate_rows(S, name, spec, per_step)
+    sample = cpu_sample_spec(S, name, spec, rows)
+    n_sample, n_full = O.grid(sample)[0], O.grid(spec)[0]
     for _ in range(max(0, args.warmup - 1)):
-        time_oracle_fixed(S, spec, n_s)
+        time_dense(sample)
     t_total, ev_total = 0.0, 0.0
     for _ in range(args.steps):
-        e, d = time_oracle_fixed(S, spec, n_s)
+        e, d = time_dense(sample)
         t_total += d
         ev_total += e
     value = ev_total / t_total
-    sample = (f"oracle_dense (C++ restatement of Recursion.java:129-161, {cores} host threads) on {n_s} of "
-              f"{spec.n_states()} states, all {spec.max_order_idx + 1} actions x {len(spec.pmf[0])} demands x T={spec.T}")
+    td_rate, td_ev, td_dt, td_rows, td_states = time_topdown(S, name, spec)
+    what = (f"oracle_dense (C++ restatement of the reference loop, {cores} host threads) on a {n_sample}-state sub-grid "
+            f"({rows} of the inventory rows) of the {n_full}-state workload; all {spec.max_order_idx + 1} actions x "
+            f"{len(spec.pmf[0])} demands x T={spec.T}")
+    cfg = workload_desc(spec, name, 1)
+    cfg["workload"] += f" -- CPU arm: RATE EXTRAPOLATED from a {n_sample}-state sub-grid (the full grid is not solved)"
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_desc(spec, args.workload, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "note": "the reference is Java (no JDK in the image); this is the C++ oracle port, "
-                                 "multi-threaded, which is faster than the single-threaded Java original"},
+        "ms_per_step_note": "time of one sub-grid solve, not of the workload; the full workload at this rate would take "
+                            f"{workload_evals(name, spec) / value:.0f} s",
+        "higher_is_better": True, "scaling": "strong" if name in ("c3", "c4") else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": what,
+                         "java_probe": java_probe(),
+                         "topdown_1thread": {"value": td_rate, "unit": UNIT,
+                                             "sample": f"oracle_topdown (the reference's memoised recursion, 1 thread) from "
+                                                       f"the initial state on a cut-down instance ({td_states} states per period, first periods "
+                                                       f"only): {td_rows} visited states, {td_dt:.1f} s -- this is the work the "
+                                                       "single-threaded Java does per evaluation"},
+                         "note": "the reference is single-threaded Java; no JDK in the image (probe above), so the C++ port "
+                                 "is timed: multi-threaded dense solve as `value`, the literal 1-thread recursion beside it"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -205,26 +272,68 @@ def run_reference(args):
     return 0
 
 
-def time_oracle_fixed(S, spec, n_states):
-    import oracle_lib as O
-    sample = cpu_sample_spec(S, spec, n_states)
-    t0 = time.perf_counter()
-    _, _, ev, _ = O.dense(sample, 0)
-    return ev, time.perf_counter() - t0
-
-
 # ---- GPU arm ----------------------------------------------------------------------------------
 def per_step_counts(sh, sync):
-    """(evals, evals_executed, fp64_ops) of ONE step.  Unsharded handles reset their counters at every
-    solve; sharded ones (stepped period by period) accumulate, so take a difference there."""
-    a = sh.solver.stats()
+    """(evals, evals_executed, fp64_ops, kernel, launches) of ONE step (the library resets its counters per solve)."""
     sh.step()
     sync()
+    if sh.world > 1 and sh.exchange_kind != "p2p":  # stepped period by period: the counters accumulate
+        a = sh.solver.stats()
+        sh.step()
+        sync()
+        b = sh.solver.stats()
+        return (b["evals"] - a["evals"], b["evals_executed"] - a["evals_executed"], b["fp64_ops"] - a["fp64_ops"],
+                b["kernel_used"], b["launches"] - a["launches"])
     b = sh.solver.stats()
-    if sh.world == 1:
-        return b["evals"], b["evals_executed"], b["fp64_ops"], b["kernel_used"]
-    return (b["evals"] - a["evals"], b["evals_executed"] - a["evals_executed"], b["fp64_ops"] - a["fp64_ops"],
-            b["kernel_used"])
+    return b["evals"], b["evals_executed"], b["fp64_ops"], b["kernel_used"], b["launches"]
+
+
+def table_hash_check(solver, gold):
+    """Whole grid, every period: SHA-256 of V_t / Q_t bytes against the frozen whole-grid oracle run."""
+    import numpy as np
+    V, Q = np.empty(solver.n_states), np.empty(solver.n_states)
+    for t in range(1, solver.T + 1):
+        solver.period_tables(t, out_v=V, out_q=Q)
+        if hashlib.sha256(V.tobytes()).hexdigest() != gold["sha256_V"][t - 1]:
+            return False
+        if hashlib.sha256(Q.tobytes()).hexdigest() != gold["sha256_Q"][t - 1]:
+            return False
+    return True
+
+
+def sample_check(spec, solver, n=32, seed=5):
+    """Inductive check on a sample: recompute V_t, Q_t on the CPU (the oracle, as the checker) at random states from
+    the GPU's own V_{t+1}, every period."""
+    import numpy as np
+    import oracle_lib as O
+    rng = np.random.default_rng(seed)
+    idx = np.unique(np.concatenate([[0, solver.n_states - 1], rng.integers(0, solver.n_states, n)]))
+    Vn = None
+    V, Q = np.empty(solver.n_states), np.empty(solver.n_states)
+    for t in range(spec.T, 0, -1):
+        solver.period_tables(t, out_v=V, out_q=Q)
+        vo, qo = O.step_states(spec, t, Vn, idx)
+        if not (np.array_equal(V[idx], vo) and np.array_equal(Q[idx], qo)):
+            return False
+        Vn = V.copy()
+    return True
+
+
+def verify_vs_unsharded(S, torch, dist, sp, sharded, local, dedup):
+    """Multi-GPU result check (outside every timed region): each rank re-solves the WHOLE grid by itself and compares
+    its own block of V_1 and Q_1, bit for bit, with what the sharded solve (real peer exchange) left in its tables."""
+    import numpy as np
+    torch.cuda.synchronize()
+    sharded.solver.sync()
+    Vm, Qm = sharded.solver.shard_tables(1)
+    lo_, hi_ = sharded.lo, sharded.hi
+    with S.Solver(sp, device=local, dedup=dedup) as ref:
+        ref.solve()
+        Vr, Qr = ref.period_tables(1)
+    ok = bool(np.array_equal(Vm, Vr[lo_:hi_]) and np.array_equal(Qm, Qr[lo_:hi_]))
+    okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{local}")
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    return bool(int(okt[0]))
 
 
 def next_rows(S, device):
@@ -240,7 +349,6 @@ def next_rows(S, device):
         r = fn()
         return r, time.perf_counter() - t0
 
-    # f-1: reachability mask + getOptTable() rows; f-2: policy roll-out -- on the C1 instance
     sp = S.configs.c1()
     with S.Solver(sp, device=device) as s:
         s.solve()
@@ -256,7 +364,6 @@ def next_rows(S, device):
         res["f2_simulate_c1"] = {"paths": n, "ms": dt_s * 1e3, "paths_per_s": n / dt_s, "mean": float(vals.mean()),
                                  "V1_init": float(v1[0]),
                                  "what": "sdpb_simulate, host samples in / per-path sums out (Simulation.java:53-74)"}
-    # f-3: two products sharing cash (MultiItemCash lambdas), scaled grid
     d1, d2 = S.PoissonDist(5), S.PoissonDist(6)
     rows = S.GetPmfMulti([[d1] * 3, [d2] * 3], 0.999, 1).tables()
     sp = S.two_product_cash_model(rows, price=(4.0, 5.0), vari_cost=(2.0, 3.0), salvage=(1.0, 1.0), q_bound=20,
@@ -270,7 +377,6 @@ def next_rows(S, device):
                                  "kernel": KERNEL_NAMES.get(st["kernel_used"]),
                                  "what": "CashRecursionMulti + MultiItemCash.java:69-121 lambdas, 41 x 41 x 401 grid, "
                                          "Qbound 20 (the reference's 201 x 201 x 10001 dense grid is 4e8 states)"}
-    # f-4: workforce planning at the reference's own instance size (WorkforcePlanning.java:33-47)
     sp = S.workforce_model([0.5, 0.5, 0.5])
     with S.Solver(sp, device=device) as s:
         s.solve()
@@ -302,28 +408,38 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     par = S.package.parallel
     _CAI = par._CAI
+    name = args.workload
+    stream = torch.cuda.Stream(device=local)
+    dev = f"cuda:{local}"
 
-    def ShardedSolve(S_, torch_, dist_, spec_, rank_, world_, device_, stream_, kernel_, dedup_):
-        return par.ShardedSolve(S_.Solver, torch_, dist_, spec_, rank_, world_, device_, stream_, kernel_, dedup_)
+    def ShardedSolve(spec_, rank_, world_, kernel_, dedup_, profile=False):
+        return par.ShardedSolve(S.Solver, torch, dist if world_ > 1 else None, spec_, rank_, world_, local, stream,
+                                kernel_, dedup_, exchange=args.exchange, profile=profile)
 
     kernel = {"auto": S.KERNEL_AUTO, "generic": S.KERNEL_GENERIC, "tiled": S.KERNEL_TILED,
               "tiled2": S.KERNEL_TILED2}[args.kernel]
-    spec = make_spec(S, args.workload, world, args.states_per_gpu)
-    stream = torch.cuda.Stream(device=local)
+    spec = make_spec(S, name, world, args.states_per_gpu)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max_sum(vals):
+        if world == 1:
+            return list(vals), list(vals)
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        mx, sm = t.clone(), t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        return [float(x) for x in mx], [float(x) for x in sm]
+
     with torch.cuda.stream(stream):
-        sh = ShardedSolve(S, torch, dist, spec, rank, world, local, stream, kernel, args.dedup)
-        # evaluations per step, whole job (exact for state-independent action sets; cash-limited
-        # workloads take the library's own count)
+        sh = ShardedSolve(spec, rank, world, kernel, args.dedup)
         for _ in range(max(0, args.warmup - 1)):
             sh.step()
         barrier()
-        ev_step, evx_step, fp_step, kernel_used = per_step_counts(sh, barrier)  # the last warm-up step
+        ev_step, evx_step, fp_step, kernel_used, launches_step = per_step_counts(sh, barrier)  # the last warm-up step
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
@@ -336,18 +452,48 @@ def run_gpu(args):
         barrier()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else None
-        ev_local = ev_step * args.steps
-        fp_local = fp_step * args.steps
-        t = torch.tensor([ms, ev_local, fp_local], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            tmax = t.clone()
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            tsum = t.clone()
-            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            ms, ev_total, fp_total = float(tmax[0]), float(tsum[1]), float(tsum[2])
-        else:
-            ev_total, fp_total = ev_local, fp_local
+        (ms, _, _, _), (_, ev_total, fp_total, launches_total) = reduce_max_sum(
+            [ms, ev_step * args.steps, fp_step * args.steps, launches_step * args.steps])
         value = ev_total / (ms * 1e-3)
+        dev_bytes = sh.solver.grid.device_bytes
+        bytes_out, bytes_in = sh.bytes_out, sh.bytes_in
+
+        # ---- verification of the timed workload's result (outside every timed region) ----
+        verify = {}
+        if not args.no_verify:
+            if world == 1:
+                verify["verified_vs_oracle_sample"] = bool(sample_check(spec, sh.solver))
+                gold_path = os.path.join(ROOT, "tests", "golden", "fullsize.json")
+                key = GOLDEN_KEY.get(name) or ("c5_1e7" if name == "c5" and spec.n_states() == 10_000_000 else None)
+                if key and os.path.exists(gold_path) and not args.dedup:
+                    gold = json.load(open(gold_path)).get(key)
+                    if gold and np.array_equal(np.asarray(gold["pmf"][0]), np.asarray(spec.pmf[0])):
+                        verify["verified_vs_golden_hash"] = bool(table_hash_check(sh.solver, gold))
+                        verify["golden"] = f"tests/golden/fullsize.json[{key}]: whole grid, all {spec.T} periods, SHA-256"
+            else:
+                verify["verified_vs_unsharded"] = verify_vs_unsharded(S, torch, dist, spec, sh, local, args.dedup)
+
+        # ---- per-period breakdown of the exchange (N > 1): two extra, profiled solves ----
+        period_profile = None
+        if world > 1 and args.exchange == "p2p":
+            sp_ = ShardedSolve(spec, rank, world, kernel, args.dedup, profile=True)
+            for _ in range(2):
+                sp_.step()
+                sp_.solver.sync()
+            prof = torch.tensor(sp_.solver.period_profile(), dtype=torch.float64, device=dev)  # [T, 3]
+            mx, mn = prof.clone(), prof.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            period_profile = {
+                "columns": ["kernels_ms", "push_and_flag_ms", "wait_for_peers_ms"],
+                "rank0": [[round(float(x), 4) for x in row] for row in prof.cpu()],
+                "max_over_ranks": [[round(float(x), 4) for x in row] for row in mx.cpu()],
+                "min_over_ranks": [[round(float(x), 4) for x in row] for row in mn.cpu()],
+                "sum_max_over_ranks_ms": [round(float(x), 3) for x in mx.sum(dim=0).cpu()],
+                "what": "device time per period (period 1 first) of one solve, CUDA events on each rank's stream: the period's "
+                        "kernels / peer copies + flag store / spin on the peers' flags (sdpb_period_profile)"}
+            dist.barrier()
+            sp_.close()
 
         # ---- e2e: through the C-ABI with host buffers; H2D of the descriptor tables and D2H of the
         # period-1 value/policy tables inside the timed region, every step ----
@@ -361,45 +507,44 @@ def run_gpu(args):
                 barrier()
                 t0 = time.perf_counter()
             p0 = time.perf_counter()
-            s2 = ShardedSolve(S, torch, dist, spec, rank, world, local, stream, kernel, args.dedup)
+            s2 = ShardedSolve(spec, rank, world, kernel, args.dedup)
             p1 = time.perf_counter()
             s2.step()
             s2.solver.sync()
             p2 = time.perf_counter()
+            nloc = s2.hi - s2.lo
             if world == 1:
-                v1, q1 = s2.solver.value(1, [[0.0] * s2.solver.ndim] if args.workload != "c3" else [[0.0, 100.0]])
+                s2.solver.value(1, INIT[name])
                 if host_v is None:
                     host_v = torch.empty(s2.solver.n_states, dtype=torch.float64).pin_memory().numpy()
                     host_q = torch.empty(s2.solver.n_states, dtype=torch.float64).pin_memory().numpy()
-                V1, Q1 = s2.solver.period_tables(1, out_v=host_v, out_q=host_q)
+                s2.solver.period_tables(1, out_v=host_v, out_q=host_q)
                 d2h = s2.n * 16 + 16
             else:
-                s2.solver.sync()
-                dv, dq = s2.solver.device_tables(1)
-                nloc = s2.hi - s2.lo
-                Vt = torch.as_tensor(_CAI(dv + 8 * s2.lo, nloc, "<f8"), device=f"cuda:{local}")
-                Qt = torch.as_tensor(_CAI(dq + 4 * s2.lo, nloc, "<i4"), device=f"cuda:{local}")
+                dv, dq = s2.solver.device_tables(1)  # first elements held: V_1[window_lo], Q_1[shard_lo]
+                wlo = s2.solver.grid.window_lo
+                Vt = torch.as_tensor(_CAI(dv + 8 * (s2.lo - wlo), nloc, "<f8"), device=dev)
+                Qt = torch.as_tensor(_CAI(dq, nloc, "<i4"), device=dev)
                 if host_v is None:  # this rank's block of the result tables, page-locked
                     host_v = torch.empty(nloc, dtype=torch.float64).pin_memory()
                     host_q = torch.empty(nloc, dtype=torch.int32).pin_memory()
                 host_v.copy_(Vt, non_blocking=True)
                 host_q.copy_(Qt, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
-                V1, Q1 = host_v, host_q
                 d2h = nloc * 12
             npmf = sum(len(r) for r in spec.pmf)
             h2d = npmf * 28 + spec.T * 32
             p3 = time.perf_counter()
+            if world > 1:
+                dist.barrier()  # nobody unmaps a table while a peer may still be raising flags in it
             s2.close()
             p4 = time.perf_counter()
             for k, v in zip(phases, (p1 - p0, p2 - p1, p3 - p2, p4 - p3)):
                 phases[k] += v / e2e_steps
         barrier()
         e2e_s = time.perf_counter() - t0
-        e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        e2e_value = (ev_total / args.steps) * e2e_steps / float(e2e_t[0])
+        (e2e_s,), _ = reduce_max_sum([e2e_s])
+        e2e_value = (ev_total / args.steps) * e2e_steps / e2e_s
 
     out = None
     if rank == 0:
@@ -410,147 +555,135 @@ def run_gpu(args):
         except Exception:
             pass
         achieved = fp_total / (ms * 1e-3) / 1e12 / world  # per GPU
-        traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
+        traffic, traffic_note = None, "no ncu --set full capture of this kernel at this size is committed"
         try:
-            if args.workload == "c5" and args.states_per_gpu == 10_000_000 and kernel_used == 5:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_tiled2.json")))
-                traffic = [v["dram_bytes_per_launch"] for k, v in tj.items() if not k.startswith("_")][0]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            ent = tj.get(KERNEL_NAMES.get(kernel_used, ""), {}).get(name)
+            if ent and world == 1:
+                traffic, traffic_note = ent["dram_bytes_per_launch"], ent["note"]
         except Exception:
-            traffic = None
+            pass
         hbm_bytes = 24.0 * sh.n * spec.T * args.steps  # 8 B read + 16 B written per state-period (whole grid)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak" if args.workload == "c5" else "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_desc(spec, args.workload, world),
+            "scaling": "weak" if name == "c5" else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_desc(spec, name, world, args.exchange),
             "solve_time_s": ms / args.steps * 1e-3,
             "evals_per_step": ev_total / args.steps,
             "kernel": KERNEL_NAMES.get(kernel_used, str(kernel_used)),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "phases_s_per_step": phases,
-                    "what": "sdpb_create (H2D pmf/parameter tables) + solve + sdpb_value + D2H of the period-1 "
-                            "value and policy tables into page-locked host buffers + sdpb_destroy, wall clock; "
-                            "one untimed warm-up cycle first"},
-            "gpu_launches": args.steps * spec.T * world,
+                    "what": "sdpb_create (H2D pmf/parameter tables" +
+                            (", CUDA-IPC export/attach of the shards" if world > 1 else "") +
+                            ") + solve + sdpb_value + D2H of the period-1 value and policy tables into page-locked host "
+                            "buffers + sdpb_destroy, wall clock; one untimed warm-up cycle first"},
+            "gpu_launches": int(launches_total),
+            "gpu_launches_note": "backward-induction kernels (+ the per-period transposition pass of bi_lead_q2) over all ranks; "
+                                 "peer copies and the two 1-CTA flag kernels per period are not counted",
             "clocks": clocks,
+            "device_bytes_per_gpu": dev_bytes,
+            "peer_bytes_per_period": {"out": bytes_out, "in": bytes_in} if world > 1 else None,
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peaks["nofma_tops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["nofma_tops"] if peaks["nofma_tops"] else None, "traffic": traffic,
-                "traffic_note": "ncu dram read+write bytes of one non-last-period launch at S=1e7 "
-                                "(profiles/r01_traffic_tiled2.json); algorithmic bytes per launch = 20 B/state = 2.0e8",
+                "traffic_note": traffic_note,
                 "what": "non-fused fp64 instructions (DADD/DMUL; Java parity forbids DFMA) the kernel executes "
                         "per GPU per second vs the same mix measured live by sdpb_microbench on this GPU; "
-                        "MEASURED_PEAKS.json has no fp64 figure",
+                        "MEASURED_PEAKS.json has no fp64 figure; the per-evaluation instruction counts are audited "
+                        "against ncu's DADD/DMUL counters in profiles/r02_fp64_audit.md",
                 "fp64_instr_per_eval": fp_total / ev_total if ev_total else None,
-                "reference_formulation_fp64_per_eval": REF_F.get(args.workload, 20),
-                "achieved_reference_formulation": ev_total * REF_F.get(args.workload, 20) / (ms * 1e-3) / 1e12 / world,
-                "frac_reference_formulation": (ev_total * REF_F.get(args.workload, 20) / (ms * 1e-3) / 1e12 / world
-                                               / peaks["nofma_tops"]) if peaks["nofma_tops"] else None,
+                "reference_formulation_fp64_per_eval": REF_F.get(name, 20),
+                "achieved_reference_formulation": ev_total * REF_F.get(name, 20) / (ms * 1e-3) / 1e12 / world,
                 "reference_formulation_note": "SURVEY.md section 8(d) counts the fp64 operations of the reference's own "
                                               "lambdas per evaluation (F_A = 20, F_B = 20, F_C = 41); evals x F / t is "
                                               "above the pipe peak because the kernels remove most of those operations "
-                                              "exactly -- `achieved` / `frac` count only instructions actually issued",
+                                              "exactly -- it is NOT a utilisation; `achieved` / `frac` count only "
+                                              "instructions actually issued",
                 "lds_peak_gbs": peaks["lds_gbs"], "fma_peak_tflops": peaks["fma_tflops"],
                 "hbm": {"achieved_gbs": hbm_bytes / (ms * 1e-3) / 1e9 / world, "peak_gbs": mp.get("hbm_gbs"),
                         "note": "algorithmic HBM bytes: 24 B per state-period; not the bound"},
             },
         }
+        out.update(verify)
+        if period_profile:
+            out["period_profile"] = period_profile
+    if world > 1:
+        dist.barrier()
     sh.close()
 
     # ---- the other configurations, solved once each (plus the C5 size sweep), rank 0 prints ----
     configs = {}
     if not args.no_configs:
-        peak = None
-        if rank == 0:
-            peak = out["roofline"]["peak"]
+        peak = out["roofline"]["peak"] if rank == 0 else None
         jobs = [("c1", "c1", False, None), ("c2", "c2", False, None), ("c3", "c3", False, None),
                 ("c4", "c4", False, None), ("c4_dedup", "c4", True, None)]
         for n_s in (10_000, 100_000, 1_000_000, 10_000_000, 100_000_000):
             jobs.append((f"c5_S{n_s:.0e}".replace("+0", ""), "c5", False, n_s))
-        for name_key, name, dedup, n_s in jobs:
+        for name_key, cname, dedup, n_s in jobs:
+            if cname == name and not dedup and n_s is None:
+                continue  # the timed workload itself
             if n_s is not None:
                 sp = S.configs.c5(n_states=n_s)
                 shard = world > 1 and n_s >= 1_000_000
             else:
-                sp = make_spec(S, name, world, args.states_per_gpu)
-                shard = name in ("c3", "c4") and world > 1
+                sp = make_spec(S, cname, world, args.states_per_gpu)
+                # never shard the folded solve: its exchange is the whole table and costs more than the 4 ms solve
+                shard = cname in ("c3", "c4") and world > 1 and not dedup
             w = world if shard else 1
             if not shard and rank != 0:
                 continue
             with torch.cuda.stream(stream):
-                s3 = ShardedSolve(S, torch, dist if shard else None, sp, rank if shard else 0, w, local, stream,
-                                  S.KERNEL_AUTO, dedup)
+                s3 = ShardedSolve(sp, rank if shard else 0, w, S.KERNEL_AUTO, dedup)
                 csync = barrier if shard else torch.cuda.synchronize
                 s3.step()  # warm (plain launches)
                 csync()
-                ev, evx, fp, kused = per_step_counts(s3, csync)  # second solve: a CUDA graph when unsharded
-                reps = 5 if (name in ("c1", "c2") or (n_s or 10**9) <= 100_000) else (3 if (n_s or 10**9) <= 1_000_000 else 1)
+                ev, evx, fp, kused, _ = per_step_counts(s3, csync)  # second solve: a CUDA graph when unsharded
+                reps = 5 if (cname in ("c1", "c2") or (n_s or 10**9) <= 100_000) else (3 if (n_s or 10**9) <= 1_000_000 else 1)
                 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                csync()
                 a0.record(stream)
                 for _ in range(reps):
                     s3.step()
                 a1.record(stream)
-                torch.cuda.synchronize()
+                csync()
                 cms = a0.elapsed_time(a1) / reps
-                tt = torch.tensor([cms, ev, evx, fp], dtype=torch.float64, device=f"cuda:{local}")
                 if shard:
-                    mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-                    sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-                    cms, ev, evx, fp = float(mx[0]), float(sm[1]), float(sm[2]), float(sm[3])
-                init = {"c1": [[0.0]], "c2": [[0.0]], "c3": [[0.0, 100.0]], "c4": [[0.0, 0.0, 0.0]], "c5": [[0.0]]}[name]
+                    (cms, _, _, _), (_, ev, evx, fp) = reduce_max_sum([cms, ev, evx, fp])
                 v0 = q0 = None
                 if not shard:
-                    v, q = s3.solver.value(1, init)
+                    v, q = s3.solver.value(1, INIT[cname])
                     v0, q0 = float(v[0]), float(q[0])
                 tops = fp / (cms * 1e-3) / 1e12 / w
                 verified = None
-                if shard and s3.n <= 20_000_000:
-                    # multi-GPU result check (outside every timed region): each rank re-solves the WHOLE grid by
-                    # itself and compares its own block of V_1 and Q_1, bit for bit, with what the sharded solve
-                    # (real NCCL exchange) left in its tables
-                    import numpy as np
-                    torch.cuda.synchronize()
-                    with S.Solver(sp, device=local, dedup=dedup) as ref:
-                        ref.solve()
-                        Vr, Qr = ref.period_tables(1)
-                        qi = np.rint(Qr / sp.step).astype(np.int64)
-                    dv, dq = s3.solver.device_tables(1)
-                    lo_, hi_ = s3.lo, s3.hi
-                    Vm = torch.as_tensor(_CAI(dv + 8 * lo_, hi_ - lo_, "<f8"), device=f"cuda:{local}").cpu().numpy()
-                    Qm = torch.as_tensor(_CAI(dq + 4 * lo_, hi_ - lo_, "<i4"), device=f"cuda:{local}").cpu().numpy()
-                    ok = bool(np.array_equal(Vm, Vr[lo_:hi_]) and np.array_equal(np.maximum(Qm, 0), qi[lo_:hi_]))
-                    okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{local}")
-                    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-                    verified = bool(int(okt[0]))
+                if shard and not args.no_verify:
+                    verified = verify_vs_unsharded(S, torch, dist, sp, s3, local, dedup)
                 configs[name_key] = {"solve_ms": cms, "evals": ev, "evals_per_s": ev / (cms * 1e-3),
                                      "exchange": s3.exchange_kind, "verified_vs_unsharded": verified,
                                      "evals_executed": evx, "n_gpus": w, "kernel": KERNEL_NAMES.get(kused),
-                                     "dedup": dedup, "fp64_tops_per_gpu": tops, "V1_init": v0, "Q1_init": q0}
+                                     "dedup": dedup, "fp64_tops_per_gpu": tops, "V1_init": v0, "Q1_init": q0,
+                                     "device_bytes_per_gpu": s3.solver.grid.device_bytes,
+                                     "peer_bytes_out_per_period": s3.bytes_out if shard else None}
+                if shard:
+                    dist.barrier()
                 s3.close()
         if rank == 0:
-            # The reference's drivers sweep hundreds of small instances (e.g. 810 in CLSPTesting.java:57-61):
-            # independent handles own independent streams, so their per-period launches overlap on the GPU.
-            nb = 32
+            # The reference's drivers sweep hundreds of small instances (810 in CLSPTesting.java:57-61): sdpb_solve_batch
+            # runs a list of independent handles as ONE CUDA graph (C-ABI entry point, no Python in the loop).
+            nb = 64
             sp = make_spec(S, "c2", 1, args.states_per_gpu)
-            # (per-period kernels: their launches overlap across streams; the fused whole-horizon kernel owns the GPU)
             batch = [S.Solver(sp, device=local, kernel=S.KERNEL_TILED) for _ in range(nb)]
-            for _ in range(2):  # plain solve, then the solve that captures the CUDA graph
-                for b in batch:
-                    b.solve_async()
-                for b in batch:
-                    b.sync()
+            for _ in range(3):  # plain solves, the capturing call, one replay
+                S.solve_batch(batch)
             t0 = time.perf_counter()
             reps = 5
             for _ in range(reps):
-                for b in batch:
-                    b.solve_async()
-                for b in batch:
-                    b.sync()
+                S.solve_batch(batch)
             dt = (time.perf_counter() - t0) / reps
             ev = batch[0].stats()["evals"] * nb
-            configs["c2_batch32"] = {"solve_ms": dt * 1e3, "ms_per_instance": dt * 1e3 / nb, "evals": ev,
+            configs["c2_batch64"] = {"solve_ms": dt * 1e3, "ms_per_instance": dt * 1e3 / nb, "evals": ev,
                                      "evals_per_s": ev / dt, "n_gpus": 1, "kernel": "bi_inv_tiled",
-                                     "note": "32 independent C2 instances in flight on 32 streams, wall clock",
+                                     "note": "64 independent C2 instances through sdpb_solve_batch (one CUDA graph), wall clock",
                                      "dedup": False, "fp64_tops_per_gpu": batch[0].stats()["fp64_ops"] * nb / dt / 1e12}
             for b in batch:
                 b.close()
@@ -561,18 +694,24 @@ def run_gpu(args):
     if rank == 0:
         out["configs"] = configs
         if not args.no_cpu_baseline:
+            import oracle_lib as O
             cores = os.cpu_count() or 1
-            base = make_spec(S, args.workload, 1, args.states_per_gpu)
-            rate, ev, dt, n_s = time_oracle(S, base, args.cpu_seconds)
-            td_rate, td_ev, td_dt, td_rows = time_topdown(S, base)
+            base = make_spec(S, name, 1, args.states_per_gpu)
+            rows = calibrate_rows(S, name, base, args.cpu_seconds)
+            sample = cpu_sample_spec(S, name, base, rows)
+            ev, dt = time_dense(sample)
+            td_rate, td_ev, td_dt, td_rows, td_states = time_topdown(S, name, base)
             out["cpu_baseline"] = {
-                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"oracle_dense on {n_s} of {base.n_states()} states (all actions, demands, T), {dt:.1f} s, "
-                          f"{cores} threads",
-                "topdown_1core": {"value": td_rate, "unit": UNIT,
-                                  "sample": f"oracle_topdown (literal memoised recursion) from x0=0 on a {2048}-state "
-                                            f"grid: {td_rows} visited states, {td_dt:.1f} s"},
-                "note": "reference is single-threaded Java (no JDK in the image): C++ port timed instead"}
+                "value": ev / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"oracle_dense on a {O.grid(sample)[0]}-state sub-grid ({rows} inventory rows) of the "
+                          f"{O.grid(base)[0]}-state workload (all actions, demands, T), {dt:.1f} s, {cores} threads; "
+                          "a rate, not a full solve",
+                "java_probe": java_probe(),
+                "topdown_1thread": {"value": td_rate, "unit": UNIT,
+                                    "sample": f"oracle_topdown (literal memoised recursion, 1 thread) from the initial state on "
+                                              f"a cut-down instance ({td_states} states per period, first periods only): {td_rows} visited states, "
+                                              f"{td_dt:.1f} s"},
+                "note": "the reference is single-threaded Java (no JDK in the image, see java_probe): the C++ port is timed instead"}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define SDPB_ABI_VERSION 3
+#define SDPB_ABI_VERSION 4
 
 typedef enum sdpb_status {
     SDPB_OK = 0,
@@ -59,8 +59,10 @@ typedef enum sdpb_status {
     SDPB_ERR_CUDA = -4,       /* a CUDA runtime call failed (see sdpb_last_error)     */
     SDPB_ERR_STATE = -5,      /* call out of order (e.g. value before solve)          */
     SDPB_ERR_NOMEM = -6,
-    SDPB_ERR_UNSOLVED = -7    /* query of a state outside the grid (Java: NullPointerException,
+    SDPB_ERR_UNSOLVED = -7,   /* query of a state outside the grid (Java: NullPointerException,
                                  Recursion.java:165-167)                               */
+    SDPB_ERR_PEER = -8        /* multi-GPU exchange: a peer's tables cannot be mapped, or a peer did not
+                                 deliver its rows of V_t in time                         */
 } sdpb_status;
 
 /* Which immediate-value / transition lambdas the descriptor stands for. */
@@ -191,6 +193,15 @@ typedef struct sdpb_model {
     const int32_t* apmf_len;
     const double*  apmf_p;
     const double*  min_level_t;
+
+    /* Terminal boundary function (FinalCash.BoundaryFuncton, src/sdp/inventory/FinalCash.java:16-18, consumed
+     * at src/sdp/cash/multiItem/CashRecursionV.java:125-128: a state of period T+1 is worth b(s)).  NULL =
+     * the engines without one: no continuation in period T (Recursion.java:140 `if (n < T)`).  Otherwise
+     * n_states doubles in the library's state order (sdpb_state_of_index gives the coordinates of entry i),
+     * V_{T+1}(s) = terminal_value[index of s]: period T then accumulates (p*gamma) * V_{T+1}(f(s,a,d)) like every
+     * other period.  Copied by sdpb_create.  Not available with SDPB_REC_SURVIVAL (its terminal rule is the
+     * indicator of RiskRecursion.java:80-84). */
+    const double* terminal_value;
 } sdpb_model;
 
 typedef enum sdpb_kernel_choice {
@@ -230,7 +241,24 @@ typedef struct sdpb_options {
     int32_t  dedup;        /* 1 = states that provably share (c,f) for every (a,d) are solved once
                               and broadcast (exact; lead-time kinds). 0 = brute force per state. */
     void*    stream;       /* cudaStream_t to launch on; NULL = a stream owned by the handle */
+    uint32_t allow;        /* sdpb_allow bits: dense-grid artefacts sdpb_reach reports as SDPB_ERR_OFFGRID unless allowed */
+    int32_t  strict_cash_bounds; /* 1: sdpb_reach also fails when a state the reference would visit has its successor cash
+                              clamped at cash_min / cash_max (the clamp is part of the reference lambdas,
+                              CashConstraint.java:128-129, so this is off by default) */
+    int32_t  profile;      /* 1: a sharded solve records CUDA events around every period's kernels, pushes and
+                              waits (sdpb_period_profile) */
+    int32_t  reserved;
 } sdpb_options;
+
+/* A dense grid solves EVERY grid state, the reference only the states it reaches from the initial state.
+ * Two artefacts of the dense grid are therefore harmless as long as no reached state is touched by them, and
+ * wrong answers otherwise; sdpb_reach checks exactly that and fails with SDPB_ERR_OFFGRID unless allowed here:
+ *   SDPB_ALLOW_CLIPPED_SUCCESSORS  a reached (state, action, demand) whose successor inventory lies outside
+ *                                  [inv_min, inv_max] although the model does not clamp (SDPB_F_CLAMP_INV off,
+ *                                  Leadtime.java:65-66): the kernels fold it onto the boundary row
+ *   SDPB_ALLOW_CAPPED_ACTIONS      a reached state of the XR kind whose order-up-to range
+ *                                  (CashConstraintXR.java:71-75, uncapped) is longer than max_order_idx + 1 */
+enum sdpb_allow { SDPB_ALLOW_CLIPPED_SUCCESSORS = 1u << 0, SDPB_ALLOW_CAPPED_ACTIONS = 1u << 1 };
 
 typedef struct sdpb_grid {
     int32_t ndim;          /* API state vector length: 1 + has_cash + lead_time */
@@ -240,6 +268,9 @@ typedef struct sdpb_grid {
     int32_t n_actions;     /* max_order_idx + 1 */
     int32_t T;
     int64_t cash_k_min;    /* integer cash index of the lowest cash point */
+    int64_t window_lo, window_hi; /* flattened range of V_t this handle holds in device memory: the whole grid when
+                              unsharded, else the rows its kernels can read (sdpb_shard_reads) plus a guard margin */
+    int64_t device_bytes;  /* bytes of device memory the handle allocated */
 } sdpb_grid;
 
 typedef struct sdpb_stats {
@@ -250,6 +281,12 @@ typedef struct sdpb_stats {
     int32_t kernel_used;    /* sdpb_kernel_choice actually run */
     double  fp64_ops;       /* fp64 add/mul/min/max instructions the kernels executed, by construction */
     double  evals_executed; /* = evals unless dedup folded identical states together */
+    /* what the last sdpb_reach saw at states the reference would visit (see sdpb_allow) */
+    double  clipped_successors; /* (s,a,d) triples whose successor inventory left the grid of an unclamped model */
+    double  capped_action_sets; /* XR states whose order-up-to range was cut at max_order_idx */
+    double  cash_bound_hits;    /* (s,a,d) triples whose successor cash was clamped at cash_min / cash_max */
+    double  exchange_ms;        /* sharded solve with sdpb_peer_attach: device time between the end of a period's
+                                   kernels and the arrival of every peer's rows, summed over periods (profile = 1) */
 } sdpb_stats;
 
 typedef struct sdpb_handle sdpb_handle;
@@ -259,6 +296,8 @@ int sdpb_abi_version(void);
  * binding (Panama FFM StructLayout, ctypes.Structure) verify its layout before the first call. */
 size_t sdpb_sizeof_model(void);
 size_t sdpb_sizeof_options(void);
+size_t sdpb_sizeof_grid(void);
+size_t sdpb_sizeof_stats(void);
 
 /* Build a solver for `m` on one GPU (opt may be NULL).  Validates that the grid is exact. */
 int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out);
@@ -334,6 +373,67 @@ int sdpb_eval_triples(sdpb_handle* h, int period, const double* states, const in
  *   lds_gbs     shared-memory LDS.128 bandwidth, GB/s
  * Any pointer may be NULL. */
 int sdpb_microbench(int device, double* nofma_tops, double* fma_tflops, double* lds_gbs);
+
+/* ---- grid bounds for models that do not clamp ------------------------------------------------------------------
+ * Inventory interval that contains every state the reference's top-down recursion can visit from the `n`
+ * period-1 states `init_states` (n * ndim doubles, API order) -- the bounds a caller must give the dense grid
+ * of an unclamped model (Leadtime.java:63-67 has none: its memo map simply grows).  Interval propagation
+ * through x' = x + (order or pipeline quantity in [0, max_order]) - d, d in [dmin_t, dmax_t], with the
+ * lost-sales lift and the model's own clamps applied; exact for the lead-time model, a superset otherwise.
+ * Pure host arithmetic: needs no device and no handle; m->inv_min / inv_max are ignored.
+ * Replaces nothing in the reference (its maps are unbounded); sdpb_reach reports a grid that is too small. */
+int sdpb_reachable_hull(const sdpb_model* m, const double* init_states, int n, double* inv_lo, double* inv_hi);
+
+/* ---- multi-GPU inside the library -------------------------------------------------------------------------------
+ * The state grid is cut into shard_count contiguous blocks of the flattened index (inventory outermost).  Each
+ * handle holds, for every period, only the window of V_t its kernels can read and the policy of its own block.
+ * After the kernels of period t every shard copies the rows of its block that a peer's window contains straight
+ * into that peer's table through peer-mapped device memory (NVLink), raises a flag in the peer's memory, and waits
+ * on the device for the flags of the peers it reads from before period t-1 starts: no host round trip, no
+ * collective library.  Two ways to connect the shards:
+ *
+ *   one process, several GPUs (what a JVM host does):   sdpb_group_create / sdpb_group_solve / ...
+ *   one process per GPU (torchrun, MPI):                sdpb_create with shard_rank / shard_count in every
+ *       process, sdpb_peer_export -> exchange the blobs by any means (they are plain bytes) ->
+ *       sdpb_peer_attach with all of them in rank order (CUDA IPC), then sdpb_solve in every process.
+ *
+ * Replaces: nothing in the reference (single-threaded Java); SURVEY.md section 8(e). */
+#define SDPB_PEER_BLOB_BYTES 256
+int sdpb_peer_export(sdpb_handle* h, void* blob /* SDPB_PEER_BLOB_BYTES */);
+int sdpb_peer_attach(sdpb_handle* h, const void* blobs /* shard_count * SDPB_PEER_BLOB_BYTES, rank order */,
+                     int n_blobs);
+/* bytes this shard sends to / receives from its peers per period (after sdpb_peer_attach) */
+int sdpb_peer_traffic(const sdpb_handle* h, int64_t* bytes_out, int64_t* bytes_in);
+/* profile = 1: device milliseconds of the last sharded solve per period, three doubles each
+ * (kernels, pushes to peers + flags, wait for the peers' flags), period 1 first. */
+int sdpb_period_profile(const sdpb_handle* h, double* ms /* 3 * T */);
+/* This shard's block of a period's tables: V and Q are (shard_hi - shard_lo) doubles each, either may be NULL. */
+int sdpb_shard_tables(sdpb_handle* h, int period, double* V, double* Q);
+
+typedef struct sdpb_group sdpb_group;
+/* n shards of one model on the CUDA devices `devices[0..n-1]` of this process (an ordinal may repeat).  opt may be
+ * NULL; its device / shard_rank / shard_count / stream are ignored. */
+int sdpb_group_create(const sdpb_model* m, const sdpb_options* opt, const int* devices, int n, sdpb_group** out);
+void sdpb_group_destroy(sdpb_group* g);
+const char* sdpb_group_last_error(const sdpb_group* g);
+int sdpb_group_solve(sdpb_group* g);            /* whole horizon on every shard; blocks */
+sdpb_handle* sdpb_group_shard(sdpb_group* g, int rank);
+/* getExpectedValue + getAction, each state answered by the shard that owns it */
+int sdpb_group_value(sdpb_group* g, int period, const double* states, int n, double* v, double* q);
+/* whole-grid tables of a period assembled from the shards' blocks (n_states doubles each) */
+int sdpb_group_period_tables(sdpb_group* g, int period, double* V, double* Q);
+/* evals / fp64_ops / launches summed over the shards, solve_ms = the slowest shard */
+int sdpb_group_stats(const sdpb_group* g, sdpb_stats* s);
+
+/* ---- many small instances at once ---------------------------------------------------------------------------------
+ * The reference's drivers sweep hundreds of small instances (810 in src/capacitated/CLSPTesting.java:57-61), one
+ * Recursion object each.  sdpb_solve_batch solves n independent unsharded handles of one device together: every
+ * handle's periods are enqueued on its own stream, the whole batch is replayed as ONE CUDA graph from the second
+ * call with the same handle list on, and the call returns when all are solved. */
+int sdpb_solve_batch(sdpb_handle* const* handles, int n);
+
+/* Return the memory cached by the library's private stream-ordered pool on `device` to the driver (-1 = current). */
+int sdpb_trim_pool(int device);
 
 #ifdef __cplusplus
 }

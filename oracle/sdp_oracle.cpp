@@ -42,6 +42,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -520,7 +521,9 @@ void solve_state(const Model& M, const St& s, NextValue&& next_value, double* va
             double dProb = M.staff() ? arow[j] : M.p(s.t, j);
             if (!survival) {
                 thisQValue += dProb * immediate(M, s, orderQty, randomDemand);
-                if (s.t < T) {
+                // Recursion.java:140 `if (n < T)`; with a boundary function the recursion goes one period further and
+                // the state of period T+1 is worth boundFinalCash.apply(s) (CashRecursionV.java:125-128)
+                if (s.t < T || m.terminal_value) {
                     St ns = transition(M, s, orderQty, randomDemand);
                     thisQValue += dProb * m.gamma * next_value(ns);
                 }
@@ -574,8 +577,10 @@ struct TopDown {
     const Model& M;
     std::map<St, double, KeyLess> cacheValues, cacheActions;
     double evals = 0;
+    std::function<double(const St&)> boundary;  // FinalCash.BoundaryFuncton: value of a state of period T+1
     explicit TopDown(const Model& m) : M(m) {}
     double getExpectedValue(const St& s) {
+        if (s.t > M.m.T) return boundary(s);  // CashRecursionV.java:125-128
         auto it = cacheValues.find(s);
         if (it != cacheValues.end()) return it->second;
         double val, best;
@@ -687,7 +692,7 @@ int oracle_dense(const sdpb_model* m, double* V, double* Q, double* evals, int64
     int nthreads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
     if (nthreads < 1) nthreads = 1;
     for (int t = T; t >= 1; t--) {
-        const double* Vn = t < T ? V + (size_t)t * S : nullptr;
+        const double* Vn = t < T ? V + (size_t)t * S : m->terminal_value;
         double* Vt = V + (size_t)(t - 1) * S;
         double* Qt = Q + (size_t)(t - 1) * S;
         std::atomic<int64_t> next{0};
@@ -741,6 +746,8 @@ int64_t oracle_topdown(const sdpb_model* m, const double* init_states, int n_ini
     Model M = make_model(m);
     Grid G(M);
     TopDown td(M);
+    if (m->terminal_value)  // the boundary function, tabulated on the grid by the caller
+        td.boundary = [&](const St& s) { bool o = false; return m->terminal_value[G.index(s, &o)]; };
     for (int i = 0; i < n_init; i++) {
         St s = G.from_api(1, init_states + (size_t)i * G.ndim());
         double v = td.getExpectedValue(s);
@@ -810,6 +817,7 @@ int oracle_step_states(const sdpb_model* m, int period, const double* Vnext, con
                        double* v_out, double* q_out) {
     Model M = make_model(m);
     Grid G(M);
+    if (!Vnext) Vnext = m->terminal_value;  // period T of a model with a boundary function
     for (int i = 0; i < n; i++) {
         St s = G.state(period, idx[i]);
         double val, best;

@@ -4,7 +4,7 @@ Everything that computes lives in libsdpb200.so (hand-written sm_100a CUDA, csrc
 is the host-side mirror of the reference's Java classes plus the descriptor builders.
 """
 from . import _abi as abi
-from ._abi import (COST_STAFF, COST_CASH_TWO_PRODUCT, KERNEL_LEAD_COL, KERNEL_LEAD_Q2, KERNEL_TWO_PRODUCT_ROW, KERNEL_FUSED, KERNEL_CASH_ROW, KERNEL_CASH_DIAG, COST_CASH_LOAN, COST_CASH_OD_LIMIT, COST_CASH_OD_TESTING, Q_TRUNC, KERNEL_CASH_INT, KERNEL_TILED2, KERNEL_LEAD_SLAB, COST_BACKORDER, COST_CASH_DEPOSIT, COST_CASH_OVERDRAFT, COST_CASH_XR, KERNEL_AUTO,
+from ._abi import (ALLOW_CAPPED_ACTIONS, ALLOW_CLIPPED_SUCCESSORS, COST_STAFF, COST_CASH_TWO_PRODUCT, KERNEL_LEAD_COL, KERNEL_LEAD_Q2, KERNEL_TWO_PRODUCT_ROW, KERNEL_FUSED, KERNEL_CASH_ROW, KERNEL_CASH_DIAG, COST_CASH_LOAN, COST_CASH_OD_LIMIT, COST_CASH_OD_TESTING, Q_TRUNC, KERNEL_CASH_INT, KERNEL_TILED2, KERNEL_LEAD_SLAB, COST_BACKORDER, COST_CASH_DEPOSIT, COST_CASH_OVERDRAFT, COST_CASH_XR, KERNEL_AUTO,
                    KERNEL_GENERIC, KERNEL_STAGED, KERNEL_TILED, MAX, MIN, Q_DIV, Q_LONGDIV, REC_EXPECT, REC_SURVIVAL,
                    SdpbError)
 from .getpmf import (GetPmfMulti, DiscreteDistribution, GammaDist, GetPmf, NormalDist, PoissonDist, UniformIntDist,
@@ -15,7 +15,7 @@ from .models import (workforce_model, two_product_cash_model, ModelSpec, cash_lo
 from .recursion import (StaffRecursion, StaffState, Actions, CashRecursionMulti, CashStateMulti, CashLeadtimeRecursion, CashLeadtimeState, CashRecursion, CashRecursionXR,
                         CashState, CashStateXR, LeadtimeRecursion, LeadtimeRecursion2, LeadtimeState,
                         OptDirection, Recursion, RiskRecursion, RiskState, State)
-from .solver import Solver
+from .solver import Group, Solver, reachable_hull, solve_batch
 from .simulation import CashSimulation, Simulation, generate_lh_samples
 from .sampling import MRG32k3a, Sampling
 from .write import WriteToCsv, WriteToExcelTxt, java_double

@@ -15,9 +15,13 @@ LIB_PATH = os.path.join(_HERE, "libsdpb200.so")
 # --- enums (include/sdpb200.h) -------------------------------------------------------------
 SDPB_OK = 0
 SDPB_ERR_ARG, SDPB_ERR_OFFGRID, SDPB_ERR_NO_DEVICE, SDPB_ERR_CUDA = -1, -2, -3, -4
-SDPB_ERR_STATE, SDPB_ERR_NOMEM, SDPB_ERR_UNSOLVED = -5, -6, -7
+SDPB_ERR_STATE, SDPB_ERR_NOMEM, SDPB_ERR_UNSOLVED, SDPB_ERR_PEER = -5, -6, -7, -8
 STATUS_NAMES = {0: "SDPB_OK", -1: "SDPB_ERR_ARG", -2: "SDPB_ERR_OFFGRID", -3: "SDPB_ERR_NO_DEVICE",
-                -4: "SDPB_ERR_CUDA", -5: "SDPB_ERR_STATE", -6: "SDPB_ERR_NOMEM", -7: "SDPB_ERR_UNSOLVED"}
+                -4: "SDPB_ERR_CUDA", -5: "SDPB_ERR_STATE", -6: "SDPB_ERR_NOMEM", -7: "SDPB_ERR_UNSOLVED",
+                -8: "SDPB_ERR_PEER"}
+ABI_VERSION = 4
+ALLOW_CLIPPED_SUCCESSORS, ALLOW_CAPPED_ACTIONS = 1, 2
+PEER_BLOB_BYTES = 256
 
 COST_BACKORDER, COST_CASH_DEPOSIT, COST_CASH_OVERDRAFT, COST_CASH_XR = 0, 1, 2, 3
 COST_CASH_OD_LIMIT, COST_CASH_OD_TESTING, COST_CASH_LOAN, COST_CASH_TWO_PRODUCT, COST_STAFF = 4, 5, 6, 7, 8
@@ -52,6 +56,7 @@ class SdpbModel(C.Structure):
         ("price2", C.c_double), ("vari_cost2", C.c_double), ("salvage2", C.c_double), ("pmf_d2", _dp),
         ("tie_tolerance", C.c_double),
         ("apmf_len", _ip), ("apmf_p", _dp), ("min_level_t", _dp),
+        ("terminal_value", _dp),
     ]
 
 
@@ -59,6 +64,7 @@ class SdpbOptions(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("shard_rank", C.c_int32),
         ("shard_count", C.c_int32), ("kernel", C.c_int32), ("dedup", C.c_int32), ("stream", C.c_void_p),
+        ("allow", C.c_uint32), ("strict_cash_bounds", C.c_int32), ("profile", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -67,6 +73,7 @@ class SdpbGrid(C.Structure):
         ("ndim", C.c_int32), ("n_inv", C.c_int32), ("n_cash", C.c_int32), ("n_q", C.c_int32),
         ("n_states", C.c_int64), ("shard_lo", C.c_int64), ("shard_hi", C.c_int64),
         ("n_actions", C.c_int32), ("T", C.c_int32), ("cash_k_min", C.c_int64),
+        ("window_lo", C.c_int64), ("window_hi", C.c_int64), ("device_bytes", C.c_int64),
     ]
 
 
@@ -75,6 +82,8 @@ class SdpbStats(C.Structure):
         ("evals", C.c_double), ("solve_ms", C.c_double), ("kernel_ms", C.c_double),
         ("launches", C.c_int32), ("kernel_used", C.c_int32), ("fp64_ops", C.c_double),
         ("evals_executed", C.c_double),
+        ("clipped_successors", C.c_double), ("capped_action_sets", C.c_double), ("cash_bound_hits", C.c_double),
+        ("exchange_ms", C.c_double),
     ]
 
 
@@ -84,6 +93,10 @@ EXPORTS = [
     "sdpb_last_error", "sdpb_grid_info", "sdpb_solve", "sdpb_solve_async", "sdpb_solve_period_async", "sdpb_sync",
     "sdpb_value", "sdpb_period_tables", "sdpb_device_tables", "sdpb_state_of_index", "sdpb_reach",
     "sdpb_opt_table", "sdpb_stats_get", "sdpb_eval_triples", "sdpb_microbench", "sdpb_simulate", "sdpb_shard_reads",
+    "sdpb_sizeof_grid", "sdpb_sizeof_stats", "sdpb_reachable_hull", "sdpb_peer_export", "sdpb_peer_attach",
+    "sdpb_peer_traffic", "sdpb_period_profile", "sdpb_shard_tables", "sdpb_group_create", "sdpb_group_destroy",
+    "sdpb_group_last_error", "sdpb_group_solve", "sdpb_group_shard", "sdpb_group_value", "sdpb_group_period_tables",
+    "sdpb_group_stats", "sdpb_solve_batch", "sdpb_trim_pool",
 ]
 
 _lib = None
@@ -140,7 +153,30 @@ def load():
     lib.sdpb_eval_triples.argtypes = [vp, C.c_int, _dp, _ip, _dp, C.c_int, _dp, _dp, _ip]
     lib.sdpb_microbench.argtypes = [C.c_int, _dp, _dp, _dp]
     lib.sdpb_simulate.argtypes = [vp, _dp, _dp, C.c_int, C.c_double, _dp]
-    if lib.sdpb_sizeof_model() != C.sizeof(SdpbModel) or lib.sdpb_sizeof_options() != C.sizeof(SdpbOptions):
-        raise ImportError("libsdpb200.so struct layout differs from the ctypes binding")
+    lib.sdpb_sizeof_grid.restype = C.c_size_t
+    lib.sdpb_sizeof_stats.restype = C.c_size_t
+    lib.sdpb_reachable_hull.argtypes = [C.POINTER(SdpbModel), _dp, C.c_int, _dp, _dp]
+    lib.sdpb_peer_export.argtypes = [vp, vp]
+    lib.sdpb_peer_attach.argtypes = [vp, vp, C.c_int]
+    lib.sdpb_peer_traffic.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.sdpb_period_profile.argtypes = [vp, _dp]
+    lib.sdpb_shard_tables.argtypes = [vp, C.c_int, _dp, _dp]
+    lib.sdpb_group_create.argtypes = [C.POINTER(SdpbModel), C.POINTER(SdpbOptions), _ip, C.c_int, C.POINTER(vp)]
+    lib.sdpb_group_destroy.argtypes = [vp]
+    lib.sdpb_group_destroy.restype = None
+    lib.sdpb_group_last_error.argtypes = [vp]
+    lib.sdpb_group_last_error.restype = C.c_char_p
+    lib.sdpb_group_solve.argtypes = [vp]
+    lib.sdpb_group_shard.argtypes = [vp, C.c_int]
+    lib.sdpb_group_shard.restype = vp
+    lib.sdpb_group_value.argtypes = [vp, C.c_int, _dp, C.c_int, _dp, _dp]
+    lib.sdpb_group_period_tables.argtypes = [vp, C.c_int, _dp, _dp]
+    lib.sdpb_group_stats.argtypes = [vp, C.POINTER(SdpbStats)]
+    lib.sdpb_solve_batch.argtypes = [C.POINTER(vp), C.c_int]
+    lib.sdpb_trim_pool.argtypes = [C.c_int]
+    if (lib.sdpb_sizeof_model() != C.sizeof(SdpbModel) or lib.sdpb_sizeof_options() != C.sizeof(SdpbOptions)
+            or lib.sdpb_sizeof_grid() != C.sizeof(SdpbGrid) or lib.sdpb_sizeof_stats() != C.sizeof(SdpbStats)
+            or lib.sdpb_abi_version() != ABI_VERSION):
+        raise ImportError("libsdpb200.so struct layout / ABI version differs from the ctypes binding")
     _lib = lib
     return lib

@@ -8,8 +8,6 @@ import numpy as np
 
 from . import _abi as A
 
-_solvers = {}
-
 
 def random_triple(spec, rng):
     """((period, *state), action, demand) with the state on the grid and the demand from the pmf."""
@@ -36,12 +34,10 @@ def random_triple(spec, rng):
     return (t, *vec), a, d
 
 
-def eval_descriptor(spec, st, a, d, solver=None):
-    """-> (c, next state vector (API order), |A(s)|), computed by the GPU library."""
-    from .solver import Solver
-    s = solver or _solvers.get(id(spec))
-    if s is None:
-        s = _solvers[id(spec)] = Solver(spec)
+def eval_descriptor(spec, st, a, d, solver):
+    """-> (c, next state vector (API order), |A(s)|), computed by the GPU library on `solver`'s handle (the engine's
+    own: no second copy of the grid, nothing cached across engines)."""
+    s = solver
     t, vec = st[0], np.ascontiguousarray([st[1:]], dtype=np.float64)
     base = vec[0, 0] if spec.cost_kind == A.COST_CASH_XR else 0.0
     ai = np.ascontiguousarray([int(round((a - base) / spec.step))], dtype=np.int32)

@@ -491,7 +491,8 @@ inline int launch_cash_diag(const CashPlan& P, const sdpb_model& m, const DevMod
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     const double waves = (double)grid.x * grid.y * (kDiagCols / 32) / (16.0 * sm_count);
     int parts = waves >= 6.0 ? 1 : (waves >= 3.0 ? 2 : 4);
-    if (const char* e = std::getenv("SDPB_DIAG_SPLIT")) parts = std::atoi(e) == 1 ? 1 : std::atoi(e) == 2 ? 2 : 4;  // tuning knob
+    static const int env_split = [] { const char* e = std::getenv("SDPB_DIAG_SPLIT"); return e ? std::atoi(e) : 0; }();
+    if (env_split) parts = env_split == 1 ? 1 : env_split == 2 ? 2 : 4;  // tuning knob, read once per process
     const size_t smem = (((size_t)D * 24 + 15) & ~(size_t)15) + (size_t)(parts - 1) * kDiagYT * kDiagCols * 12 + 16;
     const bool surv = m.recursion == SDPB_REC_SURVIVAL;
 #define SDPB_DIAG_LAUNCH(NT)                                                                      \
@@ -578,7 +579,7 @@ bi_cash_row(const __grid_constant__ DevModel M, const int t, const int D, const 
             const double endCash = A.initCash + inc;                               // CashConstraint.java:116-119
             if (endCash < 0.0) inc += M.pen * endCash;
             if (!SURVIVAL) acc += e.p * inc;                                       // CashRecursion.java:117
-            if (S.last) {
+            if (Vn == nullptr) {  // period T without a boundary function
                 if (SURVIVAL) {                                                    // RiskRecursion.java:80-84
                     const double finalCash = A.initCash + inc;
                     acc += e.p * (finalCash >= 0.0 ? 1.0 : 0.0);

@@ -184,7 +184,8 @@ inline void plan_fused(FusedPlan& P, const sdpb_model& m, const DevModel& d, con
                        const std::vector<int>& pmf_off, const std::vector<int>& pdi, int sm_count, int shard_count) {
     P.ok = false;
     if (m.cost_kind != SDPB_COST_BACKORDER || m.lead_time != 0 || shard_count != 1) return;
-    if (!(m.flags & SDPB_F_CLAMP_INV) || (m.flags & SDPB_F_GY_MODE)) return;
+    if (!(m.flags & SDPB_F_CLAMP_INV) || (m.flags & (SDPB_F_GY_MODE | SDPB_F_NO_ORDER_LAST))) return;
+    if (m.terminal_value) return;  // period T would need the boundary table: per-period kernels handle it
     const long long S = d.S;
     const int A = d.max_order_idx + 1;
     const int G = (int)std::min<long long>(sm_count, S);

@@ -30,6 +30,7 @@ struct StateCtx {
     int ix, iq1, iq2, iw;
     double x, q1, w;  // w: cash (R for the XR kind)
     int nA;           // |A(s)|
+    bool capped;      // XR kind: the order-up-to range of CashConstraintXR.java:71-75 is longer than max_order_idx + 1
     double price, v, ovh;
     bool last, lost, gy;
     long long strideX;
@@ -78,11 +79,13 @@ __device__ __forceinline__ StateCtx decode_state(const DevModel& M, int t, long 
 
     // feasible actions
     int nA = M.max_order_idx + 1;
+    S.capped = false;
     if (KIND == SDPB_COST_CASH_XR) {
         // CashConstraintXR.java:71-75
         const double rv = S.w / S.v;
         const double maxY = rv < S.x ? S.x : rv;
         const int length = (int)(maxY - S.x) + 1;
+        S.capped = length > nA;  // dense-grid artefact: the reference has no cap (sdpb_reach reports it)
         nA = length < nA ? length : nA;
     } else {
         if (M.flags & SDPB_F_CASH_LIMITED_ACTIONS) {
@@ -250,6 +253,24 @@ __device__ __forceinline__ long long successor(const DevModel& M, const StateCtx
     return il * S.strideX + A.pipe + kw;
 }
 
+// What the dense grid did to the successor that the reference's lambdas would not have done:
+// bit 0: the inventory level left [inv_min, inv_max] although the model does not clamp (Leadtime.java:65-66) and
+//        was folded onto the boundary row;  bit 1: the cash balance was clamped at cash_min / cash_max (part of
+//        the reference lambdas, CashConstraint.java:128-129; reported only on request).  Used by reach_forward.
+template <int KIND>
+__device__ __forceinline__ unsigned successor_clip(const DevModel& M, const StateCtx& S, const ActionCtx& A, int di,
+                                                   double c, double after) {
+    unsigned r = 0;
+    int il = A.iy - di;
+    if (S.lost) il = max(il, M.i_zero);
+    if (!(M.flags & SDPB_F_CLAMP_INV) && (il < 0 || il > M.nI - 1)) r |= 1u;
+    if (KIND != SDPB_COST_BACKORDER) {
+        const double nw = (KIND == SDPB_COST_CASH_OD_TESTING) ? after : A.initCash + c;
+        if (nw > M.cash_max || nw < M.cash_min) r |= 2u;
+    }
+    return r;
+}
+
 // successor() in 32-bit integer arithmetic for DevModel::small grids (identical results: every quantity is
 // below 2^31 there, checked on the host).
 template <int KIND>
@@ -304,7 +325,7 @@ bi_generic(const __grid_constant__ DevModel M, const int t, const int D, const i
     for (int i = lane; i < S.nA; i += G) {
         const ActionCtx A = prep_action<KIND>(M, S, i);
         double acc = 0.0;
-        if (S.last) {
+        if (Vn == nullptr) {  // period T of an engine without a boundary function (Recursion.java:140)
             for (int j = 0; j < D; j++) {
                 double after;
                 const double2 dp = __ldg(rec + 2 * j);
@@ -428,7 +449,7 @@ bi_backorder_staged(const __grid_constant__ DevModel M, const int t, const int D
             pipe[r] = pipe_q2 + i;
             acc[r] = 0.0;
         }
-        if (S.last) {
+        if (Vn == nullptr) {
             for (int j = 0; j < D; j++) {
                 const double2 pp = PP[j];
                 const double L = my[j].L;
@@ -492,23 +513,34 @@ expand_dedup(const __grid_constant__ DevModel M, const double* __restrict__ Hv, 
 template <int KIND, bool SURVIVAL>
 __global__ void __launch_bounds__(256)
 reach_forward(const __grid_constant__ DevModel M, const int t, const int D, const int pmf_off,
-              const unsigned char* __restrict__ mask_t, unsigned char* __restrict__ mask_n) {
+              const unsigned char* __restrict__ mask_t, unsigned char* __restrict__ mask_n,
+              unsigned long long* __restrict__ counters) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M.S || !mask_t[idx]) return;
     const StateCtx S = decode_state<KIND>(M, t, idx);
     const double* __restrict__ pd = M.pmf_d + pmf_off;
     const int* __restrict__ pdi = M.pmf_di + pmf_off;
-    for (int i = 0; i < S.nA; i++) {
+    // dense-grid artefacts at a state the reference visits: [0] clipped successors, [1] capped action sets,
+    // [2] successors whose cash hit a bound (see successor_clip)
+    unsigned n_clip = 0, n_cash = 0;
+    const bool has_next = mask_n != nullptr;  // period T: the recursion stops (no transition is evaluated)
+    for (int i = 0; has_next && i < S.nA; i++) {
         const ActionCtx A = prep_action<KIND>(M, S, i);
         for (int j = 0; j < D; j++) {
             double after;
             const double c = immediate<KIND>(M, S, A, __ldg(pd + j), after);
             bool bankrupt;
             const long long ni = successor<KIND>(M, S, A, __ldg(pdi + j), c, after, bankrupt);
+            const unsigned clip = successor_clip<KIND>(M, S, A, __ldg(pdi + j), c, after);
+            n_clip += clip & 1u;
+            n_cash += (clip >> 1) & 1u;
             // getSurvProb never recurses into a bankrupt successor (RiskRecursion.java:89-94)
             if (!(SURVIVAL && bankrupt)) mask_n[ni] = 1;
         }
     }
+    if (n_clip) atomicAdd(counters + 0, (unsigned long long)n_clip);
+    if (S.capped) atomicAdd(counters + 1, 1ull);
+    if (n_cash) atomicAdd(counters + 2, (unsigned long long)n_cash);
 }
 
 // One thread per sample path: roll the solved policy forward (Simulation.java:59-70).

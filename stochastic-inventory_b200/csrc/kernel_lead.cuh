@@ -262,7 +262,7 @@ inline int launch_lead(const LeadPlan& P, const DevModel& dm, int t, int D, int 
         rows = (hi - 1) / per_x - a.row0 + 1;
     }
     const long long blocks = rows * a.ny_tiles * a.nq2_tiles;
-    const bool last = (t == dm.T), mn = dm.is_min != 0;
+    const bool last = (Vn == nullptr), mn = dm.is_min != 0;  // period T without a terminal table
     cudaError_t e = cudaSuccess;
 #define SDPB_LEAD_LAUNCH(MN, LS, RQ_)                                                                  \
     {                                                                                                  \
@@ -460,10 +460,12 @@ inline ColPlan plan_col(const sdpb_model& m, const DevModel& d, int D, const int
     const int A = d.max_order_idx + 1;
     if (A > 512) return P;
     int max_threads = 512;  // measured best on C4 (512: 238 ms, 128: 244, 224: 270, 320: 317)
-    if (const char* e = std::getenv("SDPB_COL_THREADS")) max_threads = std::max(32, std::min(512, std::atoi(e)));  // tuning knob
+    static const int env_threads = [] { const char* e = std::getenv("SDPB_COL_THREADS"); return e ? std::atoi(e) : 0; }();
+    if (env_threads) max_threads = std::max(32, std::min(512, env_threads));  // tuning knob, read once per process
     P.NQB = m.lead_time == 2 ? std::max(1, std::min(max_threads / A, d.nQ)) : 1;
     P.nthreads = ((P.NQB * A + 31) / 32) * 32;
-    if (const char* e = std::getenv("SDPB_COL_YT")) P.YT = std::atoi(e) == 4 ? 4 : 8;  // tuning knob
+    static const int env_yt = [] { const char* e = std::getenv("SDPB_COL_YT"); return e ? std::atoi(e) : 0; }();
+    if (env_yt) P.YT = env_yt == 4 ? 4 : 8;  // tuning knob, read once per process
     const int n_levels = dedup ? d.nI + d.nQ - 1 : d.nQ;
     // real grid: one CTA walks the whole preQ1 axis; folded grid: 64 levels per CTA for parallelism
     P.LT = dedup ? 64 : ((n_levels + P.YT - 1) / P.YT) * P.YT;
@@ -494,7 +496,7 @@ inline int launch_col(const ColPlan& P, const DevModel& dm, int t, int D, int pm
         rows = (hi - 1) / per_x - a.row0 + 1;
     }
     const long long blocks = rows * a.n_ltiles * a.nq2_groups;
-    const bool last = (t == dm.T), mn = dm.is_min != 0;
+    const bool last = (Vn == nullptr), mn = dm.is_min != 0;  // period T without a terminal table
     cudaError_t e = cudaSuccess;
 #define SDPB_COL_LAUNCH(MN, LS)                                                                        \
     if (P.YT == 4) {                                                                                   \
@@ -711,7 +713,7 @@ inline Q2Plan plan_q2(const sdpb_model& m, const DevModel& d, int D, const int* 
 inline int launch_q2(const Q2Plan& P, const DevModel& dm, int t, int D, int pmf_off, const double* Vn, double* VnT,
                      double* Vt, int* Qt, long long lo, long long hi, int row0, int row1, cudaStream_t stream) {
     if (hi <= lo) return SDPB_OK;
-    const bool last = (t == dm.T), mn = dm.is_min != 0;
+    const bool last = (Vn == nullptr), mn = dm.is_min != 0;  // period T without a terminal table
     if (!last) {
         const unsigned tiles = (unsigned)((dm.nQ + 31) / 32);
         transpose_q2a<<<dim3((unsigned)(row1 - row0), tiles, tiles), dim3(32, 8), 0, stream>>>(Vn, VnT, dm.nQ, row0);
@@ -727,7 +729,8 @@ inline int launch_q2(const Q2Plan& P, const DevModel& dm, int t, int D, int pmf_
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     const double waves = (double)(a.f_end - a.f_begin) / 32.0 / (16.0 * sm_count);
     a.parts = waves >= 6.0 ? 1 : (waves >= 3.0 ? 2 : 4);
-    if (const char* e2 = std::getenv("SDPB_Q2_SPLIT")) a.parts = std::atoi(e2) == 1 ? 1 : std::atoi(e2) == 2 ? 2 : 4;  // tuning knob
+    static const int env_split = [] { const char* e2 = std::getenv("SDPB_Q2_SPLIT"); return e2 ? std::atoi(e2) : 0; }();
+    if (env_split) a.parts = env_split == 1 ? 1 : env_split == 2 ? 2 : 4;  // tuning knob, read once per process
     const int cols = P.NT / a.parts;
     const long long blocks = (a.f_end - a.f_begin + cols - 1) / cols;
     cudaError_t e = cudaSuccess;

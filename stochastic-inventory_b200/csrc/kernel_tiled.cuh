@@ -514,7 +514,7 @@ inline int launch_tiled(TiledPlan& P, const DevModel& dm, int t, int D, int pmf_
     if (!tp.ok && !tp.ok2) return SDPB_ERR_STATE;
     const long long n = hi - lo;
     if (n <= 0) return SDPB_OK;
-    const bool last = (t == dm.T);
+    const bool last = (Vn == nullptr);  // period T without a terminal table (Recursion.java:140)
     const bool mn = dm.is_min != 0;
     const long long target = 4LL * P.sm_count;  // about 4 CTAs per SM
     const double evals = (double)n * (dm.max_order_idx + 1) * D;
@@ -531,8 +531,9 @@ inline int launch_tiled(TiledPlan& P, const DevModel& dm, int t, int D, int pmf_
         int nsplit = 1;
         // enough CTAs for ~8 waves of 2 CTAs per SM: a grid of a few waves loses its last, partial one
         // (measured, C5: S = 1e6 32.9 -> 30.0 ms, S = 1e5 3.36 -> 3.17 ms; no change at 3e5 and 3e6)
+        static const int env_waves = [] { const char* e = std::getenv("SDPB_T2_WAVES"); return e ? std::max(1, std::atoi(e)) : 0; }();
         long long want = 16LL * P.sm_count;
-        if (const char* e = std::getenv("SDPB_T2_WAVES")) want = std::max(1, std::atoi(e)) * 2LL * P.sm_count;  // tuning knob
+        if (env_waves) want = env_waves * 2LL * P.sm_count;  // tuning knob, read once per process
         if (tiles2 < want) nsplit = (int)std::min<long long>(P.n_chunks2, (want + tiles2 - 1) / tiles2);
         const int cps = (P.n_chunks2 + nsplit - 1) / nsplit;
         nsplit = (P.n_chunks2 + cps - 1) / cps;

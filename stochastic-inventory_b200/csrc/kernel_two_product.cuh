@@ -16,7 +16,9 @@
 
 namespace sdpb {
 
-template <bool LAST>
+// LAST: period T (salvage, MultiItemCash.java:93-95).  NEXT: a continuation exists -- every period but T,
+// and period T too when the model carries a terminal boundary table (CashRecursionV.java:125-128).
+template <bool LAST, bool NEXT>
 __global__ void __launch_bounds__(128)
 bi_two_product(const __grid_constant__ DevModel M, const int t, const int D, const int pmf_off,
                const double* __restrict__ Vn, double* __restrict__ Vt, int* __restrict__ Qt,
@@ -64,7 +66,7 @@ bi_two_product(const __grid_constant__ DevModel M, const int t, const int D, con
                 if (LAST) salValue = M.salvage * endInventory1 + M.salvage2 * endInventory2;
                 const double c = (revenue - orderingCosts) + salValue;
                 acc += __ldg(pp + j) * c;  // CashRecursionMulti.java:101
-                if (!LAST) {
+                if (NEXT) {
                     // MultiItemCash.java:107-121: upper clamp on item 1, lower clamp on item 2 (the upper
                     // clip on item 2 is only the memory-safety bound of the dense grid)
                     int il1 = max(i1 + a1i - __ldg(di1 + j), M.i_zero);
@@ -196,7 +198,8 @@ inline bool plan_two_product_row(const sdpb_model& m, const DevModel& d, int t, 
 // Forward reachability for the two-product kind (what CashRecursionMulti's memoisation visits).
 __global__ void __launch_bounds__(128)
 reach_two_product(const __grid_constant__ DevModel M, const int t, const int D, const int pmf_off,
-                  const unsigned char* __restrict__ mask_t, unsigned char* __restrict__ mask_n) {
+                  const unsigned char* __restrict__ mask_t, unsigned char* __restrict__ mask_n,
+                  unsigned long long* __restrict__ counters) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M.S || !mask_t[idx]) return;
     long long r = idx;
@@ -207,6 +210,7 @@ reach_two_product(const __grid_constant__ DevModel M, const int t, const int D, 
     const double w = (double)(M.kmin + iw);
     const double v1 = M.v_t[t - 1], price1 = M.price_t[t - 1];
     const int Q = M.max_order_idx + 1;
+    unsigned n_clip = 0, n_cash = 0;
     for (int a1i = 0; a1i < Q; a1i++)
         for (int a2i = 0; a2i < Q; a2i++) {
             const double oc1 = v1 * (double)a1i, oc2 = M.v2 * (double)a2i;
@@ -220,9 +224,11 @@ reach_two_product(const __grid_constant__ DevModel M, const int t, const int D, 
                 const double c = revenue - orderingCosts;  // t < T here: no salvage
                 int il1 = max(i1 + a1i - M.pmf_di[pmf_off + j], M.i_zero);
                 int il2 = max(i2 + a2i - M.pmf_di2[pmf_off + j], M.i_zero);
+                n_clip += il2 > M.nI - 1;  // item 2 has no upper clamp in MultiItemCash.java:107-121: the grid's own clip
                 il1 = max(min(il1, M.nI - 1), 0);
                 il2 = min(max(il2, 0), M.nI - 1);
                 double nw = w + c;
+                n_cash += (nw > M.cash_max || nw < M.cash_min);
                 nw = nw > M.cash_max ? M.cash_max : nw;
                 nw = nw < M.cash_min ? M.cash_min : nw;
                 long long kw = (long long)nw - M.kmin;
@@ -230,6 +236,8 @@ reach_two_product(const __grid_constant__ DevModel M, const int t, const int D, 
                 mask_n[((long long)il1 * M.nI + il2) * M.nW + kw] = 1;
             }
         }
+    if (n_clip) atomicAdd(counters + 0, (unsigned long long)n_clip);
+    if (n_cash) atomicAdd(counters + 2, (unsigned long long)n_cash);
 }
 
 }  // namespace sdpb

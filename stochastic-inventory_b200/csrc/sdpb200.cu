@@ -8,8 +8,11 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
+
+#include <unistd.h>
 
 #include "../../include/sdpb200.h"
 #include "dev_model.cuh"
@@ -48,6 +51,40 @@ int upload(sdpb_handle* h, const std::vector<T>& v, T** out);
 
 }  // namespace
 
+// ---- multi-GPU: the other shards' tables, mapped into this process ------------------------------------------
+// What one shard tells the others (sdpb_peer_export): plain bytes, SDPB_PEER_BLOB_BYTES of them.
+struct PeerInfo {
+    uint32_t magic, version;
+    int32_t rank, world, device, T;
+    int64_t pid;
+    uint64_t base;             // slab address in the exporting process (used when importer and exporter share a process)
+    int64_t n_states, lo, hi;  // grid size, owned block
+    int64_t rlo, rhi;          // rows its kernels read (sdpb_shard_reads)
+    int64_t vlo, vhi;          // window it holds
+    uint64_t v_off0, v_stride; // address of V_t[i] = base + v_off0 + (t-1) * v_stride + (i - vlo) * 8
+    uint64_t flags_off;        // unsigned[64]: flags[r] = number of exchanges rank r has completed into this shard
+    uint64_t model_hash;
+    cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(PeerInfo) <= SDPB_PEER_BLOB_BYTES, "peer blob too small");
+constexpr uint32_t kPeerMagic = 0x53445042u;  // "SDPB"
+constexpr int kMaxPeers = 64;
+constexpr size_t kSlabHeader = 1024;          // flags[64], error word, padding
+
+struct PeerSend { int rank; long long a, b; };  // rows [a, b) of my block that peer `rank` reads
+struct PeerLink {
+    bool attached = false;
+    std::vector<PeerInfo> info;        // [world]
+    std::vector<char*> mapped;         // [world] peers' slabs in this address space (own slab for own rank)
+    std::vector<char> ipc_opened;      // [world] mapped with cudaIpcOpenMemHandle (must be closed)
+    std::vector<PeerSend> sends;
+    std::vector<int> recv_from;
+    unsigned** d_targets = nullptr;    // device array: address of flags[my rank] in every peer I send to
+    int* d_from = nullptr;             // device array: ranks I wait for
+    unsigned epoch = 0;                // exchanges completed so far (identical on every shard)
+    long long bytes_out = 0, bytes_in = 0;
+};
+
 struct sdpb_handle {
     sdpb_model m{};
     DevModel dm{};
@@ -83,30 +120,63 @@ struct sdpb_handle {
     long long vS = 0;          // virtual states per period
     double* dHv = nullptr;     // [vS] virtual value table of the period being solved
     int* dHa = nullptr;        // [vS] virtual policy table
-    double* dVT = nullptr;     // [S] V_{t+1} with the two pipeline axes transposed (bi_lead_q2)
+    double* dVT = nullptr;     // V_{t+1} with the two pipeline axes transposed (bi_lead_q2); indexed like dV
+    double* dTerm = nullptr;   // terminal boundary table V_{T+1} (sdpb_model.terminal_value); indexed like dV
+    // What is held in device memory.  dV[t][i] is valid for vlo <= i < vhi (the whole grid when unsharded, else
+    // the rows this shard's kernels can read plus a guard margin) and dQ[t][i] for lo <= i < hi: the pointers are
+    // biased so that kernels keep indexing with absolute flattened indices.
+    long long vlo = 0, vhi = 0;
+    size_t device_bytes = 0;
+    char* slab = nullptr;      // sharded handles: ONE cudaMalloc allocation (CUDA IPC cannot export pool memory)
+    size_t slab_bytes = 0;
+    size_t v_off0 = 0, v_stride = 0;  // byte offset of element vlo of V_1 inside the slab; bytes between periods
+    unsigned long long* dCounters = nullptr;  // [4] dense-grid artefacts seen by sdpb_reach
+    double reach_cnt[3] = {0, 0, 0};
+    PeerLink peer;
+    std::vector<cudaEvent_t> prof_ev;  // profile = 1: 4 events per period
+    std::vector<double> prof_ms;       // [3 * T] of the last sharded solve
     std::string err;
 };
 
 namespace {
 
-// Device memory comes from the stream-ordered pool allocator with the release threshold lifted, so a
-// create/solve/destroy cycle reuses the previous cycle's memory instead of paying cudaMalloc/cudaFree
-// (cudaFree of the C5 tables alone cost 1.1 s per cycle).
-cudaError_t dev_alloc(sdpb_handle* h, void** p, size_t bytes) {
-    cudaError_t e = cudaMallocAsync(p, std::max<size_t>(bytes, 16), h->stream);
-    if (e == cudaSuccess) h->dev_allocs.push_back(*p);
-    return e;
-}
+// Device memory comes from a stream-ordered pool PRIVATE to this library (one per device) whose release
+// threshold is lifted, so a create/solve/destroy cycle reuses the previous cycle's memory instead of paying
+// cudaMalloc/cudaFree (cudaFree of the C5 tables alone cost 1.1 s per cycle).  The process-wide default pool
+// is left alone: a JVM host's other libraries keep their allocator behaviour.  sdpb_trim_pool gives the cached
+// memory back.
+std::mutex g_pool_mu;
+cudaMemPool_t g_pools[64] = {};
 
-void lift_pool_threshold(int dev) {
-    static bool done[64] = {false};
-    if (dev < 0 || dev >= 64 || done[dev]) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+cudaMemPool_t library_pool(int dev) {
+    if (dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_pools[dev]) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         unsigned long long thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        g_pools[dev] = pool;
     }
-    done[dev] = true;
+    return g_pools[dev];
+}
+
+cudaError_t pool_alloc(sdpb_handle* h, void** p, size_t bytes) {
+    cudaMemPool_t pool = library_pool(h->device);
+    if (pool) return cudaMallocFromPoolAsync(p, std::max<size_t>(bytes, 16), pool, h->stream);
+    return cudaMallocAsync(p, std::max<size_t>(bytes, 16), h->stream);
+}
+
+// long-lived allocation owned by the handle
+cudaError_t dev_alloc(sdpb_handle* h, void** p, size_t bytes) {
+    cudaError_t e = pool_alloc(h, p, bytes);
+    if (e == cudaSuccess) { h->dev_allocs.push_back(*p); h->device_bytes += std::max<size_t>(bytes, 16); }
+    return e;
 }
 
 template <class T>
@@ -315,7 +385,7 @@ int dispatch_generic_d(sdpb_handle* h, int t, const double* Vn, double* Vt, int*
         const long long nst = hi - lo;
         if (nst > 0) {
             const unsigned blocks = (unsigned)((nst + 7) / 8);
-            const bool last = t == h->m.T;
+            const bool last = Vn == nullptr;
             if (mn) { if (last) bi_staff<true, true><<<blocks, 256, 0, h->stream>>>(h->dm, t, Vn, Vt, Qt, lo, hi);
                       else bi_staff<true, false><<<blocks, 256, 0, h->stream>>>(h->dm, t, Vn, Vt, Qt, lo, hi); }
             else    { if (last) bi_staff<false, true><<<blocks, 256, 0, h->stream>>>(h->dm, t, Vn, Vt, Qt, lo, hi);
@@ -327,7 +397,8 @@ int dispatch_generic_d(sdpb_handle* h, int t, const double* Vn, double* Vt, int*
         if (DEDUP) { h->err = "no lead time to fold"; return SDPB_ERR_ARG; }
         const long long nst = hi - lo;
         const int Dt = h->pmf_len[t - 1];
-        if (nst > 0 && h->opt.kernel != SDPB_KERNEL_GENERIC && plan_two_product_row(h->m, h->dm, t, Dt)) {
+        const bool term_T = t == h->m.T && Vn != nullptr;  // boundary table: the row kernel folds LAST and 'no continuation'
+        if (nst > 0 && !term_T && h->opt.kernel != SDPB_KERNEL_GENERIC && plan_two_product_row(h->m, h->dm, t, Dt)) {
             // CTA = one (inv1, inv2) pair x 128 cash levels; cash-independent terms shared through shared memory
             const int segs = (h->dm.nW + 127) / 128;
             const long long pair0 = lo / h->dm.nW, pair1 = (hi - 1) / h->dm.nW;
@@ -348,8 +419,9 @@ int dispatch_generic_d(sdpb_handle* h, int t, const double* Vn, double* Vt, int*
             h->stats.fp64_ops += count_evals_period(h, t) * (t == h->m.T ? 1.0 : 3.0);
         } else if (nst > 0) {
             const unsigned blocks = (unsigned)((nst + 127) / 128);
-            if (t == h->m.T) bi_two_product<true><<<blocks, 128, 0, h->stream>>>(h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi);
-            else bi_two_product<false><<<blocks, 128, 0, h->stream>>>(h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi);
+            if (term_T) bi_two_product<true, true><<<blocks, 128, 0, h->stream>>>(h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi);
+            else if (t == h->m.T) bi_two_product<true, false><<<blocks, 128, 0, h->stream>>>(h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi);
+            else bi_two_product<false, true><<<blocks, 128, 0, h->stream>>>(h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi);
         }
         break;
     }
@@ -404,14 +476,16 @@ bool staged_ok(const sdpb_handle* h, int t) {
 
 // Solve [lo, hi) of the real grid (or of the virtual grid when DEDUP) with the best kernel allowed.
 template <bool DEDUP>
-int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt, long long lo, long long hi) {
-    if (!DEDUP && h->dVT && (h->opt.kernel == SDPB_KERNEL_AUTO || h->opt.kernel == SDPB_KERNEL_LEAD_Q2)) {
+int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt, long long lo, long long hi,
+                      bool plain) {
+    const bool last = Vn == nullptr;  // no continuation: period T of a model without a boundary table
+    if (!plain && !DEDUP && h->dVT && (h->opt.kernel == SDPB_KERNEL_AUTO || h->opt.kernel == SDPB_KERNEL_LEAD_Q2)) {
         const Q2Plan qp = plan_q2(h->m, h->dm, h->pmf_len[t - 1], h->pmf_di.data() + h->pmf_off[t - 1]);
         if (qp.ok) {
             h->stats.kernel_used = SDPB_KERNEL_LEAD_Q2;
             const double ev = (double)(hi - lo) * (h->m.max_order_idx + 1) * h->pmf_len[t - 1];
-            h->stats.fp64_ops += ev * (t == h->m.T ? (1.0 + 2.0 * kQ2YT) / kQ2YT : (1.0 + 4.0 * kQ2YT) / kQ2YT);
-            if (t < h->m.T) h->stats.launches++;  // the transposition pass
+            h->stats.fp64_ops += ev * (last ? (1.0 + 2.0 * kQ2YT) / kQ2YT : (1.0 + 4.0 * kQ2YT) / kQ2YT);
+            if (!last) h->stats.launches++;  // the transposition pass
             int64_t rlo = 0, rhi = h->S;
             sdpb_shard_reads(h, &rlo, &rhi);
             const long long per_x = (long long)h->dm.nQ * h->dm.nQ;
@@ -419,14 +493,14 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
                              (int)(rlo / per_x), (int)(rhi / per_x), h->stream);
         }
     }
-    if (h->opt.kernel != SDPB_KERNEL_GENERIC && h->opt.kernel != SDPB_KERNEL_STAGED && h->m.lead_time >= 1 &&
+    if (!plain && h->opt.kernel != SDPB_KERNEL_GENERIC && h->opt.kernel != SDPB_KERNEL_STAGED && h->m.lead_time >= 1 &&
         h->m.cost_kind == SDPB_COST_BACKORDER) {
         const ColPlan cp = plan_col(h->m, h->dm, h->pmf_len[t - 1], h->pmf_di.data() + h->pmf_off[t - 1], DEDUP);
         if (cp.ok && h->opt.kernel != SDPB_KERNEL_LEAD_SLAB) {
             h->stats.kernel_used = SDPB_KERNEL_LEAD_COL;
             const double ev = (double)(hi - lo) * (h->m.max_order_idx + 1) * h->pmf_len[t - 1];
             // per YT evaluations: 1 new cost + YT (p*c) + YT adds (+ YT (p*gamma*V) + YT adds)
-            h->stats.fp64_ops += ev * (t == h->m.T ? (1.0 + 2.0 * cp.YT) / cp.YT : (1.0 + 4.0 * cp.YT) / cp.YT);
+            h->stats.fp64_ops += ev * (last ? (1.0 + 2.0 * cp.YT) / cp.YT : (1.0 + 4.0 * cp.YT) / cp.YT);
             return launch_col<DEDUP>(cp, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi, h->stream);
         }
         const LeadPlan lp = plan_lead(h->m, h->dm, h->pmf_len[t - 1], h->pmf_di.data() + h->pmf_off[t - 1]);
@@ -434,21 +508,21 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
             h->stats.kernel_used = SDPB_KERNEL_LEAD_SLAB;
             const double ev = (double)(hi - lo) * (h->m.max_order_idx + 1) * h->pmf_len[t - 1];
             const double q = 4.0 * lp.RQ;  // evaluations per thread per demand point
-            h->stats.fp64_ops += ev * (t == h->m.T ? (5.0 + q) / q : (5.0 + 3.0 * q) / q);
+            h->stats.fp64_ops += ev * (last ? (5.0 + q) / q : (5.0 + 3.0 * q) / q);
             return launch_lead<DEDUP>(lp, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi, h->stream);
         }
     }
     if (h->opt.kernel != SDPB_KERNEL_GENERIC && staged_ok(h, t)) {
         h->stats.kernel_used = SDPB_KERNEL_STAGED;
         // per evaluation: add, mul, add (+ mul, add when a continuation exists)
-        h->stats.fp64_ops += (double)(hi - lo) * (h->m.max_order_idx + 1) * h->pmf_len[t - 1] * (t == h->m.T ? 3.0 : 5.0);
+        h->stats.fp64_ops += (double)(hi - lo) * (plain ? 1 : h->m.max_order_idx + 1) * h->pmf_len[t - 1] * (last ? 3.0 : 5.0);
         return launch_staged<DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
     }
     if (!DEDUP && h->opt.kernel != SDPB_KERNEL_GENERIC && cash_row_ok(h->m, h->dm, h->pmf_len[t - 1])) {
         h->stats.kernel_used = SDPB_KERNEL_CASH_ROW;
         // cash-dependent tail per evaluation: deposit chain 4, salvage 1, end cash 1, p*c 2 (+ clamp / quantiser /
         // continuation 6 when a successor exists); compares and selects not counted
-        h->stats.fp64_ops += count_evals_period(h, t) * (t == h->m.T ? 8.0 : 14.0);
+        h->stats.fp64_ops += count_evals_period(h, t) * (last ? 8.0 : 14.0);
         return launch_cash_row(h->m, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi, h->stream);
     }
     if (h->stats.kernel_used == 0) h->stats.kernel_used = SDPB_KERNEL_GENERIC;
@@ -469,7 +543,8 @@ template <int KIND, bool SURV>
 void launch_reach(sdpb_handle* h, int t) {
     const long long blocks = (h->S + 255) / 256;
     reach_forward<KIND, SURV><<<(unsigned)blocks, 256, 0, h->stream>>>(
-        h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], h->dMask[t - 1], h->dMask[t]);
+        h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], h->dMask[t - 1], t < h->m.T ? h->dMask[t] : nullptr,
+        h->dCounters);
 }
 
 double count_evals_virtual(const sdpb_handle* h, int t) {
@@ -490,12 +565,12 @@ double count_evals_virtual(const sdpb_handle* h, int t) {
 
 // policy table as order quantities (doubles), converted on the device so the host copy is one memcpy
 __global__ void policy_to_double(const int* __restrict__ q, double* __restrict__ out, long long n, double step,
-                                 int xr, double inv_min, long long stride_x) {
+                                 int xr, double inv_min, long long stride_x, long long first) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int qi = q[i];
     double v = 0.0;  // bestOrderQty stays 0 when nothing beat the initial value
-    if (qi >= 0) v = xr ? (inv_min + (double)(i / stride_x) * step) + (double)qi * step : (double)qi * step;
+    if (qi >= 0) v = xr ? (inv_min + (double)((first + i) / stride_x) * step) + (double)qi * step : (double)qi * step;
     out[i] = v;
 }
 
@@ -505,16 +580,144 @@ __global__ void gather_vq(const long long* __restrict__ idx, int n, const double
     if (i < n) { v[i] = V[idx[i]]; q[i] = Q[idx[i]]; }
 }
 
+// ---- multi-GPU exchange ----------------------------------------------------------------------------------------
+// After the kernels of period t a shard copies the rows of its block that a peer reads into the peer's V_t
+// (cudaMemcpyAsync into peer-mapped memory: NVLink), then peer_signal stores the exchange count into the peer's
+// flag word; before period t-1 peer_wait spins on this shard's own flag words until every peer it reads from has
+// done the same.  Everything is stream-ordered on the device; the host never waits inside a solve.
+__global__ void peer_signal(unsigned* const* targets, int n, unsigned epoch) {
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(targets[i]), "r"(epoch) : "memory");
+}
+
+// flags[r] counts the exchanges rank r has completed into this shard.  A peer that never arrives must not hang the
+// GPU: after `timeout_ns` the kernel gives up and records which rank was missing in flags[kMaxPeers].
+__global__ void peer_wait(unsigned* flags, const int* from, int n, unsigned epoch, unsigned long long timeout_ns) {
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    unsigned* f = flags + from[i];
+    unsigned long long t0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int)(v - epoch) >= 0) break;
+        if (*(volatile unsigned*)(flags + kMaxPeers) != 0) break;  // an earlier wait already failed: do not wait again
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) { atomicExch(flags + kMaxPeers, 1u + (unsigned)from[i]); break; }
+        __nanosleep(256);
+    }
+}
+
+uint64_t model_hash(const sdpb_handle* h) {  // shards must describe the same model: a cheap fingerprint
+    uint64_t x = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) {
+        const unsigned char* b = (const unsigned char*)p;
+        for (size_t i = 0; i < n; i++) { x ^= b[i]; x *= 1099511628211ull; }
+    };
+    const sdpb_model& m = h->m;
+    mix(&m.cost_kind, sizeof(int32_t) * 7);
+    mix(&m.gamma, sizeof(double));
+    mix(&m.inv_min, sizeof(double) * 5);
+    mix(&m.fixed_cost, sizeof(double) * 14);
+    mix(h->pmf_len.data(), h->pmf_len.size() * sizeof(int));
+    mix(h->pmf_d.data(), h->pmf_d.size() * sizeof(double));
+    mix(h->pmf_p.data(), h->pmf_p.size() * sizeof(double));
+    return x;
+}
+
+int solve_period(sdpb_handle* h, int t);
+
+// One period of a sharded solve: kernels, then (t > 1) the pushes and the flag.  `wait_now`: also enqueue the wait for
+// the peers' rows (a group driven by one host thread enqueues every shard's pushes first, then every shard's wait).
+int enqueue_period_exchange_wait(sdpb_handle* h) {
+    PeerLink& P = h->peer;
+    if (!P.recv_from.empty()) {
+        peer_wait<<<1, kMaxPeers, 0, h->stream>>>(reinterpret_cast<unsigned*>(h->slab), P.d_from, (int)P.recv_from.size(),
+                                                  P.epoch, 20ull * 1000000000ull);
+        CU(cudaGetLastError());
+    }
+    return SDPB_OK;
+}
+
+int enqueue_period_sharded(sdpb_handle* h, int t, bool wait_now) {
+    PeerLink& P = h->peer;
+    const bool prof = !h->prof_ev.empty();
+    cudaEvent_t* ev = prof ? h->prof_ev.data() + 4 * (size_t)(t - 1) : nullptr;
+    if (prof) CU(cudaEventRecord(ev[0], h->stream));
+    int rc = solve_period(h, t);
+    if (rc != SDPB_OK) return rc;
+    if (prof) CU(cudaEventRecord(ev[1], h->stream));
+    if (t > 1) {  // V_1 is read by nobody
+        P.epoch++;
+        for (const PeerSend& sd : P.sends) {
+            const PeerInfo& pi = P.info[sd.rank];
+            char* dst = P.mapped[sd.rank] + pi.v_off0 + (size_t)(t - 1) * pi.v_stride + (size_t)(sd.a - pi.vlo) * sizeof(double);
+            CU(cudaMemcpyAsync(dst, h->dV[t - 1] + sd.a, (size_t)(sd.b - sd.a) * sizeof(double), cudaMemcpyDefault, h->stream));
+        }
+        if (!P.sends.empty()) {
+            peer_signal<<<1, kMaxPeers, 0, h->stream>>>(P.d_targets, (int)P.sends.size(), P.epoch);
+            CU(cudaGetLastError());
+        }
+        if (prof) CU(cudaEventRecord(ev[2], h->stream));
+        if (wait_now) {
+            rc = enqueue_period_exchange_wait(h);
+            if (rc != SDPB_OK) return rc;
+            if (prof) CU(cudaEventRecord(ev[3], h->stream));
+        }
+    } else if (prof) {
+        CU(cudaEventRecord(ev[2], h->stream));
+        CU(cudaEventRecord(ev[3], h->stream));
+    }
+    return SDPB_OK;
+}
+
+// After the stream has drained: did a wait give up?  Fill the per-period profile.
+int finish_sharded(sdpb_handle* h) {
+    unsigned errw = 0;
+    CU(cudaMemcpy(&errw, h->slab + kMaxPeers * sizeof(unsigned), sizeof errw, cudaMemcpyDeviceToHost));
+    if (errw) {
+        h->err = "shard " + std::to_string(errw - 1) + " did not deliver its rows of V_t within 20 s";
+        return SDPB_ERR_PEER;
+    }
+    if (!h->prof_ev.empty()) {
+        h->prof_ms.assign(3 * (size_t)h->m.T, 0.0);
+        double ex = 0;
+        for (int t = 1; t <= h->m.T; t++) {
+            cudaEvent_t* ev = h->prof_ev.data() + 4 * (size_t)(t - 1);
+            for (int k = 0; k < 3; k++) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) != cudaSuccess) { cudaGetLastError(); ms = 0; }
+                h->prof_ms[3 * (size_t)(t - 1) + k] = ms;
+                if (k > 0) ex += ms;
+            }
+        }
+        h->stats.exchange_ms = ex;
+    }
+    return SDPB_OK;
+}
+
 int solve_period(sdpb_handle* h, int t) {
     const sdpb_model& m = h->m;
     if (t < 1 || t > m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
     if (t < m.T && !h->solved[t]) { h->err = "period t+1 not solved yet"; return SDPB_ERR_STATE; }
-    const double* Vn = t < m.T ? h->dV[t] : nullptr;
+    // V_{t+1}: the next period's table, or in period T the boundary table when the model has one
+    // (CashRecursionV.java:125-128), else nothing (Recursion.java:140)
+    const double* Vn = t < m.T ? h->dV[t] : h->dTerm;
     int rc = SDPB_ERR_STATE;
     const int D = h->pmf_len[t - 1];
+    // A(s) = {0} in period T (SingleProductLeadtime.java:74-75): only decode_state() knows that rule, so the
+    // period runs on the kernels that call it (generic, staged, cash_row) -- one period of T, one action per state
+    const bool plain = (m.flags & SDPB_F_NO_ORDER_LAST) && t == m.T;
+    // a boundary table in period T: the integer-exact cash kernels fold "last period" and "no continuation" into one
+    // template flag, so that one period takes the general path
+    const bool term_T = t == m.T && h->dTerm != nullptr;
     if (h->dedup) {
         // lead-time models: solve each distinct (x + preQ, ...) once, then broadcast (exact)
-        rc = run_period_kernel<true>(h, t, Vn, h->dHv, h->dHa, 0, h->vS);
+        rc = run_period_kernel<true>(h, t, Vn, h->dHv, h->dHa, 0, h->vS, plain);
         if (rc != SDPB_OK) return rc;
         switch (m.cost_kind) {
         case SDPB_COST_BACKORDER: launch_expand<SDPB_COST_BACKORDER>(h, h->dV[t - 1], h->dQ[t - 1]); break;
@@ -526,17 +729,16 @@ int solve_period(sdpb_handle* h, int t) {
         h->stats.launches += 2;
         h->stats.evals += count_evals_period(h, t);
         h->stats.evals_executed += count_evals_virtual(h, t);
-        (void)D;
         return SDPB_OK;
     }
-    if (h->tiled.available && h->opt.kernel != SDPB_KERNEL_GENERIC) {
+    if (h->tiled.available && h->opt.kernel != SDPB_KERNEL_GENERIC && !plain) {
         int variant = 1;
         rc = launch_tiled(h->tiled, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, h->dV[t - 1],
                           h->dQ[t - 1], h->lo, h->hi, h->stream, &h->stats.fp64_ops, &variant);
         if (rc == SDPB_OK) h->stats.kernel_used = variant == 2 ? SDPB_KERNEL_TILED2 : SDPB_KERNEL_TILED;
         else if (rc != SDPB_ERR_STATE) { h->err = "tiled kernel launch failed"; return rc; }
     }
-    if (rc == SDPB_ERR_STATE && h->opt.kernel != SDPB_KERNEL_GENERIC) {  // integer cash models
+    if (rc == SDPB_ERR_STATE && h->opt.kernel != SDPB_KERNEL_GENERIC && !plain && !term_T) {  // integer cash models
         rc = SDPB_ERR_STATE;
         if (h->opt.kernel != SDPB_KERNEL_CASH_INT)  // (as a request: skip the diagonal-window variant)
             rc = launch_cash_diag(h->cash, m, h->dm, t, D, h->pmf_off[t - 1], Vn, h->dV[t - 1], h->dQ[t - 1], h->lo,
@@ -547,10 +749,10 @@ int solve_period(sdpb_handle* h, int t) {
                              h->stream, &h->stats.fp64_ops, count_evals_period(h, t));
             if (rc == SDPB_OK && h->stats.kernel_used != SDPB_KERNEL_CASH_DIAG) h->stats.kernel_used = SDPB_KERNEL_CASH_INT;
         }
-        else if (rc != SDPB_ERR_STATE) { h->err = "cash kernel launch failed"; return rc; }
+        if (rc != SDPB_OK && rc != SDPB_ERR_STATE) { h->err = "cash kernel launch failed"; return rc; }
     }
     if (rc == SDPB_ERR_STATE)  // no specialised plan for this model / period
-        rc = run_period_kernel<false>(h, t, Vn, h->dV[t - 1], h->dQ[t - 1], h->lo, h->hi);
+        rc = run_period_kernel<false>(h, t, Vn, h->dV[t - 1], h->dQ[t - 1], h->lo, h->hi, plain);
     if (rc != SDPB_OK) return rc;
     CU(cudaGetLastError());
     h->solved[t - 1] = 1;
@@ -568,18 +770,26 @@ extern "C" {
 int sdpb_abi_version(void) { return SDPB_ABI_VERSION; }
 size_t sdpb_sizeof_model(void) { return sizeof(sdpb_model); }
 size_t sdpb_sizeof_options(void) { return sizeof(sdpb_options); }
+size_t sdpb_sizeof_grid(void) { return sizeof(sdpb_grid); }
+size_t sdpb_sizeof_stats(void) { return sizeof(sdpb_stats); }
 
 const char* sdpb_last_error(const sdpb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 void sdpb_destroy(sdpb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);  // (peers may still be reading flags this stream raises)
     if (h->stream) for (void* p : h->dev_allocs) cudaFreeAsync(p, h->stream);
     free_tiled(h->tiled);
+    for (size_t r = 0; r < h->peer.mapped.size(); r++)
+        if (h->peer.ipc_opened[r] && h->peer.mapped[r]) cudaIpcCloseMemHandle(h->peer.mapped[r]);
+    if (h->slab) cudaFree(h->slab);
+    for (cudaEvent_t e : h->prof_ev) if (e) cudaEventDestroy(e);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    cudaGetLastError();
     delete h;
 }
 
@@ -618,6 +828,10 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         !(m->cost_kind == SDPB_COST_CASH_DEPOSIT || m->cost_kind == SDPB_COST_CASH_OVERDRAFT))
         return fail_create(nullptr, SDPB_ERR_ARG, "survival recursion needs a cash kind");
     if (m->max_order_idx < 0) return fail_create(nullptr, SDPB_ERR_ARG, "max_order_idx < 0");
+    if (m->terminal_value && m->recursion == SDPB_REC_SURVIVAL)
+        return fail_create(nullptr, SDPB_ERR_ARG, "the survival recursion has its own terminal rule (RiskRecursion.java:80-84)");
+    if (m->terminal_value && opt && opt->dedup)
+        return fail_create(nullptr, SDPB_ERR_ARG, "a terminal value table need not depend on x + preQ only: dedup is off limits");
 
     // ---- exact-grid validation: every x, a, d is an integer multiple of a power-of-two step ----
     int ex;
@@ -788,7 +1002,6 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
-    lift_pool_threshold(dev);
     mark("stream, events");
 
     double *dp = nullptr;
@@ -831,20 +1044,92 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     h->dQ.assign(T, nullptr);
     h->dMask.assign(T, nullptr);
     h->solved.assign(T, 0);
-    for (int t = 0; t < T; t++) {
-        void* p = nullptr;
-        if (dev_alloc(h, &p, (size_t)h->Spad * sizeof(double)) != cudaSuccess)
-            return fail_create(h, SDPB_ERR_NOMEM, "allocation of a value table failed");
-        h->dV[t] = (double*)p;
-        if (dev_alloc(h, &p, (size_t)h->Spad * sizeof(int)) != cudaSuccess)
-            return fail_create(h, SDPB_ERR_NOMEM, "allocation of a policy table failed");
-        h->dQ[t] = (int*)p;
-    }
 
-    mark("V/Q allocated");
     // ---- exact folding of lead-time states (opt-in) ----
-    if (h->opt.dedup && m->lead_time >= 1) {
-        h->dedup = true;
+    if (h->opt.dedup && m->lead_time >= 1) h->dedup = true;
+    if (h->opt.kernel == SDPB_KERNEL_LEAD_Q2 &&
+        !(m->cost_kind == SDPB_COST_BACKORDER && m->lead_time == 2 && !h->dedup))
+        return fail_create(h, SDPB_ERR_ARG, "SDPB_KERNEL_LEAD_Q2 needs a backorder model with lead_time 2 and dedup off");
+    const bool want_vt = !h->dedup && m->cost_kind == SDPB_COST_BACKORDER && m->lead_time == 2 &&
+                         (h->opt.kernel == SDPB_KERNEL_AUTO || h->opt.kernel == SDPB_KERNEL_LEAD_Q2);
+
+    // ---- which part of every V_t this handle holds ----
+    // Unsharded: everything.  Sharded: the rows the shard's kernels read (sdpb_shard_reads) plus a guard margin of
+    // kWindowMarginRows inventory rows on either side -- register-window kernels prefetch a few levels past the
+    // last one they use -- clipped to the grid; the whole (padded) table when that is most of it anyway, so
+    // that an in-place all-gather stays possible.
+    constexpr long long kWindowMarginRows = 16;
+    h->vlo = 0;
+    h->vhi = h->Spad;
+    if (h->opt.shard_count > 1) {
+        int64_t rlo = 0, rhi = S;
+        sdpb_shard_reads(h, &rlo, &rhi);
+        const long long per_x = S / d.nI;
+        const long long wlo = std::max<long long>(0, rlo - kWindowMarginRows * per_x);
+        const long long whi = std::min<long long>(S, rhi + kWindowMarginRows * per_x);
+        if (rhi > rlo && (double)(whi - wlo) < 0.8 * (double)S) { h->vlo = wlo; h->vhi = whi; }
+        if (rhi <= rlo) { h->vlo = 0; h->vhi = 0; }  // an empty shard (more ranks than states) holds nothing
+    }
+    const long long vlen = h->vhi - h->vlo, qlen = h->hi - h->lo;
+    // tables start on 256-byte boundaries and keep the alignment absolute index i would have in a full table:
+    // element vlo sits (vlo % 32) doubles into its slot, so address(V[i]) == 8 * i (mod 256)
+    auto round256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t v_pad = (size_t)(h->vlo % 32) * sizeof(double), q_pad = (size_t)(h->lo % 64) * sizeof(int);
+    const size_t v_slot = round256(v_pad + (size_t)vlen * sizeof(double) + 256);
+    const size_t q_slot = round256(q_pad + (size_t)qlen * sizeof(int) + 256);
+    const int n_vtabs = T + (want_vt ? 1 : 0) + (m->terminal_value ? 1 : 0);
+    char* vbase = nullptr;
+    char* qbase = nullptr;
+    if (h->opt.shard_count > 1) {
+        // one plain cudaMalloc allocation: [header: peer flags][V tables][Q tables]
+        h->slab_bytes = kSlabHeader + (size_t)n_vtabs * v_slot + (size_t)T * q_slot;
+        if (cudaMalloc((void**)&h->slab, h->slab_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail_create(h, SDPB_ERR_NOMEM, "allocation of the shard's tables failed");
+        }
+        h->device_bytes += h->slab_bytes;
+        if (cudaMemsetAsync(h->slab, 0, kSlabHeader, h->stream) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_CUDA, "cudaMemset of the peer flags failed");
+        vbase = h->slab + kSlabHeader;
+        qbase = vbase + (size_t)n_vtabs * v_slot;
+    } else {
+        void* p = nullptr;
+        if (dev_alloc(h, &p, (size_t)n_vtabs * v_slot) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "allocation of the value tables failed");
+        vbase = (char*)p;
+        if (dev_alloc(h, &p, (size_t)T * q_slot) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "allocation of the policy tables failed");
+        qbase = (char*)p;
+    }
+    h->v_off0 = (size_t)(vbase - (h->slab ? h->slab : vbase)) + v_pad;
+    h->v_stride = v_slot;
+    auto v_table = [&](int k) { return reinterpret_cast<double*>(vbase + (size_t)k * v_slot + v_pad) - h->vlo; };
+    for (int t = 0; t < T; t++) {
+        h->dV[t] = v_table(t);
+        h->dQ[t] = reinterpret_cast<int*>(qbase + (size_t)t * q_slot + q_pad) - h->lo;
+    }
+    int next_tab = T;
+    if (want_vt) h->dVT = v_table(next_tab++);  // transposed successor table for the lead-time-2 kernel
+    if (m->terminal_value) {
+        h->dTerm = v_table(next_tab++);
+        if (vlen > 0 && cudaMemcpyAsync(h->dTerm + h->vlo, m->terminal_value + h->vlo,
+                                        (size_t)(std::min<long long>(h->vhi, S) - h->vlo) * sizeof(double),
+                                        cudaMemcpyHostToDevice, h->stream) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_CUDA, "upload of the terminal value table failed");
+        // pageable host memory: the copy has left the caller's buffer when the call returns; make it so for
+        // page-locked buffers too (the caller owns terminal_value only until sdpb_create returns)
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_CUDA, "upload of the terminal value table failed");
+        // (h->m.terminal_value keeps the caller's pointer value as a marker only; it is never dereferenced again)
+    }
+    {
+        void* p = nullptr;
+        if (dev_alloc(h, &p, 4 * sizeof(unsigned long long)) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "allocation failed");
+        h->dCounters = (unsigned long long*)p;
+    }
+    mark("V/Q allocated");
+    if (h->dedup) {
         h->vS = (long long)(d.nI + d.nQ - 1) * (m->lead_time >= 2 ? d.nQ : 1) * d.nW;
         void* p = nullptr;
         if (dev_alloc(h, &p, (size_t)h->vS * sizeof(double)) != cudaSuccess)
@@ -853,18 +1138,6 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
         if (dev_alloc(h, &p, (size_t)h->vS * sizeof(int)) != cudaSuccess)
             return fail_create(h, SDPB_ERR_NOMEM, "allocation of the folded policy table failed");
         h->dHa = (int*)p;
-    }
-
-    if (h->opt.kernel == SDPB_KERNEL_LEAD_Q2 &&
-        !(m->cost_kind == SDPB_COST_BACKORDER && m->lead_time == 2 && !h->dedup))
-        return fail_create(h, SDPB_ERR_ARG, "SDPB_KERNEL_LEAD_Q2 needs a backorder model with lead_time 2 and dedup off");
-    // ---- transposed successor table for the lead-time-2 kernel ----
-    if (!h->dedup && m->cost_kind == SDPB_COST_BACKORDER && m->lead_time == 2 &&
-        (h->opt.kernel == SDPB_KERNEL_AUTO || h->opt.kernel == SDPB_KERNEL_LEAD_Q2)) {
-        void* p = nullptr;
-        if (dev_alloc(h, &p, (size_t)h->S * sizeof(double)) != cudaSuccess)
-            return fail_create(h, SDPB_ERR_NOMEM, "allocation of the transposed value table failed");
-        h->dVT = (double*)p;
     }
 
     // ---- kernel plan ----
@@ -938,6 +1211,9 @@ int sdpb_grid_info(const sdpb_handle* h, sdpb_grid* g) {
     g->n_actions = h->m.max_order_idx + 1;
     g->T = h->m.T;
     g->cash_k_min = h->dm.kmin;
+    g->window_lo = h->vlo;
+    g->window_hi = h->vhi;
+    g->device_bytes = (int64_t)h->device_bytes;
     return SDPB_OK;
 }
 
@@ -951,6 +1227,7 @@ int sdpb_sync(sdpb_handle* h) {
     if (!h) return SDPB_ERR_ARG;
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
+    if (h->peer.attached) return finish_sharded(h);  // did a peer fail to deliver?
     return SDPB_OK;
 }
 
@@ -1008,9 +1285,20 @@ static int enqueue_all_periods(sdpb_handle* h) {
 int sdpb_solve_async(sdpb_handle* h) {
     if (!h) return SDPB_ERR_ARG;
     if (h->opt.shard_count != 1) {
-        h->err = "sdpb_solve needs an unsharded handle; step sharded handles with sdpb_solve_period_async "
-                 "and all-gather V_t between periods";
-        return SDPB_ERR_STATE;
+        if (!h->peer.attached) {
+            h->err = "a sharded handle solves with its peers: connect them first (sdpb_peer_export / sdpb_peer_attach, or "
+                     "sdpb_group_create), or step it with sdpb_solve_period_async and exchange V_t yourself";
+            return SDPB_ERR_STATE;
+        }
+        CU(cudaSetDevice(h->device));
+        std::fill(h->solved.begin(), h->solved.end(), 0);
+        h->stats = sdpb_stats{};
+        for (int t = h->m.T; t >= 1; t--) {
+            const int rc = enqueue_period_sharded(h, t, true);
+            if (rc != SDPB_OK) return rc;
+        }
+        h->solve_count++;
+        return SDPB_OK;
     }
     CU(cudaSetDevice(h->device));
     h->reached = false;
@@ -1056,6 +1344,7 @@ int sdpb_solve(sdpb_handle* h) {
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->stats.solve_ms = ms;
     h->stats.kernel_ms = ms;
+    if (h->opt.shard_count != 1) return finish_sharded(h);
     return SDPB_OK;
 }
 
@@ -1073,8 +1362,8 @@ int sdpb_value(sdpb_handle* h, int period, const double* states, int n, double* 
                      "NullPointerException from getAction on an unsolved state)";
             return SDPB_ERR_UNSOLVED;
         }
-        if (h->opt.shard_count > 1 && (idx[i] < h->lo || idx[i] >= h->hi) && q) {
-            h->err = "policy of a state owned by another shard";
+        if (h->opt.shard_count > 1 && (idx[i] < h->lo || idx[i] >= h->hi)) {
+            h->err = "state " + std::to_string(i) + " is owned by another shard (sdpb_group_value routes queries)";
             return SDPB_ERR_UNSOLVED;
         }
     }
@@ -1083,9 +1372,9 @@ int sdpb_value(sdpb_handle* h, int period, const double* states, int n, double* 
     int* dq = nullptr;
     // scratch from the stream-ordered pool: plain cudaMalloc/cudaFree synchronise the device and cost
     // tens of milliseconds next to large pooled tables
-    CU(cudaMallocAsync((void**)&dIdx, n * sizeof(long long), h->stream));
-    CU(cudaMallocAsync((void**)&dv, n * sizeof(double), h->stream));
-    CU(cudaMallocAsync((void**)&dq, n * sizeof(int), h->stream));
+    CU(pool_alloc(h, (void**)&dIdx, n * sizeof(long long)));
+    CU(pool_alloc(h, (void**)&dv, n * sizeof(double)));
+    CU(pool_alloc(h, (void**)&dq, n * sizeof(int)));
     std::vector<double> hv(n);
     std::vector<int> hq(n);
     cudaError_t e = cudaMemcpyAsync(dIdx, idx.data(), n * sizeof(long long), cudaMemcpyHostToDevice, h->stream);
@@ -1105,21 +1394,21 @@ int sdpb_value(sdpb_handle* h, int period, const double* states, int n, double* 
     return SDPB_OK;
 }
 
-int sdpb_period_tables(sdpb_handle* h, int period, double* V, double* Q) {
-    if (!h) return SDPB_ERR_ARG;
-    if (period < 1 || period > h->m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
-    if (!h->solved[period - 1]) { h->err = "period not solved"; return SDPB_ERR_STATE; }
+// V_t / Q_t of the flattened range [a, b) (inside what the handle holds) into host buffers that start at `a`.
+static int copy_tables(sdpb_handle* h, int period, long long a, long long b, double* V, double* Q) {
     CU(cudaSetDevice(h->device));
-    if (V) CU(cudaMemcpyAsync(V, h->dV[period - 1], (size_t)h->S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    const long long n = b - a;
+    if (n <= 0) return SDPB_OK;
+    if (V) CU(cudaMemcpyAsync(V, h->dV[period - 1] + a, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (!Q) CU(cudaStreamSynchronize(h->stream));
     if (Q) {
         double* dq = nullptr;
-        CU(cudaMallocAsync((void**)&dq, (size_t)h->S * sizeof(double), h->stream));
-        policy_to_double<<<(unsigned)((h->S + 255) / 256), 256, 0, h->stream>>>(
-            h->dQ[period - 1], dq, h->S, h->m.step, h->m.cost_kind == SDPB_COST_CASH_XR, h->m.inv_min,
-            (long long)h->dm.nW);
+        CU(pool_alloc(h, (void**)&dq, (size_t)n * sizeof(double)));
+        policy_to_double<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
+            h->dQ[period - 1] + a, dq, n, h->m.step, h->m.cost_kind == SDPB_COST_CASH_XR, h->m.inv_min,
+            (long long)h->dm.nW, a);
         cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaMemcpyAsync(Q, dq, (size_t)h->S * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(Q, dq, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
         cudaFreeAsync(dq, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) { h->err = std::string("sdpb_period_tables: ") + cudaGetErrorString(e); return SDPB_ERR_CUDA; }
@@ -1127,11 +1416,27 @@ int sdpb_period_tables(sdpb_handle* h, int period, double* V, double* Q) {
     return SDPB_OK;
 }
 
+int sdpb_period_tables(sdpb_handle* h, int period, double* V, double* Q) {
+    if (!h) return SDPB_ERR_ARG;
+    if (period < 1 || period > h->m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
+    if (!h->solved[period - 1]) { h->err = "period not solved"; return SDPB_ERR_STATE; }
+    // a sharded handle fills its own block of the caller's n_states-long buffers and leaves the rest alone
+    return copy_tables(h, period, h->lo, h->hi, V ? V + h->lo : nullptr, Q ? Q + h->lo : nullptr);
+}
+
+int sdpb_shard_tables(sdpb_handle* h, int period, double* V, double* Q) {
+    if (!h) return SDPB_ERR_ARG;
+    if (period < 1 || period > h->m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
+    if (!h->solved[period - 1]) { h->err = "period not solved"; return SDPB_ERR_STATE; }
+    return copy_tables(h, period, h->lo, h->hi, V, Q);
+}
+
 int sdpb_device_tables(sdpb_handle* h, int period, void** dV, void** dQidx) {
     if (!h) return SDPB_ERR_ARG;
     if (period < 1 || period > h->m.T) { h->err = "period out of range"; return SDPB_ERR_ARG; }
-    if (dV) *dV = h->dV[period - 1];
-    if (dQidx) *dQidx = h->dQ[period - 1];
+    // first element held: V_t[window_lo] and Q_t[shard_lo] (sdpb_grid_info); the whole table when unsharded
+    if (dV) *dV = h->dV[period - 1] + h->vlo;
+    if (dQidx) *dQidx = h->dQ[period - 1] + h->lo;
     return SDPB_OK;
 }
 
@@ -1161,7 +1466,10 @@ int sdpb_reach(sdpb_handle* h, const double* init_states, int n) {
         CU(cudaMemsetAsync(h->dMask[0] + idx, 1, 1, h->stream));
     }
     const bool surv = h->m.recursion == SDPB_REC_SURVIVAL;
-    for (int t = 1; t < T; t++) {
+    CU(cudaMemsetAsync(h->dCounters, 0, 4 * sizeof(unsigned long long), h->stream));
+    // periods 1..T-1 mark their successors; period T is visited only to see whether a reached state's action
+    // set was capped (mask_n == nullptr: no transition is evaluated)
+    for (int t = 1; t <= T; t++) {
         switch (h->m.cost_kind) {
         case SDPB_COST_BACKORDER: launch_reach<SDPB_COST_BACKORDER, false>(h, t); break;
         case SDPB_COST_CASH_DEPOSIT:
@@ -1177,17 +1485,40 @@ int sdpb_reach(sdpb_handle* h, const double* init_states, int n) {
         case SDPB_COST_CASH_OD_TESTING: launch_reach<SDPB_COST_CASH_OD_TESTING, false>(h, t); break;
         case SDPB_COST_CASH_LOAN: launch_reach<SDPB_COST_CASH_LOAN, false>(h, t); break;
         case SDPB_COST_CASH_TWO_PRODUCT:
-            reach_two_product<<<(unsigned)((h->S + 127) / 128), 128, 0, h->stream>>>(
-                h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], h->dMask[t - 1], h->dMask[t]);
+            if (t < T)
+                reach_two_product<<<(unsigned)((h->S + 127) / 128), 128, 0, h->stream>>>(
+                    h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], h->dMask[t - 1], h->dMask[t], h->dCounters);
             break;
         case SDPB_COST_STAFF:
-            reach_staff<<<(unsigned)((h->S + 127) / 128), 128, 0, h->stream>>>(h->dm, t, h->dMask[t - 1], h->dMask[t]);
+            if (t < T)
+                reach_staff<<<(unsigned)((h->S + 127) / 128), 128, 0, h->stream>>>(h->dm, t, h->dMask[t - 1], h->dMask[t]);
             break;
         }
         CU(cudaGetLastError());
     }
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(cnt, h->dCounters, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->reached = true;
+    for (int k = 0; k < 3; k++) h->reach_cnt[k] = (double)cnt[k];  // reported by sdpb_stats_get
+    // A dense-grid artefact at a state the reference itself would visit changes that state's value: refuse unless
+    // the caller said it is acceptable.  (The mask and the opt table stay available either way.)
+    if (cnt[0] && !(h->opt.allow & SDPB_ALLOW_CLIPPED_SUCCESSORS)) {
+        h->err = std::to_string(cnt[0]) + " successor(s) of states the reference would visit lie outside the inventory grid of "
+                 "a model that does not clamp (they were folded onto the boundary row): enlarge [inv_min, inv_max] "
+                 "(sdpb_reachable_hull) or pass SDPB_ALLOW_CLIPPED_SUCCESSORS";
+        return SDPB_ERR_OFFGRID;
+    }
+    if (cnt[1] && !(h->opt.allow & SDPB_ALLOW_CAPPED_ACTIONS)) {
+        h->err = std::to_string(cnt[1]) + " reached state(s) have an order-up-to range longer than max_order_idx + 1 "
+                 "(CashConstraintXR.java:71-75 has no cap): raise max_order_idx or pass SDPB_ALLOW_CAPPED_ACTIONS";
+        return SDPB_ERR_OFFGRID;
+    }
+    if (cnt[2] && h->opt.strict_cash_bounds) {
+        h->err = std::to_string(cnt[2]) + " successor(s) of reached states had their cash clamped at cash_min / cash_max "
+                 "(strict_cash_bounds)";
+        return SDPB_ERR_OFFGRID;
+    }
     return SDPB_OK;
 }
 
@@ -1242,7 +1573,7 @@ int sdpb_eval_triples(sdpb_handle* h, int period, const double* states, const in
     int *dA = nullptr, *dDi = nullptr, *dNa = nullptr;
     double *dD = nullptr, *dC = nullptr;
     cudaError_t e = cudaSuccess;
-    auto al = [&](void** p, size_t b) { if (e == cudaSuccess) e = cudaMallocAsync(p, b, h->stream); };
+    auto al = [&](void** p, size_t b) { if (e == cudaSuccess) e = pool_alloc(h, p, b); };
     al((void**)&dS, n * 8); al((void**)&dN, n * 8); al((void**)&dA, n * 4); al((void**)&dDi, n * 4);
     al((void**)&dNa, n * 4); al((void**)&dD, n * 8); al((void**)&dC, n * 8);
     auto cp = [&](void* d, const void* s, size_t b, cudaMemcpyKind k) { if (e == cudaSuccess) e = cudaMemcpyAsync(d, s, b, k, h->stream); };
@@ -1296,7 +1627,7 @@ int sdpb_simulate(sdpb_handle* h, const double* init_state, const double* sample
     const int** dQp = nullptr;
     int* dOff = nullptr;
     cudaError_t e = cudaSuccess;
-    auto al = [&](void** p, size_t b) { if (e == cudaSuccess) e = cudaMallocAsync(p, b, h->stream); };
+    auto al = [&](void** p, size_t b) { if (e == cudaSuccess) e = pool_alloc(h, p, b); };
     al((void**)&dS, (size_t)n * T * 8); al((void**)&dP, (size_t)T * 8); al((void**)&dV, (size_t)n * 8);
     al((void**)&dQp, (size_t)T * sizeof(int*)); al((void**)&dOff, 4);
     auto cp = [&](void* d, const void* s, size_t b, cudaMemcpyKind k) { if (e == cudaSuccess) e = cudaMemcpyAsync(d, s, b, k, h->stream); };
@@ -1368,9 +1699,415 @@ int sdpb_microbench(int device, double* nofma_tops, double* fma_tflops, double* 
     return e == cudaSuccess ? SDPB_OK : SDPB_ERR_CUDA;
 }
 
+// ---- multi-GPU: connecting the shards ------------------------------------------------------------------------------
+int sdpb_peer_export(sdpb_handle* h, void* blob) {
+    if (!h || !blob) return SDPB_ERR_ARG;
+    if (h->opt.shard_count < 2 || !h->slab) { h->err = "sdpb_peer_export needs a sharded handle"; return SDPB_ERR_STATE; }
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));  // the flag words are zero before anybody can see them
+    PeerInfo pi;
+    std::memset(&pi, 0, sizeof pi);
+    pi.magic = kPeerMagic; pi.version = SDPB_ABI_VERSION;
+    pi.rank = h->opt.shard_rank; pi.world = h->opt.shard_count; pi.device = h->device; pi.T = h->m.T;
+    pi.pid = (int64_t)getpid();
+    pi.base = (uint64_t)(uintptr_t)h->slab;
+    pi.n_states = h->S; pi.lo = h->lo; pi.hi = h->hi;
+    int64_t rlo = 0, rhi = 0;
+    sdpb_shard_reads(h, &rlo, &rhi);
+    pi.rlo = rlo; pi.rhi = rhi; pi.vlo = h->vlo; pi.vhi = h->vhi;
+    pi.v_off0 = h->v_off0; pi.v_stride = h->v_stride; pi.flags_off = 0;
+    pi.model_hash = model_hash(h);
+    CU(cudaIpcGetMemHandle(&pi.ipc, h->slab));
+    std::memset(blob, 0, SDPB_PEER_BLOB_BYTES);
+    std::memcpy(blob, &pi, sizeof pi);
+    return SDPB_OK;
+}
+
+int sdpb_peer_attach(sdpb_handle* h, const void* blobs, int n_blobs) {
+    if (!h || !blobs) return SDPB_ERR_ARG;
+    const int world = h->opt.shard_count, rank = h->opt.shard_rank;
+    if (world < 2 || !h->slab) { h->err = "sdpb_peer_attach needs a sharded handle"; return SDPB_ERR_STATE; }
+    if (n_blobs != world || world > kMaxPeers) { h->err = "need one blob per shard, in rank order (at most 64 shards)"; return SDPB_ERR_ARG; }
+    if (h->peer.attached) { h->err = "already attached"; return SDPB_ERR_STATE; }
+    CU(cudaSetDevice(h->device));
+    PeerLink& P = h->peer;
+    P.info.assign(world, PeerInfo{});
+    P.mapped.assign(world, nullptr);
+    P.ipc_opened.assign(world, 0);
+    const uint64_t my_hash = model_hash(h);
+    for (int r = 0; r < world; r++) {
+        PeerInfo& pi = P.info[r];
+        std::memcpy(&pi, (const char*)blobs + (size_t)r * SDPB_PEER_BLOB_BYTES, sizeof pi);
+        if (pi.magic != kPeerMagic || pi.version != SDPB_ABI_VERSION || pi.rank != r || pi.world != world ||
+            pi.T != h->m.T || pi.n_states != h->S || pi.model_hash != my_hash) {
+            h->err = "blob " + std::to_string(r) + " does not describe shard " + std::to_string(r) + " of this model";
+            return SDPB_ERR_ARG;
+        }
+    }
+    for (int r = 0; r < world; r++) {
+        const PeerInfo& pi = P.info[r];
+        if (r == rank) { P.mapped[r] = h->slab; continue; }
+        if (pi.pid == (int64_t)getpid()) {
+            // same process (sdpb_group_create): the address is valid as it is; another device needs peer access
+            if (pi.device != h->device) {
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, h->device, pi.device) != cudaSuccess || !can) {
+                    cudaGetLastError();
+                    h->err = "device " + std::to_string(h->device) + " cannot access device " + std::to_string(pi.device) + " (no P2P path)";
+                    return SDPB_ERR_PEER;
+                }
+                const cudaError_t e = cudaDeviceEnablePeerAccess(pi.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    h->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+                    return SDPB_ERR_PEER;
+                }
+                cudaGetLastError();
+            }
+            P.mapped[r] = reinterpret_cast<char*>((uintptr_t)pi.base);
+        } else {
+            void* p = nullptr;
+            const cudaError_t e = cudaIpcOpenMemHandle(&p, pi.ipc, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                h->err = std::string("cudaIpcOpenMemHandle (shard ") + std::to_string(r) + "): " + cudaGetErrorString(e);
+                return SDPB_ERR_PEER;
+            }
+            P.mapped[r] = (char*)p;
+            P.ipc_opened[r] = 1;
+        }
+    }
+    // who needs which of my rows, and whose rows do I need
+    std::vector<unsigned*> targets;
+    P.sends.clear(); P.recv_from.clear(); P.bytes_out = P.bytes_in = 0;
+    const PeerInfo& me = P.info[rank];
+    for (int r = 0; r < world; r++) {
+        if (r == rank) continue;
+        const PeerInfo& pi = P.info[r];
+        const long long a = std::max<long long>(h->lo, pi.rlo), b = std::min<long long>(h->hi, pi.rhi);
+        if (b > a) {
+            if (a < pi.vlo || b > pi.vhi) { h->err = "a peer's window does not contain the rows it reads"; return SDPB_ERR_PEER; }
+            P.sends.push_back({r, a, b});
+            targets.push_back(reinterpret_cast<unsigned*>(P.mapped[r] + pi.flags_off) + rank);
+            P.bytes_out += (b - a) * 8;
+        }
+        const long long c = std::max<long long>(pi.lo, me.rlo), d2 = std::min<long long>(pi.hi, me.rhi);
+        if (d2 > c) { P.recv_from.push_back(r); P.bytes_in += (d2 - c) * 8; }
+    }
+    void* p = nullptr;
+    CU(dev_alloc(h, &p, std::max<size_t>(1, targets.size()) * sizeof(unsigned*)));
+    P.d_targets = (unsigned**)p;
+    CU(dev_alloc(h, &p, std::max<size_t>(1, P.recv_from.size()) * sizeof(int)));
+    P.d_from = (int*)p;
+    if (!targets.empty()) CU(cudaMemcpyAsync(P.d_targets, targets.data(), targets.size() * sizeof(unsigned*), cudaMemcpyHostToDevice, h->stream));
+    if (!P.recv_from.empty()) CU(cudaMemcpyAsync(P.d_from, P.recv_from.data(), P.recv_from.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->opt.profile) {
+        h->prof_ev.assign(4 * (size_t)h->m.T, nullptr);
+        for (cudaEvent_t& e : h->prof_ev) CU(cudaEventCreate(&e));
+    }
+    P.attached = true;
+    return SDPB_OK;
+}
+
+int sdpb_peer_traffic(const sdpb_handle* h, int64_t* bytes_out, int64_t* bytes_in) {
+    if (!h || !h->peer.attached) return SDPB_ERR_STATE;
+    if (bytes_out) *bytes_out = h->peer.bytes_out;
+    if (bytes_in) *bytes_in = h->peer.bytes_in;
+    return SDPB_OK;
+}
+
+int sdpb_period_profile(const sdpb_handle* h, double* ms) {
+    if (!h || !ms) return SDPB_ERR_ARG;
+    if (h->prof_ms.size() != 3 * (size_t)h->m.T) return SDPB_ERR_STATE;
+    std::memcpy(ms, h->prof_ms.data(), h->prof_ms.size() * sizeof(double));
+    return SDPB_OK;
+}
+
+// ---- one process, several GPUs ---------------------------------------------------------------------------------------
+struct sdpb_group {
+    std::vector<sdpb_handle*> shards;
+    std::string err;
+    double solve_ms = 0;
+};
+
+static thread_local std::string g_group_error;
+
+const char* sdpb_group_last_error(const sdpb_group* g) { return g ? g->err.c_str() : g_group_error.c_str(); }
+
+void sdpb_group_destroy(sdpb_group* g) {
+    if (!g) return;
+    for (sdpb_handle* h : g->shards)  // every stream drains before any table disappears
+        if (h) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
+    for (sdpb_handle* h : g->shards) sdpb_destroy(h);
+    delete g;
+}
+
+int sdpb_group_create(const sdpb_model* m, const sdpb_options* opt, const int* devices, int n, sdpb_group** out) {
+    g_group_error.clear();
+    if (!m || !devices || !out || n < 1 || n > kMaxPeers) { g_group_error = "bad argument"; return SDPB_ERR_ARG; }
+    *out = nullptr;
+    sdpb_group* g = new (std::nothrow) sdpb_group();
+    if (!g) return SDPB_ERR_NOMEM;
+    g->shards.assign(n, nullptr);
+    auto fail = [&](int rc, const std::string& msg) { g_group_error = msg; sdpb_group_destroy(g); return rc; };
+    for (int r = 0; r < n; r++) {
+        sdpb_options o;
+        std::memset(&o, 0, sizeof o);
+        if (opt) o = *opt;
+        o.struct_size = sizeof o;
+        o.device = devices[r]; o.shard_rank = r; o.shard_count = n; o.stream = nullptr;
+        const int rc = sdpb_create(m, &o, &g->shards[r]);
+        if (rc != SDPB_OK) return fail(rc, "shard " + std::to_string(r) + ": " + sdpb_last_error(nullptr));
+    }
+    if (n > 1) {
+        std::vector<unsigned char> blobs((size_t)n * SDPB_PEER_BLOB_BYTES);
+        for (int r = 0; r < n; r++) {
+            const int rc = sdpb_peer_export(g->shards[r], blobs.data() + (size_t)r * SDPB_PEER_BLOB_BYTES);
+            if (rc != SDPB_OK) return fail(rc, "shard " + std::to_string(r) + ": " + g->shards[r]->err);
+        }
+        for (int r = 0; r < n; r++) {
+            const int rc = sdpb_peer_attach(g->shards[r], blobs.data(), n);
+            if (rc != SDPB_OK) return fail(rc, "shard " + std::to_string(r) + ": " + g->shards[r]->err);
+        }
+    }
+    *out = g;
+    return SDPB_OK;
+}
+
+sdpb_handle* sdpb_group_shard(sdpb_group* g, int rank) {
+    return (g && rank >= 0 && rank < (int)g->shards.size()) ? g->shards[rank] : nullptr;
+}
+
+int sdpb_group_solve(sdpb_group* g) {
+    if (!g) return SDPB_ERR_ARG;
+    const int n = (int)g->shards.size();
+    if (n == 1) {
+        const int rc = sdpb_solve(g->shards[0]);
+        if (rc != SDPB_OK) g->err = g->shards[0]->err;
+        g->solve_ms = g->shards[0]->stats.solve_ms;
+        return rc;
+    }
+    auto fail = [&](sdpb_handle* h, int rc) { g->err = "shard " + std::to_string(h->opt.shard_rank) + ": " + h->err; return rc; };
+    const int T = g->shards[0]->m.T;
+    for (sdpb_handle* h : g->shards) {
+        if (cudaSetDevice(h->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(h, SDPB_ERR_CUDA); }
+        std::fill(h->solved.begin(), h->solved.end(), 0);
+        h->stats = sdpb_stats{};
+        cudaEventRecord(h->ev0, h->stream);
+    }
+    // one host thread feeds every shard's stream: for each period first every shard's kernels, pushes and flag, then
+    // every shard's wait -- no wait is ever enqueued before the flag it waits for has been enqueued
+    for (int t = T; t >= 1; t--) {
+        for (sdpb_handle* h : g->shards) {
+            cudaSetDevice(h->device);
+            const int rc = enqueue_period_sharded(h, t, false);
+            if (rc != SDPB_OK) return fail(h, rc);
+        }
+        if (t > 1)
+            for (sdpb_handle* h : g->shards) {
+                cudaSetDevice(h->device);
+                const int rc = enqueue_period_exchange_wait(h);
+                if (rc != SDPB_OK) return fail(h, rc);
+                if (!h->prof_ev.empty()) cudaEventRecord(h->prof_ev[4 * (size_t)(t - 1) + 3], h->stream);
+            }
+    }
+    g->solve_ms = 0;
+    for (sdpb_handle* h : g->shards) {
+        cudaSetDevice(h->device);
+        cudaEventRecord(h->ev1, h->stream);
+    }
+    for (sdpb_handle* h : g->shards) {
+        cudaSetDevice(h->device);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "stream synchronisation failed"; return fail(h, SDPB_ERR_CUDA); }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        h->stats.solve_ms = h->stats.kernel_ms = ms;
+        h->solve_count++;
+        g->solve_ms = std::max(g->solve_ms, (double)ms);
+        const int rc = finish_sharded(h);
+        if (rc != SDPB_OK) return fail(h, rc);
+    }
+    return SDPB_OK;
+}
+
+int sdpb_group_value(sdpb_group* g, int period, const double* states, int n, double* v, double* q) {
+    if (!g || !states || n < 0) return SDPB_ERR_ARG;
+    sdpb_handle* h0 = g->shards[0];
+    const int nd = h0->ndim;
+    // route every state to the shard that owns it, one batched call per shard
+    std::vector<std::vector<int>> who(g->shards.size());
+    for (int i = 0; i < n; i++) {
+        const long long idx = index_of_state(h0, states + (size_t)i * nd);
+        if (idx < 0) { g->err = "state " + std::to_string(i) + " is not a grid point"; return SDPB_ERR_UNSOLVED; }
+        size_t r = 0;
+        while (r + 1 < g->shards.size() && idx >= g->shards[r]->hi) r++;
+        who[r].push_back(i);
+    }
+    for (size_t r = 0; r < g->shards.size(); r++) {
+        const std::vector<int>& ids = who[r];
+        if (ids.empty()) continue;
+        std::vector<double> st(ids.size() * nd), vv(ids.size()), qq(ids.size());
+        for (size_t k = 0; k < ids.size(); k++) std::memcpy(&st[k * nd], states + (size_t)ids[k] * nd, nd * sizeof(double));
+        const int rc = sdpb_value(g->shards[r], period, st.data(), (int)ids.size(), vv.data(), qq.data());
+        if (rc != SDPB_OK) { g->err = g->shards[r]->err; return rc; }
+        for (size_t k = 0; k < ids.size(); k++) { if (v) v[ids[k]] = vv[k]; if (q) q[ids[k]] = qq[k]; }
+    }
+    return SDPB_OK;
+}
+
+int sdpb_group_period_tables(sdpb_group* g, int period, double* V, double* Q) {
+    if (!g) return SDPB_ERR_ARG;
+    for (sdpb_handle* h : g->shards) {
+        const int rc = sdpb_period_tables(h, period, V, Q);  // each shard fills its own block
+        if (rc != SDPB_OK) { g->err = h->err; return rc; }
+    }
+    return SDPB_OK;
+}
+
+int sdpb_group_stats(const sdpb_group* g, sdpb_stats* s) {
+    if (!g || !s) return SDPB_ERR_ARG;
+    *s = sdpb_stats{};
+    for (const sdpb_handle* h : g->shards) {
+        s->evals += h->stats.evals; s->evals_executed += h->stats.evals_executed; s->fp64_ops += h->stats.fp64_ops;
+        s->launches += h->stats.launches; s->kernel_used = h->stats.kernel_used;
+        s->solve_ms = std::max(s->solve_ms, h->stats.solve_ms);
+        s->kernel_ms = std::max(s->kernel_ms, h->stats.kernel_ms);
+        s->exchange_ms = std::max(s->exchange_ms, h->stats.exchange_ms);
+    }
+    return SDPB_OK;
+}
+
+// ---- many small instances at once --------------------------------------------------------------------------------------
+namespace {
+struct BatchGraph {
+    std::vector<sdpb_handle*> handles;
+    cudaGraphExec_t exec = nullptr;
+    cudaStream_t stream = nullptr;
+    int device = 0;
+    std::vector<sdpb_stats> stats;
+};
+std::mutex g_batch_mu;
+std::vector<BatchGraph> g_batches;  // a handful per process: one per distinct handle list
+}  // namespace
+
+int sdpb_solve_batch(sdpb_handle* const* handles, int n) {
+    if (!handles || n < 1) return SDPB_ERR_ARG;
+    sdpb_handle* h0 = handles[0];
+    for (int i = 0; i < n; i++) {
+        sdpb_handle* h = handles[i];
+        if (!h) return SDPB_ERR_ARG;
+        if (h->opt.shard_count != 1 || h->device != h0->device) { h->err = "sdpb_solve_batch needs unsharded handles of one device"; return SDPB_ERR_ARG; }
+    }
+    if (cudaSetDevice(h0->device) != cudaSuccess) return SDPB_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(g_batch_mu);
+    BatchGraph* B = nullptr;
+    for (BatchGraph& b : g_batches)
+        if (b.handles.size() == (size_t)n && std::equal(b.handles.begin(), b.handles.end(), handles)) { B = &b; break; }
+    if (B && B->exec) {  // replay: one launch for the whole batch
+        for (int i = 0; i < n; i++) { handles[i]->stats = B->stats[i]; std::fill(handles[i]->solved.begin(), handles[i]->solved.end(), 1); }
+        if (cudaGraphLaunch(B->exec, B->stream) != cudaSuccess || cudaStreamSynchronize(B->stream) != cudaSuccess) {
+            h0->err = std::string("batch graph launch: ") + cudaGetErrorString(cudaGetLastError());
+            return SDPB_ERR_CUDA;
+        }
+        return SDPB_OK;
+    }
+    if (!B) {
+        // first call with this list: plain solves (they create every scratch buffer); remember the list
+        for (int i = 0; i < n; i++) { const int rc = sdpb_solve_async(handles[i]); if (rc != SDPB_OK) return rc; }
+        for (int i = 0; i < n; i++) { const int rc = sdpb_sync(handles[i]); if (rc != SDPB_OK) return rc; }
+        BatchGraph b;
+        b.handles.assign(handles, handles + n);
+        b.device = h0->device;
+        g_batches.push_back(b);
+        return SDPB_OK;
+    }
+    // second call: capture every handle's periods into one graph -- a fork from the batch stream into each handle's own
+    // stream and a join back, so independent instances run side by side
+    if (cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking) != cudaSuccess) return SDPB_ERR_CUDA;
+    cudaGraph_t graph = nullptr;
+    cudaEvent_t fork = nullptr;
+    std::vector<cudaEvent_t> joins(n, nullptr);
+    cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+    for (cudaEvent_t& e : joins) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    int rc = SDPB_OK;
+    bool ok = cudaStreamBeginCapture(B->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+        ok = cudaEventRecord(fork, B->stream) == cudaSuccess;
+        for (int i = 0; ok && i < n; i++) {
+            sdpb_handle* h = handles[i];
+            ok = cudaStreamWaitEvent(h->stream, fork, 0) == cudaSuccess;
+            if (!ok) break;
+            rc = enqueue_all_periods(h);
+            if (rc != SDPB_OK) { ok = false; break; }
+            ok = cudaEventRecord(joins[i], h->stream) == cudaSuccess && cudaStreamWaitEvent(B->stream, joins[i], 0) == cudaSuccess;
+        }
+        const cudaError_t e = cudaStreamEndCapture(B->stream, &graph);
+        ok = ok && e == cudaSuccess && graph && cudaGraphInstantiate(&B->exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+    }
+    cudaEventDestroy(fork);
+    for (cudaEvent_t e : joins) cudaEventDestroy(e);
+    if (!ok) {
+        cudaGetLastError();
+        B->exec = nullptr;
+        // capture is not possible here: plain solves again (and from now on)
+        for (int i = 0; i < n; i++) { const int r2 = sdpb_solve_async(handles[i]); if (r2 != SDPB_OK) return r2; }
+        for (int i = 0; i < n; i++) { const int r2 = sdpb_sync(handles[i]); if (r2 != SDPB_OK) return r2; }
+        return SDPB_OK;
+    }
+    B->stats.resize(n);
+    for (int i = 0; i < n; i++) B->stats[i] = handles[i]->stats;
+    if (cudaGraphLaunch(B->exec, B->stream) != cudaSuccess || cudaStreamSynchronize(B->stream) != cudaSuccess) return SDPB_ERR_CUDA;
+    return SDPB_OK;
+}
+
+int sdpb_trim_pool(int device) {
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return SDPB_ERR_NO_DEVICE;
+    if (device < 0 || device >= 64) return SDPB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pools[device] && cudaMemPoolTrimTo(g_pools[device], 0) != cudaSuccess) { cudaGetLastError(); return SDPB_ERR_CUDA; }
+    return SDPB_OK;
+}
+
+// ---- grid bounds for unclamped models (host arithmetic only) -----------------------------------------------------------
+int sdpb_reachable_hull(const sdpb_model* m, const double* init_states, int n, double* inv_lo, double* inv_hi) {
+    if (!m || !init_states || n < 1 || !inv_lo || !inv_hi || m->T < 1 || !m->pmf_len || !m->pmf_d) return SDPB_ERR_ARG;
+    const bool cash = m->cost_kind != SDPB_COST_BACKORDER && m->cost_kind != SDPB_COST_STAFF;
+    const bool two = m->cost_kind == SDPB_COST_CASH_TWO_PRODUCT;
+    const int nd = 1 + (two ? 1 : 0) + (cash ? 1 : 0) + m->lead_time;
+    // level before demand: x + (order, or the quantity already in the pipeline): in [x, x + max_order]
+    const double amax = (double)m->max_order_idx * m->step;
+    double lo = init_states[0], hi = init_states[0];
+    for (int i = 0; i < n; i++) {
+        const double* st = init_states + (size_t)i * nd;
+        for (int k = 0; k < (two ? 2 : 1); k++) { lo = std::min(lo, st[k]); hi = std::max(hi, st[k]); }
+    }
+    double all_lo = lo, all_hi = hi;
+    size_t off = 0;
+    for (int t = 0; t < m->T; t++) {
+        double dmin = m->pmf_d[off], dmax = m->pmf_d[off];
+        for (int j = 0; j < m->pmf_len[t]; j++) { dmin = std::min(dmin, m->pmf_d[off + j]); dmax = std::max(dmax, m->pmf_d[off + j]); }
+        if (two && m->pmf_d2)
+            for (int j = 0; j < m->pmf_len[t]; j++) { dmin = std::min(dmin, m->pmf_d2[off + j]); dmax = std::max(dmax, m->pmf_d2[off + j]); }
+        off += (size_t)m->pmf_len[t];
+        if (t == m->T - 1 && !m->terminal_value) break;  // states of period T+1 exist only for the boundary function
+        lo = lo - dmax;            // no order, largest demand
+        hi = hi + amax - dmin;     // largest order (or pipeline quantity), smallest demand
+        if (m->flags & SDPB_F_LOST_SALES) { lo = std::max(lo, 0.0); hi = std::max(hi, 0.0); }
+        all_lo = std::min(all_lo, lo);
+        all_hi = std::max(all_hi, hi);
+    }
+    *inv_lo = all_lo;
+    *inv_hi = all_hi;
+    return SDPB_OK;
+}
+
 int sdpb_stats_get(const sdpb_handle* h, sdpb_stats* s) {
     if (!h || !s) return SDPB_ERR_ARG;
     *s = h->stats;
+    s->clipped_successors = h->reach_cnt[0];
+    s->capped_action_sets = h->reach_cnt[1];
+    s->cash_bound_hits = h->reach_cnt[2];
     return SDPB_OK;
 }
 

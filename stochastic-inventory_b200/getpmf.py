@@ -124,21 +124,35 @@ def poisson_pmf(means, truncationQuantile=0.9999, stepSize=1.0):
     return GetPmf([PoissonDist(m) for m in means], truncationQuantile, stepSize).getpmf()
 
 
-def clsp_inline_pmf(means, truncationQuantile=0.99999, stepSize=1.0):
+def clsp_inline_pmf(means_or_distributions, truncationQuantile=0.99999, stepSize=1.0):
     """The pmf CLSP.main builds inline (src/capacitated/CLSP.java:218-247): supports are
-    inverseF(1-q)..inverseF(q) without the (int) cast or the LB=0 override.  PoissonDist is not an
-    instance of SSJ's DiscreteDistribution (it extends DiscreteDistributionInt), so the else-branch
-    (cdf differences) is the one that runs."""
+    inverseF(1-q)..inverseF(q) without the (int) cast or the LB=0 override of GetPmf.  Two branches, chosen by
+    `distributions[0] instanceof DiscreteDistribution` (:236):
+      * not a DiscreteDistribution -- which includes PoissonDist, CLSP.main's own choice: SSJ's PoissonDist extends
+        DiscreteDistributionInt, a different class -- cdf differences normalised by
+        cdf(UB + step/2) - cdf(LB - step/2) (:241-245);
+      * a generic DiscreteDistribution: `prob(demand) / (2q - 1)` (:238-239), where SSJ's DiscreteDistribution.prob(i)
+        is the probability of the i-th SUPPORT POINT, so the demand value is used as an index (my reading of SSJ
+        3.3.0, which is not in the image; the quirk is kept, and the normaliser 2q - 1 is not the mass of the table).
+    Accepts Poisson means or distribution objects."""
+    dists = [d if isinstance(d, Distribution) else PoissonDist(d) for d in means_or_distributions]
+    q = float(truncationQuantile)
+    discrete_branch = isinstance(dists[0], DiscreteDistribution)
     rows = []
-    for m in means:
-        d = PoissonDist(m)
-        lb, ub = d.inverseF(1 - truncationQuantile), d.inverseF(truncationQuantile)
+    for d in dists:
+        lb, ub = d.inverseF(1 - q), d.inverseF(q)
         n = int((ub - lb + 1) / stepSize)
         row = np.zeros((n, 2))
-        psum = d.cdf(ub + 0.5 * stepSize) - d.cdf(lb - 0.5 * stepSize)
         for j in range(n):
             row[j, 0] = lb + j * stepSize
-            row[j, 1] = (d.cdf(row[j, 0] + 0.5 * stepSize) - d.cdf(row[j, 0] - 0.5 * stepSize)) / psum
+            demand = int(row[j, 0])
+            if discrete_branch:
+                probabilitySum = 2 * q - 1
+                p_i = float(d.probs[demand]) if 0 <= demand < len(d.probs) else 0.0  # prob(i): i-th support point
+                row[j, 1] = p_i / probabilitySum
+            else:
+                probabilitySum = d.cdf(ub + 0.5 * stepSize) - d.cdf(lb - 0.5 * stepSize)
+                row[j, 1] = (d.cdf(row[j, 0] + 0.5 * stepSize) - d.cdf(row[j, 0] - 0.5 * stepSize)) / probabilitySum
         rows.append(row)
     return rows
 

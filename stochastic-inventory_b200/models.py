@@ -59,6 +59,12 @@ class ModelSpec:
     tie_tolerance: float = 0.0
     apmf: Optional[Sequence] = None          # staff kind: apmf[t][y] = probabilities of turnover 0..len-1
     min_level_t: Optional[Sequence[float]] = None
+    # terminal boundary function (FinalCash.BoundaryFuncton, CashRecursionV.java:125-128): V_{T+1} on the dense grid
+    # in the library's state order, or None for the engines without one (Recursion.java:140)
+    terminal_value: Optional[np.ndarray] = None
+    # sdpb_allow bits this model is known to need (e.g. an XR instance whose order-up-to range is capped on purpose);
+    # OR-ed into sdpb_options.allow by Solver / Group
+    allow: int = 0
     name: str = ""
 
     @property
@@ -122,8 +128,67 @@ class ModelSpec:
                     raise ValueError(f"{f} must have T={self.T} entries")
                 keep.append(arr)
                 setattr(m, f, arr.ctypes.data_as(C.POINTER(C.c_double)))
+        if self.terminal_value is not None:
+            tv = np.ascontiguousarray(self.terminal_value, dtype=np.float64).ravel()
+            keep.append(tv)
+            m.terminal_value = tv.ctypes.data_as(C.POINTER(C.c_double))
         m._keep = keep  # the struct owns its arrays
         return m
+
+    # ---- the dense grid, as the library lays it out (sdpb_state_of_index) ----
+    def grid_axes(self):
+        """-> (inventory values, pipeline quantities, cash values): the axes of the dense grid.  Flattened order:
+        inventory outermost, [second inventory,] preQ1, preQ2, cash innermost."""
+        import math
+
+        def jround(x):  # Math.round
+            r = math.floor(x)
+            return int(r) + (1 if x - r >= 0.5 else 0)
+
+        n_inv = jround((self.inv_max - self.inv_min) / self.step) + 1
+        inv = self.inv_min + np.arange(n_inv, dtype=np.float64) * self.step
+        q = np.arange(self.max_order_idx + 1, dtype=np.float64) * self.step
+        cash = None
+        if self.has_cash:
+            if self.cost_kind == A.COST_CASH_XR:
+                raise NotImplementedError("the (x, R) grid is not tabulated on the host")
+
+            def quantise(w):
+                if self.quantiser == A.Q_TRUNC:
+                    return float(int(w))
+                kk = jround(w * self.q_mul)
+                return kk / self.q_div if self.quantiser == A.Q_DIV else float(int(kk / int(self.q_div)) if kk >= 0
+                                                                                 else -int(-kk / int(self.q_div)))
+
+            def k_of(wq):
+                return jround(wq * self.q_div) if self.quantiser == A.Q_DIV else int(wq)
+
+            kmin, kmax = k_of(quantise(self.cash_min)), k_of(quantise(self.cash_max))
+            k = np.arange(kmin, kmax + 1, dtype=np.float64)
+            cash = k / self.q_div if self.quantiser == A.Q_DIV else k
+        return inv, q, cash
+
+    def tabulate(self, fn):
+        """Evaluate a boundary function b(state) on every grid point, in the library's flattened order and with the
+        state in API order: (inv) | (inv, preQ[, preQ2]) | (inv, cash) | (inv, cash, preQ) | (inv1, inv2, cash).
+        `fn` receives numpy arrays (one per state dimension) and returns an array -- this is how a
+        FinalCash.BoundaryFuncton lambda becomes `terminal_value`."""
+        inv, q, cash = self.grid_axes()
+        axes = [inv]
+        if self.two_product:
+            axes.append(inv)
+        axes += [q] * self.lead_time
+        if cash is not None:
+            axes.append(cash)
+        mesh = list(np.meshgrid(*axes, indexing="ij"))
+        # API order puts the cash before the pipeline quantities
+        if cash is not None and self.lead_time:
+            n_lead = self.lead_time
+            api = mesh[:len(mesh) - 1 - n_lead] + [mesh[-1]] + mesh[len(mesh) - 1 - n_lead:-1]
+        else:
+            api = mesh
+        out = np.asarray(fn(*api), dtype=np.float64)
+        return np.ascontiguousarray(np.broadcast_to(out, mesh[0].shape)).ravel()
 
     def evals_dense(self) -> float:
         """sum_t sum_s |A_t(s)| * D_t on the dense grid for state-independent action sets."""
@@ -250,7 +315,9 @@ def cash_xr_model(pmf, price=4.0, vari_cost=2.0, fixed_cost=0.0, hold_cost=0.0, 
                   inv_max=500.0, cash_min=-100.0, cash_max=2000.0, gamma=1.0, name="cash_xr") -> ModelSpec:
     """(x, R) formulation.  Lambdas: src/cash/singleItem/CashConstraintXR.java:71-110.
     Engine: src/sdp/cash/CashRecursionXR.java:79-125.  `max_order` caps the number of order-up-to
-    levels per state on the dense grid (the reference has no cap; choose it >= R_max / v)."""
+    levels per state on the dense grid; the reference has no cap (CashConstraintXR.java:71-75), so choose it
+    >= (cash_max + v*inv_max)/v - inv_min.  A cap that bites at a state the recursion visits is reported by
+    sdpb_reach (SDPB_ERR_OFFGRID) unless `allow_cap`."""
     return ModelSpec(cost_kind=A.COST_CASH_XR, pmf=pmf, inv_min=inv_min, inv_max=inv_max,
                      max_order_idx=int(max_order), direction=A.MAX,
                      flags=A.F_CLAMP_INV | A.F_LOST_SALES, gamma=gamma, cash_min=cash_min,

@@ -53,12 +53,15 @@ def math_round_half_up(x):
 
 
 class HaloExchange:
-    """Point-to-point exchange of V_t: every rank receives, from each peer, the overlap of the peer's block
-    with the range it will read (`needs[rank]`), and sends the mirror image.  `needs` must be identical on
-    all ranks (gather_needs).  Works with NCCL (grouped sends/receives on the current stream) and gloo."""
+    """Point-to-point exchange of V_t over torch.distributed: every rank receives, from each peer, the overlap of the
+    peer's block with the range it will read (`needs[rank]`), and sends the mirror image.  `needs` must be identical
+    on all ranks (gather_needs).  Works with NCCL (grouped sends/receives on the current stream) and gloo.  `base`:
+    flattened index of element 0 of the tensors passed to __call__ (a shard holds only a window of V_t).
+    This is the host-side statement of what libsdpb200's own peer exchange does (sdpb_peer_attach); the GPU path
+    uses the library's, the gloo tests use this one."""
 
-    def __init__(self, dist, rank, world, n_states, needs):
-        self.dist, self.rank = dist, rank
+    def __init__(self, dist, rank, world, n_states, needs, base=0):
+        self.dist, self.rank, self.base = dist, rank, base
         blocks = [shard_bounds(n_states, r, world)[:2] for r in range(world)]
         self.recv = []  # (peer, lo, hi): slices of peers' blocks that I read
         self.send = []  # (peer, lo, hi): slices of my block that peers read
@@ -74,9 +77,9 @@ class HaloExchange:
         self.bytes_in = sum(b - a for _, a, b in self.recv) * 8
 
     def __call__(self, full):
-        dist = self.dist
-        ops = [dist.P2POp(dist.isend, full[a:b], peer) for peer, a, b in self.send]
-        ops += [dist.P2POp(dist.irecv, full[a:b], peer) for peer, a, b in self.recv]
+        dist, o = self.dist, self.base
+        ops = [dist.P2POp(dist.isend, full[a - o:b - o], peer) for peer, a, b in self.send]
+        ops += [dist.P2POp(dist.irecv, full[a - o:b - o], peer) for peer, a, b in self.recv]
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
@@ -121,38 +124,60 @@ def wrap_device(torch, ptr, n, typestr, device):
     return torch.as_tensor(_CAI(ptr, n, typestr), device=f"cuda:{device}")
 
 
-class ShardedSolve:
-    """One rank's share of a GPU solve (libsdpb200 handle created with shard_rank / shard_count)."""
+def gather_blobs(torch, dist, world, blob: bytes, device=None):
+    """Every shard's sdpb_peer_export() bytes, in rank order (one small all-gather at set-up)."""
+    mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).clone()
+    if device is not None:
+        mine = mine.to(device)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    return [bytes(t.cpu().numpy().tobytes()) for t in out]
 
-    def __init__(self, Solver, torch, dist, spec, rank, world, device, stream, kernel=0, dedup=False, exchange="auto"):
+
+class ShardedSolve:
+    """One rank's share of a GPU solve: a libsdpb200 handle created with shard_rank / shard_count.
+
+    exchange = "p2p" (default): the shards are connected once through CUDA IPC (sdpb_peer_export -> all-gather of
+        the 256-byte blobs -> sdpb_peer_attach); a step is then ONE library call, sdpb_solve_async, and the rows of
+        V_t travel between the GPUs' tables inside the library (peer copies + device-side flags).
+    exchange = "nccl": the round-1 path, kept for comparison -- the library is stepped period by period and V_t is
+        exchanged with torch.distributed (point-to-point halo, or an all-gather when a shard holds the whole table)."""
+
+    def __init__(self, Solver, torch, dist, spec, rank, world, device, stream, kernel=0, dedup=False, exchange="p2p",
+                 profile=False):
         self.torch, self.dist, self.world, self.rank = torch, dist, world, rank
         self.solver = Solver(spec, device=device, shard_rank=rank, shard_count=world, kernel=kernel,
-                             dedup=dedup, stream=stream.cuda_stream)
+                             dedup=dedup, stream=stream.cuda_stream, profile=profile)
         g = self.solver.grid
         self.T, self.n = g.T, g.n_states
         self.lo, self.hi, self.chunk = shard_bounds(self.n, rank, world)
         assert (self.lo, self.hi) == (g.shard_lo, g.shard_hi)
         self.V = []
         self.exchange, self.exchange_kind = None, "none"
-        if world > 1:
+        self.bytes_out = self.bytes_in = 0
+        if world > 1 and exchange == "p2p":
+            blobs = gather_blobs(torch, dist, world, self.solver.peer_export(), device=f"cuda:{device}")
+            self.solver.peer_attach(blobs)
+            self.bytes_out, self.bytes_in = self.solver.peer_traffic()
+            self.exchange_kind = "p2p"
+        elif world > 1:
+            wlo, whi = g.window_lo, g.window_hi
             for t in range(1, self.T + 1):
                 dv, _ = self.solver.device_tables(t)
-                self.V.append(wrap_device(torch, dv, self.chunk * world, "<f8", device))
-            # halo exchange when a rank reads well under the whole table (the library knows what its kernels read)
+                self.V.append(wrap_device(torch, dv, whi - wlo, "<f8", device))
             needs = gather_needs(torch, dist, world, self.solver.shard_reads(), device=f"cuda:{device}")
-            frac = max((b - a) for a, b in needs) / max(self.n, 1)
-            self.exchange_kind = "allgather"
-            if exchange == "halo" or (exchange == "auto" and frac < 0.6):
-                self.exchange = HaloExchange(dist, rank, world, self.n, needs)
-                self.exchange_kind = "halo"
+            self.exchange_kind = "nccl-allgather"
+            if not (wlo == 0 and whi == self.chunk * world):  # the shard holds a window only: halo exchange
+                self.exchange = HaloExchange(dist, rank, world, self.n, needs, base=wlo)
+                self.exchange_kind = "nccl-halo"
 
     def step(self):
-        if self.world == 1:
-            self.solver.solve_async()  # one CUDA graph per solve after the first
+        if self.world == 1 or self.exchange_kind == "p2p":
+            self.solver.solve_async()  # unsharded: one CUDA graph per solve after the first
             return
         backward_induction_sharded(
             self.T, self.n, self.rank, self.world, self.solver.solve_period_async, self.V,
-            self.dist.all_gather_into_tensor if self.world > 1 else None, self.exchange)
+            self.dist.all_gather_into_tensor, self.exchange)
 
     def close(self):
         self.solver.close()

@@ -130,16 +130,37 @@ class _Engine:
     _lead = 0
 
     def __init__(self, spec: ModelSpec, getFeasibleAction=None, stateTransition=None, immediateValue=None,
-                 device: int = -1, kernel: int = A.KERNEL_AUTO, dedup: bool = False, spot_checks: int = 200):
+                 device: int = -1, kernel: int = A.KERNEL_AUTO, dedup: bool = False, spot_checks: int = 200,
+                 boundFinalCash=None, allow: int = 0, devices=None):
+        """`boundFinalCash`: a FinalCash.BoundaryFuncton (src/sdp/inventory/FinalCash.java:16-18) -- a function of the
+        state dimensions in API order, evaluated on numpy arrays over the whole grid (ModelSpec.tabulate) -- that
+        values the states of period T+1 (CashRecursionV.java:125-128).  `allow`: sdpb_allow bits.  `devices`: a list
+        of CUDA ordinals to partition the state grid over (sdpb_group_*); value queries work as usual, the visited-state
+        tables (getOptTable) need a single-GPU engine."""
         if spec.cost_kind not in self._kinds or spec.lead_time != self._lead:
             raise ValueError(f"{type(self).__name__} does not take this descriptor "
                              f"(cost_kind={spec.cost_kind}, lead_time={spec.lead_time})")
+        if boundFinalCash is not None:
+            import copy
+            spec = copy.copy(spec)
+            spec.terminal_value = spec.tabulate(boundFinalCash)
         self.spec = spec
         self.pmf = spec.pmf
         self.getFeasibleActions = getFeasibleAction
         self.stateTransition = stateTransition
         self.immediateValue = immediateValue
-        self._solver = Solver(spec, device=device, kernel=kernel, dedup=dedup)
+        self.boundFinalCash = boundFinalCash
+        self._group = None
+        if devices is not None and len(devices) > 1:
+            from .solver import Group
+            self._group = Group(spec, list(devices), kernel=kernel, dedup=dedup, allow=allow)
+            self._solver = self._group.shards[0]
+        else:
+            self._solver = Solver(spec, device=device if devices is None else devices[0], kernel=kernel, dedup=dedup,
+                                  allow=allow)
+        # dense-grid artefacts matter only at states the reference would visit (sdpb_allow): models that can have
+        # them are checked from every queried period-1 state
+        self._check_reach = (not (spec.flags & A.F_CLAMP_INV)) or spec.cost_kind == A.COST_CASH_XR
         self._solved = False
         self._queried = []  # period-1 states asked for so far: roots of the top-down visit set
         self._tree_map = False
@@ -160,18 +181,22 @@ class _Engine:
 
     def _ensure_solved(self):
         if not self._solved:
-            self._solver.solve()
+            (self._group or self._solver).solve()
             self._solved = True
 
     def _value(self, state):
         self._ensure_solved()
-        v, q = self._solver.value(state.getPeriod(), [state._vec()])
+        v, q = (self._group or self._solver).value(state.getPeriod(), [state._vec()])
         return float(v[0]), float(q[0])
 
     def getExpectedValue(self, state):
         val, _ = self._value(state)
         if state.getPeriod() == 1 and state._vec() not in self._queried:
             self._queried.append(state._vec())
+            if self._check_reach and self._group is None:
+                # raises SDPB_ERR_OFFGRID if the dense grid clipped a successor (or capped the action set) of a state
+                # the reference's recursion visits from here: the value would not be the reference's
+                self._solver.reach(self._queried)
         return val
 
     def getAction(self, state):
@@ -184,6 +209,8 @@ class _Engine:
         """Rows [t, state dims..., Q*] for the visited states only (Recursion.java:177-186)."""
         if not self._queried:
             return np.empty((0, self._solver.ndim + 2))
+        if self._group is not None:
+            raise NotImplementedError("the visited-state table needs a single-GPU engine (sdpb_reach)")
         self._ensure_solved()
         self._solver.reach(self._queried)
         return self._solver.opt_table()
@@ -207,7 +234,7 @@ class _Engine:
         for _ in range(n):
             st, a, d = _spot.random_triple(self.spec, rng)
             state = self._make_state(st)
-            c_desc, nxt_desc, nA = _spot.eval_descriptor(self.spec, st, a, d)
+            c_desc, nxt_desc, nA = _spot.eval_descriptor(self.spec, st, a, d, solver=self._solver)
             if self.immediateValue is not None:
                 c_user = float(self.immediateValue(state, a, d))
                 if c_user != c_desc:

@@ -175,8 +175,17 @@ def case_F_small():
 
 def case_XR_small():
     # CashConstraintXR.java:34-110 scaled down (integer-valued Poisson table instead of Gamma)
-    return S.cash_xr_model(pmf([4, 4, 4], 0.99), price=4, vari_cost=2, salvage=1, max_order=30, inv_min=0,
-                           inv_max=30, cash_min=-10, cash_max=90, name="XR_small"), [[0.0, 30.0]]
+    # (the order-up-to range is capped at 31 levels on purpose: the cap bites at visited states, which the model allows)
+    spec = S.cash_xr_model(pmf([4, 4, 4], 0.99), price=4, vari_cost=2, salvage=1, max_order=30, inv_min=0,
+                           inv_max=30, cash_min=-10, cash_max=90, name="XR_small")
+    spec.allow = A.ALLOW_CAPPED_ACTIONS
+    return spec, [[0.0, 30.0]]
+
+
+def case_XR_uncapped():
+    # the reference's own action set (CashConstraintXR.java:71-75 has no cap): max_order covers R_max / v
+    return S.cash_xr_model(pmf([3, 3], 0.99), price=4, vari_cost=2, salvage=1, max_order=40, inv_min=0,
+                           inv_max=20, cash_min=0, cash_max=40, name="XR_uncapped"), [[0.0, 20.0]]
 
 
 def case_M2_small():
@@ -201,11 +210,125 @@ def case_W_small():
                              min_staff=[8, 10, 6], max_hire=20, max_x=30, name="W_small"), [[0.0]]
 
 
+# ---- terminal boundary function (FinalCash.BoundaryFuncton, CashRecursionV.java:125-128) ------------------
+def case_A_terminal():
+    # leftover stock is worth 0.75 per unit at the end of the horizon, backorders cost 2.5 per unit
+    spec, init = case_A_small()
+    spec.terminal_value = spec.tabulate(lambda x: -0.75 * np.maximum(x, 0) + 2.5 * np.maximum(-x, 0))
+    spec.name = "A_terminal"
+    return spec, init
+
+
+def case_A_terminal_big():
+    # enough states for the tiled kernels' multi-tile paths
+    spec = S.inventory_model(pmf([7, 9, 8]), fixed_cost=12, vari_cost=1, hold_cost=1, penalty_cost=6, max_order=37,
+                             inv_min=-1250, inv_max=1249, name="A_terminal_big")
+    spec.terminal_value = spec.tabulate(lambda x: 0.125 * x * np.sin(x))
+    return spec, [[0.0]]
+
+
+def case_B2_terminal():
+    spec, init = case_B2_small()
+    spec.terminal_value = spec.tabulate(lambda x, q1, q2: -1.0 * np.maximum(x + q1 + q2, 0) + 3.0 * np.maximum(-x, 0))
+    spec.name = "B2_terminal"
+    return spec, init
+
+
+def case_B1_terminal():
+    spec, init = case_B1_fixed()
+    spec.terminal_value = spec.tabulate(lambda x, q1: 0.5 * np.abs(x + q1))
+    spec.name = "B1_terminal"
+    return spec, init
+
+
+def case_C_terminal():
+    # MultiItemCashXW.java:118-121 form for one product: final cash plus the salvage value of the stock,
+    # instead of the salvage term inside the immediate value
+    spec = S.cash_constraint_model(pmf([5, 6, 5]), price=10, vari_cost=1, salvage=0.0, max_order=14, inv_min=0,
+                                   inv_max=25, cash_min=0, cash_max=200, quantiser=A.Q_LONGDIV, q_mul=1.0, q_div=1.0,
+                                   name="C_terminal")
+    spec.terminal_value = spec.tabulate(lambda x, w: w + 0.5 * x)
+    return spec, [[0.0, 12.0]]
+
+
+def case_C_terminal_frac():
+    spec, init = case_C_small()
+    spec.terminal_value = spec.tabulate(lambda x, w: 0.25 * w + 0.5 * x)
+    spec.name = "C_terminal_frac"
+    return spec, init
+
+
+def case_D_terminal():
+    spec, init = case_D_small()
+    spec.terminal_value = spec.tabulate(lambda x, w: np.minimum(w, 100.0) + 0.25 * x)
+    spec.name = "D_terminal"
+    return spec, init
+
+
+def case_E_terminal():
+    spec, init = case_E_small()
+    spec.terminal_value = spec.tabulate(lambda x, w, q: w + 0.5 * (x + q))
+    spec.name = "E_terminal"
+    return spec, init
+
+
+def case_M2_terminal():
+    # MultiItemCashXW.java:118-121: boundFinalCash = cash + salPrice1 * x1 + salPrice2 * x2
+    spec, init = case_M2_small()
+    spec.salvage = 0.0
+    spec.salvage2 = 0.0
+    spec.terminal_value = spec.tabulate(lambda x1, x2, w: w + 1.0 * x1 + 2.0 * x2)
+    spec.name = "M2_terminal"
+    return spec, init
+
+
+def case_W_terminal():
+    spec, init = case_W_small()
+    spec.terminal_value = spec.tabulate(lambda x: 3.0 * np.abs(x - 8.0))
+    spec.name = "W_terminal"
+    return spec, init
+
+
+# ---- A(s) = {0} in the last period (SingleProductLeadtime.java:74-75) on the families with specialised kernels ----
+def case_A_nolast():
+    spec, init = case_A_small()
+    spec.flags |= A.F_NO_ORDER_LAST
+    spec.name = "A_nolast"
+    return spec, init
+
+
+def case_B2_nolast():
+    spec, init = case_B2_small()
+    spec.flags |= A.F_NO_ORDER_LAST
+    spec.name = "B2_nolast"
+    return spec, init
+
+
+def case_C_int_nolast():
+    spec, init = case_C_int()
+    spec.flags |= A.F_NO_ORDER_LAST
+    spec.name = "C_int_nolast"
+    return spec, init
+
+
+def case_CLSP_main():
+    # src/capacitated/CLSP.java:196-272 scaled down: the inline pmf (no (int) cast, no LB = 0 override; the support
+    # of Poisson(53) starts at 26), fixed cost, capacity; initial inventory 1
+    table = S.clsp_inline_pmf([9, 23, 53, 29], 0.99999, 1)
+    return S.inventory_model(table, fixed_cost=500, vari_cost=0, hold_cost=2, penalty_cost=10, max_order=60,
+                             inv_min=-300, inv_max=300, name="CLSP_main"), [[1.0]]
+
+
+NOLAST = [case_A_nolast, case_B2_nolast, case_C_int_nolast]
+
+TERMINAL = [case_A_terminal, case_A_terminal_big, case_B1_terminal, case_B2_terminal, case_C_terminal,
+            case_C_terminal_frac, case_D_terminal, case_E_terminal, case_M2_terminal, case_W_terminal]
+
 ALL = [case_A_small, case_A_max, case_A_gy, case_A_twopoint, case_A_halfstep, case_A_sparse_pmf,
        case_A_degenerate, case_A_one_state, case_B1_ref, case_B1_fixed,
        case_B2_small, case_C_small, case_C_rich, case_C_int, case_C_int_K, case_D_small, case_D_rich, case_DL_small,
        case_DT_small, case_TP_small, case_M2_small, case_M2_poisson, case_W_small, case_E_small, case_F_small,
-       case_XR_small]
+       case_XR_small, case_XR_uncapped, case_CLSP_main] + TERMINAL + NOLAST
 
 
 # ---- golden fixtures --------------------------------------------------------------------------

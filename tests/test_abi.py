@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(S):
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in sdpb200.h but not exported"
     assert sorted(S.abi.EXPORTS) == declared
-    assert lib.sdpb_abi_version() == 3
+    assert lib.sdpb_abi_version() == 4
 
 
 def test_struct_layout_matches_c_compiler(S, tmp_path):

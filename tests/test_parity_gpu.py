@@ -373,117 +373,326 @@ def test_reference_style_simulation(S, oracle):
     assert np.array_equal(sim.simulate_paths(S.State(1, 0), samples), oracle.simulate(spec, Qo, [0.0], samples))
 
 
-@pytest.mark.parametrize("case,world", [(cases.case_A_small, 2), (cases.case_A_gy, 3), (cases.case_B2_small, 3),
-                                        (cases.case_B1_ref, 2), (cases.case_C_int, 3), (cases.case_C_rich, 2),
-                                        (cases.case_F_small, 2), (cases.case_E_small, 2), (cases.case_M2_small, 3),
-                                        (cases.case_W_small, 2)], ids=lambda x: getattr(x, "__name__", str(x))[5:])
-def test_sharded_handles_on_one_gpu(case, world, S, oracle):
-    """The multi-GPU data path on one device: `world` handles with shard_rank 0..world-1, stepped period
-    by period; after each period every rank's block of V_t is copied into every other rank's table (what
-    the NCCL all-gather does).  Checks the kernels' [lo, hi) handling bit for bit."""
-    import torch
-    par = S.package.parallel
-    spec, _ = case()
+GROUP_CASES = [(cases.case_A_small, 2), (cases.case_A_gy, 3), (cases.case_B2_small, 3), (cases.case_B1_ref, 2),
+               (cases.case_B1_fixed, 4), (cases.case_C_int, 3), (cases.case_C_rich, 2), (cases.case_C_small, 5),
+               (cases.case_D_small, 3), (cases.case_F_small, 2), (cases.case_E_small, 2), (cases.case_M2_small, 3),
+               (cases.case_W_small, 2), (cases.case_XR_small, 2), (cases.case_A_terminal, 3), (cases.case_B2_terminal, 4),
+               (cases.case_C_terminal, 3), (cases.case_M2_terminal, 2), (cases.case_A_one_state, 3)]
+
+
+@pytest.mark.parametrize("case,world", GROUP_CASES, ids=lambda x: getattr(x, "__name__", str(x))[5:])
+def test_group_on_one_gpu(case, world, S, oracle):
+    """The multi-GPU data path inside the library, on one device: sdpb_group_create cuts the grid into `world` shards
+    (here all on GPU 0), each holding only its window of V_t; after every period the shards copy the rows their peers
+    read straight into the peers' tables and hand over with device-side flags.  Whole grid, every period, against the
+    oracle; per-shard windows, traffic and evaluation counts."""
+    spec, init = case()
     Vo, Qo, evals, _ = oracle.dense(spec)
     n = Vo.shape[1]
-    hs = [S.Solver(spec, shard_rank=r, shard_count=world) for r in range(world)]
-    bounds = [par.shard_bounds(n, r, world) for r in range(world)]
-    chunk = bounds[0][2]
-    for t in range(spec.T, 0, -1):
-        for h in hs:
-            h.solve_period_async(t)
-        for h in hs:
-            h.sync()
-        tabs = [par.wrap_device(torch, h.device_tables(t)[0], chunk * world, "<f8", 0) for h in hs]
-        for r, (lo, hi, _) in enumerate(bounds):
-            for r2 in range(world):
-                if r2 != r:
-                    tabs[r2][lo:hi].copy_(tabs[r][lo:hi])
-        torch.cuda.synchronize()
-    total = 0.0
-    for r, (lo, hi, _) in enumerate(bounds):
+    with S.Group(spec, [0] * world) as g:
+        g.solve()
+        g.solve()  # a second solve on the same tables: the flag epochs keep counting
         for t in range(1, spec.T + 1):
-            dv, dq = hs[r].device_tables(t)
-            V = par.wrap_device(torch, dv, chunk * world, "<f8", 0)[:n].cpu().numpy()
-            Qi = par.wrap_device(torch, dq, chunk * world, "<i4", 0)[lo:hi].cpu().numpy()
-            assert np.array_equal(V, Vo[t - 1]), (r, t)
-            # policy: action index -> order quantity (pair index for the two-product kind)
-            q = np.where(Qi < 0, 0.0, Qi * spec.step)
-            if spec.cost_kind == S.COST_CASH_XR:
-                pytest.skip("XR policy needs the state's inventory")
-            assert np.array_equal(q, Qo[t - 1][lo:hi]), (r, t)
-        total += hs[r].stats()["evals"]
-    assert total == evals
+            V, Q = g.period_tables(t)
+            assert np.array_equal(V, Vo[t - 1]), t
+            assert np.array_equal(Q, Qo[t - 1]), t
+        assert g.stats()["evals"] == evals
+        v, q = g.value(1, init)
+        rows, iv, _ = oracle.topdown(spec, init)
+        assert np.array_equal(v, iv)
+        par = S.package.parallel
+        for r, sh in enumerate(g.shards):
+            lo, hi, _ = par.shard_bounds(n, r, world)
+            gi = sh.grid
+            assert (gi.shard_lo, gi.shard_hi) == (lo, hi)
+            need = sh.shard_reads()
+            assert need == par.needed_range(spec, lo, hi, n)
+            if hi > lo:
+                assert gi.window_lo <= min(need[0], lo) and gi.window_hi >= max(need[1], hi)
+                Vb, Qb = sh.shard_tables(1)
+                assert np.array_equal(Vb, Vo[0][lo:hi]) and np.array_equal(Qb, Qo[0][lo:hi])
 
 
-@pytest.mark.parametrize("case,world", [(cases.case_A_small, 3), (cases.case_A_gy, 3), (cases.case_B2_small, 4),
-                                        (cases.case_B1_ref, 3), (cases.case_C_int, 3), (cases.case_C_rich, 2),
-                                        (cases.case_D_small, 3), (cases.case_M2_small, 3), (cases.case_W_small, 2),
-                                        (cases.case_XR_small, 2)], ids=lambda x: getattr(x, "__name__", str(x))[5:])
-def test_halo_exchange_ranges_on_one_gpu(case, world, S, oracle):
-    """sdpb_shard_reads: each rank is given ONLY the rows of V_{t+1} it declared (everything else in its table
-    is NaN) and must still produce the oracle's block; the host mirror of the range agrees with the library."""
-    import torch
-    par = S.package.parallel
-    spec, _ = case()
+def test_group_kernel_choices_on_one_gpu(S, oracle):
+    """Every specialised kernel under sharding: block edges that cut through tiles, rows and diagonals."""
+    jobs = [(cases.case_B2_small, 3, S.KERNEL_GENERIC), (cases.case_B2_small, 5, S.KERNEL_STAGED),
+            (cases.case_B2_small, 3, S.KERNEL_LEAD_SLAB), (cases.case_B2_small, 4, S.KERNEL_LEAD_COL),
+            (cases.case_B2_small, 7, S.KERNEL_LEAD_Q2), (cases.case_C_int, 4, S.KERNEL_CASH_INT),
+            (cases.case_C_int_K, 5, S.KERNEL_AUTO), (cases.case_A_small, 4, S.KERNEL_TILED),
+            (cases.case_A_small, 3, S.KERNEL_TILED2), (cases.case_A_terminal_big, 3, S.KERNEL_TILED2),
+            (cases.case_A_terminal_big, 7, S.KERNEL_TILED)]
+    for case, world, kernel in jobs:
+        spec, _ = case()
+        Vo, Qo, _, _ = oracle.dense(spec)
+        with S.Group(spec, [0] * world, kernel=kernel) as g:
+            g.solve()
+            for t in range(1, spec.T + 1):
+                V, Q = g.period_tables(t)
+                assert np.array_equal(V, Vo[t - 1]) and np.array_equal(Q, Qo[t - 1]), (spec.name, world, kernel, t)
+
+
+def test_group_dedup_on_one_gpu(S, oracle):
+    spec, _ = cases.case_B2_small()
     Vo, Qo, _, _ = oracle.dense(spec)
-    n = Vo.shape[1]
-    hs = [S.Solver(spec, shard_rank=r, shard_count=world) for r in range(world)]
-    bounds = [par.shard_bounds(n, r, world) for r in range(world)]
-    chunk = bounds[0][2]
-    needs = [h.shard_reads() for h in hs]
-    for r, (lo, hi, _) in enumerate(bounds):
-        assert needs[r] == par.needed_range(spec, lo, hi, n), (r, needs[r])
-    for t in range(spec.T, 0, -1):
-        tabs = [par.wrap_device(torch, h.device_tables(t)[0], chunk * world, "<f8", 0) for h in hs]
-        for tab in tabs:
-            tab.fill_(float("nan"))
-        torch.cuda.synchronize()
-        for h in hs:
-            h.solve_period_async(t)
-        for h in hs:
-            h.sync()
-        for r, (lo, hi, _) in enumerate(bounds):       # what HaloExchange sends: overlap(block[r], needs[r2])
-            for r2 in range(world):
-                a, b = max(lo, needs[r2][0]), min(hi, needs[r2][1])
-                if r2 != r and b > a:
-                    tabs[r2][a:b].copy_(tabs[r][a:b])
-        torch.cuda.synchronize()
-        for r, (lo, hi, _) in enumerate(bounds):
-            assert np.array_equal(tabs[r][lo:hi].cpu().numpy(), Vo[t - 1][lo:hi]), (r, t)
+    with S.Group(spec, [0, 0, 0], dedup=True) as g:
+        g.solve()
+        for t in range(1, spec.T + 1):
+            V, Q = g.period_tables(t)
+            assert np.array_equal(V, Vo[t - 1]) and np.array_equal(Q, Qo[t - 1])
 
 
-def test_large_sharded_c5_on_one_gpu(S, oracle):
-    """tiled2 with shard boundaries that cut through 1021-state tiles."""
-    import torch
-    par = S.package.parallel
-    spec = S.configs.c5(n_states=300_007, T=2, n_actions=37)
+def test_large_group_c5_on_one_gpu(S, oracle):
+    """tiled2 with shard boundaries that cut through 1021-state tiles; each shard holds about a third of the memory."""
+    spec = S.configs.c5(n_states=300_007, T=3, n_actions=37)
     ref = S.Solver(spec).solve()
-    world = 3
-    hs = [S.Solver(spec, shard_rank=r, shard_count=world, kernel=S.KERNEL_TILED2) for r in range(world)]
-    n = ref.n_states
-    bounds = [par.shard_bounds(n, r, world) for r in range(world)]
-    chunk = bounds[0][2]
-    for t in (2, 1):
-        for h in hs:
-            h.solve_period_async(t)
-        for h in hs:
-            h.sync()
-        tabs = [par.wrap_device(torch, h.device_tables(t)[0], chunk * world, "<f8", 0) for h in hs]
-        for r, (lo, hi, _) in enumerate(bounds):
-            for r2 in range(world):
-                if r2 != r:
-                    tabs[r2][lo:hi].copy_(tabs[r][lo:hi])
-        torch.cuda.synchronize()
-    assert hs[0].stats()["kernel_used"] == S.KERNEL_TILED2
-    for t in (1, 2):
-        Vr, Qr = ref.period_tables(t)
-        for r, (lo, hi, _) in enumerate(bounds):
-            dv, dq = hs[r].device_tables(t)
-            V = par.wrap_device(torch, dv, chunk * world, "<f8", 0)[:n].cpu().numpy()
-            Qi = par.wrap_device(torch, dq, chunk * world, "<i4", 0)[lo:hi].cpu().numpy()
-            assert np.array_equal(V, Vr)
-            assert np.array_equal(Qi * spec.step, Qr[lo:hi])
+    full_bytes = ref.grid.device_bytes
+    with S.Group(spec, [0, 0, 0], kernel=S.KERNEL_TILED2, profile=True) as g:
+        g.solve()
+        assert g.shards[0].stats()["kernel_used"] == S.KERNEL_TILED2
+        for t in (1, 2, 3):
+            Vr, Qr = ref.period_tables(t)
+            V, Q = g.period_tables(t)
+            assert np.array_equal(V, Vr) and np.array_equal(Q, Qr)
+        for sh in g.shards:
+            assert sh.grid.device_bytes < 0.40 * full_bytes        # the window, not the whole table
+            out_b, in_b = sh.peer_traffic()
+            assert 0 < out_b < 64 * 1024 and 0 < in_b < 64 * 1024  # a halo of a few hundred states
+            prof = sh.period_profile()
+            assert prof.shape == (3, 3) and (prof[:, 0] > 0).all()
+
+
+def _ipc_worker(rank, world, case_name, kernel, q_in, q_out, out_dir):
+    """One process per shard, all on GPU 0: the torchrun layout, connected through CUDA IPC."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import numpy as np
+    import cases as cs
+    import sdpb200 as S_
+    spec, _ = getattr(cs, case_name)()
+    s = S_.Solver(spec, device=0, shard_rank=rank, shard_count=world, kernel=kernel)
+    q_out.put((rank, s.peer_export()))
+    blobs = q_in.get()
+    s.peer_attach(blobs)
+    for _ in range(2):
+        s.solve()
+    res = {}
+    for t in range(1, spec.T + 1):
+        V, Q = s.shard_tables(t)
+        res[f"V{t}"], res[f"Q{t}"] = V, Q
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), lo=s.grid.shard_lo, hi=s.grid.shard_hi, **res)
+    q_out.put((rank, b"done"))
+    q_in.get()  # keep the tables alive until every shard has finished
+    s.close()
+
+
+@pytest.mark.parametrize("case_name,world,kernel", [("case_B2_small", 3, 0), ("case_C_int", 2, 0), ("case_A_small", 2, 0)])
+def test_ipc_shards_in_separate_processes(case_name, world, kernel, S, oracle, tmp_path):
+    """sdpb_peer_export / sdpb_peer_attach across PROCESSES (cudaIpcOpenMemHandle), the layout bench.py runs under
+    torchrun -- here with every process on GPU 0, so the flags and pushes cross process boundaries but not NVLink."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q_out = ctx.Queue()
+    q_ins = [ctx.Queue() for _ in range(world)]
+    procs = [ctx.Process(target=_ipc_worker, args=(r, world, case_name, kernel, q_ins[r], q_out, str(tmp_path)))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        blobs = dict(q_out.get(timeout=180) for _ in range(world))
+        for qi in q_ins:
+            qi.put([blobs[r] for r in range(world)])
+        for _ in range(world):
+            assert q_out.get(timeout=180)[1] == b"done"
+        for qi in q_ins:
+            qi.put("bye")
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+    spec, _ = getattr(cases, case_name)()
+    Vo, Qo, _, _ = oracle.dense(spec)
+    covered = 0
+    for r in range(world):
+        gz = np.load(tmp_path / f"r{r}.npz")
+        lo, hi = int(gz["lo"]), int(gz["hi"])
+        for t in range(1, spec.T + 1):
+            assert np.array_equal(gz[f"V{t}"], Vo[t - 1][lo:hi]), (r, t)
+            assert np.array_equal(gz[f"Q{t}"], Qo[t - 1][lo:hi]), (r, t)
+        covered += hi - lo
+    assert covered == Vo.shape[1]
+
+
+# ---- dense-grid artefacts at visited states: reported, not silent -----------------------------------------------
+def _unclamped_leadtime(S, inv_min, inv_max, T=3, mean=4, maxq=12):
+    return S.leadtime_model(cases.pmf([mean] * T), fixed_cost=0, vari_cost=1, hold_cost=2, penalty_cost=10,
+                            max_order=maxq, inv_min=inv_min, inv_max=inv_max, lead_time=1, clamp=False)
+
+
+def test_reach_reports_clipped_successors(S, oracle):
+    """Leadtime.java:63-67 does not clamp: on a grid smaller than the reachable hull the kernels fold successors onto
+    the boundary row.  sdpb_reach says so (SDPB_ERR_OFFGRID) when a state the reference visits is affected, unless the
+    caller allows it; with the hull from sdpb_reachable_hull nothing is clipped and the values are the reference's."""
+    init = [[0.0, 0.0]]
+    small = _unclamped_leadtime(S, -8, 20)
+    s = S.Solver(small).solve()
+    with pytest.raises(S.SdpbError) as e:
+        s.reach(init)
+    assert e.value.code == S.abi.SDPB_ERR_OFFGRID and "outside the inventory grid" in str(e.value)
+    assert s.stats()["clipped_successors"] > 0
+    with pytest.raises(S.SdpbError):                       # the facade refuses too
+        S.LeadtimeRecursion(small).getExpectedValue(S.LeadtimeState(1, 0.0, 0.0))
+    ok = S.Solver(small, allow=S.ALLOW_CLIPPED_SUCCESSORS).solve()
+    ok.reach(init)                                         # opt-out: counted, not refused
+    assert ok.stats()["clipped_successors"] == s.stats()["clipped_successors"]
+    # the dense oracle counts the same event over the WHOLE grid, so it sees at least as many
+    assert oracle.dense(small)[3] >= ok.stats()["clipped_successors"]
+
+    lo, hi = S.reachable_hull(small, init)
+    assert lo == -2 * max(r[-1, 0] for r in small.pmf) and hi == 24.0
+    hull = _unclamped_leadtime(S, lo, hi)
+    rec = S.LeadtimeRecursion(hull)
+    v = rec.getExpectedValue(S.LeadtimeState(1, 0.0, 0.0))   # runs sdpb_reach: passes
+    assert rec.stats()["clipped_successors"] == 0
+    rows, iv, _ = oracle.topdown(hull, init)               # the reference's control flow: unbounded real-valued states
+    assert v == iv[0]
+    tab = rec.getOptTable()
+    assert np.array_equal(tab, rows[:, :-1])
+    # a clamped model never reports anything
+    c = S.Solver(cases.case_B1_fixed()[0]).solve()
+    c.reach([[0.0, 0.0]])
+    assert c.stats()["clipped_successors"] == 0
+
+
+def test_reach_reports_capped_action_sets(S, oracle):
+    capped, init = cases.case_XR_small()
+    capped.allow = 0
+    s = S.Solver(capped).solve()
+    with pytest.raises(S.SdpbError) as e:
+        s.reach(init)
+    assert e.value.code == S.abi.SDPB_ERR_OFFGRID and "order-up-to" in str(e.value)
+    assert s.stats()["capped_action_sets"] > 0
+    spec, init = cases.case_XR_uncapped()
+    u = S.Solver(spec).solve()
+    u.reach(init)
+    assert u.stats()["capped_action_sets"] == 0
+
+
+def test_strict_cash_bounds(S):
+    spec, init = cases.case_C_int()
+    s = S.Solver(spec, strict_cash_bounds=True).solve()
+    with pytest.raises(S.SdpbError) as e:                  # cash_max = 260 is reached from (0, 12) within 4 periods
+        s.reach(init)
+    assert e.value.code == S.abi.SDPB_ERR_OFFGRID and s.stats()["cash_bound_hits"] > 0
+    lax = S.Solver(spec).solve()
+    lax.reach(init)                                        # the clamp is part of the reference lambdas: fine by default
+    assert lax.stats()["cash_bound_hits"] == s.stats()["cash_bound_hits"]
+
+
+@pytest.mark.parametrize("case", cases.NOLAST, ids=lambda f: f.__name__[5:])
+def test_no_order_last_auto_equals_generic(case, S, oracle):
+    """SDPB_F_NO_ORDER_LAST on the families whose fast kernels do not know the rule: period T must take the general
+    path, every other period the specialised one; AUTO == GENERIC == oracle, counts included."""
+    spec, init = case()
+    Vo, Qo, evals, _ = oracle.dense(spec)
+    assert np.all(Qo[-1] == 0)
+    a, Va, Qa = _solve_all(S, spec)
+    g, Vg, Qg = _solve_all(S, spec, kernel=S.KERNEL_GENERIC)
+    assert np.array_equal(Va, Vo) and np.array_equal(Qa, Qo)
+    assert np.array_equal(Vg, Vo) and np.array_equal(Qg, Qo)
+    assert a.stats()["evals"] == g.stats()["evals"] == evals
+    assert a.stats()["kernel_used"] != S.KERNEL_GENERIC   # the other periods still ran on the fast kernel
+    if spec.lead_time:
+        d, Vd, Qd = _solve_all(S, spec, dedup=True)
+        assert np.array_equal(Vd, Vo) and np.array_equal(Qd, Qo)
+
+
+def test_boundary_function_facade(S, oracle):
+    """Reads like MultiItemCashXW.java:118-121 / CashRecursionV.java:125-128 for one product: the engine takes a
+    BoundaryFuncton lambda and values the states of period T+1 with it."""
+    spec = S.cash_constraint_model(cases.pmf([5, 6, 5]), price=10, vari_cost=1, salvage=0.0, max_order=14, inv_min=0,
+                                   inv_max=25, cash_min=0, cash_max=200, quantiser=S.Q_LONGDIV, q_mul=1.0, q_div=1.0)
+    salPrice = 0.5
+    boundFinalCash = lambda iniInventory, iniCash: iniCash + salPrice * iniInventory  # noqa: E731
+    recursion = S.CashRecursion(spec, boundFinalCash=boundFinalCash)
+    ref, init = cases.case_C_terminal()
+    rows, iv, _ = oracle.topdown(ref, init)
+    iniState = S.CashState(1, init[0][0], init[0][1])
+    assert recursion.getExpectedValue(iniState) == iv[0]
+    assert recursion.getAction(iniState) == rows[0][-2]
+    # without the boundary function the answer is a different one
+    assert S.CashRecursion(spec).getExpectedValue(iniState) != iv[0]
+
+
+def test_multi_gpu_facade_on_one_gpu(S, oracle):
+    spec, init = cases.case_B2_small()
+    rows, iv, _ = oracle.topdown(spec, init)
+    rec = S.LeadtimeRecursion2(spec, devices=[0, 0, 0])
+    st = S.LeadtimeRecursion2.state_cls(1, 0.0, 0.0, 0.0)
+    assert rec.getExpectedValue(st) == iv[0] and rec.getAction(st) == rows[0][-2]
+
+
+def test_solve_batch(S, oracle):
+    """sdpb_solve_batch: many small independent instances (the parameter sweeps of CLSPTesting.java:57-61) solved
+    together; first call plain, second call captures one CUDA graph for the whole batch, third call replays it."""
+    specs = []
+    for k in range(12):
+        specs.append(S.inventory_model(cases.pmf([5 + k % 3, 8, 6 + k % 2]), fixed_cost=20 + 5 * k, vari_cost=1,
+                                       hold_cost=1 + 0.5 * (k % 2), penalty_cost=5 + k, max_order=15 + k,
+                                       inv_min=-30 - k, inv_max=30 + 2 * k))
+    specs.append(cases.case_B2_small()[0])      # any unsharded handle may be in a batch
+    specs.append(cases.case_C_int()[0])
+    solvers = [S.Solver(sp, kernel=S.KERNEL_TILED if sp.cost_kind == S.COST_BACKORDER and sp.lead_time == 0 else S.KERNEL_AUTO)
+               for sp in specs]
+    for rep in range(4):
+        S.solve_batch(solvers)
+        if rep in (0, 2, 3):
+            for sp, s in zip(specs, solvers):
+                Vo, Qo, evals, _ = oracle.dense(sp)
+                for t in range(1, sp.T + 1):
+                    V, Q = s.period_tables(t)
+                    assert np.array_equal(V, Vo[t - 1]) and np.array_equal(Q, Qo[t - 1]), (rep, sp.name, t)
+                assert s.stats()["evals"] == evals
+    # AUTO handles (the fused whole-horizon kernel on these sizes) batch too
+    auto = [S.Solver(sp) for sp in specs[:6]]
+    for _ in range(3):
+        S.solve_batch(auto)
+    for sp, s in zip(specs[:6], auto):
+        Vo, Qo, _, _ = oracle.dense(sp)
+        V, Q = s.period_tables(1)
+        assert np.array_equal(V, Vo[0]) and np.array_equal(Q, Qo[0])
+
+
+def test_reference_style_driver_clsp_main(S, oracle):
+    """Reads like src/capacitated/CLSP.java:196-290 (the self-contained demo with its own inline pmf)."""
+    meanDemand = [9, 23, 53, 29]
+    truncationQuantile, stepSize, minState, maxState = 0.99999, 1, -300, 300
+    fixedOrderingCost, proportionalOrderingCost, holdingCost, penaltyCost, maxOrderQuantity = 500, 0, 2, 10, 60
+    pmf = S.clsp_inline_pmf(meanDemand, truncationQuantile, stepSize)
+    assert pmf[2][0, 0] > 0                                  # no LB = 0 override: Poisson(53) starts well above zero
+    spec = S.inventory_model(pmf, fixedOrderingCost, proportionalOrderingCost, holdingCost, penaltyCost,
+                             max_order=maxOrderQuantity, inv_min=minState, inv_max=maxState)
+    inventory = S.Recursion(spec)
+    initialState = S.State(1, 1)
+    finalValue = inventory.getExpectedValue(initialState)
+    rows, iv, _ = oracle.topdown(spec, [[1.0]])
+    assert finalValue == iv[0] and inventory.getAction(initialState) == rows[0][-2]
+    assert np.array_equal(inventory.getOptTable(), rows[:, :-1])
+
+
+def test_unattached_shard_refuses_to_solve(S):
+    spec, _ = cases.case_A_small()
+    s = S.Solver(spec, shard_rank=0, shard_count=2)
+    with pytest.raises(S.SdpbError) as e:
+        s.solve()
+    assert e.value.code == S.abi.SDPB_ERR_STATE
+
 
 
 def test_unsolved_state_raises(S):
@@ -699,3 +908,87 @@ def test_config_c5_sampled(S, oracle):
             Va, Qa = s.period_tables(t)
             Vg, Qg = g.period_tables(t)
             assert np.array_equal(Va, Vg) and np.array_equal(Qa, Qg)
+
+
+# ---- J1: the measured configurations at FULL size and FULL horizon -------------------------------
+def _fullsize_golden(name):
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/fullsize.json not generated (tests/golden/make_fullsize_golden.py)")
+    g = json.load(open(path))
+    if name not in g:
+        pytest.skip(f"{name} not in tests/golden/fullsize.json")
+    return g[name]
+
+
+def _golden_spec(spec, gold):
+    """The hashes only mean something on the very pmf table the frozen oracle run used (the fixture carries it)."""
+    assert gold["pmf_same_every_period"]
+    row = np.asarray(gold["pmf"][0], dtype=np.float64)
+    for r in spec.pmf:
+        assert np.array_equal(row, np.asarray(r)), "pmf table differs from the one the golden run used"
+
+
+def _hash_check(s, gold):
+    """Whole grid, every period: SHA-256 of the float64 V_t and Q_t bytes against the frozen oracle run."""
+    import hashlib
+    assert s.n_states == gold["n_states"] and s.T == gold["T"]
+    V = np.empty(s.n_states)
+    Q = np.empty(s.n_states)
+    for t in range(1, s.T + 1):
+        s.period_tables(t, out_v=V, out_q=Q)
+        assert hashlib.sha256(V.tobytes()).hexdigest() == gold["sha256_V"][t - 1], f"V, period {t}"
+        assert hashlib.sha256(Q.tobytes()).hexdigest() == gold["sha256_Q"][t - 1], f"Q, period {t}"
+    v, q = s.value(1, [gold["init"]])
+    assert v[0] == float.fromhex(gold["V1_init"]) and q[0] == gold["Q1_init"]
+
+
+def test_config_c3_full_horizon(S, oracle):
+    """C3 exactly as benched: 1,002,501 states, T = 12.  Every period: inductive sample check against the
+    oracle, and the whole grid against the frozen whole-grid oracle run."""
+    spec = S.configs.c3()
+    s = S.Solver(spec).solve()
+    assert s.n_states == 1002501 and spec.T == 12
+    assert s.stats()["kernel_used"] == S.KERNEL_CASH_DIAG
+    _sample_check(S, oracle, spec, s, n=32)
+    gold = _fullsize_golden("c3")
+    _golden_spec(spec, gold)
+    _hash_check(s, gold)
+    assert s.stats()["evals"] == gold["evals"]
+
+
+def test_config_c4_full_horizon(S, oracle):
+    """C4 exactly as benched: 10,211,201 states, T = 20; brute force and folded."""
+    spec = S.configs.c4()
+    s = S.Solver(spec).solve()
+    assert s.n_states == 10211201 and spec.T == 20
+    assert s.stats()["kernel_used"] == S.KERNEL_LEAD_Q2
+    _sample_check(S, oracle, spec, s, n=64)
+    gold = _fullsize_golden("c4")
+    _golden_spec(spec, gold)
+    _hash_check(s, gold)
+    assert s.stats()["evals"] == gold["evals"]
+    s.close()
+    d = S.Solver(spec, dedup=True).solve()
+    _hash_check(d, gold)
+
+
+def test_config_c5_bench_grid_full_horizon(S, oracle):
+    """The C5 point the round-1 bench line was quoted on: 1e7 states x 200 x 200, T = 4."""
+    spec = S.configs.c5(n_states=10_000_000)
+    s = S.Solver(spec).solve()
+    assert s.stats()["kernel_used"] == S.KERNEL_TILED2
+    _sample_check(S, oracle, spec, s, n=64)
+    gold = _fullsize_golden("c5_1e7")
+    _golden_spec(spec, gold)
+    _hash_check(s, gold)
+    assert s.stats()["evals"] == gold["evals"]
+
+
+def test_config_c5_1e8_sampled(S, oracle):
+    """The largest single-GPU point of the sweep (1e8 states, T = 4): inductive sample check of every period."""
+    spec = S.configs.c5(n_states=100_000_000)
+    s = S.Solver(spec).solve()
+    _sample_check(S, oracle, spec, s, n=48)
