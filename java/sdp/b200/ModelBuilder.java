@@ -81,6 +81,68 @@ public final class ModelBuilder {
 
     public ModelBuilder survival() { return i("recursion", SdpB200.REC_SURVIVAL); }   // RiskRecursion.java:64-108
 
+    /** src/cash/overdraft/SingleProductLeadtime.java:72-119: cash + lead time 1, no order in the last period (:74-75),
+     *  quantiser Math.round(w*100)/100.0 (:117).  Engine: GpuCashLeadtimeRecursion. */
+    public static ModelBuilder cashLeadtime(Arena a, double[][][] pmf, double price, double v, double salvage,
+                                            double[] overhead, double r0, double r2, double r3, double limit,
+                                            double interestFree, double maxOrderQuantity, double minInv, double maxInv,
+                                            double minCash, double maxCash) {
+        return cashOverdraft(a, pmf, price, v, 0, salvage, overhead, r0, r2, r3, limit, interestFree, maxOrderQuantity,
+                minInv, maxInv, minCash, maxCash)
+                .flags(SdpB200.F_CLAMP_INV | SdpB200.F_LOST_SALES | SdpB200.F_NO_ORDER_LAST).i("lead_time", 1)
+                .i("quantiser", SdpB200.Q_DIV).d("q_mul", 100).d("q_div", 100.0);
+    }
+
+    /** src/cash/singleItem/CashConstraintXR.java:71-110: (x, R = w + v x) coordinates, action = order-up-to level.
+     *  max_order_idx is chosen so that no state's order-up-to range x..max(x, R/v) is capped (:71-75 has no cap). */
+    public static ModelBuilder cashXR(Arena a, double[][][] pmf, double price, double v, double K, double h, double salvage,
+                                      double overhead, double minInv, double maxInv, double minCash, double maxCash,
+                                      double discountFactor) {
+        int levels = (int) Math.ceil((maxCash + v * maxInv) / v - minInv) + 1;
+        return new ModelBuilder(a, SdpB200.COST_CASH_XR, pmf).direction(false)
+                .flags(SdpB200.F_CLAMP_INV | SdpB200.F_LOST_SALES).maxOrder(levels).inventory(minInv, maxInv)
+                .d("cash_min", minCash).d("cash_max", maxCash).i("quantiser", SdpB200.Q_LONGDIV).d("q_mul", 1).d("q_div", 1)
+                .d("price", price).d("vari_cost", v).d("fixed_cost", K).d("hold_cost", h).d("salvage", salvage)
+                .d("overhead", overhead).d("gamma", discountFactor);
+    }
+
+    /** src/cash/risk/cashSurvival.java:102-147 with per-period price / cost / overhead arrays; engine GpuRiskRecursion. */
+    public static ModelBuilder cashSurvival(Arena a, double[][][] pmf, double[] price, double[] v, double[] overhead,
+                                            double salvage, double maxOrderQuantity, double minInv, double maxInv,
+                                            double minCash, double maxCash) {
+        ModelBuilder b = new ModelBuilder(a, SdpB200.COST_CASH_DEPOSIT, pmf).direction(false).survival()
+                .flags(SdpB200.F_CLAMP_INV | SdpB200.F_LOST_SALES | SdpB200.F_CASH_LIMITED_ACTIONS)
+                .maxOrder((int) maxOrderQuantity).inventory(minInv, maxInv).d("cash_min", minCash).d("cash_max", maxCash)
+                .i("quantiser", SdpB200.Q_LONGDIV).d("q_mul", 1).d("q_div", 1).d("salvage", salvage);
+        b.array("price_t", price); b.array("vari_cost_t", v); b.array("overhead_t", overhead);
+        return b;
+    }
+
+    /**
+     * The terminal boundary function (FinalCash.BoundaryFuncton, src/sdp/inventory/FinalCash.java:16-18; consumed at
+     * src/sdp/cash/multiItem/CashRecursionV.java:125-128): `table[i]` is the value of grid state i of period T+1, in
+     * the library's state order (inventory outermost, cash innermost; sdpb_state_of_index gives the coordinates).
+     */
+    public ModelBuilder boundFinalCash(double[] table) { array("terminal_value", table); return this; }
+
+    /** Leadtime.java:63-67 does not clamp: make the inventory axis the reachable hull of the initial states. */
+    public ModelBuilder reachableHull(double[] initStates, int nStates) {
+        try {
+            MemorySegment st = arena.allocate(JAVA_DOUBLE, initStates.length), lo = arena.allocate(JAVA_DOUBLE),
+                    hi = arena.allocate(JAVA_DOUBLE);
+            for (int k = 0; k < initStates.length; k++) st.setAtIndex(JAVA_DOUBLE, k, initStates[k]);
+            int rc = (int) SdpB200.REACHABLE_HULL.invokeExact(m, st, nStates, lo, hi);
+            if (rc != 0) throw new IllegalStateException("sdpb_reachable_hull: " + rc);
+            return inventory(lo.get(JAVA_DOUBLE, 0), hi.get(JAVA_DOUBLE, 0));
+        } catch (Throwable t) { throw new RuntimeException(t); }
+    }
+
+    private void array(String f, double[] v) {
+        MemorySegment s = arena.allocate(JAVA_DOUBLE, v.length);
+        for (int t = 0; t < v.length; t++) s.setAtIndex(JAVA_DOUBLE, t, v[t]);
+        setA(f, s);
+    }
+
     public MemorySegment build() { return m; }
 
     // ---- plumbing ----

@@ -17,7 +17,11 @@ public final class SdpB200 {
     public static final int COST_BACKORDER = 0, COST_CASH_DEPOSIT = 1, COST_CASH_OVERDRAFT = 2, COST_CASH_XR = 3;
     public static final int REC_EXPECT = 0, REC_SURVIVAL = 1;
     public static final int MIN = 0, MAX = 1;
-    public static final int Q_DIV = 0, Q_LONGDIV = 1;
+    public static final int COST_CASH_OD_LIMIT = 4, COST_CASH_OD_TESTING = 5, COST_CASH_LOAN = 6, COST_CASH_TWO_PRODUCT = 7,
+            COST_STAFF = 8;
+    public static final int Q_DIV = 0, Q_LONGDIV = 1, Q_TRUNC = 2;
+    public static final int ALLOW_CLIPPED_SUCCESSORS = 1, ALLOW_CAPPED_ACTIONS = 2;
+    public static final int ABI_VERSION = 4;
     public static final int F_CLAMP_INV = 1, F_LOST_SALES = 2, F_GY_MODE = 4, F_NO_ORDER_LAST = 8,
             F_CASH_LIMITED_ACTIONS = 16;
 
@@ -40,7 +44,22 @@ public final class SdpB200 {
             ADDRESS.withName("reserve_t"), JAVA_DOUBLE.withName("reserve2"),
             JAVA_DOUBLE.withName("price2"), JAVA_DOUBLE.withName("vari_cost2"), JAVA_DOUBLE.withName("salvage2"),
             ADDRESS.withName("pmf_d2"), JAVA_DOUBLE.withName("tie_tolerance"),
-            ADDRESS.withName("apmf_len"), ADDRESS.withName("apmf_p"), ADDRESS.withName("min_level_t"));
+            ADDRESS.withName("apmf_len"), ADDRESS.withName("apmf_p"), ADDRESS.withName("min_level_t"),
+            ADDRESS.withName("terminal_value"));
+
+    /** struct sdpb_options, field for field. */
+    public static final StructLayout OPTIONS = MemoryLayout.structLayout(
+            JAVA_INT.withName("struct_size"), JAVA_INT.withName("device"), JAVA_INT.withName("shard_rank"),
+            JAVA_INT.withName("shard_count"), JAVA_INT.withName("kernel"), JAVA_INT.withName("dedup"),
+            ADDRESS.withName("stream"), JAVA_INT.withName("allow"), JAVA_INT.withName("strict_cash_bounds"),
+            JAVA_INT.withName("profile"), JAVA_INT.withName("reserved"));
+
+    /** struct sdpb_grid, field for field. */
+    public static final StructLayout GRID = MemoryLayout.structLayout(
+            JAVA_INT.withName("ndim"), JAVA_INT.withName("n_inv"), JAVA_INT.withName("n_cash"), JAVA_INT.withName("n_q"),
+            JAVA_LONG.withName("n_states"), JAVA_LONG.withName("shard_lo"), JAVA_LONG.withName("shard_hi"),
+            JAVA_INT.withName("n_actions"), JAVA_INT.withName("T"), JAVA_LONG.withName("cash_k_min"),
+            JAVA_LONG.withName("window_lo"), JAVA_LONG.withName("window_hi"), JAVA_LONG.withName("device_bytes"));
 
     private static final Linker LINKER = Linker.nativeLinker();
     private static final SymbolLookup LIB =
@@ -70,10 +89,33 @@ public final class SdpB200 {
     static final MethodHandle EVAL_TRIPLES = fn("sdpb_eval_triples", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT,
             ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
 
+    static final MethodHandle ABI_VERSION_FN = fn("sdpb_abi_version", FunctionDescriptor.of(JAVA_INT));
+    static final MethodHandle SIZEOF_OPTIONS = fn("sdpb_sizeof_options", FunctionDescriptor.of(JAVA_LONG));
+    static final MethodHandle SIZEOF_GRID = fn("sdpb_sizeof_grid", FunctionDescriptor.of(JAVA_LONG));
+    static final MethodHandle GRID_INFO = fn("sdpb_grid_info", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle REACHABLE_HULL = fn("sdpb_reachable_hull",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle SOLVE_BATCH = fn("sdpb_solve_batch", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    // one process, several GPUs (a JVM is exactly that): the shards exchange rows of V_t inside the library
+    static final MethodHandle GROUP_CREATE = fn("sdpb_group_create",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
+    static final MethodHandle GROUP_DESTROY = fn("sdpb_group_destroy", FunctionDescriptor.ofVoid(ADDRESS));
+    static final MethodHandle GROUP_LAST_ERROR = fn("sdpb_group_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
+    static final MethodHandle GROUP_SOLVE = fn("sdpb_group_solve", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle GROUP_SHARD = fn("sdpb_group_shard", FunctionDescriptor.of(ADDRESS, ADDRESS, JAVA_INT));
+    static final MethodHandle GROUP_VALUE = fn("sdpb_group_value",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle GROUP_PERIOD_TABLES = fn("sdpb_group_period_tables",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+
     static {
         try {
-            if ((long) SIZEOF_MODEL.invokeExact() != MODEL.byteSize())
-                throw new IllegalStateException("libsdpb200.so struct layout differs from SdpB200.MODEL");
+            if ((int) ABI_VERSION_FN.invokeExact() != ABI_VERSION
+                    || (long) SIZEOF_MODEL.invokeExact() != MODEL.byteSize()
+                    || (long) SIZEOF_OPTIONS.invokeExact() != OPTIONS.byteSize()
+                    || (long) SIZEOF_GRID.invokeExact() != GRID.byteSize())
+                throw new IllegalStateException("libsdpb200.so struct layout differs from SdpB200 (java/LAYOUT.txt lists "
+                        + "the offsets the C compiler produced)");
         } catch (Throwable t) {
             throw new ExceptionInInitializerError(t);
         }

@@ -44,6 +44,11 @@ struct CashPlan {
     const char* why_not = "";
     int K = 0;
     std::vector<CashPeriod> period;
+    // bi_cash_diag with the action range cut into slices (gridDim.z): per slice and state the slice's optimum,
+    // merged by merge_action_slices.  Owned by the handle (allocated on first use from its pool).
+    double* slice_v = nullptr;
+    int* slice_a = nullptr;
+    size_t slice_cap = 0;  // entries
 };
 
 struct CashArgs {
@@ -54,12 +59,19 @@ struct CashArgs {
     long long lo, hi;
     int ix0;                     // first inventory row of the shard
     int price, v, K, ovh, d0, inv_min_i;
+    double* slice_v;             // [gridDim.z][hi - lo] when the action range is sliced over gridDim.z
+    int* slice_a;
 };
 
-template <bool SURVIVAL, bool IS_MIN, bool LAST>
+// R cash levels per thread.  With a successor (t < T) every level gathers its own V_{t+1} entry and R = 4; in the
+// last period there is no gather, the levels of a thread share c and p*c and differ only in their own running sum,
+// so R = 16 brings the fp64 work down to 1 + 4/16 instructions per evaluation (R = 4: 7.8 ms of the 12 periods of C3).
+constexpr int kCashRLast = 16;
+
+template <bool SURVIVAL, bool IS_MIN, bool LAST, int R = kCashR>
 __global__ void __launch_bounds__(kCashThreads)
 bi_cash_int(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs a) {
-    constexpr int R = kCashR;
+    constexpr int kCashTile = kCashThreads * R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* PP = reinterpret_cast<double2*>(smem_raw);                          // (p, p*gamma)
     double* PRd = reinterpret_cast<double*>(smem_raw + (size_t)a.D * 16);        // price * d_j
@@ -250,13 +262,23 @@ inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& d
     a.ix0 = (int)(lo / dm.nW);
     const int ix1 = (int)((hi - 1) / dm.nW);
     a.price = cp.price; a.v = cp.v; a.K = P.K; a.ovh = cp.ovh; a.d0 = cp.d0; a.inv_min_i = (int)m.inv_min;
-    const dim3 grid((unsigned)(ix1 - a.ix0 + 1), (unsigned)((dm.nW + kCashTile - 1) / kCashTile));
-    const size_t smem = (size_t)D * 28 + 16;
     const bool surv = m.recursion == SDPB_REC_SURVIVAL;
+    const int tile = kCashThreads * ((t == m.T && !surv) ? kCashRLast : kCashR);
+    const dim3 grid((unsigned)(ix1 - a.ix0 + 1), (unsigned)((dm.nW + tile - 1) / tile));
+    const size_t smem = (size_t)D * 28 + 16;
+    if (smem > 200 * 1024) return SDPB_ERR_STATE;  // demand support too long for the shared-memory tables: general path
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(bi_cash_int<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(bi_cash_int<false, true, true, kCashRLast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(bi_cash_int<false, false, true, kCashRLast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(bi_cash_int<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(bi_cash_int<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(bi_cash_int<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     if (t == m.T) {
         if (surv) bi_cash_int<true, false, true><<<grid, kCashThreads, smem, stream>>>(dm, a);
-        else if (dm.is_min) bi_cash_int<false, true, true><<<grid, kCashThreads, smem, stream>>>(dm, a);
-        else bi_cash_int<false, false, true><<<grid, kCashThreads, smem, stream>>>(dm, a);
+        else if (dm.is_min) bi_cash_int<false, true, true, kCashRLast><<<grid, kCashThreads, smem, stream>>>(dm, a);
+        else bi_cash_int<false, false, true, kCashRLast><<<grid, kCashThreads, smem, stream>>>(dm, a);
     } else {
         if (surv) bi_cash_int<true, false, false><<<grid, kCashThreads, smem, stream>>>(dm, a);
         else if (dm.is_min) bi_cash_int<false, true, false><<<grid, kCashThreads, smem, stream>>>(dm, a);
@@ -264,7 +286,7 @@ inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& d
     }
     if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
     if (fp64_ops) {
-        if (t == m.T) *fp64_ops += evals * (surv ? 2.0 + 3.0 / kCashR : 1.0 + 4.0 / kCashR);
+        if (t == m.T) *fp64_ops += evals * (surv ? 2.0 + 3.0 / kCashR : 1.0 + 4.0 / kCashRLast);
         else *fp64_ops += evals * (surv ? 2.0 : 3.0 + 2.0 / kCashR);
     }
     return SDPB_OK;
@@ -290,9 +312,10 @@ inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& d
 constexpr int kDiagYT = 8;
 constexpr int kDiagCols = 64;  // state columns (cash levels of slot 0) per CTA
 
-template <bool SURVIVAL, bool IS_MIN, int kDiagThreads, int PF = 2>
-__global__ void __launch_bounds__(kDiagThreads, 512 / kDiagThreads)
+template <bool SURVIVAL, bool IS_MIN, int PF = 2>
+__global__ void __launch_bounds__(kDiagCols, 512 / kDiagCols)
 bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs a) {
+    constexpr int kDiagThreads = kDiagCols;
     constexpr int YT = kDiagYT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* PP = reinterpret_cast<double2*>(smem_raw);                    // (p, p*gamma)
@@ -304,12 +327,13 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
     __syncthreads();
     const unsigned pp_s = (unsigned)__cvta_generic_to_shared(PP);
     const unsigned pr_s = (unsigned)__cvta_generic_to_shared(PRd);
-    // action split: the CTA is kDiagCols state columns x `parts` slices of the action range (small grids
-    // cannot fill the GPU with columns alone); slices > 0 hand their optima to slice 0 through shared memory
-    constexpr int parts = kDiagThreads / kDiagCols;
-    const int part = threadIdx.x / kDiagCols, col = threadIdx.x % kDiagCols;
-    double* MV = reinterpret_cast<double*>(smem_raw + (((size_t)a.D * 24 + 15) & ~(size_t)15));  // [parts-1][YT][cols]
-    int* MA = reinterpret_cast<int*>(MV + (size_t)(parts - 1) * YT * kDiagCols);
+    // action split: gridDim.z CTAs share a tile of state columns and take one slice of the action range each.  The
+    // grid of a 1e6-state model is only ~2000 CTAs of 2 warps -- 14 per SM, where one CTA more or less on an SM is a
+    // 7 % tail, and 1.8 per SM on an eighth of the grid -- so the unit of work is made 4-16 times smaller and the
+    // block scheduler balances the SMs; every slice writes its optimum per state and merge_action_slices picks
+    // the first best one (ascending slices hold ascending actions).
+    const int parts = (int)gridDim.z;
+    const int part = (int)blockIdx.z, col = threadIdx.x;
 
     const int D = a.D, price = a.price, nW1 = M.nW - 1;
     const int ix0 = a.ix0 + blockIdx.y * YT;                                  // inventory index of slot 0
@@ -336,7 +360,7 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
         best[k] = IS_MIN ? DBL_MAX : -DBL_MAX;
         arg[k] = kNoAction;
     }
-    if (parts == 1 && nAmax == 0) return;
+    if (nAmax == 0) return;
 
     const int xv0 = a.inv_min_i + ix0;  // inventory VALUE of slot 0
     const int row_tail = min(max(M.i_zero, 0), M.nI - 1) * M.nW;
@@ -392,10 +416,42 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
             c_run += price;                                                                          \
             j += 1;                                                                                  \
         }
-        while (j + W <= jy0) {
-#pragma unroll
-            for (int JJ = 0; JJ < W; JJ++) SDPB_DIAG_FAST(JJ)
+        // The same step with the gather address taken from ONE running offset: inside a block of W steps the unclamped
+        // row offset falls by nW and the unclamped cash index rises by price per step, so when no clamp changes state
+        // inside the block -- rows inside the grid; cash either inside [0, nW-1] throughout or at/above the upper clamp
+        // throughout -- the address is off0 + s*delta (delta = price - nW, or -nW under the upper cash clamp) and the
+        // two clamps, two running adds and the combine of gather_at (7 integer instructions per step; the fp64 pipe
+        // takes two dispatch slots per instruction, so every other instruction costs half an fp64 instruction:
+        // ncu, profiles/r02_ncu_cash_diag.md) shrink to one add.
+#define SDPB_DIAG_FAST_LIN(JJ)                                                                   \
+        {                                                                                            \
+            const double2 pp = lds_double2(pp_s + (unsigned)j * 16u);                                \
+            const double m = pp.x * (lds_double(pr_s + (unsigned)j * 8u) - Cd);  /* p_j * c */      \
+            _Pragma("unroll") for (int k = 0; k < YT; k++) {                                         \
+                acc[k] += m;                                       /* CashRecursion.java:117 */     \
+                acc[k] += pp.y * Vw[(k - (JJ) + W) % W];           /* CashRecursion.java:120 */     \
+            }                                                                                        \
+            Vw[(YT - 1 - (JJ) + W) % W] = __ldg(a.Vn + (unsigned)off_lin);                           \
+            off_lin += delta_lin;                                                                    \
+            j += 1;                                                                                  \
         }
+        while (j + W <= jy0) {
+            const int ro_last = ro_run - (W - 1) * M.nW, c_last = c_run + (W - 1) * price;  // (price > 0: checked by the launcher)
+            const bool rows_in = ro_last >= 0 && ro_run <= row_max;
+            const bool cash_in = c_run >= 0 && c_last <= nW1, cash_hi = c_run >= nW1;
+            if (!SURVIVAL && rows_in && (cash_in || cash_hi)) {
+                int off_lin = ro_run + (cash_in ? c_run : nW1);
+                const int delta_lin = cash_in ? price - M.nW : -M.nW;
+#pragma unroll
+                for (int JJ = 0; JJ < W; JJ++) SDPB_DIAG_FAST_LIN(JJ)
+                ro_run -= W * M.nW;
+                c_run += W * price;
+            } else {
+#pragma unroll
+                for (int JJ = 0; JJ < W; JJ++) SDPB_DIAG_FAST(JJ)
+            }
+        }
+#undef SDPB_DIAG_FAST_LIN
         // ---- stock-out entry: the same for every slot ----
         const int kt = min(max(iw0 + price * (xv0 + ai) - CI, 0), nW1);
         double Vtail = __ldg(a.Vn + (unsigned)(row_tail + kt));
@@ -440,39 +496,58 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
             if (ai < nA[k] && (IS_MIN ? (acc[k] < best[k]) : (acc[k] > best[k]))) { best[k] = acc[k]; arg[k] = ai; }
         }
     }
-    if (parts > 1) {
-        if (part > 0) {
-#pragma unroll
-            for (int k = 0; k < YT; k++) {
-                MV[((part - 1) * YT + k) * kDiagCols + col] = best[k];
-                MA[((part - 1) * YT + k) * kDiagCols + col] = arg[k];
-            }
-        }
-        __syncthreads();
-        if (part > 0) return;
-        // ascending slices hold ascending actions: a strict compare keeps the first optimum
-        for (int q = 0; q < parts - 1; q++) {
-#pragma unroll
-            for (int k = 0; k < YT; k++) {
-                const double v = MV[(q * YT + k) * kDiagCols + col];
-                const int av = MA[(q * YT + k) * kDiagCols + col];
-                if (av != kNoAction && (IS_MIN ? (v < best[k]) : (v > best[k]))) { best[k] = v; arg[k] = av; }
-            }
-        }
-    }
+    const long long n_local = a.hi - a.lo;
 #pragma unroll
     for (int k = 0; k < YT; k++) {
         if (nA[k] > 0) {
             const long long idx = (long long)(ix0 + k) * M.nW + (iw0 - price * k);
-            a.Vt[idx] = best[k];
-            a.Qt[idx] = arg[k] == kNoAction ? -1 : arg[k];
+            if (parts == 1) {
+                a.Vt[idx] = best[k];
+                a.Qt[idx] = arg[k] == kNoAction ? -1 : arg[k];
+            } else {
+                a.slice_v[(long long)part * n_local + (idx - a.lo)] = best[k];
+                a.slice_a[(long long)part * n_local + (idx - a.lo)] = arg[k];
+            }
         }
     }
 }
 
+// Optimum over the action slices of one state: slices in ascending order hold ascending actions, so a strict compare
+// keeps the first optimum (Recursion.java:146-157); a slice that held no feasible action of the state says kNoAction.
+template <bool IS_MIN>
+__global__ void __launch_bounds__(256)
+merge_action_slices(const double* __restrict__ sv, const int* __restrict__ sa, int parts, long long n_local,
+                    double* __restrict__ Vt, int* __restrict__ Qt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_local) return;
+    double best = IS_MIN ? DBL_MAX : -DBL_MAX;
+    int arg = kNoAction;
+    for (int q = 0; q < parts; q++) {
+        const double v = sv[(long long)q * n_local + i];
+        const int av = sa[(long long)q * n_local + i];
+        if (av != kNoAction && (IS_MIN ? (v < best) : (v > best))) { best = v; arg = av; }
+    }
+    Vt[i] = best;
+    Qt[i] = arg == kNoAction ? -1 : arg;
+}
+
+// Slices of the action range for a launch over [lo, hi): up to 16, at least ~12 actions per slice.
+inline int cash_diag_parts(const sdpb_model& m, const DevModel& dm, const CashPeriod& cp, long long lo, long long hi, int sm_count) {
+    const int ix0 = (int)(lo / dm.nW), ix1 = (int)((hi - 1) / dm.nW);
+    const int span_w = dm.nW + cp.price * (kDiagYT - 1);
+    const long long tiles = (long long)((span_w + kDiagCols - 1) / kDiagCols) * ((ix1 - ix0 + 1 + kDiagYT - 1) / kDiagYT);
+    const long long want = 256LL * sm_count;  // measured on C3: 3 slices 114.9 ms, 4: 113.7, 8: 111.5, 16: 110.2; an eighth of the grid: 4: 19.5, 8: 17.5, 16: 16.6
+    int parts = 1;
+    if (tiles < want) parts = (int)std::min<long long>((want + tiles - 1) / tiles, 16);
+    parts = std::max(1, std::min(parts, (m.max_order_idx + 1) / 12));
+    static const int env_split = [] { const char* e = std::getenv("SDPB_DIAG_SPLIT"); return e ? std::atoi(e) : 0; }();
+    if (env_split) parts = std::max(1, std::min(env_split, 32));  // tuning knob, read once per process
+    return parts;
+}
+
 inline int launch_cash_diag(const CashPlan& P, const sdpb_model& m, const DevModel& dm, int t, int D, int pmf_off,
                             const double* Vn, double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream,
-                            double* fp64_ops, double evals) {
+                            double* fp64_ops, double evals, int sm_count) {
     if (!P.available || t >= m.T || !P.period[t - 1].ok) return SDPB_ERR_STATE;
     if (hi <= lo) return SDPB_OK;
     const CashPeriod& cp = P.period[t - 1];
@@ -485,25 +560,36 @@ inline int launch_cash_diag(const CashPlan& P, const sdpb_model& m, const DevMod
     const int ix1 = (int)((hi - 1) / dm.nW);
     a.price = cp.price; a.v = cp.v; a.K = P.K; a.ovh = cp.ovh; a.d0 = cp.d0; a.inv_min_i = (int)m.inv_min;
     const int span_w = dm.nW + cp.price * (kDiagYT - 1);  // slot 0's cash index runs past the axis so slot 7 covers it
-    const dim3 grid((unsigned)((span_w + kDiagCols - 1) / kDiagCols), (unsigned)((ix1 - a.ix0 + 1 + kDiagYT - 1) / kDiagYT));
-    // slices of the action range per CTA: enough warps for ~6 waves of 16 warps per SM
-    int sm_count = 148, dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    const double waves = (double)grid.x * grid.y * (kDiagCols / 32) / (16.0 * sm_count);
-    int parts = waves >= 6.0 ? 1 : (waves >= 3.0 ? 2 : 4);
-    static const int env_split = [] { const char* e = std::getenv("SDPB_DIAG_SPLIT"); return e ? std::atoi(e) : 0; }();
-    if (env_split) parts = env_split == 1 ? 1 : env_split == 2 ? 2 : 4;  // tuning knob, read once per process
-    const size_t smem = (((size_t)D * 24 + 15) & ~(size_t)15) + (size_t)(parts - 1) * kDiagYT * kDiagCols * 12 + 16;
+    const unsigned gx = (unsigned)((span_w + kDiagCols - 1) / kDiagCols), gy = (unsigned)((ix1 - a.ix0 + 1 + kDiagYT - 1) / kDiagYT);
+    const int parts = cash_diag_parts(m, dm, cp, lo, hi, sm_count);
+    const long long n_local = hi - lo;
+    if (parts > 1) {
+        const size_t need = (size_t)parts * (size_t)n_local;
+        if (need > P.slice_cap) return SDPB_ERR_NOMEM;  // (the caller sizes the scratch: see cash_diag_scratch)
+        a.slice_v = P.slice_v; a.slice_a = P.slice_a;
+        // (every slice writes every state of [lo, hi): a valid state has at least one action, so its thread never exits early)
+    } else { a.slice_v = nullptr; a.slice_a = nullptr; }
+    const dim3 grid(gx, gy, (unsigned)parts);
+    const size_t smem = (((size_t)D * 24 + 15) & ~(size_t)15) + 16;
     const bool surv = m.recursion == SDPB_REC_SURVIVAL;
-#define SDPB_DIAG_LAUNCH(NT)                                                                      \
-    {                                                                                             \
-        if (surv) bi_cash_diag<true, false, NT><<<grid, NT, smem, stream>>>(dm, a);               \
-        else if (dm.is_min) bi_cash_diag<false, true, NT><<<grid, NT, smem, stream>>>(dm, a);     \
-        else bi_cash_diag<false, false, NT><<<grid, NT, smem, stream>>>(dm, a);                   \
+    if (smem > 200 * 1024) return SDPB_ERR_STATE;  // demand support too long for the shared-memory tables: general path
+    cudaError_t e = cudaSuccess;
+    static const int env_pf = [] { const char* e2 = std::getenv("SDPB_DIAG_PF"); return e2 ? std::atoi(e2) : 0; }();
+#define SDPB_DIAG_LAUNCH(SV, MN)                                                                              \
+    {                                                                                                         \
+        auto k = env_pf == 4 ? bi_cash_diag<SV, MN, 4> : env_pf == 3 ? bi_cash_diag<SV, MN, 3> : bi_cash_diag<SV, MN>; \
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) k<<<grid, kDiagCols, smem, stream>>>(dm, a);                                   \
     }
-    if (parts == 1) SDPB_DIAG_LAUNCH(64) else if (parts == 2) SDPB_DIAG_LAUNCH(128) else SDPB_DIAG_LAUNCH(256)
+    if (surv) SDPB_DIAG_LAUNCH(true, false) else if (dm.is_min) SDPB_DIAG_LAUNCH(false, true) else SDPB_DIAG_LAUNCH(false, false)
 #undef SDPB_DIAG_LAUNCH
-    if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+    if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+    if (parts > 1) {
+        const unsigned mb = (unsigned)((n_local + 255) / 256);
+        if (dm.is_min && !surv) merge_action_slices<true><<<mb, 256, 0, stream>>>(P.slice_v, P.slice_a, parts, n_local, Vt + lo, Qt + lo);
+        else merge_action_slices<false><<<mb, 256, 0, stream>>>(P.slice_v, P.slice_a, parts, n_local, Vt + lo, Qt + lo);
+        if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+    }
     if (fp64_ops) *fp64_ops += evals * (surv ? 2.0 : 3.0 + 2.0 / kDiagYT);
     return SDPB_OK;
 }

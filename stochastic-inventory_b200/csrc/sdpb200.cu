@@ -64,6 +64,8 @@ struct PeerInfo {
     uint64_t v_off0, v_stride; // address of V_t[i] = base + v_off0 + (t-1) * v_stride + (i - vlo) * 8
     uint64_t flags_off;        // unsigned[64]: flags[r] = number of exchanges rank r has completed into this shard
     uint64_t model_hash;
+    uint64_t handle;           // the exporting sdpb_handle* (meaningful in the exporting process only)
+    char pci[24];              // PCI bus id of the exporter's GPU: two PROCESSES must not share a GPU (see sdpb_peer_attach)
     cudaIpcMemHandle_t ipc;
 };
 static_assert(sizeof(PeerInfo) <= SDPB_PEER_BLOB_BYTES, "peer blob too small");
@@ -83,6 +85,13 @@ struct PeerLink {
     int* d_from = nullptr;             // device array: ranks I wait for
     unsigned epoch = 0;                // exchanges completed so far (identical on every shard)
     long long bytes_out = 0, bytes_in = 0;
+    // Hand-over of the pushed rows.  Shards in different processes (one per GPU): a flag word in the receiver's memory,
+    // stored after the copies and spun on by a one-CTA kernel of the receiver.  Shards of ONE process (sdpb_group_*):
+    // a CUDA event recorded after the copies, which the receivers' streams wait on -- no kernel ever waits for another
+    // kernel, so shards may share a GPU (kernels that spin on each other are not guaranteed to run at the same time).
+    bool by_events = false;
+    cudaEvent_t ev_pushed = nullptr;
+    std::vector<sdpb_handle*> peer_handles;  // [world], by_events only
 };
 
 struct sdpb_handle {
@@ -164,6 +173,60 @@ cudaMemPool_t library_pool(int dev) {
         g_pools[dev] = pool;
     }
     return g_pools[dev];
+}
+
+// Sharded handles keep their tables in ONE plain cudaMalloc allocation (CUDA IPC cannot export pool memory).  cudaMalloc /
+// cudaFree of a gigabyte and cudaIpcOpenMemHandle / cudaIpcCloseMemHandle cost 50-170 ms per create/destroy cycle, so a
+// destroyed handle's slab is parked here and the next sharded handle of the device that fits reuses it; a peer that has
+// mapped it before finds the mapping (keyed by the IPC handle's bytes) still open.  sdpb_trim_pool releases everything.
+struct Slab { char* p; size_t bytes; };
+std::vector<Slab> g_slabs[64];
+struct IpcMapping { cudaIpcMemHandle_t handle; int device; char* p; };
+std::vector<IpcMapping> g_ipc_maps;
+constexpr size_t kMaxParkedSlabs = 4;
+
+char* slab_acquire(int dev, size_t bytes, size_t* got) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto& v = g_slabs[dev];
+        size_t best = v.size();
+        for (size_t i = 0; i < v.size(); i++)
+            if (v[i].bytes >= bytes && v[i].bytes <= bytes + bytes / 4 + (1u << 20) && (best == v.size() || v[i].bytes < v[best].bytes))
+                best = i;
+        if (best != v.size()) {
+            char* p = v[best].p;
+            *got = v[best].bytes;
+            v.erase(v.begin() + (long)best);
+            return p;
+        }
+    }
+    char* p = nullptr;
+    if (cudaMalloc((void**)&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *got = bytes;
+    return p;
+}
+
+void slab_release(int dev, char* p, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto& v = g_slabs[dev];
+    if (v.size() >= kMaxParkedSlabs) {  // keep the most recent ones
+        cudaFree(v.front().p);
+        v.erase(v.begin());
+    }
+    v.push_back({p, bytes});
+}
+
+// A peer process's slab in this address space (for the CUDA device current at the call).
+cudaError_t ipc_map(const cudaIpcMemHandle_t& hd, int device, char** out) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (const IpcMapping& m : g_ipc_maps)
+        if (m.device == device && std::memcmp(&m.handle, &hd, sizeof hd) == 0) { *out = m.p; return cudaSuccess; }
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return e;
+    g_ipc_maps.push_back({hd, device, (char*)p});
+    *out = (char*)p;
+    return cudaSuccess;
 }
 
 cudaError_t pool_alloc(sdpb_handle* h, void** p, size_t bytes) {
@@ -474,6 +537,8 @@ bool staged_ok(const sdpb_handle* h, int t) {
     return h->m.cost_kind == SDPB_COST_BACKORDER && h->m.lead_time >= 1 && smem <= 200 * 1024;
 }
 
+double count_evals_virtual(const sdpb_handle* h, int t);
+
 // Solve [lo, hi) of the real grid (or of the virtual grid when DEDUP) with the best kernel allowed.
 template <bool DEDUP>
 int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* Qt, long long lo, long long hi,
@@ -526,6 +591,18 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
         return launch_cash_row(h->m, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi, h->stream);
     }
     if (h->stats.kernel_used == 0) h->stats.kernel_used = SDPB_KERNEL_GENERIC;
+    {   // bi_generic evaluates the lambdas as written: its fp64 count per evaluation is MEASURED (ncu DADD + DMUL thread
+        // instructions, profiles/r02_fp64_audit.md), not derived; kinds that were not measured report nothing
+        double per_eval = 0.0;
+        switch (h->m.cost_kind) {
+        case SDPB_COST_BACKORDER: per_eval = 8.4; break;
+        case SDPB_COST_CASH_DEPOSIT: per_eval = 18.4; break;
+        case SDPB_COST_CASH_OVERDRAFT: per_eval = 11.5; break;
+        case SDPB_COST_STAFF: per_eval = 7.4; break;
+        default: break;
+        }
+        h->stats.fp64_ops += per_eval * (DEDUP ? count_evals_virtual(h, t) : count_evals_period(h, t));
+    }
     return dispatch_generic_d<DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
 }
 
@@ -635,6 +712,10 @@ int solve_period(sdpb_handle* h, int t);
 // the peers' rows (a group driven by one host thread enqueues every shard's pushes first, then every shard's wait).
 int enqueue_period_exchange_wait(sdpb_handle* h) {
     PeerLink& P = h->peer;
+    if (P.by_events) {
+        for (int r : P.recv_from) CU(cudaStreamWaitEvent(h->stream, P.peer_handles[r]->peer.ev_pushed, 0));
+        return SDPB_OK;
+    }
     if (!P.recv_from.empty()) {
         peer_wait<<<1, kMaxPeers, 0, h->stream>>>(reinterpret_cast<unsigned*>(h->slab), P.d_from, (int)P.recv_from.size(),
                                                   P.epoch, 20ull * 1000000000ull);
@@ -658,7 +739,9 @@ int enqueue_period_sharded(sdpb_handle* h, int t, bool wait_now) {
             char* dst = P.mapped[sd.rank] + pi.v_off0 + (size_t)(t - 1) * pi.v_stride + (size_t)(sd.a - pi.vlo) * sizeof(double);
             CU(cudaMemcpyAsync(dst, h->dV[t - 1] + sd.a, (size_t)(sd.b - sd.a) * sizeof(double), cudaMemcpyDefault, h->stream));
         }
-        if (!P.sends.empty()) {
+        if (P.by_events) {
+            CU(cudaEventRecord(P.ev_pushed, h->stream));
+        } else if (!P.sends.empty()) {
             peer_signal<<<1, kMaxPeers, 0, h->stream>>>(P.d_targets, (int)P.sends.size(), P.epoch);
             CU(cudaGetLastError());
         }
@@ -678,7 +761,7 @@ int enqueue_period_sharded(sdpb_handle* h, int t, bool wait_now) {
 // After the stream has drained: did a wait give up?  Fill the per-period profile.
 int finish_sharded(sdpb_handle* h) {
     unsigned errw = 0;
-    CU(cudaMemcpy(&errw, h->slab + kMaxPeers * sizeof(unsigned), sizeof errw, cudaMemcpyDeviceToHost));
+    if (!h->peer.by_events) CU(cudaMemcpy(&errw, h->slab + kMaxPeers * sizeof(unsigned), sizeof errw, cudaMemcpyDeviceToHost));
     if (errw) {
         h->err = "shard " + std::to_string(errw - 1) + " did not deliver its rows of V_t within 20 s";
         return SDPB_ERR_PEER;
@@ -740,9 +823,23 @@ int solve_period(sdpb_handle* h, int t) {
     }
     if (rc == SDPB_ERR_STATE && h->opt.kernel != SDPB_KERNEL_GENERIC && !plain && !term_T) {  // integer cash models
         rc = SDPB_ERR_STATE;
-        if (h->opt.kernel != SDPB_KERNEL_CASH_INT)  // (as a request: skip the diagonal-window variant)
+        if (h->opt.kernel != SDPB_KERNEL_CASH_INT && h->cash.available && t < m.T && h->cash.period[t - 1].ok && h->hi > h->lo) {
+            // (as a request, SDPB_KERNEL_CASH_INT skips the diagonal-window variant)
+            // scratch for the action slices: one (value, action) entry per slice and state of the shard
+            const int parts = cash_diag_parts(m, h->dm, h->cash.period[t - 1], h->lo, h->hi, h->sm_count);
+            const size_t need = parts > 1 ? (size_t)parts * (size_t)(h->hi - h->lo) : 0;
+            if (need > h->cash.slice_cap) {
+                void* p = nullptr;
+                CU(dev_alloc(h, &p, need * sizeof(double)));
+                h->cash.slice_v = (double*)p;
+                CU(dev_alloc(h, &p, need * sizeof(int)));
+                h->cash.slice_a = (int*)p;
+                h->cash.slice_cap = need;  // (an earlier, smaller scratch stays in dev_allocs until the handle goes)
+            }
             rc = launch_cash_diag(h->cash, m, h->dm, t, D, h->pmf_off[t - 1], Vn, h->dV[t - 1], h->dQ[t - 1], h->lo,
-                                  h->hi, h->stream, &h->stats.fp64_ops, count_evals_period(h, t));
+                                  h->hi, h->stream, &h->stats.fp64_ops, count_evals_period(h, t), h->sm_count);
+            if (rc == SDPB_OK && parts > 1) h->stats.launches++;  // merge_action_slices
+        }
         if (rc == SDPB_OK) h->stats.kernel_used = SDPB_KERNEL_CASH_DIAG;
         else if (rc == SDPB_ERR_STATE) {
             rc = launch_cash(h->cash, m, h->dm, t, D, h->pmf_off[t - 1], Vn, h->dV[t - 1], h->dQ[t - 1], h->lo, h->hi,
@@ -781,9 +878,9 @@ void sdpb_destroy(sdpb_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);  // (peers may still be reading flags this stream raises)
     if (h->stream) for (void* p : h->dev_allocs) cudaFreeAsync(p, h->stream);
     free_tiled(h->tiled);
-    for (size_t r = 0; r < h->peer.mapped.size(); r++)
-        if (h->peer.ipc_opened[r] && h->peer.mapped[r]) cudaIpcCloseMemHandle(h->peer.mapped[r]);
-    if (h->slab) cudaFree(h->slab);
+    // (peers' slabs mapped through CUDA IPC stay mapped: ipc_map caches them for the next handle)
+    if (h->slab) slab_release(h->device, h->slab, h->slab_bytes);
+    if (h->peer.ev_pushed) cudaEventDestroy(h->peer.ev_pushed);
     for (cudaEvent_t e : h->prof_ev) if (e) cudaEventDestroy(e);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1082,12 +1179,10 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     char* qbase = nullptr;
     if (h->opt.shard_count > 1) {
         // one plain cudaMalloc allocation: [header: peer flags][V tables][Q tables]
-        h->slab_bytes = kSlabHeader + (size_t)n_vtabs * v_slot + (size_t)T * q_slot;
-        if (cudaMalloc((void**)&h->slab, h->slab_bytes) != cudaSuccess) {
-            cudaGetLastError();
-            return fail_create(h, SDPB_ERR_NOMEM, "allocation of the shard's tables failed");
-        }
-        h->device_bytes += h->slab_bytes;
+        const size_t need = kSlabHeader + (size_t)n_vtabs * v_slot + (size_t)T * q_slot;
+        h->slab = slab_acquire(dev, need, &h->slab_bytes);
+        if (!h->slab) return fail_create(h, SDPB_ERR_NOMEM, "allocation of the shard's tables failed");
+        h->device_bytes += need;
         if (cudaMemsetAsync(h->slab, 0, kSlabHeader, h->stream) != cudaSuccess)
             return fail_create(h, SDPB_ERR_CUDA, "cudaMemset of the peer flags failed");
         vbase = h->slab + kSlabHeader;
@@ -1288,6 +1383,10 @@ int sdpb_solve_async(sdpb_handle* h) {
         if (!h->peer.attached) {
             h->err = "a sharded handle solves with its peers: connect them first (sdpb_peer_export / sdpb_peer_attach, or "
                      "sdpb_group_create), or step it with sdpb_solve_period_async and exchange V_t yourself";
+            return SDPB_ERR_STATE;
+        }
+        if (h->peer.by_events) {
+            h->err = "the shards of one process are solved together: sdpb_group_solve";
             return SDPB_ERR_STATE;
         }
         CU(cudaSetDevice(h->device));
@@ -1717,6 +1816,8 @@ int sdpb_peer_export(sdpb_handle* h, void* blob) {
     pi.rlo = rlo; pi.rhi = rhi; pi.vlo = h->vlo; pi.vhi = h->vhi;
     pi.v_off0 = h->v_off0; pi.v_stride = h->v_stride; pi.flags_off = 0;
     pi.model_hash = model_hash(h);
+    pi.handle = (uint64_t)(uintptr_t)h;
+    if (cudaDeviceGetPCIBusId(pi.pci, (int)sizeof pi.pci, h->device) != cudaSuccess) { cudaGetLastError(); pi.pci[0] = 0; }
     CU(cudaIpcGetMemHandle(&pi.ipc, h->slab));
     std::memset(blob, 0, SDPB_PEER_BLOB_BYTES);
     std::memcpy(blob, &pi, sizeof pi);
@@ -1744,6 +1845,26 @@ int sdpb_peer_attach(sdpb_handle* h, const void* blobs, int n_blobs) {
             return SDPB_ERR_ARG;
         }
     }
+    // all shards in this process (a group), or every shard in its own process on its own GPU
+    int same_pid = 0;
+    for (int r = 0; r < world; r++) same_pid += P.info[r].pid == (int64_t)getpid();
+    if (same_pid != world && same_pid != 1) { h->err = "shards must either all live in one process or each in its own"; return SDPB_ERR_PEER; }
+    P.by_events = same_pid == world;
+    if (!P.by_events) {
+        // The receivers spin on flag words the senders store: a waiter and the kernel it waits for must never share a
+        // GPU (nothing guarantees that two processes' kernels run at the same time; the context switch can time out).
+        for (int r = 0; r < world; r++)
+            for (int q = r + 1; q < world; q++)
+                if (P.info[r].pci[0] && std::strncmp(P.info[r].pci, P.info[q].pci, sizeof P.info[r].pci) == 0) {
+                    h->err = "shards " + std::to_string(r) + " and " + std::to_string(q) + " are in different processes on the "
+                             "same GPU (" + P.info[r].pci + "): one process per GPU, or all shards in one process (sdpb_group_create)";
+                    return SDPB_ERR_PEER;
+                }
+    } else {
+        P.peer_handles.assign(world, nullptr);
+        for (int r = 0; r < world; r++) P.peer_handles[r] = reinterpret_cast<sdpb_handle*>((uintptr_t)P.info[r].handle);
+        CU(cudaEventCreateWithFlags(&P.ev_pushed, cudaEventDisableTiming));
+    }
     for (int r = 0; r < world; r++) {
         const PeerInfo& pi = P.info[r];
         if (r == rank) { P.mapped[r] = h->slab; continue; }
@@ -1765,14 +1886,14 @@ int sdpb_peer_attach(sdpb_handle* h, const void* blobs, int n_blobs) {
             }
             P.mapped[r] = reinterpret_cast<char*>((uintptr_t)pi.base);
         } else {
-            void* p = nullptr;
-            const cudaError_t e = cudaIpcOpenMemHandle(&p, pi.ipc, cudaIpcMemLazyEnablePeerAccess);
+            char* p = nullptr;
+            const cudaError_t e = ipc_map(pi.ipc, h->device, &p);
             if (e != cudaSuccess) {
                 cudaGetLastError();
                 h->err = std::string("cudaIpcOpenMemHandle (shard ") + std::to_string(r) + "): " + cudaGetErrorString(e);
                 return SDPB_ERR_PEER;
             }
-            P.mapped[r] = (char*)p;
+            P.mapped[r] = p;
             P.ipc_opened[r] = 1;
         }
     }
@@ -2065,6 +2186,17 @@ int sdpb_trim_pool(int device) {
     if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return SDPB_ERR_NO_DEVICE;
     if (device < 0 || device >= 64) return SDPB_ERR_ARG;
     std::lock_guard<std::mutex> lk(g_pool_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    for (const Slab& sl : g_slabs[device]) cudaFree(sl.p);
+    g_slabs[device].clear();
+    for (size_t i = 0; i < g_ipc_maps.size();) {
+        if (g_ipc_maps[i].device == device) { cudaIpcCloseMemHandle(g_ipc_maps[i].p); g_ipc_maps.erase(g_ipc_maps.begin() + (long)i); }
+        else i++;
+    }
+    cudaSetDevice(cur);
+    cudaGetLastError();
     if (g_pools[device] && cudaMemPoolTrimTo(g_pools[device], 0) != cudaSuccess) { cudaGetLastError(); return SDPB_ERR_CUDA; }
     return SDPB_OK;
 }

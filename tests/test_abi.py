@@ -105,3 +105,69 @@ def test_getpmf_matches_survey_shapes(S):
     # UniformInt branch (GetPmf.java:97-111)
     r = S.GetPmf([S.UniformIntDist(2, 5)] * 2, 0.99, 1).getpmf()
     assert np.array_equal(r[1][:, 0], [2, 3, 4, 5]) and np.all(r[1][:, 1] == 0.25)
+
+
+# ---- struct layouts: compiler == committed table == ctypes binding == Java StructLayouts -------------------------
+def _layout_from_compiler(tmp_path):
+    exe = tmp_path / "print_layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "print_layout.c"),
+                    "-o", str(exe)], check=True)
+    return subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+
+
+def _parse_layout(text):
+    out = {}
+    for line in text.splitlines():
+        if line.startswith("#") or not line.strip():
+            continue
+        name, off, size = line.split()
+        out[name] = (int(off), int(size))
+    return out
+
+
+def test_layout_table_is_current(tmp_path):
+    """java/LAYOUT.txt is what the C compiler produces from include/sdpb200.h today, and it lists EVERY field."""
+    now = _layout_from_compiler(tmp_path)
+    committed = open(os.path.join(ROOT, "java", "LAYOUT.txt")).read()
+    assert _parse_layout(now) == _parse_layout(committed), "regenerate java/LAYOUT.txt with tools/print_layout.c"
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for struct in ("sdpb_model", "sdpb_options", "sdpb_grid", "sdpb_stats"):
+        body = re.search(r"typedef struct " + struct + r" \{(.*?)\} " + struct + ";", src, flags=re.S).group(1)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                fields.append(re.findall(r"[A-Za-z_][A-Za-z_0-9]*", part)[-1])
+        listed = [k.split(".")[1] for k in _parse_layout(committed) if k.startswith(struct + ".") and not k.endswith(".sizeof")]
+        assert listed == fields, struct
+
+
+def test_ctypes_binding_matches_layout_table(S):
+    lay = _parse_layout(open(os.path.join(ROOT, "java", "LAYOUT.txt")).read())
+    for cname, cls in (("sdpb_model", S.abi.SdpbModel), ("sdpb_options", S.abi.SdpbOptions),
+                       ("sdpb_grid", S.abi.SdpbGrid), ("sdpb_stats", S.abi.SdpbStats)):
+        assert lay[cname + ".sizeof"][0] == C.sizeof(cls)
+        for fname, _ in cls._fields_:
+            f = getattr(cls, fname)
+            assert lay[f"{cname}.{fname}"] == (f.offset, f.size), (cname, fname)
+
+
+def test_java_struct_layouts_match_layout_table():
+    """The Java binding cannot be compiled here (no JDK), but its StructLayouts can be read: field order, names and
+    value layouts of SdpB200.MODEL / OPTIONS / GRID must give exactly the offsets of java/LAYOUT.txt under the C
+    alignment rules Panama applies (natural alignment, no implicit padding -- so the C struct must need none)."""
+    lay = _parse_layout(open(os.path.join(ROOT, "java", "LAYOUT.txt")).read())
+    src = open(os.path.join(ROOT, "java", "sdp", "b200", "SdpB200.java")).read()
+    sizes = {"JAVA_INT": 4, "JAVA_DOUBLE": 8, "JAVA_LONG": 8, "ADDRESS": 8}
+    for jname, cname in (("MODEL", "sdpb_model"), ("OPTIONS", "sdpb_options"), ("GRID", "sdpb_grid")):
+        body = re.search(r"StructLayout " + jname + r" = MemoryLayout\.structLayout\((.*?)\);", src, flags=re.S).group(1)
+        fields = re.findall(r"(JAVA_INT|JAVA_DOUBLE|JAVA_LONG|ADDRESS)\.withName\(\"([a-zA-Z_0-9]+)\"\)", body)
+        off = 0
+        for typ, name in fields:
+            assert off % sizes[typ] == 0, f"{jname}.{name}: Panama struct layouts have no implicit padding"
+            assert lay[f"{cname}.{name}"] == (off, sizes[typ]), (jname, name)
+            off += sizes[typ]
+        assert off == lay[cname + ".sizeof"][0], jname
+        assert len(fields) == sum(1 for k in lay if k.startswith(cname + ".")) - 1

@@ -461,8 +461,8 @@ def test_large_group_c5_on_one_gpu(S, oracle):
             assert prof.shape == (3, 3) and (prof[:, 0] > 0).all()
 
 
-def _ipc_worker(rank, world, case_name, kernel, q_in, q_out, out_dir):
-    """One process per shard, all on GPU 0: the torchrun layout, connected through CUDA IPC."""
+def _ipc_worker(rank, world, case_name, kernel, q_in, q_out, out_dir, same_gpu=False):
+    """One process per shard, shard r on GPU r: the torchrun layout, connected through CUDA IPC."""
     import os
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -473,9 +473,18 @@ def _ipc_worker(rank, world, case_name, kernel, q_in, q_out, out_dir):
     import cases as cs
     import sdpb200 as S_
     spec, _ = getattr(cs, case_name)()
-    s = S_.Solver(spec, device=0, shard_rank=rank, shard_count=world, kernel=kernel)
+    s = S_.Solver(spec, device=0 if same_gpu else rank, shard_rank=rank, shard_count=world, kernel=kernel)
     q_out.put((rank, s.peer_export()))
     blobs = q_in.get()
+    if same_gpu:
+        try:
+            s.peer_attach(blobs)
+            q_out.put((rank, b"attached"))
+        except S_.SdpbError as e:
+            q_out.put((rank, b"refused" if e.code == S_.abi.SDPB_ERR_PEER else b"other"))
+        q_in.get()
+        s.close()
+        return
     s.peer_attach(blobs)
     for _ in range(2):
         s.solve()
@@ -492,8 +501,12 @@ def _ipc_worker(rank, world, case_name, kernel, q_in, q_out, out_dir):
 @pytest.mark.parametrize("case_name,world,kernel", [("case_B2_small", 3, 0), ("case_C_int", 2, 0), ("case_A_small", 2, 0)])
 def test_ipc_shards_in_separate_processes(case_name, world, kernel, S, oracle, tmp_path):
     """sdpb_peer_export / sdpb_peer_attach across PROCESSES (cudaIpcOpenMemHandle), the layout bench.py runs under
-    torchrun -- here with every process on GPU 0, so the flags and pushes cross process boundaries but not NVLink."""
+    torchrun: one process per GPU.  Needs as many GPUs as shards (processes that spin on each other's flags must not
+    share a GPU); on a one-GPU box the same path is exercised by bench.py --gpus N (verified_vs_unsharded)."""
     import multiprocessing as mp
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     ctx = mp.get_context("spawn")
     q_out = ctx.Queue()
     q_ins = [ctx.Queue() for _ in range(world)]
@@ -684,6 +697,33 @@ def test_reference_style_driver_clsp_main(S, oracle):
     rows, iv, _ = oracle.topdown(spec, [[1.0]])
     assert finalValue == iv[0] and inventory.getAction(initialState) == rows[0][-2]
     assert np.array_equal(inventory.getOptTable(), rows[:, :-1])
+
+
+def test_processes_sharing_a_gpu_are_refused(S, tmp_path):
+    """Two PROCESSES on one GPU would have to spin on each other's flags from kernels that are not guaranteed to run
+    at the same time: sdpb_peer_attach refuses (SDPB_ERR_PEER) before anything is launched."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q_out = ctx.Queue()
+    q_ins = [ctx.Queue() for _ in range(2)]
+    procs = [ctx.Process(target=_ipc_worker, args=(r, 2, "case_A_small", 0, q_ins[r], q_out, str(tmp_path), True))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        blobs = dict(q_out.get(timeout=180) for _ in range(2))
+        for qi in q_ins:
+            qi.put([blobs[r] for r in range(2)])
+        answers = [q_out.get(timeout=180)[1] for _ in range(2)]
+        for qi in q_ins:
+            qi.put("bye")
+        for p in procs:
+            p.join(timeout=60)
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+    assert answers == [b"refused", b"refused"]
 
 
 def test_unattached_shard_refuses_to_solve(S):
