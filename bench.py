@@ -34,7 +34,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 REF_F = {"c1": 20, "c2": 20, "c3": 41, "c4": 20, "c5": 20}  # fp64 ops per evaluation as written
 KERNEL_NAMES = {1: "bi_generic", 2: "bi_inv_tiled", 3: "bi_backorder_staged", 4: "bi_cash_int", 5: "bi_inv_tiled2",
                 6: "bi_lead_slab", 7: "bi_lead_col", 8: "bi_cash_diag", 9: "bi_lead_q2", 10: "bi_two_product_row",
-                11: "bi_inv_fused", 12: "bi_cash_row", 13: "bi_overdraft_row"}
+                11: "bi_inv_fused", 12: "bi_cash_row", 13: "bi_cash_tail"}
 METRIC = "state-action-demand evaluations/s (fp64), full-horizon SDP solve"
 UNIT = "evals/s"
 INIT = {"c1": [[0.0]], "c2": [[0.0]], "c3": [[0.0, 100.0]], "c4": [[0.0, 0.0, 0.0]], "c5": [[0.0]]}

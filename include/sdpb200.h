@@ -225,6 +225,9 @@ typedef enum sdpb_kernel_choice {
                                          of an (action, demand) pair across a row of cash levels (integer prices) */
     SDPB_KERNEL_CASH_ROW = 12,/* reported only: cash-constraint kind on any cash grid; a CTA is one inventory level x 128
                                  cash levels and shares the cash-independent terms of each (action, demand) */
+    SDPB_KERNEL_CASH_TAIL = 13,/* reported only: cash-constraint and overdraft kinds on any rounding cash grid; row-shared terms as
+                                 SDPB_KERNEL_CASH_ROW, with the cash clamp applied to the rounded integer (as a request,
+                                 SDPB_KERNEL_CASH_ROW skips it) */
     SDPB_KERNEL_FUSED = 11,   /* the whole horizon of a small 1-D inventory model in one cooperative launch (one CTA
                                  per SM, grid-wide barrier between periods); sdpb_solve / sdpb_solve_async only;
                                  AUTO picks it when the grid has at most 64 states per SM */

@@ -65,11 +65,18 @@ __device__ __forceinline__ long long jround(double x) {
     return (long long)r + (diff >= 0.5 ? 1ll : 0ll);
 }
 
-// The same for |x| < 2^31 (DevModel::small): floor through F2I.S32 instead of the 64-bit conversion sequence.
+// The same for |x| < 2^31 (DevModel::small), without a single int<->double conversion instruction (F2I.F64 / I2F.F64
+// issue at a fraction of the DADD rate; two of them per evaluation were the largest item of the cash kernels' tail).
+// x + 1.5*2^52 is x rounded to the nearest integer (ties to even) with that integer sitting in the low mantissa bits:
+// n = rint(x) comes back as a double by subtracting the constant and as an int by reading the low word, both exactly.
+// Math.round rounds halves UP: it differs from rint only when x - n is exactly +0.5 (an exact subtraction), e.g.
+// x = 2.5 -> n = 2 -> 3, x = -2.5 -> n = -2 -> -2, x = 3.5 -> n = 4 (x - n = -0.5) -> 4.
 __device__ __forceinline__ int jround32(double x) {
-    const int fl = __double2int_rd(x);
-    const double diff = x - (double)fl;
-    return fl + (diff >= 0.5 ? 1 : 0);
+    const double magic = 6755399441055744.0;  // 2^52 + 2^51
+    const double t = __dadd_rn(x, magic);
+    const double n = __dadd_rn(t, -magic);
+    const double diff = __dadd_rn(x, -n);
+    return __double2loint(t) + (diff == 0.5 ? 1 : 0);
 }
 
 // Java `long / long` (truncation toward zero) by the run-time constant q_idiv.  For q_idiv < 2^15 and

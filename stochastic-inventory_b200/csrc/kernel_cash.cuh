@@ -698,6 +698,216 @@ bi_cash_row(const __grid_constant__ DevModel M, const int t, const int D, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// bi_cash_tail -- the row-shared kernel again, for the cash-constraint AND the overdraft lambdas
+// (CashConstraint.java:95-133; CashOverdraft.java:72-118; CashOverdraftLimit.java:62-99; CashOverdraftTesting.java:78-120), with the per-lane tail cut to what the reference's
+// arithmetic strictly needs.  ncu on bi_cash_row / bi_generic<OVERDRAFT> (profiles/r02_ncu_cash_row.md): 57 and 97
+// warp instructions per evaluation, of which 21 and 20 on the fp64 pipe (each takes two dispatch slots); the rest is
+// the clamp / round / convert / index sequence and reloads of model constants.  Here:
+//   * the cash clamp moves behind the rounding: Math.round(x * q) is monotone, so
+//     round(clamp(w', lo, hi) * q) == clamp(round(w' * q), round(lo * q), round(hi * q)) -- two integer min/max
+//     instead of two fp64 compares and four selects (the host checks |w' * q| < 2^30 for every reachable w');
+//   * the grid index needs no second clamp (the integer clamp already lands on the cash axis);
+//   * `inc += salvage term` is skipped outside the last period (the term is +0.0 and inc is never -0.0: revenue
+//     >= +0.0 for a non-negative price), the bankruptcy penalty when its rate is 0 (it would add -0.0);
+//   * model constants live in registers, the demand loop is unrolled by two.
+// Same operations on the same operands in the same order as immediate<> / successor32<> otherwise: bit-identical
+// to bi_generic (tests: whole grid, both kinds, fractional and integer cash grids, gamma < 1, fuzz).
+struct CashTailEntry {  // three 16-byte words: (rev, hold) (sal, p) (pg, row | pad)
+    double rev, hold, sal, p, pg;
+    int row, pad;
+};
+static_assert(sizeof(CashTailEntry) == 48, "three LDS.128 per entry");
+
+// MODE: 0 = a period with a successor and no salvage term (t < T), 1 = period T without a successor, 2 = period T
+// with a boundary table.  PEN: the bankruptcy penalty of CashConstraint.java:116-119 has a non-zero rate.
+// DIV: the quantiser divides the rounded integer by q_div in long arithmetic (CashOverdraft.java:116), by multiply and
+// shift (the host checks that every clamped integer is inside the exact range of the magic constant).
+template <int KIND, int MODE, bool PEN, bool DIV>
+__global__ void __launch_bounds__(128)
+bi_cash_tail(const __grid_constant__ DevModel M, const int t, const int D, const int pmf_off,
+             const double* __restrict__ Vn, double* __restrict__ Vt, int* __restrict__ Qt,
+             const long long lo, const long long hi, const long long row0, const int segs, const int kk_lo_, const int kk_hi_) {
+    constexpr bool LAST = MODE != 0, NEXT = MODE != 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CashTailEntry* TB = reinterpret_cast<CashTailEntry*>(smem_raw);
+    const int seg = (int)(blockIdx.x % segs);
+    const long long ixl = row0 + blockIdx.x / segs;
+    const int iw = min(seg * 128 + (int)threadIdx.x, M.nW - 1);
+    const long long idx = ixl * M.nW + iw;
+    const bool valid = seg * 128 + (int)threadIdx.x < M.nW && idx >= lo && idx < hi;
+    const StateCtx S = decode_state<KIND>(M, t, idx);
+    const StateCtx Stop = decode_state<KIND>(M, t, ixl * M.nW + min(seg * 128 + 127, M.nW - 1));  // longest action list
+    const int nA_cta = Stop.nA;
+    const double2* __restrict__ rec = M.pmf_rec + 2 * (size_t)pmf_off;
+    // constants of the tail, in registers
+    const double q_mul = M.q_mul, pen = M.pen, ovh = S.ovh;
+    const int kk_lo = kk_lo_, kk_hi = kk_hi_;
+    const unsigned q_magic_lo = (unsigned)M.q_magic;  // < 2^32 for q_div >= 2^15 is excluded by the plan: magic = ceil(2^47 / d)
+    const unsigned long long q_magic = M.q_magic;
+    const bool is_min = M.is_min != 0;
+    (void)q_magic_lo;
+    const unsigned tb_s = (unsigned)__cvta_generic_to_shared(TB);
+
+    double best = is_min ? DBL_MAX : -DBL_MAX;
+    int besti = kNoAction;
+    for (int i = 0; i < nA_cta; i++) {
+        const ActionCtx A = prep_action<KIND>(M, S, i);  // per lane: the deposit / interest terms depend on w
+        __syncthreads();  // the previous action's table is no longer read
+        for (int j = threadIdx.x; j < D; j += 128) {
+            const double2 dp = __ldg(rec + 2 * j), gi = __ldg(rec + 2 * j + 1);
+            const double d = dp.x;
+            const double lvl = A.stock - d;                       // stock = x + a: the same for every lane
+            const double revenue = S.price * jmin(A.stock, d);
+            CashTailEntry e;
+            e.rev = KIND == SDPB_COST_CASH_DEPOSIT ? M.one_minus_rho * revenue : revenue;
+            e.hold = KIND != SDPB_COST_CASH_OVERDRAFT ? M.h * jmax0(lvl) : 0.0;
+            e.sal = (LAST && KIND != SDPB_COST_CASH_OD_TESTING) ? M.salvage * jmax0(lvl) : 0.0;
+            e.p = dp.y;
+            e.pg = gi.x;
+            int il = A.iy - __double2loint(gi.y);
+            if (S.lost) il = max(il, M.i_zero);
+            il = min(il, M.nI - 1);
+            il = max(il, 0);
+            e.row = il * (int)S.strideX - (int)M.kmin;  // + cash index k = flattened successor
+            e.pad = 0;
+            TB[j] = e;
+        }
+        __syncthreads();
+        if (!valid || i >= S.nA) continue;
+        const double initCash = A.initCash;
+        double lane_term = KIND == SDPB_COST_CASH_DEPOSIT ? A.deposite : A.before_minus_interest;
+        if (KIND == SDPB_COST_CASH_OD_LIMIT) lane_term = (S.w - A.fixedCost) - A.variableCost;  // CashOverdraftLimit.java:73
+        const double r2 = M.r2, dr = M.dr, fixedCost = A.fixedCost, variableCost = A.variableCost;
+        double acc = 0.0;
+        unsigned ea = tb_s;
+#pragma unroll 4
+        for (int j = 0; j < D; j++, ea += (unsigned)sizeof(CashTailEntry)) {
+            const double2 e0 = lds_double2(ea);          // (rev, hold)
+            const double2 e1 = lds_double2(ea + 16u);    // (sal, p)
+            const double2 e2 = lds_double2(ea + 32u);    // (pg, row in the low word)
+            double inc, after_t = 0.0;
+            if (KIND == SDPB_COST_CASH_DEPOSIT) {
+                inc = (((e0.x + lane_term) - e0.y) - ovh) - initCash;           // CashConstraint.java:110
+            } else if (KIND == SDPB_COST_CASH_OD_LIMIT) {                        // CashOverdraftLimit.java:70-86
+                const double before = (lane_term - e0.y) - ovh;
+                const double interest = r2 * jmax0(-before);
+                const double deposite = dr * jmax0(before);
+                const double bal = ((before - interest) + deposite) + e0.x;
+                inc = bal - initCash;
+            } else if (KIND == SDPB_COST_CASH_OD_TESTING) {                      // CashOverdraftTesting.java:85-99
+                const double before = (((initCash + e0.x) - fixedCost) - variableCost) - e0.y;
+                const double interest = r2 * jmax0(-before);
+                after_t = before - interest;
+                inc = after_t - initCash;
+            } else {
+                const double after = lane_term + e0.x;                           // CashOverdraft.java:99
+                inc = after - initCash;
+            }
+            if (LAST && KIND != SDPB_COST_CASH_OD_TESTING) inc += e1.x;          // (+0.0 otherwise: see above)
+            // end cash: w + c, except that CashOverdraftTesting.java:103-111 keeps the balance it computed
+            double nw = KIND == SDPB_COST_CASH_OD_TESTING ? after_t : initCash + inc;
+            if (PEN) {                                                           // CashConstraint.java:116-119
+                const double inc2 = inc + pen * nw;
+                const bool neg = nw < 0.0;
+                inc = neg ? inc2 : inc;
+                if (NEXT) nw = neg ? initCash + inc2 : nw;
+            }
+            acc += e1.y * inc;                                                   // CashRecursion.java:117
+            if (NEXT) {
+                int kk = jround32(nw * q_mul);                                   // Math.round(w' * q)
+                kk = min(max(kk, kk_lo), kk_hi);                                 // the cash clamp, after the rounding
+                int k = kk;
+                if (DIV) {                                                       // Java long division, truncating toward zero
+                    const unsigned a = (unsigned)(kk < 0 ? -kk : kk);
+                    const int q = (int)(((unsigned long long)a * q_magic) >> 47);
+                    k = kk < 0 ? -q : q;
+                }
+                acc += e2.x * __ldg(Vn + (__double2loint(e2.y) + k));           // CashRecursion.java:120
+            }
+        }
+        if (is_min ? (acc < best) : (acc > best)) { best = acc; besti = i; }
+    }
+    if (valid) {
+        Vt[idx] = best;
+        Qt[idx] = besti == kNoAction ? -1 : besti;
+    }
+}
+
+struct CashTailPlan { bool ok = false, div = false; int kk_lo = 0, kk_hi = 0; };
+
+// Both row-shared kinds, expectation recursion, no lead time, a rounding quantiser, 32-bit grid; every w' * q the
+// kernel can form must stay below 2^30 in magnitude (jround32's low-word read and the integer clamp).
+inline CashTailPlan plan_cash_tail(const sdpb_model& m, const DevModel& d, int D, const double* pmf_d, int n_pmf) {
+    CashTailPlan P;
+    if (!(m.cost_kind == SDPB_COST_CASH_DEPOSIT || m.cost_kind == SDPB_COST_CASH_OVERDRAFT ||
+          m.cost_kind == SDPB_COST_CASH_OD_LIMIT || m.cost_kind == SDPB_COST_CASH_OD_TESTING)) return P;
+    if (m.recursion != SDPB_REC_EXPECT || m.lead_time != 0 || d.small == 0 || m.quantiser == SDPB_Q_TRUNC) return P;
+    if ((size_t)D * sizeof(CashTailEntry) > 96 * 1024) return P;
+    if (m.cost_kind == SDPB_COST_CASH_DEPOSIT && !(1.0 - m.overhead_rate >= 0.0)) return P;
+    double price = std::fabs(m.price), v = std::fabs(m.vari_cost), ovh = std::fabs(m.overhead), dmax = 0;
+    for (int t = 0; t < m.T; t++) {
+        const double pt = m.price_t ? m.price_t[t] : m.price;
+        if (!(pt >= 0.0)) return P;  // revenue must never be -0.0 (see the kernel's header)
+        price = std::max(price, std::fabs(pt));
+        if (m.vari_cost_t) v = std::max(v, std::fabs(m.vari_cost_t[t]));
+        if (m.overhead_t) ovh = std::max(ovh, std::fabs(m.overhead_t[t]));
+    }
+    for (int j = 0; j < n_pmf; j++) dmax = std::max(dmax, std::fabs(pmf_d[j]));
+    const double stock = std::max(std::fabs(m.inv_min), std::fabs(m.inv_max)) + (double)m.max_order_idx * m.step;
+    const double cash = std::max(std::fabs(m.cash_min), std::fabs(m.cash_max));
+    const double rates = 1.0 + std::fabs(m.deposit_rate) + std::fabs(m.r0) + std::fabs(m.r2) + std::fabs(m.r3) + std::fabs(m.penalty_cost);
+    // |w'| <= (cash + costs) * (1 + rates) + revenue + salvage/holding terms, generously
+    const double bound = (cash + std::fabs(m.fixed_cost) + v * m.max_order_idx * m.step + ovh + std::fabs(m.od_limit) +
+                          std::fabs(m.interest_free)) * rates * rates +
+                         (price + std::fabs(m.salvage) + std::fabs(m.hold_cost)) * (stock + dmax) * rates;
+    if (!(bound * std::fabs(m.q_mul) < 1073741824.0)) return P;
+    auto hround = [](double x) { const double r = std::floor(x); return (long long)r + ((x - r) >= 0.5 ? 1 : 0); };
+    P.kk_lo = (int)hround(m.cash_min * m.q_mul);
+    P.kk_hi = (int)hround(m.cash_max * m.q_mul);
+    P.div = m.quantiser == SDPB_Q_LONGDIV && d.q_idiv != 1;
+    if (P.div) {  // the multiply-shift division is exact for |kk| < q_div * 2^16 with q_div < 2^15 (dev_model.cuh: jdiv32)
+        const long long lim = d.q_idiv << 16;
+        if (d.q_magic == 0 || std::llabs((long long)P.kk_lo) >= lim || std::llabs((long long)P.kk_hi) >= lim) return P;
+    }
+    P.ok = true;
+    return P;
+}
+
+inline int launch_cash_tail(const CashTailPlan& P, const sdpb_model& m, const DevModel& dm, int t, int D, int pmf_off,
+                            const double* Vn, double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream) {
+    if (hi <= lo) return SDPB_OK;
+    const int segs = (dm.nW + 127) / 128;
+    const long long row0 = lo / dm.nW, row1 = (hi - 1) / dm.nW;
+    const unsigned blocks = (unsigned)((row1 - row0 + 1) * segs);
+    const size_t smem = (size_t)D * sizeof(CashTailEntry);
+    cudaError_t e = cudaSuccess;
+#define SDPB_TAIL_LAUNCH(KD, MD, PN, DV)                                                                \
+    {                                                                                                   \
+        auto k = bi_cash_tail<KD, MD, PN, DV>;                                                          \
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) k<<<blocks, 128, smem, stream>>>(dm, t, D, pmf_off, Vn, Vt, Qt, lo, hi, row0, segs, P.kk_lo, P.kk_hi); \
+    }
+#define SDPB_TAIL_MODE(KD, PN, DV)                                                                      \
+    { if (mode == 0) SDPB_TAIL_LAUNCH(KD, 0, PN, DV) else if (mode == 1) SDPB_TAIL_LAUNCH(KD, 1, PN, DV) else SDPB_TAIL_LAUNCH(KD, 2, PN, DV) }
+    const int mode = t < m.T ? 0 : (Vn == nullptr ? 1 : 2);
+    if (m.cost_kind == SDPB_COST_CASH_DEPOSIT) {
+        const bool pn = m.penalty_cost != 0.0;
+        if (pn) { if (P.div) SDPB_TAIL_MODE(SDPB_COST_CASH_DEPOSIT, true, true) else SDPB_TAIL_MODE(SDPB_COST_CASH_DEPOSIT, true, false) }
+        else    { if (P.div) SDPB_TAIL_MODE(SDPB_COST_CASH_DEPOSIT, false, true) else SDPB_TAIL_MODE(SDPB_COST_CASH_DEPOSIT, false, false) }
+    } else if (m.cost_kind == SDPB_COST_CASH_OD_LIMIT) {
+        if (P.div) SDPB_TAIL_MODE(SDPB_COST_CASH_OD_LIMIT, false, true) else SDPB_TAIL_MODE(SDPB_COST_CASH_OD_LIMIT, false, false)
+    } else if (m.cost_kind == SDPB_COST_CASH_OD_TESTING) {
+        if (P.div) SDPB_TAIL_MODE(SDPB_COST_CASH_OD_TESTING, false, true) else SDPB_TAIL_MODE(SDPB_COST_CASH_OD_TESTING, false, false)
+    } else {
+        if (P.div) SDPB_TAIL_MODE(SDPB_COST_CASH_OVERDRAFT, false, true) else SDPB_TAIL_MODE(SDPB_COST_CASH_OVERDRAFT, false, false)
+    }
+#undef SDPB_TAIL_MODE
+#undef SDPB_TAIL_LAUNCH
+    if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+    return SDPB_OK;
+}
+
 // CASH_DEPOSIT kind without lead time on a grid whose indices fit 32 bits (DevModel::small).
 inline bool cash_row_ok(const sdpb_model& m, const DevModel& d, int D) {
     return m.cost_kind == SDPB_COST_CASH_DEPOSIT && m.lead_time == 0 && d.small != 0 &&

@@ -542,7 +542,15 @@ struct Q2Args {
     int n_chunks, tpx;        // chunks of 8 levels along preQ1; threads per inventory row
     int di_max, NRW;
     int parts;                // slices of the action range per CTA (1, 2 or 4): small grids cannot fill the GPU otherwise
+    // Multi-GPU: rows of this shard's block that a peer reads are stored into the peer's V_t as well, straight from the
+    // epilogue through peer-mapped memory (the pointers are biased like Vt: indexed by the absolute flattened index),
+    // so the hand-over needs no copy after the kernel -- the NVLink writes overlap the arithmetic of the other CTAs.
+    int n_peer;
+    double* peer_v[2];
+    long long peer_lo[2], peer_hi[2];
 };
+
+struct PeerStore { double* v; long long lo, hi; };
 
 constexpr int kQ2YT = 8, kQ2PF = 2, kQ2PAD = kQ2PF + 1;
 
@@ -682,6 +690,8 @@ bi_lead_q2(const __grid_constant__ DevModel M, const __grid_constant__ Q2Args a)
         if (l0 + k < nQ && idx >= a.lo && idx < a.hi) {
             a.Vt[idx] = best[k];
             a.Qt[idx] = arg[k] == kNoAction ? -1 : arg[k];
+            for (int p = 0; p < a.n_peer; p++)
+                if (idx >= a.peer_lo[p] && idx < a.peer_hi[p]) a.peer_v[p][idx] = best[k];
         }
     }
 }
@@ -710,8 +720,11 @@ inline Q2Plan plan_q2(const sdpb_model& m, const DevModel& d, int D, const int* 
 
 // VnT: scratch of nI*nQ*nQ doubles; filled here from Vn (stream order) unless this is the last period.
 // [row0, row1): inventory rows of V_{t+1} the range [lo, hi) can read (sdpb_shard_reads); only those are transposed.
+constexpr int kQ2MaxPeers = 2;
+
 inline int launch_q2(const Q2Plan& P, const DevModel& dm, int t, int D, int pmf_off, const double* Vn, double* VnT,
-                     double* Vt, int* Qt, long long lo, long long hi, int row0, int row1, cudaStream_t stream) {
+                     double* Vt, int* Qt, long long lo, long long hi, int row0, int row1, cudaStream_t stream,
+                     const PeerStore* peers = nullptr, int n_peers = 0) {
     if (hi <= lo) return SDPB_OK;
     const bool last = (Vn == nullptr), mn = dm.is_min != 0;  // period T without a terminal table
     if (!last) {
@@ -721,6 +734,12 @@ inline int launch_q2(const Q2Plan& P, const DevModel& dm, int t, int D, int pmf_
     Q2Args a;
     a.t = t; a.D = D; a.pmf_off = pmf_off; a.VnT = last ? nullptr : VnT; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
     a.n_chunks = P.n_chunks; a.tpx = P.tpx; a.di_max = P.di_max; a.NRW = P.NRW;
+    a.n_peer = 0;
+    for (int p = 0; p < kQ2MaxPeers; p++) { a.peer_v[p] = nullptr; a.peer_lo[p] = a.peer_hi[p] = 0; }
+    for (int p = 0; p < n_peers && p < kQ2MaxPeers; p++) {
+        a.peer_v[p] = peers[p].v; a.peer_lo[p] = peers[p].lo; a.peer_hi[p] = peers[p].hi;
+        a.n_peer = p + 1;
+    }
     const long long per_x = (long long)dm.nQ * dm.nQ;
     a.f_begin = (lo / per_x) * P.tpx;
     a.f_end = ((hi - 1) / per_x + 1) * P.tpx;

@@ -142,6 +142,7 @@ struct sdpb_handle {
     unsigned long long* dCounters = nullptr;  // [4] dense-grid artefacts seen by sdpb_reach
     double reach_cnt[3] = {0, 0, 0};
     PeerLink peer;
+    bool push_fused = false;   // the period's kernel already stored the peers' rows into their tables (bi_lead_q2)
     std::vector<cudaEvent_t> prof_ev;  // profile = 1: 4 events per period
     std::vector<double> prof_ms;       // [3 * T] of the last sharded solve
     std::string err;
@@ -554,8 +555,21 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
             int64_t rlo = 0, rhi = h->S;
             sdpb_shard_reads(h, &rlo, &rhi);
             const long long per_x = (long long)h->dm.nQ * h->dm.nQ;
+            // multi-GPU: the kernel's epilogue stores the rows its (at most two) neighbours read straight into their
+            // tables; enqueue_period_sharded then skips the copies
+            PeerStore ps[kQ2MaxPeers];
+            int nps = 0;
+            h->push_fused = false;
+            if (h->peer.attached && t > 1 && !h->peer.sends.empty() && h->peer.sends.size() <= (size_t)kQ2MaxPeers) {
+                for (const PeerSend& sd : h->peer.sends) {
+                    const PeerInfo& pi = h->peer.info[sd.rank];
+                    char* base = h->peer.mapped[sd.rank] + pi.v_off0 + (size_t)(t - 1) * pi.v_stride;
+                    ps[nps++] = PeerStore{reinterpret_cast<double*>(base) - pi.vlo, sd.a, sd.b};
+                }
+                h->push_fused = true;
+            }
             return launch_q2(qp, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, h->dVT, Vt, Qt, lo, hi,
-                             (int)(rlo / per_x), (int)(rhi / per_x), h->stream);
+                             (int)(rlo / per_x), (int)(rhi / per_x), h->stream, ps, nps);
         }
     }
     if (!plain && h->opt.kernel != SDPB_KERNEL_GENERIC && h->opt.kernel != SDPB_KERNEL_STAGED && h->m.lead_time >= 1 &&
@@ -582,6 +596,18 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
         // per evaluation: add, mul, add (+ mul, add when a continuation exists)
         h->stats.fp64_ops += (double)(hi - lo) * (plain ? 1 : h->m.max_order_idx + 1) * h->pmf_len[t - 1] * (last ? 3.0 : 5.0);
         return launch_staged<DEDUP>(h, t, Vn, Vt, Qt, lo, hi);
+    }
+    if (!DEDUP && h->opt.kernel != SDPB_KERNEL_GENERIC && h->opt.kernel != SDPB_KERNEL_CASH_ROW) {
+        // row-shared kernel with the minimal per-lane tail: cash-constraint and overdraft lambdas
+        const CashTailPlan tp = plan_cash_tail(h->m, h->dm, h->pmf_len[t - 1], h->pmf_d.data(), (int)h->pmf_d.size());
+        if (tp.ok) {
+            h->stats.kernel_used = SDPB_KERNEL_CASH_TAIL;
+            // DADD + DMUL per evaluation as counted by ncu (profiles/r02_fp64_audit.md)
+            const int kd = h->m.cost_kind;  // (overdraft-limit / -testing: a few more for the two interest products)
+            const double body = kd == SDPB_COST_CASH_DEPOSIT ? 4.0 : kd == SDPB_COST_CASH_OVERDRAFT ? 2.0 : kd == SDPB_COST_CASH_OD_LIMIT ? 9.0 : 7.0;
+            h->stats.fp64_ops += count_evals_period(h, t) * (last ? body + 3.0 : body + 9.0);
+            return launch_cash_tail(tp, h->m, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi, h->stream);
+        }
     }
     if (!DEDUP && h->opt.kernel != SDPB_KERNEL_GENERIC && cash_row_ok(h->m, h->dm, h->pmf_len[t - 1])) {
         h->stats.kernel_used = SDPB_KERNEL_CASH_ROW;
@@ -729,12 +755,13 @@ int enqueue_period_sharded(sdpb_handle* h, int t, bool wait_now) {
     const bool prof = !h->prof_ev.empty();
     cudaEvent_t* ev = prof ? h->prof_ev.data() + 4 * (size_t)(t - 1) : nullptr;
     if (prof) CU(cudaEventRecord(ev[0], h->stream));
+    h->push_fused = false;
     int rc = solve_period(h, t);
     if (rc != SDPB_OK) return rc;
     if (prof) CU(cudaEventRecord(ev[1], h->stream));
     if (t > 1) {  // V_1 is read by nobody
         P.epoch++;
-        for (const PeerSend& sd : P.sends) {
+        if (!h->push_fused) for (const PeerSend& sd : P.sends) {
             const PeerInfo& pi = P.info[sd.rank];
             char* dst = P.mapped[sd.rank] + pi.v_off0 + (size_t)(t - 1) * pi.v_stride + (size_t)(sd.a - pi.vlo) * sizeof(double);
             CU(cudaMemcpyAsync(dst, h->dV[t - 1] + sd.a, (size_t)(sd.b - sd.a) * sizeof(double), cudaMemcpyDefault, h->stream));

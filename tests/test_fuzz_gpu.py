@@ -71,6 +71,16 @@ def make_model(family, rng):
                                       r2=0.125, r3=1.5, od_limit=float(rng.integers(3, 30)),
                                       interest_free=float(rng.integers(0, 3)), max_order=int(rng.integers(1, 8)),
                                       quantiser=q[0], q_mul=q[1], q_div=q[2], gamma=float(rng.choice([1.0, 0.95])), **cash)
+    if family in ("DL", "DT"):
+        q = [(A.Q_LONGDIV, 10.0, 10.0), (A.Q_DIV, 4.0, 4.0), (A.Q_LONGDIV, 1.0, 1.0)][int(rng.integers(0, 3))]
+        kw = dict(price=_cost(rng, False) + 1, vari_cost=_cost(rng, False) + 0.5, fixed_cost=_cost(rng, False),
+                  hold_cost=_cost(rng, False), interest_rate=float(rng.choice([0.0, 0.125, 0.2])),
+                  max_order=int(rng.integers(1, 8)), quantiser=q[0], q_mul=q[1], q_div=q[2],
+                  gamma=float(rng.choice([1.0, 0.95])), **cash)
+        if family == "DL":
+            return S.cash_overdraft_limit_model(_pmf(rng, T, 6), salvage=_cost(rng, False), deposit_rate=float(rng.choice([0, 0.0625])),
+                                                overhead_t=[_cost(rng, False) for _ in range(T)], **kw)
+        return S.cash_overdraft_testing_model(_pmf(rng, T, 6), min_cash_required=-float(rng.integers(0, 10)), **kw)
     if family == "E":
         m = S.cash_leadtime_model(_pmf(rng, T, 5), price=_cost(rng, False) + 1, vari_cost=_cost(rng, False) + 0.5,
                                   salvage=_cost(rng, False), overhead_t=[_cost(rng, False) for _ in range(T)],
@@ -97,9 +107,11 @@ def make_model(family, rng):
     raise ValueError(family)
 
 
-FAMILIES = ["A", "B", "C", "Cint", "F", "Fint", "D", "E", "XR", "M2"]
+FAMILIES = ["A", "B", "C", "Cint", "F", "Fint", "D", "DL", "DT", "E", "XR", "M2"]
 KERNELS = {"A": (S.KERNEL_AUTO, S.KERNEL_GENERIC, S.KERNEL_TILED, S.KERNEL_TILED2, S.KERNEL_FUSED),
            "B": (S.KERNEL_AUTO, S.KERNEL_GENERIC, S.KERNEL_STAGED, S.KERNEL_LEAD_SLAB, S.KERNEL_LEAD_COL, S.KERNEL_LEAD_Q2),
+           "C": (S.KERNEL_AUTO, S.KERNEL_GENERIC, S.KERNEL_CASH_ROW),
+           "D": (S.KERNEL_AUTO, S.KERNEL_GENERIC, S.KERNEL_CASH_ROW),
            "Cint": (S.KERNEL_AUTO, S.KERNEL_GENERIC, S.KERNEL_CASH_INT),
            "Fint": (S.KERNEL_AUTO, S.KERNEL_GENERIC, S.KERNEL_CASH_INT)}
 

@@ -131,10 +131,12 @@ def test_integer_cash_kernel_is_used(S):
     for case in (cases.case_C_int, cases.case_C_int_K, cases.case_F_small):
         spec, _ = case()
         assert S.Solver(spec).solve().stats()["kernel_used"] == S.KERNEL_CASH_DIAG, spec.name
-    # fractional cash grids: the cash-constraint kind shares its cash-independent terms across a row of cash levels,
-    # the other kinds (whose balance depends on the demand through the cash level) stay on the generic kernel
-    for case, used in ((cases.case_C_small, S.KERNEL_CASH_ROW), (cases.case_C_rich, S.KERNEL_CASH_ROW),
-                       (cases.case_D_small, S.KERNEL_GENERIC)):
+    # fractional cash grids and the overdraft lambdas: the cash-independent terms are shared across a row of cash levels
+    # (bi_cash_tail); the survival recursion keeps the older row kernel, the remaining kinds the generic one
+    for case, used in ((cases.case_C_small, S.KERNEL_CASH_TAIL), (cases.case_C_rich, S.KERNEL_CASH_TAIL),
+                       (cases.case_D_small, S.KERNEL_CASH_TAIL), (cases.case_D_rich, S.KERNEL_CASH_TAIL),
+                       (cases.case_DL_small, S.KERNEL_CASH_TAIL), (cases.case_DT_small, S.KERNEL_CASH_TAIL),
+                       (cases.case_TP_small, S.KERNEL_GENERIC), (cases.case_E_small, S.KERNEL_GENERIC)):
         spec, _ = case()
         assert S.Solver(spec).solve().stats()["kernel_used"] == used, spec.name
 
@@ -153,11 +155,25 @@ def test_cash_row_kernel_shapes(S, oracle):
                               salvage=0.5, hold_cost=0.25, deposit_rate=0.01, max_order=12, inv_min=0, inv_max=20,
                               cash_min=-20, cash_max=150),
     ]
-    for spec in specs:
+    # the overdraft lambdas (CashOverdraft.java:72-118) on an integer grid (long division by 10), on a 0.1 grid, with a
+    # fixed cost / salvage / discount, and cash bounds that the clamp hits on both sides
+    specs += [
+        S.cash_overdraft_model(cases.pmf([6, 7, 5], 0.999), price=9, vari_cost=1, fixed_cost=4, salvage=1.5, overhead_t=[15, 18, 12],
+                               r0=0.03, r2=0.11, r3=1.7, od_limit=25, interest_free=6, max_order=13, inv_min=0, inv_max=19,
+                               cash_min=-45, cash_max=131, gamma=0.93),
+        S.cash_overdraft_model(cases.pmf([5, 6], 0.99), price=8, vari_cost=2, overhead_t=[10, 10], r0=0.01, r2=0.125, r3=2.0,
+                               od_limit=15, max_order=10, inv_min=0, inv_max=15, cash_min=-20.3, cash_max=37.9,
+                               quantiser=S.abi.Q_DIV, q_mul=10.0, q_div=10.0),
+    ]
+    for n, spec in enumerate(specs):
         Vo, Qo, evals, _ = oracle.dense(spec)
         s, V, Q = _solve_all(S, spec)
-        assert s.stats()["kernel_used"] == S.KERNEL_CASH_ROW and s.stats()["evals"] == evals, spec.name
-        assert np.array_equal(V, Vo) and np.array_equal(Q, Qo), spec.name
+        want = S.KERNEL_CASH_ROW if spec.recursion == S.REC_SURVIVAL else S.KERNEL_CASH_TAIL
+        assert s.stats()["kernel_used"] == want and s.stats()["evals"] == evals, (n, spec.name)
+        assert np.array_equal(V, Vo) and np.array_equal(Q, Qo), (n, spec.name)
+        if want == S.KERNEL_CASH_TAIL:   # the older row kernel still agrees where it applies (as a request)
+            r, Vr, Qr = _solve_all(S, spec, kernel=S.KERNEL_CASH_ROW)
+            assert np.array_equal(Vr, Vo) and np.array_equal(Qr, Qo), (n, spec.name)
         g, Vg, Qg = _solve_all(S, spec, kernel=S.KERNEL_GENERIC)
         assert g.stats()["kernel_used"] == S.KERNEL_GENERIC
         assert np.array_equal(Vg, Vo) and np.array_equal(Qg, Qo), spec.name
