@@ -514,10 +514,17 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
 
 // Optimum over the action slices of one state: slices in ascending order hold ascending actions, so a strict compare
 // keeps the first optimum (Recursion.java:146-157); a slice that held no feasible action of the state says kNoAction.
+// A peer shard's V tables as this shard addresses them: V_t[idx] of the peer is at base0 + (t-1)*stride + idx*8 (the
+// base is biased by the peer's window start), and the peer reads rows [lo, hi) of this shard's block.
+struct DevPeer { char* base0; unsigned long long stride; long long lo, hi; };
+
+// Multi-GPU: the merged values a peer reads are stored into the peer's table as well (peer-mapped memory), so the
+// cash models -- where every shard reads nearly every row: 7 peers at 8 GPUs -- need no copy after the kernel either.
 template <bool IS_MIN>
 __global__ void __launch_bounds__(256)
 merge_action_slices(const double* __restrict__ sv, const int* __restrict__ sa, int parts, long long n_local,
-                    double* __restrict__ Vt, int* __restrict__ Qt) {
+                    double* __restrict__ Vt, int* __restrict__ Qt, long long lo, const DevPeer* __restrict__ peers,
+                    int n_peers, int t) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_local) return;
     double best = IS_MIN ? DBL_MAX : -DBL_MAX;
@@ -529,6 +536,12 @@ merge_action_slices(const double* __restrict__ sv, const int* __restrict__ sa, i
     }
     Vt[i] = best;
     Qt[i] = arg == kNoAction ? -1 : arg;
+    const long long idx = lo + i;
+    for (int p = 0; p < n_peers; p++) {
+        const DevPeer pr = peers[p];
+        if (idx >= pr.lo && idx < pr.hi)
+            reinterpret_cast<double*>(pr.base0 + (unsigned long long)(t - 1) * pr.stride)[idx] = best;
+    }
 }
 
 // Slices of the action range for a launch over [lo, hi): up to 16, at least ~12 actions per slice.
@@ -547,7 +560,8 @@ inline int cash_diag_parts(const sdpb_model& m, const DevModel& dm, const CashPe
 
 inline int launch_cash_diag(const CashPlan& P, const sdpb_model& m, const DevModel& dm, int t, int D, int pmf_off,
                             const double* Vn, double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream,
-                            double* fp64_ops, double evals, int sm_count) {
+                            double* fp64_ops, double evals, int sm_count, const DevPeer* d_peers = nullptr, int n_peers = 0,
+                            bool* pushed = nullptr) {
     if (!P.available || t >= m.T || !P.period[t - 1].ok) return SDPB_ERR_STATE;
     if (hi <= lo) return SDPB_OK;
     const CashPeriod& cp = P.period[t - 1];
@@ -586,9 +600,10 @@ inline int launch_cash_diag(const CashPlan& P, const sdpb_model& m, const DevMod
     if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
     if (parts > 1) {
         const unsigned mb = (unsigned)((n_local + 255) / 256);
-        if (dm.is_min && !surv) merge_action_slices<true><<<mb, 256, 0, stream>>>(P.slice_v, P.slice_a, parts, n_local, Vt + lo, Qt + lo);
-        else merge_action_slices<false><<<mb, 256, 0, stream>>>(P.slice_v, P.slice_a, parts, n_local, Vt + lo, Qt + lo);
+        if (dm.is_min && !surv) merge_action_slices<true><<<mb, 256, 0, stream>>>(P.slice_v, P.slice_a, parts, n_local, Vt + lo, Qt + lo, lo, d_peers, n_peers, t);
+        else merge_action_slices<false><<<mb, 256, 0, stream>>>(P.slice_v, P.slice_a, parts, n_local, Vt + lo, Qt + lo, lo, d_peers, n_peers, t);
         if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+        if (pushed && n_peers > 0) *pushed = true;
     }
     if (fp64_ops) *fp64_ops += evals * (surv ? 2.0 : 3.0 + 2.0 / kDiagYT);
     return SDPB_OK;

@@ -62,6 +62,8 @@ struct TiledPlan {
     int n_chunks2 = 0;                // ceil(n_actions / RA) for bi_inv_tiled2
     int variant = 0;                  // 0 = choose by size, 1 = bi_inv_tiled only, 2 = bi_inv_tiled2 when possible
     int sm_count = 148;
+    int batch = 1;                    // instances solved side by side (sdpb_solve_batch): each gets 1/batch of the GPU,
+                                      // so the action range is split only as far as THAT share needs
     // cross-CTA merge scratch for action splitting (allocated lazily by the owner)
     double* part_v = nullptr;
     int* part_a = nullptr;
@@ -516,7 +518,7 @@ inline int launch_tiled(TiledPlan& P, const DevModel& dm, int t, int D, int pmf_
     if (n <= 0) return SDPB_OK;
     const bool last = (Vn == nullptr);  // period T without a terminal table (Recursion.java:140)
     const bool mn = dm.is_min != 0;
-    const long long target = 4LL * P.sm_count;  // about 4 CTAs per SM
+    const long long target = std::max(1LL, 4LL * P.sm_count / P.batch);  // about 4 CTAs per SM (of this instance's share)
     const double evals = (double)n * (dm.max_order_idx + 1) * D;
     TiledArgs a;
     a.t = t; a.D = D; a.pmf_off = pmf_off; a.Vn = Vn; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
@@ -532,7 +534,7 @@ inline int launch_tiled(TiledPlan& P, const DevModel& dm, int t, int D, int pmf_
         // enough CTAs for ~8 waves of 2 CTAs per SM: a grid of a few waves loses its last, partial one
         // (measured, C5: S = 1e6 32.9 -> 30.0 ms, S = 1e5 3.36 -> 3.17 ms; no change at 3e5 and 3e6)
         static const int env_waves = [] { const char* e = std::getenv("SDPB_T2_WAVES"); return e ? std::max(1, std::atoi(e)) : 0; }();
-        long long want = 16LL * P.sm_count;
+        long long want = std::max(1LL, 16LL * P.sm_count / P.batch);
         if (env_waves) want = env_waves * 2LL * P.sm_count;  // tuning knob, read once per process
         if (tiles2 < want) nsplit = (int)std::min<long long>(P.n_chunks2, (want + tiles2 - 1) / tiles2);
         const int cps = (P.n_chunks2 + nsplit - 1) / nsplit;

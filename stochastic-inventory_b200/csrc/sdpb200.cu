@@ -81,6 +81,7 @@ struct PeerLink {
     std::vector<char> ipc_opened;      // [world] mapped with cudaIpcOpenMemHandle (must be closed)
     std::vector<PeerSend> sends;
     std::vector<int> recv_from;
+    void* d_peers = nullptr;           // device array of DevPeer, one per entry of `sends` (kernels that push themselves)
     unsigned** d_targets = nullptr;    // device array: address of flags[my rank] in every peer I send to
     int* d_from = nullptr;             // device array: ranks I wait for
     unsigned epoch = 0;                // exchanges completed so far (identical on every shard)
@@ -863,8 +864,11 @@ int solve_period(sdpb_handle* h, int t) {
                 h->cash.slice_a = (int*)p;
                 h->cash.slice_cap = need;  // (an earlier, smaller scratch stays in dev_allocs until the handle goes)
             }
+            const bool push = h->peer.attached && t > 1 && !h->peer.sends.empty();
             rc = launch_cash_diag(h->cash, m, h->dm, t, D, h->pmf_off[t - 1], Vn, h->dV[t - 1], h->dQ[t - 1], h->lo,
-                                  h->hi, h->stream, &h->stats.fp64_ops, count_evals_period(h, t), h->sm_count);
+                                  h->hi, h->stream, &h->stats.fp64_ops, count_evals_period(h, t), h->sm_count,
+                                  push ? (const DevPeer*)h->peer.d_peers : nullptr, push ? (int)h->peer.sends.size() : 0,
+                                  &h->push_fused);
             if (rc == SDPB_OK && parts > 1) h->stats.launches++;  // merge_action_slices
         }
         if (rc == SDPB_OK) h->stats.kernel_used = SDPB_KERNEL_CASH_DIAG;
@@ -1942,6 +1946,16 @@ int sdpb_peer_attach(sdpb_handle* h, const void* blobs, int n_blobs) {
         if (d2 > c) { P.recv_from.push_back(r); P.bytes_in += (d2 - c) * 8; }
     }
     void* p = nullptr;
+    {
+        std::vector<DevPeer> dp;
+        for (const PeerSend& sd : P.sends) {
+            const PeerInfo& pi = P.info[sd.rank];
+            dp.push_back(DevPeer{P.mapped[sd.rank] + pi.v_off0 - (long long)pi.vlo * (long long)sizeof(double), pi.v_stride, sd.a, sd.b});
+        }
+        CU(dev_alloc(h, &p, std::max<size_t>(1, dp.size()) * sizeof(DevPeer)));
+        P.d_peers = p;
+        if (!dp.empty()) CU(cudaMemcpyAsync(P.d_peers, dp.data(), dp.size() * sizeof(DevPeer), cudaMemcpyHostToDevice, h->stream));
+    }
     CU(dev_alloc(h, &p, std::max<size_t>(1, targets.size()) * sizeof(unsigned*)));
     P.d_targets = (unsigned**)p;
     CU(dev_alloc(h, &p, std::max<size_t>(1, P.recv_from.size()) * sizeof(int)));
@@ -2160,6 +2174,8 @@ int sdpb_solve_batch(sdpb_handle* const* handles, int n) {
         return SDPB_OK;
     }
     if (!B) {
+        // every instance gets 1/n of the GPU: no point in splitting its action range to fill all of it
+        for (int i = 0; i < n; i++) handles[i]->tiled.batch = n;
         // first call with this list: plain solves (they create every scratch buffer); remember the list
         for (int i = 0; i < n; i++) { const int rc = sdpb_solve_async(handles[i]); if (rc != SDPB_OK) return rc; }
         for (int i = 0; i < n; i++) { const int rc = sdpb_sync(handles[i]); if (rc != SDPB_OK) return rc; }
