@@ -377,6 +377,24 @@ def next_rows(S, device):
                                  "kernel": KERNEL_NAMES.get(st["kernel_used"]),
                                  "what": "CashRecursionMulti + MultiItemCash.java:69-121 lambdas, 41 x 41 x 401 grid, "
                                          "Qbound 20 (the reference's 201 x 201 x 10001 dense grid is 4e8 states)"}
+    # f-3, the reference's scaling wall: two products + lead time + un-quantised cash, solved over the reached states
+    import numpy as np
+    rows = np.array([(a, b, pa * pb) for a, pa in zip([10, 30], [0.5, 0.5]) for b, pb in zip([5, 15], [0.5, 0.5])], dtype=float)
+    rec = S.CashRecursionMultiLead([rows.copy() for _ in range(3)], Qbound=50, device=device)
+    t0 = time.perf_counter()
+    val = rec.getExpectedValue(S.CashStateMultiLead(1, 0, 0, 0, 0, 0.0))
+    dt = time.perf_counter() - t0
+    act = rec.getAction(S.CashStateMultiLead(1, 0, 0, 0, 0, 0.0))
+    ev = float(sum(rec.n_states)) * 2500 * 4
+    res["f3_multilead_T3"] = {"states_per_period": [int(x) for x in rec.n_states], "evals": ev, "device_ms": rec.solve_ms,
+                              "wall_ms": dt * 1e3, "evals_per_s": ev / (rec.solve_ms * 1e-3), "value": val,
+                              "Q1": act.getFirstAction(), "Q2": act.getSecondAction(),
+                              "reference_record": "final optimal cash is -76.56, Q1 = 30, Q2 = 15, running time is 1568.0s "
+                                                  "(src/cash/overdraft/MultiProductLeadtime.java:45-50)",
+                              "matches_reference_record": bool(val == -76.56 and act.getFirstAction() == 30 and act.getSecondAction() == 15),
+                              "what": "CashRecursionMultiLead + MultiProductLeadtime.java:150-224 lambdas through sdpb_multilead_solve: "
+                                      "forward enumeration of the reached states (expand, sort, unique), backward induction with "
+                                      "binary-search successor lookup"}
     sp = S.workforce_model([0.5, 0.5, 0.5])
     with S.Solver(sp, device=device) as s:
         s.solve()

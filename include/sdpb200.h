@@ -435,6 +435,37 @@ int sdpb_group_stats(const sdpb_group* g, sdpb_stats* s);
  * call with the same handle list on, and the call returns when all are solved. */
 int sdpb_solve_batch(sdpb_handle* const* handles, int n);
 
+/* ---- two products with lead time and an un-quantised cash balance: the states the recursion REACHES ---------------------
+ * The reference's own scaling wall (src/cash/overdraft/MultiProductLeadtime.java:28, "3 hour no solution"): state
+ * (period, x1, x2, preQ1, preQ2, cash) with a cash balance that is not rounded (:219 is commented out), so there is
+ * no grid.  sdpb_multilead_solve builds, period by period, the set of states the reference's memoised recursion
+ * (src/sdp/cash/multiItem/CashRecursionMultiLead.java:54-95) visits from `init_state` (expand every (state, action,
+ * demand), sort, unique), then runs the backward induction over those sets on the GPU; successors are found by binary
+ * search.  Same arithmetic and the same order-dependent acceptance rule `value > best + tie_tolerance` (:82) as the
+ * reference.  Replaces: new CashRecursionMultiLead(gamma, pmf, A, f, c, T) + getExpectedValue(iniState) +
+ * getAction(iniState) for the lambdas of MultiProductLeadtime.java:150-224. */
+typedef struct sdpb_multilead_model {
+    uint32_t struct_size;      /* = sizeof(sdpb_multilead_model) */
+    int32_t  T;                /* horizon */
+    int32_t  q_bound;          /* actions are pairs (i, j), 0 <= i, j < q_bound, scanned i-major (MultiProductLeadtime.java:150-158) */
+    int32_t  n_demands;        /* demand pairs per period */
+    const double* d1;          /* [T * n_demands] demand of product 1 (cast to int, CashRecursionMultiLead.java:76) */
+    const double* d2;          /* [T * n_demands] demand of product 2 */
+    const double* p;           /* [T * n_demands] probabilities (GetPmfMulti.getPmf(t)[j][2]) */
+    const double* overhead_t;  /* [T] */
+    double price[2], vari_cost[2], salvage[2];
+    double r0, r1, r2, limit, interest_free;   /* deposit rate, overdraft rate, penalty rate, overdraft limit, free amount */
+    double min_inv, max_inv, min_cash, max_cash;
+    double gamma, tie_tolerance;               /* discount factor; 0.1 in the reference */
+} sdpb_multilead_model;
+
+/* init_state = (x1, x2, preQ1, preQ2, cash).  value = getExpectedValue(iniState) (the driver adds iniCash,
+ * MultiProductLeadtime.java:236); action1 / action2 = getAction(iniState); n_states[t-1] = states of period t
+ * (may be NULL, T entries); solve_ms = device time.  Blocks.  No CPU fallback. */
+int sdpb_multilead_solve(const sdpb_multilead_model* m, int device, const double* init_state, double* value,
+                         int32_t* action1, int32_t* action2, int64_t* n_states, double* solve_ms);
+const char* sdpb_multilead_last_error(void);
+
 /* Return the memory cached by the library's private stream-ordered pool on `device` to the driver (-1 = current). */
 int sdpb_trim_pool(int device);
 

@@ -25,6 +25,8 @@ from __future__ import annotations
 import random
 from enum import Enum
 
+import ctypes as C
+
 import numpy as np
 
 from . import _abi as A
@@ -402,6 +404,85 @@ class CashRecursionMulti:
                 boolAlpha, alpha = 1.0, variCost[0] * Q1 / w
             out.append([t, x1, x2, w, R, boolAlpha, alpha, Q1, Q2, variCost[0], variCost[1]])
         return np.asarray(out)
+
+
+class CashStateMultiLead:
+    """src/sdp/cash/multiItem/CashStateMultiLead.java: (period, iniInventory1, iniInventory2, preQ1, preQ2, iniCash)."""
+
+    def __init__(self, period, iniInventory1, iniInventory2, preQ1, preQ2, iniCash):
+        self.period = int(period)
+        self.iniInventory1, self.iniInventory2 = float(iniInventory1), float(iniInventory2)
+        self.preQ1, self.preQ2, self.iniCash = float(preQ1), float(preQ2), float(iniCash)
+
+    def getPeriod(self):
+        return self.period
+
+    def _vec(self):
+        return (self.iniInventory1, self.iniInventory2, self.preQ1, self.preQ2, self.iniCash)
+
+
+class CashRecursionMultiLead:
+    """new CashRecursionMultiLead(discountFactor, PmfMulti, buildActionList, stateTransition, immediateValue, T)
+    (src/sdp/cash/multiItem/CashRecursionMultiLead.java:28-95) for the lambdas of
+    src/cash/overdraft/MultiProductLeadtime.java:150-224: two products, lead time 1, overdraft interest, a cash balance
+    that is NOT quantised -- no grid, so the library enumerates the states the recursion reaches
+    (sdpb_multilead_solve).  `pmf`: per period an array [D, 3] of (demand1, demand2, prob) as GetPmfMulti.getPmf returns."""
+
+    def __init__(self, pmf, price=(5.0, 10.0), variCost=(1.0, 2.0), salValueUnit=None, overheadCost=None, r0=0.0, r1=0.1,
+                 r2=2.0, limit=500.0, interestFreeAmount=0.0, Qbound=50, minInventoryState=0.0, maxInventoryState=200.0,
+                 minCashState=-500.0, maxCashState=5000.0, discountFactor=1.0, tieTolerance=0.1, device: int = -1):
+        self.lib = A.load()
+        T = len(pmf)
+        nD = len(pmf[0])
+        if any(len(r) != nD for r in pmf):
+            raise ValueError("every period needs the same number of demand pairs")
+        tab = np.stack([np.asarray(r, dtype=np.float64) for r in pmf])           # [T, D, 3]
+        self._d1 = np.ascontiguousarray(tab[:, :, 0]).ravel()
+        self._d2 = np.ascontiguousarray(tab[:, :, 1]).ravel()
+        self._p = np.ascontiguousarray(tab[:, :, 2]).ravel()
+        self._ovh = np.ascontiguousarray(overheadCost if overheadCost is not None else [100.0] * T, dtype=np.float64)
+        sal = salValueUnit if salValueUnit is not None else (variCost[0] * 0.5, variCost[1] * 0.5)
+        m = A.SdpbMultileadModel()
+        m.struct_size = C.sizeof(A.SdpbMultileadModel)
+        m.T, m.q_bound, m.n_demands = T, int(Qbound), nD
+        dp = C.POINTER(C.c_double)
+        m.d1, m.d2, m.p = self._d1.ctypes.data_as(dp), self._d2.ctypes.data_as(dp), self._p.ctypes.data_as(dp)
+        m.overhead_t = self._ovh.ctypes.data_as(dp)
+        m.price[0], m.price[1] = price
+        m.vari_cost[0], m.vari_cost[1] = variCost
+        m.salvage[0], m.salvage[1] = sal
+        m.r0, m.r1, m.r2, m.limit, m.interest_free = r0, r1, r2, limit, interestFreeAmount
+        m.min_inv, m.max_inv, m.min_cash, m.max_cash = minInventoryState, maxInventoryState, minCashState, maxCashState
+        m.gamma, m.tie_tolerance = discountFactor, tieTolerance
+        self._m, self.T, self.device = m, T, device
+        self._solved = {}
+        self.n_states = None
+        self.solve_ms = None
+
+    def _solve(self, state):
+        if state.getPeriod() != 1:
+            raise ValueError("the reached-state solve starts from a period-1 state")
+        key = state._vec()
+        if key not in self._solved:
+            st = np.ascontiguousarray(key, dtype=np.float64)
+            v, ms = C.c_double(), C.c_double()
+            a1, a2 = C.c_int32(), C.c_int32()
+            ns = (C.c_int64 * self.T)()
+            rc = self.lib.sdpb_multilead_solve(C.byref(self._m), self.device, st.ctypes.data_as(C.POINTER(C.c_double)),
+                                               C.byref(v), C.byref(a1), C.byref(a2), ns, C.byref(ms))
+            if rc != A.SDPB_OK:
+                raise A.SdpbError(rc, self.lib.sdpb_multilead_last_error().decode())
+            self._solved[key] = (v.value, Actions(a1.value, a2.value))
+            self.n_states, self.solve_ms = list(ns), ms.value
+        return self._solved[key]
+
+    def getExpectedValue(self, state):
+        return self._solve(state)[0]
+
+    def getAction(self, state):
+        if state._vec() not in self._solved:
+            raise KeyError("getAction on a state that was never solved")
+        return self._solved[state._vec()][1]
 
 
 # ---- workforce ------------------------------------------------------------------------------

@@ -1048,3 +1048,56 @@ def test_config_c5_1e8_sampled(S, oracle):
     spec = S.configs.c5(n_states=100_000_000)
     s = S.Solver(spec).solve()
     _sample_check(S, oracle, spec, s, n=48)
+
+
+# ---- the reference's own recorded outputs, on the GPU ---------------------------------------------------------------
+def _multi_pmf(vals1, probs1, vals2, probs2, T):
+    """GetPmfMulti.getPmf for DiscreteDistribution (GetPmfMulti.java:158-171): all pairs, product 1 outermost."""
+    rows = np.array([(a, b, pa * pb) for a, pa in zip(vals1, probs1) for b, pb in zip(vals2, probs2)], dtype=float)
+    return [rows.copy() for _ in range(T)]
+
+
+def test_multilead_reference_record_T2(S, oracle):
+    """src/cash/overdraft/MultiProductLeadtime.java:41-43, recorded by the reference's author: 'when T = 2, final
+    optimal cash is -17.800000000000008, optimal order quantity in the first period is: Q1 = 40, Q2 = 20'.
+    The GPU's reached-state solve (sdpb_multilead_solve) reproduces the Java program's printed output to the last
+    digit, and agrees with the CPU oracle's restatement of the same loop."""
+    vals = ([20, 30, 40], [10, 15, 20])
+    probs = ([0.25, 0.5, 0.25], [0.25, 0.5, 0.25])
+    recursion = S.CashRecursionMultiLead(_multi_pmf(vals[0], probs[0], vals[1], probs[1], 2), Qbound=50)
+    iniState = S.CashStateMultiLead(1, 0, 0, 0, 0, 0.0)
+    finalValue = 0.0 + recursion.getExpectedValue(iniState)          # iniCash + recursion.getExpectedValue(iniState), :236
+    assert finalValue == -17.800000000000008
+    act = recursion.getAction(iniState)
+    assert (act.getFirstAction(), act.getSecondAction()) == (40, 20)
+    v, q1, q2, ns = oracle.multi_lead(2, 50, vals[0], probs[0], vals[1], probs[1])
+    assert (finalValue, 40, 20) == (v, q1, q2) and sum(recursion.n_states) == ns
+
+
+@pytest.mark.parametrize("T,qb,ovh", [(3, 7, 100.0), (3, 9, 20.0), (4, 4, 35.0), (1, 12, 100.0)])
+def test_multilead_matches_oracle(T, qb, ovh, S, oracle):
+    """Horizons and action bounds the CPU oracle solves in seconds: value, first-period actions and the number of
+    visited states must equal the literal top-down recursion's."""
+    vals = ([10, 30], [5, 15])
+    probs = ([0.5, 0.5], [0.5, 0.5])
+    rec = S.CashRecursionMultiLead(_multi_pmf(vals[0], probs[0], vals[1], probs[1], T), Qbound=qb, overheadCost=[ovh] * T)
+    st = S.CashStateMultiLead(1, 0, 0, 0, 0, 0.0)
+    v = rec.getExpectedValue(st)
+    vo, q1, q2, ns = oracle.multi_lead(T, qb, vals[0], probs[0], vals[1], probs[1], overhead=ovh)
+    act = rec.getAction(st)
+    assert v == vo and (act.getFirstAction(), act.getSecondAction()) == (q1, q2)
+    assert sum(rec.n_states) == ns
+
+
+def test_multilead_reference_record_T3(S):
+    """src/cash/overdraft/MultiProductLeadtime.java:45-50 -- the live code of the reference: 3 periods, demands
+    {10,30} x {5,15}: 'final optimal cash is -76.56 ... Q1 = 30, Q2 = 15 ... running time is 1568.0s'.  1.7e7 states and
+    1.7e11 evaluations; the CPU oracle needs 34 minutes for it (tests/test_oracle.py, opt-in), the GPU about a second."""
+    rec = S.CashRecursionMultiLead(_multi_pmf([10, 30], [0.5, 0.5], [5, 15], [0.5, 0.5], 3), Qbound=50)
+    st = S.CashStateMultiLead(1, 0, 0, 0, 0, 0.0)
+    finalValue = 0.0 + rec.getExpectedValue(st)
+    act = rec.getAction(st)
+    assert finalValue == -76.56                             # Double.toString prints the shortest digits that identify the double
+    assert (act.getFirstAction(), act.getSecondAction()) == (30, 15)
+    assert rec.n_states[0] == 1 and sum(rec.n_states) > 1.6e7
+    print(f"multilead T=3: {rec.n_states} states, {rec.solve_ms:.0f} ms on the device")
