@@ -657,7 +657,7 @@ def run_gpu(args):
                 s3.step()  # warm (plain launches)
                 csync()
                 ev, evx, fp, kused, _ = per_step_counts(s3, csync)  # second solve: a CUDA graph when unsharded
-                reps = 5 if (cname in ("c1", "c2") or (n_s or 10**9) <= 100_000) else (3 if (n_s or 10**9) <= 1_000_000 else 1)
+                reps = 5 if (cname in ("c1", "c2", "c3", "c4") or (n_s or 10**9) <= 100_000) else (3 if (n_s or 10**9) <= 1_000_000 else 1)
                 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 csync()
                 a0.record(stream)

@@ -263,12 +263,19 @@ inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& d
     const int ix1 = (int)((hi - 1) / dm.nW);
     a.price = cp.price; a.v = cp.v; a.K = P.K; a.ovh = cp.ovh; a.d0 = cp.d0; a.inv_min_i = (int)m.inv_min;
     const bool surv = m.recursion == SDPB_REC_SURVIVAL;
-    const int tile = kCashThreads * ((t == m.T && !surv) ? kCashRLast : kCashR);
+    // 16 cash levels per thread in the last period -- unless that leaves the GPU short of CTAs (a shard of the grid)
+    int sm_count = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    const long long ctas16 = (long long)(ix1 - a.ix0 + 1) * ((dm.nW + kCashThreads * kCashRLast - 1) / (kCashThreads * kCashRLast));
+    const bool wide = t == m.T && !surv && ctas16 >= 3LL * sm_count;
+    const int tile = kCashThreads * (wide ? kCashRLast : kCashR);
     const dim3 grid((unsigned)(ix1 - a.ix0 + 1), (unsigned)((dm.nW + tile - 1) / tile));
     const size_t smem = (size_t)D * 28 + 16;
     if (smem > 200 * 1024) return SDPB_ERR_STATE;  // demand support too long for the shared-memory tables: general path
     if (smem > 48 * 1024) {
         cudaFuncSetAttribute(bi_cash_int<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(bi_cash_int<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(bi_cash_int<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(bi_cash_int<false, true, true, kCashRLast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(bi_cash_int<false, false, true, kCashRLast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(bi_cash_int<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -277,8 +284,13 @@ inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& d
     }
     if (t == m.T) {
         if (surv) bi_cash_int<true, false, true><<<grid, kCashThreads, smem, stream>>>(dm, a);
-        else if (dm.is_min) bi_cash_int<false, true, true, kCashRLast><<<grid, kCashThreads, smem, stream>>>(dm, a);
-        else bi_cash_int<false, false, true, kCashRLast><<<grid, kCashThreads, smem, stream>>>(dm, a);
+        else if (wide) {
+            if (dm.is_min) bi_cash_int<false, true, true, kCashRLast><<<grid, kCashThreads, smem, stream>>>(dm, a);
+            else bi_cash_int<false, false, true, kCashRLast><<<grid, kCashThreads, smem, stream>>>(dm, a);
+        } else {
+            if (dm.is_min) bi_cash_int<false, true, true><<<grid, kCashThreads, smem, stream>>>(dm, a);
+            else bi_cash_int<false, false, true><<<grid, kCashThreads, smem, stream>>>(dm, a);
+        }
     } else {
         if (surv) bi_cash_int<true, false, false><<<grid, kCashThreads, smem, stream>>>(dm, a);
         else if (dm.is_min) bi_cash_int<false, true, false><<<grid, kCashThreads, smem, stream>>>(dm, a);
@@ -286,7 +298,7 @@ inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& d
     }
     if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
     if (fp64_ops) {
-        if (t == m.T) *fp64_ops += evals * (surv ? 2.0 + 3.0 / kCashR : 1.0 + 4.0 / kCashRLast);
+        if (t == m.T) *fp64_ops += evals * (surv ? 2.0 + 3.0 / kCashR : 1.0 + 4.0 / (wide ? kCashRLast : kCashR));
         else *fp64_ops += evals * (surv ? 2.0 : 3.0 + 2.0 / kCashR);
     }
     return SDPB_OK;

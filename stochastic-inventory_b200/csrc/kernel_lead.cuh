@@ -531,7 +531,9 @@ inline int launch_col(const ColPlan& P, const DevModel& dm, int t, int D, int pm
 // load lands in its final register PF + 1 demand steps before its first use (as in bi_cash_diag).
 // fp64 per evaluation: (1 + 4*8) / 8 = 4.125 (2.125 in the last period), as bi_lead_col, but the
 // 8 x NQB shared-memory argopt, its barrier and the one-CTA-per-SM occupancy are gone.  (A warp-per-chunk
-// numbering that lets a CTA's warps share successor rows in L1 was measured slower: 149-175 ms vs 140 on C4.)
+// numbering that lets a CTA's warps share successor rows in L1 was measured slower: 149-175 ms vs 140 on C4.  So was a
+// variant with TWO actions per pass of the demand loop -- shared LDS.128 and row offsets, 66 fp64 instructions per step
+// against ~8 others -- at 168 registers and 3 CTAs per SM: 146.5 vs 141.9 ms.)
 struct Q2Args {
     int t, D, pmf_off;
     const double* VnT;        // transposed V_{t+1} (nullptr in the last period)
