@@ -157,10 +157,28 @@ class ShardedSolve:
         self.bytes_out = self.bytes_in = 0
         if world > 1 and exchange == "p2p":
             blobs = gather_blobs(torch, dist, world, self.solver.peer_export(), device=f"cuda:{device}")
-            self.solver.peer_attach(blobs)
-            self.bytes_out, self.bytes_in = self.solver.peer_traffic()
-            self.exchange_kind = "p2p"
-        elif world > 1:
+            ok, why = 1, ""
+            try:
+                self.solver.peer_attach(blobs)
+            except Exception as e:  # e.g. no peer-to-peer path between two of the GPUs
+                ok, why = 0, str(e)
+            flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{device}")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag[0]) == 1:
+                self.bytes_out, self.bytes_in = self.solver.peer_traffic()
+                self.exchange_kind = "p2p"
+            else:
+                # every rank falls back together: a fresh handle, stepped period by period with torch.distributed
+                if rank == 0:
+                    import sys
+                    print(f"[sdpb200] peer exchange unavailable ({why or 'a peer could not attach'}): using the "
+                          "torch.distributed exchange", file=sys.stderr)
+                self.solver.close()
+                self.solver = Solver(spec, device=device, shard_rank=rank, shard_count=world, kernel=kernel,
+                                     dedup=dedup, stream=stream.cuda_stream)
+                g = self.solver.grid
+                exchange = "nccl"
+        if world > 1 and exchange != "p2p":
             wlo, whi = g.window_lo, g.window_hi
             for t in range(1, self.T + 1):
                 dv, _ = self.solver.device_tables(t)
