@@ -112,8 +112,20 @@ class Model {
         fix();
     }
     Model(const Model& o) : m(o.m), len_(o.len_), d_(o.d_), p_(o.p_), price_t_(o.price_t_), vari_t_(o.vari_t_),
-                            ovh_t_(o.ovh_t_), res_t_(o.res_t_) { fix(); }
+                            ovh_t_(o.ovh_t_), res_t_(o.res_t_), terminal_(o.terminal_) { fix(); }
     Model& operator=(const Model&) = delete;
+
+    // FinalCash.BoundaryFuncton (FinalCash.java:16-18; consumed at CashRecursionV.java:125-128): the value of every grid
+    // state of period T+1, in the library's state order (inventory outermost, cash innermost)
+    Model& boundFinalCash(std::vector<double> table) { terminal_ = std::move(table); fix(); return *this; }
+
+    // Leadtime.java:63-67 does not clamp: make the inventory axis the hull of what the recursion can reach
+    Model& reachableHull(const std::vector<double>& initialState) {
+        double lo = 0, hi = 0;
+        if (sdpb_reachable_hull(&m, initialState.data(), 1, &lo, &hi) != SDPB_OK) throw SdpbError(SDPB_ERR_ARG, "sdpb_reachable_hull");
+        m.inv_min = lo; m.inv_max = hi;
+        return *this;
+    }
 
     void setPerPeriod(const std::vector<double>* price, const std::vector<double>* vari, const std::vector<double>* ovh,
                       const std::vector<double>* reserve) {
@@ -214,8 +226,9 @@ class Model {
 
  private:
     std::vector<int32_t> len_;
-    std::vector<double> d_, p_, price_t_, vari_t_, ovh_t_, res_t_;
+    std::vector<double> d_, p_, price_t_, vari_t_, ovh_t_, res_t_, terminal_;
     void fix() {
+        m.terminal_value = terminal_.empty() ? nullptr : terminal_.data();
         m.pmf_len = len_.data(); m.pmf_d = d_.data(); m.pmf_p = p_.data();
         m.price_t = price_t_.empty() ? nullptr : price_t_.data();
         m.vari_cost_t = vari_t_.empty() ? nullptr : vari_t_.data();
@@ -238,17 +251,35 @@ class Engine {
         check(sdpb_grid_info(h_, &g));
         ndim_ = g.ndim;
     }
+    // the same solve partitioned over several GPUs of this process (sdpb_group_*): bands of inventory rows, rows of
+    // V_t handed from table to table through peer-mapped memory inside the library
+    Engine(const Model& model, const std::vector<int>& devices, int kernel = SDPB_KERNEL_AUTO) : model_(model) {
+        sdpb_options o;
+        std::memset(&o, 0, sizeof o);
+        o.struct_size = (uint32_t)sizeof o;
+        o.kernel = kernel;
+        const int rc = sdpb_group_create(&model_.m, &o, devices.data(), (int)devices.size(), &g_);
+        if (rc != SDPB_OK) throw SdpbError(rc, std::string("sdpb_group_create: ") + sdpb_group_last_error(nullptr));
+        sdpb_grid g;
+        if (sdpb_grid_info(sdpb_group_shard(g_, 0), &g) != SDPB_OK) throw SdpbError(SDPB_ERR_ARG, "sdpb_grid_info");
+        ndim_ = g.ndim;
+    }
     Engine(const Engine&) = delete;
     Engine& operator=(const Engine&) = delete;
-    ~Engine() { sdpb_destroy(h_); }
+    ~Engine() { if (g_) sdpb_group_destroy(g_); else sdpb_destroy(h_); }
 
     // getExpectedValue / getAction of one state; the first call solves the whole horizon (Recursion.java:89-163
     // descends the whole reachable tree on its first call too)
     std::array<double, 2> valueAndAction(int period, const std::vector<double>& st) {
         if ((int)st.size() != ndim_) throw SdpbError(SDPB_ERR_ARG, "state has the wrong number of components");
-        if (!solved_) { check(sdpb_solve(h_)); solved_ = true; }
+        if (!solved_) {
+            if (g_) { const int rc = sdpb_group_solve(g_); if (rc != SDPB_OK) throw SdpbError(rc, sdpb_group_last_error(g_)); }
+            else check(sdpb_solve(h_));
+            solved_ = true;
+        }
         double v = 0.0, q = 0.0;
-        check(sdpb_value(h_, period, st.data(), 1, &v, &q));
+        if (g_) { const int rc = sdpb_group_value(g_, period, st.data(), 1, &v, &q); if (rc != SDPB_OK) throw SdpbError(rc, sdpb_group_last_error(g_)); }
+        else check(sdpb_value(h_, period, st.data(), 1, &v, &q));
         if (period == 1) roots_.push_back(st);
         return {v, q};
     }
@@ -259,6 +290,7 @@ class Engine {
     // from the period-1 states queried so far, sorted by (period, state) (Recursion.java:169-186)
     std::vector<std::vector<double>> optTable() {
         if (!solved_ || roots_.empty()) throw SdpbError(SDPB_ERR_UNSOLVED, "getOptTable before getExpectedValue");
+        if (g_) throw SdpbError(SDPB_ERR_STATE, "the visited-state table needs a single-GPU engine (sdpb_reach)");
         std::vector<double> flat;
         for (const auto& r : roots_) flat.insert(flat.end(), r.begin(), r.end());
         check(sdpb_reach(h_, flat.data(), (int)roots_.size()));
@@ -280,6 +312,7 @@ class Engine {
     }
     Model model_;
     sdpb_handle* h_ = nullptr;
+    sdpb_group* g_ = nullptr;
     int ndim_ = 1;
     bool solved_ = false;
     std::vector<std::vector<double>> roots_;
@@ -289,6 +322,7 @@ class Engine {
 class Recursion {
  public:
     explicit Recursion(const Model& model, int device = -1) : e_(model, device) {}
+    Recursion(const Model& model, const std::vector<int>& devices) : e_(model, devices) {}
     double getExpectedValue(const State& s) { return e_.valueAndAction(s.period, {s.iniInventory})[0]; }
     // Recursion.java:165-167 unboxes a null for a state that was never solved; the mirror throws too
     double getAction(const State& s) {
@@ -306,6 +340,8 @@ class Recursion {
 class LeadtimeRecursion {  // LeadtimeRecursion.java:28-75
  public:
     explicit LeadtimeRecursion(const Model& model, int device = -1) : e_(model, device) {}
+    LeadtimeRecursion(const Model& model, const std::vector<int>& devices) : e_(model, devices) {}
+    std::vector<std::vector<double>> getOptTable() { return e_.optTable(); }  // rows [t, x, preQ, Q*]
     double getExpectedValue(const LeadtimeState& s) { return e_.valueAndAction(s.period, {s.iniInventory, s.preQ})[0]; }
     double getAction(const LeadtimeState& s) {
         if (!e_.solved()) throw SdpbError(SDPB_ERR_UNSOLVED, "getAction on a state that was never solved");
@@ -320,6 +356,7 @@ class LeadtimeRecursion {  // LeadtimeRecursion.java:28-75
 class CashRecursion {  // CashRecursion.java:39-220
  public:
     explicit CashRecursion(const Model& model, int device = -1) : e_(model, device) {}
+    CashRecursion(const Model& model, const std::vector<int>& devices) : e_(model, devices) {}
     double getExpectedValue(const CashState& s) { return e_.valueAndAction(s.period, {s.iniInventory, s.iniCash})[0]; }
     double getAction(const CashState& s) {
         if (!e_.solved()) throw SdpbError(SDPB_ERR_UNSOLVED, "getAction on a state that was never solved");

@@ -864,7 +864,8 @@ int solve_period(sdpb_handle* h, int t) {
                 h->cash.slice_a = (int*)p;
                 h->cash.slice_cap = need;  // (an earlier, smaller scratch stays in dev_allocs until the handle goes)
             }
-            const bool push = h->peer.attached && t > 1 && !h->peer.sends.empty();
+            static const bool no_fused = std::getenv("SDPB_NO_FUSED_PUSH") != nullptr;  // A/B knob: copies after the kernel
+            const bool push = h->peer.attached && t > 1 && !h->peer.sends.empty() && !no_fused;
             rc = launch_cash_diag(h->cash, m, h->dm, t, D, h->pmf_off[t - 1], Vn, h->dV[t - 1], h->dQ[t - 1], h->lo,
                                   h->hi, h->stream, &h->stats.fp64_ops, count_evals_period(h, t), h->sm_count,
                                   push ? (const DevPeer*)h->peer.d_peers : nullptr, push ? (int)h->peer.sends.size() : 0,

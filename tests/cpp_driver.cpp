@@ -5,6 +5,7 @@
 //   section F  src/cash/risk/cashSurvival.java             (RiskRecursion.getSurvProb)
 // It writes every pmf table it built to <out>.pmf (so the Python test can hand the SAME table to the oracle)
 // and prints its results as "key value..." lines.  Exit code 77: no CUDA device (there is no CPU path).
+#include <algorithm>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -86,6 +87,32 @@ int main(int argc, char** argv) {
             CashState initialState{1, 0, 15};
             double survProb = recursion.getSurvProb(initialState);
             std::printf("F %.17g %.17g\n", survProb, recursion.getAction(initialState));
+        }
+        {   // ---- G: the capacitated model of section A on three shards (sdpb_group_*), and with a boundary function ----
+            double meanDemand[] = {9, 23, 53, 29};
+            std::vector<PoissonDist> distributions;
+            for (double m : meanDemand) distributions.emplace_back(m);
+            Pmf pmf = GetPmf(distributions, 0.9999, 1).getpmf();
+            Model model = Model::inventory(OptDirection::MIN, pmf, 500, 0, 2, 10, 60, -120, 200, 1);
+            Recursion sharded(model, std::vector<int>{0, 0, 0});
+            State initialState{1, 0};
+            std::printf("G %.17g %.17g\n", sharded.getExpectedValue(initialState), sharded.getAction(initialState));
+            // FinalCash.BoundaryFuncton: leftover stock is worth 0.75 a unit, a backorder costs 2.5 (CashRecursionV.java:125-128 form)
+            std::vector<double> boundFinalCash;
+            for (int x = -120; x <= 200; x++) boundFinalCash.push_back(-0.75 * std::max(x, 0) + 2.5 * std::max(-x, 0));
+            Model withBoundary(model);
+            withBoundary.boundFinalCash(boundFinalCash);
+            Recursion bounded(withBoundary);
+            std::printf("H %.17g %.17g\n", bounded.getExpectedValue(initialState), bounded.getAction(initialState));
+            // Leadtime.java:63-67 with the grid sized by sdpb_reachable_hull
+            double meanB[] = {4, 6, 5};
+            std::vector<PoissonDist> distB;
+            for (double m : meanB) distB.emplace_back(m);
+            Model lead = Model::leadtime(GetPmf(distB, 0.999, 1).getpmf(), 0, 1, 2, 10, 12, 0, 0, 1, 1, false);
+            lead.reachableHull({0, 0});
+            LeadtimeRecursion hull(lead);
+            LeadtimeState s0{1, 0, 0};
+            std::printf("I %.17g %.17g %.17g %.17g\n", hull.getExpectedValue(s0), hull.getAction(s0), lead.m.inv_min, lead.m.inv_max);
         }
     } catch (const SdpbError& e) {
         std::fprintf(stderr, "%s\n", e.what());

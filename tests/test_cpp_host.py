@@ -58,6 +58,12 @@ def test_cpp_host_matches_oracle(tmp_path, S, oracle):
                              inv_min=-120, inv_max=200)
     rows, iv, _ = oracle.topdown(spec, [[0.0]])
     assert res["A"] == [iv[0], rows[0][-2], float(len(rows)), 1.0]          # value, Q*, table rows, getAction threw
+    assert res["G"] == [iv[0], rows[0][-2]]                                 # the same on three shards (sdpb_group_*)
+    spec_b = S.inventory_model(pmf["A"], fixed_cost=500, vari_cost=0, hold_cost=2, penalty_cost=10, max_order=60,
+                               inv_min=-120, inv_max=200)
+    spec_b.terminal_value = spec_b.tabulate(lambda x: -0.75 * np.maximum(x, 0) + 2.5 * np.maximum(-x, 0))
+    rows_b, iv_b, _ = oracle.topdown(spec_b, [[0.0]])
+    assert res["H"] == [iv_b[0], rows_b[0][-2]] and iv_b[0] != iv[0]        # with a boundary function
     assert res["A_row0"] == [rows[0][0], rows[0][1], rows[0][-2]]
     assert res["A_rowN"] == [rows[-1][0], rows[-1][1], rows[-1][-2]]
 
@@ -65,6 +71,8 @@ def test_cpp_host_matches_oracle(tmp_path, S, oracle):
                             inv_min=-45, inv_max=36, lead_time=1, clamp=False)
     rows, iv, _ = oracle.topdown(spec, [[0.0, 0.0]])
     assert res["B"] == [iv[0], rows[0][-2]]
+    assert res["I"][:2] == [iv[0], rows[0][-2]]                             # grid sized by sdpb_reachable_hull
+    assert res["I"][2:] == list(S.reachable_hull(spec, [[0.0, 0.0]]))
 
     spec = S.cash_constraint_model(pmf["C"], price=8, vari_cost=1, fixed_cost=10, hold_cost=0.5, salvage=0.5, overhead=4,
                                    overhead_rate=0.02, deposit_rate=0.05, penalty_cost=0.3, max_order=15, inv_min=0,
