@@ -435,36 +435,53 @@ int sdpb_group_stats(const sdpb_group* g, sdpb_stats* s);
  * call with the same handle list on, and the call returns when all are solved. */
 int sdpb_solve_batch(sdpb_handle* const* handles, int n);
 
-/* ---- two products with lead time and an un-quantised cash balance: the states the recursion REACHES ---------------------
- * The reference's own scaling wall (src/cash/overdraft/MultiProductLeadtime.java:28, "3 hour no solution"): state
- * (period, x1, x2, preQ1, preQ2, cash) with a cash balance that is not rounded (:219 is commented out), so there is
- * no grid.  sdpb_multilead_solve builds, period by period, the set of states the reference's memoised recursion
- * (src/sdp/cash/multiItem/CashRecursionMultiLead.java:54-95) visits from `init_state` (expand every (state, action,
- * demand), sort, unique), then runs the backward induction over those sets on the GPU; successors are found by binary
- * search.  Same arithmetic and the same order-dependent acceptance rule `value > best + tie_tolerance` (:82) as the
- * reference.  Replaces: new CashRecursionMultiLead(gamma, pmf, A, f, c, T) + getExpectedValue(iniState) +
- * getAction(iniState) for the lambdas of MultiProductLeadtime.java:150-224. */
-typedef struct sdpb_multilead_model {
-    uint32_t struct_size;      /* = sizeof(sdpb_multilead_model) */
+/* ---- the two-product recursions: solved over the states they REACH ---------------------------------------------------
+ * The reference's own scaling wall (src/cash/overdraft/MultiProductLeadtime.java:28, "3 hour no solution").  Its
+ * two-product engines keep states that a dense grid cannot hold -- a cash balance that is not rounded at all
+ * (MultiProductLeadtime.java:219 is commented out), or a 201 x 201 x 10001 grid of which a run touches a sliver --
+ * so sdpb_reached_solve builds, period by period, the set of states the reference's memoised recursion visits from
+ * `init_state` (expand every (state, action, demand), sort, unique), then runs the backward induction over those sets
+ * on the GPU; successors are found by binary search.  Same arithmetic and the same order-dependent acceptance rule
+ * `value > best + tie_tolerance` as the reference.  Three engines + driver lambdas:
+ *   SDPB_REACHED_MULTILEAD  new CashRecursionMultiLead(...).getExpectedValue / getAction
+ *                           (src/sdp/cash/multiItem/CashRecursionMultiLead.java:54-95) with the lambdas of
+ *                           src/cash/overdraft/MultiProductLeadtime.java:150-224; state (x1, x2, preQ1, preQ2, cash),
+ *                           actions (i, j) in [0, q_bound)^2, tie 0.1
+ *   SDPB_REACHED_MULTI_XR   new CashRecursionMultiXR(...).getExpectedValue / getAction
+ *                           (src/sdp/cash/multiItem/CashRecursionMultiXR.java:61-95) with the lambdas of
+ *                           src/cash/multiItem/MultiItemCashXR.java:73-126; state (x1, x2, R), actions = order-up-to
+ *                           pairs (x1 + i, x2 + j), tie 0.1
+ *   SDPB_REACHED_MULTI_YR   new CashRecursionV(...).getExpectedValueV / getAction
+ *                           (src/sdp/cash/multiItem/CashRecursionV.java:83-131: V(x1,x2,w) = max_y Pi(y1,y2,R),
+ *                           Pi = E V_{t+1}, V_{T+1} = boundFinalCash(s) = w + salvage . x) with the lambdas of
+ *                           src/cash/multiItem/MultiItemYR.java:89-146; actions = affordable order-up-to pairs
+ *                           (v . y < R + 0.1), tie 0.01 */
+typedef enum sdpb_reached_kind { SDPB_REACHED_MULTILEAD = 0, SDPB_REACHED_MULTI_XR = 1, SDPB_REACHED_MULTI_YR = 2 } sdpb_reached_kind;
+
+typedef struct sdpb_reached_model {
+    uint32_t struct_size;      /* = sizeof(sdpb_reached_model) */
+    int32_t  kind;             /* sdpb_reached_kind */
     int32_t  T;                /* horizon */
-    int32_t  q_bound;          /* actions are pairs (i, j), 0 <= i, j < q_bound, scanned i-major (MultiProductLeadtime.java:150-158) */
+    int32_t  q_bound;          /* the action list has q_bound^2 entries, scanned first component outermost */
     int32_t  n_demands;        /* demand pairs per period */
-    const double* d1;          /* [T * n_demands] demand of product 1 (cast to int, CashRecursionMultiLead.java:76) */
+    int32_t  reserved;
+    const double* d1;          /* [T * n_demands] demand of product 1 (GetPmfMulti.getPmf(t)[j][0]) */
     const double* d2;          /* [T * n_demands] demand of product 2 */
     const double* p;           /* [T * n_demands] probabilities (GetPmfMulti.getPmf(t)[j][2]) */
-    const double* overhead_t;  /* [T] */
+    const double* overhead_t;  /* [T] (MULTILEAD; may be NULL otherwise) */
     double price[2], vari_cost[2], salvage[2];
-    double r0, r1, r2, limit, interest_free;   /* deposit rate, overdraft rate, penalty rate, overdraft limit, free amount */
+    double r0, r1, r2, limit, interest_free;   /* MULTILEAD: deposit rate, overdraft rate, penalty rate, limit, free amount */
+    double deposit_rate;                       /* MULTI_XR, MULTI_YR: depositeRate */
     double min_inv, max_inv, min_cash, max_cash;
-    double gamma, tie_tolerance;               /* discount factor; 0.1 in the reference */
-} sdpb_multilead_model;
+    double gamma, tie_tolerance;               /* discount factor; 0.1 / 0.1 / 0.01 in the reference */
+} sdpb_reached_model;
 
-/* init_state = (x1, x2, preQ1, preQ2, cash).  value = getExpectedValue(iniState) (the driver adds iniCash,
- * MultiProductLeadtime.java:236); action1 / action2 = getAction(iniState); n_states[t-1] = states of period t
+/* init_state = (x1, x2, preQ1, preQ2, cash) | (x1, x2, R) | (x1, x2, cash).  value = getExpectedValue(iniState);
+ * action1 / action2 = getAction(iniState) (order quantities, or order-up-to levels); n_states[t-1] = states of period t
  * (may be NULL, T entries); solve_ms = device time.  Blocks.  No CPU fallback. */
-int sdpb_multilead_solve(const sdpb_multilead_model* m, int device, const double* init_state, double* value,
-                         int32_t* action1, int32_t* action2, int64_t* n_states, double* solve_ms);
-const char* sdpb_multilead_last_error(void);
+int sdpb_reached_solve(const sdpb_reached_model* m, int device, const double* init_state, double* value,
+                       double* action1, double* action2, int64_t* n_states, double* solve_ms);
+const char* sdpb_reached_last_error(void);
 
 /* Return the memory cached by the library's private stream-ordered pool on `device` to the driver (-1 = current). */
 int sdpb_trim_pool(int device);

@@ -666,6 +666,146 @@ Model make_model(const sdpb_model* m) {
 
 }  // namespace
 
+// ---- two more two-product recursions of the reference, restated for the reached-state engine's parity tests ----
+// kind 1: CashRecursionMultiXR.getExpectedValue (src/sdp/cash/multiItem/CashRecursionMultiXR.java:61-95) with the
+//         lambdas of src/cash/multiItem/MultiItemCashXR.java:73-126 -- state (x1, x2, R), action = order-up-to pair;
+// kind 2: CashRecursionV.getExpectedValueV / getExpectedValuePai (src/sdp/cash/multiItem/CashRecursionV.java:83-131)
+//         with the lambdas of src/cash/multiItem/MultiItemYR.java:89-146 -- state (x1, x2, w), V_{T+1} = boundFinalCash.
+// The reference records no output for either (parity unpinned); the restatement follows the cited lines.
+struct RKey {
+    int t; double x1, x2, c;
+    bool operator<(const RKey& o) const {
+        if (t != o.t) return t < o.t;
+        if (x1 != o.x1) return x1 < o.x1;
+        if (x2 != o.x2) return x2 < o.x2;
+        return c < o.c;
+    }
+};
+struct RParamsO {
+    int kind, T, Q, nD;
+    const double *d1, *d2, *p;
+    double price[2], v[2], sal[2], deposit_rate, min_inv, max_inv, min_cash, max_cash, gamma;
+};
+struct ReachedTopDown {
+    const RParamsO& P;
+    std::map<RKey, double> values;
+    std::map<RKey, std::pair<double, double>> actions;
+    explicit ReachedTopDown(const RParamsO& p) : P(p) {}
+
+    // ---- kind 1 ----
+    double xr_immediate(const RKey& s, double action1, double action2, double demand1, double demand2) const {
+        double endInventory1 = jmax(0, action1 - demand1);
+        double endInventory2 = jmax(0, action2 - demand2);
+        double revenue1 = P.price[0] * (action1 - endInventory1);
+        double revenue2 = P.price[1] * (action2 - endInventory2);
+        double revenue = revenue1 + revenue2;
+        double initialCash = s.c - P.v[0] * s.x1 - P.v[1] * s.x2;
+        double orderingCostY1 = P.v[0] * action1;
+        double orderingCostY2 = P.v[1] * action2;
+        double orderingCostsY = orderingCostY1 + orderingCostY2;
+        double salValue = 0;
+        if (s.t == P.T) salValue = P.sal[0] * endInventory1 + P.sal[1] * endInventory2;
+        return revenue + (1 - P.deposit_rate) * (s.c - orderingCostsY) + salValue - initialCash;
+    }
+    RKey xr_transition(const RKey& s, double a1, double a2, double d1, double d2) const {
+        double endInventory1 = a1 - d1;
+        endInventory1 = jmax(0, endInventory1);
+        double endInventory2 = a2 - d2;
+        endInventory2 = jmax(0, endInventory2);
+        double initialCash = s.c - P.v[0] * s.x1 - P.v[1] * s.x2;
+        double nextCash = initialCash + xr_immediate(s, a1, a2, d1, d2);
+        nextCash = nextCash > P.max_cash ? P.max_cash : nextCash;
+        nextCash = nextCash < P.min_cash ? P.min_cash : nextCash;
+        endInventory1 = endInventory1 > P.max_inv ? P.max_inv : endInventory1;
+        endInventory2 = endInventory2 < P.min_inv ? P.min_inv : endInventory2;
+        nextCash = (int)nextCash;
+        endInventory1 = (int)endInventory1;
+        endInventory2 = (int)endInventory2;
+        double nextR = (int)nextCash + P.v[0] * endInventory1 + P.v[1] * endInventory2;
+        return RKey{s.t + 1, endInventory1, endInventory2, nextR};
+    }
+    double xr_value(const RKey& s) {
+        auto it = values.find(s);
+        if (it != values.end()) return it->second;
+        double val = -DBL_MAX;
+        std::pair<double, double> best{0, 0};
+        const int miny1 = (int)s.x1, miny2 = (int)s.x2;
+        for (int i = miny1; i < miny1 + P.Q; i++)
+            for (int j = miny2; j < miny2 + P.Q; j++) {
+                double thisActionsValue = 0;
+                for (int k = 0; k < P.nD; k++) {
+                    const double dd1 = P.d1[(s.t - 1) * P.nD + k], dd2 = P.d2[(s.t - 1) * P.nD + k], pr = P.p[(s.t - 1) * P.nD + k];
+                    thisActionsValue += pr * xr_immediate(s, i, j, dd1, dd2);
+                    if (s.t < P.T) thisActionsValue += pr * P.gamma * xr_value(xr_transition(s, i, j, dd1, dd2));
+                }
+                if (thisActionsValue > val + 0.1) { val = thisActionsValue; best = {(double)i, (double)j}; }
+            }
+        values.emplace(s, val);
+        actions.emplace(s, best);
+        return val;
+    }
+
+    // ---- kind 2 ----
+    RKey yr_transition(int period, double y1, double y2, double iniR, double d1, double d2) const {
+        double endInventory1 = y1 - d1;
+        endInventory1 = jmax(0, endInventory1);
+        double endInventory2 = y2 - d2;
+        endInventory2 = jmax(0, endInventory2);
+        double revenue1 = P.price[0] * jmin(y1, d1);
+        double revenue2 = P.price[1] * jmin(y2, d2);
+        double nextW = revenue1 + revenue2 + (1 + P.deposit_rate) * (iniR - P.v[0] * y1 - P.v[1] * y2);
+        endInventory1 = (double)(jround(endInventory1 * 10) / 10);   // long division
+        endInventory2 = (double)(jround(endInventory2 * 10) / 10);
+        nextW = (double)(jround(nextW * 10) / 10);
+        nextW = nextW > P.max_cash ? P.max_cash : nextW;
+        nextW = nextW < P.min_cash ? P.min_cash : nextW;
+        endInventory1 = endInventory1 > P.max_inv ? P.max_inv : endInventory1;
+        endInventory2 = endInventory2 < P.min_inv ? P.min_inv : endInventory2;
+        return RKey{period + 1, endInventory1, endInventory2, nextW};
+    }
+    double yr_value(const RKey& s) {
+        if (s.t > P.T) return s.c + P.sal[0] * s.x1 + P.sal[1] * s.x2;  // boundFinalCash, MultiItemYR.java:116-119
+        auto it = values.find(s);
+        if (it != values.end()) return it->second;
+        double val = -DBL_MAX;
+        std::pair<double, double> best{s.x1, s.x2};
+        const int miny1 = (int)s.x1, miny2 = (int)s.x2;
+        const double iniRf = s.c + P.v[0] * s.x1 + P.v[1] * s.x2;
+        for (double i = miny1; i < miny1 + P.Q; i = i + 1)
+            for (double j = miny2; j < miny2 + P.Q; j = j + 1) {
+                if (!(P.v[0] * i + P.v[1] * j < iniRf + 0.1)) continue;
+                const double iniR = s.c + P.v[0] * s.x1 + P.v[1] * s.x2;
+                double expectValue = 0;
+                for (int k = 0; k < P.nD; k++) {
+                    const double dd1 = P.d1[(s.t - 1) * P.nD + k], dd2 = P.d2[(s.t - 1) * P.nD + k], pr = P.p[(s.t - 1) * P.nD + k];
+                    expectValue += pr * yr_value(yr_transition(s.t, i, j, iniR, dd1, dd2));
+                }
+                if (expectValue > val + 0.01) { val = expectValue; best = {i, j}; }
+            }
+        values.emplace(s, val);
+        actions.emplace(s, best);
+        return val;
+    }
+};
+
+extern "C" int oracle_reached(int kind, int T, int Qbound, int nD, const double* d1, const double* d2, const double* p,
+                              const double* price, const double* v, const double* sal, double deposit_rate, double min_inv,
+                              double max_inv, double min_cash, double max_cash, double gamma, const double* init /* x1, x2, c */,
+                              double* value, double* a1, double* a2, int64_t* n_states) {
+    RParamsO P;
+    P.kind = kind; P.T = T; P.Q = Qbound; P.nD = nD; P.d1 = d1; P.d2 = d2; P.p = p;
+    for (int k = 0; k < 2; k++) { P.price[k] = price[k]; P.v[k] = v[k]; P.sal[k] = sal[k]; }
+    P.deposit_rate = deposit_rate; P.min_inv = min_inv; P.max_inv = max_inv; P.min_cash = min_cash; P.max_cash = max_cash;
+    P.gamma = gamma;
+    ReachedTopDown td(P);
+    const RKey s0{1, init[0], init[1], init[2]};
+    *value = kind == 1 ? td.xr_value(s0) : td.yr_value(s0);
+    *a1 = td.actions[s0].first;
+    *a2 = td.actions[s0].second;
+    if (n_states) *n_states = (int64_t)td.values.size();
+    return 0;
+}
+
 extern "C" {
 
 // Grid sizes the dense oracle uses for `m` (states per period, API state length).

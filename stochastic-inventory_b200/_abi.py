@@ -88,16 +88,20 @@ class SdpbStats(C.Structure):
     ]
 
 
-class SdpbMultileadModel(C.Structure):
+class SdpbReachedModel(C.Structure):
     _fields_ = [
-        ("struct_size", C.c_uint32), ("T", C.c_int32), ("q_bound", C.c_int32), ("n_demands", C.c_int32),
+        ("struct_size", C.c_uint32), ("kind", C.c_int32), ("T", C.c_int32), ("q_bound", C.c_int32),
+        ("n_demands", C.c_int32), ("reserved", C.c_int32),
         ("d1", _dp), ("d2", _dp), ("p", _dp), ("overhead_t", _dp),
         ("price", C.c_double * 2), ("vari_cost", C.c_double * 2), ("salvage", C.c_double * 2),
         ("r0", C.c_double), ("r1", C.c_double), ("r2", C.c_double), ("limit", C.c_double), ("interest_free", C.c_double),
+        ("deposit_rate", C.c_double),
         ("min_inv", C.c_double), ("max_inv", C.c_double), ("min_cash", C.c_double), ("max_cash", C.c_double),
         ("gamma", C.c_double), ("tie_tolerance", C.c_double),
     ]
 
+
+REACHED_MULTILEAD, REACHED_MULTI_XR, REACHED_MULTI_YR = 0, 1, 2
 
 # every symbol include/sdpb200.h declares
 EXPORTS = [
@@ -108,7 +112,7 @@ EXPORTS = [
     "sdpb_sizeof_grid", "sdpb_sizeof_stats", "sdpb_reachable_hull", "sdpb_peer_export", "sdpb_peer_attach",
     "sdpb_peer_traffic", "sdpb_period_profile", "sdpb_shard_tables", "sdpb_group_create", "sdpb_group_destroy",
     "sdpb_group_last_error", "sdpb_group_solve", "sdpb_group_shard", "sdpb_group_value", "sdpb_group_period_tables",
-    "sdpb_group_stats", "sdpb_solve_batch", "sdpb_trim_pool", "sdpb_multilead_solve", "sdpb_multilead_last_error",
+    "sdpb_group_stats", "sdpb_solve_batch", "sdpb_trim_pool", "sdpb_reached_solve", "sdpb_reached_last_error",
 ]
 
 _lib = None
@@ -186,9 +190,9 @@ def load():
     lib.sdpb_group_stats.argtypes = [vp, C.POINTER(SdpbStats)]
     lib.sdpb_solve_batch.argtypes = [C.POINTER(vp), C.c_int]
     lib.sdpb_trim_pool.argtypes = [C.c_int]
-    lib.sdpb_multilead_solve.argtypes = [C.POINTER(SdpbMultileadModel), C.c_int, _dp, _dp, _ip, _ip,
-                                         C.POINTER(C.c_int64), _dp]
-    lib.sdpb_multilead_last_error.restype = C.c_char_p
+    lib.sdpb_reached_solve.argtypes = [C.POINTER(SdpbReachedModel), C.c_int, _dp, _dp, _dp, _dp,
+                                       C.POINTER(C.c_int64), _dp]
+    lib.sdpb_reached_last_error.restype = C.c_char_p
     if (lib.sdpb_sizeof_model() != C.sizeof(SdpbModel) or lib.sdpb_sizeof_options() != C.sizeof(SdpbOptions)
             or lib.sdpb_sizeof_grid() != C.sizeof(SdpbGrid) or lib.sdpb_sizeof_stats() != C.sizeof(SdpbStats)
             or lib.sdpb_abi_version() != ABI_VERSION):

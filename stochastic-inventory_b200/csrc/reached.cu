@@ -1,7 +1,13 @@
-// multilead.cu — the reference's two-product cash + lead-time recursion on the GPU, over the states it REACHES.
+// reached.cu — the reference's two-product recursions on the GPU, over the states they REACH.
 //
-//   reference: src/sdp/cash/multiItem/CashRecursionMultiLead.java:54-95 (loop, `> val + 0.1` acceptance rule)
-//              src/cash/overdraft/MultiProductLeadtime.java:150-224 (action list, immediate value, transition)
+//   kind 0  src/sdp/cash/multiItem/CashRecursionMultiLead.java:54-95 (loop, `> val + 0.1` acceptance rule)
+//           src/cash/overdraft/MultiProductLeadtime.java:150-224 (action list, immediate value, transition)
+//   kind 1  src/sdp/cash/multiItem/CashRecursionMultiXR.java:61-95, lambdas src/cash/multiItem/MultiItemCashXR.java:73-126
+//           (state (x1, x2, R), actions = order-up-to pairs, `(int)` casts)
+//   kind 2  src/sdp/cash/multiItem/CashRecursionV.java:83-131 (V / Pi form: no immediate value, `> val + 0.01`,
+//           V_{T+1} = boundFinalCash), lambdas src/cash/multiItem/MultiItemYR.java:89-146
+//
+// (what follows describes kind 0, for which the engine was written; the other two plug their lambdas into it)
 //
 // State (period, x1, x2, preQ1, preQ2, cash): the cash balance is NOT quantised (MultiProductLeadtime.java:219 is
 // commented out), so the state space is not a grid and the dense kernels of sdpb200.cu do not apply -- this is the
@@ -48,6 +54,8 @@ struct MLKeyEq {
 };
 
 struct MLParams {
+    int kind;  // sdpb_reached_kind
+    double dr; // depositeRate of the XR / YR lambdas
     int T, Q, nD;
     double price1, price2, v1, v2, sal1, sal2;
     double r0, r1, r2, limit, interest_free;
@@ -118,22 +126,6 @@ __device__ __forceinline__ MLState ml_transition(const MLParams& P, const MLStat
     return n;
 }
 
-// F_{t+1} candidates: one entry per (state, action, demand)
-__global__ void ml_expand(MLParams P, int t, const MLKey* __restrict__ F, long long nF, MLKey* __restrict__ out) {
-    const long long A = (long long)P.Q * P.Q;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= nF * A) return;
-    const long long si = gid / A;
-    const int ai = (int)(gid - si * A);
-    const int a1 = ai / P.Q, a2 = ai - a1 * P.Q;
-    const MLState s = ml_state(F[si]);
-    for (int j = 0; j < P.nD; j++) {
-        const int d1 = (int)P.d1[(t - 1) * P.nD + j], d2 = (int)P.d2[(t - 1) * P.nD + j];
-        const double c = ml_immediate(P, t, false, s, a1, a2, d1, d2);
-        out[gid * P.nD + j] = ml_key(ml_transition(P, s, a1, a2, d1, d2, c));
-    }
-}
-
 __device__ __forceinline__ long long ml_find(const MLKey* __restrict__ F, long long n, const MLKey& k) {
     long long lo = 0, hi = n;
     while (lo < hi) {
@@ -144,17 +136,131 @@ __device__ __forceinline__ long long ml_find(const MLKey* __restrict__ F, long l
     return lo;  // the key is present by construction
 }
 
-// Q(s, a) = sum_j [ p_j c + (p_j gamma) V_{t+1}(f) ]   (CashRecursionMultiLead.java:74-80)
-__device__ __forceinline__ double ml_action_value(const MLParams& P, int t, bool last, const MLState& s, int a1, int a2,
+// ---- kind 1: MultiItemCashXR.java:87-126 ----
+__device__ __forceinline__ double xr_immediate(const MLParams& P, bool last, const MLState& s, double action1, double action2,
+                                               double demand1, double demand2) {
+    const double endInventory1 = jmax0(action1 - demand1);
+    const double endInventory2 = jmax0(action2 - demand2);
+    const double revenue1 = P.price1 * (action1 - endInventory1);
+    const double revenue2 = P.price2 * (action2 - endInventory2);
+    const double revenue = revenue1 + revenue2;
+    const double initialCash = (s.cash - P.v1 * (double)s.x1) - P.v2 * (double)s.x2;
+    const double orderingCostsY = P.v1 * action1 + P.v2 * action2;
+    double salValue = 0.0;
+    if (last) salValue = P.sal1 * endInventory1 + P.sal2 * endInventory2;
+    return ((revenue + (1.0 - P.dr) * (s.cash - orderingCostsY)) + salValue) - initialCash;
+}
+
+__device__ __forceinline__ MLState xr_transition(const MLParams& P, const MLState& s, double a1, double a2, double d1, double d2,
+                                                 double c) {
+    double e1 = jmax0(a1 - d1), e2 = jmax0(a2 - d2);
+    const double initialCash = (s.cash - P.v1 * (double)s.x1) - P.v2 * (double)s.x2;
+    double nextCash = initialCash + c;
+    nextCash = nextCash > P.max_cash ? P.max_cash : nextCash;
+    nextCash = nextCash < P.min_cash ? P.min_cash : nextCash;
+    e1 = e1 > P.max_inv ? P.max_inv : e1;
+    e2 = e2 < P.min_inv ? P.min_inv : e2;
+    nextCash = (double)(int)nextCash;
+    MLState n;
+    n.x1 = (int)e1; n.x2 = (int)e2; n.q1 = 0; n.q2 = 0;
+    n.cash = (nextCash + P.v1 * (double)n.x1) + P.v2 * (double)n.x2;  // nextR
+    return n;
+}
+
+// ---- kind 2: MultiItemYR.java:122-146 (Math.round(x * 10) / 10 is a LONG division) ----
+__device__ __forceinline__ long long ml_jround(double x) {
+    const double r = floor(x);
+    return (long long)r + ((x - r) >= 0.5 ? 1ll : 0ll);
+}
+
+__device__ __forceinline__ MLState yr_transition(const MLParams& P, double y1, double y2, double iniR, double d1, double d2) {
+    double e1 = jmax0(y1 - d1), e2 = jmax0(y2 - d2);
+    const double revenue1 = P.price1 * jmin(y1, d1);
+    const double revenue2 = P.price2 * jmin(y2, d2);
+    double nextW = (revenue1 + revenue2) + (1.0 + P.dr) * ((iniR - P.v1 * y1) - P.v2 * y2);
+    e1 = (double)(ml_jround(e1 * 10.0) / 10);
+    e2 = (double)(ml_jround(e2 * 10.0) / 10);
+    nextW = (double)(ml_jround(nextW * 10.0) / 10);
+    nextW = nextW > P.max_cash ? P.max_cash : nextW;
+    nextW = nextW < P.min_cash ? P.min_cash : nextW;
+    e1 = e1 > P.max_inv ? P.max_inv : e1;
+    e2 = e2 < P.min_inv ? P.min_inv : e2;
+    MLState n;
+    n.x1 = (int)e1; n.x2 = (int)e2; n.q1 = 0; n.q2 = 0; n.cash = nextW;
+    return n;
+}
+
+// the action with flat index ai of state s: its two components as the lambdas see them, and whether the reference's
+// action list contains it (kind 2: `v1 * i + v2 * j < iniR + 0.1`, MultiItemYR.java:104-108)
+__device__ __forceinline__ bool ml_action(const MLParams& P, const MLState& s, int ai, double& a1, double& a2) {
+    const int i = ai / P.Q, j = ai - i * P.Q;
+    if (P.kind == 0) { a1 = (double)i; a2 = (double)j; return true; }
+    a1 = (double)(s.x1 + i); a2 = (double)(s.x2 + j);  // order-up-to levels from (int) x
+    if (P.kind == 1) return true;
+    const double iniR = (s.cash + P.v1 * (double)s.x1) + P.v2 * (double)s.x2;
+    return P.v1 * a1 + P.v2 * a2 < iniR + 0.1;
+}
+
+__device__ __forceinline__ MLState ml_successor(const MLParams& P, int t, const MLState& s, double a1, double a2, int j,
+                                                double* c_out) {
+    const double d1 = P.d1[(t - 1) * P.nD + j], d2 = P.d2[(t - 1) * P.nD + j];
+    if (P.kind == 0) {
+        const double c = ml_immediate(P, t, false, s, (int)a1, (int)a2, (int)d1, (int)d2);
+        if (c_out) *c_out = c;
+        return ml_transition(P, s, (int)a1, (int)a2, (int)d1, (int)d2, c);
+    }
+    if (P.kind == 1) {
+        const double c = xr_immediate(P, false, s, a1, a2, d1, d2);
+        if (c_out) *c_out = c;
+        return xr_transition(P, s, a1, a2, d1, d2, c);
+    }
+    const double iniR = (s.cash + P.v1 * (double)s.x1) + P.v2 * (double)s.x2;
+    return yr_transition(P, a1, a2, iniR, d1, d2);
+}
+
+// F_{t+1} candidates: one entry per (state, action, demand)
+__global__ void ml_expand(MLParams P, int t, const MLKey* __restrict__ F, long long nF, MLKey* __restrict__ out) {
+    const long long A = (long long)P.Q * P.Q;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nF * A) return;
+    const long long si = gid / A;
+    const int ai = (int)(gid - si * A);
+    const MLState s = ml_state(F[si]);
+    double a1, a2;
+    const bool feasible = ml_action(P, s, ai, a1, a2);
+    // an action the reference's list does not contain reaches nothing: its slots repeat the state's first successor
+    // under a listed action... there may be none, so they are filled with an all-ones key that unique() folds into
+    // one entry and the caller drops
+    for (int j = 0; j < P.nD; j++) {
+        MLKey k;
+        if (feasible) k = ml_key(ml_successor(P, t, s, a1, a2, j, nullptr));
+        else { k.a = ~0ull; k.b = ~0ull; }
+        out[gid * P.nD + j] = k;
+    }
+}
+
+// Q(s, a): kinds 0, 1: sum_j [ p_j c + (p_j gamma) V_{t+1}(f) ] (CashRecursionMultiLead.java:74-80,
+// CashRecursionMultiXR.java:78-85); kind 2: sum_j p_j V_{t+1}(f) with V_{T+1} = boundFinalCash (CashRecursionV.java:88-97,125-128)
+__device__ __forceinline__ double ml_action_value(const MLParams& P, int t, bool last, const MLState& s, double a1, double a2,
                                                   const MLKey* __restrict__ Fn, const double* __restrict__ Vn, long long nFn) {
     double q = 0.0;
     for (int j = 0; j < P.nD; j++) {
-        const int d1 = (int)P.d1[(t - 1) * P.nD + j], d2 = (int)P.d2[(t - 1) * P.nD + j];
-        const double c = ml_immediate(P, t, last, s, a1, a2, d1, d2);
-        q += P.p[(t - 1) * P.nD + j] * c;
+        const double pj = P.p[(t - 1) * P.nD + j];
+        if (P.kind == 2) {
+            const MLState n = ml_successor(P, t, s, a1, a2, j, nullptr);
+            const double vn = last ? (n.cash + P.sal1 * (double)n.x1) + P.sal2 * (double)n.x2   // MultiItemYR.java:116-119
+                                   : Vn[ml_find(Fn, nFn, ml_key(n))];
+            q += pj * vn;
+            continue;
+        }
+        const double d1 = P.d1[(t - 1) * P.nD + j], d2 = P.d2[(t - 1) * P.nD + j];
+        const double c = P.kind == 0 ? ml_immediate(P, t, last, s, (int)a1, (int)a2, (int)d1, (int)d2)
+                                     : xr_immediate(P, last, s, a1, a2, d1, d2);
+        q += pj * c;
         if (!last) {
-            const MLKey k = ml_key(ml_transition(P, s, a1, a2, d1, d2, c));
-            q += P.pg[(t - 1) * P.nD + j] * Vn[ml_find(Fn, nFn, k)];
+            const MLState n = P.kind == 0 ? ml_transition(P, s, (int)a1, (int)a2, (int)d1, (int)d2, c)
+                                          : xr_transition(P, s, a1, a2, d1, d2, c);
+            q += P.pg[(t - 1) * P.nD + j] * Vn[ml_find(Fn, nFn, ml_key(n))];
         }
     }
     return q;
@@ -168,12 +274,14 @@ __global__ void ml_backward_state(MLParams P, int t, const MLKey* __restrict__ F
     const MLState s = ml_state(F[si]);
     const bool last = t == P.T;
     double val = -DBL_MAX;
-    int best = 0;  // bestActions = new Actions(0, 0)
-    for (int a1 = 0; a1 < P.Q; a1++)
-        for (int a2 = 0; a2 < P.Q; a2++) {
-            const double q = ml_action_value(P, t, last, s, a1, a2, Fn, Vn, nFn);
-            if (q > val + P.tie) { val = q; best = a1 * P.Q + a2; }
-        }
+    int best = 0;  // bestActions = new Actions(0, 0); kind 2: bestYs = (x1, x2) = offsets (0, 0) as well
+    const int A = P.Q * P.Q;
+    for (int ai = 0; ai < A; ai++) {
+        double a1, a2;
+        if (!ml_action(P, s, ai, a1, a2)) continue;
+        const double q = ml_action_value(P, t, last, s, a1, a2, Fn, Vn, nFn);
+        if (q > val + P.tie) { val = q; best = ai; }
+    }
     V[si] = val;
     Qa[si] = best;
 }
@@ -186,7 +294,10 @@ __global__ void ml_backward_pairs(MLParams P, int t, const MLKey* __restrict__ F
     if (gid >= nF * A) return;
     const long long si = gid / A;
     const int ai = (int)(gid - si * A);
-    QV[gid] = ml_action_value(P, t, t == P.T, ml_state(F[si]), ai / P.Q, ai % P.Q, Fn, Vn, nFn);
+    const MLState s = ml_state(F[si]);
+    double a1, a2;
+    // an action that is not in the reference's list can never be accepted: NaN fails `q > val + tie`
+    QV[gid] = ml_action(P, s, ai, a1, a2) ? ml_action_value(P, t, t == P.T, s, a1, a2, Fn, Vn, nFn) : __longlong_as_double(0x7ff8000000000000ll);
 }
 
 // ... then the serial scan per state
@@ -210,16 +321,19 @@ thread_local std::string g_ml_error;
 
 extern "C" {
 
-const char* sdpb_multilead_last_error(void) { return g_ml_error.c_str(); }
+const char* sdpb_reached_last_error(void) { return g_ml_error.c_str(); }
 
-int sdpb_multilead_solve(const sdpb_multilead_model* m, int device, const double* init_state, double* value, int32_t* action1,
-                         int32_t* action2, int64_t* n_states, double* solve_ms) {
+int sdpb_reached_solve(const sdpb_reached_model* m, int device, const double* init_state, double* value, double* action1,
+                       double* action2, int64_t* n_states, double* solve_ms) {
     g_ml_error.clear();
     auto fail = [&](int rc, const std::string& msg) { g_ml_error = msg; return rc; };
-    if (!m || !init_state || m->struct_size != sizeof(sdpb_multilead_model)) return fail(SDPB_ERR_ARG, "bad argument / struct_size");
+    if (!m || !init_state || m->struct_size != sizeof(sdpb_reached_model)) return fail(SDPB_ERR_ARG, "bad argument / struct_size");
+    if (m->kind < SDPB_REACHED_MULTILEAD || m->kind > SDPB_REACHED_MULTI_YR) return fail(SDPB_ERR_ARG, "bad kind");
     if (m->T < 1 || m->q_bound < 1 || m->q_bound > 65535 || m->n_demands < 1 || !m->d1 || !m->d2 || !m->p || !m->overhead_t)
         return fail(SDPB_ERR_ARG, "T, q_bound, n_demands must be positive and the tables non-null");
-    for (int k = 0; k < 4; k++)
+    // init_state: kind 0 (x1, x2, preQ1, preQ2, cash); kind 1 (x1, x2, R); kind 2 (x1, x2, cash)
+    const int n_int = m->kind == SDPB_REACHED_MULTILEAD ? 4 : 2;
+    for (int k = 0; k < n_int; k++)
         if (init_state[k] != (double)(int)init_state[k] || init_state[k] < 0 || init_state[k] > 65535)
             return fail(SDPB_ERR_OFFGRID, "initial inventories and pipeline quantities must be integers in [0, 65535]");
     if (!(m->max_inv <= 65535.0)) return fail(SDPB_ERR_ARG, "max_inv must fit 16 bits");
@@ -258,6 +372,7 @@ int sdpb_multilead_solve(const sdpb_multilead_model* m, int device, const double
         return p;
     };
     MLParams P;
+    P.kind = m->kind; P.dr = m->deposit_rate;
     P.T = T; P.Q = m->q_bound; P.nD = nD;
     P.price1 = m->price[0]; P.price2 = m->price[1]; P.v1 = m->vari_cost[0]; P.v2 = m->vari_cost[1];
     P.sal1 = m->salvage[0]; P.sal2 = m->salvage[1];
@@ -275,8 +390,9 @@ int sdpb_multilead_solve(const sdpb_multilead_model* m, int device, const double
     std::vector<MLKey*> F(T, nullptr);
     std::vector<long long> nF(T, 0);
     MLState s0;
-    s0.x1 = (int)init_state[0]; s0.x2 = (int)init_state[1]; s0.q1 = (int)init_state[2]; s0.q2 = (int)init_state[3];
-    s0.cash = init_state[4];
+    s0.x1 = (int)init_state[0]; s0.x2 = (int)init_state[1];
+    s0.q1 = n_int == 4 ? (int)init_state[2] : 0; s0.q2 = n_int == 4 ? (int)init_state[3] : 0;
+    s0.cash = init_state[n_int];
     const MLKey k0 = ml_key(s0);
     F[0] = (MLKey*)dalloc(sizeof(MLKey));
     if (!F[0]) { cleanup(); return fail(SDPB_ERR_NOMEM, "allocation failed"); }
@@ -298,6 +414,12 @@ int sdpb_multilead_solve(const sdpb_multilead_model* m, int device, const double
             thrust::sort(thrust::cuda::par.on(stream), buf, buf + cand, MLKeyLess());
             MLKey* end = thrust::unique(thrust::cuda::par.on(stream), buf, buf + cand, MLKeyEq());
             nF[t] = (long long)(end - buf);
+            if (nF[t] > 0) {  // the slots of actions the reference's list does not contain sort last, as one key
+                MLKey tail;
+                if (cudaMemcpyAsync(&tail, buf + nF[t] - 1, sizeof tail, cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+                    cudaStreamSynchronize(stream) == cudaSuccess && tail.a == ~0ull && tail.b == ~0ull)
+                    nF[t]--;
+            }
         } catch (const std::exception& ex) {
             const std::string msg = std::string("sort / unique: ") + ex.what();
             cleanup();
@@ -338,8 +460,12 @@ int sdpb_multilead_solve(const sdpb_multilead_model* m, int device, const double
     cudaEventElapsedTime(&ms, e0, e1);
 #undef ML_CU
     if (value) *value = v0;
-    if (action1) *action1 = a0 / m->q_bound;
-    if (action2) *action2 = a0 % m->q_bound;
+    // kind 0: order quantities (i, j); kinds 1, 2: order-up-to levels (x1 + i, x2 + j) (bestYs; the reference's default
+    // for a state without any accepted action is {0, 0} for kind 1 and (x1, x2) for kind 2)
+    const int ai = a0 / m->q_bound, aj = a0 % m->q_bound;
+    const bool none = v0 == -DBL_MAX;
+    if (action1) *action1 = m->kind == SDPB_REACHED_MULTILEAD ? ai : (m->kind == SDPB_REACHED_MULTI_XR && none ? 0.0 : s0.x1 + ai);
+    if (action2) *action2 = m->kind == SDPB_REACHED_MULTILEAD ? aj : (m->kind == SDPB_REACHED_MULTI_XR && none ? 0.0 : s0.x2 + aj);
     if (n_states) for (int t = 0; t < T; t++) n_states[t] = nF[t];
     if (solve_ms) *solve_ms = ms;
     cleanup();

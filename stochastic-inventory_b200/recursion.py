@@ -421,16 +421,15 @@ class CashStateMultiLead:
         return (self.iniInventory1, self.iniInventory2, self.preQ1, self.preQ2, self.iniCash)
 
 
-class CashRecursionMultiLead:
-    """new CashRecursionMultiLead(discountFactor, PmfMulti, buildActionList, stateTransition, immediateValue, T)
-    (src/sdp/cash/multiItem/CashRecursionMultiLead.java:28-95) for the lambdas of
-    src/cash/overdraft/MultiProductLeadtime.java:150-224: two products, lead time 1, overdraft interest, a cash balance
-    that is NOT quantised -- no grid, so the library enumerates the states the recursion reaches
-    (sdpb_multilead_solve).  `pmf`: per period an array [D, 3] of (demand1, demand2, prob) as GetPmfMulti.getPmf returns."""
+class _ReachedEngine:
+    """The two-product engines whose states do not live on a grid: solved over the states the reference's recursion
+    reaches from the queried period-1 state (sdpb_reached_solve).  `pmf`: per period an array [D, 3] of
+    (demand1, demand2, prob) as GetPmfMulti.getPmf returns."""
+    kind = A.REACHED_MULTILEAD
 
-    def __init__(self, pmf, price=(5.0, 10.0), variCost=(1.0, 2.0), salValueUnit=None, overheadCost=None, r0=0.0, r1=0.1,
-                 r2=2.0, limit=500.0, interestFreeAmount=0.0, Qbound=50, minInventoryState=0.0, maxInventoryState=200.0,
-                 minCashState=-500.0, maxCashState=5000.0, discountFactor=1.0, tieTolerance=0.1, device: int = -1):
+    def _setup(self, pmf, price, variCost, salvage, overheadCost, Qbound, minInventoryState, maxInventoryState,
+               minCashState, maxCashState, discountFactor, tieTolerance, device, depositeRate=0.0, r0=0.0, r1=0.0, r2=0.0,
+               limit=0.0, interestFreeAmount=0.0):
         self.lib = A.load()
         T = len(pmf)
         nD = len(pmf[0])
@@ -440,18 +439,18 @@ class CashRecursionMultiLead:
         self._d1 = np.ascontiguousarray(tab[:, :, 0]).ravel()
         self._d2 = np.ascontiguousarray(tab[:, :, 1]).ravel()
         self._p = np.ascontiguousarray(tab[:, :, 2]).ravel()
-        self._ovh = np.ascontiguousarray(overheadCost if overheadCost is not None else [100.0] * T, dtype=np.float64)
-        sal = salValueUnit if salValueUnit is not None else (variCost[0] * 0.5, variCost[1] * 0.5)
-        m = A.SdpbMultileadModel()
-        m.struct_size = C.sizeof(A.SdpbMultileadModel)
-        m.T, m.q_bound, m.n_demands = T, int(Qbound), nD
+        self._ovh = np.ascontiguousarray(overheadCost if overheadCost is not None else [0.0] * T, dtype=np.float64)
+        m = A.SdpbReachedModel()
+        m.struct_size = C.sizeof(A.SdpbReachedModel)
+        m.kind, m.T, m.q_bound, m.n_demands = self.kind, T, int(Qbound), nD
         dp = C.POINTER(C.c_double)
         m.d1, m.d2, m.p = self._d1.ctypes.data_as(dp), self._d2.ctypes.data_as(dp), self._p.ctypes.data_as(dp)
         m.overhead_t = self._ovh.ctypes.data_as(dp)
         m.price[0], m.price[1] = price
         m.vari_cost[0], m.vari_cost[1] = variCost
-        m.salvage[0], m.salvage[1] = sal
+        m.salvage[0], m.salvage[1] = salvage
         m.r0, m.r1, m.r2, m.limit, m.interest_free = r0, r1, r2, limit, interestFreeAmount
+        m.deposit_rate = depositeRate
         m.min_inv, m.max_inv, m.min_cash, m.max_cash = minInventoryState, maxInventoryState, minCashState, maxCashState
         m.gamma, m.tie_tolerance = discountFactor, tieTolerance
         self._m, self.T, self.device = m, T, device
@@ -465,24 +464,97 @@ class CashRecursionMultiLead:
         key = state._vec()
         if key not in self._solved:
             st = np.ascontiguousarray(key, dtype=np.float64)
-            v, ms = C.c_double(), C.c_double()
-            a1, a2 = C.c_int32(), C.c_int32()
+            v, ms, a1, a2 = C.c_double(), C.c_double(), C.c_double(), C.c_double()
             ns = (C.c_int64 * self.T)()
-            rc = self.lib.sdpb_multilead_solve(C.byref(self._m), self.device, st.ctypes.data_as(C.POINTER(C.c_double)),
-                                               C.byref(v), C.byref(a1), C.byref(a2), ns, C.byref(ms))
+            rc = self.lib.sdpb_reached_solve(C.byref(self._m), self.device, st.ctypes.data_as(C.POINTER(C.c_double)),
+                                             C.byref(v), C.byref(a1), C.byref(a2), ns, C.byref(ms))
             if rc != A.SDPB_OK:
-                raise A.SdpbError(rc, self.lib.sdpb_multilead_last_error().decode())
-            self._solved[key] = (v.value, Actions(a1.value, a2.value))
+                raise A.SdpbError(rc, self.lib.sdpb_reached_last_error().decode())
+            self._solved[key] = (v.value, (a1.value, a2.value))
             self.n_states, self.solve_ms = list(ns), ms.value
         return self._solved[key]
 
     def getExpectedValue(self, state):
         return self._solve(state)[0]
 
-    def getAction(self, state):
+    def _action(self, state):
         if state._vec() not in self._solved:
             raise KeyError("getAction on a state that was never solved")
         return self._solved[state._vec()][1]
+
+
+class CashRecursionMultiLead(_ReachedEngine):
+    """new CashRecursionMultiLead(discountFactor, PmfMulti, buildActionList, stateTransition, immediateValue, T)
+    (src/sdp/cash/multiItem/CashRecursionMultiLead.java:28-95) for the lambdas of
+    src/cash/overdraft/MultiProductLeadtime.java:150-224: two products, lead time 1, overdraft interest, a cash balance
+    that is NOT quantised."""
+    kind = A.REACHED_MULTILEAD
+
+    def __init__(self, pmf, price=(5.0, 10.0), variCost=(1.0, 2.0), salValueUnit=None, overheadCost=None, r0=0.0, r1=0.1,
+                 r2=2.0, limit=500.0, interestFreeAmount=0.0, Qbound=50, minInventoryState=0.0, maxInventoryState=200.0,
+                 minCashState=-500.0, maxCashState=5000.0, discountFactor=1.0, tieTolerance=0.1, device: int = -1):
+        sal = salValueUnit if salValueUnit is not None else (variCost[0] * 0.5, variCost[1] * 0.5)
+        self._setup(pmf, price, variCost, sal, overheadCost if overheadCost is not None else [100.0] * len(pmf), Qbound,
+                    minInventoryState, maxInventoryState, minCashState, maxCashState, discountFactor, tieTolerance, device,
+                    r0=r0, r1=r1, r2=r2, limit=limit, interestFreeAmount=interestFreeAmount)
+
+    def getAction(self, state):
+        a = self._action(state)
+        return Actions(int(a[0]), int(a[1]))
+
+
+class CashStateMultiXR:
+    """src/sdp/cash/multiItem/CashStateMultiXR.java: (period, iniInventory1, iniInventory2, iniR)."""
+
+    def __init__(self, period, iniInventory1, iniInventory2, iniR):
+        self.period = int(period)
+        self.iniInventory1, self.iniInventory2, self.iniR = float(iniInventory1), float(iniInventory2), float(iniR)
+
+    def getPeriod(self):
+        return self.period
+
+    def _vec(self):
+        return (self.iniInventory1, self.iniInventory2, self.iniR)
+
+
+class CashRecursionMultiXR(_ReachedEngine):
+    """new CashRecursionMultiXR(discountFactor, PmfMulti, buildActionList, stateTransition, immediateValue, T)
+    (src/sdp/cash/multiItem/CashRecursionMultiXR.java:39-95) for the lambdas of
+    src/cash/multiItem/MultiItemCashXR.java:73-126: state (x1, x2, R = w + v.x), actions = order-up-to pairs;
+    getAction returns the pair of order-up-to levels (double[] in the reference)."""
+    kind = A.REACHED_MULTI_XR
+
+    def __init__(self, pmf, price=(5.0, 10.0), variCost=(1.0, 2.0), salPrice=None, depositeRate=0.0, Qbound=50,
+                 minInventoryState=0.0, maxInventoryState=200.0, minCashState=0.0, maxCashState=10000.0, discountFactor=1.0,
+                 tieTolerance=0.1, device: int = -1):
+        sal = salPrice if salPrice is not None else (variCost[0] * 0.5, variCost[1] * 0.5)
+        self._setup(pmf, price, variCost, sal, None, Qbound, minInventoryState, maxInventoryState, minCashState,
+                    maxCashState, discountFactor, tieTolerance, device, depositeRate=depositeRate)
+
+    def getAction(self, state):
+        return list(self._action(state))
+
+
+class CashRecursionV(_ReachedEngine):
+    """new CashRecursionV(discountFactor, PmfMulti, buildActionListV, buildActionListPai, stateTransition,
+    boundFinalCash, T, variCost) (src/sdp/cash/multiItem/CashRecursionV.java:47-131) for the lambdas of
+    src/cash/multiItem/MultiItemYR.java:89-146: V(x1, x2, w) = max over affordable order-up-to pairs of
+    Pi(y1, y2, R) = E V_{t+1}; the states of period T+1 are valued by the boundary function
+    boundFinalCash(s) = w + salPrice . x (FinalCash.BoundaryFuncton).  State: CashStateMulti."""
+    kind = A.REACHED_MULTI_YR
+
+    def __init__(self, pmf, price=(5.0, 10.0), variCost=(1.0, 2.0), salPrice=None, depositeRate=0.0, Qbound=50,
+                 minInventoryState=0.0, maxInventoryState=200.0, minCashState=0.0, maxCashState=10000.0, discountFactor=1.0,
+                 tieTolerance=0.01, device: int = -1):
+        sal = salPrice if salPrice is not None else (variCost[0] * 0.5, variCost[1] * 0.5)
+        self._setup(pmf, price, variCost, sal, None, Qbound, minInventoryState, maxInventoryState, minCashState,
+                    maxCashState, discountFactor, tieTolerance, device, depositeRate=depositeRate)
+
+    def getExpectedValueV(self, state):
+        return self.getExpectedValue(state)
+
+    def getAction(self, state):
+        return list(self._action(state))
 
 
 # ---- workforce ------------------------------------------------------------------------------

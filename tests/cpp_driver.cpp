@@ -96,14 +96,16 @@ int main(int argc, char** argv) {
             Model model = Model::inventory(OptDirection::MIN, pmf, 500, 0, 2, 10, 60, -120, 200, 1);
             Recursion sharded(model, std::vector<int>{0, 0, 0});
             State initialState{1, 0};
-            std::printf("G %.17g %.17g\n", sharded.getExpectedValue(initialState), sharded.getAction(initialState));
+            const double shardedValue = sharded.getExpectedValue(initialState);   // (argument evaluation order is unspecified)
+            std::printf("G %.17g %.17g\n", shardedValue, sharded.getAction(initialState));
             // FinalCash.BoundaryFuncton: leftover stock is worth 0.75 a unit, a backorder costs 2.5 (CashRecursionV.java:125-128 form)
             std::vector<double> boundFinalCash;
             for (int x = -120; x <= 200; x++) boundFinalCash.push_back(-0.75 * std::max(x, 0) + 2.5 * std::max(-x, 0));
             Model withBoundary(model);
             withBoundary.boundFinalCash(boundFinalCash);
             Recursion bounded(withBoundary);
-            std::printf("H %.17g %.17g\n", bounded.getExpectedValue(initialState), bounded.getAction(initialState));
+            const double boundedValue = bounded.getExpectedValue(initialState);
+            std::printf("H %.17g %.17g\n", boundedValue, bounded.getAction(initialState));
             // Leadtime.java:63-67 with the grid sized by sdpb_reachable_hull
             double meanB[] = {4, 6, 5};
             std::vector<PoissonDist> distB;
@@ -112,7 +114,8 @@ int main(int argc, char** argv) {
             lead.reachableHull({0, 0});
             LeadtimeRecursion hull(lead);
             LeadtimeState s0{1, 0, 0};
-            std::printf("I %.17g %.17g %.17g %.17g\n", hull.getExpectedValue(s0), hull.getAction(s0), lead.m.inv_min, lead.m.inv_max);
+            const double hullValue = hull.getExpectedValue(s0);
+            std::printf("I %.17g %.17g %.17g %.17g\n", hullValue, hull.getAction(s0), lead.m.inv_min, lead.m.inv_max);
         }
     } catch (const SdpbError& e) {
         std::fprintf(stderr, "%s\n", e.what());

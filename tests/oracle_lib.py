@@ -34,6 +34,8 @@ def load():
     lib.oracle_step_states.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int64), C.c_int, dp, dp]
     lib.oracle_multi_lead.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, dp, ip, ip,
                                       C.POINTER(C.c_int64)]
+    lib.oracle_reached.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, C.c_double, C.c_double,
+                                   C.c_double, C.c_double, C.c_double, C.c_double, dp, dp, dp, dp, C.POINTER(C.c_int64)]
     lib.oracle_simulate.argtypes = [vp, dp, dp, dp, C.c_int, C.c_double, dp]
     lib.oracle_eval.argtypes = [vp, C.c_int, dp, C.c_double, C.c_double, dp, dp]
     lib.oracle_index.argtypes = [vp, dp]
@@ -137,3 +139,18 @@ def n_actions(spec, period, state):
     m = spec.to_struct()
     st = np.ascontiguousarray(state, dtype=np.float64)
     return lib.oracle_n_actions(C.byref(m), period, _dp(st))
+
+
+def reached(kind, pmf, q_bound, price, vari_cost, salvage, init, deposit_rate=0.0, min_inv=0.0, max_inv=200.0, min_cash=0.0,
+            max_cash=10000.0, gamma=1.0):
+    """CashRecursionMultiXR (kind 1) / CashRecursionV (kind 2) through the oracle's literal top-down restatement
+    -> (value, action1, action2, visited states)."""
+    lib = load()
+    tab = np.stack([np.asarray(r, dtype=np.float64) for r in pmf])
+    d1, d2, p = (np.ascontiguousarray(tab[:, :, k]).ravel() for k in range(3))
+    arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (price, vari_cost, salvage, init)]
+    v, a1, a2, ns = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+    lib.oracle_reached(kind, tab.shape[0], q_bound, tab.shape[1], _dp(d1), _dp(d2), _dp(p), _dp(arrs[0]), _dp(arrs[1]),
+                       _dp(arrs[2]), deposit_rate, min_inv, max_inv, min_cash, max_cash, gamma, _dp(arrs[3]),
+                       C.byref(v), C.byref(a1), C.byref(a2), C.byref(ns))
+    return v.value, a1.value, a2.value, ns.value

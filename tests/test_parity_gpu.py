@@ -1089,6 +1089,35 @@ def test_multilead_matches_oracle(T, qb, ovh, S, oracle):
     assert sum(rec.n_states) == ns
 
 
+@pytest.mark.parametrize("T,qb,cash", [(2, 8, 0.0), (2, 12, 25.0), (3, 5, 10.0), (1, 10, 30.0)])
+def test_multi_xr_matches_oracle(T, qb, cash, S, oracle):
+    """CashRecursionMultiXR with the MultiItemCashXR.java lambdas (Poisson demand through GetPmfMulti, `(int)` casts,
+    state (x1, x2, R)) over the reached states: value, first-period order-up-to levels and the number of visited states
+    equal the oracle's literal top-down recursion."""
+    pmf = S.GetPmfMulti([[S.PoissonDist(4)] * T, [S.PoissonDist(3)] * T], 0.99, 1).tables()
+    rec = S.CashRecursionMultiXR(pmf, price=(5, 10), variCost=(1, 2), Qbound=qb, maxInventoryState=40, maxCashState=500)
+    st = S.CashStateMultiXR(1, 0, 0, cash)
+    v = rec.getExpectedValue(st)
+    vo, a1, a2, ns = oracle.reached(1, pmf, qb, (5, 10), (1, 2), (0.5, 1.0), [0, 0, cash], max_inv=40, max_cash=500)
+    assert v == vo and rec.getAction(st) == [a1, a2]
+    assert sum(rec.n_states) == ns
+
+
+@pytest.mark.parametrize("T,qb,cash,dr", [(2, 8, 10.0, 0.0), (2, 12, 25.0, 0.05), (3, 5, 14.0, 0.0), (1, 10, 30.0, 0.0)])
+def test_cash_recursion_v_matches_oracle(T, qb, cash, dr, S, oracle):
+    """CashRecursionV (V / Pi form, the boundary function boundFinalCash valuing the states of period T+1, affordable
+    order-up-to pairs, `> val + 0.01`) with the MultiItemYR.java lambdas, over the reached states."""
+    pmf = S.GetPmfMulti([[S.PoissonDist(4)] * T, [S.PoissonDist(3)] * T], 0.99, 1).tables()
+    rec = S.CashRecursionV(pmf, price=(5, 10), variCost=(1, 2), depositeRate=dr, Qbound=qb, maxInventoryState=40,
+                           maxCashState=500)
+    st = S.CashStateMulti(1, 0, 0, cash)
+    v = rec.getExpectedValueV(st)
+    vo, a1, a2, ns = oracle.reached(2, pmf, qb, (5, 10), (1, 2), (0.5, 1.0), [0, 0, cash], deposit_rate=dr, max_inv=40,
+                                    max_cash=500)
+    assert v == vo and rec.getAction(st) == [a1, a2]
+    assert sum(rec.n_states) == ns
+
+
 def test_multilead_reference_record_T3(S):
     """src/cash/overdraft/MultiProductLeadtime.java:45-50 -- the live code of the reference: 3 periods, demands
     {10,30} x {5,15}: 'final optimal cash is -76.56 ... Q1 = 30, Q2 = 15 ... running time is 1568.0s'.  1.7e7 states and
