@@ -392,7 +392,7 @@ def next_rows(S, device):
                               "reference_record": "final optimal cash is -76.56, Q1 = 30, Q2 = 15, running time is 1568.0s "
                                                   "(src/cash/overdraft/MultiProductLeadtime.java:45-50)",
                               "matches_reference_record": bool(val == -76.56 and act.getFirstAction() == 30 and act.getSecondAction() == 15),
-                              "what": "CashRecursionMultiLead + MultiProductLeadtime.java:150-224 lambdas through sdpb_multilead_solve: "
+                              "what": "CashRecursionMultiLead + MultiProductLeadtime.java:150-224 lambdas through sdpb_reached_solve: "
                                       "forward enumeration of the reached states (expand, sort, unique), backward induction with "
                                       "binary-search successor lookup"}
     sp = S.workforce_model([0.5, 0.5, 0.5])

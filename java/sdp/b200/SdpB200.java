@@ -61,6 +61,20 @@ public final class SdpB200 {
             JAVA_INT.withName("n_actions"), JAVA_INT.withName("T"), JAVA_LONG.withName("cash_k_min"),
             JAVA_LONG.withName("window_lo"), JAVA_LONG.withName("window_hi"), JAVA_LONG.withName("device_bytes"));
 
+    /** struct sdpb_reached_model, field for field (price / vari_cost / salvage are double[2]). */
+    public static final StructLayout REACHED_MODEL = MemoryLayout.structLayout(
+            JAVA_INT.withName("struct_size"), JAVA_INT.withName("kind"), JAVA_INT.withName("T"), JAVA_INT.withName("q_bound"),
+            JAVA_INT.withName("n_demands"), JAVA_INT.withName("reserved"),
+            ADDRESS.withName("d1"), ADDRESS.withName("d2"), ADDRESS.withName("p"), ADDRESS.withName("overhead_t"),
+            MemoryLayout.sequenceLayout(2, JAVA_DOUBLE).withName("price"),
+            MemoryLayout.sequenceLayout(2, JAVA_DOUBLE).withName("vari_cost"),
+            MemoryLayout.sequenceLayout(2, JAVA_DOUBLE).withName("salvage"),
+            JAVA_DOUBLE.withName("r0"), JAVA_DOUBLE.withName("r1"), JAVA_DOUBLE.withName("r2"), JAVA_DOUBLE.withName("limit"),
+            JAVA_DOUBLE.withName("interest_free"), JAVA_DOUBLE.withName("deposit_rate"),
+            JAVA_DOUBLE.withName("min_inv"), JAVA_DOUBLE.withName("max_inv"), JAVA_DOUBLE.withName("min_cash"),
+            JAVA_DOUBLE.withName("max_cash"), JAVA_DOUBLE.withName("gamma"), JAVA_DOUBLE.withName("tie_tolerance"));
+    public static final int REACHED_MULTILEAD = 0, REACHED_MULTI_XR = 1, REACHED_MULTI_YR = 2;
+
     private static final Linker LINKER = Linker.nativeLinker();
     private static final SymbolLookup LIB =
             SymbolLookup.libraryLookup(System.getProperty("sdpb200.lib", "libsdpb200.so"), Arena.global());
@@ -105,6 +119,10 @@ public final class SdpB200 {
     static final MethodHandle GROUP_SHARD = fn("sdpb_group_shard", FunctionDescriptor.of(ADDRESS, ADDRESS, JAVA_INT));
     static final MethodHandle GROUP_VALUE = fn("sdpb_group_value",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    // the two-product recursions over the states they reach (CashRecursionMultiLead / MultiXR / V)
+    static final MethodHandle REACHED_SOLVE = fn("sdpb_reached_solve",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle REACHED_LAST_ERROR = fn("sdpb_reached_last_error", FunctionDescriptor.of(ADDRESS));
     static final MethodHandle GROUP_PERIOD_TABLES = fn("sdpb_group_period_tables",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
 

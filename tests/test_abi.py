@@ -131,7 +131,7 @@ def test_layout_table_is_current(tmp_path):
     committed = open(os.path.join(ROOT, "java", "LAYOUT.txt")).read()
     assert _parse_layout(now) == _parse_layout(committed), "regenerate java/LAYOUT.txt with tools/print_layout.c"
     src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
-    for struct in ("sdpb_model", "sdpb_options", "sdpb_grid", "sdpb_stats"):
+    for struct in ("sdpb_model", "sdpb_options", "sdpb_grid", "sdpb_stats", "sdpb_reached_model"):
         body = re.search(r"typedef struct " + struct + r" \{(.*?)\} " + struct + ";", src, flags=re.S).group(1)
         fields = []
         for decl in body.split(";"):
@@ -139,7 +139,7 @@ def test_layout_table_is_current(tmp_path):
             if not decl:
                 continue
             for part in decl.split(","):
-                fields.append(re.findall(r"[A-Za-z_][A-Za-z_0-9]*", part)[-1])
+                fields.append(re.findall(r"[A-Za-z_][A-Za-z_0-9]*", re.sub(r"\[[^\]]*\]", "", part))[-1])
         listed = [k.split(".")[1] for k in _parse_layout(committed) if k.startswith(struct + ".") and not k.endswith(".sizeof")]
         assert listed == fields, struct
 
@@ -147,7 +147,8 @@ def test_layout_table_is_current(tmp_path):
 def test_ctypes_binding_matches_layout_table(S):
     lay = _parse_layout(open(os.path.join(ROOT, "java", "LAYOUT.txt")).read())
     for cname, cls in (("sdpb_model", S.abi.SdpbModel), ("sdpb_options", S.abi.SdpbOptions),
-                       ("sdpb_grid", S.abi.SdpbGrid), ("sdpb_stats", S.abi.SdpbStats)):
+                       ("sdpb_grid", S.abi.SdpbGrid), ("sdpb_stats", S.abi.SdpbStats),
+                       ("sdpb_reached_model", S.abi.SdpbReachedModel)):
         assert lay[cname + ".sizeof"][0] == C.sizeof(cls)
         for fname, _ in cls._fields_:
             f = getattr(cls, fname)
@@ -160,13 +161,15 @@ def test_java_struct_layouts_match_layout_table():
     alignment rules Panama applies (natural alignment, no implicit padding -- so the C struct must need none)."""
     lay = _parse_layout(open(os.path.join(ROOT, "java", "LAYOUT.txt")).read())
     src = open(os.path.join(ROOT, "java", "sdp", "b200", "SdpB200.java")).read()
-    sizes = {"JAVA_INT": 4, "JAVA_DOUBLE": 8, "JAVA_LONG": 8, "ADDRESS": 8}
-    for jname, cname in (("MODEL", "sdpb_model"), ("OPTIONS", "sdpb_options"), ("GRID", "sdpb_grid")):
-        body = re.search(r"StructLayout " + jname + r" = MemoryLayout\.structLayout\((.*?)\);", src, flags=re.S).group(1)
-        fields = re.findall(r"(JAVA_INT|JAVA_DOUBLE|JAVA_LONG|ADDRESS)\.withName\(\"([a-zA-Z_0-9]+)\"\)", body)
+    sizes = {"JAVA_INT": 4, "JAVA_DOUBLE": 8, "JAVA_LONG": 8, "ADDRESS": 8, "JAVA_DOUBLE2": 16}
+    for jname, cname in (("MODEL", "sdpb_model"), ("OPTIONS", "sdpb_options"), ("GRID", "sdpb_grid"),
+                         ("REACHED_MODEL", "sdpb_reached_model")):
+        body = re.search(r"StructLayout " + jname + r" = MemoryLayout\.structLayout\((.*?)\);\n", src, flags=re.S).group(1)
+        body = body.replace("MemoryLayout.sequenceLayout(2, JAVA_DOUBLE)", "JAVA_DOUBLE2")
+        fields = re.findall(r"(JAVA_INT|JAVA_DOUBLE2|JAVA_DOUBLE|JAVA_LONG|ADDRESS)\.withName\(\"([a-zA-Z_0-9]+)\"\)", body)
         off = 0
         for typ, name in fields:
-            assert off % sizes[typ] == 0, f"{jname}.{name}: Panama struct layouts have no implicit padding"
+            assert off % min(sizes[typ], 8) == 0, f"{jname}.{name}: Panama struct layouts have no implicit padding"
             assert lay[f"{cname}.{name}"] == (off, sizes[typ]), (jname, name)
             off += sizes[typ]
         assert off == lay[cname + ".sizeof"][0], jname

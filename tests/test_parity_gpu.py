@@ -1060,7 +1060,7 @@ def _multi_pmf(vals1, probs1, vals2, probs2, T):
 def test_multilead_reference_record_T2(S, oracle):
     """src/cash/overdraft/MultiProductLeadtime.java:41-43, recorded by the reference's author: 'when T = 2, final
     optimal cash is -17.800000000000008, optimal order quantity in the first period is: Q1 = 40, Q2 = 20'.
-    The GPU's reached-state solve (sdpb_multilead_solve) reproduces the Java program's printed output to the last
+    The GPU's reached-state solve (sdpb_reached_solve) reproduces the Java program's printed output to the last
     digit, and agrees with the CPU oracle's restatement of the same loop."""
     vals = ([20, 30, 40], [10, 15, 20])
     probs = ([0.25, 0.5, 0.25], [0.25, 0.5, 0.25])
