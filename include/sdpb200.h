@@ -455,8 +455,16 @@ int sdpb_solve_batch(sdpb_handle* const* handles, int n);
  *                           (src/sdp/cash/multiItem/CashRecursionV.java:83-131: V(x1,x2,w) = max_y Pi(y1,y2,R),
  *                           Pi = E V_{t+1}, V_{T+1} = boundFinalCash(s) = w + salvage . x) with the lambdas of
  *                           src/cash/multiItem/MultiItemYR.java:89-146; actions = affordable order-up-to pairs
- *                           (v . y < R + 0.1), tie 0.01 */
-typedef enum sdpb_reached_kind { SDPB_REACHED_MULTILEAD = 0, SDPB_REACHED_MULTI_XR = 1, SDPB_REACHED_MULTI_YR = 2 } sdpb_reached_kind;
+ *                           (v . y < R + 0.1), tie 0.01
+ *   SDPB_REACHED_CASH_ROUNDED  new CashRecursion(MAX, pmf, A, f, c, gamma).getExpectedValue / getAction
+ *                           (src/sdp/cash/CashRecursion.java:79-140) with the lambdas of
+ *                           src/cash/singleItem/CashConstraintTest.java:76-116: ONE product, state (x, w) with both
+ *                           components rounded as Math.round(v * q) / q (q = 0.1: values such as 30.000000000000004, so
+ *                           neither axis is a grid with an exact step) and an initial state that need not be rounded
+ *                           (iniCash = 33); actions 0..(int) min(maxQ, max(0, (w - minCashRequired - K) / v)), strict
+ *                           compare.  q_bound = maxOrderQuantity + 1; d2 / price[1] / vari_cost[1] / salvage[1] unused */
+typedef enum sdpb_reached_kind { SDPB_REACHED_MULTILEAD = 0, SDPB_REACHED_MULTI_XR = 1, SDPB_REACHED_MULTI_YR = 2,
+                                 SDPB_REACHED_CASH_ROUNDED = 3 } sdpb_reached_kind;
 
 typedef struct sdpb_reached_model {
     uint32_t struct_size;      /* = sizeof(sdpb_reached_model) */
@@ -473,10 +481,13 @@ typedef struct sdpb_reached_model {
     double r0, r1, r2, limit, interest_free;   /* MULTILEAD: deposit rate, overdraft rate, penalty rate, limit, free amount */
     double deposit_rate;                       /* MULTI_XR, MULTI_YR: depositeRate */
     double min_inv, max_inv, min_cash, max_cash;
-    double gamma, tie_tolerance;               /* discount factor; 0.1 / 0.1 / 0.01 in the reference */
+    double gamma, tie_tolerance;               /* discount factor; 0.1 / 0.1 / 0.01 / 0 in the reference */
+    double fixed_cost, hold_cost, min_cash_required, state_q;  /* CASH_ROUNDED: K, h, minCashRequired, q; deposit_rate = interestRate */
+    const int32_t* n_demands_t; /* [T] demand points of each period when they differ (rows of d1 / d2 / p stay n_demands
+                                   apart, the tail of a shorter period is ignored); NULL = n_demands everywhere */
 } sdpb_reached_model;
 
-/* init_state = (x1, x2, preQ1, preQ2, cash) | (x1, x2, R) | (x1, x2, cash).  value = getExpectedValue(iniState);
+/* init_state = (x1, x2, preQ1, preQ2, cash) | (x1, x2, R) | (x1, x2, cash) | (x, cash).  value = getExpectedValue(iniState);
  * action1 / action2 = getAction(iniState) (order quantities, or order-up-to levels); n_states[t-1] = states of period t
  * (may be NULL, T entries); solve_ms = device time.  Blocks.  No CPU fallback. */
 int sdpb_reached_solve(const sdpb_reached_model* m, int device, const double* init_state, double* value,

@@ -72,8 +72,10 @@ public final class SdpB200 {
             JAVA_DOUBLE.withName("r0"), JAVA_DOUBLE.withName("r1"), JAVA_DOUBLE.withName("r2"), JAVA_DOUBLE.withName("limit"),
             JAVA_DOUBLE.withName("interest_free"), JAVA_DOUBLE.withName("deposit_rate"),
             JAVA_DOUBLE.withName("min_inv"), JAVA_DOUBLE.withName("max_inv"), JAVA_DOUBLE.withName("min_cash"),
-            JAVA_DOUBLE.withName("max_cash"), JAVA_DOUBLE.withName("gamma"), JAVA_DOUBLE.withName("tie_tolerance"));
-    public static final int REACHED_MULTILEAD = 0, REACHED_MULTI_XR = 1, REACHED_MULTI_YR = 2;
+            JAVA_DOUBLE.withName("max_cash"), JAVA_DOUBLE.withName("gamma"), JAVA_DOUBLE.withName("tie_tolerance"),
+            JAVA_DOUBLE.withName("fixed_cost"), JAVA_DOUBLE.withName("hold_cost"), JAVA_DOUBLE.withName("min_cash_required"),
+            JAVA_DOUBLE.withName("state_q"), ADDRESS.withName("n_demands_t"));
+    public static final int REACHED_MULTILEAD = 0, REACHED_MULTI_XR = 1, REACHED_MULTI_YR = 2, REACHED_CASH_ROUNDED = 3;
 
     private static final Linker LINKER = Linker.nativeLinker();
     private static final SymbolLookup LIB =

@@ -683,8 +683,10 @@ struct RKey {
 };
 struct RParamsO {
     int kind, T, Q, nD;
+    const int* nDt;  // demand points per period (rows are nD apart)
     const double *d1, *d2, *p;
     double price[2], v[2], sal[2], deposit_rate, min_inv, max_inv, min_cash, max_cash, gamma;
+    double K, h, min_cash_required, q;  // kind 3
 };
 struct ReachedTopDown {
     const RParamsO& P;
@@ -733,7 +735,7 @@ struct ReachedTopDown {
         for (int i = miny1; i < miny1 + P.Q; i++)
             for (int j = miny2; j < miny2 + P.Q; j++) {
                 double thisActionsValue = 0;
-                for (int k = 0; k < P.nD; k++) {
+                for (int k = 0; k < P.nDt[s.t - 1]; k++) {
                     const double dd1 = P.d1[(s.t - 1) * P.nD + k], dd2 = P.d2[(s.t - 1) * P.nD + k], pr = P.p[(s.t - 1) * P.nD + k];
                     thisActionsValue += pr * xr_immediate(s, i, j, dd1, dd2);
                     if (s.t < P.T) thisActionsValue += pr * P.gamma * xr_value(xr_transition(s, i, j, dd1, dd2));
@@ -776,7 +778,7 @@ struct ReachedTopDown {
                 if (!(P.v[0] * i + P.v[1] * j < iniRf + 0.1)) continue;
                 const double iniR = s.c + P.v[0] * s.x1 + P.v[1] * s.x2;
                 double expectValue = 0;
-                for (int k = 0; k < P.nD; k++) {
+                for (int k = 0; k < P.nDt[s.t - 1]; k++) {
                     const double dd1 = P.d1[(s.t - 1) * P.nD + k], dd2 = P.d2[(s.t - 1) * P.nD + k], pr = P.p[(s.t - 1) * P.nD + k];
                     expectValue += pr * yr_value(yr_transition(s.t, i, j, iniR, dd1, dd2));
                 }
@@ -786,20 +788,67 @@ struct ReachedTopDown {
         actions.emplace(s, best);
         return val;
     }
+
+    // ---- kind 3: CashRecursion.getExpectedValue (CashRecursion.java:98-138, MAX) with CashConstraintTest.java:76-116 ----
+    double cct_immediate(const RKey& s, double action, double randomDemand) const {
+        double revenue = P.price[0] * jmin(s.x1 + action, randomDemand);
+        double fixedCost = action > 0 ? P.K : 0;
+        double variableCost = P.v[0] * action;
+        double inventoryLevel = s.x1 + action - randomDemand;
+        double holdCosts = P.h * jmax(inventoryLevel, 0);
+        double interests = P.deposit_rate * (s.c - action * P.v[0]);
+        double cashIncrement = revenue - fixedCost - variableCost - holdCosts + interests;
+        double salValue = s.t == P.T ? P.sal[0] * jmax(inventoryLevel, 0) : 0;
+        cashIncrement += salValue;
+        return cashIncrement;
+    }
+    RKey cct_transition(const RKey& s, double action, double randomDemand) const {
+        double nextInventory = jmax(0, s.x1 + action - randomDemand);
+        double nextCash = s.c + cct_immediate(s, action, randomDemand);
+        nextCash = nextCash > P.max_cash ? P.max_cash : nextCash;
+        nextCash = nextCash < P.min_cash ? P.min_cash : nextCash;
+        nextInventory = nextInventory > P.max_inv ? P.max_inv : nextInventory;
+        nextInventory = nextInventory < P.min_inv ? P.min_inv : nextInventory;
+        nextCash = jround(nextCash * P.q) / P.q;
+        nextInventory = jround(nextInventory * P.q) / P.q;
+        return RKey{s.t + 1, nextInventory, 0.0, nextCash};
+    }
+    double cct_value(const RKey& s) {
+        auto it = values.find(s);
+        if (it != values.end()) return it->second;
+        double maxQ = (int)jmin((double)(P.Q - 1), jmax(0, (s.c - P.min_cash_required - P.K) / P.v[0]));
+        const int n = (int)maxQ + 1;
+        double val = -DBL_MAX, bestOrderQty = 0;
+        for (int i = 0; i < n; i++) {
+            double orderQty = i;
+            double thisQValue = 0;
+            for (int j = 0; j < P.nDt[s.t - 1]; j++) {
+                const double randomDemand = P.d1[(s.t - 1) * P.nD + j], dProb = P.p[(s.t - 1) * P.nD + j];
+                thisQValue += dProb * cct_immediate(s, orderQty, randomDemand);
+                if (s.t < P.T) thisQValue += dProb * P.gamma * cct_value(cct_transition(s, orderQty, randomDemand));
+            }
+            if (thisQValue > val) { val = thisQValue; bestOrderQty = orderQty; }
+        }
+        values.emplace(s, val);
+        actions.emplace(s, std::make_pair(bestOrderQty, 0.0));
+        return val;
+    }
 };
 
 extern "C" int oracle_reached(int kind, int T, int Qbound, int nD, const double* d1, const double* d2, const double* p,
                               const double* price, const double* v, const double* sal, double deposit_rate, double min_inv,
                               double max_inv, double min_cash, double max_cash, double gamma, const double* init /* x1, x2, c */,
-                              double* value, double* a1, double* a2, int64_t* n_states) {
+                              double* value, double* a1, double* a2, int64_t* n_states, const int* nDt, double fixed_cost,
+                              double hold_cost, double min_cash_required, double state_q) {
     RParamsO P;
-    P.kind = kind; P.T = T; P.Q = Qbound; P.nD = nD; P.d1 = d1; P.d2 = d2; P.p = p;
+    P.kind = kind; P.T = T; P.Q = Qbound; P.nD = nD; P.d1 = d1; P.d2 = d2; P.p = p; P.nDt = nDt;
+    P.K = fixed_cost; P.h = hold_cost; P.min_cash_required = min_cash_required; P.q = state_q;
     for (int k = 0; k < 2; k++) { P.price[k] = price[k]; P.v[k] = v[k]; P.sal[k] = sal[k]; }
     P.deposit_rate = deposit_rate; P.min_inv = min_inv; P.max_inv = max_inv; P.min_cash = min_cash; P.max_cash = max_cash;
     P.gamma = gamma;
     ReachedTopDown td(P);
     const RKey s0{1, init[0], init[1], init[2]};
-    *value = kind == 1 ? td.xr_value(s0) : td.yr_value(s0);
+    *value = kind == 1 ? td.xr_value(s0) : kind == 2 ? td.yr_value(s0) : td.cct_value(s0);
     *a1 = td.actions[s0].first;
     *a2 = td.actions[s0].second;
     if (n_states) *n_states = (int64_t)td.values.size();

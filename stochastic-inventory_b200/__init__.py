@@ -12,7 +12,7 @@ from .getpmf import (GetPmfMulti, DiscreteDistribution, GammaDist, GetPmf, Norma
 from .models import (workforce_model, two_product_cash_model, ModelSpec, cash_loan_model, cash_overdraft_limit_model, cash_overdraft_testing_model,
                      cash_constraint_model, cash_leadtime_model, cash_overdraft_model,
                      cash_survival_model, cash_xr_model, inventory_model, leadtime_model)
-from .recursion import (CashRecursionMultiLead, CashRecursionMultiXR, CashRecursionV, CashStateMultiLead, CashStateMultiXR, StaffRecursion, StaffState, Actions, CashRecursionMulti, CashStateMulti, CashLeadtimeRecursion, CashLeadtimeState, CashRecursion, CashRecursionXR,
+from .recursion import (CashRecursionMultiLead, CashRecursionMultiXR, CashRecursionRounded, CashRecursionV, CashStateMultiLead, CashStateMultiXR, StaffRecursion, StaffState, Actions, CashRecursionMulti, CashStateMulti, CashLeadtimeRecursion, CashLeadtimeState, CashRecursion, CashRecursionXR,
                         CashState, CashStateXR, LeadtimeRecursion, LeadtimeRecursion2, LeadtimeState,
                         OptDirection, Recursion, RiskRecursion, RiskState, State)
 from .solver import Group, Solver, reachable_hull, solve_batch

@@ -98,10 +98,12 @@ class SdpbReachedModel(C.Structure):
         ("deposit_rate", C.c_double),
         ("min_inv", C.c_double), ("max_inv", C.c_double), ("min_cash", C.c_double), ("max_cash", C.c_double),
         ("gamma", C.c_double), ("tie_tolerance", C.c_double),
+        ("fixed_cost", C.c_double), ("hold_cost", C.c_double), ("min_cash_required", C.c_double), ("state_q", C.c_double),
+        ("n_demands_t", _ip),
     ]
 
 
-REACHED_MULTILEAD, REACHED_MULTI_XR, REACHED_MULTI_YR = 0, 1, 2
+REACHED_MULTILEAD, REACHED_MULTI_XR, REACHED_MULTI_YR, REACHED_CASH_ROUNDED = 0, 1, 2, 3
 
 # every symbol include/sdpb200.h declares
 EXPORTS = [

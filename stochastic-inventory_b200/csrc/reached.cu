@@ -6,6 +6,8 @@
 //           (state (x1, x2, R), actions = order-up-to pairs, `(int)` casts)
 //   kind 2  src/sdp/cash/multiItem/CashRecursionV.java:83-131 (V / Pi form: no immediate value, `> val + 0.01`,
 //           V_{T+1} = boundFinalCash), lambdas src/cash/multiItem/MultiItemYR.java:89-146
+//   kind 3  src/sdp/cash/CashRecursion.java:79-140 with the lambdas of src/cash/singleItem/CashConstraintTest.java:76-116
+//           (one product; both state components rounded as Math.round(v * 0.1) / 0.1, so neither axis has an exact step)
 //
 // (what follows describes kind 0, for which the engine was written; the other two plug their lambdas into it)
 //
@@ -28,6 +30,7 @@
 #include <thrust/unique.h>
 
 #include <cfloat>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -55,8 +58,9 @@ struct MLKeyEq {
 
 struct MLParams {
     int kind;  // sdpb_reached_kind
-    double dr; // depositeRate of the XR / YR lambdas
-    int T, Q, nD;
+    double dr; // depositeRate of the XR / YR lambdas, interestRate of CashConstraintTest
+    double K, h, min_cash_req, sq;  // CASH_ROUNDED: fixed cost, holding cost, minCashRequired, rounding factor q
+    int T, Q, Q2, nD;  // the action list has Q * Q2 entries (Q2 = Q for the two-product kinds, 1 for one product)
     double price1, price2, v1, v2, sal1, sal2;
     double r0, r1, r2, limit, interest_free;
     double min_inv, max_inv, min_cash, max_cash, gamma, tie;
@@ -65,6 +69,7 @@ struct MLParams {
     const double* p;    // [T * nD]
     const double* pg;   // p * gamma
     const double* ovh;  // [T]
+    const int* nDt;     // [T] demand points of each period (<= nD, the row stride)
 };
 
 __host__ __device__ inline MLKey ml_key(const MLState& s) {
@@ -190,11 +195,44 @@ __device__ __forceinline__ MLState yr_transition(const MLParams& P, double y1, d
     return n;
 }
 
+// ---- kind 3: CashConstraintTest.java:76-116 (one product; x = k / q with k kept in the key) ----
+__device__ __forceinline__ double cct_immediate(const MLParams& P, bool last, double x, double w, double action, double d) {
+    const double revenue = P.price1 * jmin(x + action, d);
+    const double fixedCost = action > 0.0 ? P.K : 0.0;
+    const double variableCost = P.v1 * action;
+    const double inventoryLevel = (x + action) - d;
+    const double holdCosts = P.h * jmax0(inventoryLevel);
+    const double interests = P.dr * (w - action * P.v1);
+    double cashIncrement = (((revenue - fixedCost) - variableCost) - holdCosts) + interests;
+    const double salValue = last ? P.sal1 * jmax0(inventoryLevel) : 0.0;
+    cashIncrement += salValue;
+    return cashIncrement;
+}
+
+__device__ __forceinline__ MLState cct_transition(const MLParams& P, double x, double w, double action, double d, double c) {
+    double nextInventory = jmax0((x + action) - d);
+    double nextCash = w + c;
+    nextCash = nextCash > P.max_cash ? P.max_cash : nextCash;
+    nextCash = nextCash < P.min_cash ? P.min_cash : nextCash;
+    nextInventory = nextInventory > P.max_inv ? P.max_inv : nextInventory;
+    nextInventory = nextInventory < P.min_inv ? P.min_inv : nextInventory;
+    MLState n;
+    n.cash = (double)ml_jround(nextCash * P.sq) / P.sq;   // Math.round(nextCash * 0.1) / 0.1
+    n.x1 = (int)ml_jround(nextInventory * P.sq);           // the inventory is kept as k; its value is k / q
+    n.x2 = 0; n.q1 = 0; n.q2 = 0;
+    return n;
+}
+
 // the action with flat index ai of state s: its two components as the lambdas see them, and whether the reference's
 // action list contains it (kind 2: `v1 * i + v2 * j < iniR + 0.1`, MultiItemYR.java:104-108)
 __device__ __forceinline__ bool ml_action(const MLParams& P, const MLState& s, int ai, double& a1, double& a2) {
-    const int i = ai / P.Q, j = ai - i * P.Q;
+    const int i = ai / P.Q2, j = ai - i * P.Q2;
     if (P.kind == 0) { a1 = (double)i; a2 = (double)j; return true; }
+    if (P.kind == 3) {  // CashConstraintTest.java:76-80
+        a1 = (double)i; a2 = 0.0;
+        const double maxQ = (double)(int)fmin((double)(P.Q - 1), fmax(0.0, ((s.cash - P.min_cash_req) - P.K) / P.v1));
+        return i < (int)maxQ + 1;
+    }
     a1 = (double)(s.x1 + i); a2 = (double)(s.x2 + j);  // order-up-to levels from (int) x
     if (P.kind == 1) return true;
     const double iniR = (s.cash + P.v1 * (double)s.x1) + P.v2 * (double)s.x2;
@@ -214,13 +252,19 @@ __device__ __forceinline__ MLState ml_successor(const MLParams& P, int t, const 
         if (c_out) *c_out = c;
         return xr_transition(P, s, a1, a2, d1, d2, c);
     }
+    if (P.kind == 3) {
+        const double x = (double)s.x1 / P.sq;
+        const double c = cct_immediate(P, false, x, s.cash, a1, d1);
+        if (c_out) *c_out = c;
+        return cct_transition(P, x, s.cash, a1, d1, c);
+    }
     const double iniR = (s.cash + P.v1 * (double)s.x1) + P.v2 * (double)s.x2;
     return yr_transition(P, a1, a2, iniR, d1, d2);
 }
 
 // F_{t+1} candidates: one entry per (state, action, demand)
 __global__ void ml_expand(MLParams P, int t, const MLKey* __restrict__ F, long long nF, MLKey* __restrict__ out) {
-    const long long A = (long long)P.Q * P.Q;
+    const long long A = (long long)P.Q * P.Q2;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= nF * A) return;
     const long long si = gid / A;
@@ -231,9 +275,10 @@ __global__ void ml_expand(MLParams P, int t, const MLKey* __restrict__ F, long l
     // an action the reference's list does not contain reaches nothing: its slots repeat the state's first successor
     // under a listed action... there may be none, so they are filled with an all-ones key that unique() folds into
     // one entry and the caller drops
+    const int nDt = P.nDt[t - 1];
     for (int j = 0; j < P.nD; j++) {
         MLKey k;
-        if (feasible) k = ml_key(ml_successor(P, t, s, a1, a2, j, nullptr));
+        if (feasible && j < nDt) k = ml_key(ml_successor(P, t, s, a1, a2, j, nullptr));
         else { k.a = ~0ull; k.b = ~0ull; }
         out[gid * P.nD + j] = k;
     }
@@ -244,7 +289,8 @@ __global__ void ml_expand(MLParams P, int t, const MLKey* __restrict__ F, long l
 __device__ __forceinline__ double ml_action_value(const MLParams& P, int t, bool last, const MLState& s, double a1, double a2,
                                                   const MLKey* __restrict__ Fn, const double* __restrict__ Vn, long long nFn) {
     double q = 0.0;
-    for (int j = 0; j < P.nD; j++) {
+    const int nDt = P.nDt[t - 1];
+    for (int j = 0; j < nDt; j++) {
         const double pj = P.p[(t - 1) * P.nD + j];
         if (P.kind == 2) {
             const MLState n = ml_successor(P, t, s, a1, a2, j, nullptr);
@@ -254,12 +300,15 @@ __device__ __forceinline__ double ml_action_value(const MLParams& P, int t, bool
             continue;
         }
         const double d1 = P.d1[(t - 1) * P.nD + j], d2 = P.d2[(t - 1) * P.nD + j];
+        const double x3 = (double)s.x1 / P.sq;  // kind 3: the inventory value
         const double c = P.kind == 0 ? ml_immediate(P, t, last, s, (int)a1, (int)a2, (int)d1, (int)d2)
-                                     : xr_immediate(P, last, s, a1, a2, d1, d2);
+                       : P.kind == 1 ? xr_immediate(P, last, s, a1, a2, d1, d2)
+                                     : cct_immediate(P, last, x3, s.cash, a1, d1);
         q += pj * c;
         if (!last) {
             const MLState n = P.kind == 0 ? ml_transition(P, s, (int)a1, (int)a2, (int)d1, (int)d2, c)
-                                          : xr_transition(P, s, a1, a2, d1, d2, c);
+                            : P.kind == 1 ? xr_transition(P, s, a1, a2, d1, d2, c)
+                                          : cct_transition(P, x3, s.cash, a1, d1, c);
             q += P.pg[(t - 1) * P.nD + j] * Vn[ml_find(Fn, nFn, ml_key(n))];
         }
     }
@@ -275,7 +324,7 @@ __global__ void ml_backward_state(MLParams P, int t, const MLKey* __restrict__ F
     const bool last = t == P.T;
     double val = -DBL_MAX;
     int best = 0;  // bestActions = new Actions(0, 0); kind 2: bestYs = (x1, x2) = offsets (0, 0) as well
-    const int A = P.Q * P.Q;
+    const int A = P.Q * P.Q2;
     for (int ai = 0; ai < A; ai++) {
         double a1, a2;
         if (!ml_action(P, s, ai, a1, a2)) continue;
@@ -289,7 +338,7 @@ __global__ void ml_backward_state(MLParams P, int t, const MLKey* __restrict__ F
 // small frontiers: a thread per (state, action) pair ...
 __global__ void ml_backward_pairs(MLParams P, int t, const MLKey* __restrict__ F, long long nF, const MLKey* __restrict__ Fn,
                                   const double* __restrict__ Vn, long long nFn, double* __restrict__ QV) {
-    const long long A = (long long)P.Q * P.Q;
+    const long long A = (long long)P.Q * P.Q2;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= nF * A) return;
     const long long si = gid / A;
@@ -304,7 +353,7 @@ __global__ void ml_backward_pairs(MLParams P, int t, const MLKey* __restrict__ F
 __global__ void ml_scan_pairs(MLParams P, const double* __restrict__ QV, long long nF, double* __restrict__ V, int* __restrict__ Qa) {
     const long long si = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (si >= nF) return;
-    const long long A = (long long)P.Q * P.Q;
+    const long long A = (long long)P.Q * P.Q2;
     double val = -DBL_MAX;
     int best = 0;
     for (long long ai = 0; ai < A; ai++) {
@@ -328,14 +377,22 @@ int sdpb_reached_solve(const sdpb_reached_model* m, int device, const double* in
     g_ml_error.clear();
     auto fail = [&](int rc, const std::string& msg) { g_ml_error = msg; return rc; };
     if (!m || !init_state || m->struct_size != sizeof(sdpb_reached_model)) return fail(SDPB_ERR_ARG, "bad argument / struct_size");
-    if (m->kind < SDPB_REACHED_MULTILEAD || m->kind > SDPB_REACHED_MULTI_YR) return fail(SDPB_ERR_ARG, "bad kind");
+    if (m->kind < SDPB_REACHED_MULTILEAD || m->kind > SDPB_REACHED_CASH_ROUNDED) return fail(SDPB_ERR_ARG, "bad kind");
+    if (m->kind == SDPB_REACHED_CASH_ROUNDED && !(m->state_q > 0.0 && m->vari_cost[0] > 0.0)) return fail(SDPB_ERR_ARG, "CASH_ROUNDED needs state_q > 0 and a positive unit cost");
     if (m->T < 1 || m->q_bound < 1 || m->q_bound > 65535 || m->n_demands < 1 || !m->d1 || !m->d2 || !m->p || !m->overhead_t)
         return fail(SDPB_ERR_ARG, "T, q_bound, n_demands must be positive and the tables non-null");
     // init_state: kind 0 (x1, x2, preQ1, preQ2, cash); kind 1 (x1, x2, R); kind 2 (x1, x2, cash)
-    const int n_int = m->kind == SDPB_REACHED_MULTILEAD ? 4 : 2;
-    for (int k = 0; k < n_int; k++)
-        if (init_state[k] != (double)(int)init_state[k] || init_state[k] < 0 || init_state[k] > 65535)
+    const int n_int = m->kind == SDPB_REACHED_MULTILEAD ? 4 : (m->kind == SDPB_REACHED_CASH_ROUNDED ? 1 : 2);
+    double init_k[4] = {0, 0, 0, 0};
+    for (int k = 0; k < n_int; k++) {
+        init_k[k] = init_state[k];
+        if (m->kind == SDPB_REACHED_CASH_ROUNDED) {  // the inventory is kept as k = round(x * q); x must be k / q exactly
+            init_k[k] = std::floor(init_state[k] * m->state_q + 0.5);
+            if (init_k[k] / m->state_q != init_state[k]) return fail(SDPB_ERR_OFFGRID, "the initial inventory is not of the form k / state_q");
+        }
+        if (init_k[k] != (double)(int)init_k[k] || init_k[k] < 0 || init_k[k] > 65535)
             return fail(SDPB_ERR_OFFGRID, "initial inventories and pipeline quantities must be integers in [0, 65535]");
+    }
     if (!(m->max_inv <= 65535.0)) return fail(SDPB_ERR_ARG, "max_inv must fit 16 bits");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(SDPB_ERR_NO_DEVICE, "no CUDA device (libsdpb200 has no CPU path)"); }
@@ -343,7 +400,8 @@ int sdpb_reached_solve(const sdpb_reached_model* m, int device, const double* in
     if (device >= ndev || cudaSetDevice(device) != cudaSuccess) return fail(SDPB_ERR_NO_DEVICE, "cannot select the CUDA device");
 
     const int T = m->T, nD = m->n_demands;
-    const long long A = (long long)m->q_bound * m->q_bound;
+    const int q2 = m->kind == SDPB_REACHED_CASH_ROUNDED ? 1 : m->q_bound;
+    const long long A = (long long)m->q_bound * q2;
     std::vector<double> pg((size_t)T * nD);
     for (size_t i = 0; i < pg.size(); i++) pg[i] = m->p[i] * m->gamma;  // first product of p * gamma * V
     std::vector<void*> owned;
@@ -373,7 +431,8 @@ int sdpb_reached_solve(const sdpb_reached_model* m, int device, const double* in
     };
     MLParams P;
     P.kind = m->kind; P.dr = m->deposit_rate;
-    P.T = T; P.Q = m->q_bound; P.nD = nD;
+    P.K = m->fixed_cost; P.h = m->hold_cost; P.min_cash_req = m->min_cash_required; P.sq = m->state_q > 0.0 ? m->state_q : 1.0;
+    P.T = T; P.Q = m->q_bound; P.Q2 = q2; P.nD = nD;
     P.price1 = m->price[0]; P.price2 = m->price[1]; P.v1 = m->vari_cost[0]; P.v2 = m->vari_cost[1];
     P.sal1 = m->salvage[0]; P.sal2 = m->salvage[1];
     P.r0 = m->r0; P.r1 = m->r1; P.r2 = m->r2; P.limit = m->limit; P.interest_free = m->interest_free;
@@ -381,7 +440,19 @@ int sdpb_reached_solve(const sdpb_reached_model* m, int device, const double* in
     P.gamma = m->gamma; P.tie = m->tie_tolerance;
     P.d1 = upload(m->d1, (size_t)T * nD); P.d2 = upload(m->d2, (size_t)T * nD); P.p = upload(m->p, (size_t)T * nD);
     P.pg = upload(pg.data(), pg.size()); P.ovh = upload(m->overhead_t, (size_t)T);
-    if (!P.d1 || !P.d2 || !P.p || !P.pg || !P.ovh) { cleanup(); return fail(SDPB_ERR_NOMEM, "allocation of the model tables failed"); }
+    {
+        std::vector<int> lens(T, nD);
+        if (m->n_demands_t)
+            for (int t = 0; t < T; t++) {
+                if (m->n_demands_t[t] < 1 || m->n_demands_t[t] > nD) { cleanup(); return fail(SDPB_ERR_ARG, "n_demands_t out of range"); }
+                lens[t] = m->n_demands_t[t];
+            }
+        int* dl = (int*)dalloc((size_t)T * sizeof(int));
+        if (dl && cudaMemcpyAsync(dl, lens.data(), (size_t)T * sizeof(int), cudaMemcpyHostToDevice, stream) != cudaSuccess) dl = nullptr;
+        if (dl) cudaStreamSynchronize(stream);  // (lens is a local)
+        P.nDt = dl;
+    }
+    if (!P.d1 || !P.d2 || !P.p || !P.pg || !P.ovh || !P.nDt) { cleanup(); return fail(SDPB_ERR_NOMEM, "allocation of the model tables failed"); }
     ML_CU(cudaEventRecord(e0, stream));
 
     // ---- forward: the states the reference's recursion visits, period by period ----
@@ -390,8 +461,8 @@ int sdpb_reached_solve(const sdpb_reached_model* m, int device, const double* in
     std::vector<MLKey*> F(T, nullptr);
     std::vector<long long> nF(T, 0);
     MLState s0;
-    s0.x1 = (int)init_state[0]; s0.x2 = (int)init_state[1];
-    s0.q1 = n_int == 4 ? (int)init_state[2] : 0; s0.q2 = n_int == 4 ? (int)init_state[3] : 0;
+    s0.x1 = (int)init_k[0]; s0.x2 = n_int >= 2 ? (int)init_k[1] : 0;
+    s0.q1 = n_int == 4 ? (int)init_k[2] : 0; s0.q2 = n_int == 4 ? (int)init_k[3] : 0;
     s0.cash = init_state[n_int];
     const MLKey k0 = ml_key(s0);
     F[0] = (MLKey*)dalloc(sizeof(MLKey));
@@ -462,10 +533,11 @@ int sdpb_reached_solve(const sdpb_reached_model* m, int device, const double* in
     if (value) *value = v0;
     // kind 0: order quantities (i, j); kinds 1, 2: order-up-to levels (x1 + i, x2 + j) (bestYs; the reference's default
     // for a state without any accepted action is {0, 0} for kind 1 and (x1, x2) for kind 2)
-    const int ai = a0 / m->q_bound, aj = a0 % m->q_bound;
+    const int ai = a0 / q2, aj = a0 % q2;
     const bool none = v0 == -DBL_MAX;
-    if (action1) *action1 = m->kind == SDPB_REACHED_MULTILEAD ? ai : (m->kind == SDPB_REACHED_MULTI_XR && none ? 0.0 : s0.x1 + ai);
-    if (action2) *action2 = m->kind == SDPB_REACHED_MULTILEAD ? aj : (m->kind == SDPB_REACHED_MULTI_XR && none ? 0.0 : s0.x2 + aj);
+    const bool qty = m->kind == SDPB_REACHED_MULTILEAD || m->kind == SDPB_REACHED_CASH_ROUNDED;  // order quantities
+    if (action1) *action1 = qty ? ai : (m->kind == SDPB_REACHED_MULTI_XR && none ? 0.0 : s0.x1 + ai);
+    if (action2) *action2 = qty ? aj : (m->kind == SDPB_REACHED_MULTI_XR && none ? 0.0 : s0.x2 + aj);
     if (n_states) for (int t = 0; t < T; t++) n_states[t] = nF[t];
     if (solve_ms) *solve_ms = ms;
     cleanup();

@@ -429,13 +429,18 @@ class _ReachedEngine:
 
     def _setup(self, pmf, price, variCost, salvage, overheadCost, Qbound, minInventoryState, maxInventoryState,
                minCashState, maxCashState, discountFactor, tieTolerance, device, depositeRate=0.0, r0=0.0, r1=0.0, r2=0.0,
-               limit=0.0, interestFreeAmount=0.0):
+               limit=0.0, interestFreeAmount=0.0, fixedCost=0.0, holdingCost=0.0, minCashRequired=0.0, stateQ=0.0):
         self.lib = A.load()
         T = len(pmf)
-        nD = len(pmf[0])
-        if any(len(r) != nD for r in pmf):
-            raise ValueError("every period needs the same number of demand pairs")
-        tab = np.stack([np.asarray(r, dtype=np.float64) for r in pmf])           # [T, D, 3]
+        lens = [len(r) for r in pmf]
+        nD = max(lens)
+        tab = np.zeros((T, nD, 3))                                                # [T, D, 3], shorter periods padded
+        for t, r in enumerate(pmf):
+            r = np.asarray(r, dtype=np.float64)
+            if r.shape[1] == 2:                                                   # one product: (demand, prob)
+                r = np.column_stack([r[:, 0], np.zeros(len(r)), r[:, 1]])
+            tab[t, :len(r)] = r
+        self._lens = np.ascontiguousarray(lens, dtype=np.int32)
         self._d1 = np.ascontiguousarray(tab[:, :, 0]).ravel()
         self._d2 = np.ascontiguousarray(tab[:, :, 1]).ravel()
         self._p = np.ascontiguousarray(tab[:, :, 2]).ravel()
@@ -453,6 +458,8 @@ class _ReachedEngine:
         m.deposit_rate = depositeRate
         m.min_inv, m.max_inv, m.min_cash, m.max_cash = minInventoryState, maxInventoryState, minCashState, maxCashState
         m.gamma, m.tie_tolerance = discountFactor, tieTolerance
+        m.fixed_cost, m.hold_cost, m.min_cash_required, m.state_q = fixedCost, holdingCost, minCashRequired, stateQ
+        m.n_demands_t = self._lens.ctypes.data_as(C.POINTER(C.c_int32))
         self._m, self.T, self.device = m, T, device
         self._solved = {}
         self.n_states = None
@@ -533,6 +540,27 @@ class CashRecursionMultiXR(_ReachedEngine):
 
     def getAction(self, state):
         return list(self._action(state))
+
+
+class CashRecursionRounded(_ReachedEngine):
+    """new CashRecursion(OptDirection.MAX, pmf, getFeasibleAction, stateTransition, immediateValue, discountFactor)
+    (src/sdp/cash/CashRecursion.java:39-140) for the lambdas of src/cash/singleItem/CashConstraintTest.java:76-116:
+    one product, both state components rounded as Math.round(v * 0.1) / 0.1 after every transition (inventory
+    levels such as 30.000000000000004: no axis with an exact step), an initial cash that need not be rounded
+    (iniCash = 33).  Solved over the reached states.  State: CashState; getAction returns the order quantity."""
+    kind = A.REACHED_CASH_ROUNDED
+
+    def __init__(self, pmf, price=4.0, variCost=1.0, fixOrderCost=24.0, holdingCost=0.0, salvageValue=0.0,
+                 interestRate=0.0, minCashRequired=0.0, maxOrderQuantity=200, minInventoryState=0.0,
+                 maxInventoryState=500.0, minCashState=-100.0, maxCashState=2000.0, discountFactor=1.0, stateQ=0.1,
+                 device: int = -1):
+        self._setup(pmf, (price, 0.0), (variCost, 0.0), (salvageValue, 0.0), None, int(maxOrderQuantity) + 1,
+                    minInventoryState, maxInventoryState, minCashState, maxCashState, discountFactor, 0.0, device,
+                    depositeRate=interestRate, fixedCost=fixOrderCost, holdingCost=holdingCost,
+                    minCashRequired=minCashRequired, stateQ=stateQ)
+
+    def getAction(self, state):
+        return self._action(state)[0]
 
 
 class CashRecursionV(_ReachedEngine):

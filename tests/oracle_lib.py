@@ -35,7 +35,8 @@ def load():
     lib.oracle_multi_lead.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, dp, ip, ip,
                                       C.POINTER(C.c_int64)]
     lib.oracle_reached.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, C.c_double, C.c_double,
-                                   C.c_double, C.c_double, C.c_double, C.c_double, dp, dp, dp, dp, C.POINTER(C.c_int64)]
+                                   C.c_double, C.c_double, C.c_double, C.c_double, dp, dp, dp, dp, C.POINTER(C.c_int64), ip,
+                                   C.c_double, C.c_double, C.c_double, C.c_double]
     lib.oracle_simulate.argtypes = [vp, dp, dp, dp, C.c_int, C.c_double, dp]
     lib.oracle_eval.argtypes = [vp, C.c_int, dp, C.c_double, C.c_double, dp, dp]
     lib.oracle_index.argtypes = [vp, dp]
@@ -142,15 +143,23 @@ def n_actions(spec, period, state):
 
 
 def reached(kind, pmf, q_bound, price, vari_cost, salvage, init, deposit_rate=0.0, min_inv=0.0, max_inv=200.0, min_cash=0.0,
-            max_cash=10000.0, gamma=1.0):
-    """CashRecursionMultiXR (kind 1) / CashRecursionV (kind 2) through the oracle's literal top-down restatement
+            max_cash=10000.0, gamma=1.0, fixed_cost=0.0, hold_cost=0.0, min_cash_required=0.0, state_q=0.1):
+    """CashRecursionMultiXR (kind 1) / CashRecursionV (kind 2) / CashRecursion with the CashConstraintTest lambdas (kind 3:
+    one product, pmf rows (demand, prob), init = (x, 0, cash)) through the oracle's literal top-down restatement
     -> (value, action1, action2, visited states)."""
     lib = load()
-    tab = np.stack([np.asarray(r, dtype=np.float64) for r in pmf])
+    lens = np.ascontiguousarray([len(r) for r in pmf], dtype=np.int32)
+    tab = np.zeros((len(pmf), int(lens.max()), 3))
+    for t, r in enumerate(pmf):
+        r = np.asarray(r, dtype=np.float64)
+        if r.shape[1] == 2:
+            r = np.column_stack([r[:, 0], np.zeros(len(r)), r[:, 1]])
+        tab[t, :len(r)] = r
     d1, d2, p = (np.ascontiguousarray(tab[:, :, k]).ravel() for k in range(3))
     arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (price, vari_cost, salvage, init)]
     v, a1, a2, ns = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
     lib.oracle_reached(kind, tab.shape[0], q_bound, tab.shape[1], _dp(d1), _dp(d2), _dp(p), _dp(arrs[0]), _dp(arrs[1]),
                        _dp(arrs[2]), deposit_rate, min_inv, max_inv, min_cash, max_cash, gamma, _dp(arrs[3]),
-                       C.byref(v), C.byref(a1), C.byref(a2), C.byref(ns))
+                       C.byref(v), C.byref(a1), C.byref(a2), C.byref(ns), lens.ctypes.data_as(C.POINTER(C.c_int)),
+                       fixed_cost, hold_cost, min_cash_required, state_q)
     return v.value, a1.value, a2.value, ns.value

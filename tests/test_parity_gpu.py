@@ -1118,6 +1118,25 @@ def test_cash_recursion_v_matches_oracle(T, qb, cash, dr, S, oracle):
     assert sum(rec.n_states) == ns
 
 
+@pytest.mark.parametrize("means,K,cash,rate", [((6, 3, 2, 5), 8.0, 33.0, 0.0), ((20, 7, 2, 14), 24.0, 33.0, 0.0),
+                                               ((5, 4, 6), 0.0, 27.0, 0.1)])
+def test_cash_constraint_test_lambdas(means, K, cash, rate, S, oracle):
+    """src/cash/singleItem/CashConstraintTest.java:76-116 -- the one single-product driver whose states do not sit on a
+    grid: inventory and cash are rounded as Math.round(v * 0.1) / 0.1 (30.000000000000004 ...) and the initial cash, 33,
+    is not a rounded value at all.  Solved over the reached states; reads like the driver's :121-129."""
+    dists = [S.PoissonDist(m) for m in means]
+    pmf = S.GetPmf(dists, 0.9999, 1).getpmf()
+    recursion = S.CashRecursionRounded(pmf, price=4, variCost=1, fixOrderCost=K, holdingCost=0, salvageValue=0.5,
+                                       interestRate=rate, minCashRequired=0, maxOrderQuantity=60, maxInventoryState=500,
+                                       minCashState=-100, maxCashState=2000)
+    initialState = S.CashState(1, 0, cash)
+    finalValue = cash + recursion.getExpectedValue(initialState)
+    vo, a1, _, ns = oracle.reached(3, pmf, 61, (4, 0), (1, 0), (0.5, 0), [0, 0, cash], deposit_rate=rate, min_inv=0,
+                                   max_inv=500, min_cash=-100, max_cash=2000, fixed_cost=K, state_q=0.1)
+    assert finalValue == cash + vo and recursion.getAction(initialState) == a1
+    assert sum(recursion.n_states) == ns and recursion.n_states[0] == 1
+
+
 def test_multilead_reference_record_T3(S):
     """src/cash/overdraft/MultiProductLeadtime.java:45-50 -- the live code of the reference: 3 periods, demands
     {10,30} x {5,15}: 'final optimal cash is -76.56 ... Q1 = 30, Q2 = 15 ... running time is 1568.0s'.  1.7e7 states and
