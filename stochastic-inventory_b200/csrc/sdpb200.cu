@@ -904,9 +904,12 @@ size_t sdpb_sizeof_stats(void) { return sizeof(sdpb_stats); }
 
 const char* sdpb_last_error(const sdpb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+static void forget_batches_of(sdpb_handle* h);
+
 void sdpb_destroy(sdpb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    forget_batches_of(h);  // a captured batch graph must not outlive one of its handles
     if (h->stream) cudaStreamSynchronize(h->stream);  // (peers may still be reading flags this stream raises)
     if (h->stream) for (void* p : h->dev_allocs) cudaFreeAsync(p, h->stream);
     free_tiled(h->tiled);
@@ -2152,6 +2155,19 @@ struct BatchGraph {
 std::mutex g_batch_mu;
 std::vector<BatchGraph> g_batches;  // a handful per process: one per distinct handle list
 }  // namespace
+
+// sdpb_destroy: drop every remembered batch (and its graph) that contains the handle
+static void forget_batches_of(sdpb_handle* h) {
+    std::lock_guard<std::mutex> lk(g_batch_mu);
+    for (size_t i = 0; i < g_batches.size();) {
+        BatchGraph& b = g_batches[i];
+        if (std::find(b.handles.begin(), b.handles.end(), h) != b.handles.end()) {
+            if (b.exec) cudaGraphExecDestroy(b.exec);
+            if (b.stream) { cudaStreamSynchronize(b.stream); cudaStreamDestroy(b.stream); }
+            g_batches.erase(g_batches.begin() + (long)i);
+        } else i++;
+    }
+}
 
 int sdpb_solve_batch(sdpb_handle* const* handles, int n) {
     if (!handles || n < 1) return SDPB_ERR_ARG;
