@@ -113,7 +113,12 @@ bi_cash_int(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs
     }
 
     const int nW1 = M.nW - 1;
-    for (int ai = 0; ai < nAmax; ai++) {
+    // action slices over gridDim.z, as in bi_cash_diag: a band of the grid (one shard of eight) is a few hundred CTAs of
+    // two warps, each a serial loop over ~200 actions x 200 demands -- the slices make that 16 times as many CTAs
+    const int parts = (int)gridDim.z, part = (int)blockIdx.z;
+    const int per_part = (nAmax + parts - 1) / parts;
+    const int ai_end = min(nAmax, (part + 1) * per_part);
+    for (int ai = part * per_part; ai < ai_end; ai++) {
         const int yv = a.inv_min_i + ix + ai;                 // stock after ordering, as a value
         const int CI = (ai > 0 ? a.K : 0) + a.v * ai + a.ovh;  // K 1[a>0] + v a + overhead
         const double Cd = (double)CI;
@@ -197,12 +202,18 @@ bi_cash_int(const __grid_constant__ DevModel M, const __grid_constant__ CashArgs
             if (ai < nA[r] && (IS_MIN ? (acc[r] < best[r]) : (acc[r] > best[r]))) { best[r] = acc[r]; arg[r] = ai; }
         }
     }
+    const long long n_local = a.hi - a.lo;
 #pragma unroll
     for (int r = 0; r < R; r++) {
         if (valid[r]) {
             const long long idx = (long long)ix * M.nW + iw[r];
-            a.Vt[idx] = best[r];
-            a.Qt[idx] = arg[r] == kNoAction ? -1 : arg[r];
+            if (parts == 1) {
+                a.Vt[idx] = best[r];
+                a.Qt[idx] = arg[r] == kNoAction ? -1 : arg[r];
+            } else {  // merge_action_slices picks the first optimum over the slices
+                a.slice_v[(long long)part * n_local + (idx - a.lo)] = best[r];
+                a.slice_a[(long long)part * n_local + (idx - a.lo)] = arg[r];
+            }
         }
     }
 }
@@ -250,26 +261,86 @@ inline void plan_cash(CashPlan& P, const sdpb_model& m, const DevModel& d, const
     P.available = true;
 }
 
-// SDPB_OK, SDPB_ERR_STATE (no plan for this period: use the generic kernel) or SDPB_ERR_CUDA.
+// Optimum over the action slices of one state: slices in ascending order hold ascending actions, so a strict compare
+// keeps the first optimum (Recursion.java:146-157); a slice that held no feasible action of the state says kNoAction.
+// A peer shard's V tables as this shard addresses them: V_t[idx] of the peer is at base0 + (t-1)*stride + idx*8 (the
+// base is biased by the peer's window start), and the peer reads rows [lo, hi) of this shard's block.
+struct DevPeer { char* base0; unsigned long long stride; long long lo, hi; };
+
+// Multi-GPU: the merged values a peer reads are stored into the peer's table as well (peer-mapped memory), so the
+// cash models -- where every shard reads nearly every row: 7 peers at 8 GPUs -- need no copy after the kernel either.
+template <bool IS_MIN>
+__global__ void __launch_bounds__(256)
+merge_action_slices(const double* __restrict__ sv, const int* __restrict__ sa, int parts, long long n_local,
+                    double* __restrict__ Vt, int* __restrict__ Qt, long long lo, const DevPeer* __restrict__ peers,
+                    int n_peers, int t) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_local) return;
+    double best = IS_MIN ? DBL_MAX : -DBL_MAX;
+    int arg = kNoAction;
+    for (int q = 0; q < parts; q++) {
+        const double v = sv[(long long)q * n_local + i];
+        const int av = sa[(long long)q * n_local + i];
+        if (av != kNoAction && (IS_MIN ? (v < best) : (v > best))) { best = v; arg = av; }
+    }
+    Vt[i] = best;
+    Qt[i] = arg == kNoAction ? -1 : arg;
+    const long long idx = lo + i;
+    for (int p = 0; p < n_peers; p++) {
+        const DevPeer pr = peers[p];
+        if (idx >= pr.lo && idx < pr.hi)
+            reinterpret_cast<double*>(pr.base0 + (unsigned long long)(t - 1) * pr.stride)[idx] = best;
+    }
+}
+
+// Shape of a bi_cash_int launch over [lo, hi): R = 16 cash levels per thread in the last period when the grid is large
+// enough, and the action range cut into slices when the launch would otherwise leave the GPU short of CTAs.
+struct CashIntShape { bool wide; int tile, parts; dim3 grid; };
+
+inline CashIntShape cash_int_shape(const sdpb_model& m, const DevModel& dm, int t, long long lo, long long hi, int sm_count) {
+    CashIntShape s;
+    const int rows = (int)((hi - 1) / dm.nW) - (int)(lo / dm.nW) + 1;
+    const bool surv = m.recursion == SDPB_REC_SURVIVAL;
+    const long long want = 64LL * sm_count;  // CTAs of two warps: ~8 resident per SM, 8 rounds of them
+    const int max_parts = std::max(1, std::min(16, (m.max_order_idx + 1) / 12));
+    auto parts_for = [&](long long tiles) {
+        return tiles >= want ? 1 : (int)std::min<long long>((want + tiles - 1) / tiles, max_parts);
+    };
+    const long long tiles16 = (long long)rows * ((dm.nW + kCashThreads * kCashRLast - 1) / (kCashThreads * kCashRLast));
+    // 16 cash levels per thread in the last period when the action slices still leave two CTAs per SM
+    s.wide = t == m.T && !surv && dm.nW >= kCashThreads * kCashRLast / 2 && tiles16 * parts_for(tiles16) >= 2LL * sm_count;
+    s.tile = kCashThreads * (s.wide ? kCashRLast : kCashR);
+    const long long tiles = (long long)rows * ((dm.nW + s.tile - 1) / s.tile);
+    s.parts = parts_for(tiles);
+    if (s.wide && tiles16 >= 3LL * sm_count) s.parts = 1;  // measured on C3 (1002 CTAs): 103.9 ms unsliced, 104.6 in 10 slices
+    static const int env_split = [] { const char* e = std::getenv("SDPB_CASH_INT_SPLIT"); return e ? std::atoi(e) : 0; }();
+    if (env_split) s.parts = std::max(1, std::min(env_split, 32));  // tuning knob, read once per process
+    s.grid = dim3((unsigned)rows, (unsigned)((dm.nW + s.tile - 1) / s.tile), (unsigned)s.parts);
+    return s;
+}
+
+// SDPB_OK, SDPB_ERR_STATE (no plan for this period: use the generic kernel), SDPB_ERR_NOMEM (slice scratch too small:
+// the caller sizes it with cash_int_shape) or SDPB_ERR_CUDA.
 inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& dm, int t, int D, int pmf_off,
                        const double* Vn, double* Vt, int* Qt, long long lo, long long hi, cudaStream_t stream,
-                       double* fp64_ops, double evals) {
+                       double* fp64_ops, double evals, int sm_count, const DevPeer* d_peers = nullptr, int n_peers = 0,
+                       bool* pushed = nullptr) {
     if (!P.available || !P.period[t - 1].ok) return SDPB_ERR_STATE;
     if (hi <= lo) return SDPB_OK;
     const CashPeriod& cp = P.period[t - 1];
     CashArgs a;
     a.t = t; a.D = D; a.pmf_off = pmf_off; a.Vn = Vn; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
     a.ix0 = (int)(lo / dm.nW);
-    const int ix1 = (int)((hi - 1) / dm.nW);
     a.price = cp.price; a.v = cp.v; a.K = P.K; a.ovh = cp.ovh; a.d0 = cp.d0; a.inv_min_i = (int)m.inv_min;
     const bool surv = m.recursion == SDPB_REC_SURVIVAL;
-    // 16 cash levels per thread in the last period -- unless that leaves the GPU short of CTAs (a shard of the grid)
-    int sm_count = 148, dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    const long long ctas16 = (long long)(ix1 - a.ix0 + 1) * ((dm.nW + kCashThreads * kCashRLast - 1) / (kCashThreads * kCashRLast));
-    const bool wide = t == m.T && !surv && ctas16 >= 3LL * sm_count;
-    const int tile = kCashThreads * (wide ? kCashRLast : kCashR);
-    const dim3 grid((unsigned)(ix1 - a.ix0 + 1), (unsigned)((dm.nW + tile - 1) / tile));
+    const CashIntShape sh = cash_int_shape(m, dm, t, lo, hi, sm_count);
+    const bool wide = sh.wide;
+    const dim3 grid = sh.grid;
+    const long long n_local = hi - lo;
+    if (sh.parts > 1) {
+        if ((size_t)sh.parts * (size_t)n_local > P.slice_cap) return SDPB_ERR_NOMEM;
+        a.slice_v = P.slice_v; a.slice_a = P.slice_a;
+    } else { a.slice_v = nullptr; a.slice_a = nullptr; }
     const size_t smem = (size_t)D * 28 + 16;
     if (smem > 200 * 1024) return SDPB_ERR_STATE;  // demand support too long for the shared-memory tables: general path
     if (smem > 48 * 1024) {
@@ -297,6 +368,13 @@ inline int launch_cash(const CashPlan& P, const sdpb_model& m, const DevModel& d
         else bi_cash_int<false, false, false><<<grid, kCashThreads, smem, stream>>>(dm, a);
     }
     if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+    if (sh.parts > 1) {
+        const unsigned mb = (unsigned)((n_local + 255) / 256);
+        if (dm.is_min && !surv) merge_action_slices<true><<<mb, 256, 0, stream>>>(P.slice_v, P.slice_a, sh.parts, n_local, Vt + lo, Qt + lo, lo, d_peers, n_peers, t);
+        else merge_action_slices<false><<<mb, 256, 0, stream>>>(P.slice_v, P.slice_a, sh.parts, n_local, Vt + lo, Qt + lo, lo, d_peers, n_peers, t);
+        if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+        if (pushed && n_peers > 0) *pushed = true;
+    }
     if (fp64_ops) {
         if (t == m.T) *fp64_ops += evals * (surv ? 2.0 + 3.0 / kCashR : 1.0 + 4.0 / (wide ? kCashRLast : kCashR));
         else *fp64_ops += evals * (surv ? 2.0 : 3.0 + 2.0 / kCashR);
@@ -521,38 +599,6 @@ bi_cash_diag(const __grid_constant__ DevModel M, const __grid_constant__ CashArg
                 a.slice_a[(long long)part * n_local + (idx - a.lo)] = arg[k];
             }
         }
-    }
-}
-
-// Optimum over the action slices of one state: slices in ascending order hold ascending actions, so a strict compare
-// keeps the first optimum (Recursion.java:146-157); a slice that held no feasible action of the state says kNoAction.
-// A peer shard's V tables as this shard addresses them: V_t[idx] of the peer is at base0 + (t-1)*stride + idx*8 (the
-// base is biased by the peer's window start), and the peer reads rows [lo, hi) of this shard's block.
-struct DevPeer { char* base0; unsigned long long stride; long long lo, hi; };
-
-// Multi-GPU: the merged values a peer reads are stored into the peer's table as well (peer-mapped memory), so the
-// cash models -- where every shard reads nearly every row: 7 peers at 8 GPUs -- need no copy after the kernel either.
-template <bool IS_MIN>
-__global__ void __launch_bounds__(256)
-merge_action_slices(const double* __restrict__ sv, const int* __restrict__ sa, int parts, long long n_local,
-                    double* __restrict__ Vt, int* __restrict__ Qt, long long lo, const DevPeer* __restrict__ peers,
-                    int n_peers, int t) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_local) return;
-    double best = IS_MIN ? DBL_MAX : -DBL_MAX;
-    int arg = kNoAction;
-    for (int q = 0; q < parts; q++) {
-        const double v = sv[(long long)q * n_local + i];
-        const int av = sa[(long long)q * n_local + i];
-        if (av != kNoAction && (IS_MIN ? (v < best) : (v > best))) { best = v; arg = av; }
-    }
-    Vt[i] = best;
-    Qt[i] = arg == kNoAction ? -1 : arg;
-    const long long idx = lo + i;
-    for (int p = 0; p < n_peers; p++) {
-        const DevPeer pr = peers[p];
-        if (idx >= pr.lo && idx < pr.hi)
-            reinterpret_cast<double*>(pr.base0 + (unsigned long long)(t - 1) * pr.stride)[idx] = best;
     }
 }
 

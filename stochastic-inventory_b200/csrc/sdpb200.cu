@@ -851,10 +851,8 @@ int solve_period(sdpb_handle* h, int t) {
     }
     if (rc == SDPB_ERR_STATE && h->opt.kernel != SDPB_KERNEL_GENERIC && !plain && !term_T) {  // integer cash models
         rc = SDPB_ERR_STATE;
-        if (h->opt.kernel != SDPB_KERNEL_CASH_INT && h->cash.available && t < m.T && h->cash.period[t - 1].ok && h->hi > h->lo) {
-            // (as a request, SDPB_KERNEL_CASH_INT skips the diagonal-window variant)
-            // scratch for the action slices: one (value, action) entry per slice and state of the shard
-            const int parts = cash_diag_parts(m, h->dm, h->cash.period[t - 1], h->lo, h->hi, h->sm_count);
+        // scratch for the action slices: one (value, action) entry per slice and state of the shard
+        auto slice_scratch = [&](int parts) -> int {
             const size_t need = parts > 1 ? (size_t)parts * (size_t)(h->hi - h->lo) : 0;
             if (need > h->cash.slice_cap) {
                 void* p = nullptr;
@@ -864,18 +862,29 @@ int solve_period(sdpb_handle* h, int t) {
                 h->cash.slice_a = (int*)p;
                 h->cash.slice_cap = need;  // (an earlier, smaller scratch stays in dev_allocs until the handle goes)
             }
-            static const bool no_fused = std::getenv("SDPB_NO_FUSED_PUSH") != nullptr;  // A/B knob: copies after the kernel
-            const bool push = h->peer.attached && t > 1 && !h->peer.sends.empty() && !no_fused;
+            return SDPB_OK;
+        };
+        static const bool no_fused = std::getenv("SDPB_NO_FUSED_PUSH") != nullptr;  // A/B knob: copies after the kernel
+        const bool push = h->peer.attached && t > 1 && !h->peer.sends.empty() && !no_fused;
+        const DevPeer* d_peers = push ? (const DevPeer*)h->peer.d_peers : nullptr;
+        const int n_peers = push ? (int)h->peer.sends.size() : 0;
+        if (h->opt.kernel != SDPB_KERNEL_CASH_INT && h->cash.available && t < m.T && h->cash.period[t - 1].ok && h->hi > h->lo) {
+            // (as a request, SDPB_KERNEL_CASH_INT skips the diagonal-window variant)
+            const int parts = cash_diag_parts(m, h->dm, h->cash.period[t - 1], h->lo, h->hi, h->sm_count);
+            if (int e = slice_scratch(parts)) return e;
             rc = launch_cash_diag(h->cash, m, h->dm, t, D, h->pmf_off[t - 1], Vn, h->dV[t - 1], h->dQ[t - 1], h->lo,
                                   h->hi, h->stream, &h->stats.fp64_ops, count_evals_period(h, t), h->sm_count,
-                                  push ? (const DevPeer*)h->peer.d_peers : nullptr, push ? (int)h->peer.sends.size() : 0,
-                                  &h->push_fused);
+                                  d_peers, n_peers, &h->push_fused);
             if (rc == SDPB_OK && parts > 1) h->stats.launches++;  // merge_action_slices
         }
         if (rc == SDPB_OK) h->stats.kernel_used = SDPB_KERNEL_CASH_DIAG;
-        else if (rc == SDPB_ERR_STATE) {
+        else if (rc == SDPB_ERR_STATE && h->cash.available && h->cash.period[t - 1].ok && h->hi > h->lo) {
+            const int parts = cash_int_shape(m, h->dm, t, h->lo, h->hi, h->sm_count).parts;
+            if (int e = slice_scratch(parts)) return e;
             rc = launch_cash(h->cash, m, h->dm, t, D, h->pmf_off[t - 1], Vn, h->dV[t - 1], h->dQ[t - 1], h->lo, h->hi,
-                             h->stream, &h->stats.fp64_ops, count_evals_period(h, t));
+                             h->stream, &h->stats.fp64_ops, count_evals_period(h, t), h->sm_count, d_peers, n_peers,
+                             &h->push_fused);
+            if (rc == SDPB_OK && parts > 1) h->stats.launches++;  // merge_action_slices
             if (rc == SDPB_OK && h->stats.kernel_used != SDPB_KERNEL_CASH_DIAG) h->stats.kernel_used = SDPB_KERNEL_CASH_INT;
         }
         if (rc != SDPB_OK && rc != SDPB_ERR_STATE) { h->err = "cash kernel launch failed"; return rc; }

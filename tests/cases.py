@@ -112,6 +112,13 @@ def case_C_int():
                                    q_mul=1.0, q_div=1.0, name="C_int"), [[0.0, 12.0]]
 
 
+def case_C_int_tall():
+    # 75 inventory rows, so that a shard of two or three spans several 8-row tiles of bi_cash_diag; not in ALL
+    return S.cash_constraint_model(pmf([5, 6, 5]), price=10, vari_cost=1, salvage=0.5, max_order=14,
+                                   inv_min=0, inv_max=74, cash_min=0, cash_max=120, quantiser=A.Q_LONGDIV,
+                                   q_mul=1.0, q_div=1.0, name="C_int_tall"), [[0.0, 12.0]]
+
+
 def case_C_int_K():
     # integer fixed cost / overhead / unit cost 2, negative cash allowed, discounting, inventory from 2
     return S.cash_constraint_model(pmf([4, 6, 5]), price=7, vari_cost=2, fixed_cost=3, salvage=1.0, overhead=2,

@@ -393,7 +393,8 @@ GROUP_CASES = [(cases.case_A_small, 2), (cases.case_A_gy, 3), (cases.case_B2_sma
                (cases.case_B1_fixed, 4), (cases.case_C_int, 3), (cases.case_C_rich, 2), (cases.case_C_small, 5),
                (cases.case_D_small, 3), (cases.case_F_small, 2), (cases.case_E_small, 2), (cases.case_M2_small, 3),
                (cases.case_W_small, 2), (cases.case_XR_small, 2), (cases.case_A_terminal, 3), (cases.case_B2_terminal, 4),
-               (cases.case_C_terminal, 3), (cases.case_M2_terminal, 2), (cases.case_A_one_state, 3)]
+               (cases.case_C_terminal, 3), (cases.case_M2_terminal, 2), (cases.case_A_one_state, 3),
+               (cases.case_C_int_tall, 2), (cases.case_C_int_tall, 3)]
 
 
 @pytest.mark.parametrize("case,world", GROUP_CASES, ids=lambda x: getattr(x, "__name__", str(x))[5:])
