@@ -132,7 +132,11 @@ bi_inv_tiled(const __grid_constant__ DevModel M, const __grid_constant__ TiledAr
     const int c_end = min(a.n_chunks, c_begin + a.chunks_per_split);
     const int e0 = a.D - 1;  // CONSEC: e_j = (D-1) - j
 
-    for (int c = c_begin; c < c_end; c++) {
+    // A thread whose R states X0 + u - r all lie beyond the block has nothing to evaluate: in the ragged last tile
+    // (C2: 2001 states = 8 tiles of 249 + 9 states) seven of the eight warps skip the loop and leave their issue
+    // slots to the other CTAs of the SM -- 10 % of a batch of such solves.
+    const bool has_state = X0 + u - (R - 1) < a.hi;
+    for (int c = has_state ? c_begin : c_end; c < c_end; c++) {
         double fv[R], acc[R];
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -290,7 +294,8 @@ bi_inv_tiled2(const __grid_constant__ DevModel M, const __grid_constant__ TiledA
     const int c_begin = split * a.chunks_per_split;
     const int c_end = min(a.n_chunks, c_begin + a.chunks_per_split);
 
-    for (int c = c_begin; c < c_end; c++) {
+    const bool has_state = X0 + (long long)Y * u - (RA - 1) < a.hi;  // (see bi_inv_tiled: the ragged last tile)
+    for (int c = has_state ? c_begin : c_end; c < c_end; c++) {
         double fv[RA], acc[Y][RA], cst[Y][RA], Vw[Y];
 #pragma unroll
         for (int r = 0; r < RA; r++) {
@@ -528,14 +533,16 @@ inline int launch_tiled(TiledPlan& P, const DevModel& dm, int t, int D, int pmf_
     const long long tiles2 = (n + kT2BX - 1) / kT2BX;
     // measured on C5 (200 x 200): the 2-D register tile (with its action split) wins from ~64 tiles on
     // (S = 1e5: 3.36 vs 4.02 ms, 2e5: 6.8 vs 8.0, 3e5: 9.0 vs 11.9) and is level at 3e4 (1.40 vs 1.37)
-    const bool use2 = tp.ok2 && (P.variant == 2 || (P.variant == 0 && tiles2 >= 64) || !tp.ok);
+    // (a batch fills the machine with its instances: 64 C2 solves 3.62 ms on bi_inv_tiled, 3.06 ms on this one)
+    const bool use2 = tp.ok2 && (P.variant == 2 || (P.variant == 0 && tiles2 * P.batch >= 64) || !tp.ok);
     if (use2) {
         int nsplit = 1;
         // enough CTAs for ~8 waves of 2 CTAs per SM: a grid of a few waves loses its last, partial one
         // (measured, C5: S = 1e6 32.9 -> 30.0 ms, S = 1e5 3.36 -> 3.17 ms; no change at 3e5 and 3e6)
         static const int env_waves = [] { const char* e = std::getenv("SDPB_T2_WAVES"); return e ? std::max(1, std::atoi(e)) : 0; }();
-        long long want = std::max(1LL, 16LL * P.sm_count / P.batch);
-        if (env_waves) want = env_waves * 2LL * P.sm_count;  // tuning knob, read once per process
+        // (one instance of a batch: 3 waves of its share -- measured 64 x C2: 8 waves 3.15 ms, 4: 3.08, 3: 3.06, 1: 3.26)
+        long long want = P.batch > 1 ? std::max(1LL, 6LL * P.sm_count / P.batch) : 16LL * P.sm_count;
+        if (env_waves) want = std::max(1LL, env_waves * 2LL * P.sm_count / P.batch);  // tuning knob, read once per process
         if (tiles2 < want) nsplit = (int)std::min<long long>(P.n_chunks2, (want + tiles2 - 1) / tiles2);
         const int cps = (P.n_chunks2 + nsplit - 1) / nsplit;
         nsplit = (P.n_chunks2 + cps - 1) / cps;

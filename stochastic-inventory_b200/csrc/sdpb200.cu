@@ -1409,7 +1409,10 @@ static int enqueue_fused(sdpb_handle* h) {
 static int enqueue_all_periods(sdpb_handle* h) {
     std::fill(h->solved.begin(), h->solved.end(), 0);
     h->stats = sdpb_stats{};
-    if (h->fused.ok) {
+    // (one of a wide batch: the whole-horizon kernel is a cooperative launch sized for the whole GPU, and a batch of
+    //  them would run one after the other; the per-period kernels of different instances run side by side)
+    const bool in_wide_batch = h->tiled.batch >= 8 && h->opt.kernel != SDPB_KERNEL_FUSED;
+    if (h->fused.ok && !in_wide_batch) {
         const int rc = enqueue_fused(h);
         if (rc != SDPB_ERR_STATE) return rc;
         h->fused.ok = false;  // cannot be launched cooperatively here: per-period launches from now on

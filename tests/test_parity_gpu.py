@@ -699,6 +699,27 @@ def test_solve_batch(S, oracle):
         assert np.array_equal(V, Vo[0]) and np.array_equal(Q, Qo[0])
 
 
+def test_solve_batch_wide(S, oracle):
+    """A batch wide enough to fill the GPU by itself (72 instances): the library then runs every instance on the 2-D
+    register tile with a small action split; three rounds (plain, capture, replay)."""
+    specs = [S.inventory_model(cases.pmf([5 + k % 3, 8 + k % 4, 6 + k % 2]), fixed_cost=20 + 5 * (k % 6), vari_cost=k % 2,
+                               hold_cost=1 + 0.5 * (k % 2), penalty_cost=5 + k % 5, max_order=15 + k % 7,
+                               inv_min=-30 - k % 5, inv_max=30 + 2 * (k % 9)) for k in range(8)]
+    want = [oracle.dense(sp) for sp in specs]
+    solvers = [S.Solver(specs[k % 8]) for k in range(72)]
+    for rep in range(3):
+        S.solve_batch(solvers)
+    for k, s in enumerate(solvers):
+        Vo, Qo, evals, _ = want[k % 8]
+        for t in range(1, specs[k % 8].T + 1):
+            V, Q = s.period_tables(t)
+            assert np.array_equal(V, Vo[t - 1]) and np.array_equal(Q, Qo[t - 1]), (k, t)
+        assert s.stats()["evals"] == evals
+    assert solvers[0].stats()["kernel_used"] in (S.KERNEL_TILED2, S.KERNEL_FUSED, S.KERNEL_TILED)
+    for s in solvers:
+        s.close()
+
+
 def test_reference_style_driver_clsp_main(S, oracle):
     """Reads like src/capacitated/CLSP.java:196-290 (the self-contained demo with its own inline pmf)."""
     meanDemand = [9, 23, 53, 29]
