@@ -58,25 +58,21 @@ struct DevModel {
     const double2* pmf_rec;
 };
 
-// Math.round(double) -> long: round half up, without forming x + 0.5 (Java >= 7 semantics).
+// Math.round(double) -> long (Java >= 7): floor(x + 1/2) of the EXACT sum.  With round-down addition,
+// s = RD(x + 0.5) is the largest double <= x + 0.5; floor(x + 0.5) is an integer, hence representable (|x| < 2^52; above
+// that x is an integer and s = x), and it is <= the exact sum, so floor(x + 0.5) <= s <= x + 0.5 and floor(s) is the
+// answer: one DADD.RM and one flooring conversion, no compare.  (-2.5 -> -2, 2.5 -> 3, 0.49999999999999994 -> 0.)
 __device__ __forceinline__ long long jround(double x) {
-    double r = floor(x);
-    double diff = x - r;
-    return (long long)r + (diff >= 0.5 ? 1ll : 0ll);
+    return __double2ll_rd(__dadd_rd(x, 0.5));
 }
 
-// The same for |x| < 2^31 (DevModel::small), without a single int<->double conversion instruction (F2I.F64 / I2F.F64
-// issue at a fraction of the DADD rate; two of them per evaluation were the largest item of the cash kernels' tail).
-// x + 1.5*2^52 is x rounded to the nearest integer (ties to even) with that integer sitting in the low mantissa bits:
-// n = rint(x) comes back as a double by subtracting the constant and as an int by reading the low word, both exactly.
-// Math.round rounds halves UP: it differs from rint only when x - n is exactly +0.5 (an exact subtraction), e.g.
-// x = 2.5 -> n = 2 -> 3, x = -2.5 -> n = -2 -> -2, x = 3.5 -> n = 4 (x - n = -0.5) -> 4.
+// The same for |x| < 2^31 (DevModel::small), without an int<->double conversion instruction (F2I.F64 / I2F.F64 issue
+// at a fraction of the DADD rate): RD(s + 1.5*2^52) lands in [2^52, 2^53), where doubles are the integers, so it IS
+// floor(s) + 1.5*2^52 and floor(s) sits in the low mantissa word as a two's-complement int (2^51 = 0 mod 2^32).
+// Two fp64 instructions per Math.round; the first version (x + magic, - magic, x - n, compare with 0.5) took four.
 __device__ __forceinline__ int jround32(double x) {
     const double magic = 6755399441055744.0;  // 2^52 + 2^51
-    const double t = __dadd_rn(x, magic);
-    const double n = __dadd_rn(t, -magic);
-    const double diff = __dadd_rn(x, -n);
-    return __double2loint(t) + (diff == 0.5 ? 1 : 0);
+    return __double2loint(__dadd_rd(__dadd_rd(x, 0.5), magic));
 }
 
 // Java `long / long` (truncation toward zero) by the run-time constant q_idiv.  For q_idiv < 2^15 and

@@ -174,8 +174,7 @@ __device__ __forceinline__ MLState xr_transition(const MLParams& P, const MLStat
 
 // ---- kind 2: MultiItemYR.java:122-146 (Math.round(x * 10) / 10 is a LONG division) ----
 __device__ __forceinline__ long long ml_jround(double x) {
-    const double r = floor(x);
-    return (long long)r + ((x - r) >= 0.5 ? 1ll : 0ll);
+    return __double2ll_rd(__dadd_rd(x, 0.5));  // floor of the exact x + 1/2: see jround() in dev_model.cuh
 }
 
 __device__ __forceinline__ MLState yr_transition(const MLParams& P, double y1, double y2, double iniR, double d1, double d2) {

@@ -606,15 +606,15 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
             // DADD + DMUL per evaluation as counted by ncu (profiles/r02_fp64_audit.md)
             const int kd = h->m.cost_kind;  // (overdraft-limit / -testing: a few more for the two interest products)
             const double body = kd == SDPB_COST_CASH_DEPOSIT ? 4.0 : kd == SDPB_COST_CASH_OVERDRAFT ? 2.0 : kd == SDPB_COST_CASH_OD_LIMIT ? 9.0 : 7.0;
-            h->stats.fp64_ops += count_evals_period(h, t) * (last ? body + 3.0 : body + 9.0);
+            h->stats.fp64_ops += count_evals_period(h, t) * (last ? body + 3.0 : body + 8.0);
             return launch_cash_tail(tp, h->m, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi, h->stream);
         }
     }
     if (!DEDUP && h->opt.kernel != SDPB_KERNEL_GENERIC && cash_row_ok(h->m, h->dm, h->pmf_len[t - 1])) {
         h->stats.kernel_used = SDPB_KERNEL_CASH_ROW;
         // cash-dependent tail per evaluation: deposit chain 4, salvage 1, end cash 1, p*c 2 (+ clamp / quantiser /
-        // continuation 6 when a successor exists); compares and selects not counted
-        h->stats.fp64_ops += count_evals_period(h, t) * (last ? 8.0 : 14.0);
+        // continuation 5 when a successor exists); compares and selects not counted
+        h->stats.fp64_ops += count_evals_period(h, t) * (last ? 8.0 : 13.0);
         return launch_cash_row(h->m, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, Vt, Qt, lo, hi, h->stream);
     }
     if (h->stats.kernel_used == 0) h->stats.kernel_used = SDPB_KERNEL_GENERIC;

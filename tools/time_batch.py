@@ -19,7 +19,7 @@ for n in (16, 64, 256):
 if os.environ.get("BATCH_ONLY"):
     sys.exit(0)
 for name, mk in (("c1", S.configs.c1), ("c2", S.configs.c2)):
-    for kern, kn in ((S.KERNEL_AUTO, "auto"), (S.KERNEL_TILED, "tiled"), (S.KERNEL_FUSED, "fused")):
+    for kern, kn in ((S.KERNEL_AUTO, "auto"), (S.KERNEL_TILED, "tiled"), (S.KERNEL_TILED2, "tiled2"), (S.KERNEL_FUSED, "fused")):
         try:
             s = S.Solver(mk(), device=0, kernel=kern)
         except S.SdpbError as e:
