@@ -542,6 +542,7 @@ struct Q2Args {
     long long lo, hi;
     long long f_begin, f_end; // flat thread range: f = (x * n_chunks + chunk) * nQ + preQ2
     int n_chunks, tpx;        // chunks of 8 levels along preQ1; threads per inventory row
+    int half;                 // bi_lead_q2m: ceil(nQ / 2), the distance between a thread's two preQ2 columns
     int di_max, NRW;
     int parts;                // slices of the action range per CTA (1, 2 or 4): small grids cannot fill the GPU otherwise
     // Multi-GPU: rows of this shard's block that a peer reads are stored into the peer's V_t as well, straight from the
@@ -698,6 +699,238 @@ bi_lead_q2(const __grid_constant__ DevModel M, const __grid_constant__ Q2Args a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// bi_lead_q2m -- bi_lead_q2 with the products p_j * (fv_a + L(level)) shared by the threads of a CTA.
+//
+// The immediate value of (x, preQ1, preQ2) under action a and demand d_j does not depend on preQ2
+// (Leadtime.java:72-80: fixed + variable + holding/penalty of x + preQ1 - d_j), and the lanes of a warp ARE consecutive
+// preQ2 of one (x, chunk of 8 preQ1 levels): all of them form the identical product m = p_j * cst for each of their 8
+// slots.  Here a CTA tabulates, once per action, M[group][j][slot] = p_j * (fv_a + L(...)) for the few (x, chunk)
+// groups its threads belong to (4 on C4) with exactly the operations a thread used to do itself, and a thread then
+// reads its 8 products and spends (add, mul, add) per evaluation instead of (mul, add, mul, add) + 1/8.
+// A warp's LDS.128 returns 512 bytes however many lanes share an address -- four cycles of the SM's one shared-memory
+// pipe -- so with one preQ2 per thread the four product loads per demand step cost as much as the multiplies they
+// replace (measured: 138 vs 140 ms on C4).  A thread therefore owns TWO preQ2 columns (c and c + ceil(nQ/2): lanes stay
+// consecutive, every gather a coalesced row segment): 16 states, 48 fp64 instructions per demand step against five
+// shared-memory loads.  The running optimum of the 16 states lives in shared memory (read-compare-conditional-store
+// once per action), which is what lets 16 accumulators and two 10-entry successor windows fit in 128 registers.
+// The successor row offset of the window refill and p_j*gamma come from a second small table R[group][j], built once
+// per CTA.  One barrier per action (M is double-buffered).  Values are bit-identical: same operands, same order.
+template <int IMM>
+__device__ __forceinline__ double2 lds_double2_o(unsigned shared_addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(shared_addr), "n"(IMM));
+    return v;
+}
+
+constexpr int kQ2mNC = 2;  // preQ2 columns per thread
+
+struct Q2mLayout { int NG; unsigned off_rg, off_gb, off_bv, off_ba, off_mt; size_t smem; };
+
+__host__ __device__ inline Q2mLayout q2m_layout(int NRW, int D, int NT, int parts, int half) {
+    Q2mLayout L;
+    const int cols = NT / parts;
+    L.NG = (cols - 1) / half + 2;                                // distinct (x, chunk) groups among `cols` consecutive threads
+    unsigned o = (unsigned)(NRW + D) * 16u;                      // WR, PP
+    L.off_rg = o; o += (unsigned)(L.NG * D) * 16u;               // R[group][j] = (p_j*gamma, refill row offset)
+    L.off_gb = o; o += ((unsigned)L.NG * 4u + 15u) & ~15u;       // window base row of each group
+    L.off_bv = o; o += (unsigned)(kQ2mNC * kQ2YT * NT) * 8u;     // running optimum per state: value ...
+    L.off_ba = o; o += (unsigned)(kQ2mNC * kQ2YT * NT) * 4u;     // ... and action
+    L.off_mt = o; o += 2u * (unsigned)(parts * L.NG * D) * 64u;  // M[buffer][slice][group][j][8]
+    L.smem = o;
+    return L;
+}
+
+template <bool IS_MIN, bool LAST, int NT, int PARTS>
+__global__ void __launch_bounds__(NT, 512 / NT)
+bi_lead_q2m(const __grid_constant__ DevModel M, const __grid_constant__ Q2Args a) {
+    constexpr int YT = kQ2YT, PF = kQ2PF, W = YT + PF, PAD = kQ2PAD, NC = kQ2mNC;
+    static_assert(W == 10, "the demand loop below is written out for W = 10");
+    static_assert(NT % 8 == 0 && (NT / PARTS) % 8 == 0, "the table builder keeps the slot index fixed per thread");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = a.D, nQ = M.nQ, half = a.half, tid = threadIdx.x;
+    constexpr int cols = NT / PARTS;
+    const Q2mLayout L = q2m_layout(a.NRW, D, NT, PARTS, half);
+    double2* WR = reinterpret_cast<double2*>(smem_raw);  // (level cost, successor row offset in the low word)
+    double2* PP = WR + a.NRW;                            // (p, p*gamma)
+    double2* RG = reinterpret_cast<double2*>(smem_raw + L.off_rg);
+    int* GB = reinterpret_cast<int*>(smem_raw + L.off_gb);
+    double* BV = reinterpret_cast<double*>(smem_raw + L.off_bv);
+    int* BA = reinterpret_cast<int*>(smem_raw + L.off_ba);
+    double* MT = reinterpret_cast<double*>(smem_raw + L.off_mt);
+    const int NG = L.NG;
+    const int part = tid / cols, col = tid - part * cols;
+    const long long F0 = a.f_begin + (long long)blockIdx.x * cols;
+    const long long x_first = F0 / a.tpx;
+    const long long G0 = F0 / half;                      // first (x, chunk) group of the CTA: G = x * n_chunks + chunk
+    const bool lost = (M.flags & SDPB_F_LOST_SALES) != 0;
+
+    for (int j = tid; j < D; j += NT) PP[j] = make_double2(M.pmf_p[a.pmf_off + j], M.pmf_pg[a.pmf_off + j]);
+    for (int wi = tid; wi < a.NRW; wi += NT) {
+        const long long il = x_first - a.di_max - PAD + wi;
+        const double lvl = M.inv_min + (double)il * M.step;
+        long long is = il;
+        if (lost) is = is > M.i_zero ? is : M.i_zero;
+        is = is < M.nI - 1 ? is : M.nI - 1;  // upper clamp first; also the memory-safety clip
+        is = is > 0 ? is : 0;
+        WR[wi] = make_double2(M.h * fmax(lvl, 0.0) + M.pen * fmax(-lvl, 0.0),
+                              __hiloint2double(0, (int)(is * nQ * nQ)));
+    }
+    // window row of slot 0 at demand D-1 for each group
+    for (int g = tid; g < NG; g += NT) {
+        const long long G = G0 + g;
+        const long long xg = G / a.n_chunks;
+        const int chunk = (int)(G - xg * a.n_chunks);
+        int wb = (int)(xg - x_first) + chunk * YT + (D - 1) + PAD;
+        GB[g] = min(wb, a.NRW - YT);  // groups past the end of the range are built but never read
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < NC * YT; s2++) { BV[s2 * NT + tid] = IS_MIN ? DBL_MAX : -DBL_MAX; BA[s2 * NT + tid] = kNoAction; }
+    __syncthreads();
+    for (int e = tid; e < NG * D; e += NT) {
+        const int g = e / D, j = e - g * D;
+        const double2 w = WR[GB[g] - (PF + 1) - j];      // the level slot 0 reaches PF + 1 demand steps after j
+        RG[e] = make_double2(PP[j].y, w.y);
+    }
+
+    const long long F = min(F0 + col, a.f_end - 1);
+    const long long x = F / a.tpx;
+    const int f = (int)(F - x * a.tpx);
+    const int chunk = f / half, c0 = f - chunk * half, l0 = chunk * YT;
+    const int g_own = (int)(F / half - G0);
+    const bool has_b = c0 + half < nQ;                   // the second column: preQ2 = c0 + half
+    const long long idx0 = (x * nQ + l0) * nQ + c0;      // column 0, slot k: idx0 + k * nQ; column 1: + half
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < YT; k++) {
+        const long long i0 = idx0 + (long long)k * nQ;
+        any |= (l0 + k < nQ) && ((i0 >= a.lo && i0 < a.hi) || (has_b && i0 + half >= a.lo && i0 + half < a.hi));
+    }
+    any = any && F0 + col < a.f_end;
+
+    const unsigned wr0 = (unsigned)__cvta_generic_to_shared(WR) + (unsigned)((int)(x - x_first) + l0 + (D - 1) + PAD) * 16u;
+    const unsigned rg0 = (unsigned)__cvta_generic_to_shared(RG) + (unsigned)(g_own * D) * 16u;
+    const unsigned mt0 = (unsigned)__cvta_generic_to_shared(MT) + (unsigned)((part * NG + g_own) * D) * 64u;
+    const unsigned mt_buf = (unsigned)(PARTS * NG * D) * 64u;  // bytes between the two buffers
+    const unsigned bv_s = (unsigned)__cvta_generic_to_shared(BV) + (unsigned)tid * 8u;
+    const unsigned ba_s = (unsigned)__cvta_generic_to_shared(BA) + (unsigned)tid * 4u;
+    const double* __restrict__ cb = LAST ? nullptr : a.VnT + c0;
+    const int colb = has_b ? half : 0;                   // a thread without a second column gathers the first one twice
+    const double vt = M.v_t[a.t - 1];
+
+    const int per_part = (M.max_order_idx + PARTS) / PARTS;  // ceil(A / PARTS)
+    const int ai_begin = part * per_part;
+    const int ai_end = min(M.max_order_idx + 1, ai_begin + per_part);
+    if (!LAST) cb += (long long)ai_begin * nQ;
+    double* MTp = MT + (size_t)(part * NG) * D * YT;
+    // the builder's entries e = col, col + cols, ...: slot k = e & 7 is fixed, (group, demand) advance by cols / 8
+    const int k_b = col & (YT - 1);
+    const int gj_b = col >> 3;
+    for (int it = 0; it < per_part; it++) {  // every slice runs per_part rounds: the barrier below is CTA-wide
+        const int ai = ai_begin + it;
+        const unsigned buf = (unsigned)(it & 1);
+        if (ai < ai_end) {  // ---- tabulate p_j * (fv_a + L) for this slice's groups ----
+            const double av = (double)ai * M.step;
+            const double fv = (av > 0.0 ? M.K : 0.0) + vt * av;  // Leadtime.java:73-74,79
+            double* Mb = MTp + (size_t)buf * (PARTS * NG) * D * YT;
+            int g = gj_b / D, j = gj_b - g * D;
+            for (int e = col; e < NG * D * YT; e += cols) {
+                const double cst = fv + WR[GB[g] + k_b - j].x;
+                Mb[e] = PP[j].x * cst;                           // LeadtimeRecursion.java:59
+                j += cols / YT;
+                while (j >= D) { j -= D; g++; }
+            }
+        }
+        __syncthreads();
+        if (ai < ai_end && any) {
+            double acc[NC][YT], Vw[NC][W];
+#pragma unroll
+            for (int k = 0; k < YT; k++) { acc[0][k] = 0.0; acc[1][k] = 0.0; }
+            if (!LAST) {
+#pragma unroll
+                for (int k = 0; k < W; k++) {  // entries YT..W-1: the levels slot 0 reaches at demands PF..1
+                    const double2 e = lds_double2(wr0 + (unsigned)((k < YT ? k : k - W) * 16));
+                    const double* src = cb + __double2loint(e.y);
+                    Vw[0][k] = __ldg(src);
+                    Vw[1][k] = __ldg(src + colb);
+                }
+            }
+            unsigned mt_run = mt0 + buf * mt_buf, rg_run = rg0;
+#define SDPB_Q2M_STEP(JJ)                                                                             \
+            {                                                                                             \
+                const double2 m01 = lds_double2_o<(JJ) * 64>(mt_run), m23 = lds_double2_o<(JJ) * 64 + 16>(mt_run); \
+                const double2 m45 = lds_double2_o<(JJ) * 64 + 32>(mt_run), m67 = lds_double2_o<(JJ) * 64 + 48>(mt_run); \
+                const double mm[YT] = {m01.x, m01.y, m23.x, m23.y, m45.x, m45.y, m67.x, m67.y};           \
+                if (LAST) {                                                                               \
+                    _Pragma("unroll") for (int k = 0; k < YT; k++) { acc[0][k] += mm[k]; acc[1][k] += mm[k]; } \
+                } else {                                                                                  \
+                    const double2 rg = lds_double2_o<(JJ) * 16>(rg_run);                                  \
+                    _Pragma("unroll") for (int k = 0; k < YT; k++) {                                      \
+                        acc[0][k] += mm[k];                               /* LeadtimeRecursion.java:59 */ \
+                        acc[0][k] += rg.x * Vw[0][(k - (JJ) + W) % W];    /* LeadtimeRecursion.java:62 */ \
+                        acc[1][k] += mm[k];                                                               \
+                        acc[1][k] += rg.x * Vw[1][(k - (JJ) + W) % W];                                    \
+                    }                                                                                     \
+                    const double* src = cb + __double2loint(rg.y);                                        \
+                    Vw[0][(YT - 1 - (JJ) + W) % W] = __ldg(src);                                          \
+                    Vw[1][(YT - 1 - (JJ) + W) % W] = __ldg(src + colb);                                   \
+                }                                                                                         \
+            }
+            int j = 0;
+            while (j + W <= D) {
+                SDPB_Q2M_STEP(0) SDPB_Q2M_STEP(1) SDPB_Q2M_STEP(2) SDPB_Q2M_STEP(3) SDPB_Q2M_STEP(4)
+                SDPB_Q2M_STEP(5) SDPB_Q2M_STEP(6) SDPB_Q2M_STEP(7) SDPB_Q2M_STEP(8) SDPB_Q2M_STEP(9)
+                j += W; mt_run += W * 64u; rg_run += W * 16u;
+            }
+            if (j + 0 < D) SDPB_Q2M_STEP(0)
+            if (j + 1 < D) SDPB_Q2M_STEP(1)
+            if (j + 2 < D) SDPB_Q2M_STEP(2)
+            if (j + 3 < D) SDPB_Q2M_STEP(3)
+            if (j + 4 < D) SDPB_Q2M_STEP(4)
+            if (j + 5 < D) SDPB_Q2M_STEP(5)
+            if (j + 6 < D) SDPB_Q2M_STEP(6)
+            if (j + 7 < D) SDPB_Q2M_STEP(7)
+            if (j + 8 < D) SDPB_Q2M_STEP(8)
+#undef SDPB_Q2M_STEP
+            // running optimum: strictly better wins, so the first (lowest) optimal action stays (Recursion.java:146-157)
+#pragma unroll
+            for (int c2 = 0; c2 < NC; c2++)
+#pragma unroll
+                for (int k = 0; k < YT; k++) {
+                    const unsigned so = (unsigned)((c2 * YT + k) * NT);
+                    const double bv = lds_double(bv_s + so * 8u);
+                    if (IS_MIN ? (acc[c2][k] < bv) : (acc[c2][k] > bv)) {
+                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(bv_s + so * 8u), "d"(acc[c2][k]) : "memory");
+                        asm volatile("st.shared.s32 [%0], %1;" ::"r"(ba_s + so * 4u), "r"(ai) : "memory");
+                    }
+                }
+        }
+        if (!LAST) cb += nQ;
+    }
+    if (PARTS > 1) __syncthreads();
+    if (part > 0 || !any) return;
+#pragma unroll
+    for (int c2 = 0; c2 < NC; c2++) {
+        if (c2 == 1 && !has_b) break;
+#pragma unroll
+        for (int k = 0; k < YT; k++) {
+            const long long idx = idx0 + (long long)k * nQ + (c2 ? half : 0);
+            if (!(l0 + k < nQ && idx >= a.lo && idx < a.hi)) continue;
+            double best = BV[(c2 * YT + k) * NT + tid];
+            int arg = BA[(c2 * YT + k) * NT + tid];
+            for (int q = 1; q < PARTS; q++) {  // ascending slices hold ascending actions: strict compare = first wins
+                const double v = BV[(c2 * YT + k) * NT + q * cols + col];
+                const int av = BA[(c2 * YT + k) * NT + q * cols + col];
+                if (av != kNoAction && (IS_MIN ? (v < best) : (v > best))) { best = v; arg = av; }
+            }
+            a.Vt[idx] = best;
+            a.Qt[idx] = arg == kNoAction ? -1 : arg;
+            for (int p = 0; p < a.n_peer; p++)
+                if (idx >= a.peer_lo[p] && idx < a.peer_hi[p]) a.peer_v[p][idx] = best;
+        }
+    }
+}
+
 struct Q2Plan {
     bool ok = false;
     int NT = 128, n_chunks = 0, tpx = 0, di_max = 0, NRW = 0;
@@ -726,7 +959,7 @@ constexpr int kQ2MaxPeers = 2;
 
 inline int launch_q2(const Q2Plan& P, const DevModel& dm, int t, int D, int pmf_off, const double* Vn, double* VnT,
                      double* Vt, int* Qt, long long lo, long long hi, int row0, int row1, cudaStream_t stream,
-                     const PeerStore* peers = nullptr, int n_peers = 0) {
+                     const PeerStore* peers = nullptr, int n_peers = 0, bool* shared_products = nullptr) {
     if (hi <= lo) return SDPB_OK;
     const bool last = (Vn == nullptr), mn = dm.is_min != 0;  // period T without a terminal table
     if (!last) {
@@ -753,10 +986,33 @@ inline int launch_q2(const Q2Plan& P, const DevModel& dm, int t, int D, int pmf_
     static const int env_split = [] { const char* e2 = std::getenv("SDPB_Q2_SPLIT"); return e2 ? std::atoi(e2) : 0; }();
     if (env_split) a.parts = env_split == 1 ? 1 : env_split == 2 ? 2 : 4;  // tuning knob, read once per process
     const int cols = P.NT / a.parts;
-    const long long blocks = (a.f_end - a.f_begin + cols - 1) / cols;
     cudaError_t e = cudaSuccess;
+    // bi_lead_q2m (products shared through shared memory, two preQ2 columns per thread) whenever its tables leave
+    // four CTAs per SM; its threads are numbered over (x, chunk, column pair)
+    static const bool no_share = std::getenv("SDPB_Q2_NOSHARE") != nullptr;  // A/B knob, read once per process
+    const int half = (dm.nQ + 1) / 2;
+    const int tpx2 = P.n_chunks * half;
+    const int NRW2 = P.n_chunks * kQ2YT + D + kQ2PAD + (P.NT + tpx2 - 1) / tpx2 + 1;
+    const Q2mLayout L = q2m_layout(NRW2, D, P.NT, a.parts, half);
+    // (measured on C4, ms: whole grid 132.6 vs 140.3; half 69.1 vs 71.7; a quarter -- two action slices -- 37.8 vs 36.7; an
+    //  eighth -- four slices -- 20.8 vs 18.7: the per-action tables and the barrier cost more than they save once the
+    //  action range is sliced, so sliced launches stay on bi_lead_q2)
+    static const bool force_share = std::getenv("SDPB_Q2_SHARE") != nullptr;
+    const bool shared = !no_share && (a.parts == 1 || force_share) && L.smem <= 56 * 1024;
+    if (shared_products) *shared_products = shared;
+    a.half = half;
+    if (shared) {
+        a.tpx = tpx2; a.NRW = NRW2;
+        a.f_begin = (lo / per_x) * tpx2;
+        a.f_end = ((hi - 1) / per_x + 1) * tpx2;
+    }
+    const long long blocks = (a.f_end - a.f_begin + cols - 1) / cols;
 #define SDPB_Q2_LAUNCH(MN, LS, PT)                                                                     \
-    {                                                                                                  \
+    if (shared) {                                                                                      \
+        auto k = bi_lead_q2m<MN, LS, 128, PT>;                                                         \
+        if (L.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem); \
+        if (e == cudaSuccess) k<<<(unsigned)blocks, 128, L.smem, stream>>>(dm, a);                     \
+    } else {                                                                                           \
         auto k = bi_lead_q2<MN, LS, 128, PT>;                                                          \
         if (P.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem); \
         if (e == cudaSuccess) k<<<(unsigned)blocks, 128, P.smem, stream>>>(dm, a);                     \

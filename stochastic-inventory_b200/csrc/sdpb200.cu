@@ -551,7 +551,6 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
         if (qp.ok) {
             h->stats.kernel_used = SDPB_KERNEL_LEAD_Q2;
             const double ev = (double)(hi - lo) * (h->m.max_order_idx + 1) * h->pmf_len[t - 1];
-            h->stats.fp64_ops += ev * (last ? (1.0 + 2.0 * kQ2YT) / kQ2YT : (1.0 + 4.0 * kQ2YT) / kQ2YT);
             if (!last) h->stats.launches++;  // the transposition pass
             int64_t rlo = 0, rhi = h->S;
             sdpb_shard_reads(h, &rlo, &rhi);
@@ -569,8 +568,14 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
                 }
                 h->push_fused = true;
             }
-            return launch_q2(qp, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, h->dVT, Vt, Qt, lo, hi,
-                             (int)(rlo / per_x), (int)(rhi / per_x), h->stream, ps, nps);
+            bool shared_products = false;
+            const int rc = launch_q2(qp, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, h->dVT, Vt, Qt, lo, hi,
+                                     (int)(rlo / per_x), (int)(rhi / per_x), h->stream, ps, nps, &shared_products);
+            // per evaluation: (mul, add, mul, add) + one cost per 8 -- or, with the products p*(fv + L) shared by the
+            // CTA (bi_lead_q2m), (add, mul, add); the last period has no continuation term
+            if (shared_products) h->stats.fp64_ops += ev * (last ? 1.0 : 3.0);
+            else h->stats.fp64_ops += ev * (last ? (1.0 + 2.0 * kQ2YT) / kQ2YT : (1.0 + 4.0 * kQ2YT) / kQ2YT);
+            return rc;
         }
     }
     if (!plain && h->opt.kernel != SDPB_KERNEL_GENERIC && h->opt.kernel != SDPB_KERNEL_STAGED && h->m.lead_time >= 1 &&

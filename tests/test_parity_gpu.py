@@ -720,6 +720,22 @@ def test_solve_batch_wide(S, oracle):
         s.close()
 
 
+@pytest.mark.parametrize("split", ["1", "2", "4"])
+def test_lead_q2m_forced(split):
+    """bi_lead_q2m (products p*(fv + L) shared through shared memory, two preQ2 columns per thread) is chosen by itself
+    only on large unsliced grids (the full-size C4 tests); here it is forced onto 16 small random lead-time-2 instances,
+    with 1, 2 and 4 action slices per CTA, unsharded and as a three-shard group.  The knobs are read once per process,
+    hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SDPB_Q2_SHARE="1", SDPB_Q2_SPLIT=split)
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "q2m_worker.py")
+    r = subprocess.run([sys.executable, worker], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "16 instances ok" in r.stdout
+
+
 def test_reference_style_driver_clsp_main(S, oracle):
     """Reads like src/capacitated/CLSP.java:196-290 (the self-contained demo with its own inline pmf)."""
     meanDemand = [9, 23, 53, 29]
