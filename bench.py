@@ -33,7 +33,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 REF_F = {"c1": 20, "c2": 20, "c3": 41, "c4": 20, "c5": 20}  # fp64 ops per evaluation as written
 KERNEL_NAMES = {1: "bi_generic", 2: "bi_inv_tiled", 3: "bi_backorder_staged", 4: "bi_cash_int", 5: "bi_inv_tiled2",
-                6: "bi_lead_slab", 7: "bi_lead_col", 8: "bi_cash_diag", 9: "bi_lead_q2", 10: "bi_two_product_row",
+                6: "bi_lead_slab", 7: "bi_lead_col", 8: "bi_cash_diag", 9: "bi_lead_q2", 14: "bi_lead_q2m", 10: "bi_two_product_row",
                 11: "bi_inv_fused", 12: "bi_cash_row", 13: "bi_cash_tail"}
 METRIC = "state-action-demand evaluations/s (fp64), full-horizon SDP solve"
 UNIT = "evals/s"
@@ -597,7 +597,7 @@ def run_gpu(args):
                             ") + solve + sdpb_value + D2H of the period-1 value and policy tables into page-locked host "
                             "buffers + sdpb_destroy, wall clock; one untimed warm-up cycle first"},
             "gpu_launches": int(launches_total),
-            "gpu_launches_note": "backward-induction kernels (+ the per-period transposition pass of bi_lead_q2) over all ranks; "
+            "gpu_launches_note": "backward-induction kernels (+ the per-period transposition pass of bi_lead_q2 / bi_lead_q2m) over all ranks; "
                                  "peer copies and the two 1-CTA flag kernels per period are not counted",
             "clocks": clocks,
             "device_bytes_per_gpu": dev_bytes,
@@ -623,6 +623,22 @@ def run_gpu(args):
                         "note": "algorithmic HBM bytes: 24 B per state-period; not the bound"},
             },
         }
+        if kernel_used == 14:
+            # bi_lead_q2m executes ~3.0 fp64 instructions per evaluation where bi_lead_q2 executed 4.125: the solve is
+            # faster and `frac` -- instructions ISSUED over the pipe's rate -- is lower.  Its second limit is the SM's
+            # shared-memory pipe: five 16-byte loads per thread and demand step (16 evaluations).
+            lds_gbs = value * 5.0 / 1e9 / world
+            out["roofline"]["shared_memory"] = {
+                "achieved_gbs": lds_gbs, "peak_gbs": peaks["lds_gbs"],
+                "frac": lds_gbs / peaks["lds_gbs"] if peaks["lds_gbs"] else None,
+                "note": "80 B of LDS.128 per thread per demand step = 5 B per evaluation (products p*(fv+L) tabulated once "
+                        "per CTA, row offsets, p*gamma) against sdpb_microbench's LDS.128 rate; ncu: fp64 pipe 68 % and "
+                        "L1/shared data pipe 75 % busy at the same time (profiles/r02_c4_q2m_mix.txt)"}
+            out["roofline"]["frac_note"] = (
+                "round-2 kernel before the products were shared (bi_lead_q2, 4.125 fp64 instructions per evaluation): "
+                "141.6 ms at frac 0.79; this kernel: fewer instructions per evaluation, shorter solve, lower frac. The same "
+                "evaluations/s on the earlier formulation would need %.2f of the fp64 rate."
+                % (value * 4.125 / 1e12 / world / peaks["nofma_tops"]))
         out.update(verify)
         if period_profile:
             out["period_profile"] = period_profile

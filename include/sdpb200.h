@@ -221,6 +221,9 @@ typedef enum sdpb_kernel_choice {
     SDPB_KERNEL_LEAD_Q2 = 9,  /* lead time 2: a thread owns 8 preQ1 levels of one (x, preQ2), walks every action
                                  itself and reads V_{t+1} through a transposed copy; AUTO picks it when the
                                  model is not folded */
+    SDPB_KERNEL_LEAD_Q2M = 14,/* reported only: SDPB_KERNEL_LEAD_Q2 with the products p*(fixed + variable + level cost) formed once
+                                 per CTA and action in shared memory and two preQ2 columns per thread; chosen on large grids
+                                 (no action slices); request SDPB_KERNEL_LEAD_Q2 to get either */
     SDPB_KERNEL_TWO_PRODUCT_ROW = 10, /* reported only: two-product kernel that shares the cash-independent terms
                                          of an (action, demand) pair across a row of cash levels (integer prices) */
     SDPB_KERNEL_CASH_ROW = 12,/* reported only: cash-constraint kind on any cash grid; a CTA is one inventory level x 128

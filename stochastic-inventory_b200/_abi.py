@@ -32,6 +32,7 @@ F_CLAMP_INV, F_LOST_SALES, F_GY_MODE, F_NO_ORDER_LAST, F_CASH_LIMITED_ACTIONS = 
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED, KERNEL_STAGED, KERNEL_CASH_INT, KERNEL_TILED2, KERNEL_LEAD_SLAB = 0, 1, 2, 3, 4, 5, 6
 KERNEL_LEAD_COL, KERNEL_CASH_DIAG, KERNEL_LEAD_Q2, KERNEL_TWO_PRODUCT_ROW, KERNEL_FUSED, KERNEL_CASH_ROW = 7, 8, 9, 10, 11, 12
 KERNEL_CASH_TAIL = 13
+KERNEL_LEAD_Q2M = 14  # reported only
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

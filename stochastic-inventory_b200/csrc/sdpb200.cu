@@ -573,7 +573,7 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
                                      (int)(rlo / per_x), (int)(rhi / per_x), h->stream, ps, nps, &shared_products);
             // per evaluation: (mul, add, mul, add) + one cost per 8 -- or, with the products p*(fv + L) shared by the
             // CTA (bi_lead_q2m), (add, mul, add); the last period has no continuation term
-            if (shared_products) h->stats.fp64_ops += ev * (last ? 1.0 : 3.0);
+            if (shared_products) { h->stats.fp64_ops += ev * (last ? 1.0 : 3.0); h->stats.kernel_used = SDPB_KERNEL_LEAD_Q2M; }
             else h->stats.fp64_ops += ev * (last ? (1.0 + 2.0 * kQ2YT) / kQ2YT : (1.0 + 4.0 * kQ2YT) / kQ2YT);
             return rc;
         }
@@ -992,6 +992,7 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     if (opt) h->opt = *opt;
     else { h->opt.struct_size = sizeof(sdpb_options); h->opt.device = -1; h->opt.shard_count = 1; }
     if (h->opt.shard_count < 1) h->opt.shard_count = 1;
+    if (h->opt.kernel == SDPB_KERNEL_LEAD_Q2M) h->opt.kernel = SDPB_KERNEL_LEAD_Q2;  // a reported-only name: the library chooses between the two
     if (h->opt.shard_rank < 0 || h->opt.shard_rank >= h->opt.shard_count)
         return fail_create(h, SDPB_ERR_ARG, "shard_rank out of range");
 

@@ -38,7 +38,7 @@ def main():
             Vo, Qo, evals, _ = O.dense(spec)
             with S.Solver(spec, kernel=S.KERNEL_LEAD_Q2) as s:
                 s.solve()
-                assert s.stats()["kernel_used"] == S.KERNEL_LEAD_Q2
+                assert s.stats()["kernel_used"] == S.KERNEL_LEAD_Q2M
                 for t in range(1, spec.T + 1):
                     V, Q = s.period_tables(t)
                     assert np.array_equal(V, Vo[t - 1]) and np.array_equal(Q, Qo[t - 1]), (D, rep, t, spec)

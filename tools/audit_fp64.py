@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 KERNEL_NAMES = {1: "bi_generic", 2: "bi_inv_tiled", 3: "bi_backorder_staged", 4: "bi_cash_int", 5: "bi_inv_tiled2",
-                6: "bi_lead_slab", 7: "bi_lead_col", 8: "bi_cash_diag (+ bi_cash_int in period T)", 9: "bi_lead_q2",
+                6: "bi_lead_slab", 7: "bi_lead_col", 8: "bi_cash_diag (+ bi_cash_int in period T)", 9: "bi_lead_q2", 14: "bi_lead_q2m",
                 10: "bi_two_product_row", 11: "bi_inv_fused", 12: "bi_cash_row", 13: "bi_cash_tail"}
 
 
