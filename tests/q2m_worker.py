@@ -26,19 +26,22 @@ def consecutive_pmf(rng, T, D):
 def main():
     O.load()
     rng = np.random.default_rng(20260)
-    n = 0
+    n = shared = 0
     for D in (1, 3, 9, 10, 11, 19, 20, 25):
         for rep in range(2):
             T = int(rng.integers(2, 4))
             spec = S.leadtime_model(consecutive_pmf(rng, T, D), fixed_cost=float(rng.integers(0, 9)),
                                     vari_cost=float(rng.integers(0, 3)) + 0.25 * rep, hold_cost=float(rng.integers(1, 4)),
-                                    penalty_cost=float(rng.integers(2, 12)), max_order=int(rng.integers(1, 27)),
+                                    penalty_cost=float(rng.integers(2, 12)),
+                                    max_order=int(rng.integers(30, 61)) if rep == 0 else int(rng.integers(1, 30)),
                                     inv_min=-float(rng.integers(2, 12)), inv_max=float(rng.integers(3, 14)), lead_time=2,
                                     clamp=True)
             Vo, Qo, evals, _ = O.dense(spec)
             with S.Solver(spec, kernel=S.KERNEL_LEAD_Q2) as s:
                 s.solve()
-                assert s.stats()["kernel_used"] == S.KERNEL_LEAD_Q2M
+                used = s.stats()["kernel_used"]   # tiny order ranges (tables larger than the budget) stay on bi_lead_q2
+                assert used in (S.KERNEL_LEAD_Q2, S.KERNEL_LEAD_Q2M)
+                shared += used == S.KERNEL_LEAD_Q2M
                 for t in range(1, spec.T + 1):
                     V, Q = s.period_tables(t)
                     assert np.array_equal(V, Vo[t - 1]) and np.array_equal(Q, Qo[t - 1]), (D, rep, t, spec)
@@ -49,7 +52,8 @@ def main():
                     V, Q = g.period_tables(t)
                     assert np.array_equal(V, Vo[t - 1]) and np.array_equal(Q, Qo[t - 1]), ("group", D, rep, t, spec)
             n += 1
-    print(f"q2m worker: {n} instances ok (SDPB_Q2_SPLIT={os.environ.get('SDPB_Q2_SPLIT', '-')})")
+    assert shared >= 8, shared   # (the wide order ranges of rep 0 always fit the shared-memory budget)
+    print(f"q2m worker: {n} instances ok, {shared} on the shared-product kernel (SDPB_Q2_SPLIT={os.environ.get('SDPB_Q2_SPLIT', '-')})")
 
 
 if __name__ == "__main__":

@@ -32,6 +32,7 @@ def cases():
         "tiled_c5": (lambda: c.c5(n_states=200_000, T=3), dict(kernel=S.KERNEL_TILED)),
         "fused_c1": (lambda: c.c1(), dict(kernel=S.KERNEL_FUSED)),
         "q2_c4": (lambda: c.c4(T=3, inv_half=40), dict()),
+        "q2m_c4": (lambda: c.c4(T=2), dict()),   # the full grid: an unsliced launch, so the shared-product kernel
         "col_c4": (lambda: c.c4(T=3, inv_half=40), dict(kernel=S.KERNEL_LEAD_COL)),
         "slab_c4": (lambda: c.c4(T=3, inv_half=40), dict(kernel=S.KERNEL_LEAD_SLAB)),
         "staged_c4": (lambda: c.c4(T=3, inv_half=40), dict(kernel=S.KERNEL_STAGED)),
