@@ -261,38 +261,6 @@ inline void plan_cash(CashPlan& P, const sdpb_model& m, const DevModel& d, const
     P.available = true;
 }
 
-// Optimum over the action slices of one state: slices in ascending order hold ascending actions, so a strict compare
-// keeps the first optimum (Recursion.java:146-157); a slice that held no feasible action of the state says kNoAction.
-// A peer shard's V tables as this shard addresses them: V_t[idx] of the peer is at base0 + (t-1)*stride + idx*8 (the
-// base is biased by the peer's window start), and the peer reads rows [lo, hi) of this shard's block.
-struct DevPeer { char* base0; unsigned long long stride; long long lo, hi; };
-
-// Multi-GPU: the merged values a peer reads are stored into the peer's table as well (peer-mapped memory), so the
-// cash models -- where every shard reads nearly every row: 7 peers at 8 GPUs -- need no copy after the kernel either.
-template <bool IS_MIN>
-__global__ void __launch_bounds__(256)
-merge_action_slices(const double* __restrict__ sv, const int* __restrict__ sa, int parts, long long n_local,
-                    double* __restrict__ Vt, int* __restrict__ Qt, long long lo, const DevPeer* __restrict__ peers,
-                    int n_peers, int t) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_local) return;
-    double best = IS_MIN ? DBL_MAX : -DBL_MAX;
-    int arg = kNoAction;
-    for (int q = 0; q < parts; q++) {
-        const double v = sv[(long long)q * n_local + i];
-        const int av = sa[(long long)q * n_local + i];
-        if (av != kNoAction && (IS_MIN ? (v < best) : (v > best))) { best = v; arg = av; }
-    }
-    Vt[i] = best;
-    Qt[i] = arg == kNoAction ? -1 : arg;
-    const long long idx = lo + i;
-    for (int p = 0; p < n_peers; p++) {
-        const DevPeer pr = peers[p];
-        if (idx >= pr.lo && idx < pr.hi)
-            reinterpret_cast<double*>(pr.base0 + (unsigned long long)(t - 1) * pr.stride)[idx] = best;
-    }
-}
-
 // Shape of a bi_cash_int launch over [lo, hi): R = 16 cash levels per thread in the last period when the grid is large
 // enough, and the action range cut into slices when the launch would otherwise leave the GPU short of CTAs.
 struct CashIntShape { bool wide; int tile, parts; dim3 grid; };

@@ -515,6 +515,39 @@ inline int launch_col(const ColPlan& P, const DevModel& dm, int t, int D, int pm
     return SDPB_OK;
 }
 
+// ---- action slices over separate CTAs (bi_cash_diag, bi_cash_int, bi_lead_q2m): one merge kernel ----
+// Optimum over the action slices of one state: slices in ascending order hold ascending actions, so a strict compare
+// keeps the first optimum (Recursion.java:146-157); a slice that held no feasible action of the state says kNoAction.
+// A peer shard's V tables as this shard addresses them: V_t[idx] of the peer is at base0 + (t-1)*stride + idx*8 (the
+// base is biased by the peer's window start), and the peer reads rows [lo, hi) of this shard's block.
+struct DevPeer { char* base0; unsigned long long stride; long long lo, hi; };
+
+// Multi-GPU: the merged values a peer reads are stored into the peer's table as well (peer-mapped memory), so the
+// cash models -- where every shard reads nearly every row: 7 peers at 8 GPUs -- need no copy after the kernel either.
+template <bool IS_MIN>
+__global__ void __launch_bounds__(256)
+merge_action_slices(const double* __restrict__ sv, const int* __restrict__ sa, int parts, long long n_local,
+                    double* __restrict__ Vt, int* __restrict__ Qt, long long lo, const DevPeer* __restrict__ peers,
+                    int n_peers, int t) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_local) return;
+    double best = IS_MIN ? DBL_MAX : -DBL_MAX;
+    int arg = kNoAction;
+    for (int q = 0; q < parts; q++) {
+        const double v = sv[(long long)q * n_local + i];
+        const int av = sa[(long long)q * n_local + i];
+        if (av != kNoAction && (IS_MIN ? (v < best) : (v > best))) { best = v; arg = av; }
+    }
+    Vt[i] = best;
+    Qt[i] = arg == kNoAction ? -1 : arg;
+    const long long idx = lo + i;
+    for (int p = 0; p < n_peers; p++) {
+        const DevPeer pr = peers[p];
+        if (idx >= pr.lo && idx < pr.hi)
+            reinterpret_cast<double*>(pr.base0 + (unsigned long long)(t - 1) * pr.stride)[idx] = best;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // bi_lead_q2 — lead time 2, every action inside the thread (no cross-thread argopt, no barrier).
 //
@@ -543,6 +576,8 @@ struct Q2Args {
     long long f_begin, f_end; // flat thread range: f = (x * n_chunks + chunk) * nQ + preQ2
     int n_chunks, tpx;        // chunks of 8 levels along preQ1; threads per inventory row
     int half;                 // bi_lead_q2m: ceil(nQ / 2), the distance between a thread's two preQ2 columns
+    double* slice_v;          // bi_lead_q2m with the action range cut over gridDim.y: [slice][hi - lo] optima, merged by
+    int* slice_a;             // merge_action_slices (which also stores the peers' rows)
     int di_max, NRW;
     int parts;                // slices of the action range per CTA (1, 2 or 4): small grids cannot fill the GPU otherwise
     // Multi-GPU: rows of this shard's block that a peer reads are stored into the peer's V_t as well, straight from the
@@ -818,9 +853,14 @@ bi_lead_q2m(const __grid_constant__ DevModel M, const __grid_constant__ Q2Args a
     const int colb = has_b ? half : 0;                   // a thread without a second column gathers the first one twice
     const double vt = M.v_t[a.t - 1];
 
-    const int per_part = (M.max_order_idx + PARTS) / PARTS;  // ceil(A / PARTS)
-    const int ai_begin = part * per_part;
-    const int ai_end = min(M.max_order_idx + 1, ai_begin + per_part);
+    // the action range: first cut over gridDim.y (separate CTAs, merged by merge_action_slices: small grids need more
+    // CTAs than their states give), then over the PARTS thread groups of the CTA
+    const int n_sl = (int)gridDim.y, sl = (int)blockIdx.y;
+    const int per_sl = (M.max_order_idx + n_sl) / n_sl;      // ceil(A / n_sl)
+    const int sl_begin = sl * per_sl, sl_end = min(M.max_order_idx + 1, sl_begin + per_sl);
+    const int per_part = (sl_end - sl_begin + PARTS - 1) / PARTS;
+    const int ai_begin = sl_begin + part * per_part;
+    const int ai_end = min(sl_end, ai_begin + per_part);
     if (!LAST) cb += (long long)ai_begin * nQ;
     double* MTp = MT + (size_t)(part * NG) * D * YT;
     // the builder's entries e = col, col + cols, ...: slot k = e & 7 is fixed, (group, demand) advance by cols / 8
@@ -923,6 +963,11 @@ bi_lead_q2m(const __grid_constant__ DevModel M, const __grid_constant__ Q2Args a
                 const int av = BA[(c2 * YT + k) * NT + q * cols + col];
                 if (av != kNoAction && (IS_MIN ? (v < best) : (v > best))) { best = v; arg = av; }
             }
+            if (n_sl > 1) {  // this CTA saw one slice of the actions only
+                a.slice_v[(long long)sl * (a.hi - a.lo) + (idx - a.lo)] = best;
+                a.slice_a[(long long)sl * (a.hi - a.lo) + (idx - a.lo)] = arg;
+                continue;
+            }
             a.Vt[idx] = best;
             a.Qt[idx] = arg == kNoAction ? -1 : arg;
             for (int p = 0; p < a.n_peer; p++)
@@ -957,65 +1002,92 @@ inline Q2Plan plan_q2(const sdpb_model& m, const DevModel& d, int D, const int* 
 // [row0, row1): inventory rows of V_{t+1} the range [lo, hi) can read (sdpb_shard_reads); only those are transposed.
 constexpr int kQ2MaxPeers = 2;
 
+// How a launch over [lo, hi) is shaped.  Enough warps for ~6 waves: nothing to do.  Otherwise the action range is cut:
+// with the shared-product kernel over separate CTAs (gridDim.y slices, merged by merge_action_slices -- the per-action
+// product table is then still built by a full CTA), else over 2 or 4 thread groups inside a CTA of bi_lead_q2.
+struct Q2Shape { bool shared; int parts, slices, half, tpx, NRW; long long f_begin, f_end; Q2mLayout L; };
+
+inline Q2Shape q2_shape(const Q2Plan& P, const DevModel& dm, int D, long long lo, long long hi, int sm_count) {
+    Q2Shape S{};
+    const long long per_x = (long long)dm.nQ * dm.nQ;
+    const long long rows = (hi - 1) / per_x - lo / per_x + 1;
+    const double waves = (double)(rows * P.tpx) / 32.0 / (16.0 * sm_count);
+    S.parts = waves >= 6.0 ? 1 : (waves >= 3.0 ? 2 : 4);
+    static const int env_split = [] { const char* e2 = std::getenv("SDPB_Q2_SPLIT"); return e2 ? std::atoi(e2) : 0; }();
+    if (env_split) S.parts = env_split == 1 ? 1 : env_split == 2 ? 2 : 4;  // tuning knobs, read once per process
+    static const bool no_share = std::getenv("SDPB_Q2_NOSHARE") != nullptr;
+    static const bool force_share = std::getenv("SDPB_Q2_SHARE") != nullptr;
+    static const int env_slices = [] { const char* e2 = std::getenv("SDPB_Q2_SLICES"); return e2 ? std::atoi(e2) : 0; }();
+    S.half = (dm.nQ + 1) / 2;
+    const int tpx2 = P.n_chunks * S.half;
+    const int NRW2 = P.n_chunks * kQ2YT + D + kQ2PAD + (P.NT + tpx2 - 1) / tpx2 + 1;
+    S.slices = 1;
+    // bi_lead_q2m whenever its tables leave four CTAs per SM; its threads are numbered over (x, chunk, column pair)
+    const Q2mLayout L1 = q2m_layout(NRW2, D, P.NT, 1, S.half);
+    if (!no_share && !force_share && !env_split && L1.smem <= 56 * 1024) {
+        S.shared = true; S.parts = 1; S.L = L1;
+        const double ctas = (double)(rows * tpx2) / P.NT;
+        const double w = ctas / (4.0 * sm_count);                // CTA waves at four CTAs per SM
+        if (w < 8.0) S.slices = (int)std::min(8.0, std::ceil(8.0 / std::max(w, 0.01)));
+        if (env_slices) S.slices = env_slices;
+        S.slices = std::max(1, std::min(S.slices, (dm.max_order_idx + 1) / 8));
+        const int per = (dm.max_order_idx + S.slices) / S.slices;  // as the kernel cuts: no empty slice
+        S.slices = (dm.max_order_idx + per) / per;
+    } else {
+        S.L = q2m_layout(NRW2, D, P.NT, S.parts, S.half);
+        S.shared = !no_share && (S.parts == 1 || force_share) && S.L.smem <= 56 * 1024;
+    }
+    S.tpx = S.shared ? tpx2 : P.tpx;
+    S.NRW = S.shared ? NRW2 : P.NRW;
+    S.f_begin = (lo / per_x) * S.tpx;
+    S.f_end = ((hi - 1) / per_x + 1) * S.tpx;
+    return S;
+}
+
 inline int launch_q2(const Q2Plan& P, const DevModel& dm, int t, int D, int pmf_off, const double* Vn, double* VnT,
                      double* Vt, int* Qt, long long lo, long long hi, int row0, int row1, cudaStream_t stream,
-                     const PeerStore* peers = nullptr, int n_peers = 0, bool* shared_products = nullptr) {
+                     const PeerStore* peers = nullptr, int n_peers = 0, bool* shared_products = nullptr,
+                     double* slice_v = nullptr, int* slice_a = nullptr, size_t slice_cap = 0,
+                     const DevPeer* d_peers = nullptr, int n_dev_peers = 0, int* slices_used = nullptr) {
     if (hi <= lo) return SDPB_OK;
     const bool last = (Vn == nullptr), mn = dm.is_min != 0;  // period T without a terminal table
     if (!last) {
         const unsigned tiles = (unsigned)((dm.nQ + 31) / 32);
         transpose_q2a<<<dim3((unsigned)(row1 - row0), tiles, tiles), dim3(32, 8), 0, stream>>>(Vn, VnT, dm.nQ, row0);
     }
-    Q2Args a;
-    a.t = t; a.D = D; a.pmf_off = pmf_off; a.VnT = last ? nullptr : VnT; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
-    a.n_chunks = P.n_chunks; a.tpx = P.tpx; a.di_max = P.di_max; a.NRW = P.NRW;
-    a.n_peer = 0;
-    for (int p = 0; p < kQ2MaxPeers; p++) { a.peer_v[p] = nullptr; a.peer_lo[p] = a.peer_hi[p] = 0; }
-    for (int p = 0; p < n_peers && p < kQ2MaxPeers; p++) {
-        a.peer_v[p] = peers[p].v; a.peer_lo[p] = peers[p].lo; a.peer_hi[p] = peers[p].hi;
-        a.n_peer = p + 1;
-    }
-    const long long per_x = (long long)dm.nQ * dm.nQ;
-    a.f_begin = (lo / per_x) * P.tpx;
-    a.f_end = ((hi - 1) / per_x + 1) * P.tpx;
-    // slices of the action range per CTA: enough warps for ~6 waves of 16 warps per SM
     int sm_count = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    const double waves = (double)(a.f_end - a.f_begin) / 32.0 / (16.0 * sm_count);
-    a.parts = waves >= 6.0 ? 1 : (waves >= 3.0 ? 2 : 4);
-    static const int env_split = [] { const char* e2 = std::getenv("SDPB_Q2_SPLIT"); return e2 ? std::atoi(e2) : 0; }();
-    if (env_split) a.parts = env_split == 1 ? 1 : env_split == 2 ? 2 : 4;  // tuning knob, read once per process
+    const Q2Shape S = q2_shape(P, dm, D, lo, hi, sm_count);
+    const long long n_local = hi - lo;
+    if (S.slices > 1 && (size_t)S.slices * (size_t)n_local > slice_cap) return SDPB_ERR_NOMEM;  // the caller sizes it: q2_shape
+    Q2Args a;
+    a.t = t; a.D = D; a.pmf_off = pmf_off; a.VnT = last ? nullptr : VnT; a.Vt = Vt; a.Qt = Qt; a.lo = lo; a.hi = hi;
+    a.n_chunks = P.n_chunks; a.tpx = S.tpx; a.di_max = P.di_max; a.NRW = S.NRW;
+    a.f_begin = S.f_begin; a.f_end = S.f_end; a.parts = S.parts; a.half = S.half;
+    a.slice_v = slice_v; a.slice_a = slice_a;
+    a.n_peer = 0;
+    for (int p = 0; p < kQ2MaxPeers; p++) { a.peer_v[p] = nullptr; a.peer_lo[p] = a.peer_hi[p] = 0; }
+    if (S.slices == 1)  // (a sliced launch leaves the peers' rows to the merge kernel)
+        for (int p = 0; p < n_peers && p < kQ2MaxPeers; p++) {
+            a.peer_v[p] = peers[p].v; a.peer_lo[p] = peers[p].lo; a.peer_hi[p] = peers[p].hi;
+            a.n_peer = p + 1;
+        }
+    if (shared_products) *shared_products = S.shared;
+    if (slices_used) *slices_used = S.slices;
     const int cols = P.NT / a.parts;
+    const Q2mLayout L = S.L;
+    const bool shared = S.shared;
     cudaError_t e = cudaSuccess;
-    // bi_lead_q2m (products shared through shared memory, two preQ2 columns per thread) whenever its tables leave
-    // four CTAs per SM; its threads are numbered over (x, chunk, column pair)
-    static const bool no_share = std::getenv("SDPB_Q2_NOSHARE") != nullptr;  // A/B knob, read once per process
-    const int half = (dm.nQ + 1) / 2;
-    const int tpx2 = P.n_chunks * half;
-    const int NRW2 = P.n_chunks * kQ2YT + D + kQ2PAD + (P.NT + tpx2 - 1) / tpx2 + 1;
-    const Q2mLayout L = q2m_layout(NRW2, D, P.NT, a.parts, half);
-    // (measured on C4, ms: whole grid 132.6 vs 140.3; half 69.1 vs 71.7; a quarter -- two action slices -- 37.8 vs 36.7; an
-    //  eighth -- four slices -- 20.8 vs 18.7: the per-action tables and the barrier cost more than they save once the
-    //  action range is sliced, so sliced launches stay on bi_lead_q2)
-    static const bool force_share = std::getenv("SDPB_Q2_SHARE") != nullptr;
-    const bool shared = !no_share && (a.parts == 1 || force_share) && L.smem <= 56 * 1024;
-    if (shared_products) *shared_products = shared;
-    a.half = half;
-    if (shared) {
-        a.tpx = tpx2; a.NRW = NRW2;
-        a.f_begin = (lo / per_x) * tpx2;
-        a.f_end = ((hi - 1) / per_x + 1) * tpx2;
-    }
-    const long long blocks = (a.f_end - a.f_begin + cols - 1) / cols;
+    const dim3 grid((unsigned)((a.f_end - a.f_begin + cols - 1) / cols), (unsigned)S.slices);
 #define SDPB_Q2_LAUNCH(MN, LS, PT)                                                                     \
     if (shared) {                                                                                      \
         auto k = bi_lead_q2m<MN, LS, 128, PT>;                                                         \
         if (L.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem); \
-        if (e == cudaSuccess) k<<<(unsigned)blocks, 128, L.smem, stream>>>(dm, a);                     \
+        if (e == cudaSuccess) k<<<grid, 128, L.smem, stream>>>(dm, a);                                 \
     } else {                                                                                           \
         auto k = bi_lead_q2<MN, LS, 128, PT>;                                                          \
         if (P.smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem); \
-        if (e == cudaSuccess) k<<<(unsigned)blocks, 128, P.smem, stream>>>(dm, a);                     \
+        if (e == cudaSuccess) k<<<grid.x, 128, P.smem, stream>>>(dm, a);                               \
     }
 #define SDPB_Q2_NT(MN, LS)                                                                             \
     switch (a.parts) {                                                                                 \
@@ -1028,6 +1100,12 @@ inline int launch_q2(const Q2Plan& P, const DevModel& dm, int t, int D, int pmf_
 #undef SDPB_Q2_NT
 #undef SDPB_Q2_LAUNCH
     if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+    if (S.slices > 1) {
+        const unsigned mb = (unsigned)((n_local + 255) / 256);
+        if (mn) merge_action_slices<true><<<mb, 256, 0, stream>>>(slice_v, slice_a, S.slices, n_local, Vt + lo, Qt + lo, lo, d_peers, n_dev_peers, t);
+        else merge_action_slices<false><<<mb, 256, 0, stream>>>(slice_v, slice_a, S.slices, n_local, Vt + lo, Qt + lo, lo, d_peers, n_dev_peers, t);
+        if (cudaGetLastError() != cudaSuccess) return SDPB_ERR_CUDA;
+    }
     return SDPB_OK;
 }
 

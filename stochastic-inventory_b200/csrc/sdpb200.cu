@@ -144,6 +144,9 @@ struct sdpb_handle {
     double reach_cnt[3] = {0, 0, 0};
     PeerLink peer;
     bool push_fused = false;   // the period's kernel already stored the peers' rows into their tables (bi_lead_q2)
+    double* q2_slice_v = nullptr;  // bi_lead_q2m with action slices over separate CTAs: per slice and state the slice's optimum
+    int* q2_slice_a = nullptr;
+    size_t q2_slice_cap = 0;
     std::vector<cudaEvent_t> prof_ev;  // profile = 1: 4 events per period
     std::vector<double> prof_ms;       // [3 * T] of the last sharded solve
     std::string err;
@@ -560,7 +563,21 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
             PeerStore ps[kQ2MaxPeers];
             int nps = 0;
             h->push_fused = false;
-            if (h->peer.attached && t > 1 && !h->peer.sends.empty() && h->peer.sends.size() <= (size_t)kQ2MaxPeers) {
+            const bool pushing = h->peer.attached && t > 1 && !h->peer.sends.empty();
+            // a launch whose action range is cut over separate CTAs needs one (value, action) entry per slice and state
+            const Q2Shape shape = q2_shape(qp, h->dm, h->pmf_len[t - 1], lo, hi, h->sm_count);
+            if (shape.slices > 1) {
+                const size_t need = (size_t)shape.slices * (size_t)(hi - lo);
+                if (need > h->q2_slice_cap) {
+                    void* p = nullptr;
+                    CU(dev_alloc(h, &p, need * sizeof(double)));
+                    h->q2_slice_v = (double*)p;
+                    CU(dev_alloc(h, &p, need * sizeof(int)));
+                    h->q2_slice_a = (int*)p;
+                    h->q2_slice_cap = need;
+                }
+                if (pushing) h->push_fused = true;  // merge_action_slices stores the peers' rows
+            } else if (pushing && h->peer.sends.size() <= (size_t)kQ2MaxPeers) {
                 for (const PeerSend& sd : h->peer.sends) {
                     const PeerInfo& pi = h->peer.info[sd.rank];
                     char* base = h->peer.mapped[sd.rank] + pi.v_off0 + (size_t)(t - 1) * pi.v_stride;
@@ -569,8 +586,14 @@ int run_period_kernel(sdpb_handle* h, int t, const double* Vn, double* Vt, int* 
                 h->push_fused = true;
             }
             bool shared_products = false;
+            int slices_used = 1;
+            const bool merge_pushes = pushing && shape.slices > 1;
             const int rc = launch_q2(qp, h->dm, t, h->pmf_len[t - 1], h->pmf_off[t - 1], Vn, h->dVT, Vt, Qt, lo, hi,
-                                     (int)(rlo / per_x), (int)(rhi / per_x), h->stream, ps, nps, &shared_products);
+                                     (int)(rlo / per_x), (int)(rhi / per_x), h->stream, ps, nps, &shared_products,
+                                     h->q2_slice_v, h->q2_slice_a, h->q2_slice_cap,
+                                     merge_pushes ? (const DevPeer*)h->peer.d_peers : nullptr,
+                                     merge_pushes ? (int)h->peer.sends.size() : 0, &slices_used);
+            if (rc == SDPB_OK && slices_used > 1) h->stats.launches++;  // merge_action_slices
             // per evaluation: (mul, add, mul, add) + one cost per 8 -- or, with the products p*(fv + L) shared by the
             // CTA (bi_lead_q2m), (add, mul, add); the last period has no continuation term
             if (shared_products) { h->stats.fp64_ops += ev * (last ? 1.0 : 3.0); h->stats.kernel_used = SDPB_KERNEL_LEAD_Q2M; }
