@@ -1,3 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python tools/time_shards.py c4 1 2 4 8
-for s in 2 4 16; do echo "slices $s"; SDPB_Q2_SLICES=$s python tools/time_shards.py c4 8 4; done
+cd $GRAFT_REPO_ROOT
+timeout 900 python bench.py --steps 20 --warmup 3 2> gpurun_out/r02_bench_n1.err | grep -a "^{" > gpurun_out/r02_bench_n1.json; python tools/show_bench.py gpurun_out/r02_bench_n1.json | head -14
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2> gpurun_out/r02_bench_ref.err | grep -a "^{" > gpurun_out/r02_bench_reference_arm.json; head -c 300 gpurun_out/r02_bench_reference_arm.json; echo
