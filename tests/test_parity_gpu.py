@@ -720,16 +720,22 @@ def test_solve_batch_wide(S, oracle):
         s.close()
 
 
-@pytest.mark.parametrize("split", ["1", "2", "4"])
+@pytest.mark.parametrize("split", ["default", "1", "2", "4"])
 def test_lead_q2m_forced(split):
     """bi_lead_q2m (products p*(fv + L) shared through shared memory, two preQ2 columns per thread) is chosen by itself
-    only on large unsliced grids (the full-size C4 tests); here it is forced onto 16 small random lead-time-2 instances,
-    with 1, 2 and 4 action slices per CTA, unsharded and as a three-shard group.  The knobs are read once per process,
-    hence the subprocess."""
+    on 16 small random lead-time-2 instances, unsharded and as a three-shard group: as the library shapes the launch
+    by itself (action slices over separate CTAs + merge kernel), and forced to 1, 2 and 4 action slices inside a CTA.
+    The knobs are read once per process, hence the subprocess."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, SDPB_Q2_SHARE="1", SDPB_Q2_SPLIT=split)
+    env = dict(os.environ)
+    if split == "default":
+        # no knob: on these small grids the library cuts the action range over separate CTAs (gridDim.y) and merges
+        # with merge_action_slices -- the path the multi-GPU shards of C4 take
+        env.pop("SDPB_Q2_SHARE", None), env.pop("SDPB_Q2_SPLIT", None)
+    else:
+        env.update(SDPB_Q2_SHARE="1", SDPB_Q2_SPLIT=split)
     worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "q2m_worker.py")
     r = subprocess.run([sys.executable, worker], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
