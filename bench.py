@@ -33,7 +33,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 REF_F = {"c1": 20, "c2": 20, "c3": 41, "c4": 20, "c5": 20}  # fp64 ops per evaluation as written
 KERNEL_NAMES = {1: "bi_generic", 2: "bi_inv_tiled", 3: "bi_backorder_staged", 4: "bi_cash_int", 5: "bi_inv_tiled2",
-                6: "bi_lead_slab", 7: "bi_lead_col", 8: "bi_cash_diag", 9: "bi_lead_q2", 14: "bi_lead_q2m", 10: "bi_two_product_row",
+                6: "bi_lead_slab", 7: "bi_lead_col", 8: "bi_cash_diag", 9: "bi_lead_q2", 14: "bi_lead_q2m", 15: "collapsed_levels + collapsed_actions", 10: "bi_two_product_row",
                 11: "bi_inv_fused", 12: "bi_cash_row", 13: "bi_cash_tail"}
 METRIC = "state-action-demand evaluations/s (fp64), full-horizon SDP solve"
 UNIT = "evals/s"
@@ -723,6 +723,30 @@ def run_gpu(args):
                 b.close()
             for c in configs.values():
                 c["fp64_frac"] = c["fp64_tops_per_gpu"] / peak if peak else None
+            # OPT-IN, reported on its own and never in evals/s: the collapsed solve of the 1-D inventory family
+            # (G(y) per order-up-to level, then V(x) = opt_a cost(a) + G(x + a)); values within 1e-9 relative of the
+            # exact kernels (observed ~1e-13), not bit-identical, never chosen by AUTO.
+            sp = make_spec(S, "c5", 1, 10_000_000)
+            with S.Solver(sp, device=local) as ex, S.Solver(sp, device=local, kernel=S.KERNEL_COLLAPSED) as co:  # (rank 0's GPU)
+                ex.solve()
+                co.solve()
+                co.solve()
+                t0 = time.perf_counter()
+                reps = 5
+                for _ in range(reps):
+                    co.solve_async()
+                co.sync()
+                dt = (time.perf_counter() - t0) / reps
+                Ve, Qe = ex.period_tables(1)
+                Vc, Qc = co.period_tables(1)
+                st = co.stats()
+                out["collapsed_opt_in"] = {
+                    "workload": "c5_S1e7 (10,000,000 states x 200 actions x 200 demands, T=4)", "solve_ms": dt * 1e3,
+                    "exact_solve_ms": configs.get("c5_S1e7", {}).get("solve_ms"),
+                    "evals_reference": st["evals"], "evals_executed": st["evals_executed"],
+                    "max_rel_diff_V1_vs_exact_kernel": float(np.max(np.abs(Vc - Ve) / np.maximum(1.0, np.abs(Ve)))),
+                    "policy_agreement_period1": float((Qc == Qe).mean()),
+                    "note": "SDPB_KERNEL_COLLAPSED: opt-in, not bit-identical, not part of `value` or of any evals/s figure"}
     if rank == 0 and not args.no_configs:
         out["next_rows"] = next_rows(S, local)
     if rank == 0:

@@ -224,6 +224,13 @@ typedef enum sdpb_kernel_choice {
     SDPB_KERNEL_LEAD_Q2M = 14,/* reported only: SDPB_KERNEL_LEAD_Q2 with the products p*(fixed + variable + level cost) formed once
                                  per CTA and action in shared memory and two preQ2 columns per thread; chosen on large grids
                                  (no action slices); request SDPB_KERNEL_LEAD_Q2 to get either */
+    SDPB_KERNEL_COLLAPSED = 15,/* REQUEST ONLY, never chosen by AUTO, NOT bit-identical to the reference: the 1-D inventory family
+                                 solved as G(y) = sum_j p_j L(y-d_j) + p_j gamma V(y-d_j) per order-up-to level and
+                                 V(x) = opt_a ordering cost(a) + G(x+a) per state -- D operations per level and A per
+                                 state instead of A*D per state.  Values agree with the exact kernels to ~1e-13 relative
+                                 (the rounding of the demand sum and 1 - sum_j p_j); the optimal action can move between
+                                 actions whose values are that close.  Unsharded handles, no G(y) pass, no
+                                 SDPB_F_NO_ORDER_LAST; sdpb_create fails with SDPB_ERR_ARG otherwise */
     SDPB_KERNEL_TWO_PRODUCT_ROW = 10, /* reported only: two-product kernel that shares the cash-independent terms
                                          of an (action, demand) pair across a row of cash levels (integer prices) */
     SDPB_KERNEL_CASH_ROW = 12,/* reported only: cash-constraint kind on any cash grid; a CTA is one inventory level x 128

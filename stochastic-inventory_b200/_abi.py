@@ -33,6 +33,7 @@ KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED, KERNEL_STAGED, KERNEL_CASH_INT, KERNE
 KERNEL_LEAD_COL, KERNEL_CASH_DIAG, KERNEL_LEAD_Q2, KERNEL_TWO_PRODUCT_ROW, KERNEL_FUSED, KERNEL_CASH_ROW = 7, 8, 9, 10, 11, 12
 KERNEL_CASH_TAIL = 13
 KERNEL_LEAD_Q2M = 14  # reported only
+KERNEL_COLLAPSED = 15  # request only: opt-in, ~1e-13 relative, not bit-identical
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

@@ -22,6 +22,7 @@
 #include "kernel_cash.cuh"
 #include "kernel_two_product.cuh"
 #include "kernel_staff.cuh"
+#include "kernel_collapsed.cuh"
 #include "kernel_fused.cuh"
 #include "microbench.cuh"
 
@@ -147,6 +148,9 @@ struct sdpb_handle {
     double* q2_slice_v = nullptr;  // bi_lead_q2m with action slices over separate CTAs: per slice and state the slice's optimum
     int* q2_slice_a = nullptr;
     size_t q2_slice_cap = 0;
+    double* dG = nullptr;          // SDPB_KERNEL_COLLAPSED: G over the nI + max_order order-up-to levels
+    double* dLc = nullptr;         // ... and the level costs over [lc_il0, lc_il0 + n)
+    long long lc_il0 = 0;
     std::vector<cudaEvent_t> prof_ev;  // profile = 1: 4 events per period
     std::vector<double> prof_ms;       // [3 * T] of the last sharded solve
     std::string err;
@@ -854,6 +858,18 @@ int solve_period(sdpb_handle* h, int t) {
     // a boundary table in period T: the integer-exact cash kernels fold "last period" and "no continuation" into one
     // template flag, so that one period takes the general path
     const bool term_T = t == m.T && h->dTerm != nullptr;
+    if (h->opt.kernel == SDPB_KERNEL_COLLAPSED) {  // opt-in, not bit-identical (kernel_collapsed.cuh); validated by sdpb_create
+        rc = launch_collapsed(h->dm, t, D, h->pmf_off[t - 1], Vn, h->dLc, h->lc_il0, h->dG, h->dV[t - 1], h->dQ[t - 1], h->stream);
+        if (rc != SDPB_OK) { h->err = "collapsed kernel launch failed"; return rc; }
+        const double nY = (double)h->dm.nI + m.max_order_idx, nA = m.max_order_idx + 1.0;
+        h->solved[t - 1] = 1;
+        h->stats.kernel_used = SDPB_KERNEL_COLLAPSED;
+        h->stats.launches += 2;
+        h->stats.evals += count_evals_period(h, t);            // what the reference evaluates
+        h->stats.evals_executed += nY * D + (double)h->S * nA;  // level-demand pairs + state-action pairs
+        h->stats.fp64_ops += nY * D * (Vn ? 7.0 : 5.0) + (double)h->S * nA * 3.0;
+        return SDPB_OK;
+    }
     if (h->dedup) {
         // lead-time models: solve each distinct (x + preQ, ...) once, then broadcast (exact)
         rc = run_period_kernel<true>(h, t, Vn, h->dHv, h->dHa, 0, h->vS, plain);
@@ -1335,6 +1351,27 @@ int sdpb_create(const sdpb_model* m, const sdpb_options* opt, sdpb_handle** out)
     if (h->opt.kernel == SDPB_KERNEL_FUSED && !h->fused.ok)
         return fail_create(h, SDPB_ERR_ARG, "SDPB_KERNEL_FUSED needs an unsharded lead-0 backorder model with the "
                                             "inventory clamp, no G(y) pass and at most 64 states per SM");
+    if (h->opt.kernel == SDPB_KERNEL_COLLAPSED) {
+        if (!collapsed_ok(h->m) || h->opt.shard_count != 1 || h->dedup)
+            return fail_create(h, SDPB_ERR_ARG, "SDPB_KERNEL_COLLAPSED needs an unsharded lead-0 backorder model with the "
+                                                "inventory clamp, no G(y) pass and no SDPB_F_NO_ORDER_LAST");
+        void* p = nullptr;
+        if (dev_alloc(h, &p, ((size_t)h->dm.nI + h->m.max_order_idx + 1) * sizeof(double)) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "allocation of the level table failed");
+        h->dG = (double*)p;
+        int dmin = 0, dmax = 0;
+        bool long_pmf = false;
+        for (int v : h->pmf_di) { dmin = std::min(dmin, v); dmax = std::max(dmax, v); }
+        for (int len : h->pmf_len) long_pmf = long_pmf || len > 2000;
+        if (long_pmf) return fail_create(h, SDPB_ERR_ARG, "SDPB_KERNEL_COLLAPSED: demand support too long");
+        h->lc_il0 = -(long long)dmax;
+        const long long n_lc = (long long)h->dm.nI + h->m.max_order_idx - dmin + dmax + 1;
+        if (dev_alloc(h, &p, (size_t)n_lc * sizeof(double)) != cudaSuccess)
+            return fail_create(h, SDPB_ERR_NOMEM, "allocation of the level-cost table failed");
+        h->dLc = (double*)p;
+        collapsed_level_costs<<<(unsigned)((n_lc + 255) / 256), 256, 0, h->stream>>>(h->dm, h->lc_il0, n_lc, h->dLc);
+        if (cudaGetLastError() != cudaSuccess) return fail_create(h, SDPB_ERR_CUDA, "level-cost kernel launch failed");
+    }
     mark("planned");
     *out = h;
     return SDPB_OK;

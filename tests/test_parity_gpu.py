@@ -742,6 +742,48 @@ def test_lead_q2m_forced(split):
     assert "16 instances ok" in r.stdout
 
 
+def test_collapsed_kernel_is_opt_in_and_close(S, oracle):
+    """SDPB_KERNEL_COLLAPSED: G(y) per order-up-to level, then V(x) = opt_a cost(a) + G(x + a).  Opt-in, NOT bit-identical:
+    values within 1e-9 relative of the oracle (observed ~1e-13), the policy equal except between near-tied actions;
+    never chosen by AUTO; refused for models it does not cover."""
+    for case in (cases.case_A_small, cases.case_A_max, cases.case_A_twopoint, cases.case_A_halfstep,
+                 cases.case_A_sparse_pmf, cases.case_A_degenerate, cases.case_A_one_state, cases.case_A_terminal,
+                 cases.case_CLSP_main):
+        spec, _ = case()
+        Vo, Qo, evals, _ = oracle.dense(spec)
+        with S.Solver(spec, kernel=S.KERNEL_COLLAPSED) as s:
+            s.solve()
+            s.solve()   # the second solve replays the captured graph
+            st = s.stats()
+            assert st["kernel_used"] == S.KERNEL_COLLAPSED and st["evals"] == evals
+            agree = total = 0
+            for t in range(1, spec.T + 1):
+                V, Q = s.period_tables(t)
+                np.testing.assert_allclose(V, Vo[t - 1], rtol=1e-9, atol=1e-9, err_msg=f"{spec.name} t={t}")
+                agree += int((Q == Qo[t - 1]).sum())
+                total += Q.size
+            assert agree >= 0.98 * total, (spec.name, agree, total)
+        with S.Solver(spec) as s:                           # AUTO never picks it
+            assert s.solve().stats()["kernel_used"] != S.KERNEL_COLLAPSED
+    # a large grid against the exact GPU solve: C5 at 1e6 states
+    spec = S.configs.c5(n_states=1_000_000, T=3)
+    with S.Solver(spec) as ex, S.Solver(spec, kernel=S.KERNEL_COLLAPSED) as co:
+        ex.solve(), co.solve()
+        for t in range(1, spec.T + 1):
+            Ve, Qe = ex.period_tables(t)
+            Vc, Qc = co.period_tables(t)
+            np.testing.assert_allclose(Vc, Ve, rtol=1e-9)
+            assert (Qc == Qe).mean() > 0.999
+        assert co.stats()["evals"] == ex.stats()["evals"] and co.stats()["evals_executed"] < 0.02 * ex.stats()["evals"]
+    # refused where it does not apply
+    for bad in (cases.case_B2_small()[0], cases.case_C_int()[0], cases.case_A_nolast()[0], cases.case_A_gy()[0]):
+        with pytest.raises(S.SdpbError) as e:
+            S.Solver(bad, kernel=S.KERNEL_COLLAPSED)
+        assert e.value.code == S.abi.SDPB_ERR_ARG
+    with pytest.raises(S.SdpbError):
+        S.Solver(cases.case_A_small()[0], kernel=S.KERNEL_COLLAPSED, shard_rank=0, shard_count=2)
+
+
 def test_reference_style_driver_clsp_main(S, oracle):
     """Reads like src/capacitated/CLSP.java:196-290 (the self-contained demo with its own inline pmf)."""
     meanDemand = [9, 23, 53, 29]
