@@ -1,14 +1,6 @@
-python -m pytest tests -m gpu -x -q -k "collapsed" 2>&1 | tail -15
-python - <<'PY'
-import sys, time
-sys.path.insert(0, '.')
-import sdpb200 as S, numpy as np
-for n in (1_000_000, 10_000_000):
-    sp = S.configs.c5(n_states=n)
-    with S.Solver(sp, kernel=S.KERNEL_COLLAPSED) as co:
-        co.solve(); co.solve()
-        t0=time.perf_counter()
-        for _ in range(5): co.solve_async()
-        co.sync(); dt=(time.perf_counter()-t0)/5
-        print(n, "collapsed ms", dt*1e3, co.stats()["evals_executed"]/co.stats()["evals"])
-PY
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/r02_pytest_gpu.log; cat gpurun_out/r02_pytest_gpu.log
+timeout 900 python bench.py --steps 20 --warmup 3 2> gpurun_out/r02_bench_n1.err | grep -a "^{" > gpurun_out/r02_bench_n1.json; python tools/show_bench.py gpurun_out/r02_bench_n1.json | head -13
+python -c "
+import json; d=json.loads(open('gpurun_out/r02_bench_n1.json').read()); print(d.get('collapsed_opt_in'))"
+python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -2
