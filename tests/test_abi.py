@@ -174,3 +174,30 @@ def test_java_struct_layouts_match_layout_table():
             off += sizes[typ]
         assert off == lay[cname + ".sizeof"][0], jname
         assert len(fields) == sum(1 for k in lay if k.startswith(cname + ".")) - 1
+
+
+def test_python_constants_match_header_enums(S):
+    """Every enumerator of include/sdpb200.h that _abi.py mirrors has the header's value (kernel names, cost kinds,
+    quantisers, flags, status codes): a renumbered enum would otherwise select the wrong kernel silently."""
+    import re
+    text = open(os.path.join(ROOT, "include", "sdpb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    enums = dict(re.findall(r"\b(SDPB_[A-Z0-9_]+)\s*=\s*(\d+u?\s*<<\s*\d+|-?\d+)", text))
+    assert len(enums) >= 50, len(enums)
+
+    def val(expr):
+        m = re.match(r"(\d+)u?\s*<<\s*(\d+)", expr)
+        return int(m.group(1)) << int(m.group(2)) if m else int(expr)
+
+    A = S.abi
+    checked = 0
+    for name, expr in enums.items():
+        short = name[len("SDPB_"):]
+        for cand in (short, name):
+            if hasattr(A, cand):
+                assert getattr(A, cand) == val(expr), (name, getattr(A, cand), expr)
+                checked += 1
+                break
+    assert checked >= 40, checked
+    for k in ("KERNEL_LEAD_Q2M", "KERNEL_COLLAPSED", "KERNEL_CASH_TAIL", "KERNEL_LEAD_Q2"):
+        assert getattr(A, k) == val(enums["SDPB_" + k])
