@@ -26,6 +26,14 @@ abstract class GpuEngine implements AutoCloseable {
 
     /** `devices` == null: one GPU.  Otherwise the state grid is partitioned over the listed CUDA ordinals. */
     protected GpuEngine(MemorySegment model, int ndim, int[] devices, int allow) {
+        this(model, ndim, devices, allow, SdpB200.KERNEL_AUTO);
+    }
+
+    /**
+     * `kernel`: SdpB200.KERNEL_AUTO (every kernel the library picks by itself is bit-identical to the Java loop), or a
+     * request such as SdpB200.KERNEL_COLLAPSED (1-D inventory family only: G(y) per order-up-to level, ~1e-13 relative).
+     */
+    protected GpuEngine(MemorySegment model, int ndim, int[] devices, int allow, int kernel) {
         this.ndim = ndim;
         try {
             MemorySegment opt = arena.allocate(SdpB200.OPTIONS);
@@ -34,6 +42,7 @@ abstract class GpuEngine implements AutoCloseable {
             opt.set(JAVA_INT, SdpB200.OPTIONS.byteOffset(MemoryLayout.PathElement.groupElement("device")), -1);
             opt.set(JAVA_INT, SdpB200.OPTIONS.byteOffset(MemoryLayout.PathElement.groupElement("shard_count")), 1);
             opt.set(JAVA_INT, SdpB200.OPTIONS.byteOffset(MemoryLayout.PathElement.groupElement("allow")), allow);
+            opt.set(JAVA_INT, SdpB200.OPTIONS.byteOffset(MemoryLayout.PathElement.groupElement("kernel")), kernel);
             MemorySegment out = arena.allocate(ADDRESS);
             if (devices == null || devices.length < 2) {
                 int rc = (int) SdpB200.CREATE.invokeExact(model, opt, out);
@@ -103,6 +112,26 @@ abstract class GpuEngine implements AutoCloseable {
                 for (int k = 0; k < w; k++) arr[i][k] = buf.getAtIndex(JAVA_DOUBLE, (long) w * i + k);
             return arr;
         } catch (Throwable t) { throw new RuntimeException(t); }
+    }
+
+    /**
+     * Solve many independent single-GPU engines together (sdpb_solve_batch): the parameter sweeps of
+     * CLSPTesting.java:57-61 build hundreds of small recursions one after the other; here their periods run side by side
+     * as ONE CUDA graph (first call with a given list: plain solves; second: capture; later: replay).
+     */
+    public static void solveBatch(List<? extends GpuEngine> engines) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment hs = a.allocate(ADDRESS, Math.max(1, engines.size()));
+            for (int i = 0; i < engines.size(); i++) {
+                GpuEngine e = engines.get(i);
+                if (!e.group.equals(MemorySegment.NULL))
+                    throw new IllegalArgumentException("sdpb_solve_batch takes single-GPU engines");
+                hs.setAtIndex(ADDRESS, i, e.handle);
+            }
+            int rc = (int) SdpB200.SOLVE_BATCH.invokeExact(hs, engines.size());
+            if (rc != 0) throw new IllegalStateException("sdpb_solve_batch: " + SdpB200.lastError(engines.get(0).handle));
+            for (GpuEngine e : engines) e.solved = true;
+        } catch (RuntimeException r) { throw r; } catch (Throwable t) { throw new RuntimeException(t); }
     }
 
     /** Recursion.java:80-86 and siblings: the tables are produced in key order already. */

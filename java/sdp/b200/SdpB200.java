@@ -54,6 +54,10 @@ public final class SdpB200 {
             ADDRESS.withName("stream"), JAVA_INT.withName("allow"), JAVA_INT.withName("strict_cash_bounds"),
             JAVA_INT.withName("profile"), JAVA_INT.withName("reserved"));
 
+    /** enum sdpb_kernel_choice (include/sdpb200.h): the requests a host may make; sdpb_stats.kernel_used reports the rest. */
+    public static final int KERNEL_AUTO = 0, KERNEL_GENERIC = 1, KERNEL_TILED = 2, KERNEL_LEAD_Q2 = 9, KERNEL_FUSED = 11,
+            KERNEL_COLLAPSED = 15;
+
     /** struct sdpb_grid, field for field. */
     public static final StructLayout GRID = MemoryLayout.structLayout(
             JAVA_INT.withName("ndim"), JAVA_INT.withName("n_inv"), JAVA_INT.withName("n_cash"), JAVA_INT.withName("n_q"),
