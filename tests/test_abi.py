@@ -201,3 +201,9 @@ def test_python_constants_match_header_enums(S):
     assert checked >= 40, checked
     for k in ("KERNEL_LEAD_Q2M", "KERNEL_COLLAPSED", "KERNEL_CASH_TAIL", "KERNEL_LEAD_Q2"):
         assert getattr(A, k) == val(enums["SDPB_" + k])
+    # the (uncompiled) Java binding carries a few of them as literals
+    java = open(os.path.join(ROOT, "java", "sdp", "b200", "SdpB200.java")).read()
+    lits = re.findall(r"\b(KERNEL_[A-Z0-9_]+)\s*=\s*(\d+)", java)
+    assert len(lits) >= 5
+    for name, v in lits:
+        assert int(v) == val(enums["SDPB_" + name]), name
