@@ -1022,7 +1022,11 @@ inline Q2Shape q2_shape(const Q2Plan& P, const DevModel& dm, int D, long long lo
     const int tpx2 = P.n_chunks * S.half;
     const int NRW2 = P.n_chunks * kQ2YT + D + kQ2PAD + (P.NT + tpx2 - 1) / tpx2 + 1;
     S.slices = 1;
-    // bi_lead_q2m whenever its tables leave four CTAs per SM; its threads are numbered over (x, chunk, column pair)
+    // bi_lead_q2m whenever its tables leave four CTAs per SM; its threads are numbered over (x, chunk, column pair).
+    // Measured on C4 (ms, bi_lead_q2m vs bi_lead_q2): whole grid 131.0 vs 140.3.  Shards: with the action range cut over
+    // thread groups INSIDE a CTA the per-action tables and the barrier cost more than they save (a quarter of the grid
+    // 37.8 vs 36.7, an eighth 20.8 vs 18.7); cut over SEPARATE CTAs they do not (34.1 and 17.7; 2 / 4 / 8 / 16 slices on
+    // the eighth: 18.4 / 17.5 / 17.7 / 18.0), so that is the shape every launch takes when the tables fit.
     const Q2mLayout L1 = q2m_layout(NRW2, D, P.NT, 1, S.half);
     if (!no_share && !force_share && !env_split && L1.smem <= 56 * 1024) {
         S.shared = true; S.parts = 1; S.L = L1;
