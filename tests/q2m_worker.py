@@ -28,12 +28,12 @@ def main():
     rng = np.random.default_rng(20260)
     n = shared = 0
     for D in (1, 3, 9, 10, 11, 19, 20, 25):
-        for rep in range(2):
+        for rep in range(int(os.environ.get("SDPB_Q2M_REPS", "2"))):  # raise for a one-off campaign
             T = int(rng.integers(2, 4))
             spec = S.leadtime_model(consecutive_pmf(rng, T, D), fixed_cost=float(rng.integers(0, 9)),
                                     vari_cost=float(rng.integers(0, 3)) + 0.25 * rep, hold_cost=float(rng.integers(1, 4)),
                                     penalty_cost=float(rng.integers(2, 12)),
-                                    max_order=int(rng.integers(30, 61)) if rep == 0 else int(rng.integers(1, 30)),
+                                    max_order=int(rng.integers(30, 61)) if rep % 2 == 0 else int(rng.integers(1, 30)),
                                     inv_min=-float(rng.integers(2, 12)), inv_max=float(rng.integers(3, 14)), lead_time=2,
                                     clamp=True)
             Vo, Qo, evals, _ = O.dense(spec)
