@@ -306,6 +306,21 @@ class Engine {
     sdpb_stats stats() const { sdpb_stats s; sdpb_stats_get(h_, &s); return s; }
     sdpb_handle* handle() { return h_; }
 
+    // Many independent single-GPU engines solved together (sdpb_solve_batch): the parameter sweeps of
+    // CLSPTesting.java:57-61 build hundreds of small recursions one after the other; here their periods run side by
+    // side as ONE CUDA graph (first call with a given list: plain solves; second: capture; later: replay).
+    static void solveBatch(const std::vector<Engine*>& engines) {
+        std::vector<sdpb_handle*> hs;
+        for (Engine* e : engines) {
+            if (e->g_) throw SdpbError(SDPB_ERR_ARG, "sdpb_solve_batch takes single-GPU engines");
+            hs.push_back(e->h_);
+        }
+        if (hs.empty()) return;
+        const int rc = sdpb_solve_batch(hs.data(), (int)hs.size());
+        if (rc != SDPB_OK) throw SdpbError(rc, sdpb_last_error(hs[0]));
+        for (Engine* e : engines) e->solved_ = true;
+    }
+
  private:
     void check(int rc) const {
         if (rc != SDPB_OK) throw SdpbError(rc, sdpb_last_error(h_));
@@ -321,7 +336,9 @@ class Engine {
 // new Recursion(OptDirection, pmf, getFeasibleAction, stateTransition, immediateValue) -> new Recursion(model)
 class Recursion {
  public:
-    explicit Recursion(const Model& model, int device = -1) : e_(model, device) {}
+    // `kernel`: SDPB_KERNEL_AUTO -- every kernel the library picks by itself is bit-identical to the Java loop -- or a
+    // request, e.g. SDPB_KERNEL_COLLAPSED (G(y) per order-up-to level: ~1e-13 relative, opt-in)
+    explicit Recursion(const Model& model, int device = -1, int kernel = SDPB_KERNEL_AUTO) : e_(model, device, kernel) {}
     Recursion(const Model& model, const std::vector<int>& devices) : e_(model, devices) {}
     double getExpectedValue(const State& s) { return e_.valueAndAction(s.period, {s.iniInventory})[0]; }
     // Recursion.java:165-167 unboxes a null for a state that was never solved; the mirror throws too

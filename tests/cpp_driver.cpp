@@ -116,6 +116,19 @@ int main(int argc, char** argv) {
             LeadtimeState s0{1, 0, 0};
             const double hullValue = hull.getExpectedValue(s0);
             std::printf("I %.17g %.17g %.17g %.17g\n", hullValue, hull.getAction(s0), lead.m.inv_min, lead.m.inv_max);
+            // CLSPTesting.java:57-61: a sweep over the fixed ordering cost, solved as one batch (sdpb_solve_batch)
+            Recursion sweep0(Model::inventory(OptDirection::MIN, pmf, 300, 0, 2, 10, 60, -120, 200, 1));
+            Recursion sweep1(Model::inventory(OptDirection::MIN, pmf, 500, 0, 2, 10, 60, -120, 200, 1));
+            Recursion sweep2(Model::inventory(OptDirection::MIN, pmf, 700, 0, 2, 10, 60, -120, 200, 1));
+            for (int round = 0; round < 3; round++)   // plain, capture, replay
+                Engine::solveBatch({&sweep0.engine(), &sweep1.engine(), &sweep2.engine()});
+            const double v0 = sweep0.getExpectedValue(initialState), v1 = sweep1.getExpectedValue(initialState);
+            const double v2 = sweep2.getExpectedValue(initialState);
+            std::printf("J %.17g %.17g %.17g\n", v0, v1, v2);
+            // the opt-in collapsed kernel: close to, not identical with, the exact value of section A
+            Recursion collapsed(model, -1, SDPB_KERNEL_COLLAPSED);
+            const double vc = collapsed.getExpectedValue(initialState);
+            std::printf("K %.17g %.17g\n", vc, collapsed.getAction(initialState));
         }
     } catch (const SdpbError& e) {
         std::fprintf(stderr, "%s\n", e.what());

@@ -64,6 +64,13 @@ def test_cpp_host_matches_oracle(tmp_path, S, oracle):
     spec_b.terminal_value = spec_b.tabulate(lambda x: -0.75 * np.maximum(x, 0) + 2.5 * np.maximum(-x, 0))
     rows_b, iv_b, _ = oracle.topdown(spec_b, [[0.0]])
     assert res["H"] == [iv_b[0], rows_b[0][-2]] and iv_b[0] != iv[0]        # with a boundary function
+    sweep = []
+    for K in (300, 500, 700):                                               # Engine::solveBatch: three engines, one graph
+        sp = S.inventory_model(pmf["A"], fixed_cost=K, vari_cost=0, hold_cost=2, penalty_cost=10, max_order=60,
+                               inv_min=-120, inv_max=200)
+        sweep.append(oracle.topdown(sp, [[0.0]])[1][0])
+    assert res["J"] == sweep and sweep[1] == iv[0]
+    assert abs(res["K"][0] - iv[0]) <= 1e-9 * abs(iv[0]) and res["K"][1] == rows[0][-2]   # the opt-in collapsed kernel
     assert res["A_row0"] == [rows[0][0], rows[0][1], rows[0][-2]]
     assert res["A_rowN"] == [rows[-1][0], rows[-1][1], rows[-1][-2]]
 
