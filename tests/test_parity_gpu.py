@@ -1223,6 +1223,20 @@ def test_cash_constraint_test_lambdas(means, K, cash, rate, S, oracle):
     assert sum(recursion.n_states) == ns and recursion.n_states[0] == 1
 
 
+def test_multilead_reference_record_T3_three_point(S):
+    """src/cash/overdraft/MultiProductLeadtime.java:35-39 -- the third output the reference's author recorded: 3 periods,
+    demands {20,30,40} x {10,15,20} with probabilities {.25,.5,.25}: 'final optimal cash is 91.19499999999998 ... Q1 = 40,
+    Q2 = 20 ... running time is 2863.0s'.  1.78e7 reached states; about 1.6 s on the device."""
+    rec = S.CashRecursionMultiLead(_multi_pmf([20, 30, 40], [0.25, 0.5, 0.25], [10, 15, 20], [0.25, 0.5, 0.25], 3),
+                                   Qbound=50)
+    st = S.CashStateMultiLead(1, 0, 0, 0, 0, 0.0)
+    finalValue = 0.0 + rec.getExpectedValue(st)
+    act = rec.getAction(st)
+    assert finalValue == 91.19499999999998
+    assert (act.getFirstAction(), act.getSecondAction()) == (40, 20)
+    assert rec.n_states == [1, 2500, 17772500]
+
+
 def test_multilead_reference_record_T3(S):
     """src/cash/overdraft/MultiProductLeadtime.java:45-50 -- the live code of the reference: 3 periods, demands
     {10,30} x {5,15}: 'final optimal cash is -76.56 ... Q1 = 30, Q2 = 15 ... running time is 1568.0s'.  1.7e7 states and
