@@ -1240,8 +1240,9 @@ def test_multilead_reference_record_T3_three_point(S):
 def test_multilead_reference_record_T3_no_overhead(S):
     """src/cash/overdraft/MultiProductLeadtime.java:30 -- 'final optimal cash is 441.57499999999993 for overhead cost 0'
     (3 periods, the three-point demands).  The two other figures of that older comment line (91.26875 and
-    272.23749999999995 for overhead 100 and 50) are superseded by the author's own later run of the overhead-100 instance
-    (:37, 91.19499999999998 -- reproduced above); with overhead 50 this library and the oracle's loop give 272.254375."""
+    272.23749999999995 for overhead 100 and 50) come from parameters the comment does not state: the author's own later
+    run of the overhead-100 instance (:37) prints 91.19499999999998 -- reproduced above -- and with overhead 50 this library
+    gives 272.254375."""
     pmf = _multi_pmf([20, 30, 40], [0.25, 0.5, 0.25], [10, 15, 20], [0.25, 0.5, 0.25], 3)
     rec = S.CashRecursionMultiLead(pmf, Qbound=50, overheadCost=[0.0] * 3)
     st = S.CashStateMultiLead(1, 0, 0, 0, 0, 0.0)
